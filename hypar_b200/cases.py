@@ -1,0 +1,249 @@
+"""Synthetic cases for the five BASELINE.json configurations.
+
+Each builder returns a ``Case``: the same information a HyPar run directory holds
+(solver.inp / boundary.inp / physics.inp / weno.inp / initial.inp), as Python data.
+``Case.write(dir)`` materialises the directory in the reference's own formats, so the
+reference executable (oracle/_ref) and this library consume identical inputs.
+
+Initial conditions follow the reference's example generators:
+  C1  Examples/1D/LinearAdvection/SineWave/aux/init.c
+  C2  Examples/1D/Euler1D/SodShockTube/aux/init.c
+  C3  Examples/2D/NavierStokes2D/InviscidVortexConvection/aux/exact.c:65-92
+  C4  Taylor-Green vortex + deterministic solenoidal Fourier modes (no FFTW available)
+  C5a Examples/3D/NavierStokes3D/DensitySineWave/aux/exact.C:54-81
+  C5b Examples/3D/NavierStokes3D/RisingThermalBubble_Config1/aux/init.c:108-133
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import hypario
+
+
+@dataclasses.dataclass
+class Case:
+    name: str
+    solver: Dict[str, object]
+    boundary: List[dict]
+    physics: Dict[str, object]
+    weno: Optional[Dict[str, object]]
+    x: List[np.ndarray]            # global coordinates per dimension
+    u0: np.ndarray                 # shape (N_{nd-1}, ..., N_0, nvars)
+
+    @property
+    def ndims(self) -> int:
+        return int(self.solver["ndims"])
+
+    @property
+    def nvars(self) -> int:
+        return int(self.solver["nvars"])
+
+    @property
+    def dims(self) -> List[int]:
+        return [int(v) for v in self.solver["size"]]
+
+    def write(self, d: str) -> None:
+        os.makedirs(d, exist_ok=True)
+        hypario.write_keyword_file(os.path.join(d, "solver.inp"), self.solver)
+        hypario.write_boundary_inp(os.path.join(d, "boundary.inp"), self.boundary)
+        hypario.write_keyword_file(os.path.join(d, "physics.inp"), self.physics)
+        if self.weno is not None:
+            hypario.write_keyword_file(os.path.join(d, "weno.inp"), self.weno)
+        hypario.write_initial_bin(os.path.join(d, "initial.inp"), self.x, self.u0)
+
+
+def _solver(ndims, nvars, size, model, *, iproc=None, ts="rk", tstype="44", dt=1e-3,
+            interp="components", par_type="nonconservative-1stage", par_scheme="2",
+            n_iter=1) -> Dict[str, object]:
+    return {
+        "ndims": ndims, "nvars": nvars, "size": list(size),
+        "iproc": list(iproc) if iproc is not None else [1] * ndims,
+        "ghost": 3, "n_iter": n_iter, "restart_iter": 0,
+        "time_scheme": ts, "time_scheme_type": tstype,
+        "hyp_space_scheme": "weno5", "hyp_flux_split": "no", "hyp_interp_type": interp,
+        "par_space_type": par_type, "par_space_scheme": par_scheme,
+        "dt": float(dt), "conservation_check": "no",
+        "screen_op_iter": 1, "file_op_iter": 1000000,
+        "ip_file_type": "binary", "input_mode": "serial", "output_mode": "serial",
+        "op_file_format": "binary", "op_overwrite": "yes", "model": model,
+    }
+
+
+def weno_inp(kind: str = "js", eps: float = 1e-6, no_limiting: int = 0) -> Dict[str, object]:
+    """kind in {js, mapped, z, yc} (WENOInitialize.c:62-96)."""
+    return {
+        "mapped": int(kind == "mapped"), "borges": int(kind == "z"), "yc": int(kind == "yc"),
+        "no_limiting": no_limiting, "epsilon": float(eps), "p": 2.0, "rc": 0.3, "xi": 0.001,
+    }
+
+
+def _zones(ndims, kind_per_face, lo, hi, wall_velocity=None):
+    """One zone per (dim, face); extents as in the reference's examples: the normal
+    extent is degenerate (0 0), tangential extents span the domain."""
+    zones = []
+    for d in range(ndims):
+        for face in (1, -1):
+            kind = kind_per_face[(d, face)] if isinstance(kind_per_face, dict) else kind_per_face
+            xmin = [0.0 if k == d else float(lo[k]) for k in range(ndims)]
+            xmax = [0.0 if k == d else float(hi[k]) for k in range(ndims)]
+            z = {"type": kind, "dim": d, "face": face, "xmin": xmin, "xmax": xmax}
+            if kind in ("slip-wall", "noslip-wall"):
+                z["wall_velocity"] = list(wall_velocity or [0.0] * ndims)
+            zones.append(z)
+    return zones
+
+
+# ------------------------------------------------------------------------------------- C1
+def linear_advection_sine(n: int = 1024, weno: str = "js", dt: float = 5e-4,
+                          diffusion: float = 0.0, par_scheme: str = "2") -> Case:
+    x = np.arange(n, dtype=np.float64) / n
+    u = np.sin(2.0 * np.pi * x).reshape(n, 1)
+    phys: Dict[str, object] = {"advection": 1.0}
+    if diffusion != 0.0:
+        phys["diffusion"] = float(diffusion)
+    return Case(
+        name=f"c1_linadv_{n}_{weno}",
+        solver=_solver(1, 1, [n], "linear-advection-diffusion-reaction", dt=dt, par_scheme=par_scheme),
+        boundary=_zones(1, "periodic", [-1e3], [1e3]),
+        physics=phys, weno=weno_inp(weno), x=[x], u0=u)
+
+
+# ------------------------------------------------------------------------------------- C2
+def euler1d_sod(n: int = 201, weno: str = "js", interp: str = "characteristic",
+                upwinding: str = "roe", tstype: str = "ssprk3") -> Case:
+    x = np.arange(n, dtype=np.float64) / (n - 1)
+    gamma = 1.4
+    rho = np.where(x < 0.5, 1.0, 0.125)
+    p = np.where(x < 0.5, 1.0, 0.1)
+    v = np.zeros_like(x)
+    u = np.stack([rho, rho * v, p / (gamma - 1.0) + 0.5 * rho * v * v], axis=-1)
+    return Case(
+        name=f"c2_sod_{n}_{weno}_{interp}_{upwinding}",
+        solver=_solver(1, 3, [n], "euler1d", ts="rk", tstype=tstype, dt=2.5e-3 * (201.0 / n),
+                       interp=interp),
+        boundary=_zones(1, "extrapolate", [-1e3], [1e3]),
+        physics={"gamma": gamma, "upwinding": upwinding}, weno=weno_inp(weno), x=[x], u0=u)
+
+
+# ------------------------------------------------------------------------------------- C3
+def ns2d_vortex(n: Sequence[int] = (1024, 1024), weno: str = "js", tstype: str = "ssprk3",
+                iproc=None) -> Case:
+    nx, ny = n
+    L = 10.0
+    x = np.arange(nx, dtype=np.float64) * (L / nx)
+    y = np.arange(ny, dtype=np.float64) * (L / ny)
+    X, Y = np.meshgrid(x, y, indexing="xy")          # shape (ny, nx): dim 0 fastest
+    gamma, b, x0, y0, uinf, vinf = 1.4, 0.5, 5.0, 5.0, 0.5, 0.0
+    rx, ry = X - x0, Y - y0
+    rsq = rx * rx + ry * ry
+    rho = (1.0 - ((gamma - 1.0) * b * b) / (8.0 * gamma * np.pi * np.pi) * np.exp(1.0 - rsq)) ** (1.0 / (gamma - 1.0))
+    du = -b / (2.0 * np.pi) * np.exp(0.5 * (1.0 - rsq)) * ry
+    dv = b / (2.0 * np.pi) * np.exp(0.5 * (1.0 - rsq)) * rx
+    vx, vy = uinf + du, vinf + dv
+    p = rho ** gamma
+    u = np.stack([rho, rho * vx, rho * vy, p / (gamma - 1.0) + 0.5 * rho * (vx * vx + vy * vy)], axis=-1)
+    return Case(
+        name=f"c3_vortex_{nx}x{ny}_{weno}",
+        solver=_solver(2, 4, [nx, ny], "navierstokes2d", ts="rk", tstype=tstype, dt=0.005 * 1024.0 / max(nx, ny),
+                       iproc=iproc),
+        boundary=_zones(2, "periodic", [-1e3, -1e3], [1e3, 1e3]),
+        physics={"gamma": gamma, "upwinding": "rusanov"}, weno=weno_inp(weno), x=[x, y], u0=u)
+
+
+# ------------------------------------------------------------------------------------- C4
+def _grid3(n, L):
+    xs = [np.arange(n[d], dtype=np.float64) * (L[d] / n[d]) for d in range(3)]
+    Z, Y, X = np.meshgrid(xs[2], xs[1], xs[0], indexing="ij")   # shape (nz, ny, nx)
+    return xs, X, Y, Z
+
+
+def ns3d_turbulence(n: Sequence[int] = (512, 512, 512), weno: str = "mapped", viscous: bool = True,
+                    upwinding: str = "rusanov", tstype: str = "44", dt: float = 0.005,
+                    iproc=None, seed: int = 20261017, interp: str = "components") -> Case:
+    """Taylor-Green vortex plus 16 solenoidal Fourier modes |k|<=4 (deterministic phases),
+    rho = 1, p = 1/gamma, Minf = 0.3: smooth, fully 3-D, every term of the RHS active."""
+    gamma, Minf = 1.4, 0.3
+    xs, X, Y, Z = _grid3(n, [2.0 * np.pi] * 3)
+    vx = Minf * np.sin(X) * np.cos(Y) * np.cos(Z)
+    vy = -Minf * np.cos(X) * np.sin(Y) * np.cos(Z)
+    vz = np.zeros_like(vx)
+    rng = np.random.RandomState(seed)
+    for _ in range(16):
+        k = rng.randint(-4, 5, size=3).astype(np.float64)
+        if not k.any():
+            k[0] = 1.0
+        a = rng.standard_normal(3)
+        a -= k * (a @ k) / (k @ k)                    # a . k = 0 -> divergence free
+        nrm = np.linalg.norm(a)
+        if nrm < 1e-12:
+            continue
+        a *= 0.1 * Minf / (4.0 * nrm)
+        ph = rng.uniform(0.0, 2.0 * np.pi)
+        s = np.sin(k[0] * X + k[1] * Y + k[2] * Z + ph)
+        vx += a[0] * s
+        vy += a[1] * s
+        vz += a[2] * s
+    rho = np.ones_like(vx)
+    p = np.full_like(vx, 1.0 / gamma)
+    u = np.stack([rho, rho * vx, rho * vy, rho * vz,
+                  p / (gamma - 1.0) + 0.5 * rho * (vx * vx + vy * vy + vz * vz)], axis=-1)
+    phys: Dict[str, object] = {"gamma": gamma, "upwinding": upwinding, "Pr": 0.72, "Minf": Minf}
+    phys["Re"] = 333.333333333333333 if viscous else -1.0
+    return Case(
+        name=f"c4_turb_{n[0]}x{n[1]}x{n[2]}_{weno}_{'visc' if viscous else 'inv'}",
+        solver=_solver(3, 5, n, "navierstokes3d", ts="rk", tstype=tstype, dt=dt, iproc=iproc, interp=interp,
+                       par_type="nonconservative-2stage", par_scheme="4"),
+        boundary=_zones(3, "periodic", [-1e3] * 3, [1e3] * 3),
+        physics=phys, weno=weno_inp(weno), x=xs, u0=u)
+
+
+# ------------------------------------------------------------------------------------- C5a
+def ns3d_density_wave(n: Sequence[int] = (64, 64, 64), weno: str = "js", tstype: str = "44",
+                      dt: float = 1e-3, iproc=None) -> Case:
+    gamma = 1.4
+    xs, X, Y, Z = _grid3(n, [1.0] * 3)
+    rho = 1.0 + 0.1 * np.sin(2 * np.pi * X) * np.sin(2 * np.pi * Y) * np.sin(2 * np.pi * Z)
+    v = np.ones_like(rho)
+    p = np.full_like(rho, 1.0 / gamma)
+    u = np.stack([rho, rho * v, rho * v, rho * v, p / (gamma - 1.0) + 0.5 * rho * 3.0 * v * v], axis=-1)
+    return Case(
+        name=f"c5a_denswave_{n[0]}x{n[1]}x{n[2]}_{weno}",
+        solver=_solver(3, 5, n, "navierstokes3d", ts="rk", tstype=tstype, dt=dt, iproc=iproc,
+                       par_type="nonconservative-2stage", par_scheme="4"),
+        boundary=_zones(3, "periodic", [-1e3] * 3, [1e3] * 3),
+        physics={"gamma": gamma, "upwinding": "rusanov"}, weno=weno_inp(weno), x=xs, u0=u)
+
+
+# ------------------------------------------------------------------------------------- C5b
+def ns3d_rising_bubble(n: Sequence[int] = (64, 64, 64), weno: str = "yc", tstype: str = "ssprk3",
+                       dt: float = 0.01, iproc=None, hb: int = 2) -> Case:
+    """Rising thermal bubble: slip walls, gravity (0, 9.8, 0), HB = 2 hydrostatic balance."""
+    gamma, R, g = 1.4, 287.058, 9.8
+    rho_ref, p_ref = 1.1612055171196529, 100000.0
+    L = 1000.0
+    # cell-centred-at-nodes grid of the example: x_i = i * L/(N-1)
+    xs = [np.arange(n[d], dtype=np.float64) * (L / (n[d] - 1)) for d in range(3)]
+    Z, Y, X = np.meshgrid(xs[2], xs[1], xs[0], indexing="ij")
+    T_ref = p_ref / (R * rho_ref)
+    Cp = gamma / (gamma - 1.0) * R
+    tc, xc, yc, zc, rc = 1.0, 500.0, 260.0, 500.0, 250.0
+    r = np.sqrt((X - xc) ** 2 + (Y - yc) ** 2 + (Z - zc) ** 2)
+    dtheta = np.where(r > rc, 0.0, 0.5 * tc * (1.0 + np.cos(np.pi * r / rc)))
+    theta = T_ref + dtheta
+    Pexner = 1.0 - (g / (Cp * T_ref)) * Y
+    rho = (p_ref / (R * theta)) * Pexner ** (1.0 / (gamma - 1.0))
+    E = rho * (R / (gamma - 1.0)) * theta * Pexner
+    zero = np.zeros_like(rho)
+    u = np.stack([rho, zero, zero, zero, E], axis=-1)
+    return Case(
+        name=f"c5b_bubble_{n[0]}x{n[1]}x{n[2]}_{weno}",
+        solver=_solver(3, 5, n, "navierstokes3d", ts="rk", tstype=tstype, dt=dt, iproc=iproc,
+                       par_type="nonconservative-2stage", par_scheme="4"),
+        boundary=_zones(3, "slip-wall", [0.0] * 3, [L] * 3, wall_velocity=[0.0, 0.0, 0.0]),
+        physics={"gamma": gamma, "upwinding": "rusanov", "gravity": [0.0, g, 0.0],
+                 "rho_ref": rho_ref, "p_ref": p_ref, "R": R, "HB": hb},
+        weno=weno_inp(weno), x=xs, u0=u)
