@@ -1,0 +1,645 @@
+// capi.cu -- the extern "C" boundary (include/hypar_b200.h): solver life cycle, the host-array
+// entry points that mirror HyPar's function-pointer surface, the device-resident time loop and the
+// staged multi-GPU step. No CPU fallback: every compute entry point requires a CUDA device.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include "hpb_internal.h"
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int g_err_state = 0;
+
+int hpb_fail(int code, const char* fmt, ...)
+{
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  g_err_state = code;
+  fprintf(stderr, "hypar_b200: error %d: %s\n", code, g_err);     // callers may drop return values (basic.h:15-23)
+  return code;
+}
+
+extern "C" const char* hpb_last_error(void) { return g_err; }
+extern "C" int hpb_error_state(void) { return g_err_state; }
+extern "C" void hpb_clear_error(void) { g_err_state = 0; g_err[0] = 0; }
+extern "C" const char* hpb_version(void) { return "hypar_b200 0.1 (sm_100a)"; }
+
+extern "C" int hpb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" void hpb_config_defaults(hpb_config* c)
+{
+  memset(c, 0, sizeof(*c));
+  c->ndims = 1; c->nvars = 1; c->ghosts = 1;                 // ReadInputs.c:112-115
+  for (int d = 0; d < HPB_MAX_NDIMS; d++) { c->iproc[d] = 1; c->dim_global[d] = 1; }
+  c->interp_char = 1;                                         // ReadInputs.c:136 "characteristic"
+  c->par_scheme = 2;                                          // ReadInputs.c:135
+  c->rk_type = HPB_RK_44;
+  c->weno_type = HPB_WENO_JS; c->no_limiting = 0; c->weno_eps = 1e-6;   // WENOInitialize.c:51-60
+  c->upwind = HPB_UPWIND_ROE;
+  c->gamma = 1.4; c->Re = -1.0; c->Pr = 0.72; c->Minf = 1.0;   // NavierStokes3DInitialize.c:78-91
+  c->rho_ref = 1.0; c->p_ref = 1.0; c->R = 1.0; c->HB = 1; c->N_bv = 0.0;
+  c->device = -1;
+  c->use_fused = 1;
+}
+
+// ------------------------------------------------------------------------------------ helpers
+static long long ncell(const hpb_solver* h) { return h->geo.npg * h->geo.nvars; }
+
+static long long nif(const hpb_solver* h, int dir)
+{
+  const Geom& G = h->geo;
+  return (long long)(G.N[0] + (dir == 0)) * (G.N[1] + (dir == 1)) * (G.N[2] + (dir == 2));
+}
+static long long nif_max(const hpb_solver* h)
+{
+  long long m = 0;
+  for (int d = 0; d < h->geo.ndims; d++) { long long k = nif(h, d); if (k > m) m = k; }
+  return m;
+}
+
+static int dalloc(double** p, long long n)
+{
+  if (*p) return HPB_OK;
+  cudaError_t e = cudaMalloc((void**)p, (size_t)n * sizeof(double));
+  if (e != cudaSuccess) return hpb_fail(HPB_ERR_ALLOC, "cudaMalloc of %lld doubles failed: %s", n, cudaGetErrorString(e));
+  e = cudaMemset(*p, 0, (size_t)n * sizeof(double));
+  if (e != cudaSuccess) return hpb_fail(HPB_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+  return HPB_OK;
+}
+#define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+static int need_device(hpb_solver* h)
+{
+  if (!h) return hpb_fail(HPB_ERR_INVALID, "null solver");
+  if (!h->device_ready) return hpb_fail(HPB_ERR_NO_DEVICE, "no CUDA device: hypar_b200 has no CPU path");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return hpb_fail(HPB_ERR_CUDA, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+  return HPB_OK;
+}
+
+static int check_async(hpb_solver* h, const char* what)
+{
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return hpb_fail(HPB_ERR_CUDA, "%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+  (void)h;
+  return HPB_OK;
+}
+
+static int sync_check(hpb_solver* h, const char* what)
+{
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return hpb_fail(HPB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return HPB_OK;
+}
+
+// host AoS (HyPar layout) -> device SoA and back, n points, nv components
+static int upload(hpb_solver* h, const double* host_aos, double* dev_soa, long long npts, int nv)
+{
+  TRY(dalloc(&h->d_stage_aos, (h->geo.npg > nif_max(h) ? h->geo.npg : nif_max(h)) * h->geo.nvars * 3));
+  HPB_CUDA(cudaMemcpyAsync(h->d_stage_aos, host_aos, (size_t)npts * nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  hpbk::aos_to_soa(h, h->d_stage_aos, dev_soa, npts, nv);
+  return check_async(h, "upload");
+}
+static int download(hpb_solver* h, const double* dev_soa, double* host_aos, long long npts, int nv)
+{
+  TRY(dalloc(&h->d_stage_aos, (h->geo.npg > nif_max(h) ? h->geo.npg : nif_max(h)) * h->geo.nvars * 3));
+  hpbk::soa_to_aos(h, dev_soa, h->d_stage_aos, npts, nv);
+  HPB_CUDA(cudaMemcpyAsync(host_aos, h->d_stage_aos, (size_t)npts * nv * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return sync_check(h, "download");
+}
+
+static bool viscous_on(const hpb_solver* h)
+{
+  return (h->cfg.model == HPB_MODEL_NS3D || h->cfg.model == HPB_MODEL_NS2D) && h->phys.Re > 0;
+}
+
+static int alloc_main(hpb_solver* h)
+{
+  const long long n = ncell(h);
+  TRY(dalloc(&h->d_u, n)); TRY(dalloc(&h->d_uprev, n)); TRY(dalloc(&h->d_U, n));
+  for (int s = 0; s < h->rk.ns; s++) TRY(dalloc(&h->d_Udot[s], n));
+  TRY(dalloc(&h->d_fI, nif_max(h) * h->geo.nvars));
+  if (h->phys.has_grav) TRY(dalloc(&h->d_sI, nif_max(h) * 2));
+  if (viscous_on(h)) {
+    for (int d = 0; d < h->geo.ndims; d++) TRY(dalloc(&h->d_QD[d], n));
+    TRY(dalloc(&h->d_FV, h->geo.npg * (h->geo.nvars - 1)));
+  }
+  return HPB_OK;
+}
+
+// ------------------------------------------------------------------------------------ life cycle
+extern "C" int hpb_create(const hpb_config* cfg, hpb_solver** out)
+{
+  if (!cfg || !out) return hpb_fail(HPB_ERR_INVALID, "hpb_create: null argument");
+  *out = nullptr;
+  hpb_solver* h = new (std::nothrow) hpb_solver();
+  if (!h) return hpb_fail(HPB_ERR_ALLOC, "out of host memory");
+  h->cfg = *cfg;
+  int rc = hpb_setup_host(h);
+  if (rc) { delete h; return rc; }
+  // keep a private copy of the global grid (the caller's pointer need not outlive this call)
+  h->cfg.x_global = nullptr;
+
+  int ndev = hpb_device_count();
+  if (ndev > 0) {
+    int dev = cfg->device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) { delete h; return hpb_fail(HPB_ERR_INVALID, "device %d not present (%d devices)", dev, ndev); }
+    h->device = dev;
+    cudaError_t e = cudaSetDevice(dev);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return hpb_fail(HPB_ERR_CUDA, "device init: %s", cudaGetErrorString(e)); }
+    const Geom& G = h->geo;
+    const size_t nx = h->x_h.size();
+    rc = dalloc(&h->d_x, (long long)nx);           if (rc) { hpb_destroy(h); return rc; }
+    rc = dalloc(&h->d_dxinv, (long long)nx);       if (rc) { hpb_destroy(h); return rc; }
+    rc = dalloc(&h->d_gravf, G.npg);               if (rc) { hpb_destroy(h); return rc; }
+    rc = dalloc(&h->d_gravg, G.npg);               if (rc) { hpb_destroy(h); return rc; }
+    rc = dalloc(&h->d_red, 8);                     if (rc) { hpb_destroy(h); return rc; }
+    cudaMemcpy(h->d_x, h->x_h.data(), nx * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_dxinv, h->dxinv_h.data(), nx * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_gravf, h->gravf_h.data(), (size_t)G.npg * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_gravg, h->gravg_h.data(), (size_t)G.npg * sizeof(double), cudaMemcpyHostToDevice);
+    if (cudaMallocHost((void**)&h->h_red, 8 * sizeof(double)) != cudaSuccess) { hpb_destroy(h); return hpb_fail(HPB_ERR_ALLOC, "pinned alloc"); }
+    // halo buffers (only for faces that have a neighbour)
+    for (int d = 0; d < G.ndims; d++) {
+      long long nf = (long long)G.nvars * G.g;
+      for (int k = 0; k < G.ndims; k++) if (k != d) nf *= G.N[k];
+      h->face_bytes[2*d] = h->face_bytes[2*d+1] = (size_t)nf * sizeof(double);
+      const int nfields = viscous_on(h) ? 3 : 1;
+      for (int f = 0; f < nfields; f++) for (int s = 0; s < 2; s++) if (h->neighbor[2*d+s] >= 0) {
+        rc = dalloc(&h->d_send[f][2*d+s], nf); if (rc) { hpb_destroy(h); return rc; }
+        rc = dalloc(&h->d_recv[f][2*d+s], nf); if (rc) { hpb_destroy(h); return rc; }
+      }
+    }
+    rc = alloc_main(h);
+    if (rc) { hpb_destroy(h); return rc; }
+    h->device_ready = true;
+  }
+  *out = h;
+  return HPB_OK;
+}
+
+extern "C" int hpb_destroy(hpb_solver* h)
+{
+  if (!h) return HPB_OK;
+  if (h->stream || h->d_x) cudaSetDevice(h->device);
+  double** ptrs[] = { &h->d_x, &h->d_dxinv, &h->d_gravf, &h->d_gravg, &h->d_u, &h->d_uprev, &h->d_U, &h->d_fI, &h->d_sI,
+                      &h->d_FV, &h->d_stage_aos, &h->d_w, &h->d_red };
+  for (double** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
+  for (int i = 0; i < 4; i++) { if (h->d_Udot[i]) cudaFree(h->d_Udot[i]); if (h->d_tmp[i]) cudaFree(h->d_tmp[i]); }
+  for (int i = 0; i < 3; i++) if (h->d_QD[i]) cudaFree(h->d_QD[i]);
+  for (int i = 0; i < 5; i++) if (h->d_iface[i]) cudaFree(h->d_iface[i]);
+  for (int f = 0; f < 3; f++) for (int k = 0; k < 6; k++) {
+    if (h->d_send[f][k]) cudaFree(h->d_send[f][k]);
+    if (h->d_recv[f][k]) cudaFree(h->d_recv[f][k]);
+  }
+  if (h->h_red) cudaFreeHost(h->h_red);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return HPB_OK;
+}
+
+// ------------------------------------------------------------------------------------ queries
+extern "C" int hpb_get_local_dims(const hpb_solver* h, int* dim_local, int* is_global)
+{
+  for (int d = 0; d < h->geo.ndims; d++) { if (dim_local) dim_local[d] = h->geo.N[d]; if (is_global) is_global[d] = h->is_global[d]; }
+  return HPB_OK;
+}
+extern "C" long long hpb_npoints_local_wghosts(const hpb_solver* h) { return h->geo.npg; }
+extern "C" long long hpb_ninterfaces(const hpb_solver* h, int dir) { return nif(h, dir); }
+extern "C" int hpb_get_grid(const hpb_solver* h, double* x, double* dxinv)
+{
+  if (x) memcpy(x, h->x_h.data(), h->x_h.size() * sizeof(double));
+  if (dxinv) memcpy(dxinv, h->dxinv_h.data(), h->dxinv_h.size() * sizeof(double));
+  return HPB_OK;
+}
+extern "C" int hpb_get_neighbors(const hpb_solver* h, int* nb)
+{
+  for (int k = 0; k < 2 * h->geo.ndims; k++) nb[k] = h->neighbor[k];
+  return HPB_OK;
+}
+extern "C" int hpb_get_zone_extent(const hpb_solver* h, int zone, int* is, int* ie, int* on)
+{
+  if (zone < 0 || zone >= (int)h->zones.size()) return hpb_fail(HPB_ERR_INVALID, "zone index out of range");
+  for (int d = 0; d < h->geo.ndims; d++) { is[d] = h->zones[zone].is[d]; ie[d] = h->zones[zone].ie[d]; }
+  *on = h->zones[zone].on;
+  return HPB_OK;
+}
+extern "C" int hpb_get_gravity_field(const hpb_solver* h, double* f, double* g)
+{
+  if (f) memcpy(f, h->gravf_h.data(), h->gravf_h.size() * sizeof(double));
+  if (g) memcpy(g, h->gravg_h.data(), h->gravg_h.size() * sizeof(double));
+  return HPB_OK;
+}
+extern "C" long long hpb_kernel_launch_count(const hpb_solver* h) { return h->launches; }
+extern "C" void* hpb_stream(hpb_solver* h) { return (void*)h->stream; }
+extern "C" int hpb_synchronize(hpb_solver* h) { TRY(need_device(h)); return sync_check(h, "synchronize"); }
+extern "C" double hpb_current_time(const hpb_solver* h) { return h->t; }
+extern "C" int hpb_nstages(const hpb_solver* h) { return h->rk.ns; }
+extern "C" int hpb_needs_viscous_exchange(const hpb_solver* h) { return viscous_on(h) ? 1 : 0; }
+
+// ------------------------------------------------------------------------------------ RHS assembly (device)
+// rhs = -hyp + par + source of TimeRHSFunctionExplicit.c:70-92, split at the viscous halo exchange.
+static void rhs_part_a(hpb_solver* h, const double* U, double* rhs)
+{
+  hpbk::hyperbolic(h, U, rhs, /*negate=*/true, /*with_source=*/true, rhs);
+  if (viscous_on(h)) hpbk::parabolic_phase1(h, U);
+}
+static void rhs_part_b(hpb_solver* h, const double* U, double* rhs)
+{
+  if (viscous_on(h)) hpbk::parabolic_phase2(h, U, rhs, /*accumulate=*/true);
+  else if (h->cfg.model == HPB_MODEL_LINEAR_ADR) hpbk::parabolic_nc1(h, U, rhs, true);
+}
+static bool multi_rank(const hpb_solver* h)
+{
+  for (int k = 0; k < 6; k++) if (h->neighbor[k] >= 0) return true;
+  return false;
+}
+#define SINGLE_RANK_ONLY(h, name) do { if (multi_rank(h)) return hpb_fail(HPB_ERR_INVALID, \
+  name ": this rank has neighbours; drive the step with the staged hpb_stage_* calls and exchange the halo buffers"); } while (0)
+
+// ------------------------------------------------------------------------------------ HOST entry points
+static int tmp(hpb_solver* h, int k) { return dalloc(&h->d_tmp[k], ncell(h)); }
+
+extern "C" int hpb_ApplyBoundaryConditions(hpb_solver* h, double* u, double t)
+{
+  (void)t;
+  TRY(need_device(h)); TRY(tmp(h, 0));
+  TRY(upload(h, u, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  hpbk::apply_bc(h, h->d_tmp[0]);
+  TRY(check_async(h, "ApplyBoundaryConditions"));
+  return download(h, h->d_tmp[0], u, h->geo.npg, h->geo.nvars);
+}
+
+extern "C" int hpb_HyperbolicFunction(hpb_solver* h, double* hyp, const double* u, double t, int LimFlag)
+{
+  (void)t;
+  TRY(need_device(h));
+  if (!LimFlag && !h->cfg.no_limiting)
+    return hpb_fail(HPB_ERR_INVALID, "HyperbolicFunction: LimFlag = 0 (frozen WENO weights) is used by implicit time "
+                                     "integration only and is not implemented: the device path never stores weights");
+  TRY(tmp(h, 0)); TRY(tmp(h, 1));
+  TRY(upload(h, u, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  hpbk::set_zero(h, h->d_tmp[1], ncell(h));
+  hpbk::hyperbolic(h, h->d_tmp[0], h->d_tmp[1], false, false, nullptr);
+  TRY(check_async(h, "HyperbolicFunction"));
+  return download(h, h->d_tmp[1], hyp, h->geo.npg, h->geo.nvars);
+}
+
+extern "C" int hpb_ParabolicFunction(hpb_solver* h, double* par, const double* u, double t)
+{
+  (void)t;
+  TRY(need_device(h));
+  SINGLE_RANK_ONLY(h, "ParabolicFunction");
+  TRY(tmp(h, 0)); TRY(tmp(h, 1));
+  TRY(upload(h, u, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  hpbk::set_zero(h, h->d_tmp[1], ncell(h));
+  if (viscous_on(h)) { hpbk::parabolic_phase1(h, h->d_tmp[0]); hpbk::parabolic_phase2(h, h->d_tmp[0], h->d_tmp[1], true); }
+  else if (h->cfg.model == HPB_MODEL_LINEAR_ADR) hpbk::parabolic_nc1(h, h->d_tmp[0], h->d_tmp[1], true);
+  TRY(check_async(h, "ParabolicFunction"));
+  return download(h, h->d_tmp[1], par, h->geo.npg, h->geo.nvars);
+}
+
+extern "C" int hpb_SourceFunction(hpb_solver* h, double* source, const double* u, double t)
+{
+  (void)t;
+  TRY(need_device(h));
+  TRY(tmp(h, 0)); TRY(tmp(h, 1)); TRY(tmp(h, 2));
+  TRY(upload(h, u, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  hpbk::set_zero(h, h->d_tmp[1], ncell(h));
+  // the source reuses the flux weights of the hyperbolic sweep of the same u (quirk Q5): the sweep is
+  // re-evaluated here with the source enabled; its hyperbolic output goes to scratch
+  if (h->phys.has_grav) hpbk::hyperbolic_generic(h, h->d_tmp[0], h->d_tmp[2], false, true, h->d_tmp[1]);
+  TRY(check_async(h, "SourceFunction"));
+  return download(h, h->d_tmp[1], source, h->geo.npg, h->geo.nvars);
+}
+
+extern "C" int hpb_RHSFunction(hpb_solver* h, double* rhs, double* u, double t)
+{
+  (void)t;
+  TRY(need_device(h));
+  SINGLE_RANK_ONLY(h, "RHSFunction");
+  TRY(upload(h, u, h->d_U, h->geo.npg, h->geo.nvars));
+  hpbk::apply_bc(h, h->d_U);
+  hpbk::set_zero(h, h->d_Udot[0], ncell(h));
+  rhs_part_a(h, h->d_U, h->d_Udot[0]);
+  rhs_part_b(h, h->d_U, h->d_Udot[0]);
+  TRY(check_async(h, "RHSFunction"));
+  TRY(download(h, h->d_Udot[0], rhs, h->geo.npg, h->geo.nvars));
+  return download(h, h->d_U, u, h->geo.npg, h->geo.nvars);
+}
+
+extern "C" int hpb_FFunction(hpb_solver* h, double* f, const double* u, int dir, double t)
+{
+  (void)t;
+  TRY(need_device(h)); TRY(tmp(h, 0)); TRY(tmp(h, 1));
+  if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "FFunction: dir %d", dir);
+  TRY(upload(h, u, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  hpbk::flux(h, h->d_tmp[0], h->d_tmp[1], dir);
+  TRY(check_async(h, "FFunction"));
+  return download(h, h->d_tmp[1], f, h->geo.npg, h->geo.nvars);
+}
+
+extern "C" int hpb_UFunction(hpb_solver* h, double* uC, const double* u, int dir, double t)
+{
+  (void)t; (void)dir;
+  TRY(need_device(h)); TRY(tmp(h, 0)); TRY(tmp(h, 1));
+  TRY(upload(h, u, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  hpbk::modified_solution(h, h->d_tmp[0], h->d_tmp[1]);
+  TRY(check_async(h, "UFunction"));
+  return download(h, h->d_tmp[1], uC, h->geo.npg, h->geo.nvars);
+}
+
+static long long woff(const hpb_solver* h, int dir)
+{
+  long long o = 0;
+  for (int d = 0; d < dir; d++) o += 12 * nif(h, d) * h->geo.nvars;
+  return o;
+}
+
+extern "C" int hpb_SetInterpLimiterVar(hpb_solver* h, const double* fC, const double* u, int dir)
+{
+  TRY(need_device(h)); TRY(tmp(h, 0)); TRY(tmp(h, 1));
+  if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "SetInterpLimiterVar: dir %d", dir);
+  TRY(dalloc(&h->d_w, woff(h, h->geo.ndims)));
+  TRY(upload(h, fC, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  TRY(upload(h, u, h->d_tmp[1], h->geo.npg, h->geo.nvars));
+  hpbk::weno_weights(h, h->d_tmp[0], h->d_tmp[1], dir, h->d_w + woff(h, dir));
+  h->w_valid = true;
+  return check_async(h, "SetInterpLimiterVar");
+}
+
+extern "C" int hpb_GetInterpWeights(hpb_solver* h, int dir, double* w)
+{
+  TRY(need_device(h));
+  if (!h->d_w) return hpb_fail(HPB_ERR_INVALID, "GetInterpWeights: SetInterpLimiterVar has not been called");
+  // device: [(3*blk+k)][v][q]  ->  host: [(3*blk+k)][q][v] (the reference's per-block AoS)
+  const long long ni = nif(h, dir);
+  for (int b = 0; b < 12; b++)
+    TRY(download(h, h->d_w + woff(h, dir) + (long long)b * ni * h->geo.nvars, w + (long long)b * ni * h->geo.nvars, ni, h->geo.nvars));
+  return HPB_OK;
+}
+
+extern "C" int hpb_InterpolateInterfacesHyp(hpb_solver* h, double* fI, const double* fC, const double* u,
+                                            int upw, int dir, int uflag)
+{
+  TRY(need_device(h)); TRY(tmp(h, 0)); TRY(tmp(h, 1));
+  if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "InterpolateInterfacesHyp: dir %d", dir);
+  TRY(dalloc(&h->d_w, woff(h, h->geo.ndims)));
+  if (!h->w_valid) {
+    // WENOInitialize.c:170-178: weights start at their optimal values
+    std::vector<double> w((size_t)woff(h, h->geo.ndims));
+    for (int d = 0; d < h->geo.ndims; d++) {
+      const long long n = nif(h, d) * h->geo.nvars;
+      for (int b = 0; b < 4; b++) for (long long i = 0; i < n; i++) {
+        w[(size_t)(woff(h, d) + (3*b+0)*n + i)] = 0.1; w[(size_t)(woff(h, d) + (3*b+1)*n + i)] = 0.6; w[(size_t)(woff(h, d) + (3*b+2)*n + i)] = 0.3;
+      }
+    }
+    HPB_CUDA(cudaMemcpy(h->d_w, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->w_valid = true;
+  }
+  TRY(dalloc(&h->d_iface[0], nif_max(h) * h->geo.nvars));
+  TRY(upload(h, fC, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  TRY(upload(h, u, h->d_tmp[1], h->geo.npg, h->geo.nvars));
+  hpbk::weno_interp(h, h->d_iface[0], h->d_tmp[0], h->d_tmp[1], h->d_w + woff(h, dir), upw, dir, uflag);
+  TRY(check_async(h, "InterpolateInterfacesHyp"));
+  return download(h, h->d_iface[0], fI, nif(h, dir), h->geo.nvars);
+}
+
+extern "C" int hpb_Upwind(hpb_solver* h, double* fI, const double* fL, const double* fR, const double* uL,
+                          const double* uR, const double* u, int dir, double t)
+{
+  (void)t;
+  TRY(need_device(h)); TRY(tmp(h, 0));
+  if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "Upwind: dir %d", dir);
+  for (int k = 0; k < 5; k++) TRY(dalloc(&h->d_iface[k], nif_max(h) * h->geo.nvars));
+  const long long ni = nif(h, dir);
+  TRY(upload(h, fL, h->d_iface[1], ni, h->geo.nvars));
+  TRY(upload(h, fR, h->d_iface[2], ni, h->geo.nvars));
+  TRY(upload(h, uL, h->d_iface[3], ni, h->geo.nvars));
+  TRY(upload(h, uR, h->d_iface[4], ni, h->geo.nvars));
+  TRY(upload(h, u, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  hpbk::upwind(h, h->d_iface[0], h->d_iface[1], h->d_iface[2], h->d_iface[3], h->d_iface[4], h->d_tmp[0], dir);
+  TRY(check_async(h, "Upwind"));
+  return download(h, h->d_iface[0], fI, ni, h->geo.nvars);
+}
+
+extern "C" int hpb_FirstDerivativePar(hpb_solver* h, double* Df, const double* f, int dir, int bias)
+{
+  (void)bias;   // the fourth-order central operator ignores the bias, as in the reference
+  TRY(need_device(h)); TRY(tmp(h, 0)); TRY(tmp(h, 1));
+  if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "FirstDerivativePar: dir %d", dir);
+  TRY(upload(h, f, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  TRY(upload(h, Df, h->d_tmp[1], h->geo.npg, h->geo.nvars));      // entries outside the computed lines are kept
+  hpbk::first_derivative(h, h->d_tmp[1], h->d_tmp[0], dir, h->geo.nvars);
+  TRY(check_async(h, "FirstDerivativePar"));
+  return download(h, h->d_tmp[1], Df, h->geo.npg, h->geo.nvars);
+}
+
+extern "C" int hpb_SecondDerivativePar(hpb_solver* h, double* D2f, const double* f, int dir)
+{
+  TRY(need_device(h)); TRY(tmp(h, 0)); TRY(tmp(h, 1));
+  if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "SecondDerivativePar: dir %d", dir);
+  TRY(upload(h, f, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  TRY(upload(h, D2f, h->d_tmp[1], h->geo.npg, h->geo.nvars));
+  hpbk::second_derivative(h, h->d_tmp[1], h->d_tmp[0], dir, h->geo.nvars, h->cfg.par_scheme == 4 ? 4 : 2);
+  TRY(check_async(h, "SecondDerivativePar"));
+  return download(h, h->d_tmp[1], D2f, h->geo.npg, h->geo.nvars);
+}
+
+extern "C" int hpb_ComputeCFL(hpb_solver* h, const double* u, double dt, double t, double* cfl)
+{
+  (void)t;
+  TRY(need_device(h)); TRY(tmp(h, 0));
+  TRY(upload(h, u, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  hpbk::cfl(h, h->d_tmp[0], dt, cfl);
+  return check_async(h, "ComputeCFL");
+}
+
+// ------------------------------------------------------------------------------------ device-resident path
+extern "C" int hpb_dev_set_solution(hpb_solver* h, const double* u_host)
+{
+  TRY(need_device(h));
+  TRY(upload(h, u_host, h->d_u, h->geo.npg, h->geo.nvars));
+  return sync_check(h, "dev_set_solution");
+}
+
+extern "C" int hpb_dev_get_solution(hpb_solver* h, double* u_host)
+{
+  TRY(need_device(h));
+  return download(h, h->d_u, u_host, h->geo.npg, h->geo.nvars);
+}
+
+extern "C" int hpb_dev_fill_solution_from_global(hpb_solver* h, const double* ug)
+{
+  // host-side gather of this rank's block out of the global AoS array (initial.inp layout), ghosts = 0
+  TRY(need_device(h));
+  const Geom& G = h->geo;
+  const hpb_config& c = h->cfg;
+  std::vector<double> loc((size_t)ncell(h), 0.0);
+  const long long g0 = c.dim_global[0], g1 = (G.ndims > 1 ? c.dim_global[1] : 1);
+  for (int k = 0; k < G.N[2]; k++) for (int j = 0; j < G.N[1]; j++) {
+    const long long pg = (h->is_global[0]) + g0 * ((j + (G.ndims > 1 ? h->is_global[1] : 0)) + g1 * (k + (G.ndims > 2 ? h->is_global[2] : 0)));
+    long long pl = G.g;
+    if (G.ndims > 1) pl += (long long)G.P[0] * (j + G.g);
+    if (G.ndims > 2) pl += (long long)G.P[0] * G.P[1] * (k + G.g);
+    memcpy(&loc[(size_t)pl * G.nvars], ug + pg * G.nvars, (size_t)G.N[0] * G.nvars * sizeof(double));
+  }
+  return hpb_dev_set_solution(h, loc.data());
+}
+
+static int step_single(hpb_solver* h)
+{
+  const long long n = ncell(h);
+  // TimePreStep.c:50-76: boundary conditions on u; copy for the step norm
+  hpbk::apply_bc(h, h->d_u);
+  hpbk::copy(h, h->d_uprev, h->d_u, n);
+  for (int s = 0; s < h->rk.ns; s++) {
+    hpbk::rk_stage(h, s);                       // TimeRK.c:131-141
+    hpbk::apply_bc(h, h->d_U);                  // TimeRHSFunctionExplicit.c:46
+    rhs_part_a(h, h->d_U, h->d_Udot[s]);
+    rhs_part_b(h, h->d_U, h->d_Udot[s]);
+  }
+  hpbk::rk_finish(h);                           // TimeRK.c:182-193
+  h->t += h->cfg.dt;                            // TimePostStep.c:36
+  return check_async(h, "TimeStep");
+}
+
+extern "C" int hpb_TimeStep(hpb_solver* h)
+{
+  TRY(need_device(h));
+  SINGLE_RANK_ONLY(h, "TimeStep");
+  return step_single(h);
+}
+
+extern "C" int hpb_TimeSteps(hpb_solver* h, int nsteps)
+{
+  TRY(need_device(h));
+  SINGLE_RANK_ONLY(h, "TimeSteps");
+  for (int i = 0; i < nsteps; i++) TRY(step_single(h));
+  return sync_check(h, "TimeSteps");
+}
+
+extern "C" int hpb_TimeIntegrate(hpb_solver* h, double* u, int nsteps, double t0)
+{
+  TRY(need_device(h));
+  SINGLE_RANK_ONLY(h, "TimeIntegrate");
+  h->t = t0;
+  TRY(upload(h, u, h->d_u, h->geo.npg, h->geo.nvars));
+  for (int i = 0; i < nsteps; i++) TRY(step_single(h));
+  return download(h, h->d_u, u, h->geo.npg, h->geo.nvars);
+}
+
+extern "C" int hpb_dev_ComputeCFL(hpb_solver* h, double* cfl_local_max)
+{
+  TRY(need_device(h));
+  hpbk::cfl(h, h->d_u, h->cfg.dt, cfl_local_max);
+  return check_async(h, "dev_ComputeCFL");
+}
+
+extern "C" int hpb_dev_StepNormSumSq(hpb_solver* h, double* sumsq_local)
+{
+  TRY(need_device(h));
+  hpbk::sumsq_diff(h, h->d_u, h->d_uprev, sumsq_local);
+  return check_async(h, "dev_StepNormSumSq");
+}
+
+extern "C" int hpb_dev_RHS(hpb_solver* h, double t, double* rhs_host)
+{
+  (void)t;
+  TRY(need_device(h));
+  SINGLE_RANK_ONLY(h, "dev_RHS");
+  hpbk::copy(h, h->d_U, h->d_u, ncell(h));
+  hpbk::apply_bc(h, h->d_U);
+  rhs_part_a(h, h->d_U, h->d_Udot[0]);
+  rhs_part_b(h, h->d_U, h->d_Udot[0]);
+  TRY(check_async(h, "dev_RHS"));
+  if (rhs_host) return download(h, h->d_Udot[0], rhs_host, h->geo.npg, h->geo.nvars);
+  return sync_check(h, "dev_RHS");
+}
+
+// ------------------------------------------------------------------------------------ staged multi-GPU step
+extern "C" int hpb_halo_buffers(hpb_solver* h, int field, void** send, void** recv, size_t* bytes)
+{
+  if (field < 0 || field > 2) return hpb_fail(HPB_ERR_INVALID, "halo_buffers: field %d", field);
+  for (int k = 0; k < 2 * h->geo.ndims; k++) {
+    send[k] = h->d_send[field][k]; recv[k] = h->d_recv[field][k];
+    bytes[k] = (h->neighbor[k] >= 0) ? h->face_bytes[k] : 0;
+  }
+  return HPB_OK;
+}
+
+extern "C" int hpb_step_begin(hpb_solver* h)
+{
+  TRY(need_device(h));
+  hpbk::apply_bc(h, h->d_u);                          // TimePreStep.c:50-70
+  hpbk::pack(h, h->d_u, h->geo.nvars, HPB_FIELD_U);
+  return check_async(h, "step_begin");
+}
+
+extern "C" int hpb_step_halo_done(hpb_solver* h)
+{
+  TRY(need_device(h));
+  hpbk::unpack(h, h->d_u, h->geo.nvars, HPB_FIELD_U);
+  hpbk::copy(h, h->d_uprev, h->d_u, ncell(h));
+  return check_async(h, "step_halo_done");
+}
+
+extern "C" int hpb_stage_begin(hpb_solver* h, int stage)
+{
+  TRY(need_device(h));
+  if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
+  hpbk::rk_stage(h, stage);
+  hpbk::apply_bc(h, h->d_U);
+  hpbk::pack(h, h->d_U, h->geo.nvars, HPB_FIELD_U);
+  return check_async(h, "stage_begin");
+}
+
+extern "C" int hpb_stage_halo_done(hpb_solver* h, int field)
+{
+  TRY(need_device(h));
+  if (field == HPB_FIELD_U) hpbk::unpack(h, h->d_U, h->geo.nvars, HPB_FIELD_U);
+  else if (field == HPB_FIELD_QDERIVX || field == HPB_FIELD_QDERIVY) {
+    if (!viscous_on(h)) return hpb_fail(HPB_ERR_INVALID, "stage_halo_done: no viscous exchange in this configuration");
+    hpbk::unpack(h, h->d_QD[field - 1], h->geo.nvars, field);
+  } else return hpb_fail(HPB_ERR_INVALID, "stage_halo_done: field %d", field);
+  return check_async(h, "stage_halo_done");
+}
+
+extern "C" int hpb_stage_rhs_a(hpb_solver* h, int stage)
+{
+  TRY(need_device(h));
+  if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
+  rhs_part_a(h, h->d_U, h->d_Udot[stage]);
+  if (viscous_on(h)) {
+    // NavierStokes3DParabolicFunction.c:125-130: QDerivX and QDerivY are exchanged, QDerivZ is not (Q1)
+    hpbk::pack(h, h->d_QD[0], h->geo.nvars, HPB_FIELD_QDERIVX);
+    hpbk::pack(h, h->d_QD[1], h->geo.nvars, HPB_FIELD_QDERIVY);
+  }
+  return check_async(h, "stage_rhs_a");
+}
+
+extern "C" int hpb_stage_rhs_b(hpb_solver* h, int stage)
+{
+  TRY(need_device(h));
+  if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
+  rhs_part_b(h, h->d_U, h->d_Udot[stage]);
+  return check_async(h, "stage_rhs_b");
+}
+
+extern "C" int hpb_step_finish(hpb_solver* h)
+{
+  TRY(need_device(h));
+  hpbk::rk_finish(h);
+  h->t += h->cfg.dt;
+  return check_async(h, "step_finish");
+}

@@ -1,0 +1,258 @@
+// host_setup.cpp -- host-side set-up of one rank: the C restatement of what HyPar's start-up does
+// for the data the hot path consumes. Pure host code (no CUDA calls), usable without a GPU.
+//
+//   partition / rank maps   reference src/MPIFunctions/MPIPartition1D.c, MPIRanknD.c, MPIRank1D.c
+//   ghost coordinates       reference src/IOFunctions/ReadArray.c:60-100
+//   dxinv                   reference src/Simulation/InitialSolution.c:74-119
+//   neighbours, bcperiodic  reference src/MPIFunctions/MPIExchangeBoundariesnD.c:65-76,
+//                           src/Simulation/InitializeBoundaries.c:190-201
+//   zone extents            reference src/Simulation/InitializeBoundaries.c:380-440, MathFunctions/FindInterval.c
+//   gravity field           reference src/PhysicalModels/NavierStokes3D/NavierStokes3DGravityField.c:33-152
+//   RK tableaux             reference src/TimeIntegration/TimeExplicitRKInitialize.c:58-79
+#include <math.h>
+#include <string.h>
+#include "hpb_internal.h"
+
+extern "C" int hpb_partition1d(int nglobal, int nproc, int rank)
+{
+  int n = nglobal / nproc;
+  if (rank == nproc - 1) n = nglobal - n * (nproc - 1);   // remainder to the last rank
+  return n;
+}
+
+extern "C" int hpb_rank1d(int ndims, const int* iproc, const int* ip)
+{
+  int r = 0, f = 1;
+  for (int d = 0; d < ndims; d++) { r += f * ip[d]; f *= iproc[d]; }
+  return r;
+}
+
+extern "C" void hpb_ranknd(int ndims, int rank, const int* iproc, int* ip)
+{
+  for (int d = 0; d < ndims; d++) { ip[d] = rank % iproc[d]; rank /= iproc[d]; }
+}
+
+static void find_interval(double a, double b, const double* x, int N, int* imin, int* imax)
+{
+  *imax = -1; *imin = N;
+  double min_dx = x[1] - x[0];
+  for (int i = 2; i < N; i++) { double dx = x[i] - x[i-1]; if (dx < min_dx) min_dx = dx; }
+  double tol = 1e-10 * min_dx;
+  for (int i = 0; i < N; i++) if (x[i] <= (b + tol)) *imax = i + 1;
+  for (int i = N - 1; i > -1; i--) if (x[i] >= (a - tol)) *imin = i;
+}
+
+static inline double raiseto(double x, double a) { return exp(a * log(x)); }   // math_ops.h:37
+
+int hpb_setup_host(hpb_solver* h)
+{
+  const hpb_config& c = h->cfg;
+  const int nd = c.ndims, g = c.ghosts;
+
+  // ---- validation: what the device path implements (anything else fails loudly)
+  if (nd < 1 || nd > 3) return hpb_fail(HPB_ERR_INVALID, "ndims = %d not supported (1..3)", nd);
+  if (g != HPB_G) return hpb_fail(HPB_ERR_INVALID, "ghost = %d: the WENO5 device path needs exactly %d ghost layers", g, HPB_G);
+  static const int model_nv[4] = { -1, 3, 4, 5 }, model_nd[4] = { -1, 1, 2, 3 };
+  if (c.model < 0 || c.model > 3) return hpb_fail(HPB_ERR_INVALID, "unknown model id %d", c.model);
+  if (c.model != HPB_MODEL_LINEAR_ADR && (c.nvars != model_nv[c.model] || nd != model_nd[c.model]))
+    return hpb_fail(HPB_ERR_INVALID, "model %d needs ndims=%d nvars=%d (got %d, %d)", c.model, model_nd[c.model],
+                    model_nv[c.model], nd, c.nvars);
+  if (c.nvars < 1 || c.nvars > HPB_MAX_NVARS) return hpb_fail(HPB_ERR_INVALID, "nvars = %d not supported", c.nvars);
+  if (c.weno_type < 0 || c.weno_type > 3) return hpb_fail(HPB_ERR_INVALID, "unknown WENO weight type %d", c.weno_type);
+  if (c.rk_type != HPB_RK_44 && c.rk_type != HPB_RK_SSPRK3)
+    return hpb_fail(HPB_ERR_INVALID, "time_scheme_type %d not supported (rk 44, ssprk3)", c.rk_type);
+  if (c.model == HPB_MODEL_NS2D && c.upwind != HPB_UPWIND_RUSANOV)
+    return hpb_fail(HPB_ERR_INVALID, "navierstokes2d: only rusanov upwinding is implemented on the device");
+  if ((c.model == HPB_MODEL_NS3D || c.model == HPB_MODEL_EULER1D) && c.upwind != HPB_UPWIND_RUSANOV && c.upwind != HPB_UPWIND_ROE)
+    return hpb_fail(HPB_ERR_INVALID, "upwinding %d not implemented (roe, rusanov)", c.upwind);
+  if (c.model == HPB_MODEL_NS2D && c.interp_char)
+    return hpb_fail(HPB_ERR_INVALID, "navierstokes2d: characteristic WENO5 is not implemented on the device");
+  const bool has_grav = (c.gravity[0] != 0.0 || c.gravity[1] != 0.0 || c.gravity[2] != 0.0);
+  if (has_grav && c.model != HPB_MODEL_NS3D)
+    return hpb_fail(HPB_ERR_INVALID, "gravity is implemented for navierstokes3d only");
+  if (has_grav && c.upwind != HPB_UPWIND_RUSANOV)      // NavierStokes3DInitialize.c:371-378
+    return hpb_fail(HPB_ERR_INVALID, "rusanov upwinding is needed for flows with gravitational forces");
+  if (c.model == HPB_MODEL_LINEAR_ADR && c.par_scheme != 2 && c.par_scheme != 4)
+    return hpb_fail(HPB_ERR_INVALID, "par_space_scheme %d not supported (2, 4)", c.par_scheme);
+  if (c.nzones > HPB_MAX_ZONES) return hpb_fail(HPB_ERR_INVALID, "too many boundary zones");
+  int nranks = 1;
+  for (int d = 0; d < nd; d++) {
+    if (c.iproc[d] < 1) return hpb_fail(HPB_ERR_INVALID, "iproc[%d] < 1", d);
+    nranks *= c.iproc[d];
+  }
+  if (c.rank < 0 || c.rank >= nranks) return hpb_fail(HPB_ERR_INVALID, "rank %d outside iproc grid (%d ranks)", c.rank, nranks);
+  if (!c.x_global) return hpb_fail(HPB_ERR_INVALID, "x_global is NULL");
+
+  // ---- partition
+  hpb_ranknd(nd, c.rank, c.iproc, h->ip);
+  Geom& G = h->geo;
+  memset(&G, 0, sizeof(G));
+  G.ndims = nd; G.nvars = c.nvars; G.g = g;
+  for (int d = 0; d < 3; d++) { G.N[d] = 1; G.P[d] = 1; h->is_global[d] = 0; }
+  int xo = 0;
+  for (int d = 0; d < nd; d++) {
+    G.N[d] = hpb_partition1d(c.dim_global[d], c.iproc[d], h->ip[d]);
+    if (G.N[d] < 2 * g) return hpb_fail(HPB_ERR_INVALID, "local size %d along dim %d is smaller than 2*ghosts", G.N[d], d);
+    h->is_global[d] = (c.dim_global[d] / c.iproc[d]) * h->ip[d];
+    G.P[d] = G.N[d] + 2 * g;
+    G.xoff[d] = xo;
+    xo += G.P[d];
+  }
+  G.st[0] = 1; G.st[1] = G.P[0]; G.st[2] = (long long)G.P[0] * G.P[1];
+  G.npg = (long long)G.P[0] * G.P[1] * G.P[2];
+
+  // ---- periodic flags and neighbours
+  for (int d = 0; d < 3; d++) h->bcperiodic[d] = 0;
+  for (int n = 0; n < c.nzones; n++) {
+    const hpb_boundary_zone& z = c.zones[n];
+    if (z.dim < 0 || z.dim >= nd) return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: dim %d is invalid (ndims = %d)", n, z.dim, nd);
+    if (z.face != 1 && z.face != -1) return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: face must be +1/-1", n);
+    if (z.type < 0 || z.type > HPB_BC_SLIP_WALL)
+      return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: type %d not implemented (periodic, extrapolate, slip-wall)", n, z.type);
+    if (z.type == HPB_BC_SLIP_WALL && c.model == HPB_MODEL_LINEAR_ADR)
+      return hpb_fail(HPB_ERR_INVALID, "slip-wall needs an Euler/Navier-Stokes model");
+    if (z.type == HPB_BC_PERIODIC && c.iproc[z.dim] > 1) h->bcperiodic[z.dim] = 1;
+  }
+  for (int d = 0; d < 3; d++) h->neighbor[2*d] = h->neighbor[2*d+1] = -1;
+  for (int d = 0; d < nd; d++) {
+    int nip[3] = { h->ip[0], h->ip[1], h->ip[2] };
+    if (h->ip[d] == 0) nip[d] = c.iproc[d] - 1; else nip[d]--;
+    if (!(h->ip[d] == 0 && !h->bcperiodic[d])) h->neighbor[2*d] = hpb_rank1d(nd, c.iproc, nip);
+    nip[d] = h->ip[d];
+    if (h->ip[d] == c.iproc[d] - 1) nip[d] = 0; else nip[d]++;
+    if (!(h->ip[d] == c.iproc[d] - 1 && !h->bcperiodic[d])) h->neighbor[2*d+1] = hpb_rank1d(nd, c.iproc, nip);
+    if (c.iproc[d] == 1) h->neighbor[2*d] = h->neighbor[2*d+1] = -1;   // bcperiodic is 0 then
+  }
+
+  // ---- coordinates with ghosts and dxinv
+  h->x_h.assign(xo, 0.0);
+  h->dxinv_h.assign(xo, 0.0);
+  int goff = 0;
+  for (int d = 0; d < nd; d++) {
+    const int n = G.N[d], ng = c.dim_global[d], i0 = h->is_global[d];
+    const double* xg = c.x_global + goff;
+    double* X = h->x_h.data() + G.xoff[d];
+    for (int i = 0; i < n; i++) X[g + i] = xg[i0 + i];
+    if (h->ip[d] == 0) {
+      for (int i = 0; i < g; i++) { int delta = g - i; X[i] = X[g] + ((double)delta) * (X[g] - X[g+1]); }
+    } else {
+      for (int i = 0; i < g; i++) X[i] = xg[i0 - g + i];
+    }
+    if (h->ip[d] == c.iproc[d] - 1) {
+      for (int i = n + g; i < n + 2*g; i++) { int delta = i - (n + g - 1); X[i] = X[n+g-1] + ((double)delta) * (X[n+g-1] - X[n+g-2]); }
+    } else {
+      for (int i = 0; i < g; i++) X[n + g + i] = xg[i0 + n + i];
+    }
+    // dxinv over the globally extended grid: every owner computes 2/(x[i+1]-x[i-1]) from its local x,
+    // whose internal-face ghosts are the neighbour's true coordinates
+    std::vector<double> xe(ng + 2*g), de(ng + 2*g, 0.0);
+    for (int i = 0; i < ng; i++) xe[g + i] = xg[i];
+    for (int i = 0; i < g; i++) {
+      xe[i] = xg[0] + ((double)(g - i)) * (xg[0] - xg[1]);
+      xe[ng + g + i] = xg[ng-1] + ((double)(i + 1)) * (xg[ng-1] - xg[ng-2]);
+    }
+    for (int i = 0; i < ng; i++) de[g + i] = 2.0 / (xe[g + i + 1] - xe[g + i - 1]);
+    double* DX = h->dxinv_h.data() + G.xoff[d];
+    for (int i = 0; i < n + 2*g; i++) DX[i] = de[i0 + i];
+    if (h->ip[d] == 0) for (int i = 0; i < g; i++) DX[i] = DX[g];
+    if (h->ip[d] == c.iproc[d] - 1) for (int i = n + g; i < n + 2*g; i++) DX[i] = DX[n + g - 1];
+    goff += ng;
+  }
+
+  // ---- boundary zone extents
+  h->zones.clear();
+  for (int n = 0; n < c.nzones; n++) {
+    const hpb_boundary_zone& z = c.zones[n];
+    ZoneDev zd; memset(&zd, 0, sizeof(zd));
+    zd.type = z.type; zd.dim = z.dim; zd.face = z.face; zd.on = 0;
+    for (int d = 0; d < 3; d++) { zd.is[d] = 0; zd.ie[d] = 1; zd.wall[d] = z.wall_velocity[d]; }
+    const bool edge = (z.face == 1) ? (h->ip[z.dim] == 0) : (h->ip[z.dim] == c.iproc[z.dim] - 1);
+    if (edge) {
+      zd.on = 1;
+      for (int d = 0; d < nd; d++) {
+        if (d == z.dim) {
+          if (z.face == 1) { zd.is[d] = -g; zd.ie[d] = 0; }
+          else             { zd.is[d] = G.N[d]; zd.ie[d] = G.N[d] + g; }
+        } else {
+          int is, ie;
+          find_interval(z.xmin[d], z.xmax[d], h->x_h.data() + G.xoff[d] + g, G.N[d], &is, &ie);
+          zd.is[d] = is; zd.ie[d] = ie;
+          if ((ie - is) <= 0) zd.on = 0;
+        }
+      }
+    }
+    h->zones.push_back(zd);
+  }
+
+  // ---- physics parameters
+  Phys& P = h->phys;
+  memset(&P, 0, sizeof(P));
+  P.model = c.model; P.weno = c.weno_type; P.no_limiting = c.no_limiting;
+  P.interp_char = (c.interp_char && c.nvars > 1) ? 1 : 0;        // WENOInitialize.c:156
+  P.upwind = c.upwind; P.par_scheme = c.par_scheme; P.has_grav = has_grav ? 1 : 0;
+  P.eps = c.weno_eps; P.gamma = c.gamma;
+  P.Re = c.Re / c.Minf;                                          // NavierStokes3DInitialize.c:368
+  P.Pr = c.Pr;
+  P.RT = c.p_ref / c.rho_ref;
+  for (int d = 0; d < 3; d++) P.grav[d] = c.gravity[d];
+  for (int i = 0; i < 15; i++) { P.adv[i] = c.advection[i]; P.diff[i] = c.diffusion[i]; }
+
+  // ---- gravity field (NS3D); 1.0 everywhere for the other models
+  h->gravf_h.assign((size_t)G.npg, 1.0);
+  h->gravg_h.assign((size_t)G.npg, 1.0);
+  if (c.model == HPB_MODEL_NS3D) {
+    double p0 = c.p_ref, rho0 = c.rho_ref, RT = p0 / rho0, gamma = c.gamma, R = c.R;
+    double Cp = gamma * R / (gamma - 1.0), T0 = p0 / (rho0 * R);
+    double gx = c.gravity[0], gy = c.gravity[1], gz = c.gravity[2], Nbv = c.N_bv;
+    if (c.HB == 3 && (gx != 0 || gy != 0))
+      return hpb_fail(HPB_ERR_INVALID, "HB = 3 is implemented only for gravity force along the z-coordinate");
+    const double* X = h->x_h.data();
+    for (int k = 0; k < G.P[2]; k++) for (int j = 0; j < G.P[1]; j++) for (int i = 0; i < G.P[0]; i++) {
+      size_t p = i + (size_t)G.P[0] * (j + (size_t)G.P[1] * k);
+      double xc = X[G.xoff[0] + i], yc = X[G.xoff[1] + j], zc = X[G.xoff[2] + k];
+      double f, gg;
+      if (c.HB == 1) {
+        f  = exp( (gx*xc+gy*yc+gz*zc)/RT);
+        gg = exp(-(gx*xc+gy*yc+gz*zc)/RT);
+      } else if (c.HB == 2) {
+        f  = raiseto((1.0-(gx*xc+gy*yc+gz*zc)/(Cp*T0)), (-1.0 /(gamma-1.0)));
+        gg = raiseto((1.0-(gx*xc+gy*yc+gz*zc)/(Cp*T0)), (gamma/(gamma-1.0)));
+      } else if (c.HB == 3) {
+        double Pexner = 1 + ((gz*gz)/(Cp*T0*Nbv*Nbv)) * (exp(-(Nbv*Nbv/gz)*zc)-1.0);
+        f  = raiseto(Pexner, (-1.0 /(gamma-1.0))) * exp(Nbv*Nbv*zc/gz);
+        gg = raiseto(Pexner, (gamma/(gamma-1.0)));
+      } else { f = gg = 1.0; }
+      h->gravf_h[p] = f; h->gravg_h[p] = gg;
+    }
+    for (int d = 0; d < 3; d++) for (int side = 0; side < 2; side++) {
+      if (side == 0 && h->ip[d] != 0) continue;
+      if (side == 1 && h->ip[d] != c.iproc[d] - 1) continue;
+      int b[3] = { G.N[0], G.N[1], G.N[2] };
+      b[d] = g;
+      for (int k = 0; k < b[2]; k++) for (int j = 0; j < b[1]; j++) for (int i = 0; i < b[0]; i++) {
+        int ib[3] = { i, j, k }, i1[3] = { i, j, k }, i2[3] = { i, j, k };
+        if (side == 0) { i1[d] = ib[d] - g;        i2[d] = g - 1 - ib[d]; }
+        else           { i1[d] = ib[d] + G.N[d];   i2[d] = G.N[d] - 1 - ib[d]; }
+        size_t p1 = (i1[0]+g) + (size_t)G.P[0] * ((i1[1]+g) + (size_t)G.P[1] * (i1[2]+g));
+        size_t p2 = (i2[0]+g) + (size_t)G.P[0] * ((i2[1]+g) + (size_t)G.P[1] * (i2[2]+g));
+        h->gravf_h[p1] = h->gravf_h[p2]; h->gravg_h[p1] = h->gravg_h[p2];
+      }
+    }
+  }
+
+  // ---- RK tableau
+  RKTableau& T = h->rk;
+  memset(&T, 0, sizeof(T));
+  if (c.rk_type == HPB_RK_44) {
+    T.ns = 4;
+    T.A[4] = 0.5; T.A[9] = 0.5; T.A[14] = 1.0;
+    T.c[0] = 0.0; T.c[1] = T.c[2] = 0.5; T.c[3] = 1.0;
+    T.b[0] = T.b[3] = 1.0/6.0; T.b[1] = T.b[2] = 1.0/3.0;
+  } else {
+    T.ns = 3;
+    T.A[3] = 1.0; T.A[6] = 0.25; T.A[7] = 0.25;
+    T.c[1] = 1.0; T.c[2] = 0.5; T.c[0] = 0.0;
+    T.b[0] = T.b[1] = 1.0/6.0; T.b[2] = 2.0/3.0;
+  }
+  return HPB_OK;
+}

@@ -1,0 +1,119 @@
+// hpb_internal.h -- internal types shared by the host layer and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/hypar_b200.h"
+
+#define HPB_G 3   // ghost layers required by WENO5 (_MINIMUM_GHOSTS_ 3)
+
+// ---------------------------------------------------------------------------------------------
+// Device-side description of one rank's block. All index arithmetic is 64-bit (the reference's
+// 32-bit int products overflow beyond ~329^3 points per rank).
+// Device layout of a cell array: SoA, a[v*npg + p], p = (i0+g) + P0*((i1+g) + P1*(i2+g)),
+// P_d = N_d + 2g -- the reference's ghost-padded index (arrayfunctions.h:40-47) per component.
+// Interface array for sweep d: a[v*ni + q], q = i0 + M0*(i1 + M1*i2), M_k = N_k + (k==d).
+struct Geom {
+  int ndims, nvars, g;
+  int N[3];            // local interior size (1 for unused dims)
+  int P[3];            // padded size N+2g (1 for unused dims)
+  long long st[3];     // stride of dim d in cells
+  long long npg;       // points with ghosts
+  int xoff[3];         // offset of dim d in the concatenated x/dxinv arrays
+};
+
+struct Phys {
+  int model, weno, no_limiting, interp_char, upwind, par_scheme, has_grav;
+  double eps, gamma, Re, Pr, RT;     // Re already / Minf ; RT = p0/rho0
+  double grav[3];
+  double adv[15], diff[15];
+};
+
+struct ZoneDev {
+  int type, dim, face, on;
+  int is[3], ie[3];
+  double wall[3];
+};
+
+struct RKTableau { int ns; double A[16], b[4], c[4]; };
+
+// ---------------------------------------------------------------------------------------------
+struct hpb_solver {
+  hpb_config cfg;
+  Geom geo;
+  Phys phys;
+  RKTableau rk;
+  int ip[3], is_global[3];
+  int neighbor[6];                 // rank of the neighbour across face 2d (low) / 2d+1 (high), -1 none
+  int bcperiodic[3];               // mpi->bcperiodic: periodic AND iproc>1
+  std::vector<ZoneDev> zones;
+  std::vector<double> x_h, dxinv_h, gravf_h, gravg_h;   // host copies (set-up products)
+  bool device_ready = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  double t = 0.0;
+
+  // device arrays
+  double *d_x = nullptr, *d_dxinv = nullptr, *d_gravf = nullptr, *d_gravg = nullptr;
+  double *d_u = nullptr;           // solution (SoA, ghosts)
+  double *d_uprev = nullptr;       // u at the start of the step (norm)
+  double *d_U = nullptr;           // stage solution
+  double *d_Udot[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *d_fI = nullptr;          // interface flux (generic path), max over dirs
+  double *d_sI = nullptr;          // interface gravity-source function (generic path)
+  double *d_QD[3] = {nullptr, nullptr, nullptr};   // scaled primitive derivatives (viscous)
+  double *d_FV = nullptr;          // viscous flux scratch
+  double *d_stage_aos = nullptr;   // AoS staging for host<->device transposes
+  double *d_tmp[4] = {nullptr, nullptr, nullptr, nullptr};   // scratch cell arrays for the fine-grained API
+  double *d_w = nullptr;           // stored WENO weights of the fine-grained API (all dirs)
+  double *d_iface[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // interface scratch (fine-grained API)
+  double *d_red = nullptr;         // reduction scratch
+  double *h_red = nullptr;         // pinned
+  // halo buffers per field: send/recv per face
+  double *d_send[3][6] = {}, *d_recv[3][6] = {};
+  size_t face_bytes[6] = {};
+  bool w_valid = false;
+};
+
+// error plumbing (capi.cu)
+int hpb_fail(int code, const char* fmt, ...);
+#define HPB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return hpb_fail(HPB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// host set-up (host_setup.cpp)
+int hpb_setup_host(hpb_solver* h);
+
+// kernel launchers (kernels.cu); all asynchronous on h->stream
+namespace hpbk {
+void aos_to_soa(hpb_solver* h, const double* aos, double* soa, long long npts, int nv);
+void soa_to_aos(hpb_solver* h, const double* soa, double* aos, long long npts, int nv);
+void apply_bc(hpb_solver* h, double* u);
+void pack(hpb_solver* h, const double* a, int nv, int field);
+void unpack(hpb_solver* h, double* a, int nv, int field);
+// hyperbolic term. negate=true: out = -sum_d dxinv*(fhat_{j+1}-fhat_j) (the first direction overwrites the
+// interior, i.e. includes the zeroing of TimeRHSFunctionExplicit.c:89); negate=false: out = +hyp.
+// with_source: gravity-source contribution of each gravity direction is ADDED to src (quirk Q5).
+void hyperbolic(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src);
+void hyperbolic_generic(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src);
+bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src);
+void parabolic_phase1(hpb_solver* h, const double* u);
+void parabolic_phase2(hpb_solver* h, const double* u, double* out, bool accumulate);
+void parabolic_nc1(hpb_solver* h, const double* u, double* out, bool accumulate);
+void set_zero(hpb_solver* h, double* a, long long n);
+void rk_stage(hpb_solver* h, int stage);
+void rk_finish(hpb_solver* h);
+void copy(hpb_solver* h, double* dst, const double* src, long long n);
+void cfl(hpb_solver* h, const double* u, double dt, double* out_host);
+void sumsq_diff(hpb_solver* h, const double* a, const double* b, double* out_host);
+// fine-grained API kernels
+void flux(hpb_solver* h, const double* u, double* f, int dir);
+void modified_solution(hpb_solver* h, const double* u, double* uC);
+void weno_weights(hpb_solver* h, const double* fC, const double* u, int dir, double* w);
+void weno_interp(hpb_solver* h, double* fI, const double* fC, const double* u, const double* w, int upw, int dir, int uflag);
+void upwind(hpb_solver* h, double* fI, const double* fL, const double* fR, const double* uL, const double* uR,
+            const double* u, int dir);
+void first_derivative(hpb_solver* h, double* Df, const double* f, int dir, int nv);
+void second_derivative(hpb_solver* h, double* D2f, const double* f, int dir, int nv, int order);
+}

@@ -1,0 +1,1001 @@
+// kernels.cu -- CUDA kernels (sm_100a) of the explicit-RHS path: layout transposes, boundary
+// conditions, halo pack/unpack, the generic per-interface hyperbolic kernel (all models, component
+// and characteristic WENO5, Rusanov/Roe), flux divergence + gravity source, Navier-Stokes viscous
+// terms, LinearADR diffusion, RK stage updates and reductions.
+// The fused per-cell sweep kernels for the component-wise hot configurations live in sweep_fused.cu.
+#include "hpb_internal.h"
+#include "physics.cuh"
+#include "weno.cuh"
+
+namespace {
+
+constexpr int TPB = 128;
+
+#define MODEL_SWITCH(model, CALL)                                            \
+  switch (model) {                                                           \
+    case HPB_MODEL_LINEAR_ADR: { CALL(HPB_MODEL_LINEAR_ADR); } break;        \
+    case HPB_MODEL_EULER1D:    { CALL(HPB_MODEL_EULER1D); } break;           \
+    case HPB_MODEL_NS2D:       { CALL(HPB_MODEL_NS2D); } break;              \
+    default:                   { CALL(HPB_MODEL_NS3D); } break;              \
+  }
+
+__device__ __forceinline__ long long cell_index(const Geom& G, int i0, int i1, int i2)
+{
+  // local interior indices (may be negative / >= N for ghosts)
+  long long p = i0 + G.g;
+  if (G.ndims > 1) p += (long long)G.P[0] * (i1 + G.g);
+  if (G.ndims > 2) p += (long long)G.P[0] * G.P[1] * (i2 + G.g);
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// layout transposes: HyPar AoS (nvars innermost) <-> device SoA (component-major)
+__global__ void k_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, long long n, int nv)
+{
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  for (int v = 0; v < nv; v++) soa[v * n + p] = aos[p * nv + v];
+}
+__global__ void k_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, long long n, int nv)
+{
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  for (int v = 0; v < nv; v++) aos[p * nv + v] = soa[v * n + p];
+}
+
+// ------------------------------------------------------------------------------------------
+// boundary conditions: one thread per ghost point of the zone box [is, ie)
+// BCPeriodic.c:19-63 (only iproc[dim]==1), BCExtrapolate.c, BCSlipWall.c
+__global__ void k_bc_zone(Geom G, ZoneDev z, double gamma, double* __restrict__ phi)
+{
+  const int b0 = z.ie[0] - z.is[0], b1 = z.ie[1] - z.is[1];
+  int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y, t2 = blockIdx.z;
+  if (t0 >= b0) return;
+  (void)b1;
+  int ib[3] = { t0, t1, t2 };
+  int i1[3] = { t0 + z.is[0], t1 + z.is[1], t2 + z.is[2] };
+  int i2[3] = { i1[0], i1[1], i1[2] };
+  const int dim = z.dim, nv = G.nvars;
+  if (z.type == HPB_BC_PERIODIC) {
+    // source index uses the box-local index (no zone offset), as the reference does
+    i2[0] = ib[0]; i2[1] = ib[1]; i2[2] = ib[2];
+    if (z.face == 1) i2[dim] = ib[dim] + G.N[dim] - G.g;
+  } else {
+    if (z.face == 1) i2[dim] = G.g - 1 - ib[dim];
+    else             i2[dim] = G.N[dim] - ib[dim] - 1;
+  }
+  const long long p1 = cell_index(G, i1[0], i1[1], i1[2]);
+  const long long p2 = cell_index(G, i2[0], i2[1], i2[2]);
+  if (z.type != HPB_BC_SLIP_WALL) {
+    for (int v = 0; v < nv; v++) phi[v * G.npg + p1] = phi[v * G.npg + p2];
+    return;
+  }
+  // slip wall: rho, p copied; normal velocity 2*v_wall - v; energy recomputed
+  const int ndv = nv - 2;
+  const double rho = phi[p2];
+  double vel[3] = { 0.0, 0.0, 0.0 }, vsq = 0.0;
+  for (int k = 0; k < ndv; k++) {
+    // 3-D uses _NavierStokes3DGetFlowVar_ (rho==0 guard); 1-D/2-D use the unguarded Euler macros
+    vel[k] = (ndv == 3 && rho == 0) ? 0.0 : phi[(1 + k) * G.npg + p2] / rho;
+  }
+  for (int k = 0; k < ndv; k++) vsq += vel[k] * vel[k];
+  const double energy = phi[(nv - 1) * G.npg + p2];
+  const double pressure = (energy - 0.5 * rho * vsq) * (gamma - 1.0);
+  const double inv_gamma_m1 = 1.0 / (gamma - 1.0);
+  double vg[3] = { vel[0], vel[1], vel[2] };
+  vg[dim] = 2.0 * z.wall[dim] - vel[dim];
+  double vgsq = 0.0;
+  for (int k = 0; k < ndv; k++) vgsq += vg[k] * vg[k];
+  const double energy_gpt = inv_gamma_m1 * pressure + 0.5 * rho * vgsq;
+  phi[p1] = rho;
+  for (int k = 0; k < ndv; k++) phi[(1 + k) * G.npg + p1] = rho * vg[k];
+  phi[(nv - 1) * G.npg + p1] = energy_gpt;
+}
+
+// ------------------------------------------------------------------------------------------
+// halo pack / unpack (MPIExchangeBoundariesnD.c:42-173). Face box: bounds[d] = g, other dims N.
+// Buffer layout: component-major, then the face box with dim 0 fastest.
+__global__ void k_face_copy(Geom G, double* __restrict__ a, int nv, int d, int off_d, double* __restrict__ buf, int to_buf)
+{
+  int b[3] = { G.N[0], G.N[1], G.N[2] };
+  b[d] = G.g;
+  int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y, t2 = blockIdx.z;
+  if (t0 >= b[0]) return;
+  int s[3] = { t0, t1, t2 };
+  s[d] += off_d;
+  const long long p1 = cell_index(G, s[0], s[1], s[2]);
+  const long long nface = (long long)b[0] * b[1] * b[2];
+  const long long p2 = t0 + (long long)b[0] * (t1 + (long long)b[1] * t2);
+  if (to_buf) for (int v = 0; v < nv; v++) buf[v * nface + p2] = a[v * G.npg + p1];
+  else        for (int v = 0; v < nv; v++) a[v * G.npg + p1] = buf[v * nface + p2];
+}
+
+// ------------------------------------------------------------------------------------------
+// GENERIC hyperbolic kernel: one thread per interface. Restates ReconstructHyperbolic
+// (HyperbolicFunction.c:167-222) without materialising fluxC, uC, the 12 weight arrays or
+// uL/uR/fL/fR: flux + modified solution of the six stencil cells, the four weight sets
+// (L/R x {flux, raw u}: WENOFifthOrderCalculateWeights.c:111-745; characteristic :760-1440),
+// the four reconstructions (Interp1PrimFifthOrderWENO.c:74 / ...Char.c:86), the upwind flux,
+// and -- in gravity directions -- the interface value of the well-balanced source function
+// reconstructed with the SAME flux weights (NavierStokes3DSource.c:77-78, quirk Q5).
+template <int MODEL>
+__global__ void __launch_bounds__(TPB)
+k_iface(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict__ gf,
+        const double* __restrict__ gg, int dir, double* __restrict__ fI, double* __restrict__ sI)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= M0) return;
+  const long long q = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
+  const long long ni = (long long)M0 * M1 * M2;
+  const long long st = G.st[dir];
+  const long long pm1 = cell_index(G, i0, i1, i2) - st;      // cell left of the interface
+
+  double U[6][NV], F[6][NV], V[6][NV], GG[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const long long p = pm1 + (k - 2) * st;
+#pragma unroll
+    for (int v = 0; v < NV; v++) U[k][v] = u[v * G.npg + p];
+    const double gfk = gf ? gf[p] : 1.0;
+    GG[k] = gg ? gg[p] : 1.0;
+    flux_fn<MODEL>(ph, U[k], dir, F[k]);
+    modified_fn<MODEL>(ph, U[k], gfk, GG[k], V[k]);
+  }
+  const double kL = (MODEL == HPB_MODEL_EULER1D) ? (gf ? gf[pm1] : 1.0) : GG[2];
+  const double kR = (MODEL == HPB_MODEL_EULER1D) ? (gf ? gf[pm1 + st] : 1.0) : GG[3];
+
+  double fL[NV], fR[NV], uL[NV], uR[NV];
+  double wLF[NV][3], wRF[NV][3];
+  const bool use_char = ph.interp_char && (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D);
+
+  if (!use_char) {
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      double w1, w2, w3;
+      if (ph.no_limiting) { w1 = 0.1; w2 = 0.6; w3 = 0.3; }
+      else weno_weights_ref(ph.weno, ph.eps, F[0][v], F[1][v], F[2][v], F[3][v], F[4][v], w1, w2, w3);
+      wLF[v][0] = w1; wLF[v][1] = w2; wLF[v][2] = w3;
+      fL[v] = weno_combine(w1, w2, w3, F[0][v], F[1][v], F[2][v], F[3][v], F[4][v]);
+      if (!ph.no_limiting) weno_weights_ref(ph.weno, ph.eps, F[5][v], F[4][v], F[3][v], F[2][v], F[1][v], w1, w2, w3);
+      wRF[v][0] = w1; wRF[v][1] = w2; wRF[v][2] = w3;
+      fR[v] = weno_combine(w1, w2, w3, F[5][v], F[4][v], F[3][v], F[2][v], F[1][v]);
+      // weights from RAW u, applied to the modified solution (quirk Q4)
+      if (!ph.no_limiting) weno_weights_ref(ph.weno, ph.eps, U[0][v], U[1][v], U[2][v], U[3][v], U[4][v], w1, w2, w3);
+      uL[v] = weno_combine(w1, w2, w3, V[0][v], V[1][v], V[2][v], V[3][v], V[4][v]);
+      if (!ph.no_limiting) weno_weights_ref(ph.weno, ph.eps, U[5][v], U[4][v], U[3][v], U[2][v], U[1][v], w1, w2, w3);
+      uR[v] = weno_combine(w1, w2, w3, V[5][v], V[4][v], V[3][v], V[2][v], V[1][v]);
+    }
+  } else {
+    // characteristic: project the stencils with L(Roe average of raw u at cells i-1, i)
+    double uavg[NV], lam[NV], L[NV * NV], R[NV * NV];
+    roe_average<MODEL>(ph, U[2], U[3], uavg);
+    eigen<MODEL>(ph, uavg, dir, lam, L, R);
+    double fLc[NV], fRc[NV], uLc[NV], uRc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      double cF[6], cU[6], cV[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        double sF = 0.0, sU = 0.0, sV = 0.0;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+          sF += L[v * NV + j] * F[k][j];
+          sU += L[v * NV + j] * U[k][j];
+          sV += L[v * NV + j] * V[k][j];
+        }
+        cF[k] = sF; cU[k] = sU; cV[k] = sV;
+      }
+      double w1, w2, w3;
+      if (ph.no_limiting) { w1 = 0.1; w2 = 0.6; w3 = 0.3; }
+      else weno_weights_ref(ph.weno, ph.eps, cF[0], cF[1], cF[2], cF[3], cF[4], w1, w2, w3);
+      wLF[v][0] = w1; wLF[v][1] = w2; wLF[v][2] = w3;
+      fLc[v] = weno_combine(w1, w2, w3, cF[0], cF[1], cF[2], cF[3], cF[4]);
+      if (!ph.no_limiting) weno_weights_ref(ph.weno, ph.eps, cF[5], cF[4], cF[3], cF[2], cF[1], w1, w2, w3);
+      wRF[v][0] = w1; wRF[v][1] = w2; wRF[v][2] = w3;
+      fRc[v] = weno_combine(w1, w2, w3, cF[5], cF[4], cF[3], cF[2], cF[1]);
+      if (!ph.no_limiting) weno_weights_ref(ph.weno, ph.eps, cU[0], cU[1], cU[2], cU[3], cU[4], w1, w2, w3);
+      uLc[v] = weno_combine(w1, w2, w3, cV[0], cV[1], cV[2], cV[3], cV[4]);
+      if (!ph.no_limiting) weno_weights_ref(ph.weno, ph.eps, cU[5], cU[4], cU[3], cU[2], cU[1], w1, w2, w3);
+      uRc[v] = weno_combine(w1, w2, w3, cV[5], cV[4], cV[3], cV[2], cV[1]);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+#pragma unroll
+      for (int j = 0; j < NV; j++) {
+        a += R[i * NV + j] * fLc[j]; b += R[i * NV + j] * fRc[j];
+        c += R[i * NV + j] * uLc[j]; d += R[i * NV + j] * uRc[j];
+      }
+      fL[i] = a; fR[i] = b; uL[i] = c; uR[i] = d;
+    }
+  }
+
+  double fhat[NV];
+  upwind_fn<MODEL>(ph, dir, fL, fR, uL, uR, U[2], U[3], kL, kR, fhat);
+#pragma unroll
+  for (int v = 0; v < NV; v++) fI[v * ni + q] = fhat[v];
+
+  if (MODEL == HPB_MODEL_NS3D && sI != nullptr) {
+    // source function G_j = g_grav_j * (0, d_x, d_y, d_z, 1): only components dir+1 and 4 are non-zero
+    const int vm = dir + 1;
+    const double sLm = weno_combine(wLF[vm][0], wLF[vm][1], wLF[vm][2], GG[0], GG[1], GG[2], GG[3], GG[4]);
+    const double sRm = weno_combine(wRF[vm][0], wRF[vm][1], wRF[vm][2], GG[5], GG[4], GG[3], GG[2], GG[1]);
+    const double sLe = weno_combine(wLF[NV-1][0], wLF[NV-1][1], wLF[NV-1][2], GG[0], GG[1], GG[2], GG[3], GG[4]);
+    const double sRe = weno_combine(wRF[NV-1][0], wRF[NV-1][1], wRF[NV-1][2], GG[5], GG[4], GG[3], GG[2], GG[1]);
+    sI[q]      = 0.5 * (sLm + sRm);
+    sI[ni + q] = 0.5 * (sLe + sRe);
+  }
+}
+
+// flux divergence (HyperbolicFunction.c:94-109): mode 0: out = -dxinv*(fI[p2]-fI[p1]); 1: out -= ...;
+// 2: out = +...; 3: out += ... (the positive forms serve hpb_HyperbolicFunction)
+__global__ void k_divergence(Geom G, const double* __restrict__ dxinv, const double* __restrict__ fI, int dir,
+                             double* __restrict__ out, int mode)
+{
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= G.N[0]) return;
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  const long long ni = (long long)M0 * M1 * M2;
+  const long long q1 = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
+  const long long qs = (dir == 0 ? 1 : dir == 1 ? (long long)M0 : (long long)M0 * M1);
+  const long long p = cell_index(G, i0, i1, i2);
+  const int idx = (dir == 0 ? i0 : dir == 1 ? i1 : i2);
+  const double dxi = dxinv[G.xoff[dir] + G.g + idx];
+  for (int v = 0; v < G.nvars; v++) {
+    const double t = dxi * (fI[v * ni + q1 + qs] - fI[v * ni + q1]);
+    const long long a = v * G.npg + p;
+    if (mode == 0) out[a] = -t;
+    else if (mode == 1) out[a] -= t;
+    else if (mode == 2) out[a] = t;
+    else out[a] += t;
+  }
+}
+
+// gravity source (NavierStokes3DSource.c:80-100): src_v += (term_v*f_grav) * (S_I[p2]-S_I[p1]) * dxinv
+__global__ void k_ns3d_source(Geom G, Phys ph, const double* __restrict__ dxinv, const double* __restrict__ u,
+                              const double* __restrict__ gf, const double* __restrict__ sI, int dir,
+                              double* __restrict__ out)
+{
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= G.N[0]) return;
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  const long long ni = (long long)M0 * M1 * M2;
+  const long long q1 = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
+  const long long qs = (dir == 0 ? 1 : dir == 1 ? (long long)M0 : (long long)M0 * M1);
+  const long long p = cell_index(G, i0, i1, i2);
+  const int idx = (dir == 0 ? i0 : dir == 1 ? i1 : i2);
+  const double dxi = dxinv[G.xoff[dir] + G.g + idx];
+  const double rho = u[p];
+  const double vd = (rho == 0) ? 0.0 : u[(1 + dir) * G.npg + p] / rho;
+  const double f = gf[p];
+  const double tm = rho * ph.RT, te = rho * ph.RT * vd;
+  out[(1 + dir) * G.npg + p] += ((tm * f) * (sI[q1 + qs] - sI[q1]) * dxi);
+  out[4 * G.npg + p]         += ((te * f) * (sI[ni + q1 + qs] - sI[ni + q1]) * dxi);
+}
+
+// ------------------------------------------------------------------------------------------
+// Navier-Stokes viscous terms (NavierStokes3DParabolicFunction.c:50-325, 2-D :38-230).
+// phase 1: QD[dir] = dxinv * D_dir(Q), Q = (rho, u, v, w, T), on every line along dir whose transverse
+// indices are interior; ghosts along the line included, one-sided at the line ends
+// (FirstDerivativeFourthOrder.c:36-129). Locations never written stay 0 (the reference callocs them).
+template <int MODEL>
+__device__ __forceinline__ void prim_fn(double gamma, const double* __restrict__ u, long long npg, long long p, double* Q)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  double uu[NV], rho, vel[3], e, P;
+#pragma unroll
+  for (int v = 0; v < NV; v++) uu[v] = u[v * npg + p];
+  flowvar<MODEL>(uu, gamma, rho, vel, e, P);
+  Q[0] = rho;
+#pragma unroll
+  for (int k = 0; k < NV - 2; k++) Q[1 + k] = vel[k];
+  Q[NV - 1] = gamma * P / rho;
+}
+
+__device__ __forceinline__ double d1_coeffs(int i, int N, int g, const double* f /* f[-4..4] centred */)
+{
+  const double one_twelve = 1.0 / 12.0;
+  if (i == -g)            return (-25*f[0]+48*f[1]-36*f[2]+16*f[3]-3*f[4])*one_twelve;
+  else if (i == -g + 1)   return (-3*f[-1]-10*f[0]+18*f[1]-6*f[2]+f[3])*one_twelve;
+  else if (i < N + g - 2) return (f[-2]-8*f[-1]+8*f[1]-f[2])*one_twelve;
+  else if (i == N + g - 2)return (-f[-3]+6*f[-2]-18*f[-1]+10*f[0]+3*f[1])*one_twelve;
+  else                    return (3*f[-4]-16*f[-3]+36*f[-2]-48*f[-1]+25*f[0])*one_twelve;
+}
+
+template <int MODEL>
+__global__ void k_ns_qderiv(Geom G, double gamma, const double* __restrict__ dxinv, const double* __restrict__ u,
+                            int dir, double* __restrict__ QD)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  // thread box: full (with ghosts) along dir, interior along the others
+  int B[3] = { G.N[0], G.N[1], G.N[2] };
+  B[dir] = G.P[dir];
+  int t[3] = { (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)blockIdx.y, (int)blockIdx.z };
+  if (t[0] >= B[0]) return;
+  int ii[3] = { t[0], t[1], t[2] };
+  ii[dir] -= G.g;
+  const int i = ii[dir], N = G.N[dir], g = G.g;
+  const long long p = cell_index(G, ii[0], ii[1], ii[2]);
+  const long long st = G.st[dir];
+  // stencil range needed
+  int lo, hi;
+  if (i == -g) { lo = 0; hi = 4; } else if (i == -g + 1) { lo = -1; hi = 3; }
+  else if (i < N + g - 2) { lo = -2; hi = 2; } else if (i == N + g - 2) { lo = -3; hi = 1; } else { lo = -4; hi = 0; }
+  double f[NV][9];
+  for (int k = lo; k <= hi; k++) {
+    double Q[NV];
+    prim_fn<MODEL>(gamma, u, G.npg, p + k * st, Q);
+#pragma unroll
+    for (int v = 0; v < NV; v++) f[v][k + 4] = Q[v];
+  }
+  const double dxi = dxinv[G.xoff[dir] + g + i];
+#pragma unroll
+  for (int v = 0; v < NV; v++) QD[v * G.npg + p] = d1_coeffs(i, N, g, &f[v][4]) * dxi;
+}
+
+// viscous flux of direction dir at one point (NavierStokes3DParabolicFunction.c:152-195 etc.)
+template <int MODEL>
+__device__ __forceinline__ void fviscous_fn(const Phys& ph, const Geom& G, const double* __restrict__ u,
+                                            const double* __restrict__ QDx, const double* __restrict__ QDy,
+                                            const double* __restrict__ QDz, long long p, int dir, double* FV)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  const double two_third = 2.0 / 3.0;
+  const double inv_gamma_m1 = 1.0 / (ph.gamma - 1.0), inv_Re = 1.0 / ph.Re, inv_Pr = 1.0 / ph.Pr;
+  double Q[NV];
+  prim_fn<MODEL>(ph.gamma, u, G.npg, p, Q);
+  const double T = Q[NV - 1];
+  const double mu = exp(0.76 * log(T));            // raiseto(T, 0.76), math_ops.h:37
+  const long long n = G.npg;
+  if (MODEL == HPB_MODEL_NS3D) {
+    const double uvel = Q[1], vvel = Q[2], wvel = Q[3];
+    const double ux = QDx[1*n+p], vx = QDx[2*n+p], wx = QDx[3*n+p];
+    const double uy = QDy[1*n+p], vy = QDy[2*n+p], wy = QDy[3*n+p];
+    const double uz = QDz[1*n+p], vz = QDz[2*n+p], wz = QDz[3*n+p];
+    double t1, t2, t3, q;
+    if (dir == 0) {
+      t1 = two_third * (mu*inv_Re) * (2*ux - vy - wz);
+      t2 = (mu*inv_Re) * (uy + vx);
+      t3 = (mu*inv_Re) * (uz + wx);
+      q  = ( mu*inv_Re * inv_gamma_m1 * inv_Pr ) * QDx[4*n+p];
+    } else if (dir == 1) {
+      t1 = (mu*inv_Re) * (uy + vx);
+      t2 = two_third * (mu*inv_Re) * (-ux + 2*vy - wz);
+      t3 = (mu*inv_Re) * (vz + wy);
+      q  = ( mu*inv_Re * inv_gamma_m1 * inv_Pr ) * QDy[4*n+p];
+    } else {
+      t1 = (mu*inv_Re) * (uz + wx);
+      t2 = (mu*inv_Re) * (vz + wy);
+      t3 = two_third * (mu*inv_Re) * (-ux - vy + 2*wz);
+      q  = ( mu*inv_Re * inv_gamma_m1 * inv_Pr ) * QDz[4*n+p];
+    }
+    FV[0] = t1; FV[1] = t2; FV[2] = t3; FV[3] = uvel*t1 + vvel*t2 + wvel*t3 + q;
+  } else {
+    const double uvel = Q[1], vvel = Q[2];
+    const double ux = QDx[1*n+p], vx = QDx[2*n+p];
+    const double uy = QDy[1*n+p], vy = QDy[2*n+p];
+    double t1, t2, q;
+    if (dir == 0) {
+      t1 = two_third * (mu*inv_Re) * (2*ux - vy);
+      t2 = (mu*inv_Re) * (uy + vx);
+      q  = ( (mu*inv_Re) * inv_gamma_m1 * inv_Pr ) * QDx[3*n+p];
+    } else {
+      t1 = (mu*inv_Re) * (uy + vx);
+      t2 = two_third * (mu*inv_Re) * (-ux + 2*vy);
+      q  = ( (mu*inv_Re) * inv_gamma_m1 * inv_Pr ) * QDy[3*n+p];
+    }
+    FV[0] = t1; FV[1] = t2; FV[2] = uvel*t1 + vvel*t2 + q;
+  }
+}
+
+// phase 2a: FV (components 1..NV-1; component 0 is identically zero) for direction dir at the points
+// the interior derivative needs: interior transverse, [-2, N+2) along dir
+template <int MODEL>
+__global__ void k_ns_fviscous(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict__ QDx,
+                              const double* __restrict__ QDy, const double* __restrict__ QDz, int dir,
+                              double* __restrict__ FV)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  int B[3] = { G.N[0], G.N[1], G.N[2] };
+  B[dir] += 4;
+  int t[3] = { (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)blockIdx.y, (int)blockIdx.z };
+  if (t[0] >= B[0]) return;
+  int ii[3] = { t[0], t[1], t[2] };
+  ii[dir] -= 2;
+  const long long p = cell_index(G, ii[0], ii[1], ii[2]);
+  double F[NV - 1];
+  fviscous_fn<MODEL>(ph, G, u, QDx, QDy, QDz, p, dir, F);
+#pragma unroll
+  for (int v = 0; v < NV - 1; v++) FV[v * G.npg + p] = F[v];
+}
+
+// phase 2b: out += dxinv * D_dir(FV) at interior points (central stencil only is reached there)
+__global__ void k_ns_par_accum(Geom G, const double* __restrict__ dxinv, const double* __restrict__ FV, int dir,
+                               double* __restrict__ out)
+{
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= G.N[0]) return;
+  const long long p = cell_index(G, i0, i1, i2);
+  const long long st = G.st[dir];
+  const int idx = (dir == 0 ? i0 : dir == 1 ? i1 : i2);
+  const double dxi = dxinv[G.xoff[dir] + G.g + idx];
+  const double one_twelve = 1.0 / 12.0;
+  for (int v = 1; v < G.nvars; v++) {
+    const double* f = FV + (v - 1) * G.npg + p;
+    const double d = (f[-2*st] - 8*f[-st] + 8*f[st] - f[2*st]) * one_twelve;
+    out[v * G.npg + p] += (dxi * d);
+  }
+}
+
+// LinearADR diffusion through ParabolicFunctionNC1Stage.c: out += dxinv^2 * D2_d(nu_d u)
+__global__ void k_linadr_par(Geom G, Phys ph, const double* __restrict__ dxinv, const double* __restrict__ u,
+                             double* __restrict__ out)
+{
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= G.N[0]) return;
+  const long long p = cell_index(G, i0, i1, i2);
+  const int idx[3] = { i0, i1, i2 };
+  const double one_twelve = 1.0 / 12.0;
+  for (int v = 0; v < G.nvars; v++) {
+    double par = 0.0;
+    for (int d = 0; d < G.ndims; d++) {
+      const double nu = ph.diff[G.nvars * d + v];
+      const double* f = u + v * G.npg + p;
+      const long long st = G.st[d];
+      double d2;
+      if (ph.par_scheme == 2) d2 = nu*f[-st] - 2*(nu*f[0]) + nu*f[st];
+      else d2 = (-(nu*f[-2*st]) + 16*(nu*f[-st]) - 30*(nu*f[0]) + 16*(nu*f[st]) - (nu*f[2*st])) * one_twelve;
+      const double dxi = dxinv[G.xoff[d] + G.g + idx[d]];
+      par += (dxi * dxi * d2);
+    }
+    out[v * G.npg + p] += par;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// RK stage vector and step completion (TimeRK.c:126-195), over the ghost-padded length like the
+// reference. Products are rounded before the add (no FMA contraction) so the update carries the
+// reference's own rounding.
+struct RKArgs { const double* k[4]; double a[4]; int n; };
+
+__global__ void k_rk_combine(const double* __restrict__ u, RKArgs args, double* __restrict__ out, long long n)
+{
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    double t = u[i];
+    for (int s = 0; s < args.n; s++) t = __dadd_rn(t, __dmul_rn(args.a[s], args.k[s][i]));
+    out[i] = t;
+  }
+}
+
+__global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src, long long n)
+{
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// reductions: max CFL (NavierStokes3DComputeCFL.c:16-49 and the 2-D/1-D/LinearADR twins) and the
+// interior sum of squares of (a - b) (TimePostStep.c:44-63)
+__device__ __forceinline__ double block_reduce(double v, bool is_max)
+{
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_down_sync(0xffffffffu, v, o);
+    v = is_max ? fmax(v, other) : v + other;
+  }
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (lane < nw) ? sh[lane] : (is_max ? 0.0 : 0.0);
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_down_sync(0xffffffffu, v, o);
+      v = is_max ? fmax(v, other) : v + other;
+    }
+  }
+  return v;
+}
+
+__device__ __forceinline__ void atomic_max_double(double* addr, double val)
+{
+  // values are non-negative: the bit patterns order like the doubles
+  atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(val));
+}
+
+template <int MODEL>
+__global__ void k_cfl(Geom G, Phys ph, const double* __restrict__ dxinv, const double* __restrict__ u, double dt,
+                      double* __restrict__ out)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  double m = 0.0;
+  if (i0 < G.N[0]) {
+    const int idx[3] = { i0, i1, i2 };
+    if (MODEL == HPB_MODEL_LINEAR_ADR) {
+      for (int d = 0; d < G.ndims; d++) {
+        const double c = ph.adv[G.nvars * d] * dt * dxinv[G.xoff[d] + G.g + idx[d]];
+        if (c > m) m = c;
+      }
+    } else {
+      const long long p = cell_index(G, i0, i1, i2);
+      double uu[NV], rho, vel[3], e, P;
+#pragma unroll
+      for (int v = 0; v < NV; v++) uu[v] = u[v * G.npg + p];
+      flowvar<MODEL>(uu, ph.gamma, rho, vel, e, P);
+      const double c = sqrt(ph.gamma * P / rho);
+      for (int d = 0; d < NV - 2; d++) {
+        const double l = (fabs(vel[d]) + c) * dt * dxinv[G.xoff[d] + G.g + idx[d]];
+        if (l > m) m = l;
+      }
+    }
+  }
+  m = block_reduce(m, true);
+  if (threadIdx.x == 0) atomic_max_double(out, m);
+}
+
+__global__ void k_sumsq_diff(Geom G, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out)
+{
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  double s = 0.0;
+  if (i0 < G.N[0]) {
+    const long long p = cell_index(G, i0, i1, i2);
+    for (int v = 0; v < G.nvars; v++) { const double d = a[v * G.npg + p] - b[v * G.npg + p]; s += d * d; }
+  }
+  s = block_reduce(s, false);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// fine-grained API kernels (the reference's individual function pointers)
+template <int MODEL>
+__global__ void k_flux(Geom G, Phys ph, const double* __restrict__ u, int dir, double* __restrict__ f)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= G.npg) return;
+  double uu[NV], ff[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) uu[v] = u[v * G.npg + p];
+  flux_fn<MODEL>(ph, uu, dir, ff);
+#pragma unroll
+  for (int v = 0; v < NV; v++) f[v * G.npg + p] = ff[v];
+}
+
+template <int MODEL>
+__global__ void k_modified(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict__ gf,
+                           const double* __restrict__ gg, double* __restrict__ uC)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= G.npg) return;
+  double uu[NV], cc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) uu[v] = u[v * G.npg + p];
+  modified_fn<MODEL>(ph, uu, gf ? gf[p] : 1.0, gg ? gg[p] : 1.0, cc);
+#pragma unroll
+  for (int v = 0; v < NV; v++) uC[v * G.npg + p] = cc[v];
+}
+
+// SetInterpLimiterVar: the 12 weight arrays of one direction, w[(3*blk+k)*ni*NV + v*ni + q],
+// blk = LF, LU, RF, RU (WENOFifthOrderCalculateWeights.c:147-158)
+template <int MODEL>
+__global__ void k_weights(Geom G, Phys ph, const double* __restrict__ fC, const double* __restrict__ u, int dir,
+                          double* __restrict__ w)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= M0) return;
+  const long long q = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
+  const long long ni = (long long)M0 * M1 * M2;
+  const long long st = G.st[dir];
+  const long long pm1 = cell_index(G, i0, i1, i2) - st;
+  double U[6][NV], F[6][NV];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const long long p = pm1 + (k - 2) * st;
+#pragma unroll
+    for (int v = 0; v < NV; v++) { U[k][v] = u[v * G.npg + p]; F[k][v] = fC[v * G.npg + p]; }
+  }
+  const bool use_char = ph.interp_char && (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D);
+  double L[NV * NV];
+  if (use_char) {
+    double uavg[NV], lam[NV], R[NV * NV];
+    roe_average<MODEL>(ph, U[2], U[3], uavg);
+    eigen<MODEL>(ph, uavg, dir, lam, L, R);
+  }
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    double cF[6], cU[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      if (use_char) {
+        double sF = 0.0, sU = 0.0;
+#pragma unroll
+        for (int j = 0; j < NV; j++) { sF += L[v * NV + j] * F[k][j]; sU += L[v * NV + j] * U[k][j]; }
+        cF[k] = sF; cU[k] = sU;
+      } else { cF[k] = F[k][v]; cU[k] = U[k][v]; }
+    }
+    double ws[4][3];
+    if (ph.no_limiting) {
+      for (int b = 0; b < 4; b++) { ws[b][0] = 0.1; ws[b][1] = 0.6; ws[b][2] = 0.3; }
+    } else {
+      weno_weights_ref(ph.weno, ph.eps, cF[0], cF[1], cF[2], cF[3], cF[4], ws[0][0], ws[0][1], ws[0][2]);
+      weno_weights_ref(ph.weno, ph.eps, cU[0], cU[1], cU[2], cU[3], cU[4], ws[1][0], ws[1][1], ws[1][2]);
+      weno_weights_ref(ph.weno, ph.eps, cF[5], cF[4], cF[3], cF[2], cF[1], ws[2][0], ws[2][1], ws[2][2]);
+      weno_weights_ref(ph.weno, ph.eps, cU[5], cU[4], cU[3], cU[2], cU[1], ws[3][0], ws[3][1], ws[3][2]);
+    }
+    for (int b = 0; b < 4; b++)
+      for (int k = 0; k < 3; k++) w[((3 * b + k) * NV + v) * ni + q] = ws[b][k];
+  }
+}
+
+// InterpolateInterfacesHyp with stored weights (Interp1PrimFifthOrderWENO.c:74, ...Char.c:86)
+template <int MODEL>
+__global__ void k_interp(Geom G, Phys ph, const double* __restrict__ fC, const double* __restrict__ u,
+                         const double* __restrict__ w, int upw, int dir, int uflag, double* __restrict__ fI)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= M0) return;
+  const long long q = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
+  const long long ni = (long long)M0 * M1 * M2;
+  const long long st = G.st[dir];
+  const long long pm1 = cell_index(G, i0, i1, i2) - st;
+  const int blk = (upw < 0 ? 2 : 0) + (uflag ? 1 : 0);
+  // stencil (m3,m2,m1,p1,p2): left-biased = cells i-3..i+1, right-biased = i+2..i-2
+  long long ps[5];
+  for (int k = 0; k < 5; k++) ps[k] = (upw > 0) ? pm1 + (k - 2) * st : pm1 + (3 - k) * st;
+  double S[5][NV];
+#pragma unroll
+  for (int k = 0; k < 5; k++)
+#pragma unroll
+    for (int v = 0; v < NV; v++) S[k][v] = fC[v * G.npg + ps[k]];
+  const bool use_char = ph.interp_char && (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D);
+  double out[NV];
+  if (!use_char) {
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      const double w1 = w[((3 * blk + 0) * NV + v) * ni + q], w2 = w[((3 * blk + 1) * NV + v) * ni + q],
+                   w3 = w[((3 * blk + 2) * NV + v) * ni + q];
+      out[v] = weno_combine(w1, w2, w3, S[0][v], S[1][v], S[2][v], S[3][v], S[4][v]);
+    }
+  } else {
+    double UL[NV], UR[NV], uavg[NV], lam[NV], L[NV * NV], R[NV * NV], fc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) { UL[v] = u[v * G.npg + pm1]; UR[v] = u[v * G.npg + pm1 + st]; }
+    roe_average<MODEL>(ph, UL, UR, uavg);
+    eigen<MODEL>(ph, uavg, dir, lam, L, R);
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      double c[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NV; j++) s += L[v * NV + j] * S[k][j];
+        c[k] = s;
+      }
+      const double w1 = w[((3 * blk + 0) * NV + v) * ni + q], w2 = w[((3 * blk + 1) * NV + v) * ni + q],
+                   w3 = w[((3 * blk + 2) * NV + v) * ni + q];
+      fc[v] = weno_combine(w1, w2, w3, c[0], c[1], c[2], c[3], c[4]);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NV; j++) s += R[i * NV + j] * fc[j];
+      out[i] = s;
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; v++) fI[v * ni + q] = out[v];
+}
+
+template <int MODEL>
+__global__ void k_upwind(Geom G, Phys ph, const double* __restrict__ fL, const double* __restrict__ fR,
+                         const double* __restrict__ uL, const double* __restrict__ uR, const double* __restrict__ u,
+                         const double* __restrict__ gf, const double* __restrict__ gg, int dir, double* __restrict__ fI)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= M0) return;
+  const long long q = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
+  const long long ni = (long long)M0 * M1 * M2;
+  const long long st = G.st[dir];
+  const long long pL = cell_index(G, i0, i1, i2) - st, pR = pL + st;
+  double a[NV], b[NV], c[NV], d[NV], cl[NV], cr[NV], out[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    a[v] = fL[v * ni + q]; b[v] = fR[v * ni + q]; c[v] = uL[v * ni + q]; d[v] = uR[v * ni + q];
+    cl[v] = u[v * G.npg + pL]; cr[v] = u[v * G.npg + pR];
+  }
+  const double* kk = (MODEL == HPB_MODEL_EULER1D) ? gf : gg;
+  upwind_fn<MODEL>(ph, dir, a, b, c, d, cl, cr, kk ? kk[pL] : 1.0, kk ? kk[pR] : 1.0, out);
+#pragma unroll
+  for (int v = 0; v < NV; v++) fI[v * ni + q] = out[v];
+}
+
+// FirstDerivativeFourthOrderCentral over any nv-component SoA array (un-scaled)
+__global__ void k_first_derivative(Geom G, const double* __restrict__ f, int dir, int nv, double* __restrict__ Df)
+{
+  int B[3] = { G.N[0], G.N[1], G.N[2] };
+  B[dir] = G.P[dir];
+  int t[3] = { (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)blockIdx.y, (int)blockIdx.z };
+  if (t[0] >= B[0]) return;
+  int ii[3] = { t[0], t[1], t[2] };
+  ii[dir] -= G.g;
+  const int i = ii[dir];
+  const long long p = cell_index(G, ii[0], ii[1], ii[2]);
+  const long long st = G.st[dir];
+  int lo, hi;
+  const int N = G.N[dir], g = G.g;
+  if (i == -g) { lo = 0; hi = 4; } else if (i == -g + 1) { lo = -1; hi = 3; }
+  else if (i < N + g - 2) { lo = -2; hi = 2; } else if (i == N + g - 2) { lo = -3; hi = 1; } else { lo = -4; hi = 0; }
+  for (int v = 0; v < nv; v++) {
+    double s[9];
+    for (int k = lo; k <= hi; k++) s[k + 4] = f[v * G.npg + p + k * st];
+    Df[v * G.npg + p] = d1_coeffs(i, N, g, &s[4]);
+  }
+}
+
+__global__ void k_second_derivative(Geom G, const double* __restrict__ f, int dir, int nv, int order, double* __restrict__ D2f)
+{
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= G.N[0]) return;
+  const long long p = cell_index(G, i0, i1, i2);
+  const long long st = G.st[dir];
+  const double one_twelve = 1.0 / 12.0;
+  for (int v = 0; v < nv; v++) {
+    const double* s = f + v * G.npg + p;
+    if (order == 2) D2f[v * G.npg + p] = s[-st] - 2*s[0] + s[st];
+    else D2f[v * G.npg + p] = (-s[-2*st] + 16*s[-st] - 30*s[0] + 16*s[st] - s[2*st]) * one_twelve;
+  }
+}
+
+inline dim3 grid3(int n0, int n1, int n2) { return dim3((n0 + TPB - 1) / TPB, n1, n2); }
+inline unsigned grid1(long long n) { long long b = (n + 255) / 256; return (unsigned)(b > 148LL * 64 ? 148 * 64 : (b < 1 ? 1 : b)); }
+
+} // namespace
+
+// =============================================================================================
+// launchers
+namespace hpbk {
+
+#define LAUNCHED(h) ((h)->launches++)
+
+void aos_to_soa(hpb_solver* h, const double* aos, double* soa, long long npts, int nv)
+{
+  k_aos_to_soa<<<(unsigned)((npts + 255) / 256), 256, 0, h->stream>>>(aos, soa, npts, nv); LAUNCHED(h);
+}
+void soa_to_aos(hpb_solver* h, const double* soa, double* aos, long long npts, int nv)
+{
+  k_soa_to_aos<<<(unsigned)((npts + 255) / 256), 256, 0, h->stream>>>(soa, aos, npts, nv); LAUNCHED(h);
+}
+
+void apply_bc(hpb_solver* h, double* u)
+{
+  const Geom& G = h->geo;
+  for (const ZoneDev& z : h->zones) {
+    if (!z.on) continue;
+    if (z.type == HPB_BC_PERIODIC && h->cfg.iproc[z.dim] != 1) continue;
+    const int b0 = z.ie[0] - z.is[0], b1 = (G.ndims > 1 ? z.ie[1] - z.is[1] : 1), b2 = (G.ndims > 2 ? z.ie[2] - z.is[2] : 1);
+    if (b0 <= 0 || b1 <= 0 || b2 <= 0) continue;
+    k_bc_zone<<<grid3(b0, b1, b2), TPB, 0, h->stream>>>(G, z, h->phys.gamma, u); LAUNCHED(h);
+  }
+}
+
+static void face_launch(hpb_solver* h, double* a, int nv, int d, int off_d, double* buf, int to_buf)
+{
+  const Geom& G = h->geo;
+  int b[3] = { G.N[0], G.N[1], G.N[2] };
+  b[d] = G.g;
+  k_face_copy<<<grid3(b[0], b[1], b[2]), TPB, 0, h->stream>>>(G, a, nv, d, off_d, buf, to_buf); LAUNCHED(h);
+}
+
+void pack(hpb_solver* h, const double* a, int nv, int field)
+{
+  const Geom& G = h->geo;
+  for (int d = 0; d < G.ndims; d++) {
+    if (h->neighbor[2*d] >= 0)   face_launch(h, (double*)a, nv, d, 0, h->d_send[field][2*d], 1);
+    if (h->neighbor[2*d+1] >= 0) face_launch(h, (double*)a, nv, d, G.N[d] - G.g, h->d_send[field][2*d+1], 1);
+  }
+}
+void unpack(hpb_solver* h, double* a, int nv, int field)
+{
+  const Geom& G = h->geo;
+  for (int d = 0; d < G.ndims; d++) {
+    if (h->neighbor[2*d] >= 0)   face_launch(h, a, nv, d, -G.g, h->d_recv[field][2*d], 0);
+    if (h->neighbor[2*d+1] >= 0) face_launch(h, a, nv, d, G.N[d], h->d_recv[field][2*d+1], 0);
+  }
+}
+
+void set_zero(hpb_solver* h, double* a, long long n) { cudaMemsetAsync(a, 0, n * sizeof(double), h->stream); }
+
+void copy(hpb_solver* h, double* dst, const double* src, long long n)
+{
+  k_copy<<<grid1(n), 256, 0, h->stream>>>(dst, src, n); LAUNCHED(h);
+}
+
+void hyperbolic_generic(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src)
+{
+  const Geom& G = h->geo;
+  const bool grav = h->phys.has_grav;
+  const double* gf = (h->cfg.model == HPB_MODEL_LINEAR_ADR) ? nullptr : h->d_gravf;
+  const double* gg = (h->cfg.model == HPB_MODEL_LINEAR_ADR) ? nullptr : h->d_gravg;
+  for (int d = 0; d < G.ndims; d++) {
+    const int M[3] = { G.N[0] + (d == 0), G.N[1] + (d == 1), G.N[2] + (d == 2) };
+    double* sI = (with_source && grav && h->phys.grav[d] != 0.0) ? h->d_sI : nullptr;
+#define CALL(M_) k_iface<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, u, gf, gg, d, h->d_fI, sI)
+    MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+    LAUNCHED(h);
+    const int mode = negate ? (d == 0 ? 0 : 1) : (d == 0 ? 2 : 3);
+    k_divergence<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, h->d_dxinv, h->d_fI, d, out, mode); LAUNCHED(h);
+    if (sI) {
+      k_ns3d_source<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, h->phys, h->d_dxinv, u, h->d_gravf, sI, d, src);
+      LAUNCHED(h);
+    }
+  }
+}
+
+void parabolic_phase1(hpb_solver* h, const double* u)
+{
+  const Geom& G = h->geo;
+  for (int d = 0; d < G.ndims; d++) {
+    int B[3] = { G.N[0], G.N[1], G.N[2] };
+    B[d] = G.P[d];
+    if (h->cfg.model == HPB_MODEL_NS3D)
+      k_ns_qderiv<HPB_MODEL_NS3D><<<grid3(B[0], B[1], B[2]), TPB, 0, h->stream>>>(G, h->phys.gamma, h->d_dxinv, u, d, h->d_QD[d]);
+    else
+      k_ns_qderiv<HPB_MODEL_NS2D><<<grid3(B[0], B[1], B[2]), TPB, 0, h->stream>>>(G, h->phys.gamma, h->d_dxinv, u, d, h->d_QD[d]);
+    LAUNCHED(h);
+  }
+}
+
+void parabolic_phase2(hpb_solver* h, const double* u, double* out, bool accumulate)
+{
+  const Geom& G = h->geo;
+  if (!accumulate) set_zero(h, out, G.npg * G.nvars);
+  for (int d = 0; d < G.ndims; d++) {
+    int B[3] = { G.N[0], G.N[1], G.N[2] };
+    B[d] += 4;
+    if (h->cfg.model == HPB_MODEL_NS3D)
+      k_ns_fviscous<HPB_MODEL_NS3D><<<grid3(B[0], B[1], B[2]), TPB, 0, h->stream>>>(G, h->phys, u, h->d_QD[0], h->d_QD[1], h->d_QD[2], d, h->d_FV);
+    else
+      k_ns_fviscous<HPB_MODEL_NS2D><<<grid3(B[0], B[1], B[2]), TPB, 0, h->stream>>>(G, h->phys, u, h->d_QD[0], h->d_QD[1], nullptr, d, h->d_FV);
+    LAUNCHED(h);
+    k_ns_par_accum<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, h->d_dxinv, h->d_FV, d, out); LAUNCHED(h);
+  }
+}
+
+void parabolic_nc1(hpb_solver* h, const double* u, double* out, bool accumulate)
+{
+  const Geom& G = h->geo;
+  if (!accumulate) set_zero(h, out, G.npg * G.nvars);
+  bool any = false;
+  for (int i = 0; i < G.ndims * G.nvars; i++) any = any || (h->phys.diff[i] != 0.0);
+  if (h->cfg.model != HPB_MODEL_LINEAR_ADR || !any) return;   // identically zero term
+  k_linadr_par<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, h->phys, h->d_dxinv, u, out); LAUNCHED(h);
+}
+
+void rk_stage(hpb_solver* h, int stage)
+{
+  const long long n = h->geo.npg * h->geo.nvars;
+  RKArgs a; a.n = 0;
+  for (int i = 0; i < stage; i++) {
+    // the reference adds every i < stage, including zero coefficients (adds 0*k: a no-op on finite data)
+    const double c = h->cfg.dt * h->rk.A[stage * h->rk.ns + i];
+    if (c == 0.0) continue;
+    a.k[a.n] = h->d_Udot[i]; a.a[a.n] = c; a.n++;
+  }
+  k_rk_combine<<<grid1(n), 256, 0, h->stream>>>(h->d_u, a, h->d_U, n); LAUNCHED(h);
+}
+
+void rk_finish(hpb_solver* h)
+{
+  const long long n = h->geo.npg * h->geo.nvars;
+  RKArgs a; a.n = h->rk.ns;
+  for (int s = 0; s < h->rk.ns; s++) { a.k[s] = h->d_Udot[s]; a.a[s] = h->cfg.dt * h->rk.b[s]; }
+  k_rk_combine<<<grid1(n), 256, 0, h->stream>>>(h->d_u, a, h->d_u, n); LAUNCHED(h);
+}
+
+void cfl(hpb_solver* h, const double* u, double dt, double* out_host)
+{
+  const Geom& G = h->geo;
+  cudaMemsetAsync(h->d_red, 0, sizeof(double), h->stream);
+#define CALL(M_) k_cfl<M_><<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, h->phys, h->d_dxinv, u, dt, h->d_red)
+  MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+  LAUNCHED(h);
+  cudaMemcpyAsync(h->h_red, h->d_red, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  *out_host = h->h_red[0];
+}
+
+void sumsq_diff(hpb_solver* h, const double* a, const double* b, double* out_host)
+{
+  const Geom& G = h->geo;
+  cudaMemsetAsync(h->d_red, 0, sizeof(double), h->stream);
+  k_sumsq_diff<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, a, b, h->d_red); LAUNCHED(h);
+  cudaMemcpyAsync(h->h_red, h->d_red, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  *out_host = h->h_red[0];
+}
+
+void flux(hpb_solver* h, const double* u, double* f, int dir)
+{
+  const Geom& G = h->geo;
+#define CALL(M_) k_flux<M_><<<(unsigned)((G.npg + 255) / 256), 256, 0, h->stream>>>(G, h->phys, u, dir, f)
+  MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+  LAUNCHED(h);
+}
+
+void modified_solution(hpb_solver* h, const double* u, double* uC)
+{
+  const Geom& G = h->geo;
+  const double* gf = (h->cfg.model == HPB_MODEL_LINEAR_ADR) ? nullptr : h->d_gravf;
+  const double* gg = (h->cfg.model == HPB_MODEL_LINEAR_ADR) ? nullptr : h->d_gravg;
+#define CALL(M_) k_modified<M_><<<(unsigned)((G.npg + 255) / 256), 256, 0, h->stream>>>(G, h->phys, u, gf, gg, uC)
+  MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+  LAUNCHED(h);
+}
+
+void weno_weights(hpb_solver* h, const double* fC, const double* u, int dir, double* w)
+{
+  const Geom& G = h->geo;
+  const int M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
+#define CALL(M_) k_weights<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, fC, u, dir, w)
+  MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+  LAUNCHED(h);
+}
+
+void weno_interp(hpb_solver* h, double* fI, const double* fC, const double* u, const double* w, int upw, int dir, int uflag)
+{
+  const Geom& G = h->geo;
+  const int M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
+#define CALL(M_) k_interp<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, fC, u, w, upw, dir, uflag, fI)
+  MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+  LAUNCHED(h);
+}
+
+void upwind(hpb_solver* h, double* fI, const double* fL, const double* fR, const double* uL, const double* uR,
+            const double* u, int dir)
+{
+  const Geom& G = h->geo;
+  const int M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
+  const double* gf = (h->cfg.model == HPB_MODEL_LINEAR_ADR) ? nullptr : h->d_gravf;
+  const double* gg = (h->cfg.model == HPB_MODEL_LINEAR_ADR) ? nullptr : h->d_gravg;
+#define CALL(M_) k_upwind<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, fL, fR, uL, uR, u, gf, gg, dir, fI)
+  MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+  LAUNCHED(h);
+}
+
+void first_derivative(hpb_solver* h, double* Df, const double* f, int dir, int nv)
+{
+  const Geom& G = h->geo;
+  int B[3] = { G.N[0], G.N[1], G.N[2] };
+  B[dir] = G.P[dir];
+  k_first_derivative<<<grid3(B[0], B[1], B[2]), TPB, 0, h->stream>>>(G, f, dir, nv, Df); LAUNCHED(h);
+}
+
+void second_derivative(hpb_solver* h, double* D2f, const double* f, int dir, int nv, int order)
+{
+  const Geom& G = h->geo;
+  k_second_derivative<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, f, dir, nv, order, D2f); LAUNCHED(h);
+}
+
+} // namespace hpbk

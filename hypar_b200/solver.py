@@ -1,0 +1,372 @@
+"""Host-side mirror of HyPar's solver object for the explicit-RHS path.
+
+``Solver`` wraps one ``hpb_solver`` (one rank / one GPU) of libhypar_b200.so. Its methods carry the
+names and argument meaning of the function pointers in the reference's ``struct HyPar``
+(include/hypar.h:211-359): ``ApplyBoundaryConditions``, ``HyperbolicFunction``, ``ParabolicFunction``,
+``SourceFunction``, ``FFunction``, ``UFunction``, ``SetInterpLimiterVar``,
+``InterpolateInterfacesHyp``, ``Upwind``, ``FirstDerivativePar``, ``SecondDerivativePar``,
+``ComputeCFL``, and ``RHSFunction`` / ``TimeIntegrate`` of ``struct TimeIntegration``. Arrays are
+numpy float64 in HyPar's own layout (ghost-padded AoS, flattened). Every call goes through the C ABI
+into CUDA kernels; errors raise ``HyParB200Error`` (the C layer also keeps a sticky error state).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib, hypario
+
+MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3}
+BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2}
+UPWINDS = {"roe": 1, "rusanov": 2}
+RK_TYPES = {"44": 0, "ssprk3": 1}
+FIELD_U, FIELD_QDERIVX, FIELD_QDERIVY = 0, 1, 2
+
+
+class HyParB200Error(RuntimeError):
+    pass
+
+
+def _dp(a: np.ndarray):
+    if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+        raise HyParB200Error("arrays must be C-contiguous float64")
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], physics: Dict[str, object],
+                       weno: Optional[Dict[str, object]], x: Sequence[np.ndarray], rank: int = 0,
+                       device: int = -1, use_fused: bool = True):
+    """Translate the contents of solver.inp / boundary.inp / physics.inp / weno.inp (as parsed
+    dictionaries) into an ``hpb_config``. Unsupported choices raise here or in ``hpb_create``."""
+    L = _lib.load()
+    c = _lib.Config()
+    L.hpb_config_defaults(C.byref(c))
+    nd = int(solver["ndims"])
+    c.ndims, c.nvars, c.ghosts = nd, int(solver["nvars"]), int(solver.get("ghost", 1))
+    size = solver["size"]
+    iproc = solver.get("iproc", [1] * nd)
+    for d in range(nd):
+        c.dim_global[d] = int(size[d])
+        c.iproc[d] = int(iproc[d])
+    c.rank = rank
+    model = str(solver.get("model", "none"))
+    if model not in MODELS:
+        raise HyParB200Error(f"model '{model}' is not on the B200 path (supported: {sorted(MODELS)})")
+    c.model = MODELS[model]
+    if str(solver.get("hyp_space_scheme", "1")) != "weno5":
+        raise HyParB200Error(f"hyp_space_scheme '{solver.get('hyp_space_scheme')}' is not on the B200 path (weno5 only)")
+    if str(solver.get("time_scheme", "euler")) != "rk":
+        raise HyParB200Error(f"time_scheme '{solver.get('time_scheme')}' is not on the B200 path (rk only)")
+    tst = str(solver.get("time_scheme_type", " "))
+    if tst not in RK_TYPES:
+        raise HyParB200Error(f"time_scheme_type '{tst}' is not on the B200 path (44, ssprk3)")
+    c.rk_type = RK_TYPES[tst]
+    if str(solver.get("hyp_flux_split", "no")) != "no":
+        raise HyParB200Error("hyp_flux_split yes is not on the B200 path")
+    it = str(solver.get("hyp_interp_type", "characteristic"))
+    if it not in ("characteristic", "components"):
+        raise HyParB200Error(f"{it} is not a supported interpolation type")
+    c.interp_char = int(it == "characteristic")
+    c.par_scheme = int(solver.get("par_space_scheme", "2"))
+    c.dt = float(solver.get("dt", 0.0))
+    w = weno or {}
+    c.weno_type = 3 if int(w.get("yc", 0)) else 2 if int(w.get("borges", 0)) else 1 if int(w.get("mapped", 0)) else 0
+    c.no_limiting = int(w.get("no_limiting", 0))
+    c.weno_eps = float(w.get("epsilon", 1e-6))
+    ph = physics or {}
+    if c.model == 0:
+        c.upwind = 0
+        if str(ph.get("centered_flux", "no")) != "no":
+            raise HyParB200Error("LinearADR centered_flux is not on the B200 path")
+        if "advection_filename" in ph:
+            raise HyParB200Error("LinearADR spatially-varying advection is not on the B200 path")
+        if c.nvars != 1:
+            raise HyParB200Error("LinearADR: nvars must be 1 on the B200 path")
+    else:
+        up = str(ph.get("upwinding", "roe"))
+        if up not in UPWINDS:
+            raise HyParB200Error(f"upwinding '{up}' is not on the B200 path (roe, rusanov)")
+        c.upwind = UPWINDS[up]
+    c.gamma = float(ph.get("gamma", 1.4))
+    c.Re, c.Pr, c.Minf = float(ph.get("Re", -1.0)), float(ph.get("Pr", 0.72)), float(ph.get("Minf", 1.0))
+    if c.model in (2, 3) and c.Re > 0 and str(solver.get("par_space_type")) != "nonconservative-2stage":
+        raise HyParB200Error('Parabolic term spatial discretization must be "nonconservative-2stage"')
+    grav = ph.get("gravity", [0.0] * 3)
+    grav = list(grav) if isinstance(grav, (list, tuple)) else [grav]
+    if c.model == 2:
+        if any(float(v) != 0.0 for v in grav):
+            raise HyParB200Error("navierstokes2d with gravity is not on the B200 path")
+    elif c.model == 1:
+        if float(ph.get("gravity", 0.0) if not isinstance(ph.get("gravity", 0.0), (list, tuple)) else 0.0) != 0.0:
+            raise HyParB200Error("euler1d with gravity is not on the B200 path")
+        grav = [0.0] * 3
+    for d in range(min(3, len(grav))):
+        c.gravity[d] = float(grav[d])
+    c.rho_ref, c.p_ref, c.R = float(ph.get("rho_ref", 1.0)), float(ph.get("p_ref", 1.0)), float(ph.get("R", 1.0))
+    c.HB, c.N_bv = int(ph.get("HB", 1)), float(ph.get("N_bv", 0.0))
+    adv = ph.get("advection", [])
+    adv = list(adv) if isinstance(adv, (list, tuple)) else [adv]
+    for i, a in enumerate(adv):
+        c.advection[i] = float(a)
+    dif = ph.get("diffusion", [])
+    dif = list(dif) if isinstance(dif, (list, tuple)) else [dif]
+    for i, a in enumerate(dif):
+        c.diffusion[i] = float(a)
+    if len(boundary) > _lib.MAX_ZONES:
+        raise HyParB200Error("too many boundary zones")
+    c.nzones = len(boundary)
+    for n, z in enumerate(boundary):
+        if z["type"] not in BCTYPES:
+            raise HyParB200Error(f"boundary type '{z['type']}' is not on the B200 path (periodic, extrapolate, slip-wall)")
+        cz = c.zones[n]
+        cz.type, cz.dim, cz.face = BCTYPES[z["type"]], int(z["dim"]), int(z["face"])
+        for d in range(nd):
+            cz.xmin[d], cz.xmax[d] = float(z["xmin"][d]), float(z["xmax"][d])
+            cz.wall_velocity[d] = float(z.get("wall_velocity", [0.0] * nd)[d])
+    xg = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in x]))
+    c.x_global = _dp(xg)
+    c.device = device
+    c.use_fused = int(use_fused)
+    return c, xg
+
+
+class Solver:
+    """One rank of the B200 explicit-RHS path."""
+
+    def __init__(self, solver: Dict[str, object], boundary, physics, weno, x, rank: int = 0,
+                 device: int = -1, use_fused: bool = True):
+        self.L = _lib.load()
+        self.inputs = {"solver": solver, "boundary": boundary, "physics": physics, "weno": weno}
+        cfg, self._xg = config_from_inputs(solver, boundary, physics, weno, x, rank, device, use_fused)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.L.hpb_create(C.byref(cfg), C.byref(self.h))
+        if rc:
+            raise HyParB200Error(self.L.hpb_last_error().decode())
+        self.ndims, self.nvars, self.ghosts = cfg.ndims, cfg.nvars, cfg.ghosts
+        dl, isg = (C.c_int * 3)(), (C.c_int * 3)()
+        self.L.hpb_get_local_dims(self.h, dl, isg)
+        self.dim_local = [dl[d] for d in range(self.ndims)]
+        self.is_global = [isg[d] for d in range(self.ndims)]
+        self.dim_global = [cfg.dim_global[d] for d in range(self.ndims)]
+        self.iproc = [cfg.iproc[d] for d in range(self.ndims)]
+        self.rank = rank
+        self.npoints_local_wghosts = int(self.L.hpb_npoints_local_wghosts(self.h))
+        self.dt = cfg.dt
+        nb = (C.c_int * 6)()
+        self.L.hpb_get_neighbors(self.h, nb)
+        self.neighbors = [nb[k] for k in range(2 * self.ndims)]
+
+    # -- construction helpers
+    @classmethod
+    def from_case(cls, case, rank: int = 0, device: int = -1, use_fused: bool = True) -> "Solver":
+        return cls(case.solver, case.boundary, case.physics, case.weno, case.x, rank, device, use_fused)
+
+    @classmethod
+    def from_directory(cls, path: str, rank: int = 0, device: int = -1, use_fused: bool = True) -> "Solver":
+        """Attach to an existing HyPar run directory (solver.inp, boundary.inp, physics.inp,
+        [weno.inp], initial.inp), unchanged."""
+        s = hypario.read_solver_inp(os.path.join(path, "solver.inp"))
+        nd, nv = int(s["ndims"]), int(s["nvars"])
+        b = hypario.read_boundary_inp(os.path.join(path, "boundary.inp"), nd, nv)
+        vk = {"gravity": 3 if s["model"] == "navierstokes3d" else 2 if s["model"] == "navierstokes2d" else 1,
+              "advection": nd * nv, "diffusion": nd * nv}
+        pf = os.path.join(path, "physics.inp")
+        ph = hypario.read_keyword_file(pf, vector_keys=vk) if os.path.exists(pf) else {}
+        for k in ("advection", "diffusion", "gravity"):
+            if k in ph:
+                ph[k] = [float(v) for v in ph[k]]
+        wf = os.path.join(path, "weno.inp")
+        w = hypario.read_keyword_file(wf) if os.path.exists(wf) else None
+        if str(s.get("ip_file_type", "ascii")) not in ("binary", "bin"):
+            raise HyParB200Error("only binary initial.inp is read by the B200 host layer")
+        x, u0 = hypario.read_initial_bin(os.path.join(path, "initial.inp"), s["size"], nv)
+        obj = cls(s, b, ph, w, x, rank, device, use_fused)
+        obj.u0_global = u0
+        return obj
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.hpb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise HyParB200Error(self.L.hpb_last_error().decode())
+
+    # -- sizes / set-up products
+    def zeros(self) -> np.ndarray:
+        return np.zeros(self.npoints_local_wghosts * self.nvars)
+
+    def ninterfaces(self, d: int) -> int:
+        return int(self.L.hpb_ninterfaces(self.h, d))
+
+    def shape_g(self):
+        g = self.ghosts
+        return tuple(n + 2 * g for n in reversed(self.dim_local)) + (self.nvars,)
+
+    def interior(self, a: np.ndarray) -> np.ndarray:
+        g = self.ghosts
+        sl = tuple(slice(g, g + n) for n in reversed(self.dim_local))
+        return a.reshape(self.shape_g())[sl]
+
+    def grid(self):
+        n = sum(d + 2 * self.ghosts for d in self.dim_local)
+        x, dxinv = np.zeros(n), np.zeros(n)
+        self.L.hpb_get_grid(self.h, _dp(x), _dp(dxinv))
+        return x, dxinv
+
+    def zone_extent(self, n: int):
+        a, b, on = (C.c_int * 3)(), (C.c_int * 3)(), C.c_int()
+        self._ck(self.L.hpb_get_zone_extent(self.h, n, a, b, C.byref(on)))
+        return [a[d] for d in range(self.ndims)], [b[d] for d in range(self.ndims)], on.value
+
+    def gravity_field(self):
+        f, g = np.zeros(self.npoints_local_wghosts), np.zeros(self.npoints_local_wghosts)
+        self.L.hpb_get_gravity_field(self.h, _dp(f), _dp(g))
+        return f, g
+
+    def local_from_global(self, ug: np.ndarray) -> np.ndarray:
+        """This rank's ghost-padded AoS block (ghosts zero) out of a global (N_{nd-1},...,N_0,nvars) array."""
+        g = self.ghosts
+        u = np.zeros(self.shape_g())
+        src = tuple(slice(self.is_global[d], self.is_global[d] + self.dim_local[d]) for d in reversed(range(self.ndims)))
+        dst = tuple(slice(g, g + n) for n in reversed(self.dim_local))
+        u[dst] = ug[src]
+        return np.ascontiguousarray(u).reshape(-1)
+
+    # -- the reference's function-pointer surface (host arrays)
+    def ApplyBoundaryConditions(self, u: np.ndarray, t: float = 0.0) -> np.ndarray:
+        self._ck(self.L.hpb_ApplyBoundaryConditions(self.h, _dp(u), t))
+        return u
+
+    def HyperbolicFunction(self, u: np.ndarray, t: float = 0.0, LimFlag: int = 1) -> np.ndarray:
+        hyp = self.zeros()
+        self._ck(self.L.hpb_HyperbolicFunction(self.h, _dp(hyp), _dp(u), t, LimFlag))
+        return hyp
+
+    def ParabolicFunction(self, u: np.ndarray, t: float = 0.0) -> np.ndarray:
+        par = self.zeros()
+        self._ck(self.L.hpb_ParabolicFunction(self.h, _dp(par), _dp(u), t))
+        return par
+
+    def SourceFunction(self, u: np.ndarray, t: float = 0.0) -> np.ndarray:
+        src = self.zeros()
+        self._ck(self.L.hpb_SourceFunction(self.h, _dp(src), _dp(u), t))
+        return src
+
+    def RHSFunction(self, u: np.ndarray, t: float = 0.0) -> np.ndarray:
+        rhs = self.zeros()
+        self._ck(self.L.hpb_RHSFunction(self.h, _dp(rhs), _dp(u), t))
+        return rhs
+
+    def FFunction(self, u: np.ndarray, d: int, t: float = 0.0) -> np.ndarray:
+        f = self.zeros()
+        self._ck(self.L.hpb_FFunction(self.h, _dp(f), _dp(u), d, t))
+        return f
+
+    def UFunction(self, u: np.ndarray, d: int = 0, t: float = 0.0) -> np.ndarray:
+        uC = self.zeros()
+        self._ck(self.L.hpb_UFunction(self.h, _dp(uC), _dp(u), d, t))
+        return uC
+
+    def SetInterpLimiterVar(self, fC: np.ndarray, u: np.ndarray, d: int) -> None:
+        self._ck(self.L.hpb_SetInterpLimiterVar(self.h, _dp(fC), _dp(u), d))
+
+    def GetInterpWeights(self, d: int) -> np.ndarray:
+        w = np.zeros(12 * self.ninterfaces(d) * self.nvars)
+        self._ck(self.L.hpb_GetInterpWeights(self.h, d, _dp(w)))
+        return w
+
+    def InterpolateInterfacesHyp(self, fC: np.ndarray, u: np.ndarray, upw: int, d: int, uflag: int) -> np.ndarray:
+        fI = np.zeros(self.ninterfaces(d) * self.nvars)
+        self._ck(self.L.hpb_InterpolateInterfacesHyp(self.h, _dp(fI), _dp(fC), _dp(u), upw, d, uflag))
+        return fI
+
+    def Upwind(self, fL, fR, uL, uR, u, d: int, t: float = 0.0) -> np.ndarray:
+        fI = np.zeros_like(fL)
+        self._ck(self.L.hpb_Upwind(self.h, _dp(fI), _dp(fL), _dp(fR), _dp(uL), _dp(uR), _dp(u), d, t))
+        return fI
+
+    def FirstDerivativePar(self, f: np.ndarray, d: int, bias: int = 1) -> np.ndarray:
+        Df = self.zeros()
+        self._ck(self.L.hpb_FirstDerivativePar(self.h, _dp(Df), _dp(f), d, bias))
+        return Df
+
+    def SecondDerivativePar(self, f: np.ndarray, d: int) -> np.ndarray:
+        D2 = self.zeros()
+        self._ck(self.L.hpb_SecondDerivativePar(self.h, _dp(D2), _dp(f), d))
+        return D2
+
+    def ComputeCFL(self, u: np.ndarray, dt: Optional[float] = None, t: float = 0.0) -> float:
+        out = C.c_double()
+        self._ck(self.L.hpb_ComputeCFL(self.h, _dp(u), self.dt if dt is None else dt, t, C.byref(out)))
+        return out.value
+
+    def TimeIntegrate(self, u: np.ndarray, nsteps: int = 1, t0: float = 0.0) -> np.ndarray:
+        self._ck(self.L.hpb_TimeIntegrate(self.h, _dp(u), nsteps, t0))
+        return u
+
+    # -- device-resident path
+    def set_solution(self, u: np.ndarray) -> None:
+        self._ck(self.L.hpb_dev_set_solution(self.h, _dp(u)))
+
+    def get_solution(self) -> np.ndarray:
+        u = self.zeros()
+        self._ck(self.L.hpb_dev_get_solution(self.h, _dp(u)))
+        return u
+
+    def TimeStep(self) -> None:
+        self._ck(self.L.hpb_TimeStep(self.h))
+
+    def TimeSteps(self, n: int) -> None:
+        self._ck(self.L.hpb_TimeSteps(self.h, n))
+
+    def dev_RHS(self, t: float = 0.0, want: bool = True) -> Optional[np.ndarray]:
+        rhs = self.zeros() if want else None
+        self._ck(self.L.hpb_dev_RHS(self.h, t, _dp(rhs) if want else None))
+        return rhs
+
+    def dev_ComputeCFL(self) -> float:
+        out = C.c_double()
+        self._ck(self.L.hpb_dev_ComputeCFL(self.h, C.byref(out)))
+        return out.value
+
+    def dev_StepNormSumSq(self) -> float:
+        out = C.c_double()
+        self._ck(self.L.hpb_dev_StepNormSumSq(self.h, C.byref(out)))
+        return out.value
+
+    def synchronize(self) -> None:
+        self._ck(self.L.hpb_synchronize(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.hpb_stream(self.h) or 0)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.L.hpb_kernel_launch_count(self.h))
+
+    @property
+    def nstages(self) -> int:
+        return int(self.L.hpb_nstages(self.h))
+
+    @property
+    def time(self) -> float:
+        return float(self.L.hpb_current_time(self.h))
+
+    def halo_buffers(self, field: int):
+        n = 2 * self.ndims
+        send, recv, nbytes = (C.c_void_p * 6)(), (C.c_void_p * 6)(), (C.c_size_t * 6)()
+        self._ck(self.L.hpb_halo_buffers(self.h, field, send, recv, nbytes))
+        return [send[k] for k in range(n)], [recv[k] for k in range(n)], [nbytes[k] for k in range(n)]

@@ -1,0 +1,226 @@
+/* hypar_b200.h -- C ABI of the B200-native explicit-RHS path for HyPar.
+ *
+ * Drop-in boundary: HyPar has no plugin loader; its "operator API" is the set of function
+ * pointers in `struct HyPar` (reference include/hypar.h:211-359) and
+ * `TimeIntegration::RHSFunction / TimeIntegrate` (include/timeintegration_struct.h), assigned in
+ * src/Simulation/InitializeSolvers.c:71-393 and <Model>Initialize. Every entry point below
+ * replaces one of those pointers (cited per function); `void *s, void *m` (HyPar*, MPIVariables*)
+ * of the reference collapse into the opaque `hpb_solver*` created from the same inputs HyPar
+ * reads (solver.inp / boundary.inp / physics.inp / weno.inp / the grid). INTEGRATION.md shows the
+ * ~100-line C glue (`hyparb200_attach`) a HyPar maintainer adds to install them.
+ *
+ * Conventions
+ *   - plain C, `extern "C"`, pointers + sizes only; return 0 = ok, non-zero = error
+ *     (message via hpb_last_error()); like the reference, callers may drop the return value, so
+ *     every error is also made sticky: hpb_error_state() stays non-zero until cleared.
+ *   - "HOST" entry points take host arrays in HyPar's own layout (ghost-padded AoS, nvars
+ *     innermost, dim 0 fastest: include/arrayfunctions.h:40-47); the library moves them to the
+ *     GPU, runs the CUDA kernels and copies results back. There is NO CPU fallback: without a
+ *     CUDA device every compute call fails with HPB_ERR_NO_DEVICE.
+ *   - "DEVICE-RESIDENT" entry points (hpb_dev_*, hpb_Time*) keep the state on the GPU between
+ *     calls (device layout: ghost-padded SoA, component-major) -- this is the production path
+ *     the time loop uses.
+ *   - one hpb_solver per rank/GPU; calls on one solver are serialized by the caller
+ *     (same contract as HyPar: one thread per rank).
+ */
+#ifndef HYPAR_B200_H
+#define HYPAR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPB_MAX_NDIMS 3
+#define HPB_MAX_NVARS 5
+#define HPB_MAX_ZONES 16
+
+/* error codes */
+#define HPB_OK             0
+#define HPB_ERR_INVALID    1   /* bad / unsupported configuration (scheme, model, BC type ...) */
+#define HPB_ERR_NO_DEVICE  2   /* no CUDA device: the product has no CPU path                  */
+#define HPB_ERR_CUDA       3   /* a CUDA runtime call or kernel failed                         */
+#define HPB_ERR_ALLOC      4
+
+/* `model` (solver.inp) -- reference src/Simulation/InitializePhysics.c:84-157 */
+#define HPB_MODEL_LINEAR_ADR 0  /* "linear-advection-diffusion-reaction" */
+#define HPB_MODEL_EULER1D    1  /* "euler1d"        */
+#define HPB_MODEL_NS2D       2  /* "navierstokes2d" */
+#define HPB_MODEL_NS3D       3  /* "navierstokes3d" */
+
+/* weno.inp -- reference src/InterpolationFunctions/WENOFifthOrderCalculateWeights.c:40-61 */
+#define HPB_WENO_JS 0
+#define HPB_WENO_M  1   /* mapped  */
+#define HPB_WENO_Z  2   /* borges  */
+#define HPB_WENO_YC 3   /* yc      */
+
+/* physics.inp `upwinding` */
+#define HPB_UPWIND_DEFAULT 0    /* LinearADRUpwind */
+#define HPB_UPWIND_ROE     1
+#define HPB_UPWIND_RUSANOV 2
+
+/* boundary.inp zone types implemented on the device (reference: 17 types; the three the
+   BASELINE configurations use) */
+#define HPB_BC_PERIODIC    0
+#define HPB_BC_EXTRAPOLATE 1
+#define HPB_BC_SLIP_WALL   2
+
+/* time_scheme_type for time_scheme "rk" -- reference TimeExplicitRKInitialize.c:58-79 */
+#define HPB_RK_44     0
+#define HPB_RK_SSPRK3 1
+
+/* fields that have a halo exchange (reference MPIExchangeBoundariesnD call sites) */
+#define HPB_FIELD_U       0   /* TimeRHSFunctionExplicit.c:60, TimePreStep.c:71         */
+#define HPB_FIELD_QDERIVX 1   /* NavierStokes3DParabolicFunction.c:125                  */
+#define HPB_FIELD_QDERIVY 2   /* NavierStokes3DParabolicFunction.c:127 (and :129, sic)  */
+
+typedef struct hpb_boundary_zone {
+  int    type;                         /* HPB_BC_*                                       */
+  int    dim, face;                    /* face = +1 (low side) / -1 (high side)          */
+  double xmin[HPB_MAX_NDIMS], xmax[HPB_MAX_NDIMS];
+  double wall_velocity[HPB_MAX_NDIMS]; /* slip-wall only                                 */
+} hpb_boundary_zone;
+
+typedef struct hpb_config {
+  /* --- solver.inp --- */
+  int    ndims, nvars, ghosts;
+  int    dim_global[HPB_MAX_NDIMS];
+  int    iproc[HPB_MAX_NDIMS];         /* ranks per dimension                            */
+  int    rank;                         /* this rank: ip0 + iproc0*(ip1 + iproc1*ip2)     */
+  int    model;                        /* HPB_MODEL_*                                    */
+  int    interp_char;                  /* hyp_interp_type: 1 characteristic, 0 components*/
+  int    par_scheme;                   /* par_space_scheme: 2 or 4                       */
+  int    rk_type;                      /* HPB_RK_*                                       */
+  double dt;
+  /* --- weno.inp --- */
+  int    weno_type;                    /* HPB_WENO_*                                     */
+  int    no_limiting;
+  double weno_eps;
+  /* --- physics.inp --- */
+  int    upwind;                       /* HPB_UPWIND_*                                   */
+  double gamma, Re, Pr, Minf;          /* Re as given in physics.inp (divided by Minf inside) */
+  double gravity[HPB_MAX_NDIMS], rho_ref, p_ref, R, N_bv;
+  int    HB;
+  double advection[HPB_MAX_NDIMS*HPB_MAX_NVARS];  /* LinearADR a[nvars*dir+v]              */
+  double diffusion[HPB_MAX_NDIMS*HPB_MAX_NVARS];  /* LinearADR nu[nvars*dir+v]             */
+  /* --- boundary.inp --- */
+  int    nzones;
+  hpb_boundary_zone zones[HPB_MAX_ZONES];
+  /* --- grid: GLOBAL coordinates, concatenated per dimension (as in initial.inp) --- */
+  const double* x_global;
+  /* --- device --- */
+  int    device;                       /* CUDA device ordinal; -1 = current              */
+  int    use_fused;                    /* 1 (default): fused sweep kernels where available;
+                                          0: generic per-interface kernels only          */
+} hpb_config;
+
+typedef struct hpb_solver hpb_solver;
+
+/* ------------------------------------------------------------------ life cycle / errors */
+void        hpb_config_defaults(hpb_config* cfg);   /* the defaults of ReadInputs.c:112-146 etc. */
+int         hpb_create(const hpb_config* cfg, hpb_solver** out);
+int         hpb_destroy(hpb_solver* h);
+const char* hpb_last_error(void);
+int         hpb_error_state(void);
+void        hpb_clear_error(void);
+int         hpb_device_count(void);                 /* 0 when no CUDA device is visible  */
+const char* hpb_version(void);
+
+/* ------------------------------------------------------------------ host set-up queries
+ * (pure host code, usable without a GPU: partitioning as MPIPartition1D.c / MPIRanknD.c, ghost
+ * coordinates as ReadArray.c:60-100, dxinv as InitialSolution.c:74-119, zone extents as
+ * InitializeBoundaries.c:380-440, gravity field as NavierStokes3DGravityField.c:33-152) */
+int  hpb_partition1d(int nglobal, int nproc, int rank);
+int  hpb_rank1d(int ndims, const int* iproc, const int* ip);
+void hpb_ranknd(int ndims, int rank, const int* iproc, int* ip);
+int  hpb_get_local_dims(const hpb_solver* h, int* dim_local, int* is_global);
+long long hpb_npoints_local_wghosts(const hpb_solver* h);
+long long hpb_ninterfaces(const hpb_solver* h, int dir);
+int  hpb_get_grid(const hpb_solver* h, double* x_wghosts, double* dxinv_wghosts); /* size sum(dim+2g) */
+int  hpb_get_neighbors(const hpb_solver* h, int* neighbor_rank /* [2*ndims], -1 = none */);
+int  hpb_get_zone_extent(const hpb_solver* h, int zone, int* is, int* ie, int* on_this_proc);
+int  hpb_get_gravity_field(const hpb_solver* h, double* grav_f, double* grav_g);
+
+/* ------------------------------------------------------------------ HOST entry points
+ * (the reference's function-pointer surface; arrays = host, HyPar layout, local + ghosts) */
+
+/* solver->ApplyBoundaryConditions (hypar.h:214; ApplyBoundaryConditions.c) : fills face ghosts of u */
+int hpb_ApplyBoundaryConditions(hpb_solver* h, double* u, double t);
+/* solver->HyperbolicFunction (hypar.h:250-253; HyperbolicFunction.c:31) with the model's
+   FFunction/Upwind; LimFlag as in the reference */
+int hpb_HyperbolicFunction(hpb_solver* h, double* hyp, const double* u, double t, int LimFlag);
+/* solver->ParabolicFunction (hypar.h:256; NavierStokes3DParabolicFunction.c:50,
+   NavierStokes2DParabolicFunction.c:38, ParabolicFunctionNC1Stage.c) -- single rank */
+int hpb_ParabolicFunction(hpb_solver* h, double* par, const double* u, double t);
+/* solver->SourceFunction (hypar.h:259; SourceFunction.c + NavierStokes3DSource.c:38): uses the
+   flux weights of the LAST hpb_HyperbolicFunction call, like the reference */
+int hpb_SourceFunction(hpb_solver* h, double* source, const double* u, double t);
+/* TimeIntegration::RHSFunction = TimeRHSFunctionExplicit (TimeRHSFunctionExplicit.c:30).
+   u is modified (boundary conditions), as in the reference. Single rank. */
+int hpb_RHSFunction(hpb_solver* h, double* rhs, double* u, double t);
+/* fine-grained pointers: FFunction (hypar.h:276), UFunction (:321), SetInterpLimiterVar (:234),
+   InterpolateInterfacesHyp (:224), Upwind (:295), FirstDerivativePar (:243),
+   SecondDerivativePar (:247), ComputeCFL (:269) */
+int hpb_FFunction(hpb_solver* h, double* f, const double* u, int dir, double t);
+int hpb_UFunction(hpb_solver* h, double* uC, const double* u, int dir, double t);
+int hpb_SetInterpLimiterVar(hpb_solver* h, const double* fC, const double* u, int dir);
+int hpb_GetInterpWeights(hpb_solver* h, int dir, double* w /* [12*ninterfaces*nvars]: LF,LU,RF,RU x w1..w3 */);
+int hpb_InterpolateInterfacesHyp(hpb_solver* h, double* fI, const double* fC, const double* u,
+                                 int upw, int dir, int uflag);
+int hpb_Upwind(hpb_solver* h, double* fI, const double* fL, const double* fR, const double* uL,
+               const double* uR, const double* u, int dir, double t);
+int hpb_FirstDerivativePar(hpb_solver* h, double* Df, const double* f, int dir, int bias);
+int hpb_SecondDerivativePar(hpb_solver* h, double* D2f, const double* f, int dir);
+int hpb_ComputeCFL(hpb_solver* h, const double* u, double dt, double t, double* cfl);
+/* TimeIntegration::TimeIntegrate = TimeRK (TimeRK.c:35) preceded by TimePreStep's BC/halo
+   (TimePreStep.c:50-76): advances host u by nsteps steps of size cfg.dt. Single rank. */
+int hpb_TimeIntegrate(hpb_solver* h, double* u, int nsteps, double t0);
+
+/* ------------------------------------------------------------------ DEVICE-RESIDENT path */
+int hpb_dev_set_solution(hpb_solver* h, const double* u_host);     /* H2D + AoS->SoA */
+int hpb_dev_get_solution(hpb_solver* h, double* u_host);           /* SoA->AoS + D2H */
+int hpb_dev_fill_solution_from_global(hpb_solver* h, const double* u_global); /* global AoS, no ghosts */
+/* one full time step on the device (TimePreStep BC/halo + TimeRK + time update). Single rank. */
+int hpb_TimeStep(hpb_solver* h);
+int hpb_TimeSteps(hpb_solver* h, int nsteps);
+double hpb_current_time(const hpb_solver* h);
+/* reductions on the device solution: CFL (ComputeCFL) and the step norm of TimePostStep.c:44-63
+   (returns the LOCAL sum of squares of u - u_prev and the local max CFL; callers all-reduce) */
+int hpb_dev_ComputeCFL(hpb_solver* h, double* cfl_local_max);
+int hpb_dev_StepNormSumSq(hpb_solver* h, double* sumsq_local);
+/* evaluate rhs(u_dev) once into an internal buffer and copy it to the host (HyPar layout) */
+int hpb_dev_RHS(hpb_solver* h, double t, double* rhs_host /* may be NULL */);
+
+/* ---- multi-GPU: one solver per rank; the host (torch.distributed / NCCL) moves the buffers.
+ * A time step is driven stage by stage so that the exchange overlaps the interior sweeps:
+ *   hpb_stage_begin(s)            U_s = u + dt*sum a_si*Udot_i ; BCs ; pack u halos
+ *   [exchange FIELD_U]            (on a comm stream; hpb_stage_interior may run meanwhile)
+ *   hpb_stage_halo_done(FIELD_U)  unpack
+ *   hpb_stage_rhs_a(s)            hyperbolic sweeps (+source), viscous phase 1, pack QDerivX/Y
+ *   [exchange FIELD_QDERIVX, FIELD_QDERIVY]
+ *   hpb_stage_halo_done(...)      unpack
+ *   hpb_stage_rhs_b(s)            viscous phase 2 ; Udot_s complete
+ *   hpb_step_finish()             u += dt*sum b_s*Udot_s ; t += dt
+ */
+int hpb_halo_buffers(hpb_solver* h, int field, void** send /*[2*ndims]*/, void** recv /*[2*ndims]*/,
+                     size_t* bytes /*[2*ndims]*/);     /* device pointers; face 2*d = low, 2*d+1 = high */
+int hpb_step_begin(hpb_solver* h);                    /* TimePreStep: BCs on u + pack (exchange FIELD_U follows) */
+int hpb_step_halo_done(hpb_solver* h);                /* unpack into u */
+int hpb_stage_begin(hpb_solver* h, int stage);
+int hpb_stage_halo_done(hpb_solver* h, int field);
+int hpb_stage_rhs_a(hpb_solver* h, int stage);
+int hpb_stage_rhs_b(hpb_solver* h, int stage);
+int hpb_step_finish(hpb_solver* h);
+int hpb_nstages(const hpb_solver* h);
+int hpb_needs_viscous_exchange(const hpb_solver* h);
+void* hpb_stream(hpb_solver* h);                      /* cudaStream_t the kernels run on */
+int hpb_synchronize(hpb_solver* h);
+
+/* ------------------------------------------------------------------ instrumentation */
+long long hpb_kernel_launch_count(const hpb_solver* h);   /* kernels launched by this solver so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPAR_B200_H */
