@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the explicit-RHS hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 512]
+
+A "step" is one RK4 time step (TimePreStep BCs + 4 x [stage vector, BCs, halo, hyperbolic sweeps,
+viscous terms] + step completion) of configuration C4 -- NavierStokes3D, WENO5 (mapped weights),
+Rusanov upwinding, viscous terms (Re 333.33, Pr 0.72, Minf 0.3), periodic box -- on a synthetic
+Taylor-Green + 16 solenoidal Fourier modes field, 512^3 points PER GPU (weak scaling: the global
+grid is 512x512x512 / 512x512x1024 / 512x1024x1024 / 1024^3 at 1 / 2 / 4 / 8 GPUs).
+
+Metric: Mpoint-RK-stage/s = global interior points x RK stages x steps / seconds.
+  value : device-resident time loop (hpb_TimeStep), inputs already in HBM, CUDA events, max over ranks
+  e2e   : the host-array entry point a HyPar caller binds (hpb_TimeIntegrate: H2D of u from pinned host
+          memory + the step + D2H of u), every step
+  roofline    : dominant kernel (one directional sweep), algorithmic bytes / CUDA-event time, vs the
+                measured HBM copy bandwidth in MEASURED_PEAKS.json (see DESIGN.md for the byte counts)
+  cpu_baseline: the reference's own CPU implementation (oracle/_ref, unmodified HyPar sources) on this
+                box's host cores, same physics, 64^3 sample
+--impl reference: only the reference CPU arm (bounded sample), same metric/unit/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+METRIC = "3D NS WENO5 Mpoint-RK-stage/s"
+UNIT = "Mpoint-RK-stage/s"
+NSTAGES = 4
+# algorithmic bytes per point (FP64, nvars = 5), DESIGN.md section "Roofline":
+#   one directional sweep launch: read u (40 B) + read-modify-write rhs (80 B; the first direction only writes: 40 B)
+#   whole RK stage (k never stored twice): 200 B  
+SWEEP_BYTES = {"sweep_x": 80.0, "sweep_y": 120.0, "sweep_z": 120.0}
+STAGE_BYTES = 200.0
+
+
+def weak_grid(n: int, ngpus: int):
+    """global size and iproc for `ngpus` blocks of n^3 (slowest dimensions split first)."""
+    iproc = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[ngpus]
+    return [n * iproc[0], n * iproc[1], n * iproc[2]], list(iproc)
+
+
+def c4_inputs(size, iproc, dt=0.005):
+    """solver.inp / boundary.inp / physics.inp / weno.inp of configuration C4 (hypar_b200.cases)."""
+    from hypar_b200 import cases
+    import numpy as np
+    s = cases._solver(3, 5, size, "navierstokes3d", ts="rk", tstype="44", dt=dt, iproc=iproc,
+                      par_type="nonconservative-2stage", par_scheme="4")
+    b = cases._zones(3, "periodic", [-1e3] * 3, [1e3] * 3)
+    ph = {"gamma": 1.4, "upwinding": "rusanov", "Pr": 0.72, "Minf": 0.3, "Re": 333.333333333333333}
+    w = cases.weno_inp("mapped")
+    x = [np.arange(size[d], dtype=np.float64) * (2.0 * np.pi / size[d]) for d in range(3)]
+    return s, b, ph, w, x
+
+
+def synth_field_torch(x_loc, device, seed=20261017):
+    """The C4 synthetic field of hypar_b200.cases.ns3d_turbulence evaluated on this rank's block, on the
+    GPU (torch is plumbing here: it only creates the input). Returns (nz, ny, nx, 5) float64."""
+    import numpy as np
+    import torch
+    gamma, Minf = 1.4, 0.3
+    X = torch.as_tensor(x_loc[0], device=device)[None, None, :]
+    Y = torch.as_tensor(x_loc[1], device=device)[None, :, None]
+    Z = torch.as_tensor(x_loc[2], device=device)[:, None, None]
+    vx = Minf * torch.sin(X) * torch.cos(Y) * torch.cos(Z)
+    vy = -Minf * torch.cos(X) * torch.sin(Y) * torch.cos(Z)
+    vz = torch.zeros_like(vx)
+    rng = np.random.RandomState(seed)
+    for _ in range(16):
+        k = rng.randint(-4, 5, size=3).astype(np.float64)
+        if not k.any():
+            k[0] = 1.0
+        a = rng.standard_normal(3)
+        a -= k * (a @ k) / (k @ k)
+        nrm = np.linalg.norm(a)
+        if nrm < 1e-12:
+            continue
+        a *= 0.1 * Minf / (4.0 * nrm)
+        ph = rng.uniform(0.0, 2.0 * np.pi)
+        s = torch.sin(k[0] * X + k[1] * Y + k[2] * Z + ph)
+        vx += a[0] * s
+        vy += a[1] * s
+        vz += a[2] * s
+        del s
+    rho = torch.ones_like(vx)
+    e = (1.0 / gamma) / (gamma - 1.0) + 0.5 * rho * (vx * vx + vy * vy + vz * vz)
+    return torch.stack([rho, rho * vx, rho * vy, rho * vz, e], dim=-1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------ reference CPU arm
+def run_reference_cpu(n: int, nsteps: int, warmup: int, threads: int):
+    """Times the UNMODIFIED reference (oracle/_ref/hypar_ref: HyPar's own TimePreStep/TimeStep/TimePostStep
+    loop, its own per-step wctime) on a n^3 sample of the C4 configuration. Returns (Mpt-stage/s, seconds/step)."""
+    from hypar_b200 import cases
+    from refrun import run_reference, ref_available
+    if not ref_available("hypar_ref"):
+        raise RuntimeError("oracle/_ref/hypar_ref is missing (build it where /root/reference exists: make -C oracle ref)")
+    case = cases.ns3d_turbulence((n, n, n), "mapped")
+    out = run_reference(case, "steps", [warmup + nsteps], exe="hypar_ref", threads=threads, timeout=3000)
+    wct = [float(ln.split()[3]) for ln in out["stdout"].splitlines() if ln.startswith("STEP ")]
+    wct = wct[warmup:]
+    sec = sum(wct) / len(wct)
+    return n ** 3 * NSTAGES / sec / 1e6, sec
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.ref_n
+    t0 = time.time()
+    val, sec = run_reference_cpu(n, args.steps, max(args.warmup, 1), threads)
+    size, iproc = weak_grid(args.n, args.gpus)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C4 NavierStokes3D WENO5(mapped)+Rusanov+viscous RK4, {size[0]}x{size[1]}x{size[2]} periodic",
+                   "sample": f"{n}^3 grid, same physics and scheme, one RK4 step per bench step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": f"{n}^3, {args.steps} RK4 steps after {max(args.warmup, 1)} warm-up, OMP_NUM_THREADS={threads}, "
+                                   "HyPar's own per-step wctime"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def gpu_arm(args):
+    import numpy as np
+    import torch
+    from hypar_b200.solver import Solver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    size, iproc = weak_grid(args.n, world)
+    s, b, ph, w, x = c4_inputs(size, iproc)
+    if world == 1:
+        sv = Solver(s, b, ph, w, x, rank=0, device=local_rank)
+        stepper = None
+    else:
+        from hypar_b200.multigpu import DistributedSolver
+        stepper = DistributedSolver(s, b, ph, w, x, rank=rank, device=local_rank)
+        sv = stepper.solver
+    g = sv.ghosts
+    nloc = sv.dim_local
+    x_loc = [x[d][sv.is_global[d]:sv.is_global[d] + nloc[d]] for d in range(3)]
+
+    # synthetic input, created on the device, staged into a pinned host array in HyPar's own layout
+    u_host_t = torch.zeros(sv.npoints_local_wghosts * 5, dtype=torch.float64).pin_memory()
+    u_host = u_host_t.numpy()
+    fld = synth_field_torch(x_loc, dev)
+    u_host_t.view(nloc[2] + 2 * g, nloc[1] + 2 * g, nloc[0] + 2 * g, 5)[g:-g, g:-g, g:-g, :].copy_(fld)
+    del fld
+    torch.cuda.empty_cache()
+    sv.set_solution(u_host)
+
+    stream = torch.cuda.ExternalStream(sv.stream, device=dev)
+    npts_global = float(size[0]) * size[1] * size[2]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        if stepper is None:
+            sv.TimeStep()
+        else:
+            stepper.time_step()
+
+    def timed(fn, nsteps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(nsteps):
+            fn()
+        e1.record(stream)
+        sv.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident loop
+    for _ in range(args.warmup):
+        one_step()
+    sv.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sv.profile_enable(True)
+    l0 = sv.kernel_launches
+    ms = timed(one_step, args.steps)
+    launches = sv.kernel_launches - l0
+    prof = sv.profile_query()
+    sv.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    value = npts_global * NSTAGES * args.steps / (ms * 1e-3) / 1e6
+
+    # sanity: the field must still be finite after the timed steps
+    cfl = sv.dev_ComputeCFL()
+    if not np.isfinite(cfl) or cfl <= 0 or cfl > 10:
+        raise RuntimeError(f"solution blew up during the bench (CFL = {cfl})")
+
+    # ---- end to end through the host-array entry point (single GPU: hpb_TimeIntegrate; multi GPU: the
+    # distributed stepper's host-array step): H2D of u + step + D2H of u inside the timed region
+    nbytes = u_host.nbytes
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        if stepper is None:
+            sv.TimeIntegrate(u_host, 1, sv.time)
+        else:
+            stepper.time_integrate_host(u_host, 1)
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, e2e_steps)
+    e2e_val = npts_global * NSTAGES * e2e_steps / (ms_e2e * 1e-3) / 1e6
+    if not np.isfinite(u_host).all():
+        raise RuntimeError("non-finite values in the host solution after the end-to-end steps")
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per-launch CUDA-event time, this rank)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    npts_local = float(nloc[0]) * nloc[1] * nloc[2]
+    sweeps = {k: v for k, v in prof.items() if k.startswith("sweep") and v[1] > 0}
+    dom = max(sweeps, key=lambda k: sweeps[k][0] / sweeps[k][1])
+    dom_ms = sweeps[dom][0] / sweeps[dom][1]
+    achieved = SWEEP_BYTES[dom] * npts_local / (dom_ms * 1e-3) / 1e9
+    total_prof = sum(v[0] for v in prof.values())
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": peak_src, "ms_per_launch": dom_ms,
+        "bytes_per_point": SWEEP_BYTES[dom],
+        "share_of_step": {k: (v[0] / total_prof if total_prof > 0 else None) for k, v in prof.items() if v[1] > 0},
+        "whole_stage": {"bytes_per_point_stage": STAGE_BYTES,
+                        "achieved": STAGE_BYTES * npts_local * NSTAGES * args.steps / (ms * 1e-3) / 1e9,
+                        "frac": STAGE_BYTES * npts_local * NSTAGES * args.steps / (ms * 1e-3) / 1e9 / peak},
+        "note": "FP64-issue-bound kernel (DESIGN.md): the HBM fraction is reported as the metric demands; "
+                "see profiles/ for the FP64 pipe utilisation",
+    }
+
+    # ---- CPU baseline: the reference itself on a bounded sample
+    cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable"}
+    if not args.no_cpu:
+        try:
+            threads = os.cpu_count() or 1
+            v, sec = run_reference_cpu(args.cpu_n, 2, 1, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
+                   "sample": f"{args.cpu_n}^3 grid, same physics/scheme, 2 RK4 steps after 1 warm-up, "
+                             f"{sec:.2f} s/step, OMP_NUM_THREADS={threads} (unmodified HyPar sources, oracle/_ref)"}
+        except Exception as ex:  # the baseline is a report, not a dependency of the GPU number
+            cpu["sample"] = f"failed: {ex}"
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C4 NavierStokes3D WENO5(mapped)+Rusanov+viscous RK4, {size[0]}x{size[1]}x{size[2]} periodic",
+                   "points_per_gpu": f"{nloc[0]}x{nloc[1]}x{nloc[2]}", "iproc": iproc, "rk_stages_per_step": NSTAGES,
+                   "l2": "working set (5.6 GB per array) >> L2, no flush needed"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                "api": "hpb_TimeIntegrate(host u, 1 step)" if stepper is None else "DistributedSolver.time_integrate_host"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "cfl": cfl,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="points per dimension per GPU")
+    ap.add_argument("--cpu-n", type=int, default=64, help="grid of the cpu_baseline sample")
+    ap.add_argument("--ref-n", type=int, default=64, help="grid of the --impl reference sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,7 +3,7 @@
 Each builder returns a ``Case``: the same information a HyPar run directory holds
 (solver.inp / boundary.inp / physics.inp / weno.inp / initial.inp), as Python data.
 ``Case.write(dir)`` materialises the directory in the reference's own formats, so the
-reference executable (oracle/_ref) and this library consume identical inputs.
+reference executable and this library consume identical inputs.
 
 Initial conditions follow the reference's example generators:
   C1  Examples/1D/LinearAdvection/SineWave/aux/init.c

@@ -135,6 +135,7 @@ static int alloc_main(hpb_solver* h)
   return HPB_OK;
 }
 
+static void prof_release(hpb_solver* h);
 // ------------------------------------------------------------------------------------ life cycle
 extern "C" int hpb_create(const hpb_config* cfg, hpb_solver** out)
 {
@@ -203,6 +204,8 @@ extern "C" int hpb_destroy(hpb_solver* h)
     if (h->d_recv[f][k]) cudaFree(h->d_recv[f][k]);
   }
   if (h->h_red) cudaFreeHost(h->h_red);
+  prof_release(h);
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return HPB_OK;
@@ -246,6 +249,51 @@ extern "C" int hpb_synchronize(hpb_solver* h) { TRY(need_device(h)); return sync
 extern "C" double hpb_current_time(const hpb_solver* h) { return h->t; }
 extern "C" int hpb_nstages(const hpb_solver* h) { return h->rk.ns; }
 extern "C" int hpb_needs_viscous_exchange(const hpb_solver* h) { return viscous_on(h) ? 1 : 0; }
+
+// ------------------------------------------------------------------------------------ device timing
+ProfScope::ProfScope(hpb_solver* h_, int cat) : h(h_), idx(-1)
+{
+  if (!h->prof_on || h->prof.size() >= 16384) return;
+  hpb_solver::ProfRec r; r.cat = cat;
+  cudaEvent_t* e[2] = { &r.a, &r.b };
+  for (int k = 0; k < 2; k++) {
+    if (!h->prof_pool.empty()) { *e[k] = h->prof_pool.back(); h->prof_pool.pop_back(); }
+    else if (cudaEventCreate(e[k]) != cudaSuccess) { cudaGetLastError(); return; }
+  }
+  cudaEventRecord(r.a, h->stream);
+  idx = (int)h->prof.size();
+  h->prof.push_back(r);
+}
+ProfScope::~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof[idx].b, h->stream); }
+
+static void prof_release(hpb_solver* h)
+{
+  for (auto& r : h->prof) { h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b); }
+  h->prof.clear();
+}
+
+extern "C" int hpb_profile_enable(hpb_solver* h, int on)
+{
+  TRY(need_device(h));
+  TRY(sync_check(h, "profile_enable"));
+  prof_release(h);
+  h->prof_on = (on != 0);
+  return HPB_OK;
+}
+
+extern "C" int hpb_profile_query(hpb_solver* h, int category, double* total_ms, long long* count)
+{
+  TRY(need_device(h));
+  TRY(sync_check(h, "profile_query"));
+  double t = 0.0; long long n = 0;
+  for (auto& r : h->prof) if (r.cat == category) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { t += ms; n++; } else cudaGetLastError();
+  }
+  if (total_ms) *total_ms = t;
+  if (count) *count = n;
+  return HPB_OK;
+}
 
 // ------------------------------------------------------------------------------------ RHS assembly (device)
 // rhs = -hyp + par + source of TimeRHSFunctionExplicit.c:70-92, split at the viscous halo exchange.

@@ -75,6 +75,18 @@ struct hpb_solver {
   double *d_send[3][6] = {}, *d_recv[3][6] = {};
   size_t face_bytes[6] = {};
   bool w_valid = false;
+  // optional per-category device timing (hpb_profile_*): CUDA event pairs on h->stream
+  bool prof_on = false;
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> prof_pool;
+};
+
+// RAII scope: when profiling is on, brackets the kernels launched inside it with an event pair
+struct ProfScope {
+  hpb_solver* h; int idx;
+  ProfScope(hpb_solver* h_, int cat);
+  ~ProfScope();
 };
 
 // error plumbing (capi.cu)

@@ -783,6 +783,7 @@ void soa_to_aos(hpb_solver* h, const double* soa, double* aos, long long npts, i
 
 void apply_bc(hpb_solver* h, double* u)
 {
+  ProfScope ps(h, HPB_PROF_BC);
   const Geom& G = h->geo;
   for (const ZoneDev& z : h->zones) {
     if (!z.on) continue;
@@ -803,6 +804,7 @@ static void face_launch(hpb_solver* h, double* a, int nv, int d, int off_d, doub
 
 void pack(hpb_solver* h, const double* a, int nv, int field)
 {
+  ProfScope ps(h, HPB_PROF_HALO);
   const Geom& G = h->geo;
   for (int d = 0; d < G.ndims; d++) {
     if (h->neighbor[2*d] >= 0)   face_launch(h, (double*)a, nv, d, 0, h->d_send[field][2*d], 1);
@@ -811,6 +813,7 @@ void pack(hpb_solver* h, const double* a, int nv, int field)
 }
 void unpack(hpb_solver* h, double* a, int nv, int field)
 {
+  ProfScope ps(h, HPB_PROF_HALO);
   const Geom& G = h->geo;
   for (int d = 0; d < G.ndims; d++) {
     if (h->neighbor[2*d] >= 0)   face_launch(h, a, nv, d, -G.g, h->d_recv[field][2*d], 0);
@@ -834,6 +837,7 @@ void hyperbolic_generic(hpb_solver* h, const double* u, double* out, bool negate
   for (int d = 0; d < G.ndims; d++) {
     const int M[3] = { G.N[0] + (d == 0), G.N[1] + (d == 1), G.N[2] + (d == 2) };
     double* sI = (with_source && grav && h->phys.grav[d] != 0.0) ? h->d_sI : nullptr;
+    ProfScope ps(h, HPB_PROF_SWEEP_X + d);
 #define CALL(M_) k_iface<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, u, gf, gg, d, h->d_fI, sI)
     MODEL_SWITCH(h->cfg.model, CALL)
 #undef CALL
@@ -849,6 +853,7 @@ void hyperbolic_generic(hpb_solver* h, const double* u, double* out, bool negate
 
 void parabolic_phase1(hpb_solver* h, const double* u)
 {
+  ProfScope ps(h, HPB_PROF_VISCOUS);
   const Geom& G = h->geo;
   for (int d = 0; d < G.ndims; d++) {
     int B[3] = { G.N[0], G.N[1], G.N[2] };
@@ -863,6 +868,7 @@ void parabolic_phase1(hpb_solver* h, const double* u)
 
 void parabolic_phase2(hpb_solver* h, const double* u, double* out, bool accumulate)
 {
+  ProfScope ps(h, HPB_PROF_VISCOUS);
   const Geom& G = h->geo;
   if (!accumulate) set_zero(h, out, G.npg * G.nvars);
   for (int d = 0; d < G.ndims; d++) {
@@ -889,6 +895,7 @@ void parabolic_nc1(hpb_solver* h, const double* u, double* out, bool accumulate)
 
 void rk_stage(hpb_solver* h, int stage)
 {
+  ProfScope ps(h, HPB_PROF_RK);
   const long long n = h->geo.npg * h->geo.nvars;
   RKArgs a; a.n = 0;
   for (int i = 0; i < stage; i++) {
@@ -902,6 +909,7 @@ void rk_stage(hpb_solver* h, int stage)
 
 void rk_finish(hpb_solver* h)
 {
+  ProfScope ps(h, HPB_PROF_RK);
   const long long n = h->geo.npg * h->geo.nvars;
   RKArgs a; a.n = h->rk.ns;
   for (int s = 0; s < h->rk.ns; s++) { a.k[s] = h->d_Udot[s]; a.a[s] = h->cfg.dt * h->rk.b[s]; }

@@ -365,6 +365,20 @@ class Solver:
     def time(self) -> float:
         return float(self.L.hpb_current_time(self.h))
 
+    PROF = {"sweep_x": 0, "sweep_y": 1, "sweep_z": 2, "viscous": 3, "rk": 4, "bc": 5, "halo": 6, "other": 7}
+
+    def profile_enable(self, on: bool = True) -> None:
+        self._ck(self.L.hpb_profile_enable(self.h, int(on)))
+
+    def profile_query(self) -> Dict[str, tuple]:
+        """{category: (total ms, launch groups)} since profile_enable(True)."""
+        out = {}
+        for name, cat in self.PROF.items():
+            ms, n = C.c_double(), C.c_longlong()
+            self._ck(self.L.hpb_profile_query(self.h, cat, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
     def halo_buffers(self, field: int):
         n = 2 * self.ndims
         send, recv, nbytes = (C.c_void_p * 6)(), (C.c_void_p * 6)(), (C.c_size_t * 6)()

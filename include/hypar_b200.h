@@ -219,6 +219,21 @@ int hpb_synchronize(hpb_solver* h);
 
 /* ------------------------------------------------------------------ instrumentation */
 long long hpb_kernel_launch_count(const hpb_solver* h);   /* kernels launched by this solver so far */
+/* Device timing per kernel category (the analogue of the reference's GPU_STAT cudaEvent timers,
+   HyperbolicFunction.c:69-121): when enabled, every launch group of a category is bracketed by a
+   CUDA event pair on the solver's stream. hpb_profile_query synchronises and returns the summed
+   milliseconds and the number of launch groups recorded since hpb_profile_enable(h, 1). */
+#define HPB_PROF_SWEEP_X  0   /* hyperbolic sweep kernels, direction 0 / 1 / 2 */
+#define HPB_PROF_SWEEP_Y  1
+#define HPB_PROF_SWEEP_Z  2
+#define HPB_PROF_VISCOUS  3   /* parabolic kernels */
+#define HPB_PROF_RK       4   /* stage-vector and step-completion kernels */
+#define HPB_PROF_BC       5   /* boundary-condition kernels */
+#define HPB_PROF_HALO     6   /* pack / unpack kernels */
+#define HPB_PROF_OTHER    7
+#define HPB_PROF_NCAT     8
+int hpb_profile_enable(hpb_solver* h, int on);
+int hpb_profile_query(hpb_solver* h, int category, double* total_ms, long long* count);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,177 @@
+"""C ABI: the library loads, exports every symbol include/hypar_b200.h declares, validates
+configurations with the reference's error behaviour, refuses to compute without a GPU, and its host
+set-up (partition, ghost coordinates, dxinv, neighbours, zone extents, gravity field) agrees with the
+independent numpy/C restatement in oracle/hpo.py. No compute calls: runs on a CPU-only box."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from hypar_b200 import _lib, cases
+from hypar_b200.solver import HyParB200Error, Solver
+from oracle import hpo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "hypar_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(hpb_[A-Za-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 55
+    for name in sorted(declared):
+        assert hasattr(L, name), f"libhypar_b200.so does not export {name}"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert b"sm_100a" in L.hpb_version()
+
+
+def test_config_struct_layout_matches_header():
+    """the ctypes mirror must have the C struct's size: hpb_config_defaults writes the whole struct"""
+    L = _lib.load()
+    c = _lib.Config()
+    guard = (C.c_char * 64)()
+    L.hpb_config_defaults(C.byref(c))
+    assert c.ghosts == 1 and c.gamma == 1.4 and c.weno_eps == 1e-6 and c.use_fused == 1 and c.device == -1
+    assert bytes(guard) == b"\0" * 64
+
+
+def test_partition_and_rank_maps():
+    L = _lib.load()
+    for ng, npr in ((512, 2), (50, 3), (201, 4), (64, 1)):
+        sizes = [L.hpb_partition1d(ng, npr, r) for r in range(npr)]
+        assert sum(sizes) == ng and sizes[:-1] == [ng // npr] * (npr - 1)          # MPIPartition1D.c
+        assert sizes == [hpo.partition1d(ng, npr, r) for r in range(npr)]
+    iproc = (C.c_int * 3)(2, 3, 2)
+    for r in range(12):
+        ip = (C.c_int * 3)()
+        L.hpb_ranknd(3, r, iproc, ip)
+        assert list(ip) == hpo.rank_nd([2, 3, 2], r)
+        assert L.hpb_rank1d(3, iproc, ip) == r
+
+
+ALL_CASES = [
+    cases.linear_advection_sine(64, "js"),
+    cases.euler1d_sod(101, "js"),
+    cases.ns2d_vortex((40, 28), "yc"),
+    cases.ns3d_turbulence((20, 14, 12), "mapped"),
+    cases.ns3d_rising_bubble((12, 16, 10), "yc"),
+    cases.ns3d_rising_bubble((10, 14, 12), "mapped", hb=1),
+]
+
+
+@pytest.mark.parametrize("case", ALL_CASES, ids=[c.name for c in ALL_CASES])
+def test_host_setup_matches_oracle_setup(case):
+    S = hpo.Setup(case)
+    sv = Solver.from_case(case)
+    assert sv.dim_local == S.dim and sv.npoints_local_wghosts == S.npoints_g
+    x, dxinv = sv.grid()
+    assert np.array_equal(x, S.x) and np.array_equal(dxinv, S.dxinv)
+    for n, z in enumerate(S.zones):
+        a, b, on = sv.zone_extent(n)
+        assert on == z["on"]
+        if on:
+            assert a == z["is"] and b == z["ie"]
+    f, g = sv.gravity_field()
+    assert np.array_equal(f, S.grav_f) and np.array_equal(g, S.grav_g)
+    assert sv.neighbors == [-1] * (2 * S.ndims)
+    assert sv.nstages == (4 if case.solver["time_scheme_type"] == "44" else 3)
+    for d in range(S.ndims):
+        assert sv.ninterfaces(d) == S.ninterfaces(d)
+    sv.close()
+
+
+def test_decomposed_setup_neighbors_and_remainders():
+    """50^3 over iproc 2x2x2 and 50x40x36 over 2x1x3: remainder on the last rank, periodic wrap,
+    same-peer left/right neighbours when iproc = 2 (MPIExchangeBoundariesnD.c:65-76)."""
+    for n, iproc in (((50, 50, 50), (2, 2, 2)), ((50, 40, 37), (2, 1, 3))):
+        case = cases.ns3d_turbulence(n, "js", iproc=iproc)
+        nranks = int(np.prod(iproc))
+        for r in range(nranks):
+            S = hpo.Setup(case, rank=r)
+            sv = Solver.from_case(case, rank=r)
+            assert sv.dim_local == S.dim and sv.is_global == S.is_
+            x, dxinv = sv.grid()
+            assert np.array_equal(x, S.x) and np.array_equal(dxinv, S.dxinv)
+            ip = hpo.rank_nd(iproc, r)
+            for d in range(3):
+                lo, hi = sv.neighbors[2 * d], sv.neighbors[2 * d + 1]
+                if iproc[d] == 1:
+                    assert lo == -1 and hi == -1
+                else:
+                    ipl, iph = list(ip), list(ip)
+                    ipl[d] = (ip[d] - 1) % iproc[d]
+                    iph[d] = (ip[d] + 1) % iproc[d]
+                    assert lo == hpo.rank_1d(iproc, ipl) and hi == hpo.rank_1d(iproc, iph)
+                    if iproc[d] == 2:
+                        assert lo == hi
+            sv.close()
+    # non-periodic: physical faces have no neighbour
+    case = cases.ns3d_rising_bubble((24, 24, 24), "yc", iproc=(2, 2, 1))
+    sv = Solver.from_case(case, rank=0)
+    assert sv.neighbors == [-1, 1, -1, 2, -1, -1]
+    sv.close()
+
+
+@pytest.mark.parametrize("mutate, msg", [
+    (lambda c: c.solver.__setitem__("hyp_space_scheme", "crweno5"), "weno5"),
+    (lambda c: c.solver.__setitem__("time_scheme", "glm-gee"), "rk"),
+    (lambda c: c.solver.__setitem__("time_scheme_type", "ssprk2"), "ssprk3"),
+    (lambda c: c.solver.__setitem__("ghost", 2), "ghost"),
+    (lambda c: c.solver.__setitem__("model", "shallow-water-2d"), "model"),
+    (lambda c: c.boundary[0].__setitem__("type", "noslip-wall"), "boundary type"),
+    (lambda c: c.physics.__setitem__("upwinding", "llf-char"), "upwinding"),
+    (lambda c: c.solver.__setitem__("par_space_type", "conservative-1stage"), "nonconservative-2stage"),
+])
+def test_unsupported_configurations_fail_loudly(mutate, msg):
+    case = cases.ns3d_turbulence((12, 12, 12), "js")
+    mutate(case)
+    with pytest.raises(HyParB200Error) as e:
+        Solver.from_case(case)
+    assert msg in str(e.value)
+    _lib.load().hpb_clear_error()
+
+
+def test_gravity_needs_rusanov_like_reference():
+    case = cases.ns3d_rising_bubble((12, 12, 12), "yc")
+    case.physics["upwinding"] = "roe"               # NavierStokes3DInitialize.c:371-378
+    with pytest.raises(HyParB200Error) as e:
+        Solver.from_case(case)
+    assert "rusanov" in str(e.value).lower()
+    _lib.load().hpb_clear_error()
+
+
+def test_no_cpu_fallback():
+    """without a CUDA device every compute entry point fails with HPB_ERR_NO_DEVICE and the error is sticky"""
+    L = _lib.load()
+    if L.hpb_device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    case = cases.linear_advection_sine(64, "js")
+    sv = Solver.from_case(case)                       # host set-up works without a GPU
+    u = hpo.Setup(case).local_u0()
+    for call in (lambda: sv.RHSFunction(u), lambda: sv.HyperbolicFunction(u), lambda: sv.TimeIntegrate(u, 1),
+                 lambda: sv.TimeStep(), lambda: sv.ApplyBoundaryConditions(u), lambda: sv.set_solution(u)):
+        with pytest.raises(HyParB200Error) as e:
+            call()
+        assert "no CUDA device" in str(e.value)
+    assert L.hpb_error_state() == 2
+    L.hpb_clear_error()
+    assert L.hpb_error_state() == 0
+    sv.close()
+
+
+def test_product_never_touches_the_oracle():
+    """the shipped package must not import, link or execute anything under oracle/"""
+    import subprocess
+    pkg = os.path.join(ROOT, "hypar_b200")
+    banned = ("import oracle", "from oracle", "hpo.", "libhypar_oracle", "hypar_oracle", "oracle/_ref", "hypar_ref")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dp, f)).read()
+                for b in banned:
+                    assert b not in txt, f"hypar_b200/{f} references the oracle ({b})"
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out

@@ -1,0 +1,180 @@
+"""The CPU oracle (oracle/hypar_oracle.c) pinned against golden vectors produced by the UNMODIFIED
+reference (tests/golden/*.npz, generator: tools/make_golden.py), and -- where oracle/_ref is present --
+against the reference executable run live on further cases.
+
+The reference's own tests hold no value-pinning vectors for this path: its
+WENO5 test only bounds the output and the baselines of its regression suite live in external
+repositories. The pin is therefore the reference executable itself; the comparison is BIT-EXACT
+(the oracle restates the same arithmetic in the same order, compiled by the same gcc -O3).
+"""
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from hypar_b200 import cases  # noqa: E402
+from oracle import hpo  # noqa: E402
+
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+
+
+def load(path):
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in meta["kwargs"].items()}
+    return z, getattr(cases, meta["builder"])(**kw), meta
+
+
+def same(a, b, what):
+    """bit-exact where both are finite; NaNs (never-filled corner ghosts, 0/0) must coincide"""
+    a, b = np.asarray(a).ravel(), np.asarray(b).ravel()
+    assert a.shape == b.shape, what
+    na, nb = np.isnan(a), np.isnan(b)
+    assert np.array_equal(na, nb), f"{what}: NaN pattern differs"
+    assert np.array_equal(a[~na], b[~nb]), f"{what}: max abs diff {np.abs(a[~na] - b[~nb]).max():.3e}"
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 14
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_matches_reference_golden(path):
+    z, case, meta = load(path)
+    S = hpo.Setup(case)
+    O = hpo.Oracle(S)
+    same(S.x, z["rhs_x"], "x with ghosts")
+    same(S.dxinv, z["rhs_dxinv"], "dxinv")
+    u = S.local_u0()
+    rhs, hyp, par, src = O.rhs(u, parts=True)
+    same(u, z["rhs_u"], "u after boundary conditions")
+    same(hyp, z["rhs_hyp"], "hyp")
+    same(par, z["rhs_par"], "par")
+    same(src, z["rhs_source"], "source")
+    same(rhs, z["rhs_rhs"], "rhs")
+    # three steps of the reference's own time loop
+    u = S.local_u0()
+    rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    for _ in range(3):
+        O.time_step(u, float(case.solver["dt"]), rk)
+    same(S.interior(u), S.interior(z["steps3_u"]), "u after 3 steps")
+    if "pieces_u" not in z:
+        return
+    # the function-pointer pieces, per direction
+    u = S.local_u0()
+    O.apply_bc(u)
+    same(u, z["pieces_u"], "pieces: u")
+    assert O.cfl(u, float(case.solver["dt"])) == float(z["pieces_cfl"][0])
+    for d in range(S.ndims):
+        f = O.flux(u, d)
+        same(f, z[f"pieces_fluxC_{d}"], f"FFunction {d}")
+        uc = O.modified_solution(u)
+        same(uc, z[f"pieces_uC_{d}"], f"UFunction {d}")
+        w = O.weno_weights(f, u, d)
+        same(w, z[f"pieces_weights_{d}"], f"WENO weights {d}")
+        outs = {}
+        for name, arr, upw, uflag in (("uL", uc, 1, 1), ("uR", uc, -1, 1), ("fL", f, 1, 0), ("fR", f, -1, 0)):
+            outs[name] = O.interp(arr, u, w, upw, d, uflag)
+            same(outs[name], z[f"pieces_{name}_{d}"], f"{name} {d}")
+        fi = O.upwind(outs["fL"], outs["fR"], outs["uL"], outs["uR"], u, d)
+        same(fi, z[f"pieces_fluxI_{d}"], f"Upwind {d}")
+        if f"pieces_D1_{d}" in z:
+            same(O.first_derivative(u, d), z[f"pieces_D1_{d}"], f"FirstDerivativePar {d}")
+        if f"pieces_D2_{d}" in z:
+            same(O.second_derivative(u, d, int(case.solver["par_space_scheme"])), z[f"pieces_D2_{d}"],
+                 f"SecondDerivativePar {d}")
+
+
+# ---- live reference (only where oracle/_ref was built: this container, or the GPU box via gpurun)
+def _live_cases():
+    return [
+        cases.linear_advection_sine(96, "z"),
+        cases.linear_advection_sine(80, "yc", diffusion=0.02, par_scheme="2"),
+        cases.euler1d_sod(151, "yc"),
+        cases.euler1d_sod(101, "js", interp="components", upwinding="roe"),
+        cases.euler1d_sod(101, "mapped", interp="characteristic", upwinding="rusanov"),
+        cases.ns2d_vortex((24, 40), "z"),
+        cases.ns3d_turbulence((20, 14, 12), "yc"),
+        cases.ns3d_turbulence((12, 10, 14), "mapped", viscous=True, interp="characteristic", upwinding="roe"),
+        cases.ns3d_rising_bubble((10, 14, 12), "z", hb=3) if False else cases.ns3d_rising_bubble((10, 14, 12), "z"),
+    ]
+
+
+LIVE = _live_cases()
+
+
+@pytest.mark.parametrize("case", LIVE, ids=[c.name for c in LIVE])
+@pytest.mark.parametrize("exe", ["hypar_ref", "hypar_ref_mpi1"])
+def test_oracle_matches_reference_live(case, exe):
+    from refrun import ref_available, run_reference
+    if not ref_available(exe):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    o = run_reference(case, "rhs", exe=exe)
+    S = hpo.Setup(case, mpi_semantics=exe.endswith("mpi1"))
+    O = hpo.Oracle(S)
+    u = S.local_u0()
+    rhs, hyp, par, src = O.rhs(u, parts=True)
+    for k, a in (("u", u), ("hyp", hyp), ("par", par), ("source", src), ("rhs", rhs)):
+        same(a, o[k]["data"], f"{exe} {k}")
+    o = run_reference(case, "steps", [2], exe=exe)
+    u = S.local_u0()
+    for _ in range(2):
+        O.time_step(u, float(case.solver["dt"]), hpo.RK_TYPES[case.solver["time_scheme_type"]])
+    same(S.interior(u), S.interior(o["ufinal"]["data"]), f"{exe} u after 2 steps")
+
+
+# ---- the reference's own unit tests for this path, re-run against the oracle
+def test_first_derivative_polynomial_exactness():
+    """tests/FirstDerivative/test_first_derivative.c: the 4th-order central operator differentiates
+    polynomials up to degree 4 exactly (interior points), tolerance 1e-10 as in the reference's harness."""
+    n = 40
+    case = cases.linear_advection_sine(n, "js")
+    S = hpo.Setup(case)
+    O = hpo.Oracle(S)
+    g = S.ghosts
+    xi = np.arange(-g, n + g, dtype=np.float64)
+    for deg in range(5):
+        f = np.ascontiguousarray(xi ** deg)
+        d = O.first_derivative(f, 0)
+        exact = deg * xi ** (deg - 1) if deg > 0 else np.zeros_like(xi)
+        assert np.abs(d - exact).max() <= 1e-10 * max(1.0, np.abs(exact).max()), f"degree {deg}"
+
+
+def test_second_derivative_polynomial_exactness():
+    """tests/SecondDerivative/test_second_derivative.c: 2nd order exact to degree 3, 4th order to degree 5."""
+    n = 40
+    case = cases.linear_advection_sine(n, "js")
+    S = hpo.Setup(case)
+    O = hpo.Oracle(S)
+    g = S.ghosts
+    xi = np.arange(-g, n + g, dtype=np.float64) / 8.0
+    h = 1.0 / 8.0
+    for order, maxdeg in ((2, 3), (4, 5)):
+        for deg in range(maxdeg + 1):
+            f = np.ascontiguousarray(xi ** deg)
+            d = O.second_derivative(f, 0, order)[g:g + n] / (h * h)
+            exact = (deg * (deg - 1) * xi ** (deg - 2) if deg > 1 else np.zeros_like(xi))[g:g + n]
+            assert np.abs(d - exact).max() <= 1e-10 * max(1.0, np.abs(exact).max()), f"order {order} degree {deg}"
+
+
+def test_weno5_smoke_bounded_like_reference():
+    """tests/InterpolationFunctions/test_interpolation.c:310-403: with weights frozen at (0.1,0.6,0.3)
+    (no_limiting) the interface values of a smooth function stay bounded (|fI| < 1.5) -- and are the
+    5th-order polynomial interpolant."""
+    case = cases.linear_advection_sine(64, "js")
+    case.weno["no_limiting"] = 1
+    S = hpo.Setup(case)
+    O = hpo.Oracle(S)
+    u = S.local_u0()
+    O.apply_bc(u)
+    w = O.weno_weights(u, u, 0)
+    assert np.allclose(w.reshape(4, 3, -1)[:, 0], 0.1) and np.allclose(w.reshape(4, 3, -1)[:, 1], 0.6)
+    fI = O.interp(u, u, w, 1, 0, 0)
+    assert np.abs(fI).max() < 1.5
+    xh = (np.arange(65) - 0.5) / 64.0
+    assert np.abs(fI - np.sin(2 * np.pi * xh)).max() < 1e-6

@@ -1,0 +1,77 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, built from /root/reference).
+
+    python tools/make_golden.py
+
+Each fixture holds, for one small case of a BASELINE.json configuration family, the outputs of the
+reference's own code on that case's input files:
+  rhs mode   : u after ApplyBoundaryConditions, hyp, par, source, rhs of ONE TimeRHSFunctionExplicit
+  steps mode : u after 3 time steps of the reference's TimePreStep/TimeStep/TimePostStep loop
+  pieces mode: (selected cases) FFunction, WENO weights, uL/uR/fL/fR, Upwind result per direction
+The case itself is re-created from hypar_b200.cases by name + arguments (stored in the fixture), so the
+inputs are not duplicated. TEST INFRASTRUCTURE ONLY.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from hypar_b200 import cases  # noqa: E402
+from refrun import run_reference  # noqa: E402
+
+# (fixture name, builder, kwargs, exe, with pieces)
+GOLDEN = [
+    ("c1_linadv_js", "linear_advection_sine", dict(n=64, weno="js"), "hypar_ref", True),
+    ("c1_linadv_mapped_diff4", "linear_advection_sine", dict(n=64, weno="mapped", diffusion=0.01, par_scheme="4"), "hypar_ref", False),
+    ("c1_linadv_1024_mapped", "linear_advection_sine", dict(n=1024, weno="mapped"), "hypar_ref", False),
+    ("c2_sod_js_char_roe", "euler1d_sod", dict(n=101, weno="js"), "hypar_ref", True),
+    ("c2_sod_201_mapped_char_roe", "euler1d_sod", dict(n=201, weno="mapped"), "hypar_ref", False),
+    ("c2_sod_z_comp_rusanov", "euler1d_sod", dict(n=101, weno="z", interp="components", upwinding="rusanov"), "hypar_ref", False),
+    ("c3_vortex_yc", "ns2d_vortex", dict(n=(20, 16), weno="yc"), "hypar_ref", True),
+    ("c3_vortex_mapped", "ns2d_vortex", dict(n=(28, 36), weno="mapped"), "hypar_ref", False),
+    ("c4_turb_mapped_visc", "ns3d_turbulence", dict(n=(10, 8, 8), weno="mapped"), "hypar_ref_mpi1", True),
+    ("c4_turb_js_roe_inv", "ns3d_turbulence", dict(n=(12, 10, 14), weno="js", upwinding="roe", viscous=False), "hypar_ref", False),
+    ("c4_turb_z_char_inv", "ns3d_turbulence", dict(n=(12, 12, 10), weno="z", interp="characteristic", viscous=False), "hypar_ref", False),
+    ("c5a_denswave_js", "ns3d_density_wave", dict(n=(12, 10, 8), weno="js"), "hypar_ref", False),
+    ("c5b_bubble_yc", "ns3d_rising_bubble", dict(n=(12, 16, 10), weno="yc"), "hypar_ref_mpi1", True),
+    ("c5b_bubble_mapped_hb1", "ns3d_rising_bubble", dict(n=(10, 12, 14), weno="mapped", hb=1), "hypar_ref", False),
+]
+
+
+def build_case(builder, kwargs):
+    kw = dict(kwargs)
+    if "n" in kw and isinstance(kw["n"], list):
+        kw["n"] = tuple(kw["n"])
+    return getattr(cases, builder)(**kw)
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, builder, kwargs, exe, pieces in GOLDEN:
+        case = build_case(builder, kwargs)
+        data = {}
+        o = run_reference(case, "rhs", exe=exe)
+        for k in ("u", "hyp", "par", "source", "rhs", "x", "dxinv"):
+            data["rhs_" + k] = o[k]["data"]
+        o = run_reference(case, "steps", [3], exe=exe)
+        data["steps3_u"] = o["ufinal"]["data"]
+        if pieces:
+            o = run_reference(case, "pieces", exe=exe)
+            for k, v in o.items():
+                if isinstance(v, dict):
+                    data["pieces_" + k] = v["data"]
+                elif k == "cfl":
+                    data["pieces_cfl"] = np.array([v])
+        meta = {"builder": builder, "kwargs": {k: (list(v) if isinstance(v, tuple) else v) for k, v in kwargs.items()},
+                "exe": exe, "reference": "debog/hypar sources under /root/reference, gcc -O3 -std=c99 (oracle/Makefile)"}
+        data["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **data)
+        print(name, {k: v.shape for k, v in data.items() if k != "meta"} if False else len(data))
+
+
+if __name__ == "__main__":
+    main()
