@@ -170,7 +170,11 @@ def test_weno5_smoke_bounded_like_reference():
     case.weno["no_limiting"] = 1
     S = hpo.Setup(case)
     O = hpo.Oracle(S)
-    u = S.local_u0()
+    # cell averages of sin(2 pi x) over [x_i - h/2, x_i + h/2]: the scheme reconstructs interface POINT values
+    h, g = 1.0 / 64, S.ghosts
+    xc = np.arange(64) * h
+    u = np.zeros(64 + 2 * g)
+    u[g:g + 64] = (np.cos(2 * np.pi * (xc - h / 2)) - np.cos(2 * np.pi * (xc + h / 2))) / (2 * np.pi * h)
     O.apply_bc(u)
     w = O.weno_weights(u, u, 0)
     assert np.allclose(w.reshape(4, 3, -1)[:, 0], 0.1) and np.allclose(w.reshape(4, 3, -1)[:, 1], 0.6)
