@@ -121,17 +121,31 @@ static bool viscous_on(const hpb_solver* h)
   return (h->cfg.model == HPB_MODEL_NS3D || h->cfg.model == HPB_MODEL_NS2D) && h->phys.Re > 0;
 }
 
+// production path = fused sweeps; NavierStokes3D viscous terms inside the sweeps
+static bool fused_path(const hpb_solver* h) { return hpbk::fused_available(h); }
+static bool fused_visc(const hpb_solver* h) { return fused_path(h) && h->cfg.model == HPB_MODEL_NS3D && viscous_on(h); }
+
+// buffers of the exact (generic) kernels; allocated on first use so that a production run does not carry them
+static int ensure_generic(hpb_solver* h)
+{
+  const long long n = ncell(h);
+  TRY(dalloc(&h->d_fI, nif_max(h) * h->geo.nvars));
+  if (h->phys.has_grav) { TRY(dalloc(&h->d_sI, nif_max(h) * 2)); TRY(dalloc(&h->d_src, n)); }
+  if (viscous_on(h)) {
+    for (int d = 0; d < h->geo.ndims; d++) TRY(dalloc(&h->d_QD[d], n));
+    TRY(dalloc(&h->d_FV, h->geo.npg * (h->geo.nvars - 1)));
+  }
+  if (viscous_on(h) || h->cfg.model == HPB_MODEL_LINEAR_ADR) TRY(dalloc(&h->d_par, n));
+  return HPB_OK;
+}
+
 static int alloc_main(hpb_solver* h)
 {
   const long long n = ncell(h);
   TRY(dalloc(&h->d_u, n)); TRY(dalloc(&h->d_uprev, n)); TRY(dalloc(&h->d_U, n));
   for (int s = 0; s < h->rk.ns; s++) TRY(dalloc(&h->d_Udot[s], n));
-  TRY(dalloc(&h->d_fI, nif_max(h) * h->geo.nvars));
-  if (h->phys.has_grav) TRY(dalloc(&h->d_sI, nif_max(h) * 2));
-  if (viscous_on(h)) {
-    for (int d = 0; d < h->geo.ndims; d++) TRY(dalloc(&h->d_QD[d], n));
-    TRY(dalloc(&h->d_FV, h->geo.npg * (h->geo.nvars - 1)));
-  }
+  if (fused_visc(h)) TRY(dalloc(&h->d_qd4, 12 * h->geo.npg));
+  if (!fused_path(h) || (viscous_on(h) && !fused_visc(h))) TRY(ensure_generic(h));
   return HPB_OK;
 }
 
@@ -194,7 +208,7 @@ extern "C" int hpb_destroy(hpb_solver* h)
   if (!h) return HPB_OK;
   if (h->stream || h->d_x) cudaSetDevice(h->device);
   double** ptrs[] = { &h->d_x, &h->d_dxinv, &h->d_gravf, &h->d_gravg, &h->d_u, &h->d_uprev, &h->d_U, &h->d_fI, &h->d_sI,
-                      &h->d_FV, &h->d_stage_aos, &h->d_w, &h->d_red };
+                      &h->d_FV, &h->d_stage_aos, &h->d_w, &h->d_red, &h->d_qd4, &h->d_par, &h->d_src };
   for (double** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
   for (int i = 0; i < 4; i++) { if (h->d_Udot[i]) cudaFree(h->d_Udot[i]); if (h->d_tmp[i]) cudaFree(h->d_tmp[i]); }
   for (int i = 0; i < 3; i++) if (h->d_QD[i]) cudaFree(h->d_QD[i]);
@@ -297,15 +311,38 @@ extern "C" int hpb_profile_query(hpb_solver* h, int category, double* total_ms, 
 
 // ------------------------------------------------------------------------------------ RHS assembly (device)
 // rhs = -hyp + par + source of TimeRHSFunctionExplicit.c:70-92, split at the viscous halo exchange.
-static void rhs_part_a(hpb_solver* h, const double* U, double* rhs)
+// Production path: [Q-derivatives] | sweeps with the viscous flux and the gravity source inside.
+// Exact path (use_fused = 0 or a configuration the fused kernels do not cover): generic kernels, par and
+// source accumulated separately and combined in the reference's order, so that the result is bit-identical.
+static int rhs_part_a(hpb_solver* h, const double* U, double* rhs)
 {
-  hpbk::hyperbolic(h, U, rhs, /*negate=*/true, /*with_source=*/true, rhs);
+  if (fused_path(h)) {
+    if (fused_visc(h)) hpbk::qderiv_fused(h, U);
+    else {
+      hpbk::hyperbolic_fused(h, U, rhs, /*negate=*/true, /*with_source=*/true, rhs, nullptr);
+      if (viscous_on(h)) hpbk::parabolic_phase1(h, U);          // NavierStokes2D viscous terms: generic kernels
+    }
+    return HPB_OK;
+  }
+  TRY(ensure_generic(h));
+  if (h->d_src) hpbk::set_zero(h, h->d_src, ncell(h));
+  hpbk::hyperbolic_generic(h, U, rhs, /*negate=*/true, /*with_source=*/true, h->d_src);
   if (viscous_on(h)) hpbk::parabolic_phase1(h, U);
+  return HPB_OK;
 }
-static void rhs_part_b(hpb_solver* h, const double* U, double* rhs)
+static int rhs_part_b(hpb_solver* h, const double* U, double* rhs)
 {
-  if (viscous_on(h)) hpbk::parabolic_phase2(h, U, rhs, /*accumulate=*/true);
-  else if (h->cfg.model == HPB_MODEL_LINEAR_ADR) hpbk::parabolic_nc1(h, U, rhs, true);
+  if (fused_path(h)) {
+    if (fused_visc(h)) hpbk::hyperbolic_fused(h, U, rhs, true, true, rhs, h->d_qd4);
+    else if (viscous_on(h)) hpbk::parabolic_phase2(h, U, rhs, /*accumulate=*/true);
+    else if (h->cfg.model == HPB_MODEL_LINEAR_ADR) hpbk::parabolic_nc1(h, U, rhs, true);
+    return HPB_OK;
+  }
+  const double* par = nullptr;
+  if (viscous_on(h)) { hpbk::parabolic_phase2(h, U, h->d_par, /*accumulate=*/false); par = h->d_par; }
+  else if (h->cfg.model == HPB_MODEL_LINEAR_ADR) { hpbk::parabolic_nc1(h, U, h->d_par, false); par = h->d_par; }
+  if (par || (h->d_src && h->phys.has_grav)) hpbk::combine_rhs(h, rhs, par, h->phys.has_grav ? h->d_src : nullptr);
+  return HPB_OK;
 }
 static bool multi_rank(const hpb_solver* h)
 {
@@ -338,6 +375,7 @@ extern "C" int hpb_HyperbolicFunction(hpb_solver* h, double* hyp, const double* 
   TRY(tmp(h, 0)); TRY(tmp(h, 1));
   TRY(upload(h, u, h->d_tmp[0], h->geo.npg, h->geo.nvars));
   hpbk::set_zero(h, h->d_tmp[1], ncell(h));
+  if (!fused_path(h)) TRY(ensure_generic(h));
   hpbk::hyperbolic(h, h->d_tmp[0], h->d_tmp[1], false, false, nullptr);
   TRY(check_async(h, "HyperbolicFunction"));
   return download(h, h->d_tmp[1], hyp, h->geo.npg, h->geo.nvars);
@@ -351,6 +389,7 @@ extern "C" int hpb_ParabolicFunction(hpb_solver* h, double* par, const double* u
   TRY(tmp(h, 0)); TRY(tmp(h, 1));
   TRY(upload(h, u, h->d_tmp[0], h->geo.npg, h->geo.nvars));
   hpbk::set_zero(h, h->d_tmp[1], ncell(h));
+  TRY(ensure_generic(h));
   if (viscous_on(h)) { hpbk::parabolic_phase1(h, h->d_tmp[0]); hpbk::parabolic_phase2(h, h->d_tmp[0], h->d_tmp[1], true); }
   else if (h->cfg.model == HPB_MODEL_LINEAR_ADR) hpbk::parabolic_nc1(h, h->d_tmp[0], h->d_tmp[1], true);
   TRY(check_async(h, "ParabolicFunction"));
@@ -366,6 +405,7 @@ extern "C" int hpb_SourceFunction(hpb_solver* h, double* source, const double* u
   hpbk::set_zero(h, h->d_tmp[1], ncell(h));
   // the source reuses the flux weights of the hyperbolic sweep of the same u (quirk Q5): the sweep is
   // re-evaluated here with the source enabled; its hyperbolic output goes to scratch
+  TRY(ensure_generic(h));
   if (h->phys.has_grav) hpbk::hyperbolic_generic(h, h->d_tmp[0], h->d_tmp[2], false, true, h->d_tmp[1]);
   TRY(check_async(h, "SourceFunction"));
   return download(h, h->d_tmp[1], source, h->geo.npg, h->geo.nvars);
@@ -378,9 +418,8 @@ extern "C" int hpb_RHSFunction(hpb_solver* h, double* rhs, double* u, double t)
   SINGLE_RANK_ONLY(h, "RHSFunction");
   TRY(upload(h, u, h->d_U, h->geo.npg, h->geo.nvars));
   hpbk::apply_bc(h, h->d_U);
-  hpbk::set_zero(h, h->d_Udot[0], ncell(h));
-  rhs_part_a(h, h->d_U, h->d_Udot[0]);
-  rhs_part_b(h, h->d_U, h->d_Udot[0]);
+  TRY(rhs_part_a(h, h->d_U, h->d_Udot[0]));
+  TRY(rhs_part_b(h, h->d_U, h->d_Udot[0]));
   TRY(check_async(h, "RHSFunction"));
   TRY(download(h, h->d_Udot[0], rhs, h->geo.npg, h->geo.nvars));
   return download(h, h->d_U, u, h->geo.npg, h->geo.nvars);
@@ -545,6 +584,16 @@ extern "C" int hpb_dev_fill_solution_from_global(hpb_solver* h, const double* ug
   return hpb_dev_set_solution(h, loc.data());
 }
 
+// stage solution U_s = u + dt sum_{i<s} a_si Udot_i (TimeRK.c:131-141). For s = 0 it equals u, whose ghosts
+// TimePreStep has just filled: the device loop uses u itself instead of a copy (the boundary conditions
+// re-applied by the RHS are idempotent), saving one pass over memory per step.
+static double* stage_U(hpb_solver* h, int s)
+{
+  if (s == 0) return h->d_u;
+  hpbk::rk_stage(h, s);
+  return h->d_U;
+}
+
 static int step_single(hpb_solver* h)
 {
   const long long n = ncell(h);
@@ -552,10 +601,10 @@ static int step_single(hpb_solver* h)
   hpbk::apply_bc(h, h->d_u);
   hpbk::copy(h, h->d_uprev, h->d_u, n);
   for (int s = 0; s < h->rk.ns; s++) {
-    hpbk::rk_stage(h, s);                       // TimeRK.c:131-141
-    hpbk::apply_bc(h, h->d_U);                  // TimeRHSFunctionExplicit.c:46
-    rhs_part_a(h, h->d_U, h->d_Udot[s]);
-    rhs_part_b(h, h->d_U, h->d_Udot[s]);
+    double* U = stage_U(h, s);                  // TimeRK.c:131-141
+    hpbk::apply_bc(h, U);                       // TimeRHSFunctionExplicit.c:46
+    TRY(rhs_part_a(h, U, h->d_Udot[s]));
+    TRY(rhs_part_b(h, U, h->d_Udot[s]));
   }
   hpbk::rk_finish(h);                           // TimeRK.c:182-193
   h->t += h->cfg.dt;                            // TimePostStep.c:36
@@ -608,8 +657,8 @@ extern "C" int hpb_dev_RHS(hpb_solver* h, double t, double* rhs_host)
   SINGLE_RANK_ONLY(h, "dev_RHS");
   hpbk::copy(h, h->d_U, h->d_u, ncell(h));
   hpbk::apply_bc(h, h->d_U);
-  rhs_part_a(h, h->d_U, h->d_Udot[0]);
-  rhs_part_b(h, h->d_U, h->d_Udot[0]);
+  TRY(rhs_part_a(h, h->d_U, h->d_Udot[0]));
+  TRY(rhs_part_b(h, h->d_U, h->d_Udot[0]));
   TRY(check_async(h, "dev_RHS"));
   if (rhs_host) return download(h, h->d_Udot[0], rhs_host, h->geo.npg, h->geo.nvars);
   return sync_check(h, "dev_RHS");
@@ -622,6 +671,7 @@ extern "C" int hpb_halo_buffers(hpb_solver* h, int field, void** send, void** re
   for (int k = 0; k < 2 * h->geo.ndims; k++) {
     send[k] = h->d_send[field][k]; recv[k] = h->d_recv[field][k];
     bytes[k] = (h->neighbor[k] >= 0) ? h->face_bytes[k] : 0;
+    if (field != HPB_FIELD_U && fused_visc(h)) bytes[k] = bytes[k] / h->geo.nvars * 4;   // (u,v,w,T) derivatives only
   }
   return HPB_OK;
 }
@@ -646,19 +696,21 @@ extern "C" int hpb_stage_begin(hpb_solver* h, int stage)
 {
   TRY(need_device(h));
   if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
-  hpbk::rk_stage(h, stage);
-  hpbk::apply_bc(h, h->d_U);
-  hpbk::pack(h, h->d_U, h->geo.nvars, HPB_FIELD_U);
+  double* U = stage_U(h, stage);
+  h->U_cur = U;
+  hpbk::apply_bc(h, U);
+  hpbk::pack(h, U, h->geo.nvars, HPB_FIELD_U);
   return check_async(h, "stage_begin");
 }
 
 extern "C" int hpb_stage_halo_done(hpb_solver* h, int field)
 {
   TRY(need_device(h));
-  if (field == HPB_FIELD_U) hpbk::unpack(h, h->d_U, h->geo.nvars, HPB_FIELD_U);
+  if (field == HPB_FIELD_U) hpbk::unpack(h, h->U_cur ? h->U_cur : h->d_U, h->geo.nvars, HPB_FIELD_U);
   else if (field == HPB_FIELD_QDERIVX || field == HPB_FIELD_QDERIVY) {
     if (!viscous_on(h)) return hpb_fail(HPB_ERR_INVALID, "stage_halo_done: no viscous exchange in this configuration");
-    hpbk::unpack(h, h->d_QD[field - 1], h->geo.nvars, field);
+    if (fused_visc(h)) hpbk::unpack_qd4(h, field);
+    else hpbk::unpack(h, h->d_QD[field - 1], h->geo.nvars, field);
   } else return hpb_fail(HPB_ERR_INVALID, "stage_halo_done: field %d", field);
   return check_async(h, "stage_halo_done");
 }
@@ -667,11 +719,14 @@ extern "C" int hpb_stage_rhs_a(hpb_solver* h, int stage)
 {
   TRY(need_device(h));
   if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
-  rhs_part_a(h, h->d_U, h->d_Udot[stage]);
+  TRY(rhs_part_a(h, h->U_cur ? h->U_cur : h->d_U, h->d_Udot[stage]));
   if (viscous_on(h)) {
     // NavierStokes3DParabolicFunction.c:125-130: QDerivX and QDerivY are exchanged, QDerivZ is not (Q1)
-    hpbk::pack(h, h->d_QD[0], h->geo.nvars, HPB_FIELD_QDERIVX);
-    hpbk::pack(h, h->d_QD[1], h->geo.nvars, HPB_FIELD_QDERIVY);
+    if (fused_visc(h)) { hpbk::pack_qd4(h, HPB_FIELD_QDERIVX); hpbk::pack_qd4(h, HPB_FIELD_QDERIVY); }
+    else {
+      hpbk::pack(h, h->d_QD[0], h->geo.nvars, HPB_FIELD_QDERIVX);
+      hpbk::pack(h, h->d_QD[1], h->geo.nvars, HPB_FIELD_QDERIVY);
+    }
   }
   return check_async(h, "stage_rhs_a");
 }
@@ -680,8 +735,15 @@ extern "C" int hpb_stage_rhs_b(hpb_solver* h, int stage)
 {
   TRY(need_device(h));
   if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
-  rhs_part_b(h, h->d_U, h->d_Udot[stage]);
+  TRY(rhs_part_b(h, h->U_cur ? h->U_cur : h->d_U, h->d_Udot[stage]));
   return check_async(h, "stage_rhs_b");
+}
+
+extern "C" int hpb_dev_get_stage_rhs(hpb_solver* h, int stage, double* rhs_host)
+{
+  TRY(need_device(h));
+  if (stage < 0 || stage >= h->rk.ns || !rhs_host) return hpb_fail(HPB_ERR_INVALID, "dev_get_stage_rhs: stage %d", stage);
+  return download(h, h->d_Udot[stage], rhs_host, h->geo.npg, h->geo.nvars);
 }
 
 extern "C" int hpb_step_finish(hpb_solver* h)

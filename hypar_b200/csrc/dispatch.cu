@@ -5,7 +5,7 @@
 namespace hpbk {
 void hyperbolic(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src)
 {
-  if (h->cfg.use_fused && hyperbolic_fused(h, u, out, negate, with_source, src)) return;
+  if (h->cfg.use_fused && fused_available(h) && hyperbolic_fused(h, u, out, negate, with_source, src, nullptr)) return;
   hyperbolic_generic(h, u, out, negate, with_source, src);
 }
 }

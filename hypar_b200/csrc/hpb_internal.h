@@ -60,11 +60,14 @@ struct hpb_solver {
   double *d_u = nullptr;           // solution (SoA, ghosts)
   double *d_uprev = nullptr;       // u at the start of the step (norm)
   double *d_U = nullptr;           // stage solution
+  double *U_cur = nullptr;         // staged API: the array holding the current stage solution (d_u for stage 0)
   double *d_Udot[4] = {nullptr, nullptr, nullptr, nullptr};
   double *d_fI = nullptr;          // interface flux (generic path), max over dirs
   double *d_sI = nullptr;          // interface gravity-source function (generic path)
   double *d_QD[3] = {nullptr, nullptr, nullptr};   // scaled primitive derivatives (viscous)
   double *d_FV = nullptr;          // viscous flux scratch
+  double *d_qd4 = nullptr;         // fused path: scaled derivatives of (u,v,w,T), [dir][comp][npg]
+  double *d_par = nullptr, *d_src = nullptr;   // exact path: separate accumulators of par and source
   double *d_stage_aos = nullptr;   // AoS staging for host<->device transposes
   double *d_tmp[4] = {nullptr, nullptr, nullptr, nullptr};   // scratch cell arrays for the fine-grained API
   double *d_w = nullptr;           // stored WENO weights of the fine-grained API (all dirs)
@@ -109,7 +112,16 @@ void unpack(hpb_solver* h, double* a, int nv, int field);
 // with_source: gravity-source contribution of each gravity direction is ADDED to src (quirk Q5).
 void hyperbolic(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src);
 void hyperbolic_generic(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src);
-bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src);
+// fused sweeps (sweep_fused.cu); qd != nullptr: the NavierStokes3D viscous terms are evaluated inside the sweeps
+bool fused_available(const hpb_solver* h);
+bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src,
+                      const double* qd);
+// fused viscous path (viscous_fused.cu)
+void qderiv_fused(hpb_solver* h, const double* u);
+void pack_qd4(hpb_solver* h, int field);
+void unpack_qd4(hpb_solver* h, int field);
+// exact path: rhs = (rhs + par) + src in the reference's order (TimeRHSFunctionExplicit.c:89-92)
+void combine_rhs(hpb_solver* h, double* rhs, const double* par, const double* src);
 void parabolic_phase1(hpb_solver* h, const double* u);
 void parabolic_phase2(hpb_solver* h, const double* u, double* out, bool accumulate);
 void parabolic_nc1(hpb_solver* h, const double* u, double* out, bool accumulate);

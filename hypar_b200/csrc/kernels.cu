@@ -471,6 +471,19 @@ __global__ void k_rk_combine(const double* __restrict__ u, RKArgs args, double* 
   }
 }
 
+// exact path: rhs = (rhs + par) + src, the summation order of TimeRHSFunctionExplicit.c:89-92 (rhs holds -hyp)
+__global__ void k_combine_rhs(double* __restrict__ rhs, const double* __restrict__ par, const double* __restrict__ src, long long n)
+{
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    double t = rhs[i];
+    if (par) t = __dadd_rn(t, par[i]);
+    if (src) t = __dadd_rn(t, src[i]);
+    rhs[i] = t;
+  }
+}
+
 __global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src, long long n)
 {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -822,6 +835,12 @@ void unpack(hpb_solver* h, double* a, int nv, int field)
 }
 
 void set_zero(hpb_solver* h, double* a, long long n) { cudaMemsetAsync(a, 0, n * sizeof(double), h->stream); }
+
+void combine_rhs(hpb_solver* h, double* rhs, const double* par, const double* src)
+{
+  const long long n = h->geo.npg * h->geo.nvars;
+  k_combine_rhs<<<grid1(n), 256, 0, h->stream>>>(rhs, par, src, n); LAUNCHED(h);
+}
 
 void copy(hpb_solver* h, double* dst, const double* src, long long n)
 {

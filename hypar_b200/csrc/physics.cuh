@@ -267,20 +267,27 @@ HPB_DEV void upwind_fn(const Phys& ph, int dir, const double* fL, const double* 
         for (int k = 0; k < NV; k++)
           lam[k] = (hpb_abs(lam[k]) < delta ? (lam[k] * lam[k] + delta2) / (2 * delta) : hpb_abs(lam[k]));
       }
-      // udiss = R (|D| (L udiff))  -- same product as R*(D*L) applied to udiff
-      double a[NV];
+      // udiss = (R (|D| L)) udiff, multiplied out in the reference's own order (MatMult, MatMult, MatVecMult:
+      // NavierStokes3DUpwind.c:104-106, Euler1DUpwind.c:84-86) so that the result carries its rounding
+      double DL[NV * NV], modA[NV * NV];
+#pragma unroll
+      for (int i = 0; i < NV; i++)
+#pragma unroll
+        for (int j = 0; j < NV; j++) DL[i * NV + j] = lam[i] * L[i * NV + j];
+#pragma unroll
+      for (int i = 0; i < NV; i++)
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+          double s = R[i * NV + 0] * DL[0 * NV + j];
+#pragma unroll
+          for (int k = 1; k < NV; k++) s += R[i * NV + k] * DL[k * NV + j];
+          modA[i * NV + j] = s;
+        }
 #pragma unroll
       for (int i = 0; i < NV; i++) {
-        double s = 0.0;
+        double s = modA[i * NV + 0] * udiff[0];
 #pragma unroll
-        for (int j = 0; j < NV; j++) s += L[i * NV + j] * udiff[j];
-        a[i] = lam[i] * s;
-      }
-#pragma unroll
-      for (int i = 0; i < NV; i++) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < NV; j++) s += R[i * NV + j] * a[j];
+        for (int j = 1; j < NV; j++) s += modA[i * NV + j] * udiff[j];
         fI[i] = 0.5 * (fL[i] + fR[i]) - s;
       }
     }

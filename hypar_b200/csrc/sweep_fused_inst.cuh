@@ -1,0 +1,57 @@
+// sweep_fused_inst.cuh -- launcher of the fused sweep for one weight type (one translation unit per
+// weight type keeps the build parallel: sweep_fused_wt{0..4}.cu).
+#pragma once
+#include "sweep_fused.cuh"
+
+namespace hpbf {
+
+template <int MODEL, int WT, bool MAPX, bool GRAV, bool VISC>
+static bool launch_one(hpb_solver* h, const SweepArgs& a)
+{
+  constexpr size_t smem = sweep_smem_bytes<MODEL, GRAV, VISC>();
+  static bool configured = false;
+  auto kern = k_sweep<MODEL, WT, MAPX, GRAV, VISC>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = true;
+  }
+  const int N = a.G.N[a.dir];
+  dim3 grid((a.nlines + TW - 1) / TW, (N + OUTL - 1) / OUTL, 1);
+  if (grid.y > 65535u) return false;
+  kern<<<grid, NT, smem, h->stream>>>(a);
+  h->launches++;
+  return true;
+}
+
+template <int MODEL, int WT, bool MAPX>
+static bool launch_map(hpb_solver* h, const SweepArgs& a, bool grav, bool visc)
+{
+  constexpr bool NS3 = (MODEL == HPB_MODEL_NS3D);
+  if (NS3 && grav && visc) return launch_one<MODEL, WT, MAPX, NS3, NS3>(h, a);
+  if (NS3 && grav)         return launch_one<MODEL, WT, MAPX, NS3, false>(h, a);
+  if (NS3 && visc)         return launch_one<MODEL, WT, MAPX, false, NS3>(h, a);
+  return launch_one<MODEL, WT, MAPX, false, false>(h, a);
+}
+
+template <int MODEL, int WT>
+static bool launch_model(hpb_solver* h, const SweepArgs& a, bool grav, bool visc)
+{
+  return (a.dir == 0) ? launch_map<MODEL, WT, true>(h, a, grav, visc) : launch_map<MODEL, WT, false>(h, a, grav, visc);
+}
+
+template <int WT>
+bool launch_sweep(hpb_solver* h, const SweepArgs& a)
+{
+  const bool grav = h->phys.has_grav != 0;
+  switch (h->cfg.model) {
+    case HPB_MODEL_LINEAR_ADR: return launch_model<HPB_MODEL_LINEAR_ADR, WT>(h, a, false, false);
+    case HPB_MODEL_NS2D:       return launch_model<HPB_MODEL_NS2D, WT>(h, a, false, false);
+    case HPB_MODEL_NS3D:       return launch_model<HPB_MODEL_NS3D, WT>(h, a, grav, a.qd != nullptr);
+    default: return false;
+  }
+}
+
+} // namespace hpbf

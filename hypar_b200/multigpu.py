@@ -1,0 +1,167 @@
+"""One rank of a domain-decomposed run: the halo exchange of MPIExchangeBoundariesnD
+(reference src/MPIFunctions/MPIExchangeBoundariesnD.c:42-173) over torch.distributed (NCCL on the
+GPUs of one NVSwitch box; gloo in the CPU tests), wrapped around the staged C-ABI step
+(``hpb_step_begin`` ... ``hpb_step_finish``, include/hypar_b200.h).
+
+Decomposition = HyPar's: ``iproc[d]`` blocks per dimension, remainder on the last block, rank =
+ip0 + iproc0*(ip1 + iproc1*ip2); faces only (edges/corners are never exchanged, as in the reference).
+The path has exactly one real exchange step per field -- no other collective is on the data path;
+CFL / norm reductions are scalar all-reduces outside the hot loop.
+
+Message matching. NCCL point-to-point has no tags: between one pair of ranks, sends and receives
+match in issue order. The reference distinguishes the two messages of a pair with tags 1630/1631
+(:95-100, :132-137); they matter when iproc[d] == 2 with periodic boundaries, where the left and the
+right neighbour are the same peer. Here every rank issues, per dimension, ``send(low face)``,
+``send(high face)`` and ``recv(high ghost)``, ``recv(low ghost)`` -- the peer's low-face send is the
+first message it sends us and lands in our high ghost, its high-face send is the second.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .solver import FIELD_QDERIVX, FIELD_QDERIVY, FIELD_U, Solver
+
+
+def exchange_ops(neighbors: Sequence[int], dims: Optional[Sequence[int]] = None):
+    """The ordered list of point-to-point operations of one face exchange:
+    [("send" | "recv", face index 2*d + side, peer rank)], side 0 = low, 1 = high."""
+    nd = len(neighbors) // 2
+    ops = []
+    for d in (range(nd) if dims is None else dims):
+        lo, hi = neighbors[2 * d], neighbors[2 * d + 1]
+        if lo >= 0:
+            ops.append(("send", 2 * d, lo))
+        if hi >= 0:
+            ops.append(("send", 2 * d + 1, hi))
+        if hi >= 0:
+            ops.append(("recv", 2 * d + 1, hi))
+        if lo >= 0:
+            ops.append(("recv", 2 * d, lo))
+    return ops
+
+
+class HaloExchanger:
+    """Face exchange between persistent send/receive buffers (torch tensors: CUDA for NCCL, CPU for gloo)."""
+
+    def __init__(self, neighbors: Sequence[int], send: Sequence, recv: Sequence, group=None):
+        self.neighbors, self.send, self.recv, self.group = list(neighbors), list(send), list(recv), group
+
+    def start(self, dims: Optional[Sequence[int]] = None):
+        import torch.distributed as dist
+        p2p = []
+        for kind, face, peer in exchange_ops(self.neighbors, dims):
+            if kind == "send":
+                p2p.append(dist.P2POp(dist.isend, self.send[face], peer, self.group))
+            else:
+                p2p.append(dist.P2POp(dist.irecv, self.recv[face], peer, self.group))
+        return dist.batch_isend_irecv(p2p) if p2p else []
+
+    @staticmethod
+    def finish(works) -> None:
+        for w in works:
+            w.wait()
+
+    def exchange(self, dims: Optional[Sequence[int]] = None) -> None:
+        self.finish(self.start(dims))
+
+
+class _DevBuf:
+    """a raw device allocation seen through __cuda_array_interface__ (no copy, no ownership)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class DistributedSolver:
+    """Drives the staged step of one rank and exchanges its halo buffers.
+
+    The library's kernels run on the solver's own CUDA stream; that stream is made torch's current
+    stream around every exchange, so NCCL's send/recv are ordered after the pack kernels and before the
+    unpack kernels without any host synchronisation.
+    """
+
+    def __init__(self, solver_inp, boundary, physics, weno, x, rank: int, device: int, group=None,
+                 use_fused: bool = True):
+        import torch
+        self.torch = torch
+        self.solver = Solver(solver_inp, boundary, physics, weno, x, rank=rank, device=device, use_fused=use_fused)
+        sv = self.solver
+        self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.ExternalStream(sv.stream, device=self.device)
+        self.viscous = bool(sv.L.hpb_needs_viscous_exchange(sv.h))
+        self.ex = {}
+        fields = [FIELD_U] + ([FIELD_QDERIVX, FIELD_QDERIVY] if self.viscous else [])
+        for f in fields:
+            send, recv, nbytes = sv.halo_buffers(f)
+            st = [torch.as_tensor(_DevBuf(p, n), device=self.device) if (p and n) else None for p, n in zip(send, nbytes)]
+            rt = [torch.as_tensor(_DevBuf(p, n), device=self.device) if (p and n) else None for p, n in zip(recv, nbytes)]
+            self.ex[f] = HaloExchanger(sv.neighbors, st, rt, group)
+        self.group = group
+
+    def _exchange(self, fields) -> None:
+        with self.torch.cuda.stream(self.stream):
+            works = []
+            for f in fields:
+                works += self.ex[f].start()
+            HaloExchanger.finish(works)
+
+    def time_step(self) -> None:
+        """TimePreStep (BCs + halo on u) and TimeRK (TimeRK.c:126-195), one step."""
+        sv, L = self.solver, self.solver.L
+        sv._ck(L.hpb_step_begin(sv.h))
+        self._exchange([FIELD_U])
+        sv._ck(L.hpb_step_halo_done(sv.h))
+        for s in range(sv.nstages):
+            sv._ck(L.hpb_stage_begin(sv.h, s))
+            self._exchange([FIELD_U])
+            sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_U))
+            sv._ck(L.hpb_stage_rhs_a(sv.h, s))
+            if self.viscous:
+                self._exchange([FIELD_QDERIVX, FIELD_QDERIVY])
+                sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_QDERIVX))
+                sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_QDERIVY))
+            sv._ck(L.hpb_stage_rhs_b(sv.h, s))
+        sv._ck(L.hpb_step_finish(sv.h))
+
+    def time_steps(self, n: int) -> None:
+        for _ in range(n):
+            self.time_step()
+
+    def time_integrate_host(self, u_host: np.ndarray, nsteps: int = 1) -> np.ndarray:
+        """TimeIntegrate on a host array in HyPar's layout (this rank's block with ghosts): H2D, steps, D2H."""
+        self.solver.set_solution(u_host)
+        self.time_steps(nsteps)
+        self.solver._ck(self.solver.L.hpb_dev_get_solution(self.solver.h,
+                                                           u_host.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double))))
+        return u_host
+
+    def rhs(self, want: bool = True):
+        """One TimeRHSFunctionExplicit of the device solution (stage 0 buffers); returns this rank's rhs."""
+        sv, L = self.solver, self.solver.L
+        sv._ck(L.hpb_stage_begin(sv.h, 0))
+        self._exchange([FIELD_U])
+        sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_U))
+        sv._ck(L.hpb_stage_rhs_a(sv.h, 0))
+        if self.viscous:
+            self._exchange([FIELD_QDERIVX, FIELD_QDERIVY])
+            sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_QDERIVX))
+            sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_QDERIVY))
+        sv._ck(L.hpb_stage_rhs_b(sv.h, 0))
+        return sv.get_stage_rhs(0) if want else None
+
+    # scalar reductions of TimePreStep.c:81-107 / TimePostStep.c:44-63
+    def max_cfl(self) -> float:
+        import torch.distributed as dist
+        t = self.torch.tensor([self.solver.dev_ComputeCFL()], device=self.device, dtype=self.torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
+    def step_norm(self) -> float:
+        import torch.distributed as dist
+        t = self.torch.tensor([self.solver.dev_StepNormSumSq()], device=self.device, dtype=self.torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        npts = float(np.prod(self.solver.dim_global))
+        return float(np.sqrt(t.item() / npts))

@@ -336,6 +336,11 @@ class Solver:
         self._ck(self.L.hpb_dev_RHS(self.h, t, _dp(rhs) if want else None))
         return rhs
 
+    def get_stage_rhs(self, stage: int = 0) -> np.ndarray:
+        rhs = self.zeros()
+        self._ck(self.L.hpb_dev_get_stage_rhs(self.h, stage, _dp(rhs)))
+        return rhs
+
     def dev_ComputeCFL(self) -> float:
         out = C.c_double()
         self._ck(self.L.hpb_dev_ComputeCFL(self.h, C.byref(out)))

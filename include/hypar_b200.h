@@ -212,6 +212,7 @@ int hpb_stage_halo_done(hpb_solver* h, int field);
 int hpb_stage_rhs_a(hpb_solver* h, int stage);
 int hpb_stage_rhs_b(hpb_solver* h, int stage);
 int hpb_step_finish(hpb_solver* h);
+int hpb_dev_get_stage_rhs(hpb_solver* h, int stage, double* rhs_host);   /* Udot[stage] -> host (HyPar layout) */
 int hpb_nstages(const hpb_solver* h);
 int hpb_needs_viscous_exchange(const hpb_solver* h);
 void* hpb_stream(hpb_solver* h);                      /* cudaStream_t the kernels run on */
