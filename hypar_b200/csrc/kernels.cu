@@ -80,13 +80,16 @@ __global__ void k_bc_zone(Geom G, ZoneDev z, double gamma, double* __restrict__ 
   }
   for (int k = 0; k < ndv; k++) vsq += vel[k] * vel[k];
   const double energy = phi[(nv - 1) * G.npg + p2];
-  const double pressure = (energy - 0.5 * rho * vsq) * (gamma - 1.0);
+  // 1-D: _Euler1DGetFlowVar_ multiplies 0.5*rho*v*v left to right (BCSlipWall.c 1-D branch)
+  const double pressure = (ndv == 1) ? (energy - 0.5 * rho * vel[0] * vel[0]) * (gamma - 1.0)
+                                     : (energy - 0.5 * rho * vsq) * (gamma - 1.0);
   const double inv_gamma_m1 = 1.0 / (gamma - 1.0);
   double vg[3] = { vel[0], vel[1], vel[2] };
   vg[dim] = 2.0 * z.wall[dim] - vel[dim];
   double vgsq = 0.0;
   for (int k = 0; k < ndv; k++) vgsq += vg[k] * vg[k];
-  const double energy_gpt = inv_gamma_m1 * pressure + 0.5 * rho * vgsq;
+  const double energy_gpt = (ndv == 1) ? inv_gamma_m1 * pressure + 0.5 * rho * vg[0] * vg[0]
+                                       : inv_gamma_m1 * pressure + 0.5 * rho * vgsq;
   phi[p1] = rho;
   for (int k = 0; k < ndv; k++) phi[(1 + k) * G.npg + p1] = rho * vg[k];
   phi[(nv - 1) * G.npg + p1] = energy_gpt;

@@ -34,7 +34,8 @@ HPB_DEV void flowvar(const double* u, double gamma, double& rho, double* vel, do
     for (int k = 0; k < NDV; k++) vsq += vel[k] * vel[k];
   }
   e = u[NV - 1];
-  P = (e - 0.5 * rho * vsq) * (gamma - 1.0);
+  if (MODEL == HPB_MODEL_EULER1D) P = (e - 0.5 * rho * vel[0] * vel[0]) * (gamma - 1.0);   // euler1d.h: 0.5*rho*v*v, left to right
+  else P = (e - 0.5 * rho * vsq) * (gamma - 1.0);
 }
 
 // ---- FFunction: NavierStokes3DFlux.c:24 (_NavierStokes3DSetFlux_ navierstokes3d.h:114-139),
@@ -109,8 +110,13 @@ HPB_DEV void roe_average(const Phys& ph, const double* uL, const double* uR, dou
     double sL = 0.0, sR = 0.0;
 #pragma unroll
     for (int k = 0; k < NDV; k++) { sL += vL[k] * vL[k]; sR += vR[k] * vR[k]; }
-    PL = (eL - 0.5 * rhoL * sL) * (gamma - 1.0);
-    PR = (eR - 0.5 * rhoR * sR) * (gamma - 1.0);
+    if (MODEL == HPB_MODEL_EULER1D) {                       // _Euler1DRoeAverage_: 0.5*rho*v*v, left to right
+      PL = (eL - 0.5 * rhoL * vL[0] * vL[0]) * (gamma - 1.0);
+      PR = (eR - 0.5 * rhoR * vR[0] * vR[0]) * (gamma - 1.0);
+    } else {
+      PL = (eL - 0.5 * rhoL * sL) * (gamma - 1.0);
+      PR = (eR - 0.5 * rhoR * sR) * (gamma - 1.0);
+    }
   }
   double vsqL = 0.0, vsqR = 0.0;
 #pragma unroll
@@ -132,7 +138,8 @@ HPB_DEV void roe_average(const Phys& ph, const double* uL, const double* uR, dou
     const double csq = (gamma - 1.0) * (H - 0.5 * vsq);
     P = csq * rho / gamma;
   }
-  const double e = P / (gamma - 1.0) + 0.5 * rho * vsq;
+  const double e = (MODEL == HPB_MODEL_EULER1D) ? (P / (gamma - 1.0) + 0.5 * rho * v[0] * v[0])
+                                                : (P / (gamma - 1.0) + 0.5 * rho * vsq);
   uavg[0] = rho;
 #pragma unroll
   for (int k = 0; k < NDV; k++) uavg[1 + k] = rho * v[k];

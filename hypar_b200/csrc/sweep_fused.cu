@@ -14,14 +14,13 @@ bool fused_available(const hpb_solver* h)
   if (c.model == HPB_MODEL_EULER1D) return false;
   if ((c.model == HPB_MODEL_NS2D || c.model == HPB_MODEL_NS3D) && c.upwind != HPB_UPWIND_RUSANOV) return false;
   if (c.model == HPB_MODEL_LINEAR_ADR && c.nvars != 1) return false;
-  for (int d = 0; d < h->geo.ndims; d++)
-    if ((h->geo.N[d] + hpbf::OUTL - 1) / hpbf::OUTL > 65535) return false;   // grid.y limit
   return true;
 }
 
 bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src,
                       const double* qd)
 {
+  if (with_source && src != nullptr && src != out) return false;     // the fused kernels accumulate the source into `out`
   const Geom& G = h->geo;
   const int wt = h->phys.no_limiting ? hpbf::WT_NOLIM : h->phys.weno;
   for (int d = 0; d < G.ndims; d++) {
@@ -32,6 +31,10 @@ bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, 
     a.mode = negate ? (d == 0 ? 0 : 1) : (d == 0 ? 2 : 3);
     a.with_source = (with_source && h->phys.has_grav && h->phys.grav[d] != 0.0 && src != nullptr) ? 1 : 0;
     a.qd = qd;
+    {
+      static const int tab[3][8] = { { 0, 1, 2, 3, 4, 5, 8, 10 }, { 4, 5, 6, 7, 0, 1, 9, 10 }, { 8, 9, 10, 11, 0, 2, 5, 6 } };
+      for (int k = 0; k < 8; k++) a.qidx[k] = tab[d][k];
+    }
     a.nlines = (d == 0 ? G.N[1] * G.N[2] : d == 1 ? G.N[0] * G.N[2] : G.N[0] * G.N[1]);
     ProfScope ps(h, HPB_PROF_SWEEP_X + d);
     bool ok;

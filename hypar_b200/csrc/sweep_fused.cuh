@@ -1,31 +1,43 @@
 // sweep_fused.cuh -- the fused directional sweep: for one sweep direction, ONE kernel goes from the
-// conserved variables to the flux divergence (and the well-balanced gravity source):
+// conserved variables to the flux divergence, the viscous flux derivative and the gravity source:
 //
 //   flux f_d(u), modified solution uC(u)                 NavierStokes3DFlux.c:24, ...ModifiedSolution.c:31
 //   WENO5 weights, L/R-biased x {flux, raw u}            WENOFifthOrderCalculateWeights.c:111-745
 //   fL, fR (flux, F-weights), uL, uR (uC, U-weights)     Interp1PrimFifthOrderWENO.c:74-168
 //   Rusanov upwinding                                    NavierStokes3DUpwind.c:349-418
 //   out -= dxinv (fhat_{j+1} - fhat_j)                   HyperbolicFunction.c:94-109
+//   out += dxinv D_d(FViscous_d)                         NavierStokes3DParabolicFunction.c:152-314
 //   out += gravity source, same F-weights (quirk Q5)     NavierStokes3DSource.c:38-104
 //
-// without materialising fluxC, uC, the 12 weight arrays or the 5 interface arrays of the reference
-// (about 9 kB per point-stage of memory traffic there; here: read u once, update out once).
+// without materialising fluxC, uC, the 12 weight arrays, the 5 interface arrays or FViscous/FDeriv of the
+// reference (about 9 kB per point-stage of memory traffic there; here: read u (+8 derivative scalars) once,
+// update out once).
 //
-// Work decomposition. A CTA owns TW = 8 grid lines along the sweep direction and a chunk of
-// TL - 2 = 30 cells of each line. One thread per "reconstruction cell" j (TL = 32 per line: the 30
-// output cells plus one on either side):
-//   phase 1  every stencil cell (36 per line) gets its record in shared memory, computed ONCE:
-//            u, f_d(u), uC_energy, sqrt(rho), velocity, total enthalpy, c + |v_d|   (17 doubles)
-//   phase 2  thread j reads the 5-cell windows of f and u centred on j and reconstructs BOTH values
-//            the centred stencil serves: the left-biased value at j+1/2 and the right-biased value
-//            at j-1/2. The three smoothness indicators are the same for both (the stencil is only
-//            mirrored), so they -- and (beta+eps)^2 and their pair products -- are computed once.
-//   phase 3  thread j owns interface j+1/2: its own left-biased values + the right-biased values of
-//            thread j+1 (through shared memory) -> Rusanov flux
-//   phase 4  thread j differences the interface fluxes j+1/2 (own) and j-1/2 (thread j-1) and
-//            updates `out` (and the source) with coalesced stores.
-// The x-sweep maps the 32 lanes of a warp along the line (contiguous x); y- and z-sweeps map 8
-// consecutive threads to 8 x-contiguous lines, so global accesses are 64-256 B contiguous runs.
+// Work decomposition: a persistent line march, one WARP per grid line. A CTA (8 warps) owns TW = 8 grid lines
+// along the sweep direction and marches along them in steps of TL = 32 cells; lane l of warp w works on cell l
+// of the step on line w. Everything between loading the inputs and storing the result is private to the warp
+// (its own region of shared memory, __syncwarp only); the CTA only cooperates to move data between global
+// and shared memory with contiguous accesses (the lines of a CTA are x-adjacent for the y-/z-sweeps).
+// Per step m (cells are numbered along the line, -3..N+2 with ghosts):
+//   B1  cp.async of step m landed; results of step m-1 staged                                  (CTA barrier)
+//   C   cooperative: results of step m-1 -> global (read-modify-write when accumulating; the old values were
+//       requested before B1)
+//   P1  record of cell 32m+3+l in shared memory, computed ONCE per cell: u, f_d(u), uC_energy, sqrt(rho),
+//       velocity, total enthalpy, c+|v_d| (, viscous flux, gravity fields)
+//   B2  staging consumed                                                                         (CTA barrier)
+//   P0  cp.async prefetch of the raw inputs of step m+1 (u, and for the viscous terms 8 derivative scalars):
+//       overlaps the arithmetic of P2..P4
+//   P2  lane reconstructs, from the 5-cell windows centred on cell j = 32m+1+l, BOTH values that centred
+//       stencil serves: the left-biased value at j+1/2 and the right-biased value at j-1/2. The three
+//       smoothness indicators are the same for both (the stencil is only mirrored), so they -- and
+//       (beta+eps)^2 and their pair products -- are computed once.
+//   P3  lane owns interface j-1/2: its own right-biased values + the left-biased values of cell j-1
+//       (neighbour lane through shared memory; across steps through a carry slot) -> Rusanov flux
+//   P4  lane forms the update of cell j-1 = 32m+l: difference of the interface fluxes j-1/2 (own) and j-3/2
+//       (neighbour / carry), central derivative of the viscous flux, gravity source -> staged for C
+//   then the last 5 records and the carry slots are shifted to the front for the next step (warp-private).
+// Every record, reconstruction, interface and output is computed exactly once per cell (one mostly idle
+// start-up step per line produces the records of the low ghost cells and the first interface).
 //
 // Arithmetic. FP64 throughout, FMA contraction on. The weights are evaluated in a division-free
 // homogeneous form (one reciprocal per weight set instead of 4 (JS/Z/YC) or 9 (mapped) divisions):
@@ -37,11 +49,15 @@
 
 namespace hpbf {
 
-constexpr int TL = 32;            // reconstruction cells per line chunk (threads along the line)
+constexpr int TL = 32;            // cells per line per march step
 constexpr int TW = 8;             // lines per CTA
 constexpr int NT = TL * TW;       // threads per CTA
-constexpr int SC = TL + 4;        // stencil cells per line chunk (j0-3 .. j0+TL)
-constexpr int OUTL = TL - 2;      // output cells per line chunk
+constexpr int RP = TL + 5;        // record positions per line: cells [32m-2, 32m+35) of step m
+constexpr int NREC = RP * TW;     // record slots per field  (index: line * RP + position)
+constexpr int SS = TW + 1;        // y-/z-sweeps: staging stride per cell (padded; index: cell * SS + line)
+constexpr int NSTG = TL * SS;     // staging slots per field (x-sweep: index line * TL + cell)
+constexpr int XP = TL + 1;        // exchange slots per line (slot 0 = carry from the previous step)
+constexpr int NEX = XP * TW;      // exchange slots per field (index: line * XP + slot)
 
 // weight type as template parameter: HPB_WENO_JS/M/Z/YC, 4 = no_limiting (optimal weights)
 constexpr int WT_NOLIM = 4;
@@ -54,12 +70,14 @@ struct SweepArgs {
   const double* gg;      // gravity field g
   const double* dxinv;   // concatenated, with ghosts
   double* out;           // rhs / hyp accumulator (SoA, ghosts)
-  double* src;           // gravity source accumulator (may alias out) or nullptr
+  double* src;           // gravity source accumulator: must be `out` itself (or nullptr)
   int dir;
   int mode;              // 0: out = -div ; 1: out -= div ; 2: out = +div ; 3: out += div
   int with_source;       // add the gravity source of this direction to src
   int nlines;            // number of grid lines along dir
-  const double* qd;      // VISC: scaled derivatives of (u,v,w,T): qd[(dir*4 + comp) * npg + p] (viscous_fused.cu)
+  const double* qd;      // VISC: (mu/Re) x scaled derivatives of (u,v,w,T): qd[(dir*4 + comp) * npg + p] (viscous_fused.cu)
+  int qidx[8];           // VISC: the 8 derivative scalars the viscous flux of `dir` needs (indices dir*4+comp into qd):
+                         //   dir 0: ux vx wx Tx | uy vy | uz wz   dir 1: uy vy wy Ty | ux vx | vz wz   dir 2: uz vz wz Tz | ux wx | vy wy
 };
 
 __device__ __forceinline__ double rcp_fast(double x)
@@ -169,55 +187,64 @@ __device__ __forceinline__ void recon_pair(const double (&X)[5], const double (&
 }
 
 // ------------------------------------------------------------------------------------------
-// record layout in shared memory (field-major: rec[field * NCELL + cell])
+// record layout in shared memory (field-major: rec[field * NREC + pos * TW + line])
 template <int MODEL> struct RecLayout;
-template <> struct RecLayout<HPB_MODEL_LINEAR_ADR> { enum { NV = 1, U = 0, F = 1, NF = 2, V4 = 0, SR = 0, VEL = 0, H = 0, A = 0, GF = 0, GG = 0 }; };
-template <> struct RecLayout<HPB_MODEL_NS2D> { enum { NV = 4, U = 0, F = 4, V4 = 8, SR = 9, VEL = 10, H = 12, A = 13, NF = 14, GF = 14, GG = 14 }; };
-template <> struct RecLayout<HPB_MODEL_NS3D> { enum { NV = 5, U = 0, F = 5, V4 = 10, SR = 11, VEL = 12, H = 15, A = 16, GF = 17, GG = 18, NF = 17 }; };
+template <> struct RecLayout<HPB_MODEL_LINEAR_ADR> { enum { NV = 1, U = 0, F = 1, NF = 2, V4 = 0, SR = 0, VEL = 0, H = 0, A = 0 }; };
+template <> struct RecLayout<HPB_MODEL_NS2D> { enum { NV = 4, U = 0, F = 4, V4 = 8, SR = 9, VEL = 10, H = 12, A = 13, NF = 14 }; };
+template <> struct RecLayout<HPB_MODEL_NS3D> { enum { NV = 5, U = 0, F = 5, V4 = 10, SR = 11, VEL = 12, H = 15, A = 16, NF = 17 }; };
 
 template <int MODEL, bool GRAV, bool VISC>
-constexpr int rec_fields()
+struct SweepLayout {
+  using RL = RecLayout<MODEL>;
+  static constexpr bool G3 = GRAV && MODEL == HPB_MODEL_NS3D;
+  static constexpr bool V3 = VISC && MODEL == HPB_MODEL_NS3D;
+  static constexpr int NV = RL::NV;
+  static constexpr int GFI = RL::NF;                       // record fields: gravity f, g
+  static constexpr int FVI = RL::NF + (G3 ? 2 : 0);        // record fields: viscous flux (4)
+  static constexpr int NFREC = FVI + (V3 ? 4 : 0);
+  static constexpr int SGI = NV;                           // staging fields: gravity f, g
+  static constexpr int SQI = NV + (G3 ? 2 : 0);            // staging fields: 8 derivative scalars
+  static constexpr int NFSTG = SQI + (V3 ? 8 : 0);
+  static constexpr int NFL = 2 * NV + (G3 ? 2 : 0);        // exchange: left-biased fL, uL (, sL x2)
+  static constexpr int NFF = NV + (G3 ? 2 : 0);            // exchange: interface flux (, S x2)
+  static constexpr size_t smem_bytes = sizeof(double) * ((size_t)NFREC * NREC + (size_t)NFSTG * NSTG + (size_t)(NFL + NFF) * NEX);
+};
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src)
 {
-  return RecLayout<MODEL>::NF + ((GRAV && MODEL == HPB_MODEL_NS3D) ? 2 : 0) + ((VISC && MODEL == HPB_MODEL_NS3D) ? 4 : 0);
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(s), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// exchange buffers: per reconstruction cell: right-biased values fR, uR (+ sR x2) ; interface flux (+ S x2)
-template <int MODEL, bool GRAV>
-constexpr int exch_fields() { return 3 * RecLayout<MODEL>::NV + ((GRAV && MODEL == HPB_MODEL_NS3D) ? 4 : 0); }
-
-template <int MODEL, bool GRAV, bool VISC>
-constexpr size_t sweep_smem_bytes()
-{
-  return sizeof(double) * ((size_t)rec_fields<MODEL, GRAV, VISC>() * SC * TW + (size_t)exch_fields<MODEL, GRAV>() * NT);
-}
-
-// MAPX: true  -> lanes run along the sweep line (x-sweep);
-//       false -> 8 consecutive threads = 8 x-contiguous lines (y-, z-sweeps)
-// VISC (NavierStokes3D): the viscous flux of the sweep direction is evaluated per stencil cell from the
-// derivative arrays of viscous_fused.cu and its fourth-order central derivative is added to `out`
-// (NavierStokes3DParabolicFunction.c:152-208, :210-261, :263-314)
-template <int MODEL, int WT, bool MAPX, bool GRAV, bool VISC>
+// LOADX: the cooperative global<->shared mapping runs lanes along the sweep line (x-sweep: the line itself is
+//        contiguous); otherwise 8 consecutive threads = the 8 x-adjacent lines of the CTA (y-, z-sweeps).
+template <int MODEL, int WT, bool LOADX, bool GRAV, bool VISC>
 __global__ void __launch_bounds__(NT, 2) k_sweep(const SweepArgs a)
 {
+  using SL = SweepLayout<MODEL, GRAV, VISC>;
   using RL = RecLayout<MODEL>;
   constexpr int NV = RL::NV;
   constexpr bool FLUID = (MODEL != HPB_MODEL_LINEAR_ADR);
-  constexpr bool G3 = GRAV && MODEL == HPB_MODEL_NS3D;
-  constexpr bool V3 = VISC && MODEL == HPB_MODEL_NS3D;
-  constexpr int FVI = RL::NF + (G3 ? 2 : 0);          // record fields of the viscous flux (4)
-  constexpr int NCELL = SC * TW;
+  constexpr bool G3 = SL::G3, V3 = SL::V3;
   extern __shared__ double smem[];
   double* rec = smem;
-  double* exR = smem + rec_fields<MODEL, GRAV, VISC>() * NCELL;      // [2*NV (+2)][NT]
-  double* exF = exR + (2 * NV + (G3 ? 2 : 0)) * NT;            // [NV (+2)][NT]
+  double* stg = rec + SL::NFREC * NREC;
+  double* exL = stg + SL::NFSTG * NSTG;
+  double* exF = exL + SL::NFL * NEX;
 
   const Geom& G = a.G;
   const int dir = a.dir;
   const int N = G.N[dir];
   const long long st = G.st[dir];
+  const long long npg = G.npg;
   const int tid = threadIdx.x;
-  const int j0 = blockIdx.y * OUTL;                     // first output cell of this chunk
+  const int w = tid >> 5, l = tid & 31;                      // compute mapping: warp = line, lane = cell of the step
+  const int lw = LOADX ? w : (tid & (TW - 1));               // cooperative mapping
+  const int ll = LOADX ? l : (tid >> 3);
   const int line0 = blockIdx.x * TW;
+  const bool accumulate = (a.mode & 1) != 0;
 
   // line -> offset of its cell j = 0 in the ghost-padded array
   auto line_base = [&](int line) -> long long {
@@ -228,213 +255,269 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const SweepArgs a)
     else               { ia = line % G.N[0]; ib = line / G.N[0]; p = (ia + G.g) + (long long)G.P[0] * ((ib + G.g) + (long long)G.P[1] * G.g); }
     return p;
   };
-  auto cidx = [&](int l, int w) -> int { return MAPX ? (w * SC + l) : (l * TW + w); };
-
+  const bool line_ok = (line0 + w) < a.nlines;
+  const bool lline_ok = (line0 + lw) < a.nlines;
+  const long long lbase = lline_ok ? line_base(line0 + lw) : 0;
   const double gamma = a.ph.gamma;
+  const int M = (N + TL - 1) / TL;
+  const int sidx_c = LOADX ? (lw * TL + ll) : (ll * SS + lw);   // staging slot, cooperative mapping
+  const int sidx_p = LOADX ? (w * TL + l) : (l * SS + w);       // staging slot, compute mapping
+  const int rbase = w * RP;                                      // this warp's records
+  const int xbase = w * XP;                                      // this warp's exchange slots
 
-  // ---------------- phase 1: records of the stencil cells
-  for (int c = tid; c < NCELL; c += NT) {
-    int l, w;
-    if (MAPX) { l = c % SC; w = c / SC; } else { w = c % TW; l = c / TW; }
-    const int j = j0 - 3 + l;
-    const int line = line0 + w;
-    if (line >= a.nlines || j > N + 2) continue;
-    const long long p = line_base(line) + (long long)j * st;
-    const int ci = cidx(l, w);
-    double U[NV];
+  auto prefetch = [&](int m) {
+    const int c = TL * m + 3 + ll;
+    if (lline_ok && c >= -3 && c <= N + 2) {
+      const long long p = lbase + (long long)c * st;
+      double* d = stg + sidx_c;
 #pragma unroll
-    for (int v = 0; v < NV; v++) U[v] = a.u[v * G.npg + p];
+      for (int v = 0; v < NV; v++) cp_async8(d + v * NSTG, a.u + v * npg + p);
+      if (G3) { cp_async8(d + SL::SGI * NSTG, a.gf + p); cp_async8(d + (SL::SGI + 1) * NSTG, a.gg + p); }
+      if (V3) {
 #pragma unroll
-    for (int v = 0; v < NV; v++) rec[(RL::U + v) * NCELL + ci] = U[v];
-    if (!FLUID) {
-      rec[RL::F * NCELL + ci] = a.ph.adv[dir] * U[0];
-    } else {
-      constexpr int NDV = NV - 2;
-      const double rho = U[0];
-      double vel[3] = { 0.0, 0.0, 0.0 };
-      const double rinv = 1.0 / rho;
-#pragma unroll
-      for (int k = 0; k < NDV; k++) vel[k] = (rho == 0) ? 0.0 : U[1 + k] * rinv;
-      double vsq = 0.0;
-#pragma unroll
-      for (int k = 0; k < NDV; k++) vsq += vel[k] * vel[k];
-      const double e = U[NV - 1];
-      const double ke = 0.5 * rho * vsq;
-      const double P = (e - ke) * (gamma - 1.0);
-      const double vn = (dir == 0) ? vel[0] : (dir == 1 ? vel[1] : vel[2]);
-      rec[(RL::F + 0) * NCELL + ci] = rho * vn;
-#pragma unroll
-      for (int k = 0; k < NDV; k++) rec[(RL::F + 1 + k) * NCELL + ci] = rho * vn * vel[k] + (k == dir ? P : 0.0);
-      rec[(RL::F + NV - 1) * NCELL + ci] = (e + P) * vn;
-      double gfv = 1.0, ggv = 1.0;
-      if (G3) { gfv = a.gf[p]; ggv = a.gg[p]; rec[RL::GF * NCELL + ci] = gfv; rec[RL::GG * NCELL + ci] = ggv; }
-      const double igm1 = 1.0 / (gamma - 1.0);
-      rec[RL::V4 * NCELL + ci] = G3 ? ((P * igm1) * (1.0 / ggv) + ke * gfv) : (P * igm1 + ke);
-      const double c2 = gamma * P * rinv;
-      rec[RL::SR * NCELL + ci] = sqrt(rho);
-#pragma unroll
-      for (int k = 0; k < NDV; k++) rec[(RL::VEL + k) * NCELL + ci] = vel[k];
-      rec[RL::H * NCELL + ci] = 0.5 * vsq + c2 * igm1;
-      rec[RL::A * NCELL + ci] = sqrt(c2) + fabs(vn);
-      if (V3 && l >= 1 && l <= TL + 2) {
-        // viscous flux of direction dir at this cell: mu = T^0.76 (raiseto, math_ops.h:37), T = gamma P / rho
-        const double T = gamma * P / rho;
-        const double mu = exp(0.76 * log(T));
-        const double two_third = 2.0 / 3.0;
-        const double muRe = mu * (1.0 / a.ph.Re);
-        const double kq = muRe * igm1 * (1.0 / a.ph.Pr);
-        const long long n = G.npg;
-        const double* qx = a.qd + p;              // + (0*4 + c) * n
-        const double* qy = a.qd + 4 * n + p;
-        const double* qz = a.qd + 8 * n + p;
-        double t1, t2, t3, q;
-        if (dir == 0) {
-          const double ux = qx[0], vx = qx[n], wx = qx[2*n], Tx = qx[3*n];
-          const double uy = qy[0], vy = qy[n], uz = qz[0], wz = qz[2*n];
-          t1 = two_third * muRe * (2 * ux - vy - wz); t2 = muRe * (uy + vx); t3 = muRe * (uz + wx); q = kq * Tx;
-        } else if (dir == 1) {
-          const double uy = qy[0], vy = qy[n], wy = qy[2*n], Ty = qy[3*n];
-          const double ux = qx[0], vx = qx[n], vz = qz[n], wz = qz[2*n];
-          t1 = muRe * (uy + vx); t2 = two_third * muRe * (-ux + 2 * vy - wz); t3 = muRe * (vz + wy); q = kq * Ty;
-        } else {
-          const double uz = qz[0], vz = qz[n], wz = qz[2*n], Tz = qz[3*n];
-          const double ux = qx[0], wx = qx[2*n], vy = qy[n], wy = qy[2*n];
-          t1 = muRe * (uz + wx); t2 = muRe * (vz + wy); t3 = two_third * muRe * (-ux - vy + 2 * wz); q = kq * Tz;
-        }
-        rec[(FVI + 0) * NCELL + ci] = t1;
-        rec[(FVI + 1) * NCELL + ci] = t2;
-        rec[(FVI + 2) * NCELL + ci] = t3;
-        rec[(FVI + 3) * NCELL + ci] = vel[0] * t1 + vel[1] * t2 + vel[2] * t3 + q;
+        for (int k = 0; k < 8; k++) cp_async8(d + (SL::SQI + k) * NSTG, a.qd + (long long)a.qidx[k] * npg + p);
       }
     }
-  }
-  __syncthreads();
-
-  // ---------------- phase 2: both reconstructions of the centred stencil of cell j
-  int l, w;
-  if (MAPX) { l = tid % TL; w = tid / TL; } else { w = tid % TW; l = tid / TW; }
-  const int j = j0 - 1 + l;                 // reconstruction cell
-  const int line = line0 + w;
-  const bool line_ok = line < a.nlines;
-  const bool rc_ok = line_ok && j <= N;     // j >= -1 always
-  const int cc = cidx(l + 2, w);            // record index of cell j
-  const int cs = MAPX ? 1 : TW;             // record stride along the line
-  double fLv[NV], uLv[NV], sL[2] = { 0.0, 0.0 };
-  if (rc_ok) {
-    double Zg[5] = { 0, 0, 0, 0, 0 };
-    if (G3) {
+    cp_async_commit();
+  };
+  // results of step m are staged in the exchange slots 1..32 of fields 0..NV-1 (free after P3) and written to
+  // global by the cooperative mapping at the top of step m+1: cell 32m+ll of line lw
+  double old[NV];
 #pragma unroll
-      for (int k = 0; k < 5; k++) Zg[k] = rec[RL::GG * NCELL + cc + (k - 2) * cs];
+  for (int v = 0; v < NV; v++) old[v] = 0.0;
+  auto request_old = [&](int m) {
+    const int jo = TL * m + ll;
+    if (accumulate && lline_ok && jo >= 0 && jo < N) {
+      const long long po = lbase + (long long)jo * st;
+#pragma unroll
+      for (int v = 0; v < NV; v++) old[v] = a.out[v * npg + po];
     }
+  };
+  auto flush = [&](int m) {
+    const int jo = TL * m + ll;
+    if (lline_ok && jo >= 0 && jo < N) {
+      const long long po = lbase + (long long)jo * st;
+      const int xs = lw * XP + 1 + ll;
 #pragma unroll
-    for (int v = 0; v < NV; v++) {
-      double X[5], Y[5], R, zl, zr;
+      for (int v = 0; v < NV; v++) a.out[v * npg + po] = old[v] + exL[v * NEX + xs];
+    }
+  };
+
+  prefetch(-1);
+  for (int m = -1; m < M; m++) {
+    cp_async_wait_all();
+    __syncthreads();                 // B1: staging of step m visible; results of step m-1 staged
+
+    if (m >= 0) flush(m - 1);        // (step -1 stages nothing)
+
+    // ---------------- P1: record of cell c1 = 32m+3+l (record position 5+l)
+    const int c1 = TL * m + 3 + l;
+    if (line_ok && c1 >= -3 && c1 <= N + 2) {
+      const double* s = stg + sidx_p;
+      const int ci = rbase + 5 + l;
+      double U[NV];
 #pragma unroll
-      for (int k = 0; k < 5; k++) X[k] = rec[(RL::F + v) * NCELL + cc + (k - 2) * cs];
-      const bool zsrc = G3 && a.with_source && (v == dir + 1 || v == NV - 1);
-      if (G3 && zsrc) {
-        recon_pair<WT, true>(X, X, Zg, a.ph.eps, fLv[v], R, zl, zr);
-        const int s = (v == NV - 1) ? 1 : 0;
-        sL[s] = zl;
-        exR[(2 * NV + s) * NT + tid] = zr;
+      for (int v = 0; v < NV; v++) U[v] = s[v * NSTG];
+#pragma unroll
+      for (int v = 0; v < NV; v++) rec[(RL::U + v) * NREC + ci] = U[v];
+      if (!FLUID) {
+        rec[RL::F * NREC + ci] = a.ph.adv[dir] * U[0];
       } else {
-        recon_pair<WT, false>(X, X, X, a.ph.eps, fLv[v], R, zl, zr);
-      }
-      exR[v * NT + tid] = R;
-      // solution: weights from raw u, applied to the modified solution (Q4)
+        constexpr int NDV = NV - 2;
+        const double rho = U[0];
+        double vel[3] = { 0.0, 0.0, 0.0 };
+        const double rinv = 1.0 / rho;
 #pragma unroll
-      for (int k = 0; k < 5; k++) X[k] = rec[(RL::U + v) * NCELL + cc + (k - 2) * cs];
-      if (FLUID && (G3 || v == NV - 1)) {
+        for (int k = 0; k < NDV; k++) vel[k] = (rho == 0) ? 0.0 : U[1 + k] * rinv;
+        double vsq = 0.0;
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-          if (v == NV - 1) Y[k] = rec[RL::V4 * NCELL + cc + (k - 2) * cs];
-          else Y[k] = X[k] * rec[RL::GF * NCELL + cc + (k - 2) * cs];
+        for (int k = 0; k < NDV; k++) vsq += vel[k] * vel[k];
+        const double e = U[NV - 1];
+        const double ke = 0.5 * rho * vsq;
+        const double P = (e - ke) * (gamma - 1.0);
+        const double vn = (dir == 0) ? vel[0] : (dir == 1 ? vel[1] : vel[2]);
+        rec[(RL::F + 0) * NREC + ci] = rho * vn;
+#pragma unroll
+        for (int k = 0; k < NDV; k++) rec[(RL::F + 1 + k) * NREC + ci] = rho * vn * vel[k] + (k == dir ? P : 0.0);
+        rec[(RL::F + NV - 1) * NREC + ci] = (e + P) * vn;
+        double gfv = 1.0, ggv = 1.0;
+        if (G3) {
+          gfv = s[SL::SGI * NSTG]; ggv = s[(SL::SGI + 1) * NSTG];
+          rec[SL::GFI * NREC + ci] = gfv; rec[(SL::GFI + 1) * NREC + ci] = ggv;
         }
-        recon_pair<WT, false>(X, Y, Y, a.ph.eps, uLv[v], R, zl, zr);
-      } else {
-        recon_pair<WT, false>(X, X, X, a.ph.eps, uLv[v], R, zl, zr);
-      }
-      exR[(NV + v) * NT + tid] = R;
-    }
-  }
-  __syncthreads();
-
-  // ---------------- phase 3: interface j+1/2 (between cells j and j+1): upwind flux
-  const int tnb = MAPX ? tid + 1 : tid + TW;        // thread of cell j+1
-  const bool if_ok = rc_ok && (l < TL - 1) && (j + 1 <= N);
-  if (if_ok) {
-    double fh[NV];
-    if (!FLUID) {
-      fh[0] = (a.ph.adv[dir] > 0) ? fLv[0] : exR[0 * NT + tnb];
-    } else {
-      constexpr int NDV = NV - 2;
-      const int cL = cc, cR = cc + cs;
-      const double tL = rec[RL::SR * NCELL + cL], tR = rec[RL::SR * NCELL + cR];
-      const double rs = 1.0 / (tL + tR);
-      double vsq = 0.0, vn = 0.0;
+        const double igm1 = 1.0 / (gamma - 1.0);
+        rec[RL::V4 * NREC + ci] = G3 ? ((P * igm1) * (1.0 / ggv) + ke * gfv) : (P * igm1 + ke);
+        const double c2 = gamma * P * rinv;
+        rec[RL::SR * NREC + ci] = sqrt(rho);
 #pragma unroll
-      for (int k = 0; k < NDV; k++) {
-        const double v = (tL * rec[(RL::VEL + k) * NCELL + cL] + tR * rec[(RL::VEL + k) * NCELL + cR]) * rs;
-        vsq += v * v;
-        if (k == dir) vn = v;
+        for (int k = 0; k < NDV; k++) rec[(RL::VEL + k) * NREC + ci] = vel[k];
+        rec[RL::H * NREC + ci] = 0.5 * vsq + c2 * igm1;
+        rec[RL::A * NREC + ci] = sqrt(c2) + fabs(vn);
+        if (V3) {
+          // viscous flux of direction dir from the (mu/Re)-weighted derivatives (viscous_fused.cu)
+          double q[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) q[k] = s[(SL::SQI + k) * NSTG];
+          const double two_third = 2.0 / 3.0;
+          const double kq = igm1 * (1.0 / a.ph.Pr);
+          double t1, t2, t3;
+          if (dir == 0)      { t1 = two_third * (2 * q[0] - q[5] - q[7]); t2 = q[4] + q[1]; t3 = q[6] + q[2]; }
+          else if (dir == 1) { t1 = q[0] + q[5]; t2 = two_third * (-q[4] + 2 * q[1] - q[7]); t3 = q[6] + q[2]; }
+          else               { t1 = q[0] + q[5]; t2 = q[1] + q[7]; t3 = two_third * (-q[4] - q[6] + 2 * q[2]); }
+          rec[(SL::FVI + 0) * NREC + ci] = t1;
+          rec[(SL::FVI + 1) * NREC + ci] = t2;
+          rec[(SL::FVI + 2) * NREC + ci] = t3;
+          rec[(SL::FVI + 3) * NREC + ci] = vel[0] * t1 + vel[1] * t2 + vel[2] * t3 + kq * q[3];
+        }
       }
-      const double H = (tL * rec[RL::H * NCELL + cL] + tR * rec[RL::H * NCELL + cR]) * rs;
-      const double cavg = sqrt((gamma - 1.0) * (H - 0.5 * vsq));
-      const double aavg = cavg + fabs(vn);
-      double alpha = fmax(fmax(rec[RL::A * NCELL + cL], rec[RL::A * NCELL + cR]), aavg);
-      if (G3) alpha *= fmax(rec[RL::GG * NCELL + cL], rec[RL::GG * NCELL + cR]);
+    }
+    __syncthreads();                         // B2: staging and staged results consumed
+    if (m + 1 < M) prefetch(m + 1);          // overlaps P2..P4
+    request_old(m);                          // old values of the cells this step updates: in flight until the next B1
+
+    // ---------------- P2: both reconstructions of the centred stencil of cell j = 32m+1+l (position l+3)
+    const int j = TL * m + 1 + l;
+    const bool rc_ok = line_ok && j >= -1 && j <= N;
+    const int cc = rbase + l + 3;
+    double fRv[NV], uRv[NV], sR[2] = { 0.0, 0.0 };
+    if (rc_ok) {
+      double Zg[5] = { 0, 0, 0, 0, 0 };
+      if (G3) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) Zg[k] = rec[(SL::GFI + 1) * NREC + cc + (k - 2)];
+      }
+      const int ex = xbase + l + 1;
 #pragma unroll
       for (int v = 0; v < NV; v++) {
-        const double fR = exR[v * NT + tnb], uR = exR[(NV + v) * NT + tnb];
-        fh[v] = 0.5 * (fLv[v] + fR) - alpha * (0.5 * (uR - uLv[v]));
+        double X[5], Y[5], L, zl, zr;
+#pragma unroll
+        for (int k = 0; k < 5; k++) X[k] = rec[(RL::F + v) * NREC + cc + (k - 2)];
+        const bool zsrc = G3 && a.with_source && (v == dir + 1 || v == NV - 1);
+        if (G3 && zsrc) {
+          recon_pair<WT, true>(X, X, Zg, a.ph.eps, L, fRv[v], zl, zr);
+          const int sidx = (v == NV - 1) ? 1 : 0;
+          sR[sidx] = zr;
+          exL[(2 * NV + sidx) * NEX + ex] = zl;
+        } else {
+          recon_pair<WT, false>(X, X, X, a.ph.eps, L, fRv[v], zl, zr);
+        }
+        exL[v * NEX + ex] = L;
+        // solution: weights from raw u, applied to the modified solution (Q4)
+#pragma unroll
+        for (int k = 0; k < 5; k++) X[k] = rec[(RL::U + v) * NREC + cc + (k - 2)];
+        if (FLUID && (G3 || v == NV - 1)) {
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            if (v == NV - 1) Y[k] = rec[RL::V4 * NREC + cc + (k - 2)];
+            else Y[k] = X[k] * rec[SL::GFI * NREC + cc + (k - 2)];
+          }
+          recon_pair<WT, false>(X, Y, Y, a.ph.eps, L, uRv[v], zl, zr);
+        } else {
+          recon_pair<WT, false>(X, X, X, a.ph.eps, L, uRv[v], zl, zr);
+        }
+        exL[(NV + v) * NEX + ex] = L;
       }
     }
+    __syncwarp();
+
+    // ---------------- P3: interface j-1/2 (between cells j-1 and j): upwind flux
+    const bool if_ok = line_ok && j >= 0 && j <= N;
+    double fh[NV], Sh[2] = { 0.0, 0.0 };
 #pragma unroll
-    for (int v = 0; v < NV; v++) exF[v * NT + tid] = fh[v];
-    if (G3 && a.with_source) {
-      exF[(NV + 0) * NT + tid] = 0.5 * (sL[0] + exR[(2 * NV + 0) * NT + tnb]);
-      exF[(NV + 1) * NT + tid] = 0.5 * (sL[1] + exR[(2 * NV + 1) * NT + tnb]);
+    for (int v = 0; v < NV; v++) fh[v] = 0.0;
+    if (if_ok) {
+      const int exl = xbase + l;              // left-biased values of cell j-1 (slot 0: carry)
+      if (!FLUID) {
+        fh[0] = (a.ph.adv[dir] > 0) ? exL[0 * NEX + exl] : fRv[0];
+      } else {
+        constexpr int NDV = NV - 2;
+        const int cL = cc - 1, cR = cc;
+        const double tL = rec[RL::SR * NREC + cL], tR = rec[RL::SR * NREC + cR];
+        const double rs = 1.0 / (tL + tR);
+        double vsq = 0.0, vn = 0.0;
+#pragma unroll
+        for (int k = 0; k < NDV; k++) {
+          const double v = (tL * rec[(RL::VEL + k) * NREC + cL] + tR * rec[(RL::VEL + k) * NREC + cR]) * rs;
+          vsq += v * v;
+          if (k == dir) vn = v;
+        }
+        const double H = (tL * rec[RL::H * NREC + cL] + tR * rec[RL::H * NREC + cR]) * rs;
+        const double cavg = sqrt((gamma - 1.0) * (H - 0.5 * vsq));
+        const double aavg = cavg + fabs(vn);
+        double alpha = fmax(fmax(rec[RL::A * NREC + cL], rec[RL::A * NREC + cR]), aavg);
+        if (G3) alpha *= fmax(rec[(SL::GFI + 1) * NREC + cL], rec[(SL::GFI + 1) * NREC + cR]);
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          const double fL = exL[v * NEX + exl], uL = exL[(NV + v) * NEX + exl];
+          fh[v] = 0.5 * (fL + fRv[v]) - alpha * (0.5 * (uRv[v] - uL));
+        }
+      }
+      const int exo = xbase + l + 1;
+#pragma unroll
+      for (int v = 0; v < NV; v++) exF[v * NEX + exo] = fh[v];
+      if (G3 && a.with_source) {
+        Sh[0] = 0.5 * (exL[(2 * NV + 0) * NEX + exl] + sR[0]);
+        Sh[1] = 0.5 * (exL[(2 * NV + 1) * NEX + exl] + sR[1]);
+        exF[(NV + 0) * NEX + exo] = Sh[0];
+        exF[(NV + 1) * NEX + exo] = Sh[1];
+      }
     }
+    __syncwarp();
+    // carry of the left-biased values (slot 32 -> slot 0) before the slots 1..32 are reused for the results
+    if (l < SL::NFL) exL[l * NEX + xbase] = exL[l * NEX + xbase + TL];
+    __syncwarp();
+
+    // ---------------- P4: cell jo = j-1 = 32m+l (position l+2): interfaces j-1/2 (own) and j-3/2 (neighbour / carry)
+    const int jo = j - 1;
+    if (line_ok && jo >= 0 && jo < N) {
+      const int exl = xbase + l;
+      const int co = cc - 1;
+      const double dxi = a.dxinv[G.xoff[dir] + G.g + jo];
+      double res[NV];
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        const double t = dxi * (fh[v] - exF[v * NEX + exl]);
+        res[v] = (a.mode < 2) ? -t : t;
+      }
+      if (V3) {
+        // par_v += dxinv * (FV[j-2] - 8 FV[j-1] + 8 FV[j+1] - FV[j+2]) / 12   (components 1..4)
+        const double s12 = 1.0 / 12.0;
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          const double* f = rec + (SL::FVI + v) * NREC + co;
+          const double dfv = (f[-2] - 8 * f[-1] + 8 * f[1] - f[2]) * s12;
+          res[1 + v] += dxi * dfv;
+        }
+      }
+      if (G3 && a.with_source) {
+        // NavierStokes3DSource.c:80-100 (the source accumulates into the same array as the flux divergence)
+        const double rho = rec[RL::U * NREC + co];
+        const double vd = rec[(RL::VEL + dir) * NREC + co];
+        const double f = rec[SL::GFI * NREC + co];
+        const double tm = rho * a.ph.RT, te = rho * a.ph.RT * vd;
+        const double sm = (tm * f) * (Sh[0] - exF[(NV + 0) * NEX + exl]) * dxi;
+        const double se = (te * f) * (Sh[1] - exF[(NV + 1) * NEX + exl]) * dxi;
+#pragma unroll
+        for (int v = 1; v < NV; v++) res[v] += ((v == dir + 1) ? sm : 0.0) + ((v == NV - 1) ? se : 0.0);
+      }
+#pragma unroll
+      for (int v = 0; v < NV; v++) exL[v * NEX + xbase + 1 + l] = res[v];      // staged for the cooperative store
+    }
+    __syncwarp();
+
+    // ---------------- shift (warp-private): the last 5 records and the interface-flux carry move to the front
+    for (int i = l; i < SL::NFREC * 5; i += 32) {
+      const int f = i / 5, r = i % 5;
+      rec[f * NREC + rbase + r] = rec[f * NREC + rbase + TL + r];
+    }
+    if (l < SL::NFF) exF[l * NEX + xbase] = exF[l * NEX + xbase + TL];
+    __syncwarp();
   }
   __syncthreads();
-
-  // ---------------- phase 4: flux difference of cell j (interfaces j+1/2: own, j-1/2: thread of cell j-1)
-  if (line_ok && l >= 1 && l <= OUTL && j < N) {
-    const int tpv = MAPX ? tid - 1 : tid - TW;
-    const long long p = line_base(line) + (long long)j * st;
-    const double dxi = a.dxinv[G.xoff[dir] + G.g + j];
-#pragma unroll
-    for (int v = 0; v < NV; v++) {
-      const double t = dxi * (exF[v * NT + tid] - exF[v * NT + tpv]);
-      const long long q = v * G.npg + p;
-      if (a.mode == 0) a.out[q] = -t;
-      else if (a.mode == 1) a.out[q] -= t;
-      else if (a.mode == 2) a.out[q] = t;
-      else a.out[q] += t;
-    }
-    if (V3) {
-      // par_v += dxinv * (FV[j-2] - 8 FV[j-1] + 8 FV[j+1] - FV[j+2]) / 12   (components 1..4)
-      const double s12 = 1.0 / 12.0;
-#pragma unroll
-      for (int v = 0; v < 4; v++) {
-        const double* f = rec + (FVI + v) * NCELL + cc;
-        const double dfv = (f[-2 * cs] - 8 * f[-cs] + 8 * f[cs] - f[2 * cs]) * s12;
-        a.out[(1 + v) * G.npg + p] += dxi * dfv;
-      }
-    }
-    if (G3 && a.with_source) {
-      // NavierStokes3DSource.c:80-100
-      const double rho = rec[RL::U * NCELL + cc];
-      const double vd = rec[(RL::VEL + dir) * NCELL + cc];
-      const double f = rec[RL::GF * NCELL + cc];
-      const double tm = rho * a.ph.RT, te = rho * a.ph.RT * vd;
-      a.src[(1 + dir) * G.npg + p] += (tm * f) * (exF[(NV + 0) * NT + tid] - exF[(NV + 0) * NT + tpv]) * dxi;
-      a.src[(NV - 1) * G.npg + p]  += (te * f) * (exF[(NV + 1) * NT + tid] - exF[(NV + 1) * NT + tpv]) * dxi;
-    }
-  }
+  flush(M - 1);
 }
 
-// host-side launcher of one (MODEL, WT) family; defined in sweep_fused_wt.inc per weight type
+// host-side launcher of one (MODEL, WT) family; defined in sweep_fused_inst.cuh per weight type
 template <int WT>
 bool launch_sweep(hpb_solver* h, const SweepArgs& a);
 

@@ -8,7 +8,7 @@ namespace hpbf {
 template <int MODEL, int WT, bool MAPX, bool GRAV, bool VISC>
 static bool launch_one(hpb_solver* h, const SweepArgs& a)
 {
-  constexpr size_t smem = sweep_smem_bytes<MODEL, GRAV, VISC>();
+  constexpr size_t smem = SweepLayout<MODEL, GRAV, VISC>::smem_bytes;
   static bool configured = false;
   auto kern = k_sweep<MODEL, WT, MAPX, GRAV, VISC>;
   if (!configured) {
@@ -18,9 +18,7 @@ static bool launch_one(hpb_solver* h, const SweepArgs& a)
     }
     configured = true;
   }
-  const int N = a.G.N[a.dir];
-  dim3 grid((a.nlines + TW - 1) / TW, (N + OUTL - 1) / OUTL, 1);
-  if (grid.y > 65535u) return false;
+  dim3 grid((a.nlines + TW - 1) / TW, 1, 1);
   kern<<<grid, NT, smem, h->stream>>>(a);
   h->launches++;
   return true;

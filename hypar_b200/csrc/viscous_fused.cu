@@ -3,8 +3,9 @@
 // The reference evaluates the parabolic term in ~20 passes over memory (Q, three QDeriv arrays, per
 // direction FViscous and FDeriv, all ghost-padded 5-component temporaries calloc'ed per call). Here:
 //   (1) k_qderiv3 (this file): ONE kernel writes the scaled first derivatives of (u, v, w, T) in all three
-//       directions (12 scalars per point; the density derivative is never used). Q is evaluated in
-//       registers from the conserved variables.
+//       directions (12 scalars per point; the density derivative is never used), each multiplied by the
+//       local mu/Re, mu = T^0.76 -- every term of the viscous flux is (mu/Re) x a derivative, so the sweeps
+//       need neither the viscosity nor exp/log. Q is evaluated in registers from the conserved variables.
 //   (2) [halo exchange of the x- and y-derivative arrays; the z-derivatives are NOT exchanged: quirk Q1]
 //   (3) the viscous flux of direction d and its derivative are evaluated INSIDE the hyperbolic sweep
 //       kernel of direction d (sweep_fused.cuh, VISC = true), whose tile already holds the stencil cells.
@@ -19,7 +20,7 @@ namespace {
 
 struct QD3Args {
   Geom G;
-  double gamma;
+  double gamma, inv_Re;
   const double* u;
   const double* dxinv;
   double* qd;          // [dir][comp 0..3 = u, v, w, T][npg]
@@ -49,6 +50,10 @@ __global__ void __launch_bounds__(128) k_qderiv3(const QD3Args a)
   const int idx[3] = { i, j, k };
   const bool inn[3] = { in0, in1, in2 };
   const double s12 = 1.0 / 12.0;
+  // mu/Re at this point: mu = exp(0.76 log T) (raiseto, math_ops.h:37; NavierStokes3DParabolicFunction.c:174)
+  double qc[4];
+  prim4(a.u, G.npg, p, a.gamma, qc);
+  const double muRe = exp(0.76 * log(qc[3])) * a.inv_Re;
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     // transverse indices must be interior
@@ -76,7 +81,7 @@ __global__ void __launch_bounds__(128) k_qderiv3(const QD3Args a)
 #pragma unroll
       for (int c = 0; c < 4; c++) D[c] = (fm2[c] - 8 * fm1[c] + 8 * fp1[c] - fp2[c]) * s12;
     }
-    const double dxi = a.dxinv[G.xoff[d] + g + x];
+    const double dxi = a.dxinv[G.xoff[d] + g + x] * muRe;
 #pragma unroll
     for (int c = 0; c < 4; c++) a.qd[(long long)(d * 4 + c) * G.npg + p] = D[c] * dxi;
   }
@@ -106,7 +111,7 @@ void qderiv_fused(hpb_solver* h, const double* u)
 {
   ProfScope ps(h, HPB_PROF_VISCOUS);
   const Geom& G = h->geo;
-  QD3Args a; a.G = G; a.gamma = h->phys.gamma; a.u = u; a.dxinv = h->d_dxinv; a.qd = h->d_qd4;
+  QD3Args a; a.G = G; a.gamma = h->phys.gamma; a.inv_Re = 1.0 / h->phys.Re; a.u = u; a.dxinv = h->d_dxinv; a.qd = h->d_qd4;
   dim3 grid((G.P[0] + 127) / 128, G.P[1], G.P[2]);
   k_qderiv3<<<grid, 128, 0, h->stream>>>(a);
   h->launches++;
