@@ -333,16 +333,21 @@ __global__ void k_ns_qderiv(Geom G, double gamma, const double* __restrict__ dxi
 #pragma unroll
     for (int v = 0; v < NV; v++) f[v][k + 4] = Q[v];
   }
-  const double dxi = dxinv[G.xoff[dir] + g + i];
+  // un-scaled, as FirstDerivativePar leaves it: the reference exchanges the halos first and THEN scales every
+  // point, ghosts included, by the LOCAL dxinv (NavierStokes3DParabolicFunction.c:125-146); on a periodic wrap
+  // the receiver's ghost dxinv is a copy of its first interior value, not the sender's -- the scaling is applied
+  // where the derivatives are consumed (fviscous_fn)
+  (void)dxinv;
 #pragma unroll
-  for (int v = 0; v < NV; v++) QD[v * G.npg + p] = d1_coeffs(i, N, g, &f[v][4]) * dxi;
+  for (int v = 0; v < NV; v++) QD[v * G.npg + p] = d1_coeffs(i, N, g, &f[v][4]);
 }
 
 // viscous flux of direction dir at one point (NavierStokes3DParabolicFunction.c:152-195 etc.)
 template <int MODEL>
 __device__ __forceinline__ void fviscous_fn(const Phys& ph, const Geom& G, const double* __restrict__ u,
                                             const double* __restrict__ QDx, const double* __restrict__ QDy,
-                                            const double* __restrict__ QDz, long long p, int dir, double* FV)
+                                            const double* __restrict__ QDz, long long p, int dir,
+                                            double dxi, double dyi, double dzi, double* FV)
 {
   constexpr int NV = ModelTraits<MODEL>::NV;
   const double two_third = 2.0 / 3.0;
@@ -354,40 +359,40 @@ __device__ __forceinline__ void fviscous_fn(const Phys& ph, const Geom& G, const
   const long long n = G.npg;
   if (MODEL == HPB_MODEL_NS3D) {
     const double uvel = Q[1], vvel = Q[2], wvel = Q[3];
-    const double ux = QDx[1*n+p], vx = QDx[2*n+p], wx = QDx[3*n+p];
-    const double uy = QDy[1*n+p], vy = QDy[2*n+p], wy = QDy[3*n+p];
-    const double uz = QDz[1*n+p], vz = QDz[2*n+p], wz = QDz[3*n+p];
+    const double ux = QDx[1*n+p] * dxi, vx = QDx[2*n+p] * dxi, wx = QDx[3*n+p] * dxi;
+    const double uy = QDy[1*n+p] * dyi, vy = QDy[2*n+p] * dyi, wy = QDy[3*n+p] * dyi;
+    const double uz = QDz[1*n+p] * dzi, vz = QDz[2*n+p] * dzi, wz = QDz[3*n+p] * dzi;
     double t1, t2, t3, q;
     if (dir == 0) {
       t1 = two_third * (mu*inv_Re) * (2*ux - vy - wz);
       t2 = (mu*inv_Re) * (uy + vx);
       t3 = (mu*inv_Re) * (uz + wx);
-      q  = ( mu*inv_Re * inv_gamma_m1 * inv_Pr ) * QDx[4*n+p];
+      q  = ( mu*inv_Re * inv_gamma_m1 * inv_Pr ) * (QDx[4*n+p] * dxi);
     } else if (dir == 1) {
       t1 = (mu*inv_Re) * (uy + vx);
       t2 = two_third * (mu*inv_Re) * (-ux + 2*vy - wz);
       t3 = (mu*inv_Re) * (vz + wy);
-      q  = ( mu*inv_Re * inv_gamma_m1 * inv_Pr ) * QDy[4*n+p];
+      q  = ( mu*inv_Re * inv_gamma_m1 * inv_Pr ) * (QDy[4*n+p] * dyi);
     } else {
       t1 = (mu*inv_Re) * (uz + wx);
       t2 = (mu*inv_Re) * (vz + wy);
       t3 = two_third * (mu*inv_Re) * (-ux - vy + 2*wz);
-      q  = ( mu*inv_Re * inv_gamma_m1 * inv_Pr ) * QDz[4*n+p];
+      q  = ( mu*inv_Re * inv_gamma_m1 * inv_Pr ) * (QDz[4*n+p] * dzi);
     }
     FV[0] = t1; FV[1] = t2; FV[2] = t3; FV[3] = uvel*t1 + vvel*t2 + wvel*t3 + q;
   } else {
     const double uvel = Q[1], vvel = Q[2];
-    const double ux = QDx[1*n+p], vx = QDx[2*n+p];
-    const double uy = QDy[1*n+p], vy = QDy[2*n+p];
+    const double ux = QDx[1*n+p] * dxi, vx = QDx[2*n+p] * dxi;
+    const double uy = QDy[1*n+p] * dyi, vy = QDy[2*n+p] * dyi;
     double t1, t2, q;
     if (dir == 0) {
       t1 = two_third * (mu*inv_Re) * (2*ux - vy);
       t2 = (mu*inv_Re) * (uy + vx);
-      q  = ( (mu*inv_Re) * inv_gamma_m1 * inv_Pr ) * QDx[3*n+p];
+      q  = ( (mu*inv_Re) * inv_gamma_m1 * inv_Pr ) * (QDx[3*n+p] * dxi);
     } else {
       t1 = (mu*inv_Re) * (uy + vx);
       t2 = two_third * (mu*inv_Re) * (-ux + 2*vy);
-      q  = ( (mu*inv_Re) * inv_gamma_m1 * inv_Pr ) * QDy[3*n+p];
+      q  = ( (mu*inv_Re) * inv_gamma_m1 * inv_Pr ) * (QDy[3*n+p] * dyi);
     }
     FV[0] = t1; FV[1] = t2; FV[2] = uvel*t1 + vvel*t2 + q;
   }
@@ -396,9 +401,9 @@ __device__ __forceinline__ void fviscous_fn(const Phys& ph, const Geom& G, const
 // phase 2a: FV (components 1..NV-1; component 0 is identically zero) for direction dir at the points
 // the interior derivative needs: interior transverse, [-2, N+2) along dir
 template <int MODEL>
-__global__ void k_ns_fviscous(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict__ QDx,
-                              const double* __restrict__ QDy, const double* __restrict__ QDz, int dir,
-                              double* __restrict__ FV)
+__global__ void k_ns_fviscous(Geom G, Phys ph, const double* __restrict__ dxinv, const double* __restrict__ u,
+                              const double* __restrict__ QDx, const double* __restrict__ QDy,
+                              const double* __restrict__ QDz, int dir, double* __restrict__ FV)
 {
   constexpr int NV = ModelTraits<MODEL>::NV;
   int B[3] = { G.N[0], G.N[1], G.N[2] };
@@ -409,7 +414,10 @@ __global__ void k_ns_fviscous(Geom G, Phys ph, const double* __restrict__ u, con
   ii[dir] -= 2;
   const long long p = cell_index(G, ii[0], ii[1], ii[2]);
   double F[NV - 1];
-  fviscous_fn<MODEL>(ph, G, u, QDx, QDy, QDz, p, dir, F);
+  const double dxi = dxinv[G.xoff[0] + G.g + ii[0]];
+  const double dyi = dxinv[G.xoff[1] + G.g + ii[1]];
+  const double dzi = (G.ndims > 2) ? dxinv[G.xoff[2] + G.g + ii[2]] : 1.0;
+  fviscous_fn<MODEL>(ph, G, u, QDx, QDy, QDz, p, dir, dxi, dyi, dzi, F);
 #pragma unroll
   for (int v = 0; v < NV - 1; v++) FV[v * G.npg + p] = F[v];
 }
@@ -897,9 +905,9 @@ void parabolic_phase2(hpb_solver* h, const double* u, double* out, bool accumula
     int B[3] = { G.N[0], G.N[1], G.N[2] };
     B[d] += 4;
     if (h->cfg.model == HPB_MODEL_NS3D)
-      k_ns_fviscous<HPB_MODEL_NS3D><<<grid3(B[0], B[1], B[2]), TPB, 0, h->stream>>>(G, h->phys, u, h->d_QD[0], h->d_QD[1], h->d_QD[2], d, h->d_FV);
+      k_ns_fviscous<HPB_MODEL_NS3D><<<grid3(B[0], B[1], B[2]), TPB, 0, h->stream>>>(G, h->phys, h->d_dxinv, u, h->d_QD[0], h->d_QD[1], h->d_QD[2], d, h->d_FV);
     else
-      k_ns_fviscous<HPB_MODEL_NS2D><<<grid3(B[0], B[1], B[2]), TPB, 0, h->stream>>>(G, h->phys, u, h->d_QD[0], h->d_QD[1], nullptr, d, h->d_FV);
+      k_ns_fviscous<HPB_MODEL_NS2D><<<grid3(B[0], B[1], B[2]), TPB, 0, h->stream>>>(G, h->phys, h->d_dxinv, u, h->d_QD[0], h->d_QD[1], nullptr, d, h->d_FV);
     LAUNCHED(h);
     k_ns_par_accum<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, h->d_dxinv, h->d_FV, d, out); LAUNCHED(h);
   }

@@ -75,7 +75,7 @@ struct SweepArgs {
   int mode;              // 0: out = -div ; 1: out -= div ; 2: out = +div ; 3: out += div
   int with_source;       // add the gravity source of this direction to src
   int nlines;            // number of grid lines along dir
-  const double* qd;      // VISC: (mu/Re) x scaled derivatives of (u,v,w,T): qd[(dir*4 + comp) * npg + p] (viscous_fused.cu)
+  const double* qd;      // VISC: (mu/Re) x first differences of (u,v,w,T): qd[(dir*4 + comp) * npg + p] (viscous_fused.cu)
   int qidx[8];           // VISC: the 8 derivative scalars the viscous flux of `dir` needs (indices dir*4+comp into qd):
                          //   dir 0: ux vx wx Tx | uy vy | uz wz   dir 1: uy vy wy Ty | ux vx | vz wz   dir 2: uz vz wz Tz | ux wx | vy wy
 };
@@ -262,6 +262,16 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const SweepArgs a)
   const int M = (N + TL - 1) / TL;
   const int sidx_c = LOADX ? (lw * TL + ll) : (ll * SS + lw);   // staging slot, cooperative mapping
   const int sidx_p = LOADX ? (w * TL + l) : (l * SS + w);       // staging slot, compute mapping
+  // VISC: dxinv of the two transverse directions of this warp's line, in the order the staged scalars use them
+  // (dir 0: y, z ; dir 1: x, z ; dir 2: x, y)
+  double vsc0 = 1.0, vsc1 = 1.0;
+  if (V3 && line_ok) {
+    const int line = line0 + w;
+    const int ta = (dir == 0) ? 1 : 0, tb = (dir == 2) ? 1 : 2;
+    const int ia = line % G.N[ta], ib = line / G.N[ta];
+    vsc0 = a.dxinv[G.xoff[ta] + G.g + ia];
+    vsc1 = a.dxinv[G.xoff[tb] + G.g + ib];
+  }
   const int rbase = w * RP;                                      // this warp's records
   const int xbase = w * XP;                                      // this warp's exchange slots
 
@@ -355,9 +365,12 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const SweepArgs a)
         rec[RL::A * NREC + ci] = sqrt(c2) + fabs(vn);
         if (V3) {
           // viscous flux of direction dir from the (mu/Re)-weighted derivatives (viscous_fused.cu)
+          // each difference is scaled by the LOCAL dxinv of its own direction (after the halo exchange, as the
+          // reference does): along the sweep line for the first four, the line's transverse indices for the rest
           double q[8];
+          const double dd = a.dxinv[G.xoff[dir] + G.g + c1];
 #pragma unroll
-          for (int k = 0; k < 8; k++) q[k] = s[(SL::SQI + k) * NSTG];
+          for (int k = 0; k < 8; k++) q[k] = s[(SL::SQI + k) * NSTG] * (k < 4 ? dd : (k < 6 ? vsc0 : vsc1));
           const double two_third = 2.0 / 3.0;
           const double kq = igm1 * (1.0 / a.ph.Pr);
           double t1, t2, t3;

@@ -2,7 +2,7 @@
 //
 // The reference evaluates the parabolic term in ~20 passes over memory (Q, three QDeriv arrays, per
 // direction FViscous and FDeriv, all ghost-padded 5-component temporaries calloc'ed per call). Here:
-//   (1) k_qderiv3 (this file): ONE kernel writes the scaled first derivatives of (u, v, w, T) in all three
+//   (1) k_qderiv3 (this file): ONE kernel writes the (un-scaled) first differences of (u, v, w, T) in all three
 //       directions (12 scalars per point; the density derivative is never used), each multiplied by the
 //       local mu/Re, mu = T^0.76 -- every term of the viscous flux is (mu/Re) x a derivative, so the sweeps
 //       need neither the viscosity nor exp/log. Q is evaluated in registers from the conserved variables.
@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(128) k_qderiv3(const QD3Args a)
 #pragma unroll
       for (int c = 0; c < 4; c++) D[c] = (fm2[c] - 8 * fm1[c] + 8 * fp1[c] - fp2[c]) * s12;
     }
-    const double dxi = a.dxinv[G.xoff[d] + g + x] * muRe;
+    // NOT scaled by dxinv here: the reference scales AFTER the halo exchange with the receiver's local dxinv
+    // (NavierStokes3DParabolicFunction.c:125-146); the sweeps apply it per cell
+    const double dxi = muRe;
 #pragma unroll
     for (int c = 0; c < 4; c++) a.qd[(long long)(d * 4 + c) * G.npg + p] = D[c] * dxi;
   }

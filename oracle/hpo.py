@@ -355,6 +355,18 @@ class Oracle:
             self.L.hpo_parabolic_nc1(self.c, _p(par), _p(u))
         return par
 
+    def parabolic_p1(self, u):
+        """NavierStokes parabolic term up to the halo exchange: Q and the un-scaled derivatives."""
+        Q, QDx, QDy, QDz = self.zeros(), self.zeros(), self.zeros(), self.zeros()
+        self.L.hpo_ns_parabolic_p1(self.c, _p(u), _p(Q), _p(QDx), _p(QDy), _p(QDz))
+        return Q, QDx, QDy, QDz
+
+    def parabolic_p2(self, Q, QDx, QDy, QDz):
+        """... and after it (QDx/QDy/QDz are scaled in place)."""
+        par = self.zeros()
+        self.L.hpo_ns_parabolic_p2(self.c, _p(Q), _p(QDx), _p(QDy), _p(QDz), _p(par))
+        return par
+
     def source(self, u, w):
         src = self.zeros()
         if self.s.ctx.model == 3:

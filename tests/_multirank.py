@@ -1,0 +1,180 @@
+"""All ranks of a decomposed run inside ONE process (TEST INFRASTRUCTURE).
+
+MultiRankOracle : one oracle context per rank; the halo exchange of MPIExchangeBoundariesnD is a copy
+                  of packed faces between the ranks' arrays. Gives the reference result of a run with
+                  the SAME iproc -- needed because the viscous term depends on the decomposition
+                  (QDerivZ is never exchanged, un-exchanged ghost derivatives
+                  are one-sided).
+LocalRanks      : one hpb_solver per rank on ONE GPU, driven through the staged C-ABI step; the halo
+                  buffers are copied device-to-device instead of sent over NCCL. Exercises exactly the
+                  pack / unpack / staged-step code the multi-GPU run uses.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from hypar_b200.solver import FIELD_QDERIVX, FIELD_QDERIVY, FIELD_U, Solver
+from oracle import hpo
+
+
+def _neighbors(S):
+    """[2*nd] neighbour ranks of hpo.Setup S (-1: none), MPIExchangeBoundariesnD.c:65-76."""
+    nb = []
+    for d in range(S.ndims):
+        for side in (0, 1):
+            ip = list(S.ip)
+            edge = (S.ip[d] == 0) if side == 0 else (S.ip[d] == S.iproc[d] - 1)
+            if S.iproc[d] == 1 or (edge and not S.periodic[d]):
+                nb.append(-1)
+                continue
+            ip[d] = (S.ip[d] + (-1 if side == 0 else 1)) % S.iproc[d]
+            nb.append(hpo.rank_1d(S.iproc, ip))
+    return nb
+
+
+class MultiRankOracle:
+    def __init__(self, case):
+        self.case = case
+        self.nranks = int(np.prod(case.solver["iproc"]))
+        self.S = [hpo.Setup(case, rank=r) for r in range(self.nranks)]
+        self.O = [hpo.Oracle(s) for s in self.S]
+        self.nb = [_neighbors(s) for s in self.S]
+        self.nd = self.S[0].ndims
+        self.viscous = case.solver["model"] in ("navierstokes3d", "navierstokes2d") and float(case.physics.get("Re", -1)) > 0
+
+    def exchange(self, arrs):
+        bufs = {}
+        for r in range(self.nranks):
+            for d in range(self.nd):
+                for side in (0, 1):
+                    if self.nb[r][2 * d + side] >= 0:
+                        bufs[(r, d, side)] = self.O[r].pack(arrs[r], d, side)
+        for r in range(self.nranks):
+            for d in range(self.nd):
+                for side in (0, 1):
+                    peer = self.nb[r][2 * d + side]
+                    if peer >= 0:
+                        # my ghost on `side` = the peer's interior layers on its opposite face
+                        self.O[r].unpack(arrs[r], d, side, bufs[(peer, d, 1 - side)])
+
+    def local_u0(self):
+        return [s.local_u0() for s in self.S]
+
+    def rhs(self, u):
+        """TimeRHSFunctionExplicit on every rank (u modified: BCs + halos). Returns [rhs_r]."""
+        for r in range(self.nranks):
+            self.O[r].apply_bc(u[r])
+        self.exchange(u)
+        out = []
+        pieces = []
+        for r in range(self.nranks):
+            hyp, w = self.O[r].hyperbolic(u[r], want_weights=True)
+            pieces.append((hyp, w))
+        par = [o.zeros() for o in self.O]
+        if self.viscous:
+            P1 = [self.O[r].parabolic_p1(u[r]) for r in range(self.nranks)]
+            self.exchange([p[1] for p in P1])          # QDerivX
+            self.exchange([p[2] for p in P1])          # QDerivY (the reference exchanges it twice, QDerivZ never)
+            par = [self.O[r].parabolic_p2(*P1[r]) for r in range(self.nranks)]
+        elif self.case.solver["model"] == "linear-advection-diffusion-reaction":
+            par = [self.O[r].parabolic(u[r]) for r in range(self.nranks)]
+        for r in range(self.nranks):
+            hyp, w = pieces[r]
+            src = self.O[r].source(u[r], w)
+            rhs = np.zeros_like(hyp)
+            rhs += -1.0 * hyp
+            rhs += par[r]
+            rhs += src
+            out.append(rhs)
+        return out
+
+    def time_step(self, u, dt, rk_type):
+        """TimePreStep BC/halo + TimeRK (TimeRK.c:126-195) on every rank, in place."""
+        A, b, c = np.zeros(16), np.zeros(4), np.zeros(4)
+        ns = hpo.lib().hpo_rk_tableau(rk_type, hpo._p(A), hpo._p(b), hpo._p(c))
+        for r in range(self.nranks):
+            self.O[r].apply_bc(u[r])
+        self.exchange(u)
+        k = []
+        for s in range(ns):
+            U = [x.copy() for x in u]
+            for i in range(s):
+                for r in range(self.nranks):
+                    U[r] += (dt * A[s * ns + i]) * k[i][r]
+            k.append(self.rhs(U))
+        for s in range(ns):
+            for r in range(self.nranks):
+                u[r] += (dt * b[s]) * k[s][r]
+        return u
+
+
+class LocalRanks:
+    def __init__(self, case, use_fused=True, device=0):
+        import torch
+        from hypar_b200.multigpu import _DevBuf
+        self.torch = torch
+        self.nranks = int(np.prod(case.solver["iproc"]))
+        self.sv = [Solver.from_case(case, rank=r, device=device, use_fused=use_fused) for r in range(self.nranks)]
+        self.viscous = bool(self.sv[0].L.hpb_needs_viscous_exchange(self.sv[0].h))
+        dev = torch.device("cuda", device)
+        self.buf = {}
+        for f in [FIELD_U] + ([FIELD_QDERIVX, FIELD_QDERIVY] if self.viscous else []):
+            for r, sv in enumerate(self.sv):
+                send, recv, nbytes = sv.halo_buffers(f)
+                for k in range(2 * sv.ndims):
+                    if nbytes[k]:
+                        self.buf[(f, r, k, "s")] = torch.as_tensor(_DevBuf(send[k], nbytes[k]), device=dev)
+                        self.buf[(f, r, k, "r")] = torch.as_tensor(_DevBuf(recv[k], nbytes[k]), device=dev)
+
+    def _sync(self):
+        for sv in self.sv:
+            sv.synchronize()
+        self.torch.cuda.synchronize()
+
+    def exchange(self, fields):
+        self._sync()
+        for f in fields:
+            for r, sv in enumerate(self.sv):
+                for k in range(2 * sv.ndims):
+                    peer = sv.neighbors[k]
+                    if peer >= 0:
+                        self.buf[(f, r, k, "r")].copy_(self.buf[(f, peer, k ^ 1, "s")])
+        self.torch.cuda.synchronize()
+
+    def _all(self, name, *args):
+        for sv in self.sv:
+            sv._ck(getattr(sv.L, name)(sv.h, *args))
+
+    def set_solution(self, u):
+        for sv, x in zip(self.sv, u):
+            sv.set_solution(x)
+
+    def get_solution(self):
+        return [sv.get_solution() for sv in self.sv]
+
+    def _stage(self, s):
+        self._all("hpb_stage_begin", s)
+        self.exchange([FIELD_U])
+        self._all("hpb_stage_halo_done", FIELD_U)
+        self._all("hpb_stage_rhs_a", s)
+        if self.viscous:
+            self.exchange([FIELD_QDERIVX, FIELD_QDERIVY])
+            self._all("hpb_stage_halo_done", FIELD_QDERIVX)
+            self._all("hpb_stage_halo_done", FIELD_QDERIVY)
+        self._all("hpb_stage_rhs_b", s)
+
+    def rhs(self):
+        self._stage(0)
+        return [sv.get_stage_rhs(0) for sv in self.sv]
+
+    def time_step(self):
+        self._all("hpb_step_begin")
+        self.exchange([FIELD_U])
+        self._all("hpb_step_halo_done")
+        for s in range(self.sv[0].nstages):
+            self._stage(s)
+        self._all("hpb_step_finish")
+
+    def close(self):
+        for sv in self.sv:
+            sv.close()

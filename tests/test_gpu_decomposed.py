@@ -1,0 +1,90 @@
+"""Domain-decomposed runs: every rank's CUDA result against an oracle run WITH THE SAME iproc (the viscous
+term depends on the decomposition: SURVEY.md Q1/Q2). All ranks live in one process on one GPU
+(tests/_multirank.py): the staged C-ABI step, the pack/unpack kernels and the face-buffer plumbing are the
+ones the NCCL run uses; only the transport (device-to-device copy vs ncclSend/Recv) differs, and that one is
+covered by tests/test_multigpu_gloo.py and the 2-GPU check in tools/multigpu_check.py."""
+import numpy as np
+import pytest
+
+from _multirank import LocalRanks, MultiRankOracle
+from conftest import rel_linf
+from hypar_b200 import cases
+from oracle import hpo
+
+pytestmark = pytest.mark.gpu
+
+DECOMP = [
+    cases.ns3d_turbulence((25, 14, 13), "mapped", iproc=(2, 1, 1)),                     # viscous, remainder in x
+    cases.ns3d_turbulence((14, 26, 27), "js", iproc=(1, 2, 2)),                          # viscous, y/z split (Q1: z)
+    cases.ns3d_turbulence((26, 25, 27), "z", iproc=(2, 2, 2)),                           # 8 ranks, remainders
+    cases.ns3d_turbulence((14, 13, 38), "yc", viscous=False, iproc=(1, 1, 3)),           # inviscid, 3 ranks
+    cases.ns3d_rising_bubble((14, 26, 12), "yc", iproc=(1, 2, 1)),                       # walls + gravity
+    cases.ns2d_vortex((40, 27), "mapped", iproc=(2, 2)),
+    cases.euler1d_sod(101, "js", interp="characteristic", upwinding="roe"),              # iproc 1 (generic path)
+    cases.linear_advection_sine(96, "z"),
+]
+DECOMP[-2].solver["iproc"] = [2]
+DECOMP[-1].solver["iproc"] = [3]
+for c in DECOMP:
+    c.name += "_iproc" + "x".join(str(v) for v in c.solver["iproc"])
+
+
+@pytest.mark.parametrize("case", DECOMP, ids=[c.name for c in DECOMP])
+@pytest.mark.parametrize("fused", [False, True], ids=["exact", "fused"])
+def test_decomposed_rhs_and_steps(need_gpu, case, fused):
+    MO = MultiRankOracle(case)
+    u_ref = MO.local_u0()
+    rhs_ref = MO.rhs(u_ref)
+    LR = LocalRanks(case, use_fused=fused)
+    LR.set_solution(MO.local_u0())
+    rhs = LR.rhs()
+    scale = max(np.abs(r).max() for r in rhs_ref)
+    for r in range(MO.nranks):
+        assert np.isfinite(rhs[r]).all()
+        if not fused:
+            assert np.array_equal(rhs[r], rhs_ref[r]), \
+                f"rank {r}: rhs not bit-identical (max abs diff {np.abs(rhs[r] - rhs_ref[r]).max():.3e})"
+        else:
+            lam = MO.O[r].cfl(u_ref[r], float(case.solver["dt"])) / float(case.solver["dt"])
+            tol = 1e-12 * scale + 16 * np.finfo(np.float64).eps * lam * np.abs(u_ref[r]).max()
+            assert np.abs(rhs[r] - rhs_ref[r]).max() <= tol, \
+                f"rank {r}: rhs abs err {np.abs(rhs[r] - rhs_ref[r]).max():.3e} > {tol:.3e}"
+    # two full time steps
+    dt = float(case.solver["dt"])
+    rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    u_ref = MO.local_u0()
+    for _ in range(2):
+        MO.time_step(u_ref, dt, rk)
+    LR.set_solution(MO.local_u0())
+    for _ in range(2):
+        LR.time_step()
+    u = LR.get_solution()
+    for r in range(MO.nranks):
+        a, b = MO.S[r].interior(u[r]), MO.S[r].interior(u_ref[r])
+        if not fused:
+            assert np.array_equal(a, b), f"rank {r}: u after 2 steps not bit-identical ({np.abs(a - b).max():.3e})"
+        else:
+            assert rel_linf(a, b) <= 1e-11, f"rank {r}: u after 2 steps rel err {rel_linf(a, b):.3e}"
+    LR.close()
+
+
+def test_inviscid_rhs_is_decomposition_invariant(need_gpu):
+    """hyperbolic term: the 8-rank result equals the single-rank result on every block (exact path: bit for bit)"""
+    kw = dict(n=(26, 25, 27), weno="mapped", viscous=False)
+    c8, c1 = cases.ns3d_turbulence(iproc=(2, 2, 2), **kw), cases.ns3d_turbulence(**kw)
+    S1 = hpo.Setup(c1)
+    r1 = hpo.Oracle(S1).rhs(S1.local_u0()).reshape(S1.shape_g())
+    for fused in (False, True):
+        LR = LocalRanks(c8, use_fused=fused)
+        MO = MultiRankOracle(c8)
+        LR.set_solution(MO.local_u0())
+        rhs = LR.rhs()
+        g = S1.ghosts
+        for r, S in enumerate(MO.S):
+            sl = tuple(slice(g + S.is_[k], g + S.is_[k] + S.dim[k]) for k in reversed(range(3)))
+            a, b = S.interior(rhs[r]), r1[sl]
+            if not fused:
+                assert np.array_equal(a, b)
+            else:
+                assert rel_linf(a, b) <= 1e-12
+        LR.close()

@@ -1,0 +1,72 @@
+"""2..8-GPU parity check over NCCL (TEST INFRASTRUCTURE; run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multigpu_check.py
+
+Every rank drives hypar_b200.multigpu.DistributedSolver on its block of a small decomposed case and compares
+its RHS and its solution after 2 steps with the multi-rank oracle (all ranks evaluated in-process)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from _multirank import MultiRankOracle
+from hypar_b200 import cases
+from hypar_b200.multigpu import DistributedSolver
+from oracle import hpo
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    iprocs = {2: [(1, 1, 2), (2, 1, 1)], 4: [(1, 2, 2), (2, 2, 1)], 8: [(2, 2, 2)]}[world]
+    ok = True
+    for iproc in iprocs:
+        for name, case in (("visc", cases.ns3d_turbulence((26, 25, 27), "mapped", iproc=iproc)),
+                           ("bubble", cases.ns3d_rising_bubble((26, 24, 28), "yc", iproc=iproc))):
+            for fused in (False, True):
+                MO = MultiRankOracle(case)
+                u_ref = MO.local_u0()
+                rhs_ref = MO.rhs(u_ref)
+                ds = DistributedSolver(case.solver, case.boundary, case.physics, case.weno, case.x, rank=rank,
+                                       device=local, use_fused=fused)
+                ds.solver.set_solution(MO.local_u0()[rank])
+                rhs = ds.rhs()
+                scale = max(np.abs(r).max() for r in rhs_ref)
+                e_rhs = np.abs(rhs - rhs_ref[rank]).max() / scale
+                dt = float(case.solver["dt"])
+                rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+                u_ref = MO.local_u0()
+                for _ in range(2):
+                    MO.time_step(u_ref, dt, rk)
+                ds.solver.set_solution(MO.local_u0()[rank])
+                ds.time_steps(2)
+                u = ds.solver.get_solution()
+                S = MO.S[rank]
+                a, b = S.interior(u), S.interior(u_ref[rank])
+                e_u = np.abs(a - b).max() / np.abs(b).max()
+                cfl = ds.max_cfl()
+                good = (e_rhs == 0 and e_u == 0) if (not fused and name == "visc") else (e_rhs <= 5e-11 and e_u <= 1e-11)
+                ok = ok and good
+                print(f"[rank {rank}/{world}] iproc {iproc} {name:6s} {'fused' if fused else 'exact'}: "
+                      f"rhs err/scale {e_rhs:.2e}, u(2 steps) rel err {e_u:.2e}, max CFL {cfl:.4f} {'ok' if good else 'FAIL'}",
+                      flush=True)
+                ds.solver.close()
+    t = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(t)
+    dist.destroy_process_group()
+    if int(t.item()):
+        sys.exit(1)
+    if rank == 0:
+        print("MULTIGPU CHECK PASSED")
+
+
+if __name__ == "__main__":
+    main()
