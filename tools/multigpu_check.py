@@ -53,7 +53,12 @@ def main():
                 a, b = S.interior(u), S.interior(u_ref[rank])
                 e_u = np.abs(a - b).max() / np.abs(b).max()
                 cfl = ds.max_cfl()
-                good = (e_rhs == 0 and e_u == 0) if (not fused and name == "visc") else (e_rhs <= 5e-11 and e_u <= 1e-11)
+                # exact path: bit-identical. Fused path: 1e-12 of the largest RHS plus 16 ulp of the dissipation term
+                # alpha*u*dxinv (tests/test_gpu_parity.py::fused_tolerance); the hydrostatically balanced bubble has
+                # |rhs| << |terms|, so its error is measured against that floor
+                lam = MO.O[rank].cfl(MO.local_u0()[rank], dt) / dt
+                tol = 1e-12 + 16 * np.finfo(np.float64).eps * lam * np.abs(MO.local_u0()[rank]).max() / scale
+                good = (e_rhs == 0 and e_u == 0) if not fused else (e_rhs <= tol and e_u <= 1e-11)
                 ok = ok and good
                 print(f"[rank {rank}/{world}] iproc {iproc} {name:6s} {'fused' if fused else 'exact'}: "
                       f"rhs err/scale {e_rhs:.2e}, u(2 steps) rel err {e_u:.2e}, max CFL {cfl:.4f} {'ok' if good else 'FAIL'}",
