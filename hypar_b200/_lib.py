@@ -53,7 +53,7 @@ SYMBOLS = [
     "hpb_TimeSteps", "hpb_current_time", "hpb_dev_ComputeCFL", "hpb_dev_StepNormSumSq", "hpb_dev_RHS",
     "hpb_halo_buffers", "hpb_step_begin", "hpb_step_halo_done", "hpb_stage_begin", "hpb_stage_halo_done",
     "hpb_stage_rhs_a", "hpb_stage_rhs_b", "hpb_step_finish", "hpb_dev_get_stage_rhs", "hpb_nstages", "hpb_needs_viscous_exchange",
-    "hpb_stream", "hpb_synchronize", "hpb_kernel_launch_count", "hpb_profile_enable", "hpb_profile_query",
+    "hpb_stream", "hpb_synchronize", "hpb_kernel_launch_count", "hpb_tma_launch_count", "hpb_profile_enable", "hpb_profile_query",
 ]
 
 _lib = None
@@ -123,6 +123,8 @@ def load():
     L.hpb_stream.restype = vp
     L.hpb_kernel_launch_count.argtypes = [vp]
     L.hpb_kernel_launch_count.restype = C.c_longlong
+    L.hpb_tma_launch_count.argtypes = [vp]
+    L.hpb_tma_launch_count.restype = C.c_longlong
     L.hpb_profile_enable.argtypes = [vp, C.c_int]
     L.hpb_profile_query.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_longlong)]
     _lib = L

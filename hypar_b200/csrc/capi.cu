@@ -258,6 +258,7 @@ extern "C" int hpb_get_gravity_field(const hpb_solver* h, double* f, double* g)
   return HPB_OK;
 }
 extern "C" long long hpb_kernel_launch_count(const hpb_solver* h) { return h->launches; }
+extern "C" long long hpb_tma_launch_count(const hpb_solver* h) { return h->tma_launches; }
 extern "C" void* hpb_stream(hpb_solver* h) { return (void*)h->stream; }
 extern "C" int hpb_synchronize(hpb_solver* h) { TRY(need_device(h)); return sync_check(h, "synchronize"); }
 extern "C" double hpb_current_time(const hpb_solver* h) { return h->t; }

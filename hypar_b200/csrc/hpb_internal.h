@@ -53,6 +53,7 @@ struct hpb_solver {
   int device = 0;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  long long tma_launches = 0;
   double t = 0.0;
 
   // device arrays
@@ -83,6 +84,10 @@ struct hpb_solver {
   struct ProfRec { int cat; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> prof_pool;
+  // cached TMA descriptors of the fused sweeps (sweep_fused.cu): one per (array, field count, box kind)
+  struct alignas(64) TmaBlob { unsigned char b[128]; };
+  struct TmaEntry { const void* ptr; int nf, kind; TmaBlob map; };
+  std::vector<TmaEntry> tma_cache;
 };
 
 // RAII scope: when profiling is on, brackets the kernels launched inside it with an event pair

@@ -3,6 +3,83 @@
 // NavierStokes3D with Rusanov upwinding (with or without gravity). Everything else (characteristic
 // reconstruction, Roe upwinding, Euler1D) is served by the generic per-interface kernels.
 #include "sweep_fused.cuh"
+#include "sweep_tma.cuh"
+#include <cstdlib>
+#include <cstring>
+
+namespace hpbf {
+
+// ---- TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point: no libcuda link)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn()
+{
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* off = getenv("HPB_NO_TMA");
+    if (!(off && off[0] == '1')) {
+      void* p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+          q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+      else cudaGetLastError();
+    }
+  }
+  return fn;
+}
+
+// ghost-padded SoA array of nf fields as a 4-D tensor (x, y, z, field); kind 0: x-sweep box 32 x 8 lines(y),
+// kind 1 / 2: y- / z-sweep box 8 lines(x) x 32 cells with the 64-byte swizzle. boxf = fields per box.
+static bool get_map(hpb_solver* h, const void* ptr, int nf, int boxf, int kind, CUtensorMap* out)
+{
+  for (const auto& e : h->tma_cache)
+    if (e.ptr == ptr && e.nf == nf * 16 + boxf && e.kind == kind) { memcpy(out, e.map.b, sizeof(CUtensorMap)); return true; }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  const Geom& G = h->geo;
+  if ((G.P[0] & 1) || (reinterpret_cast<uintptr_t>(ptr) & 15)) return false;
+  cuuint64_t dims[4] = { (cuuint64_t)G.P[0], (cuuint64_t)G.P[1], (cuuint64_t)G.P[2], (cuuint64_t)nf };
+  cuuint64_t strides[3] = { (cuuint64_t)G.P[0] * 8, (cuuint64_t)G.P[0] * G.P[1] * 8, (cuuint64_t)G.npg * 8 };
+  cuuint32_t box[4] = { 1, 1, 1, (cuuint32_t)boxf };
+  if (kind == 0) { box[0] = TL; box[1] = TW; }
+  else { box[0] = TW; box[kind] = TL; }
+  cuuint32_t es[4] = { 1, 1, 1, 1 };
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, kind == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  hpb_solver::TmaEntry e;
+  e.ptr = ptr; e.nf = nf * 16 + boxf; e.kind = kind;
+  memcpy(e.map.b, &m, sizeof(CUtensorMap));
+  if (h->tma_cache.size() > 256) h->tma_cache.clear();
+  h->tma_cache.push_back(e);
+  *out = m;
+  return true;
+}
+
+bool tma_maps_for(hpb_solver* h, const SweepArgs& a, bool xs, bool grav, bool visc, TmaMaps* tm)
+{
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  const Geom& G = a.G;
+  if (G.ndims < 2 || G.g != HPB_G) return false;
+  if (xs != (a.dir == 0)) return false;
+  const int kind = a.dir;
+  const int nv = G.nvars;
+  memset(tm, 0, sizeof(*tm));
+  if (!get_map(h, a.u, nv, nv, kind, &tm->u)) return false;
+  if (xs) tm->out = tm->u;    // unused by the x-sweep (direct stores)
+  else if (!get_map(h, a.out, nv, nv, kind, &tm->out)) return false;
+  tm->qd = tm->u; tm->gf = tm->u; tm->gg = tm->u;
+  if (visc && !get_map(h, a.qd, 12, 1, kind, &tm->qd)) return false;
+  if (grav && (!get_map(h, a.gf, 1, 1, kind, &tm->gf) || !get_map(h, a.gg, 1, 1, kind, &tm->gg))) return false;
+  return true;
+}
+
+} // namespace hpbf
 
 namespace hpbk {
 

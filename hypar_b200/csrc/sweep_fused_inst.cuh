@@ -2,6 +2,7 @@
 // weight type keeps the build parallel: sweep_fused_wt{0..4}.cu).
 #pragma once
 #include "sweep_fused.cuh"
+#include "sweep_tma.cuh"
 
 namespace hpbf {
 
@@ -24,14 +25,57 @@ static bool launch_one(hpb_solver* h, const SweepArgs& a)
   return true;
 }
 
+// TMA variant (sweep_tma.cuh): NavierStokes2D/3D, even padded row length, x-sweep overwriting / y-,z-sweeps
+// accumulating (what hyperbolic_fused always asks for). Returns false when not applicable: the caller then
+// launches k_sweep.
+template <int MODEL, int WT, bool XS, bool GRAV, bool VISC>
+static bool launch_one_tma(hpb_solver* h, const SweepArgs& a)
+{
+  using LY = TmaLayout<MODEL, GRAV, VISC>;
+  constexpr size_t smem = LY::smem_bytes;
+  if (smem > 227 * 1024) return false;
+  const bool accumulate = (a.mode & 1) != 0;
+  if (XS == accumulate) return false;
+  TmaMaps tm;
+  if (!tma_maps_for(h, a, XS, GRAV, VISC, &tm)) return false;
+  static bool configured = false;
+  auto kern = k_sweep_tma<MODEL, WT, XS, GRAV, VISC>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = true;
+  }
+  const Geom& G = a.G;
+  long long nblk;
+  if (XS) nblk = (long long)((G.N[1] + TW - 1) / TW) * G.N[2];
+  else    nblk = (long long)((G.N[0] + 1 + TW - 1) / TW) * (a.dir == 1 ? G.N[2] : G.N[1]);
+  if (nblk <= 0 || nblk > 2147483647LL) return false;
+  kern<<<dim3((unsigned)nblk, 1, 1), NT, smem, h->stream>>>(a, tm);
+  h->launches++;
+  h->tma_launches++;
+  return true;
+}
+
+template <int MODEL, int WT, bool MAPX, bool GRAV, bool VISC>
+static bool launch_pick(hpb_solver* h, const SweepArgs& a)
+{
+  if (MODEL != HPB_MODEL_LINEAR_ADR && h->cfg.use_fused != 2) {
+    constexpr int M2 = (MODEL == HPB_MODEL_LINEAR_ADR) ? HPB_MODEL_NS3D : MODEL;   // never instantiated for LinearADR
+    if (launch_one_tma<M2, WT, MAPX, GRAV, VISC>(h, a)) return true;
+  }
+  return launch_one<MODEL, WT, MAPX, GRAV, VISC>(h, a);
+}
+
 template <int MODEL, int WT, bool MAPX>
 static bool launch_map(hpb_solver* h, const SweepArgs& a, bool grav, bool visc)
 {
   constexpr bool NS3 = (MODEL == HPB_MODEL_NS3D);
-  if (NS3 && grav && visc) return launch_one<MODEL, WT, MAPX, NS3, NS3>(h, a);
-  if (NS3 && grav)         return launch_one<MODEL, WT, MAPX, NS3, false>(h, a);
-  if (NS3 && visc)         return launch_one<MODEL, WT, MAPX, false, NS3>(h, a);
-  return launch_one<MODEL, WT, MAPX, false, false>(h, a);
+  if (NS3 && grav && visc) return launch_pick<MODEL, WT, MAPX, NS3, NS3>(h, a);
+  if (NS3 && grav)         return launch_pick<MODEL, WT, MAPX, NS3, false>(h, a);
+  if (NS3 && visc)         return launch_pick<MODEL, WT, MAPX, false, NS3>(h, a);
+  return launch_pick<MODEL, WT, MAPX, false, false>(h, a);
 }
 
 template <int MODEL, int WT>

@@ -1,0 +1,461 @@
+// sweep_tma.cuh -- the fused directional sweep of sweep_fused.cuh with all global<->shared traffic moved
+// to the TMA unit and every CTA-wide barrier of the march removed (NavierStokes2D / NavierStokes3D).
+//
+// Same arithmetic and work decomposition as k_sweep (one WARP per grid line, 8 lines per CTA, 32 cells
+// per march step, records / exchanges warp-private in shared memory, reference citations in
+// sweep_fused.cuh). What changes is how the data moves (profiles/r01b: in k_sweep 22 % of the warp-stall
+// samples of the y/z sweeps sat in the cp.async / LDG / STG phases and their address arithmetic):
+//
+//   inputs   one elected thread issues cp.async.bulk.tensor (4-D tiled, ghost-padded SoA array seen as
+//            [field][z][y][x]) for the whole CTA tile of the next step: u (all components in one box),
+//            8 derivative scalars, gravity fields. x-sweep: box 32(x) x 8 lines(y); y-/z-sweep: box
+//            8 lines(x) x 32 cells, written with the 64-byte swizzle so that a warp reading ITS line
+//            (stride 64 B) is 2-way instead of 16-way bank conflicted. Completion: mbarrier expect_tx.
+//            Ghost cells beyond the array and the start-up step use the TMA's zero fill (negative
+//            coordinates are legal for loads).
+//   results  y-/z-sweep (always accumulating): the CTA's 32x8 tile of each component is staged in shared
+//            memory (same swizzle) and ONE cp.reduce.async.bulk.tensor ... .add per step performs the
+//            read-modify-write in L2: no loads of the old right-hand side, no registers for them. Cells
+//            outside the interior are staged as +0.0 (adding zero to a ghost entry changes nothing; the
+//            box is clipped at the array bounds by the TMA).  x-sweep (always the first direction:
+//            overwrites): lanes run along x, so each warp stores its own 256 contiguous bytes from
+//            registers.
+//   sync     no __syncthreads in the march. The last warp to finish reading the input tile of step m
+//            (shared atomic counter) issues the loads of step m+1; the last warp to stage its results
+//            issues the reduce and, when the TMA has read the tile, frees it through an mbarrier. Warps
+//            of a CTA can drift by up to one step.
+//
+// TMA constraints (tools/tma_probe.cu, checked on the B200): the innermost box coordinate must be
+// 16-byte aligned (even index) for loads and stores, stores must not start at negative coordinates,
+// FP64 reduce-add is supported. Hence: x-sweep loads start at padded index 32m+6; the 8-line tiles of
+// the y-/z-sweeps start at padded x index 8t+2 (grid line x = 8t-1: the first line of the first tile is
+// a ghost line and idles); the padded row length P0 must be even (otherwise the caller falls back to
+// k_sweep).
+#pragma once
+#include <cuda.h>
+#include "sweep_fused.cuh"
+
+namespace hpbf {
+
+struct TmaMaps {
+  CUtensorMap u, qd, out, gf, gg;
+};
+// host (sweep_fused.cu): descriptors for the arrays of one launch; false when the TMA path does not apply
+// (driver entry point missing, odd padded row length, misaligned array)
+bool tma_maps_for(hpb_solver* h, const SweepArgs& a, bool xs, bool grav, bool visc, TmaMaps* tm);
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  unsigned done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load4(void* dst, const CUtensorMap* m, unsigned long long* bar, int c0, int c1, int c2, int c3)
+{
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               :: "r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add4(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3)
+{
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :: "l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// shared-memory carve-up (doubles). TMA tiles first (the 64-byte swizzle is a function of address bits 4..8: the
+// dynamic shared memory is declared 1024-byte aligned and every tile is 2048 B), then the warp-private
+// records and exchanges of k_sweep. Without gravity the mass flux rho*v_d IS the conserved momentum component
+// (to rounding), so its record field, reconstruction and exchange slot are dropped (SKIPF0).
+template <int MODEL, bool GRAV, bool VISC>
+struct TmaLayout {
+  using SL = SweepLayout<MODEL, GRAV, VISC>;
+  static constexpr int NV = RecLayout<MODEL>::NV;
+  static constexpr int NDV = NV - 2;
+  static constexpr bool G3 = SL::G3, V3 = SL::V3;
+  static constexpr bool SKIPF0 = !G3;
+  static constexpr int SK = SKIPF0 ? 1 : 0;
+  // record fields
+  static constexpr int rU = 0;
+  static constexpr int rF = NV - SK;                        // flux component v at rF + v (v >= SK)
+  static constexpr int rV4 = 2 * NV - SK;
+  static constexpr int rSR = rV4 + 1;
+  static constexpr int rVEL = rSR + 1;
+  static constexpr int rH = rVEL + NDV;
+  static constexpr int rA = rH + 1;
+  static constexpr int rGF = rA + 1;                        // gravity f, g
+  static constexpr int rFV = rGF + (G3 ? 2 : 0);            // viscous flux (4)
+  static constexpr int NFREC = rFV + (V3 ? 4 : 0);
+  // exchange fields (left-biased values): flux v at xF + v (v >= SK), solution v at xU + v, gravity source xZ + {0,1}
+  static constexpr int xF = -SK;
+  static constexpr int xU = NV - SK;
+  static constexpr int xZ = 2 * NV - SK;
+  static constexpr int NFL = xZ + (G3 ? 2 : 0);
+  static constexpr int NFF = SL::NFF;                       // interface flux (, S x2)
+  static constexpr int TILE = TL * TW;                      // doubles per field tile (2048 B)
+  static constexpr int NFIN = SL::NFSTG;                    // input fields: u, (gf, gg), (8 derivative scalars)
+  static constexpr int o_in = 0;
+  static constexpr int o_out = o_in + NFIN * TILE;          // result tile (y-/z-sweeps)
+  static constexpr int o_rec = o_out + NV * TILE;
+  static constexpr int o_exL = o_rec + NFREC * NREC;
+  static constexpr int o_exF = o_exL + NFL * NEX;
+  static constexpr int o_sync = o_exF + NFF * NEX;          // 2 mbarriers + 2 counters
+  static constexpr size_t smem_bytes = sizeof(double) * (size_t)(o_sync + 4);
+};
+
+template <int MODEL, int WT, bool XS, bool GRAV, bool VISC>
+__global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __grid_constant__ TmaMaps tm)
+{
+  using LY = TmaLayout<MODEL, GRAV, VISC>;
+  using SL = SweepLayout<MODEL, GRAV, VISC>;
+  constexpr int NV = LY::NV;
+  constexpr int NDV = NV - 2;
+  constexpr bool G3 = SL::G3, V3 = SL::V3;
+  constexpr bool SKIPF0 = LY::SKIPF0;
+  constexpr int TILE = LY::TILE;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  double* stg = smem + LY::o_in;
+  double* ost = smem + LY::o_out;
+  double* rec = smem + LY::o_rec;
+  double* exL = smem + LY::o_exL;
+  double* exF = smem + LY::o_exF;
+  unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(smem + LY::o_sync);
+  unsigned long long* free_bar = full_bar + 1;
+  unsigned* cons_cnt = reinterpret_cast<unsigned*>(full_bar + 2);
+  unsigned* res_cnt = cons_cnt + 1;
+
+  const Geom& G = a.G;
+  const int dir = a.dir;
+  const int N = G.N[dir];
+  const long long npg = G.npg;
+  const int tid = threadIdx.x;
+  const int w = tid >> 5, l = tid & 31;
+  const int g1 = (G.ndims > 1) ? G.g : 0, g2 = (G.ndims > 2) ? G.g : 0;
+
+  // tile -> lines. x-sweep: 8 consecutive y at one z; y-sweep: 8 consecutive x (from x = 8t-1) at one z;
+  // z-sweep: 8 consecutive x at one y.
+  int tc0, tc1, tc2;               // TMA coordinates of the tile origin (the entry along `dir` is set per step)
+  bool line_ok;
+  long long pline = 0;             // x-sweep: offset of cell 0 of this warp's line
+  int ia, ib;                      // transverse indices of this warp's line, increasing dimension order
+  if (XS) {
+    const int nty = (G.N[1] + TW - 1) / TW;
+    const int ty = blockIdx.x % nty, z = blockIdx.x / nty;
+    ia = ty * TW + w; ib = z;
+    line_ok = ia < G.N[1];
+    tc0 = 0; tc1 = ty * TW + g1; tc2 = z + g2;
+    pline = G.g + (long long)G.P[0] * ((ia + g1) + (long long)G.P[1] * (ib + g2));
+  } else {
+    const int ntx = (G.N[0] + 1 + TW - 1) / TW;
+    const int tx = blockIdx.x % ntx, o = blockIdx.x / ntx;
+    ia = tx * TW - 1 + w; ib = o;
+    line_ok = ia >= 0 && ia < G.N[0];
+    tc0 = tx * TW + 2;
+    if (dir == 1) { tc1 = 0; tc2 = o + g2; } else { tc1 = o + G.g; tc2 = 0; }
+  }
+  const double gamma = a.ph.gamma;
+  const int M = (N + TL - 1) / TL;
+
+  // staging slot of (cell l of the step, line w): x-sweep [w][l]; y-/z-sweep [l][w] with the 64-byte swizzle
+  // (16-byte chunk index ^= bits 7..8 of the byte offset = (l >> 1) & 3)
+  const int sidx = XS ? (w * TL + l) : (l * TW + (w ^ (((l >> 1) & 3) << 1)));
+
+  double vsc0 = 1.0, vsc1 = 1.0;
+  if (V3 && line_ok) {
+    const int ta = (dir == 0) ? 1 : 0, tb = (dir == 2) ? 1 : 2;
+    vsc0 = a.dxinv[G.xoff[ta] + G.g + ia];
+    vsc1 = a.dxinv[G.xoff[tb] + G.g + ib];
+  }
+  const int rbase = w * RP;
+  const int xbase = w * XP;
+  const double* dxl = a.dxinv + G.xoff[dir] + G.g;
+
+  auto issue_loads = [&](int m) {
+    // executed by ONE thread: the input tile of step m (cells 32m+3 .. 32m+34 of the 8 lines)
+    mbar_expect_tx(full_bar, (unsigned)(LY::NFIN * TILE * sizeof(double)));
+    const int cd = TL * m + 3 + G.g;
+    int c0 = tc0, c1 = tc1, c2 = tc2;
+    if (dir == 0) c0 = cd; else if (dir == 1) c1 = cd; else c2 = cd;
+    tma_load4(stg, &tm.u, full_bar, c0, c1, c2, 0);
+    if (G3) {
+      tma_load4(stg + SL::SGI * TILE, &tm.gf, full_bar, c0, c1, c2, 0);
+      tma_load4(stg + (SL::SGI + 1) * TILE, &tm.gg, full_bar, c0, c1, c2, 0);
+    }
+    if (V3) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) tma_load4(stg + (SL::SQI + k) * TILE, &tm.qd, full_bar, c0, c1, c2, a.qidx[k]);
+    }
+  };
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();      // the swizzled tiles assume the declared alignment
+  if (tid == 0) {
+    mbar_init(full_bar, 1);
+    mbar_init(free_bar, 1);
+    *cons_cnt = 0; *res_cnt = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (tid == 0) issue_loads(-1);
+
+  for (int m = -1; m < M; m++) {
+    const int c1 = TL * m + 3 + l;
+    const int j = TL * m + 1 + l;
+    const int jo = j - 1;
+    // grid metrics of this step's cells (L1 hits: the same values serve all lines), requested before the wait
+    double dd = 0.0, dxi = 0.0;
+    if (V3 && c1 >= -3 && c1 <= N + 2) dd = dxl[c1];
+    if (jo >= 0 && jo < N) dxi = dxl[jo];
+
+    mbar_wait(full_bar, (unsigned)(m + 1) & 1u);
+
+    // ---------------- P1: record of cell c1 = 32m+3+l (record position 5+l)
+    if (line_ok && c1 >= -3 && c1 <= N + 2) {
+      const double* s = stg + sidx;
+      const int ci = rbase + 5 + l;
+      double U[NV];
+#pragma unroll
+      for (int v = 0; v < NV; v++) U[v] = s[v * TILE];
+#pragma unroll
+      for (int v = 0; v < NV; v++) rec[(LY::rU + v) * NREC + ci] = U[v];
+      const double rho = U[0];
+      double vel[3] = { 0.0, 0.0, 0.0 };
+      const double rinv = 1.0 / rho;
+#pragma unroll
+      for (int k = 0; k < NDV; k++) vel[k] = (rho == 0) ? 0.0 : U[1 + k] * rinv;
+      double vsq = 0.0;
+#pragma unroll
+      for (int k = 0; k < NDV; k++) vsq += vel[k] * vel[k];
+      const double e = U[NV - 1];
+      const double ke = 0.5 * rho * vsq;
+      const double P = (e - ke) * (gamma - 1.0);
+      const double vn = (dir == 0) ? vel[0] : (dir == 1 ? vel[1] : vel[2]);
+      if (!SKIPF0) rec[(LY::rF + 0) * NREC + ci] = rho * vn;
+#pragma unroll
+      for (int k = 0; k < NDV; k++) rec[(LY::rF + 1 + k) * NREC + ci] = rho * vn * vel[k] + (k == dir ? P : 0.0);
+      rec[(LY::rF + NV - 1) * NREC + ci] = (e + P) * vn;
+      double gfv = 1.0, ggv = 1.0;
+      if (G3) {
+        gfv = s[SL::SGI * TILE]; ggv = s[(SL::SGI + 1) * TILE];
+        rec[LY::rGF * NREC + ci] = gfv; rec[(LY::rGF + 1) * NREC + ci] = ggv;
+      }
+      const double igm1 = 1.0 / (gamma - 1.0);
+      rec[LY::rV4 * NREC + ci] = G3 ? ((P * igm1) * (1.0 / ggv) + ke * gfv) : (P * igm1 + ke);
+      const double c2 = gamma * P * rinv;
+      rec[LY::rSR * NREC + ci] = sqrt(rho);
+#pragma unroll
+      for (int k = 0; k < NDV; k++) rec[(LY::rVEL + k) * NREC + ci] = vel[k];
+      rec[LY::rH * NREC + ci] = 0.5 * vsq + c2 * igm1;
+      rec[LY::rA * NREC + ci] = sqrt(c2) + fabs(vn);
+      if (V3) {
+        double q[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) q[k] = s[(SL::SQI + k) * TILE] * (k < 4 ? dd : (k < 6 ? vsc0 : vsc1));
+        const double two_third = 2.0 / 3.0;
+        const double kq = igm1 * (1.0 / a.ph.Pr);
+        double t1, t2, t3;
+        if (dir == 0)      { t1 = two_third * (2 * q[0] - q[5] - q[7]); t2 = q[4] + q[1]; t3 = q[6] + q[2]; }
+        else if (dir == 1) { t1 = q[0] + q[5]; t2 = two_third * (-q[4] + 2 * q[1] - q[7]); t3 = q[6] + q[2]; }
+        else               { t1 = q[0] + q[5]; t2 = q[1] + q[7]; t3 = two_third * (-q[4] - q[6] + 2 * q[2]); }
+        rec[(LY::rFV + 0) * NREC + ci] = t1;
+        rec[(LY::rFV + 1) * NREC + ci] = t2;
+        rec[(LY::rFV + 2) * NREC + ci] = t3;
+        rec[(LY::rFV + 3) * NREC + ci] = vel[0] * t1 + vel[1] * t2 + vel[2] * t3 + kq * q[3];
+      }
+    }
+    __syncwarp();
+    // the input tile is consumed by this warp; the last warp of the CTA to get here requests the next one
+    if (l == 0) {
+      __threadfence_block();
+      const unsigned old = atomicAdd(cons_cnt, 1u);
+      if ((old & (TW - 1)) == TW - 1 && m + 1 < M) {
+        __threadfence_block();
+        issue_loads(m + 1);
+      }
+    }
+
+    // ---------------- P2: both reconstructions of the centred stencil of cell j = 32m+1+l (position l+3)
+    const bool rc_ok = line_ok && j >= -1 && j <= N;
+    const int cc = rbase + l + 3;
+    double fRv[NV], uRv[NV], sR[2] = { 0.0, 0.0 };
+#pragma unroll
+    for (int v = 0; v < NV; v++) { fRv[v] = 0.0; uRv[v] = 0.0; }
+    if (rc_ok) {
+      double Zg[5] = { 0, 0, 0, 0, 0 };
+      if (G3) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) Zg[k] = rec[(LY::rGF + 1) * NREC + cc + (k - 2)];
+      }
+      const int ex = xbase + l + 1;
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        double X[5], Y[5], L, zl, zr;
+        if (!(SKIPF0 && v == 0)) {
+#pragma unroll
+          for (int k = 0; k < 5; k++) X[k] = rec[(LY::rF + v) * NREC + cc + (k - 2)];
+          const bool zsrc = G3 && a.with_source && (v == dir + 1 || v == NV - 1);
+          if (G3 && zsrc) {
+            recon_pair<WT, true>(X, X, Zg, a.ph.eps, L, fRv[v], zl, zr);
+            const int si = (v == NV - 1) ? 1 : 0;
+            sR[si] = zr;
+            exL[(LY::xZ + si) * NEX + ex] = zl;
+          } else {
+            recon_pair<WT, false>(X, X, X, a.ph.eps, L, fRv[v], zl, zr);
+          }
+          exL[(LY::xF + v) * NEX + ex] = L;
+        }
+        // solution: weights from raw u, applied to the modified solution (Q4)
+#pragma unroll
+        for (int k = 0; k < 5; k++) X[k] = rec[(LY::rU + v) * NREC + cc + (k - 2)];
+        if (G3 || v == NV - 1) {
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            if (v == NV - 1) Y[k] = rec[LY::rV4 * NREC + cc + (k - 2)];
+            else Y[k] = X[k] * rec[LY::rGF * NREC + cc + (k - 2)];
+          }
+          recon_pair<WT, false>(X, Y, Y, a.ph.eps, L, uRv[v], zl, zr);
+        } else {
+          recon_pair<WT, false>(X, X, X, a.ph.eps, L, uRv[v], zl, zr);
+        }
+        exL[(LY::xU + v) * NEX + ex] = L;
+      }
+      if (SKIPF0) fRv[0] = (dir == 0) ? uRv[1] : ((dir == 1 || NDV < 3) ? uRv[2] : uRv[NDV]);       // f_0 = rho v_d is the conserved momentum component itself
+    }
+    __syncwarp();
+
+    // ---------------- P3: interface j-1/2 (between cells j-1 and j): Rusanov flux
+    const bool if_ok = line_ok && j >= 0 && j <= N;
+    double fh[NV], Sh[2] = { 0.0, 0.0 };
+#pragma unroll
+    for (int v = 0; v < NV; v++) fh[v] = 0.0;
+    if (if_ok) {
+      const int exl = xbase + l;              // left-biased values of cell j-1 (slot 0: carry)
+      const int cL = cc - 1, cR = cc;
+      const double tL = rec[LY::rSR * NREC + cL], tR = rec[LY::rSR * NREC + cR];
+      const double rs = 1.0 / (tL + tR);
+      double vsq = 0.0, vn = 0.0;
+#pragma unroll
+      for (int k = 0; k < NDV; k++) {
+        const double v = (tL * rec[(LY::rVEL + k) * NREC + cL] + tR * rec[(LY::rVEL + k) * NREC + cR]) * rs;
+        vsq += v * v;
+        if (k == dir) vn = v;
+      }
+      const double H = (tL * rec[LY::rH * NREC + cL] + tR * rec[LY::rH * NREC + cR]) * rs;
+      const double cavg = sqrt((gamma - 1.0) * (H - 0.5 * vsq));
+      const double aavg = cavg + fabs(vn);
+      double alpha = fmax(fmax(rec[LY::rA * NREC + cL], rec[LY::rA * NREC + cR]), aavg);
+      if (G3) alpha *= fmax(rec[(LY::rGF + 1) * NREC + cL], rec[(LY::rGF + 1) * NREC + cR]);
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        const double uL = exL[(LY::xU + v) * NEX + exl];
+        const double fL = (SKIPF0 && v == 0) ? exL[(LY::xU + 1 + dir) * NEX + exl] : exL[(LY::xF + v) * NEX + exl];
+        fh[v] = 0.5 * (fL + fRv[v]) - alpha * (0.5 * (uRv[v] - uL));
+      }
+      const int exo = xbase + l + 1;
+#pragma unroll
+      for (int v = 0; v < NV; v++) exF[v * NEX + exo] = fh[v];
+      if (G3 && a.with_source) {
+        Sh[0] = 0.5 * (exL[(LY::xZ + 0) * NEX + exl] + sR[0]);
+        Sh[1] = 0.5 * (exL[(LY::xZ + 1) * NEX + exl] + sR[1]);
+        exF[(NV + 0) * NEX + exo] = Sh[0];
+        exF[(NV + 1) * NEX + exo] = Sh[1];
+      }
+    }
+    __syncwarp();
+    // carry of the left-biased values (slot 32 -> slot 0)
+    if (l < LY::NFL) exL[l * NEX + xbase] = exL[l * NEX + xbase + TL];
+    __syncwarp();
+
+    // ---------------- P4: cell jo = j-1 = 32m+l (position l+2): interfaces j-1/2 (own) and j-3/2 (neighbour / carry)
+    if (m >= 0) {
+      const bool out_ok = line_ok && jo >= 0 && jo < N;
+      double res[NV];
+#pragma unroll
+      for (int v = 0; v < NV; v++) res[v] = 0.0;
+      if (out_ok) {
+        const int exl = xbase + l;
+        const int co = cc - 1;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          const double t = dxi * (fh[v] - exF[v * NEX + exl]);
+          res[v] = (a.mode < 2) ? -t : t;
+        }
+        if (V3) {
+          // par_v += dxinv * (FV[j-2] - 8 FV[j-1] + 8 FV[j+1] - FV[j+2]) / 12   (components 1..4)
+          const double s12 = 1.0 / 12.0;
+#pragma unroll
+          for (int v = 0; v < 4; v++) {
+            const double* f = rec + (LY::rFV + v) * NREC + co;
+            const double dfv = (f[-2] - 8 * f[-1] + 8 * f[1] - f[2]) * s12;
+            res[1 + v] += dxi * dfv;
+          }
+        }
+        if (G3 && a.with_source) {
+          // NavierStokes3DSource.c:80-100 (the source accumulates into the same array as the flux divergence)
+          const double rho = rec[LY::rU * NREC + co];
+          const double vd = rec[(LY::rVEL + dir) * NREC + co];
+          const double f = rec[LY::rGF * NREC + co];
+          const double tmm = rho * a.ph.RT, te = rho * a.ph.RT * vd;
+          const double sm = (tmm * f) * (Sh[0] - exF[(NV + 0) * NEX + exl]) * dxi;
+          const double se = (te * f) * (Sh[1] - exF[(NV + 1) * NEX + exl]) * dxi;
+#pragma unroll
+          for (int v = 1; v < NV; v++) res[v] += ((v == dir + 1) ? sm : 0.0) + ((v == NV - 1) ? se : 0.0);
+        }
+      }
+      if (XS) {
+        // first direction: overwrite; the warp's 32 cells are contiguous
+        if (out_ok) {
+#pragma unroll
+          for (int v = 0; v < NV; v++) a.out[v * npg + pline + jo] = res[v];
+        }
+      } else {
+        if (m >= 1) mbar_wait(free_bar, (unsigned)(m - 1) & 1u);     // the reduce of step m-1 has read the tile
+#pragma unroll
+        for (int v = 0; v < NV; v++) ost[v * TILE + sidx] = res[v];
+        fence_proxy_async();
+        __syncwarp();
+        if (l == 0) {
+          __threadfence_block();
+          const unsigned old = atomicAdd(res_cnt, 1u);
+          if ((old & (TW - 1)) == TW - 1) {
+            __threadfence_block();
+            fence_proxy_async();
+            const int cd = TL * m + G.g;
+            int c0 = tc0, c1t = tc1, c2t = tc2;
+            if (dir == 1) c1t = cd; else c2t = cd;
+            tma_reduce_add4(&tm.out, ost, c0, c1t, c2t, 0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(free_bar);
+          }
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---------------- shift (warp-private): the last 5 records and the interface-flux carry move to the front
+    for (int i = l; i < LY::NFREC * 5; i += 32) {
+      const int f = i / 5, r = i % 5;
+      rec[f * NREC + rbase + r] = rec[f * NREC + rbase + TL + r];
+    }
+    if (l < LY::NFF) exF[l * NEX + xbase] = exF[l * NEX + xbase + TL];
+    __syncwarp();
+  }
+}
+
+} // namespace hpbf

@@ -363,6 +363,11 @@ class Solver:
         return int(self.L.hpb_kernel_launch_count(self.h))
 
     @property
+    def tma_launches(self) -> int:
+        """launches of the TMA-fed fused sweep (sweep_tma.cuh) so far"""
+        return int(self.L.hpb_tma_launch_count(self.h))
+
+    @property
     def nstages(self) -> int:
         return int(self.L.hpb_nstages(self.h))
 

@@ -111,8 +111,9 @@ typedef struct hpb_config {
   const double* x_global;
   /* --- device --- */
   int    device;                       /* CUDA device ordinal; -1 = current              */
-  int    use_fused;                    /* 1 (default): fused sweep kernels where available;
-                                          0: generic per-interface kernels only          */
+  int    use_fused;                    /* 1 (default): fused sweep kernels where available (TMA-fed variant
+                                             when the padded row length is even), 2: fused sweeps without
+                                             the TMA variant, 0: generic per-interface kernels only */
 } hpb_config;
 
 typedef struct hpb_solver hpb_solver;
@@ -220,6 +221,7 @@ int hpb_synchronize(hpb_solver* h);
 
 /* ------------------------------------------------------------------ instrumentation */
 long long hpb_kernel_launch_count(const hpb_solver* h);   /* kernels launched by this solver so far */
+long long hpb_tma_launch_count(const hpb_solver* h);      /* of those, launches of the TMA-fed fused sweep */
 /* Device timing per kernel category (the analogue of the reference's GPU_STAT cudaEvent timers,
    HyperbolicFunction.c:69-121): when enabled, every launch group of a category is bracketed by a
    CUDA event pair on the solver's stream. hpb_profile_query synchronises and returns the summed
