@@ -48,10 +48,11 @@ __global__ void k_soa_to_aos(const double* __restrict__ soa, double* __restrict_
 // BCPeriodic.c:19-63 (only iproc[dim]==1), BCExtrapolate.c, BCSlipWall.c
 __global__ void k_bc_zone(Geom G, ZoneDev z, double gamma, double* __restrict__ phi)
 {
-  const int b0 = z.ie[0] - z.is[0], b1 = z.ie[1] - z.is[1];
-  int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y, t2 = blockIdx.z;
-  if (t0 >= b0) return;
-  (void)b1;
+  // linear thread index over the zone box, dim 0 fastest (x-faces are only g = 3 points wide)
+  const int b0 = z.ie[0] - z.is[0], b1 = (G.ndims > 1 ? z.ie[1] - z.is[1] : 1), b2 = (G.ndims > 2 ? z.ie[2] - z.is[2] : 1);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)b0 * b1 * b2) return;
+  const int t0 = (int)(t % b0), t1 = (int)((t / b0) % b1), t2 = (int)(t / ((long long)b0 * b1));
   int ib[3] = { t0, t1, t2 };
   int i1[3] = { t0 + z.is[0], t1 + z.is[1], t2 + z.is[2] };
   int i2[3] = { i1[0], i1[1], i1[2] };
@@ -102,13 +103,12 @@ __global__ void k_face_copy(Geom G, double* __restrict__ a, int nv, int d, int o
 {
   int b[3] = { G.N[0], G.N[1], G.N[2] };
   b[d] = G.g;
-  int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y, t2 = blockIdx.z;
-  if (t0 >= b[0]) return;
-  int s[3] = { t0, t1, t2 };
+  const long long nface = (long long)b[0] * b[1] * b[2];
+  const long long p2 = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // linear over the face box, dim 0 fastest
+  if (p2 >= nface) return;
+  int s[3] = { (int)(p2 % b[0]), (int)((p2 / b[0]) % b[1]), (int)(p2 / ((long long)b[0] * b[1])) };
   s[d] += off_d;
   const long long p1 = cell_index(G, s[0], s[1], s[2]);
-  const long long nface = (long long)b[0] * b[1] * b[2];
-  const long long p2 = t0 + (long long)b[0] * (t1 + (long long)b[1] * t2);
   if (to_buf) for (int v = 0; v < nv; v++) buf[v * nface + p2] = a[v * G.npg + p1];
   else        for (int v = 0; v < nv; v++) a[v * G.npg + p1] = buf[v * nface + p2];
 }
@@ -814,7 +814,7 @@ void apply_bc(hpb_solver* h, double* u)
     if (z.type == HPB_BC_PERIODIC && h->cfg.iproc[z.dim] != 1) continue;
     const int b0 = z.ie[0] - z.is[0], b1 = (G.ndims > 1 ? z.ie[1] - z.is[1] : 1), b2 = (G.ndims > 2 ? z.ie[2] - z.is[2] : 1);
     if (b0 <= 0 || b1 <= 0 || b2 <= 0) continue;
-    k_bc_zone<<<grid3(b0, b1, b2), TPB, 0, h->stream>>>(G, z, h->phys.gamma, u); LAUNCHED(h);
+    k_bc_zone<<<(unsigned)(((long long)b0 * b1 * b2 + TPB - 1) / TPB), TPB, 0, h->stream>>>(G, z, h->phys.gamma, u); LAUNCHED(h);
   }
 }
 
@@ -823,7 +823,7 @@ static void face_launch(hpb_solver* h, double* a, int nv, int d, int off_d, doub
   const Geom& G = h->geo;
   int b[3] = { G.N[0], G.N[1], G.N[2] };
   b[d] = G.g;
-  k_face_copy<<<grid3(b[0], b[1], b[2]), TPB, 0, h->stream>>>(G, a, nv, d, off_d, buf, to_buf); LAUNCHED(h);
+  k_face_copy<<<(unsigned)(((long long)b[0] * b[1] * b[2] + TPB - 1) / TPB), TPB, 0, h->stream>>>(G, a, nv, d, off_d, buf, to_buf); LAUNCHED(h);
 }
 
 void pack(hpb_solver* h, const double* a, int nv, int field)

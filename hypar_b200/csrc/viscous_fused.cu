@@ -24,7 +24,20 @@ struct QD3Args {
   const double* u;
   const double* dxinv;
   double* qd;          // [dir][comp 0..3 = u, v, w, T][npg]
+  int lo[3], ext[3];   // k_qderiv3: box of points (interior-relative origin, extent)
+  int zchunk;          // k_qderiv_int: interior planes per CTA
 };
+
+__device__ __forceinline__ double rcp_nr(double x)
+{
+  // MUFU.RCP64H seed + one cubic Newton step (relative error <= 2.2e-16, profiles/r01_microbench.txt);
+  // x is a density: positive and normal wherever the result is used
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  e = fma(e, e, e);
+  return fma(r, e, r);
+}
 
 __device__ __forceinline__ void prim4(const double* __restrict__ u, long long npg, long long p, double gamma, double (&q)[4])
 {
@@ -38,12 +51,18 @@ __device__ __forceinline__ void prim4(const double* __restrict__ u, long long np
   q[0] = vx; q[1] = vy; q[2] = vz; q[3] = gamma * P * rinv;
 }
 
+// One thread per point of a box, general in position (biased stencils next to the line ends, transverse
+// indices must be interior). The production path uses it for the six ghost slabs only (3.5 % of the points at
+// 512^3); the interior is k_qderiv_int below.
 __global__ void __launch_bounds__(128) k_qderiv3(const QD3Args a)
 {
   const Geom& G = a.G;
   const int g = G.g;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x - g, j = blockIdx.y - g, k = blockIdx.z - g;
-  if (i >= G.N[0] + g) return;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)a.ext[0] * a.ext[1] * a.ext[2]) return;
+  const int i = a.lo[0] + (int)(t % a.ext[0]);
+  const int j = a.lo[1] + (int)((t / a.ext[0]) % a.ext[1]);
+  const int k = a.lo[2] + (int)(t / ((long long)a.ext[0] * a.ext[1]));
   const bool in0 = (i >= 0 && i < G.N[0]), in1 = (j >= 0 && j < G.N[1]), in2 = (k >= 0 && k < G.N[2]);
   if ((int)in0 + (int)in1 + (int)in2 < 2) return;                     // edges / corners: never touched
   const long long p = (i + g) + (long long)G.P[0] * ((j + g) + (long long)G.P[1] * (k + g));
@@ -89,18 +108,114 @@ __global__ void __launch_bounds__(128) k_qderiv3(const QD3Args a)
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Interior points: all three differences are the central one, (f[-2] - 8 f[-1] + 8 f[+1] - f[+2]) / 12
+// (FirstDerivativeFourthOrder.c:103). A CTA owns a 32(x) x 8(y) column and marches over `zchunk` planes:
+//   * the primitive variables (u, v, w, T) of a point are evaluated ONCE per column and kept in a 5-plane
+//     register window (z-difference from registers);
+//   * the centre plane plus a 2-cell x/y halo (evaluated by the first 160 threads) is staged in shared memory,
+//     double-buffered: one __syncthreads per plane (x- and y-differences from shared memory);
+//   * 12 coalesced stores per point.
+// Work per point: 1.6 primitive evaluations instead of 13, one reciprocal (Newton, no IEEE division),
+// exp + log for mu = T^0.76. HBM: 40 B read + 96 B written per point.
+constexpr int QTX = 32, QTY = 8, QH = 2;
+constexpr int QSX = QTX + 2 * QH + 1;      // padded row (37): conflict-free column access is not needed, rows are read along x
+constexpr int QSY = QTY + 2 * QH;
+
+__device__ __forceinline__ void prim4f(const double* __restrict__ u, long long npg, long long p, double gamma, double (&q)[4])
+{
+  const double rho = __ldg(u + p);
+  const double m0 = __ldg(u + npg + p), m1 = __ldg(u + 2 * npg + p), m2 = __ldg(u + 3 * npg + p);
+  const double e = __ldg(u + 4 * npg + p);
+  const double rinv = rcp_nr(rho);
+  const double vx = m0 * rinv, vy = m1 * rinv, vz = m2 * rinv;
+  const double P = (e - 0.5 * rho * (vx * vx + vy * vy + vz * vz)) * (gamma - 1.0);
+  q[0] = vx; q[1] = vy; q[2] = vz; q[3] = gamma * P * rinv;
+}
+
+__global__ void __launch_bounds__(QTX * QTY, 2) k_qderiv_int(const QD3Args a)
+{
+  __shared__ double Q[2][4][QSY][QSX];
+  const Geom& G = a.G;
+  const int g = G.g;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * QTX + tx;
+  const int i0 = blockIdx.x * QTX, j0 = blockIdx.y * QTY;
+  const int i = i0 + tx, j = j0 + ty;
+  const int kb = blockIdx.z * a.zchunk, ke = min(kb + a.zchunk, G.N[2]);
+  const bool ok = (i < G.N[0]) && (j < G.N[1]);
+  // partial tiles: the two ghost columns / rows next to the interior lie INSIDE the thread tile; their threads
+  // own no output but must stage the centre plane for their neighbours
+  const bool edge = !ok && ((i < G.N[0] + QH && j < G.N[1]) || (i < G.N[0] && j < G.N[1] + QH));
+  const long long npg = G.npg, sz = G.st[2];
+  const long long pcol = (i + g) + (long long)G.P[0] * (j + g);             // + P0*P1*(k+g)
+  // halo assignment of threads 0..159: 4 columns x 8 rows (x-halo), then 32 columns x 4 rows (y-halo)
+  int hi = 0, hj = 0; bool hok = false;
+  if (tid < 4 * QTY) {
+    const int c = tid % 4, r = tid / 4;
+    hi = (c < 2) ? (c - 2) : (QTX + c - 2); hj = r; hok = true;
+  } else if (tid < 4 * QTY + 4 * QTX) {
+    const int t = tid - 4 * QTY, c = t % QTX, r = t / QTX;
+    hi = c; hj = (r < 2) ? (r - 2) : (QTY + r - 2); hok = true;
+  }
+  // the halo point must exist in the array and have at least one interior transverse index partner: x-halo rows
+  // are interior in y iff j0+hj < N1; y-halo columns interior in x iff i0+hi < N0 (otherwise never consumed)
+  const int ghi = i0 + hi, ghj = j0 + hj;
+  hok = hok && (ghi + g < G.P[0]) && (ghj + g < G.P[1]) && (ghi < G.N[0] + g) && (ghj < G.N[1] + g);
+  const long long phalo = (ghi + g) + (long long)G.P[0] * (ghj + g);
+
+  double w[5][4];                                                            // planes k-2 .. k+2
+#pragma unroll
+  for (int s = 0; s < 5; s++) { w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0.0; }
+  if (ok) {
+#pragma unroll
+    for (int s = 1; s < 5; s++) prim4f(a.u, npg, pcol + sz * (kb + s - 3 + g), a.gamma, w[s]);
+  }
+  const double s12 = 1.0 / 12.0;
+  for (int k = kb; k < ke; k++) {
+    const int b = (k - kb) & 1;
+    const long long pk = sz * (k + g);
+    // shift the window, evaluate plane k+2
+#pragma unroll
+    for (int s = 0; s < 4; s++) { w[s][0] = w[s + 1][0]; w[s][1] = w[s + 1][1]; w[s][2] = w[s + 1][2]; w[s][3] = w[s + 1][3]; }
+    if (ok) prim4f(a.u, npg, pcol + pk + 2 * sz, a.gamma, w[4]);
+    if (edge) prim4f(a.u, npg, pcol + pk, a.gamma, w[2]);
+#pragma unroll
+    for (int c = 0; c < 4; c++) Q[b][c][ty + QH][tx + QH] = w[2][c];
+    if (hok) {
+      double h[4];
+      prim4f(a.u, npg, phalo + pk, a.gamma, h);
+#pragma unroll
+      for (int c = 0; c < 4; c++) Q[b][c][hj + QH][hi + QH] = h[c];
+    }
+    __syncthreads();
+    if (ok) {
+      const double muRe = exp(0.76 * log(w[2][3])) * a.inv_Re;
+      const long long p = pcol + pk;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const double* r = &Q[b][c][ty + QH][tx + QH];
+        const double dx = (r[-2] - 8 * r[-1] + 8 * r[1] - r[2]) * s12;
+        const double dy = (r[-2 * QSX] - 8 * r[-QSX] + 8 * r[QSX] - r[2 * QSX]) * s12;
+        const double dz = (w[0][c] - 8 * w[1][c] + 8 * w[3][c] - w[4][c]) * s12;
+        a.qd[(long long)(0 * 4 + c) * npg + p] = dx * muRe;
+        a.qd[(long long)(1 * 4 + c) * npg + p] = dy * muRe;
+        a.qd[(long long)(2 * 4 + c) * npg + p] = dz * muRe;
+      }
+    }
+  }
+}
+
 // pack / unpack of one 4-component derivative array face (same face boxes as the solution exchange)
 __global__ void k_face4(Geom G, double* __restrict__ a, int d, int off_d, double* __restrict__ buf, int to_buf)
 {
   int b[3] = { G.N[0], G.N[1], G.N[2] };
   b[d] = G.g;
-  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y, t2 = blockIdx.z;
-  if (t0 >= b[0]) return;
-  int s[3] = { t0, t1, t2 };
+  const long long nface = (long long)b[0] * b[1] * b[2];
+  const long long p2 = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // linear over the face box, dim 0 fastest
+  if (p2 >= nface) return;
+  int s[3] = { (int)(p2 % b[0]), (int)((p2 / b[0]) % b[1]), (int)(p2 / ((long long)b[0] * b[1])) };
   s[d] += off_d;
   const long long p1 = (s[0] + G.g) + (long long)G.P[0] * ((s[1] + G.g) + (long long)G.P[1] * (s[2] + G.g));
-  const long long nface = (long long)b[0] * b[1] * b[2];
-  const long long p2 = t0 + (long long)b[0] * (t1 + (long long)b[1] * t2);
   if (to_buf) for (int v = 0; v < 4; v++) buf[v * nface + p2] = a[v * G.npg + p1];
   else        for (int v = 0; v < 4; v++) a[v * G.npg + p1] = buf[v * nface + p2];
 }
@@ -114,9 +229,25 @@ void qderiv_fused(hpb_solver* h, const double* u)
   ProfScope ps(h, HPB_PROF_VISCOUS);
   const Geom& G = h->geo;
   QD3Args a; a.G = G; a.gamma = h->phys.gamma; a.inv_Re = 1.0 / h->phys.Re; a.u = u; a.dxinv = h->d_dxinv; a.qd = h->d_qd4;
-  dim3 grid((G.P[0] + 127) / 128, G.P[1], G.P[2]);
-  k_qderiv3<<<grid, 128, 0, h->stream>>>(a);
-  h->launches++;
+  // interior: tiled march
+  a.zchunk = 64;
+  for (int d = 0; d < 3; d++) { a.lo[d] = 0; a.ext[d] = G.N[d]; }
+  {
+    dim3 grid((G.N[0] + QTX - 1) / QTX, (G.N[1] + QTY - 1) / QTY, (G.N[2] + a.zchunk - 1) / a.zchunk);
+    k_qderiv_int<<<grid, dim3(QTX, QTY, 1), 0, h->stream>>>(a);
+    h->launches++;
+  }
+  // the six ghost slabs (normal derivative only; the outermost layer is skipped inside the kernel)
+  for (int d = 0; d < 3; d++) {
+    for (int f = 0; f < 2; f++) {
+      for (int k = 0; k < 3; k++) { a.lo[k] = 0; a.ext[k] = G.N[k]; }
+      a.lo[d] = f ? G.N[d] : -G.g;
+      a.ext[d] = G.g;
+      const long long n = (long long)a.ext[0] * a.ext[1] * a.ext[2];
+      k_qderiv3<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a);
+      h->launches++;
+    }
+  }
 }
 
 static void face4(hpb_solver* h, double* a, int d, int off_d, double* buf, int to_buf)
@@ -124,7 +255,7 @@ static void face4(hpb_solver* h, double* a, int d, int off_d, double* buf, int t
   const Geom& G = h->geo;
   int b[3] = { G.N[0], G.N[1], G.N[2] };
   b[d] = G.g;
-  k_face4<<<dim3((b[0] + 127) / 128, b[1], b[2]), 128, 0, h->stream>>>(G, a, d, off_d, buf, to_buf);
+  k_face4<<<(unsigned)(((long long)b[0] * b[1] * b[2] + 127) / 128), 128, 0, h->stream>>>(G, a, d, off_d, buf, to_buf);
   h->launches++;
 }
 
