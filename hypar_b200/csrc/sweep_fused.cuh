@@ -92,6 +92,19 @@ __device__ __forceinline__ double rcp_fast(double x)
   return fma(r, e, r);
 }
 
+__device__ __forceinline__ double sqrt_fast(double x)
+{
+  // MUFU.RSQ64H seed (relative error ~1e-6) + two coupled Newton steps on (sqrt x, 1 / (2 sqrt x)): the error
+  // is squared twice (below 1e-20 before rounding). x > 0 and normal (densities, squared sound speeds).
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-h, g, 0.5);
+  return fma(g, r, g);
+}
+
 // ------------------------------------------------------------------------------------------
 // Both reconstructions a centred 5-cell stencil serves. X = values the weights are computed from,
 // Y = values that are reconstructed (Y == X for the flux; Y = uC, X = raw u for the solution: Q4).
@@ -126,24 +139,27 @@ __device__ __forceinline__ void recon_pair(const double (&X)[5], const double (&
     if (HASZ) { ZL = c1 * zL1 + c2 * zL2 + c3 * zL3; ZR = c3 * zR1 + c2 * zR2 + c1 * zR3; }
     return;
   }
-  // smoothness indicators of the three sub-stencils (shared by both biases)
-  const double t12 = 13.0 / 12.0;
+  // smoothness indicators of the three sub-stencils (shared by both biases), scaled by 4: b_k = 4 beta_k =
+  // 13/3 d^2 + e^2 (one operation less each). The weights are homogeneous of degree 0 in (beta + eps), so
+  // eps and tau are scaled alike and nothing else changes.
+  const double t133 = 13.0 / 3.0;
   const double d1 = X[0] - 2*X[1] + X[2], e1 = X[0] - 4*X[1] + 3*X[2];
   const double d2 = X[1] - 2*X[2] + X[3], e2 = X[1] - X[3];
   const double d3 = X[2] - 2*X[3] + X[4], e3 = 3*X[2] - 4*X[3] + X[4];
-  const double b1 = t12 * d1 * d1 + 0.25 * e1 * e1;
-  const double b2 = t12 * d2 * d2 + 0.25 * e2 * e2;
-  const double b3 = t12 * d3 * d3 + 0.25 * e3 * e3;
-  const double s1 = b1 + eps, s2 = b2 + eps, s3 = b3 + eps;
+  const double b1 = fma(e1, e1, (t133 * d1) * d1);
+  const double b2 = fma(e2, e2, (t133 * d2) * d2);
+  const double b3 = fma(e3, e3, (t133 * d3) * d3);
+  const double eps4 = 4.0 * eps;
+  const double s1 = b1 + eps4, s2 = b2 + eps4, s3 = b3 + eps4;
   const double q1 = s1 * s1, q2 = s2 * s2, q3 = s3 * s3;
   // h_k proportional to 1/q_k (JS, M) or (1 + tau^2/q_k) (Z, YC), common positive factor dropped
   double h1, h2, h3;
   if (WT == HPB_WENO_JS || WT == HPB_WENO_M) {
     h1 = q2 * q3; h2 = q1 * q3; h3 = q1 * q2;
   } else {
-    double tau;
+    double tau;                                           // 4 tau
     if (WT == HPB_WENO_Z) tau = fabs(b3 - b1);
-    else { const double t = X[0] - 4*X[1] + 6*X[2] - 4*X[3] + X[4]; tau = t * t; }
+    else { const double t = 2*X[0] - 8*X[1] + 12*X[2] - 8*X[3] + 2*X[4]; tau = t * t; }
     const double tt = tau * tau;
     h1 = (q1 + tt) * (q2 * q3); h2 = (q2 + tt) * (q1 * q3); h3 = (q3 + tt) * (q1 * q2);
   }

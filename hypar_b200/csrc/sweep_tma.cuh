@@ -235,9 +235,9 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
       for (int v = 0; v < NV; v++) rec[(LY::rU + v) * NREC + ci] = U[v];
       const double rho = U[0];
       double vel[3] = { 0.0, 0.0, 0.0 };
-      const double rinv = 1.0 / rho;
+      const double rinv = rcp_fast(rho);          // face ghosts are filled: rho > 0 wherever a record is built
 #pragma unroll
-      for (int k = 0; k < NDV; k++) vel[k] = (rho == 0) ? 0.0 : U[1 + k] * rinv;
+      for (int k = 0; k < NDV; k++) vel[k] = U[1 + k] * rinv;
       double vsq = 0.0;
 #pragma unroll
       for (int k = 0; k < NDV; k++) vsq += vel[k] * vel[k];
@@ -255,13 +255,13 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
         rec[LY::rGF * NREC + ci] = gfv; rec[(LY::rGF + 1) * NREC + ci] = ggv;
       }
       const double igm1 = 1.0 / (gamma - 1.0);
-      rec[LY::rV4 * NREC + ci] = G3 ? ((P * igm1) * (1.0 / ggv) + ke * gfv) : (P * igm1 + ke);
+      rec[LY::rV4 * NREC + ci] = G3 ? ((P * igm1) * rcp_fast(ggv) + ke * gfv) : (P * igm1 + ke);
       const double c2 = gamma * P * rinv;
-      rec[LY::rSR * NREC + ci] = sqrt(rho);
+      rec[LY::rSR * NREC + ci] = sqrt_fast(rho);
 #pragma unroll
       for (int k = 0; k < NDV; k++) rec[(LY::rVEL + k) * NREC + ci] = vel[k];
       rec[LY::rH * NREC + ci] = 0.5 * vsq + c2 * igm1;
-      rec[LY::rA * NREC + ci] = sqrt(c2) + fabs(vn);
+      rec[LY::rA * NREC + ci] = sqrt_fast(c2) + fabs(vn);
       if (V3) {
         double q[8];
 #pragma unroll
@@ -295,7 +295,37 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
     double fRv[NV], uRv[NV], sR[2] = { 0.0, 0.0 };
 #pragma unroll
     for (int v = 0; v < NV; v++) { fRv[v] = 0.0; uRv[v] = 0.0; }
-    if (rc_ok) {
+    if (!G3 && m == -1) {
+      // start-up step: only the stencils centred on cells -1 and 0 exist (lanes 30, 31 in the regular mapping, which
+      // would cost the warp a full step for two cells). Spread their 2 x (2 NV - 1) reconstructions over the lanes
+      // instead: lane t < 2 NP handles (cell t / NP, pair t % NP), pairs = flux components 1..NV-1, then solution
+      // components 0..NV-1. Left-biased values go to the exchange slots the regular P3 reads (31, 32), the
+      // right-biased values of cell 0 to slot 1 (free during this step), from where lane 31 picks them up.
+      constexpr int NP = 2 * NV - 1;
+      if (line_ok && l < 2 * NP) {
+        const int ce = l / NP, pr = l - ce * NP;
+        const bool isU = pr >= NV - 1;
+        const int v = isU ? pr - (NV - 1) : pr + 1;
+        const int fx = isU ? LY::rU + v : LY::rF + v;
+        const int fy = (isU && v == NV - 1) ? LY::rV4 : fx;
+        const int cp = rbase + 33 + ce;
+        double X[5], Y[5], L, R, zl, zr;
+#pragma unroll
+        for (int k = 0; k < 5; k++) { X[k] = rec[fx * NREC + cp + (k - 2)]; Y[k] = rec[fy * NREC + cp + (k - 2)]; }
+        recon_pair<WT, false>(X, Y, Y, a.ph.eps, L, R, zl, zr);
+        const int xf = isU ? LY::xU + v : LY::xF + v;
+        exL[xf * NEX + xbase + 31 + ce] = L;
+        if (ce == 1) exL[xf * NEX + xbase + 1] = R;
+      }
+      __syncwarp();
+      if (line_ok && l == 31) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) uRv[v] = exL[(LY::xU + v) * NEX + xbase + 1];
+#pragma unroll
+        for (int v = 1; v < NV; v++) fRv[v] = exL[(LY::xF + v) * NEX + xbase + 1];
+        fRv[0] = (dir == 0) ? uRv[1] : ((dir == 1 || NDV < 3) ? uRv[2] : uRv[NDV]);
+      }
+    } else if (rc_ok) {
       double Zg[5] = { 0, 0, 0, 0, 0 };
       if (G3) {
 #pragma unroll
@@ -347,7 +377,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
       const int exl = xbase + l;              // left-biased values of cell j-1 (slot 0: carry)
       const int cL = cc - 1, cR = cc;
       const double tL = rec[LY::rSR * NREC + cL], tR = rec[LY::rSR * NREC + cR];
-      const double rs = 1.0 / (tL + tR);
+      const double rs = rcp_fast(tL + tR);
       double vsq = 0.0, vn = 0.0;
 #pragma unroll
       for (int k = 0; k < NDV; k++) {
@@ -356,7 +386,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
         if (k == dir) vn = v;
       }
       const double H = (tL * rec[LY::rH * NREC + cL] + tR * rec[LY::rH * NREC + cR]) * rs;
-      const double cavg = sqrt((gamma - 1.0) * (H - 0.5 * vsq));
+      const double cavg = sqrt_fast((gamma - 1.0) * (H - 0.5 * vsq));
       const double aavg = cavg + fabs(vn);
       double alpha = fmax(fmax(rec[LY::rA * NREC + cL], rec[LY::rA * NREC + cR]), aavg);
       if (G3) alpha *= fmax(rec[(LY::rGF + 1) * NREC + cL], rec[(LY::rGF + 1) * NREC + cR]);

@@ -122,14 +122,17 @@ constexpr int QTX = 32, QTY = 8, QH = 2;
 constexpr int QSX = QTX + 2 * QH + 1;      // padded row (37): conflict-free column access is not needed, rows are read along x
 constexpr int QSY = QTY + 2 * QH;
 
-__device__ __forceinline__ void prim4f(const double* __restrict__ u, long long npg, long long p, double gamma, double (&q)[4])
+__device__ __forceinline__ void load5(const double* __restrict__ u, long long npg, long long p, double (&r)[5])
 {
-  const double rho = __ldg(u + p);
-  const double m0 = __ldg(u + npg + p), m1 = __ldg(u + 2 * npg + p), m2 = __ldg(u + 3 * npg + p);
-  const double e = __ldg(u + 4 * npg + p);
+#pragma unroll
+  for (int v = 0; v < 5; v++) r[v] = __ldg(u + v * npg + p);
+}
+__device__ __forceinline__ void prim_of(const double (&r)[5], double gamma, double (&q)[4])
+{
+  const double rho = r[0];
   const double rinv = rcp_nr(rho);
-  const double vx = m0 * rinv, vy = m1 * rinv, vz = m2 * rinv;
-  const double P = (e - 0.5 * rho * (vx * vx + vy * vy + vz * vz)) * (gamma - 1.0);
+  const double vx = r[1] * rinv, vy = r[2] * rinv, vz = r[3] * rinv;
+  const double P = (r[4] - 0.5 * rho * (vx * vx + vy * vy + vz * vz)) * (gamma - 1.0);
   q[0] = vx; q[1] = vy; q[2] = vz; q[3] = gamma * P * rinv;
 }
 
@@ -157,33 +160,46 @@ __global__ void __launch_bounds__(QTX * QTY, 2) k_qderiv_int(const QD3Args a)
     const int t = tid - 4 * QTY, c = t % QTX, r = t / QTX;
     hi = c; hj = (r < 2) ? (r - 2) : (QTY + r - 2); hok = true;
   }
-  // the halo point must exist in the array and have at least one interior transverse index partner: x-halo rows
-  // are interior in y iff j0+hj < N1; y-halo columns interior in x iff i0+hi < N0 (otherwise never consumed)
   const int ghi = i0 + hi, ghj = j0 + hj;
-  hok = hok && (ghi + g < G.P[0]) && (ghj + g < G.P[1]) && (ghi < G.N[0] + g) && (ghj < G.N[1] + g);
+  hok = hok && (ghi + g < G.P[0]) && (ghj + g < G.P[1]);
   const long long phalo = (ghi + g) + (long long)G.P[0] * (ghj + g);
 
   double w[5][4];                                                            // planes k-2 .. k+2
 #pragma unroll
   for (int s = 0; s < 5; s++) { w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0.0; }
+  double nu[5] = { 1.0, 0.0, 0.0, 0.0, 1.0 };                                // raw u, own column, plane k+2 (one plane ahead)
+  double hu[5] = { 1.0, 0.0, 0.0, 0.0, 1.0 };                                // raw u, halo / edge point, plane k
   if (ok) {
 #pragma unroll
-    for (int s = 1; s < 5; s++) prim4f(a.u, npg, pcol + sz * (kb + s - 3 + g), a.gamma, w[s]);
+    for (int s = 1; s < 5; s++) {                                            // w[1..4] = planes kb-2 .. kb+1
+      double r[5];
+      load5(a.u, npg, pcol + sz * (kb + s - 3 + g), r);
+      prim_of(r, a.gamma, w[s]);
+    }
+    load5(a.u, npg, pcol + sz * (kb + 2 + g), nu);
   }
+  if (edge) load5(a.u, npg, pcol + sz * (kb + g), nu);                       // edge threads: centre plane only
+  if (hok) load5(a.u, npg, phalo + sz * (kb + g), hu);
   const double s12 = 1.0 / 12.0;
   for (int k = kb; k < ke; k++) {
     const int b = (k - kb) & 1;
     const long long pk = sz * (k + g);
-    // shift the window, evaluate plane k+2
+    // shift the window; plane k+2 from the values requested one iteration ago; request the next ones
 #pragma unroll
     for (int s = 0; s < 4; s++) { w[s][0] = w[s + 1][0]; w[s][1] = w[s + 1][1]; w[s][2] = w[s + 1][2]; w[s][3] = w[s + 1][3]; }
-    if (ok) prim4f(a.u, npg, pcol + pk + 2 * sz, a.gamma, w[4]);
-    if (edge) prim4f(a.u, npg, pcol + pk, a.gamma, w[2]);
+    if (ok) {
+      prim_of(nu, a.gamma, w[4]);
+      if (k + 1 < ke) load5(a.u, npg, pcol + pk + 3 * sz, nu);
+    } else if (edge) {
+      prim_of(nu, a.gamma, w[2]);
+      if (k + 1 < ke) load5(a.u, npg, pcol + pk + sz, nu);
+    }
 #pragma unroll
     for (int c = 0; c < 4; c++) Q[b][c][ty + QH][tx + QH] = w[2][c];
     if (hok) {
       double h[4];
-      prim4f(a.u, npg, phalo + pk, a.gamma, h);
+      prim_of(hu, a.gamma, h);
+      if (k + 1 < ke) load5(a.u, npg, phalo + pk + sz, hu);
 #pragma unroll
       for (int c = 0; c < 4; c++) Q[b][c][hj + QH][hi + QH] = h[c];
     }
