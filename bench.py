@@ -211,7 +211,7 @@ def gpu_arm(args):
         stepper = None
     else:
         from hypar_b200.multigpu import DistributedSolver
-        stepper = DistributedSolver(s, b, ph, w, x, rank=rank, device=local_rank)
+        stepper = DistributedSolver(s, b, ph, w, x, rank=rank, device=local_rank, overlap=not args.no_overlap)
         sv = stepper.solver
     g = sv.ghosts
     nloc = sv.dim_local
@@ -357,6 +357,8 @@ def gpu_arm(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"C4 NavierStokes3D WENO5(mapped)+Rusanov+viscous RK4, {size[0]}x{size[1]}x{size[2]} periodic",
                    "points_per_gpu": f"{nloc[0]}x{nloc[1]}x{nloc[2]}", "iproc": iproc, "rk_stages_per_step": NSTAGES,
+                   "halo": (None if stepper is None else ("NCCL send/recv on a communication stream, overlapped with the "
+                            "Q-derivative kernel and the sweeps" if stepper.overlap else "NCCL send/recv, serial")),
                    "l2": "working set (5.6 GB per array) >> L2, no flush needed"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
@@ -379,6 +381,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=64, help="grid of the cpu_baseline sample")
     ap.add_argument("--ref-n", type=int, default=64, help="grid of the --impl reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: serial halo exchange (no communication stream)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

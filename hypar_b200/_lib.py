@@ -52,7 +52,8 @@ SYMBOLS = [
     "hpb_dev_set_solution", "hpb_dev_get_solution", "hpb_dev_fill_solution_from_global", "hpb_TimeStep",
     "hpb_TimeSteps", "hpb_current_time", "hpb_dev_ComputeCFL", "hpb_dev_StepNormSumSq", "hpb_dev_RHS",
     "hpb_halo_buffers", "hpb_step_begin", "hpb_step_halo_done", "hpb_stage_begin", "hpb_stage_halo_done",
-    "hpb_stage_rhs_a", "hpb_stage_rhs_b", "hpb_step_finish", "hpb_dev_get_stage_rhs", "hpb_nstages", "hpb_needs_viscous_exchange",
+    "hpb_stage_rhs_a", "hpb_stage_rhs_b", "hpb_step_finish", "hpb_stage_overlap_supported", "hpb_stage_interior",
+    "hpb_stage_halo_done_dim", "hpb_stage_sweep", "hpb_dev_get_stage_rhs", "hpb_nstages", "hpb_needs_viscous_exchange",
     "hpb_stream", "hpb_synchronize", "hpb_kernel_launch_count", "hpb_tma_launch_count", "hpb_profile_enable", "hpb_profile_query",
 ]
 
@@ -116,8 +117,11 @@ def load():
     for name in ("hpb_step_begin", "hpb_step_halo_done", "hpb_step_finish", "hpb_nstages",
                  "hpb_needs_viscous_exchange", "hpb_synchronize"):
         getattr(L, name).argtypes = [vp]
-    for name in ("hpb_stage_begin", "hpb_stage_halo_done", "hpb_stage_rhs_a", "hpb_stage_rhs_b"):
+    for name in ("hpb_stage_begin", "hpb_stage_halo_done", "hpb_stage_rhs_a", "hpb_stage_rhs_b", "hpb_stage_interior"):
         getattr(L, name).argtypes = [vp, C.c_int]
+    L.hpb_stage_overlap_supported.argtypes = [vp]
+    L.hpb_stage_halo_done_dim.argtypes = [vp, C.c_int, C.c_int]
+    L.hpb_stage_sweep.argtypes = [vp, C.c_int, C.c_int]
     L.hpb_dev_get_stage_rhs.argtypes = [vp, C.c_int, dp]
     L.hpb_stream.argtypes = [vp]
     L.hpb_stream.restype = vp

@@ -318,8 +318,11 @@ extern "C" int hpb_profile_query(hpb_solver* h, int category, double* total_ms, 
 static int rhs_part_a(hpb_solver* h, const double* U, double* rhs)
 {
   if (fused_path(h)) {
-    if (fused_visc(h)) hpbk::qderiv_fused(h, U);
-    else {
+    if (fused_visc(h)) {
+      // part 2 when hpb_stage_interior already did the halo-independent part of this stage
+      hpbk::qderiv_fused(h, U, h->interior_stage >= 0 ? 2 : 0);
+      h->interior_stage = -1;
+    } else {
       hpbk::hyperbolic_fused(h, U, rhs, /*negate=*/true, /*with_source=*/true, rhs, nullptr);
       if (viscous_on(h)) hpbk::parabolic_phase1(h, U);          // NavierStokes2D viscous terms: generic kernels
     }
@@ -704,16 +707,62 @@ extern "C" int hpb_stage_begin(hpb_solver* h, int stage)
   return check_async(h, "stage_begin");
 }
 
-extern "C" int hpb_stage_halo_done(hpb_solver* h, int field)
+static int halo_done(hpb_solver* h, int field, int dim)
 {
   TRY(need_device(h));
-  if (field == HPB_FIELD_U) hpbk::unpack(h, h->U_cur ? h->U_cur : h->d_U, h->geo.nvars, HPB_FIELD_U);
+  if (dim >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "stage_halo_done: dimension %d", dim);
+  if (field == HPB_FIELD_U) hpbk::unpack(h, h->U_cur ? h->U_cur : h->d_U, h->geo.nvars, HPB_FIELD_U, dim);
   else if (field == HPB_FIELD_QDERIVX || field == HPB_FIELD_QDERIVY) {
     if (!viscous_on(h)) return hpb_fail(HPB_ERR_INVALID, "stage_halo_done: no viscous exchange in this configuration");
-    if (fused_visc(h)) hpbk::unpack_qd4(h, field);
-    else hpbk::unpack(h, h->d_QD[field - 1], h->geo.nvars, field);
+    if (fused_visc(h)) hpbk::unpack_qd4(h, field, dim);
+    else hpbk::unpack(h, h->d_QD[field - 1], h->geo.nvars, field, dim);
   } else return hpb_fail(HPB_ERR_INVALID, "stage_halo_done: field %d", field);
   return check_async(h, "stage_halo_done");
+}
+extern "C" int hpb_stage_halo_done(hpb_solver* h, int field) { return halo_done(h, field, -1); }
+extern "C" int hpb_stage_halo_done_dim(hpb_solver* h, int field, int dim)
+{
+  if (dim < 0) return hpb_fail(HPB_ERR_INVALID, "stage_halo_done_dim: dimension %d", dim);
+  return halo_done(h, field, dim);
+}
+
+// 1 when the production path of this configuration can be driven sweep by sweep (hpb_stage_interior /
+// hpb_stage_sweep): fused sweeps with everything but the Q-derivatives inside them
+extern "C" int hpb_stage_overlap_supported(const hpb_solver* h)
+{
+  if (!fused_path(h)) return 0;
+  if (viscous_on(h) && !fused_visc(h)) return 0;
+  if (h->cfg.model == HPB_MODEL_LINEAR_ADR) return 0;
+  return 1;
+}
+
+// the part of stage `stage` that reads no ghost cell of the stage solution: may be issued while the exchange of
+// FIELD_U is in flight (viscous production path: Q-derivatives of the deep interior; otherwise nothing)
+extern "C" int hpb_stage_interior(hpb_solver* h, int stage)
+{
+  TRY(need_device(h));
+  if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
+  if (!hpb_stage_overlap_supported(h)) return hpb_fail(HPB_ERR_INVALID, "stage_interior: configuration is not driven sweep by sweep");
+  if (fused_visc(h)) {
+    hpbk::qderiv_fused(h, h->U_cur ? h->U_cur : h->d_U, 1);
+    h->interior_stage = stage;
+  }
+  return check_async(h, "stage_interior");
+}
+
+// one directional sweep of stage `stage` (needs the FIELD_U halo of dimension `dir` and, with viscous terms, the
+// Q-derivative halos of dimension `dir` only); dir = 0 must come first (it overwrites Udot[stage])
+extern "C" int hpb_stage_sweep(hpb_solver* h, int stage, int dir)
+{
+  TRY(need_device(h));
+  if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
+  if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "stage_sweep: direction %d", dir);
+  if (!hpb_stage_overlap_supported(h)) return hpb_fail(HPB_ERR_INVALID, "stage_sweep: configuration is not driven sweep by sweep");
+  double* U = h->U_cur ? h->U_cur : h->d_U;
+  double* rhs = h->d_Udot[stage];
+  if (!hpbk::hyperbolic_fused(h, U, rhs, true, true, rhs, fused_visc(h) ? h->d_qd4 : nullptr, dir))
+    return hpb_fail(HPB_ERR_CUDA, "stage_sweep: launch failed");
+  return check_async(h, "stage_sweep");
 }
 
 extern "C" int hpb_stage_rhs_a(hpb_solver* h, int stage)

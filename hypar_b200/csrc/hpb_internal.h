@@ -61,6 +61,7 @@ struct hpb_solver {
   double *d_u = nullptr;           // solution (SoA, ghosts)
   double *d_uprev = nullptr;       // u at the start of the step (norm)
   double *d_U = nullptr;           // stage solution
+  int interior_stage = -1;         // staged API: stage whose halo-independent work (hpb_stage_interior) is already done
   double *U_cur = nullptr;         // staged API: the array holding the current stage solution (d_u for stage 0)
   double *d_Udot[4] = {nullptr, nullptr, nullptr, nullptr};
   double *d_fI = nullptr;          // interface flux (generic path), max over dirs
@@ -111,7 +112,7 @@ void aos_to_soa(hpb_solver* h, const double* aos, double* soa, long long npts, i
 void soa_to_aos(hpb_solver* h, const double* soa, double* aos, long long npts, int nv);
 void apply_bc(hpb_solver* h, double* u);
 void pack(hpb_solver* h, const double* a, int nv, int field);
-void unpack(hpb_solver* h, double* a, int nv, int field);
+void unpack(hpb_solver* h, double* a, int nv, int field, int only_dim = -1);
 // hyperbolic term. negate=true: out = -sum_d dxinv*(fhat_{j+1}-fhat_j) (the first direction overwrites the
 // interior, i.e. includes the zeroing of TimeRHSFunctionExplicit.c:89); negate=false: out = +hyp.
 // with_source: gravity-source contribution of each gravity direction is ADDED to src (quirk Q5).
@@ -120,11 +121,11 @@ void hyperbolic_generic(hpb_solver* h, const double* u, double* out, bool negate
 // fused sweeps (sweep_fused.cu); qd != nullptr: the NavierStokes3D viscous terms are evaluated inside the sweeps
 bool fused_available(const hpb_solver* h);
 bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src,
-                      const double* qd);
+                      const double* qd, int only_dir = -1);
 // fused viscous path (viscous_fused.cu)
-void qderiv_fused(hpb_solver* h, const double* u);
+void qderiv_fused(hpb_solver* h, const double* u, int part = 0);
 void pack_qd4(hpb_solver* h, int field);
-void unpack_qd4(hpb_solver* h, int field);
+void unpack_qd4(hpb_solver* h, int field, int only_dim = -1);
 // exact path: rhs = (rhs + par) + src in the reference's order (TimeRHSFunctionExplicit.c:89-92)
 void combine_rhs(hpb_solver* h, double* rhs, const double* par, const double* src);
 void parabolic_phase1(hpb_solver* h, const double* u);

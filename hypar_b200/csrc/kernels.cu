@@ -835,11 +835,12 @@ void pack(hpb_solver* h, const double* a, int nv, int field)
     if (h->neighbor[2*d+1] >= 0) face_launch(h, (double*)a, nv, d, G.N[d] - G.g, h->d_send[field][2*d+1], 1);
   }
 }
-void unpack(hpb_solver* h, double* a, int nv, int field)
+void unpack(hpb_solver* h, double* a, int nv, int field, int only_dim)
 {
   ProfScope ps(h, HPB_PROF_HALO);
   const Geom& G = h->geo;
   for (int d = 0; d < G.ndims; d++) {
+    if (only_dim >= 0 && d != only_dim) continue;
     if (h->neighbor[2*d] >= 0)   face_launch(h, a, nv, d, -G.g, h->d_recv[field][2*d], 0);
     if (h->neighbor[2*d+1] >= 0) face_launch(h, a, nv, d, G.N[d], h->d_recv[field][2*d+1], 0);
   }

@@ -95,12 +95,13 @@ bool fused_available(const hpb_solver* h)
 }
 
 bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src,
-                      const double* qd)
+                      const double* qd, int only_dir)
 {
   if (with_source && src != nullptr && src != out) return false;     // the fused kernels accumulate the source into `out`
   const Geom& G = h->geo;
   const int wt = h->phys.no_limiting ? hpbf::WT_NOLIM : h->phys.weno;
   for (int d = 0; d < G.ndims; d++) {
+    if (only_dir >= 0 && d != only_dir) continue;
     hpbf::SweepArgs a;
     a.G = G; a.ph = h->phys; a.u = u;
     a.gf = h->d_gravf; a.gg = h->d_gravg; a.dxinv = h->d_dxinv;
@@ -125,7 +126,7 @@ bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, 
     if (!ok) {
       // only possible before the first direction has written anything (attribute / grid limits are
       // direction-independent for a given configuration)
-      if (d == 0) return false;
+      if (d == 0 || only_dir >= 0) return false;
       hpb_fail(HPB_ERR_CUDA, "fused sweep launch failed in direction %d", d);
       return true;
     }

@@ -39,16 +39,41 @@ __device__ __forceinline__ double rcp_nr(double x)
   return fma(r, e, r);
 }
 
+__device__ __forceinline__ void load5(const double* __restrict__ u, long long npg, long long p, double (&r)[5])
+{
+#pragma unroll
+  for (int v = 0; v < 5; v++) r[v] = __ldg(u + v * npg + p);
+}
+// (u, v, w, T = gamma p / rho) from the conserved variables; shared by both kernels so that a point gets the same
+// bits whichever kernel evaluates it (the overlapped multi-GPU schedule splits the interior differently)
+__device__ __forceinline__ void prim_of(const double (&r)[5], double gamma, double (&q)[4])
+{
+  // every operation spelled out (explicit fma / _rn intrinsics): no compiler-chosen contraction, so the two kernels
+  // cannot round differently
+  const double rho = r[0];
+  const double rinv = rcp_nr(rho);
+  const double vx = (rho == 0) ? 0.0 : __dmul_rn(r[1], rinv);
+  const double vy = (rho == 0) ? 0.0 : __dmul_rn(r[2], rinv);
+  const double vz = (rho == 0) ? 0.0 : __dmul_rn(r[3], rinv);
+  const double vsq = fma(vz, vz, fma(vy, vy, __dmul_rn(vx, vx)));
+  const double P = __dmul_rn(fma(__dmul_rn(-0.5, rho), vsq, r[4]), gamma - 1.0);
+  q[0] = vx; q[1] = vy; q[2] = vz; q[3] = __dmul_rn(__dmul_rn(gamma, P), rinv);
+}
+__device__ __forceinline__ double central4(double m2, double m1, double p1, double p2)
+{
+  return __dmul_rn(__dsub_rn(fma(8.0, p1, fma(-8.0, m1, m2)), p2), 1.0 / 12.0);
+}
+__device__ __forceinline__ double mu_over_Re(double T, double inv_Re)
+{
+  // mu = exp(0.76 log T) (raiseto, math_ops.h:37; NavierStokes3DParabolicFunction.c:174)
+  return __dmul_rn(exp(__dmul_rn(0.76, log(T))), inv_Re);
+}
+
 __device__ __forceinline__ void prim4(const double* __restrict__ u, long long npg, long long p, double gamma, double (&q)[4])
 {
-  const double rho = __ldg(u + p);
-  const double rinv = 1.0 / rho;
-  const double vx = (rho == 0) ? 0.0 : __ldg(u + npg + p) * rinv;
-  const double vy = (rho == 0) ? 0.0 : __ldg(u + 2 * npg + p) * rinv;
-  const double vz = (rho == 0) ? 0.0 : __ldg(u + 3 * npg + p) * rinv;
-  const double e = __ldg(u + 4 * npg + p);
-  const double P = (e - 0.5 * rho * (vx * vx + vy * vy + vz * vz)) * (gamma - 1.0);
-  q[0] = vx; q[1] = vy; q[2] = vz; q[3] = gamma * P * rinv;
+  double r[5];
+  load5(u, npg, p, r);
+  prim_of(r, gamma, q);
 }
 
 // One thread per point of a box, general in position (biased stencils next to the line ends, transverse
@@ -72,7 +97,7 @@ __global__ void __launch_bounds__(128) k_qderiv3(const QD3Args a)
   // mu/Re at this point: mu = exp(0.76 log T) (raiseto, math_ops.h:37; NavierStokes3DParabolicFunction.c:174)
   double qc[4];
   prim4(a.u, G.npg, p, a.gamma, qc);
-  const double muRe = exp(0.76 * log(qc[3])) * a.inv_Re;
+  const double muRe = mu_over_Re(qc[3], a.inv_Re);
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     // transverse indices must be interior
@@ -98,13 +123,13 @@ __global__ void __launch_bounds__(128) k_qderiv3(const QD3Args a)
       prim4(a.u, G.npg, p - 2 * st, a.gamma, fm2); prim4(a.u, G.npg, p - st, a.gamma, fm1);
       prim4(a.u, G.npg, p + st, a.gamma, fp1); prim4(a.u, G.npg, p + 2 * st, a.gamma, fp2);
 #pragma unroll
-      for (int c = 0; c < 4; c++) D[c] = (fm2[c] - 8 * fm1[c] + 8 * fp1[c] - fp2[c]) * s12;
+      for (int c = 0; c < 4; c++) D[c] = central4(fm2[c], fm1[c], fp1[c], fp2[c]);
     }
     // NOT scaled by dxinv here: the reference scales AFTER the halo exchange with the receiver's local dxinv
     // (NavierStokes3DParabolicFunction.c:125-146); the sweeps apply it per cell
     const double dxi = muRe;
 #pragma unroll
-    for (int c = 0; c < 4; c++) a.qd[(long long)(d * 4 + c) * G.npg + p] = D[c] * dxi;
+    for (int c = 0; c < 4; c++) a.qd[(long long)(d * 4 + c) * G.npg + p] = __dmul_rn(D[c], dxi);
   }
 }
 
@@ -122,33 +147,22 @@ constexpr int QTX = 32, QTY = 8, QH = 2;
 constexpr int QSX = QTX + 2 * QH + 1;      // padded row (37): conflict-free column access is not needed, rows are read along x
 constexpr int QSY = QTY + 2 * QH;
 
-__device__ __forceinline__ void load5(const double* __restrict__ u, long long npg, long long p, double (&r)[5])
-{
-#pragma unroll
-  for (int v = 0; v < 5; v++) r[v] = __ldg(u + v * npg + p);
-}
-__device__ __forceinline__ void prim_of(const double (&r)[5], double gamma, double (&q)[4])
-{
-  const double rho = r[0];
-  const double rinv = rcp_nr(rho);
-  const double vx = r[1] * rinv, vy = r[2] * rinv, vz = r[3] * rinv;
-  const double P = (r[4] - 0.5 * rho * (vx * vx + vy * vy + vz * vz)) * (gamma - 1.0);
-  q[0] = vx; q[1] = vy; q[2] = vz; q[3] = gamma * P * rinv;
-}
-
 __global__ void __launch_bounds__(QTX * QTY, 2) k_qderiv_int(const QD3Args a)
 {
   __shared__ double Q[2][4][QSY][QSX];
   const Geom& G = a.G;
   const int g = G.g;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * QTX + tx;
-  const int i0 = blockIdx.x * QTX, j0 = blockIdx.y * QTY;
+  // the box of points this launch owns: [lo, lo + ext) in interior-relative indices (the whole interior, or the
+  // part of it that does not read ghost cells when the halo exchange is still in flight)
+  const int i0 = a.lo[0] + blockIdx.x * QTX, j0 = a.lo[1] + blockIdx.y * QTY;
   const int i = i0 + tx, j = j0 + ty;
-  const int kb = blockIdx.z * a.zchunk, ke = min(kb + a.zchunk, G.N[2]);
-  const bool ok = (i < G.N[0]) && (j < G.N[1]);
-  // partial tiles: the two ghost columns / rows next to the interior lie INSIDE the thread tile; their threads
+  const int ie = a.lo[0] + a.ext[0], je = a.lo[1] + a.ext[1];
+  const int kb = a.lo[2] + blockIdx.z * a.zchunk, ke = min(kb + a.zchunk, a.lo[2] + a.ext[2]);
+  const bool ok = (i < ie) && (j < je);
+  // partial tiles: the two columns / rows just outside the box lie INSIDE the thread tile; their threads
   // own no output but must stage the centre plane for their neighbours
-  const bool edge = !ok && ((i < G.N[0] + QH && j < G.N[1]) || (i < G.N[0] && j < G.N[1] + QH));
+  const bool edge = !ok && ((i < ie + QH && j < je) || (i < ie && j < je + QH));
   const long long npg = G.npg, sz = G.st[2];
   const long long pcol = (i + g) + (long long)G.P[0] * (j + g);             // + P0*P1*(k+g)
   // halo assignment of threads 0..159: 4 columns x 8 rows (x-halo), then 32 columns x 4 rows (y-halo)
@@ -180,7 +194,6 @@ __global__ void __launch_bounds__(QTX * QTY, 2) k_qderiv_int(const QD3Args a)
   }
   if (edge) load5(a.u, npg, pcol + sz * (kb + g), nu);                       // edge threads: centre plane only
   if (hok) load5(a.u, npg, phalo + sz * (kb + g), hu);
-  const double s12 = 1.0 / 12.0;
   for (int k = kb; k < ke; k++) {
     const int b = (k - kb) & 1;
     const long long pk = sz * (k + g);
@@ -205,17 +218,17 @@ __global__ void __launch_bounds__(QTX * QTY, 2) k_qderiv_int(const QD3Args a)
     }
     __syncthreads();
     if (ok) {
-      const double muRe = exp(0.76 * log(w[2][3])) * a.inv_Re;
+      const double muRe = mu_over_Re(w[2][3], a.inv_Re);
       const long long p = pcol + pk;
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         const double* r = &Q[b][c][ty + QH][tx + QH];
-        const double dx = (r[-2] - 8 * r[-1] + 8 * r[1] - r[2]) * s12;
-        const double dy = (r[-2 * QSX] - 8 * r[-QSX] + 8 * r[QSX] - r[2 * QSX]) * s12;
-        const double dz = (w[0][c] - 8 * w[1][c] + 8 * w[3][c] - w[4][c]) * s12;
-        a.qd[(long long)(0 * 4 + c) * npg + p] = dx * muRe;
-        a.qd[(long long)(1 * 4 + c) * npg + p] = dy * muRe;
-        a.qd[(long long)(2 * 4 + c) * npg + p] = dz * muRe;
+        const double dx = central4(r[-2], r[-1], r[1], r[2]);
+        const double dy = central4(r[-2 * QSX], r[-QSX], r[QSX], r[2 * QSX]);
+        const double dz = central4(w[0][c], w[1][c], w[3][c], w[4][c]);
+        a.qd[(long long)(0 * 4 + c) * npg + p] = __dmul_rn(dx, muRe);
+        a.qd[(long long)(1 * 4 + c) * npg + p] = __dmul_rn(dy, muRe);
+        a.qd[(long long)(2 * 4 + c) * npg + p] = __dmul_rn(dz, muRe);
       }
     }
   }
@@ -240,28 +253,49 @@ __global__ void k_face4(Geom G, double* __restrict__ a, int d, int off_d, double
 
 namespace hpbk {
 
-void qderiv_fused(hpb_solver* h, const double* u)
+// part 0: everything. part 1: only the interior points at least 2 cells away from every face (they read no
+// ghost cell: may run while the halo exchange of u is in flight). part 2: the rest (the 2-cell shell of the
+// interior with the per-point kernel, and the ghost slabs).
+void qderiv_fused(hpb_solver* h, const double* u, int part)
 {
   ProfScope ps(h, HPB_PROF_VISCOUS);
   const Geom& G = h->geo;
   QD3Args a; a.G = G; a.gamma = h->phys.gamma; a.inv_Re = 1.0 / h->phys.Re; a.u = u; a.dxinv = h->d_dxinv; a.qd = h->d_qd4;
-  // interior: tiled march
   a.zchunk = 64;
-  for (int d = 0; d < 3; d++) { a.lo[d] = 0; a.ext[d] = G.N[d]; }
-  {
-    dim3 grid((G.N[0] + QTX - 1) / QTX, (G.N[1] + QTY - 1) / QTY, (G.N[2] + a.zchunk - 1) / a.zchunk);
+  auto box_points = [&](const int lo[3], const int ext[3]) {
+    for (int d = 0; d < 3; d++) { a.lo[d] = lo[d]; a.ext[d] = ext[d]; }
+    const long long n = (long long)ext[0] * ext[1] * ext[2];
+    if (n <= 0) return;
+    k_qderiv3<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a);
+    h->launches++;
+  };
+  const bool splittable = G.N[0] > 2 * QH && G.N[1] > 2 * QH && G.N[2] > 2 * QH;
+  if (part == 1 && !splittable) return;
+  if (part == 2 && !splittable) part = 0;
+  if (part == 0 || part == 1) {
+    const int sh = (part == 1) ? QH : 0;
+    for (int d = 0; d < 3; d++) { a.lo[d] = sh; a.ext[d] = G.N[d] - 2 * sh; }
+    dim3 grid((a.ext[0] + QTX - 1) / QTX, (a.ext[1] + QTY - 1) / QTY, (a.ext[2] + a.zchunk - 1) / a.zchunk);
     k_qderiv_int<<<grid, dim3(QTX, QTY, 1), 0, h->stream>>>(a);
     h->launches++;
+    if (part == 1) return;
+  }
+  if (part == 2) {
+    // the 2-cell shell of the interior as six disjoint boxes
+    const int N0 = G.N[0], N1 = G.N[1], N2 = G.N[2];
+    const int boxes[6][6] = {
+      { 0, 0, 0, N0, N1, QH }, { 0, 0, N2 - QH, N0, N1, QH },
+      { 0, 0, QH, N0, QH, N2 - 2 * QH }, { 0, N1 - QH, QH, N0, QH, N2 - 2 * QH },
+      { 0, QH, QH, QH, N1 - 2 * QH, N2 - 2 * QH }, { N0 - QH, QH, QH, QH, N1 - 2 * QH, N2 - 2 * QH } };
+    for (int b = 0; b < 6; b++) box_points(&boxes[b][0], &boxes[b][3]);
   }
   // the six ghost slabs (normal derivative only; the outermost layer is skipped inside the kernel)
   for (int d = 0; d < 3; d++) {
     for (int f = 0; f < 2; f++) {
-      for (int k = 0; k < 3; k++) { a.lo[k] = 0; a.ext[k] = G.N[k]; }
-      a.lo[d] = f ? G.N[d] : -G.g;
-      a.ext[d] = G.g;
-      const long long n = (long long)a.ext[0] * a.ext[1] * a.ext[2];
-      k_qderiv3<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a);
-      h->launches++;
+      int lo[3] = { 0, 0, 0 }, ext[3] = { G.N[0], G.N[1], G.N[2] };
+      lo[d] = f ? G.N[d] : -G.g;
+      ext[d] = G.g;
+      box_points(lo, ext);
     }
   }
 }
@@ -286,12 +320,13 @@ void pack_qd4(hpb_solver* h, int field)
     if (h->neighbor[2*d+1] >= 0) face4(h, a, d, G.N[d] - G.g, h->d_send[field][2*d+1], 1);
   }
 }
-void unpack_qd4(hpb_solver* h, int field)
+void unpack_qd4(hpb_solver* h, int field, int only_dim)
 {
   ProfScope ps(h, HPB_PROF_HALO);
   const Geom& G = h->geo;
   double* a = h->d_qd4 + (long long)(field - 1) * 4 * G.npg;
   for (int d = 0; d < G.ndims; d++) {
+    if (only_dim >= 0 && d != only_dim) continue;
     if (h->neighbor[2*d] >= 0)   face4(h, a, d, -G.g, h->d_recv[field][2*d], 0);
     if (h->neighbor[2*d+1] >= 0) face4(h, a, d, G.N[d], h->d_recv[field][2*d+1], 0);
   }

@@ -78,13 +78,23 @@ class _DevBuf:
 class DistributedSolver:
     """Drives the staged step of one rank and exchanges its halo buffers.
 
-    The library's kernels run on the solver's own CUDA stream; that stream is made torch's current
-    stream around every exchange, so NCCL's send/recv are ordered after the pack kernels and before the
-    unpack kernels without any host synchronisation.
+    The library's kernels run on the solver's own CUDA stream. Serial schedule (``overlap=False``, and every
+    configuration the library cannot drive sweep by sweep): that stream is made torch's current stream around
+    every exchange, so NCCL's send/recv are ordered after the pack kernels and before the unpack kernels
+    without any host synchronisation. Overlapped schedule (default for the production path): the exchanges
+    are issued on a second (communication) stream, dimension by dimension, ordered against the compute stream
+    with CUDA events only:
+
+      u halos (all dimensions)            ||  Q-derivatives of the deep interior        (viscous)
+      Q-derivative halos of dimension d+1 ||  sweep d
+      u halos of dimension d+1            ||  sweep d                                   (inviscid)
+
+    Sweep d reads the halos of dimension d only (faces, never edges/corners: MPIExchangeBoundariesnD.c:60-76),
+    so the result is identical to the serial schedule.
     """
 
     def __init__(self, solver_inp, boundary, physics, weno, x, rank: int, device: int, group=None,
-                 use_fused: bool = True):
+                 use_fused: bool = True, overlap: bool = True):
         import torch
         self.torch = torch
         self.solver = Solver(solver_inp, boundary, physics, weno, x, rank=rank, device=device, use_fused=use_fused)
@@ -100,6 +110,51 @@ class DistributedSolver:
             rt = [torch.as_tensor(_DevBuf(p, n), device=self.device) if (p and n) else None for p, n in zip(recv, nbytes)]
             self.ex[f] = HaloExchanger(sv.neighbors, st, rt, group)
         self.group = group
+        self.overlap = bool(overlap) and bool(sv.L.hpb_stage_overlap_supported(sv.h))
+        if self.overlap:
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+            self._ev = [torch.cuda.Event() for _ in range(8)]
+
+    # ---- overlapped schedule -------------------------------------------------------------------------------
+    def _exchange_async(self, fields, dims, ev_ready, ev_done) -> None:
+        """issue the exchange of `fields` restricted to `dims` on the communication stream: it starts when the compute
+        stream has reached `ev_ready` (already recorded) and records ev_done[d] after the messages of dimension d"""
+        torch = self.torch
+        self.comm_stream.wait_event(ev_ready)
+        with torch.cuda.stream(self.comm_stream):
+            for d in dims:
+                works = []
+                for f in fields:
+                    works += self.ex[f].start([d])
+                HaloExchanger.finish(works)
+                ev_done[d].record(self.comm_stream)
+
+    def _stage_overlapped(self, s: int) -> None:
+        sv, L = self.solver, self.solver.L
+        nd = sv.ndims
+        dims = list(range(nd))
+        ev_pack, ev_pack2, ev_dim = self._ev[0], self._ev[1], self._ev[2:2 + nd]
+        sv._ck(L.hpb_stage_begin(sv.h, s))                       # stage vector, BCs, pack u
+        ev_pack.record(self.stream)
+        if self.viscous:
+            self._exchange_async([FIELD_U], dims, ev_pack, ev_dim)
+            sv._ck(L.hpb_stage_interior(sv.h, s))                # || exchange of u
+            self.stream.wait_event(ev_dim[nd - 1])
+            sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_U))
+            sv._ck(L.hpb_stage_rhs_a(sv.h, s))                   # shell + ghost slabs of the Q-derivatives, pack
+            ev_pack2.record(self.stream)
+            self._exchange_async([FIELD_QDERIVX, FIELD_QDERIVY], dims, ev_pack2, ev_dim)
+            for d in dims:
+                self.stream.wait_event(ev_dim[d])
+                sv._ck(L.hpb_stage_halo_done_dim(sv.h, FIELD_QDERIVX, d))
+                sv._ck(L.hpb_stage_halo_done_dim(sv.h, FIELD_QDERIVY, d))
+                sv._ck(L.hpb_stage_sweep(sv.h, s, d))            # || exchange of dimensions d+1..
+        else:
+            self._exchange_async([FIELD_U], dims, ev_pack, ev_dim)
+            for d in dims:
+                self.stream.wait_event(ev_dim[d])
+                sv._ck(L.hpb_stage_halo_done_dim(sv.h, FIELD_U, d))
+                sv._ck(L.hpb_stage_sweep(sv.h, s, d))
 
     def _exchange(self, fields) -> None:
         with self.torch.cuda.stream(self.stream):
@@ -115,6 +170,9 @@ class DistributedSolver:
         self._exchange([FIELD_U])
         sv._ck(L.hpb_step_halo_done(sv.h))
         for s in range(sv.nstages):
+            if self.overlap:
+                self._stage_overlapped(s)
+                continue
             sv._ck(L.hpb_stage_begin(sv.h, s))
             self._exchange([FIELD_U])
             sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_U))
@@ -141,6 +199,9 @@ class DistributedSolver:
     def rhs(self, want: bool = True):
         """One TimeRHSFunctionExplicit of the device solution (stage 0 buffers); returns this rank's rhs."""
         sv, L = self.solver, self.solver.L
+        if self.overlap:
+            self._stage_overlapped(0)
+            return sv.get_stage_rhs(0) if want else None
         sv._ck(L.hpb_stage_begin(sv.h, 0))
         self._exchange([FIELD_U])
         sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_U))

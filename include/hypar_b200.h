@@ -213,6 +213,20 @@ int hpb_stage_halo_done(hpb_solver* h, int field);
 int hpb_stage_rhs_a(hpb_solver* h, int stage);
 int hpb_stage_rhs_b(hpb_solver* h, int stage);
 int hpb_step_finish(hpb_solver* h);
+/* Overlapped variant (production path of NavierStokes2D/3D; hpb_stage_overlap_supported() == 1): the exchange runs
+ * on a communication stream, dimension by dimension, while this rank computes:
+ *   hpb_stage_begin(s)
+ *   [exchange FIELD_U]                         || hpb_stage_interior(s)   Q-derivatives that read no ghost cell
+ *   hpb_stage_halo_done(FIELD_U)
+ *   hpb_stage_rhs_a(s)                         remaining Q-derivatives, pack QDerivX/Y   (viscous only)
+ *   for d = 0..ndims-1:
+ *     [exchange dimension d of QDerivX/Y, or of FIELD_U when inviscid]   || sweep d-1
+ *     hpb_stage_halo_done_dim(field, d) ; hpb_stage_sweep(s, d)          sweep d needs the halos of dimension d only
+ * (faces only, no edges/corners, as MPIExchangeBoundariesnD.c: the dimensions are independent).            */
+int hpb_stage_overlap_supported(const hpb_solver* h);
+int hpb_stage_interior(hpb_solver* h, int stage);
+int hpb_stage_halo_done_dim(hpb_solver* h, int field, int dim);
+int hpb_stage_sweep(hpb_solver* h, int stage, int dir);
 int hpb_dev_get_stage_rhs(hpb_solver* h, int stage, double* rhs_host);   /* Udot[stage] -> host (HyPar layout) */
 int hpb_nstages(const hpb_solver* h);
 int hpb_needs_viscous_exchange(const hpb_solver* h);

@@ -109,13 +109,18 @@ class MultiRankOracle:
 
 
 class LocalRanks:
-    def __init__(self, case, use_fused=True, device=0):
+    def __init__(self, case, use_fused=True, device=0, sweepwise=False):
+        """sweepwise: drive the stages with the call sequence of the overlapped schedule (hpb_stage_interior,
+        hpb_stage_halo_done_dim, hpb_stage_sweep) -- same order of calls as DistributedSolver._stage_overlapped."""
         import torch
         from hypar_b200.multigpu import _DevBuf
         self.torch = torch
         self.nranks = int(np.prod(case.solver["iproc"]))
         self.sv = [Solver.from_case(case, rank=r, device=device, use_fused=use_fused) for r in range(self.nranks)]
         self.viscous = bool(self.sv[0].L.hpb_needs_viscous_exchange(self.sv[0].h))
+        self.sweepwise = bool(sweepwise)
+        if self.sweepwise:
+            assert all(sv.L.hpb_stage_overlap_supported(sv.h) for sv in self.sv), "configuration is not driven sweep by sweep"
         dev = torch.device("cuda", device)
         self.buf = {}
         for f in [FIELD_U] + ([FIELD_QDERIVX, FIELD_QDERIVY] if self.viscous else []):
@@ -152,7 +157,28 @@ class LocalRanks:
     def get_solution(self):
         return [sv.get_solution() for sv in self.sv]
 
+    def _stage_sweepwise(self, s):
+        nd = self.sv[0].ndims
+        self._all("hpb_stage_begin", s)
+        if self.viscous:
+            self._all("hpb_stage_interior", s)          # before the halos of u have arrived
+            self.exchange([FIELD_U])
+            self._all("hpb_stage_halo_done", FIELD_U)
+            self._all("hpb_stage_rhs_a", s)
+            self.exchange([FIELD_QDERIVX, FIELD_QDERIVY])
+            for d in range(nd):
+                self._all("hpb_stage_halo_done_dim", FIELD_QDERIVX, d)
+                self._all("hpb_stage_halo_done_dim", FIELD_QDERIVY, d)
+                self._all("hpb_stage_sweep", s, d)
+        else:
+            self.exchange([FIELD_U])
+            for d in range(nd):
+                self._all("hpb_stage_halo_done_dim", FIELD_U, d)
+                self._all("hpb_stage_sweep", s, d)
+
     def _stage(self, s):
+        if self.sweepwise:
+            return self._stage_sweepwise(s)
         self._all("hpb_stage_begin", s)
         self.exchange([FIELD_U])
         self._all("hpb_stage_halo_done", FIELD_U)
