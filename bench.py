@@ -211,7 +211,7 @@ def gpu_arm(args):
         stepper = None
     else:
         from hypar_b200.multigpu import DistributedSolver
-        stepper = DistributedSolver(s, b, ph, w, x, rank=rank, device=local_rank, overlap=not args.no_overlap)
+        stepper = DistributedSolver(s, b, ph, w, x, rank=rank, device=local_rank, overlap=args.overlap)
         sv = stepper.solver
     g = sv.ghosts
     nloc = sv.dim_local
@@ -381,7 +381,8 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=64, help="grid of the cpu_baseline sample")
     ap.add_argument("--ref-n", type=int, default=64, help="grid of the --impl reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: serial halo exchange (no communication stream)")
+    ap.add_argument("--overlap", action="store_true", help="multi-GPU: halo exchange on a communication stream, overlapped "
+                    "with the derivative kernel / sweeps (measured slower than the serial schedule on NVLink 5: DESIGN.md)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

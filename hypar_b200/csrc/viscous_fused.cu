@@ -272,22 +272,28 @@ void qderiv_fused(hpb_solver* h, const double* u, int part)
   const bool splittable = G.N[0] > 2 * QH && G.N[1] > 2 * QH && G.N[2] > 2 * QH;
   if (part == 1 && !splittable) return;
   if (part == 2 && !splittable) part = 0;
-  if (part == 0 || part == 1) {
-    const int sh = (part == 1) ? QH : 0;
-    for (int d = 0; d < 3; d++) { a.lo[d] = sh; a.ext[d] = G.N[d] - 2 * sh; }
-    dim3 grid((a.ext[0] + QTX - 1) / QTX, (a.ext[1] + QTY - 1) / QTY, (a.ext[2] + a.zchunk - 1) / a.zchunk);
+  auto box_tiled = [&](const int lo[3], const int ext[3]) {
+    for (int d = 0; d < 3; d++) { a.lo[d] = lo[d]; a.ext[d] = ext[d]; }
+    if (ext[0] <= 0 || ext[1] <= 0 || ext[2] <= 0) return;
+    dim3 grid((ext[0] + QTX - 1) / QTX, (ext[1] + QTY - 1) / QTY, (ext[2] + a.zchunk - 1) / a.zchunk);
     k_qderiv_int<<<grid, dim3(QTX, QTY, 1), 0, h->stream>>>(a);
     h->launches++;
+  };
+  if (part == 0 || part == 1) {
+    const int sh = (part == 1) ? QH : 0;
+    const int lo[3] = { sh, sh, sh }, ext[3] = { G.N[0] - 2 * sh, G.N[1] - 2 * sh, G.N[2] - 2 * sh };
+    box_tiled(lo, ext);
     if (part == 1) return;
   }
   if (part == 2) {
-    // the 2-cell shell of the interior as six disjoint boxes
+    // the 2-cell shell of the interior as six disjoint boxes, same kernel (thin boxes waste most of a tile, but the
+    // shell is ~2 % of the points)
     const int N0 = G.N[0], N1 = G.N[1], N2 = G.N[2];
     const int boxes[6][6] = {
       { 0, 0, 0, N0, N1, QH }, { 0, 0, N2 - QH, N0, N1, QH },
       { 0, 0, QH, N0, QH, N2 - 2 * QH }, { 0, N1 - QH, QH, N0, QH, N2 - 2 * QH },
       { 0, QH, QH, QH, N1 - 2 * QH, N2 - 2 * QH }, { N0 - QH, QH, QH, QH, N1 - 2 * QH, N2 - 2 * QH } };
-    for (int b = 0; b < 6; b++) box_points(&boxes[b][0], &boxes[b][3]);
+    for (int b = 0; b < 6; b++) box_tiled(&boxes[b][0], &boxes[b][3]);
   }
   // the six ghost slabs (normal derivative only; the outermost layer is skipped inside the kernel)
   for (int d = 0; d < 3; d++) {

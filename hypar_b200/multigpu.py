@@ -78,23 +78,29 @@ class _DevBuf:
 class DistributedSolver:
     """Drives the staged step of one rank and exchanges its halo buffers.
 
-    The library's kernels run on the solver's own CUDA stream. Serial schedule (``overlap=False``, and every
-    configuration the library cannot drive sweep by sweep): that stream is made torch's current stream around
-    every exchange, so NCCL's send/recv are ordered after the pack kernels and before the unpack kernels
-    without any host synchronisation. Overlapped schedule (default for the production path): the exchanges
-    are issued on a second (communication) stream, dimension by dimension, ordered against the compute stream
-    with CUDA events only:
+    The library's kernels run on the solver's own CUDA stream. Serial schedule (``overlap=False``, the default, and
+    every configuration the library cannot drive sweep by sweep): that stream is made torch's current stream
+    around every exchange, so NCCL's send/recv are ordered after the pack kernels and before the unpack kernels
+    without any host synchronisation. Overlapped schedule (``overlap=True``): the exchanges are issued on a second
+    (communication) stream, dimension by dimension, ordered against the compute stream with CUDA events only:
 
       u halos (all dimensions)            ||  Q-derivatives of the deep interior        (viscous)
       Q-derivative halos of dimension d+1 ||  sweep d
       u halos of dimension d+1            ||  sweep d                                   (inviscid)
 
     Sweep d reads the halos of dimension d only (faces, never edges/corners: MPIExchangeBoundariesnD.c:60-76),
-    so the result is identical to the serial schedule.
+    so the result is identical to the serial schedule (tests/test_gpu_decomposed.py: bit for bit).
+
+    Measured on 8 B200 (C4, 512^3 per GPU, 2x2x2; profiles/r01f_bench8*.json): serial 193.0 ms/step (95.5 % of the
+    single-GPU rate), overlapped 201.6 ms/step. The exchange itself is ~1 ms of a 48 ms stage (NVLink 5), the
+    pack/unpack kernels another ~0.9 ms; splitting the derivative kernel into deep interior + six thin shell
+    boxes and running NCCL's copy kernels next to FP64-saturated SMs costs more than the ~1 ms it hides. The
+    overlapped schedule is kept for slower links / smaller blocks; the serial one is the default because it is
+    faster here.
     """
 
     def __init__(self, solver_inp, boundary, physics, weno, x, rank: int, device: int, group=None,
-                 use_fused: bool = True, overlap: bool = True):
+                 use_fused: bool = True, overlap: bool = False):
         import torch
         self.torch = torch
         self.solver = Solver(solver_inp, boundary, physics, weno, x, rank=rank, device=device, use_fused=use_fused)
