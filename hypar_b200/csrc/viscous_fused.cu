@@ -147,9 +147,22 @@ constexpr int QTX = 32, QTY = 8, QH = 2;
 constexpr int QSX = QTX + 2 * QH + 1;      // padded row (37): conflict-free column access is not needed, rows are read along x
 constexpr int QSY = QTY + 2 * QH;
 
+constexpr int QD = 4;                      // depth of the cp.async input ring (planes in flight per thread)
+constexpr int QNH = 4 * QTY + 4 * QTX;     // halo points per plane (160)
+constexpr size_t QSMEM = sizeof(double) * (2 * 4 * QSY * QSX + QD * 5 * (QTX * QTY) + QD * 5 * QNH);
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+
 __global__ void __launch_bounds__(QTX * QTY, 2) k_qderiv_int(const QD3Args a)
 {
-  __shared__ double Q[2][4][QSY][QSX];
+  extern __shared__ double qsm[];
+  double (*Q)[4][QSY][QSX] = reinterpret_cast<double (*)[4][QSY][QSX]>(qsm);            // [2][4][QSY][QSX]
+  double* rawA = qsm + 2 * 4 * QSY * QSX;                                               // [QD][5][256]: own column
+  double* rawB = rawA + QD * 5 * (QTX * QTY);                                           // [QD][5][160]: halo point
   const Geom& G = a.G;
   const int g = G.g;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * QTX + tx;
@@ -170,7 +183,7 @@ __global__ void __launch_bounds__(QTX * QTY, 2) k_qderiv_int(const QD3Args a)
   if (tid < 4 * QTY) {
     const int c = tid % 4, r = tid / 4;
     hi = (c < 2) ? (c - 2) : (QTX + c - 2); hj = r; hok = true;
-  } else if (tid < 4 * QTY + 4 * QTX) {
+  } else if (tid < QNH) {
     const int t = tid - 4 * QTY, c = t % QTX, r = t / QTX;
     hi = c; hj = (r < 2) ? (r - 2) : (QTY + r - 2); hok = true;
   }
@@ -178,11 +191,34 @@ __global__ void __launch_bounds__(QTX * QTY, 2) k_qderiv_int(const QD3Args a)
   hok = hok && (ghi + g < G.P[0]) && (ghj + g < G.P[1]);
   const long long phalo = (ghi + g) + (long long)G.P[0] * (ghj + g);
 
+  // Inputs arrive through a QD-deep cp.async ring, each thread copying (and later reading) only its own slots, so no
+  // barrier is involved: stream A = the thread's own column (plane k+2 for owners: it enters the z-window; plane k for
+  // the edge threads), stream B = its halo point (plane k). QD-1 planes are in flight per thread.
+  const bool actA = ok || edge;
+  const int offA = ok ? 2 : 0;
+  auto issue = [&](int it) {                                                 // inputs of iteration it (plane kb + it)
+    const int k = kb + it;
+    if (k < ke) {
+      const int slot = it % QD;
+      if (actA) {
+        const long long p = pcol + sz * (k + offA + g);
+#pragma unroll
+        for (int v = 0; v < 5; v++) cp_async8(rawA + (slot * 5 + v) * (QTX * QTY) + tid, a.u + v * npg + p);
+      }
+      if (hok) {
+        const long long p = phalo + sz * (k + g);
+#pragma unroll
+        for (int v = 0; v < 5; v++) cp_async8(rawB + (slot * 5 + v) * QNH + tid, a.u + v * npg + p);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int it = 0; it < QD - 1; it++) issue(it);
+
   double w[5][4];                                                            // planes k-2 .. k+2
 #pragma unroll
   for (int s = 0; s < 5; s++) { w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0.0; }
-  double nu[5] = { 1.0, 0.0, 0.0, 0.0, 1.0 };                                // raw u, own column, plane k+2 (one plane ahead)
-  double hu[5] = { 1.0, 0.0, 0.0, 0.0, 1.0 };                                // raw u, halo / edge point, plane k
   if (ok) {
 #pragma unroll
     for (int s = 1; s < 5; s++) {                                            // w[1..4] = planes kb-2 .. kb+1
@@ -190,32 +226,32 @@ __global__ void __launch_bounds__(QTX * QTY, 2) k_qderiv_int(const QD3Args a)
       load5(a.u, npg, pcol + sz * (kb + s - 3 + g), r);
       prim_of(r, a.gamma, w[s]);
     }
-    load5(a.u, npg, pcol + sz * (kb + 2 + g), nu);
   }
-  if (edge) load5(a.u, npg, pcol + sz * (kb + g), nu);                       // edge threads: centre plane only
-  if (hok) load5(a.u, npg, phalo + sz * (kb + g), hu);
   for (int k = kb; k < ke; k++) {
-    const int b = (k - kb) & 1;
+    const int it = k - kb;
+    const int b = it & 1, slot = it % QD;
     const long long pk = sz * (k + g);
-    // shift the window; plane k+2 from the values requested one iteration ago; request the next ones
+    asm volatile("cp.async.wait_group %0;" :: "n"(QD - 2) : "memory");      // this thread's copies of iteration `it` landed
+    // shift the window; plane k+2 enters
 #pragma unroll
     for (int s = 0; s < 4; s++) { w[s][0] = w[s + 1][0]; w[s][1] = w[s + 1][1]; w[s][2] = w[s + 1][2]; w[s][3] = w[s + 1][3]; }
-    if (ok) {
-      prim_of(nu, a.gamma, w[4]);
-      if (k + 1 < ke) load5(a.u, npg, pcol + pk + 3 * sz, nu);
-    } else if (edge) {
-      prim_of(nu, a.gamma, w[2]);
-      if (k + 1 < ke) load5(a.u, npg, pcol + pk + sz, nu);
+    if (actA) {
+      double r[5];
+#pragma unroll
+      for (int v = 0; v < 5; v++) r[v] = rawA[(slot * 5 + v) * (QTX * QTY) + tid];
+      if (ok) prim_of(r, a.gamma, w[4]); else prim_of(r, a.gamma, w[2]);
     }
 #pragma unroll
     for (int c = 0; c < 4; c++) Q[b][c][ty + QH][tx + QH] = w[2][c];
     if (hok) {
-      double h[4];
-      prim_of(hu, a.gamma, h);
-      if (k + 1 < ke) load5(a.u, npg, phalo + pk + sz, hu);
+      double r[5], h[4];
+#pragma unroll
+      for (int v = 0; v < 5; v++) r[v] = rawB[(slot * 5 + v) * QNH + tid];
+      prim_of(r, a.gamma, h);
 #pragma unroll
       for (int c = 0; c < 4; c++) Q[b][c][hj + QH][hi + QH] = h[c];
     }
+    issue(it + QD - 1);                                                       // refills the slot consumed one iteration ago
     __syncthreads();
     if (ok) {
       const double muRe = mu_over_Re(w[2][3], a.inv_Re);
@@ -260,6 +296,14 @@ void qderiv_fused(hpb_solver* h, const double* u, int part)
 {
   ProfScope ps(h, HPB_PROF_VISCOUS);
   const Geom& G = h->geo;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(k_qderiv_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QSMEM) != cudaSuccess) {
+      hpb_fail(HPB_ERR_CUDA, "k_qderiv_int: cannot reserve %zu bytes of shared memory", QSMEM);
+      return;
+    }
+    configured = true;
+  }
   QD3Args a; a.G = G; a.gamma = h->phys.gamma; a.inv_Re = 1.0 / h->phys.Re; a.u = u; a.dxinv = h->d_dxinv; a.qd = h->d_qd4;
   a.zchunk = 64;
   auto box_points = [&](const int lo[3], const int ext[3]) {
@@ -276,7 +320,7 @@ void qderiv_fused(hpb_solver* h, const double* u, int part)
     for (int d = 0; d < 3; d++) { a.lo[d] = lo[d]; a.ext[d] = ext[d]; }
     if (ext[0] <= 0 || ext[1] <= 0 || ext[2] <= 0) return;
     dim3 grid((ext[0] + QTX - 1) / QTX, (ext[1] + QTY - 1) / QTY, (ext[2] + a.zchunk - 1) / a.zchunk);
-    k_qderiv_int<<<grid, dim3(QTX, QTY, 1), 0, h->stream>>>(a);
+    k_qderiv_int<<<grid, dim3(QTX, QTY, 1), QSMEM, h->stream>>>(a);
     h->launches++;
   };
   if (part == 0 || part == 1) {
