@@ -72,6 +72,11 @@ def lib():
         _lib.hpo_sumsq_diff.restype = C.c_double
         _lib.hpo_cfl.argtypes = [cp, dp, C.c_double]
         _lib.hpo_time_step.argtypes = [cp, dp, C.c_double, C.c_int, C.c_int]
+        _lib.hpo_time_step_cons.argtypes = [cp, dp, C.c_double, C.c_int, C.c_int, dp]
+        _lib.hpo_volume_integral.argtypes = [cp, dp, dp]
+        _lib.hpo_boundary_integral.argtypes = [cp, dp, dp]
+        _lib.hpo_conservation_error.argtypes = [C.c_int, dp, dp, dp, dp]
+        _lib.hpo_set_boundary_flux_sink.argtypes = [dp]
     return _lib
 
 
@@ -386,6 +391,37 @@ class Oracle:
 
     def cfl(self, u, dt):
         return float(self.L.hpo_cfl(self.c, _p(u), C.c_double(dt)))
+
+    # ---- conservation diagnostics (VolumeIntegral.c, BoundaryIntegral.c, CalculateConservationError.c, the
+    #      StageBoundaryIntegral bookkeeping of HyperbolicFunction.c:103-106 / TimeRK.c:172-193); local (this rank's) parts
+    def stage_boundary_integral(self, u, mpi_semantics=None):
+        """StageBoundaryIntegral left by one TimeRHSFunctionExplicit(u): [(2d+face)*nvars+v]"""
+        sbi = np.zeros(2 * self.s.ndims * self.s.nvars)
+        self.L.hpo_set_boundary_flux_sink(_p(sbi))
+        try:
+            self.rhs(u, mpi_semantics=mpi_semantics)
+        finally:
+            self.L.hpo_set_boundary_flux_sink(None)
+        return sbi
+
+    def time_step_cons(self, u, dt, rk_type, mpi_semantics=None):
+        """one step; returns StepBoundaryIntegral of that step"""
+        ms = self.s.mpi_semantics if mpi_semantics is None else mpi_semantics
+        sbi = np.zeros(2 * self.s.ndims * self.s.nvars)
+        self.L.hpo_time_step_cons(self.c, _p(u), C.c_double(dt), C.c_int(rk_type), C.c_int(int(ms)), _p(sbi))
+        return sbi
+
+    def volume_integral(self, u):
+        out = np.zeros(self.s.nvars); self.L.hpo_volume_integral(self.c, _p(u), _p(out)); return out
+
+    def boundary_integral(self, step_bi):
+        out = np.zeros(self.s.nvars); self.L.hpo_boundary_integral(self.c, _p(np.ascontiguousarray(step_bi)), _p(out)); return out
+
+    def conservation_error(self, vol, vol0, total_bi):
+        err = np.zeros(self.s.nvars)
+        self.L.hpo_conservation_error(C.c_int(self.s.nvars), _p(np.ascontiguousarray(vol)), _p(np.ascontiguousarray(vol0)),
+                                      _p(np.ascontiguousarray(total_bi)), _p(err))
+        return err
 
     def pack(self, a, d, side, nvars=None):
         nv = nvars or self.s.nvars

@@ -15,7 +15,9 @@
  *                               weights, uL/uR/fL/fR, Upwind result (HyperbolicFunction.c:167-222)
  *                               + FirstDerivativePar / SecondDerivativePar / ComputeCFL
  *   hypar_ref steps N        -> TimeInitialize + N x (TimePreStep, TimeStep, TimePostStep);
- *                               dumps ref_ufinal.bin (with ghosts) and prints per-step wctime
+ *                               dumps ref_ufinal.bin (with ghosts) and prints per-step wctime; with
+ *                               `conservation_check yes` also the volume / boundary-flux integrals and the
+ *                               conservation error of every step
  *
  * All dumps: header {int ndims, nvars, ghosts, dim[ndims]} then raw doubles in the
  * reference's own layout (ghost-padded AoS for cell arrays).
@@ -192,12 +194,28 @@ int main(int argc, char** argv)
     int nsteps = (argc > 2 ? atoi(argv[2]) : 1);
     TimeIntegration TS;
     TimeInitialize(sim, 1, rank, nproc, &TS);
+    if (!strcmp(solver->ConservationCheck, "yes")) {
+      printf("CONS0");
+      for (int v = 0; v < solver->nvars; v++) printf(" %.17e", solver->VolumeIntegralInitial[v]);
+      printf("\n");
+    }
     double total = 0.0;
     for (TS.iter = TS.restart_iter; TS.iter < TS.restart_iter + nsteps; TS.iter++) {
       TimePreStep(&TS);
       TimeStep(&TS);
       TimePostStep(&TS);
       printf("STEP %d wctime %.6e norm %.17e maxcfl %.17e\n", TS.iter+1, TS.iter_wctime, TS.norm, TS.max_cfl);
+      if (!strcmp(solver->ConservationCheck, "yes")) {
+        /* conservation diagnostics of TimePostStep.c:81-93 (VolumeIntegral.c, BoundaryIntegral.c,
+           CalculateConservationError.c) and the per-face flux integrals TimeRK.c:182-193 accumulates */
+        printf("CONS %d", TS.iter+1);
+        for (int v = 0; v < solver->nvars; v++) printf(" %.17e", solver->VolumeIntegral[v]);
+        for (int v = 0; v < solver->nvars; v++) printf(" %.17e", solver->TotalBoundaryIntegral[v]);
+        for (int v = 0; v < solver->nvars; v++) printf(" %.17e", solver->ConservationError[v]);
+        printf("\nSTEPBI %d", TS.iter+1);
+        for (int k = 0; k < 2*solver->ndims*solver->nvars; k++) printf(" %.17e", solver->StepBoundaryIntegral[k]);
+        printf("\n");
+      }
       total += TS.iter_wctime;
     }
     printf("TOTAL_WCTIME %.6e NSTEPS %d\n", total, nsteps);

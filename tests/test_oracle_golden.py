@@ -63,6 +63,19 @@ def test_oracle_matches_reference_golden(path):
     for _ in range(3):
         O.time_step(u, float(case.solver["dt"]), rk)
     same(S.interior(u), S.interior(z["steps3_u"]), "u after 3 steps")
+    # conservation diagnostics of the same three steps (TimePostStep.c:81-93)
+    u = S.local_u0()
+    vol0 = O.volume_integral(u)
+    same(vol0, z["cons_vol0"], "VolumeIntegralInitial")
+    tbi = np.zeros(S.nvars)
+    for k in range(3):
+        sbi = O.time_step_cons(u, float(case.solver["dt"]), rk)
+        same(sbi, z["cons_stepbi"][k], f"StepBoundaryIntegral, step {k + 1}")
+        tbi = tbi + O.boundary_integral(sbi)
+        vol = O.volume_integral(u)
+        same(np.concatenate([vol, tbi, O.conservation_error(vol, vol0, tbi)]), z["cons_steps"][k],
+             f"VolumeIntegral | TotalBoundaryIntegral | ConservationError, step {k + 1}")
+    same(S.interior(u), S.interior(z["steps3_u"]), "u after 3 steps (conservation bookkeeping on)")
     if "pieces_u" not in z:
         return
     # the function-pointer pieces, per direction

@@ -5,7 +5,8 @@
 Each fixture holds, for one small case of a BASELINE.json configuration family, the outputs of the
 reference's own code on that case's input files:
   rhs mode   : u after ApplyBoundaryConditions, hyp, par, source, rhs of ONE TimeRHSFunctionExplicit
-  steps mode : u after 3 time steps of the reference's TimePreStep/TimeStep/TimePostStep loop
+  steps mode : u after 3 time steps of the reference's TimePreStep/TimeStep/TimePostStep loop, and (run with
+               conservation_check yes) the volume integral, boundary-flux integrals and conservation error of every step
   pieces mode: (selected cases) FFunction, WENO weights, uL/uR/fL/fR, Upwind result per direction
 The case itself is re-created from hypar_b200.cases by name + arguments (stored in the fixture), so the
 inputs are not duplicated. TEST INFRASTRUCTURE ONLY.
@@ -41,6 +42,20 @@ GOLDEN = [
 ]
 
 
+def parse_conservation(stdout):
+    """CONS0 / CONS / STEPBI lines of oracle/ref_harness.cpp (steps mode, conservation_check yes)"""
+    r = {"vol0": None, "cons": [], "stepbi": []}
+    for ln in stdout.splitlines():
+        t = ln.split()
+        if ln.startswith("CONS0"):
+            r["vol0"] = np.array([float(x) for x in t[1:]])
+        elif ln.startswith("CONS "):
+            r["cons"].append([float(x) for x in t[2:]])
+        elif ln.startswith("STEPBI "):
+            r["stepbi"].append([float(x) for x in t[2:]])
+    return r
+
+
 def build_case(builder, kwargs):
     kw = dict(kwargs)
     if "n" in kw and isinstance(kw["n"], list):
@@ -57,8 +72,14 @@ def main():
         o = run_reference(case, "rhs", exe=exe)
         for k in ("u", "hyp", "par", "source", "rhs", "x", "dxinv"):
             data["rhs_" + k] = o[k]["data"]
+        case.solver["conservation_check"] = "yes"          # diagnostics only: the solution is unaffected
         o = run_reference(case, "steps", [3], exe=exe)
+        case.solver["conservation_check"] = "no"
         data["steps3_u"] = o["ufinal"]["data"]
+        cons = parse_conservation(o["stdout"])
+        data["cons_vol0"] = cons["vol0"]
+        data["cons_steps"] = np.array(cons["cons"])          # per step: VolumeIntegral | TotalBoundaryIntegral | ConservationError
+        data["cons_stepbi"] = np.array(cons["stepbi"])       # per step: StepBoundaryIntegral [(2d+face)*nvars+v]
         if pieces:
             o = run_reference(case, "pieces", exe=exe)
             for k, v in o.items():
