@@ -35,7 +35,7 @@ class Config(C.Structure):
         ("diffusion", C.c_double * (MAX_NDIMS * MAX_NVARS)),
         ("nzones", C.c_int), ("zones", BoundaryZone * MAX_ZONES),
         ("x_global", C.POINTER(C.c_double)),
-        ("device", C.c_int), ("use_fused", C.c_int),
+        ("device", C.c_int), ("use_fused", C.c_int), ("conservation_check", C.c_int),
     ]
 
 
@@ -54,6 +54,8 @@ SYMBOLS = [
     "hpb_halo_buffers", "hpb_step_begin", "hpb_step_halo_done", "hpb_stage_begin", "hpb_stage_halo_done",
     "hpb_stage_rhs_a", "hpb_stage_rhs_b", "hpb_step_finish", "hpb_stage_overlap_supported", "hpb_stage_interior",
     "hpb_stage_halo_done_dim", "hpb_stage_sweep", "hpb_dev_get_stage_rhs", "hpb_nstages", "hpb_needs_viscous_exchange",
+    "hpb_dev_VolumeIntegral", "hpb_dev_StageBoundaryIntegral", "hpb_dev_StepBoundaryIntegral", "hpb_BoundaryIntegral",
+    "hpb_CalculateConservationError", "hpb_dev_ErrorSums",
     "hpb_stream", "hpb_synchronize", "hpb_kernel_launch_count", "hpb_tma_launch_count", "hpb_profile_enable", "hpb_profile_query",
 ]
 
@@ -123,6 +125,12 @@ def load():
     L.hpb_stage_halo_done_dim.argtypes = [vp, C.c_int, C.c_int]
     L.hpb_stage_sweep.argtypes = [vp, C.c_int, C.c_int]
     L.hpb_dev_get_stage_rhs.argtypes = [vp, C.c_int, dp]
+    L.hpb_dev_VolumeIntegral.argtypes = [vp, dp]
+    L.hpb_dev_StageBoundaryIntegral.argtypes = [vp, C.c_int, dp]
+    L.hpb_dev_StepBoundaryIntegral.argtypes = [vp, dp]
+    L.hpb_BoundaryIntegral.argtypes = [vp, dp, dp]
+    L.hpb_CalculateConservationError.argtypes = [C.c_int, dp, dp, dp, dp]
+    L.hpb_dev_ErrorSums.argtypes = [vp, dp, dp]
     L.hpb_stream.argtypes = [vp]
     L.hpb_stream.restype = vp
     L.hpb_kernel_launch_count.argtypes = [vp]

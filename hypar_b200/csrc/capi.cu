@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" boundary (include/hypar_b200.h): solver life cycle, the host-array
 // entry points that mirror HyPar's function-pointer surface, the device-resident time loop and the
 // staged multi-GPU step. No CPU fallback: every compute entry point requires a CUDA device.
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -47,6 +48,7 @@ extern "C" void hpb_config_defaults(hpb_config* c)
   c->rho_ref = 1.0; c->p_ref = 1.0; c->R = 1.0; c->HB = 1; c->N_bv = 0.0;
   c->device = -1;
   c->use_fused = 1;
+  c->conservation_check = 0;
 }
 
 // ------------------------------------------------------------------------------------ helpers
@@ -139,6 +141,25 @@ static int ensure_generic(hpb_solver* h)
   return HPB_OK;
 }
 
+// boundary-flux bookkeeping (conservation_check): 6 slots of 2*ndims*nvars sums + the compact face scratch
+static constexpr int CONS_SLOT_LAST = 4, CONS_SLOT_STEP = 5, CONS_NSLOT = 6;
+static int nbf(const hpb_solver* h) { return 2 * h->geo.ndims * h->geo.nvars; }
+static double* cons_slot(hpb_solver* h, int slot) { return h->d_cons + (size_t)slot * nbf(h); }
+static int ensure_conservation(hpb_solver* h)
+{
+  long long nface = 1;
+  for (int d = 0; d < h->geo.ndims; d++) { long long k = (long long)h->geo.N[0] * h->geo.N[1] * h->geo.N[2] / h->geo.N[d]; if (k > nface) nface = k; }
+  TRY(dalloc(&h->d_face, nface * h->geo.nvars));
+  TRY(dalloc(&h->d_cons, (long long)CONS_NSLOT * nbf(h)));
+  return HPB_OK;
+}
+// StageBoundaryIntegral of the state U (all directions, or one) into slot `slot`
+static void stage_boundary_flux(hpb_solver* h, const double* U, int slot, int only_dir = -1)
+{
+  if (!h->cfg.conservation_check) return;
+  for (int d = 0; d < h->geo.ndims; d++) if (only_dir < 0 || d == only_dir) hpbk::boundary_flux(h, U, d, cons_slot(h, slot));
+}
+
 static int alloc_main(hpb_solver* h)
 {
   const long long n = ncell(h);
@@ -146,6 +167,8 @@ static int alloc_main(hpb_solver* h)
   for (int s = 0; s < h->rk.ns; s++) TRY(dalloc(&h->d_Udot[s], n));
   if (fused_visc(h)) TRY(dalloc(&h->d_qd4, 12 * h->geo.npg));
   if (!fused_path(h) || (viscous_on(h) && !fused_visc(h))) TRY(ensure_generic(h));
+  TRY(dalloc(&h->d_part, hpbk::diag_partial_size()));
+  if (h->cfg.conservation_check) TRY(ensure_conservation(h));
   return HPB_OK;
 }
 
@@ -208,7 +231,8 @@ extern "C" int hpb_destroy(hpb_solver* h)
   if (!h) return HPB_OK;
   if (h->stream || h->d_x) cudaSetDevice(h->device);
   double** ptrs[] = { &h->d_x, &h->d_dxinv, &h->d_gravf, &h->d_gravg, &h->d_u, &h->d_uprev, &h->d_U, &h->d_fI, &h->d_sI,
-                      &h->d_FV, &h->d_stage_aos, &h->d_w, &h->d_red, &h->d_qd4, &h->d_par, &h->d_src };
+                      &h->d_FV, &h->d_stage_aos, &h->d_w, &h->d_red, &h->d_qd4, &h->d_par, &h->d_src,
+                      &h->d_cons, &h->d_face, &h->d_part };
   for (double** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
   for (int i = 0; i < 4; i++) { if (h->d_Udot[i]) cudaFree(h->d_Udot[i]); if (h->d_tmp[i]) cudaFree(h->d_tmp[i]); }
   for (int i = 0; i < 3; i++) if (h->d_QD[i]) cudaFree(h->d_QD[i]);
@@ -381,6 +405,7 @@ extern "C" int hpb_HyperbolicFunction(hpb_solver* h, double* hyp, const double* 
   hpbk::set_zero(h, h->d_tmp[1], ncell(h));
   if (!fused_path(h)) TRY(ensure_generic(h));
   hpbk::hyperbolic(h, h->d_tmp[0], h->d_tmp[1], false, false, nullptr);
+  stage_boundary_flux(h, h->d_tmp[0], CONS_SLOT_LAST);
   TRY(check_async(h, "HyperbolicFunction"));
   return download(h, h->d_tmp[1], hyp, h->geo.npg, h->geo.nvars);
 }
@@ -424,6 +449,7 @@ extern "C" int hpb_RHSFunction(hpb_solver* h, double* rhs, double* u, double t)
   hpbk::apply_bc(h, h->d_U);
   TRY(rhs_part_a(h, h->d_U, h->d_Udot[0]));
   TRY(rhs_part_b(h, h->d_U, h->d_Udot[0]));
+  stage_boundary_flux(h, h->d_U, CONS_SLOT_LAST);
   TRY(check_async(h, "RHSFunction"));
   TRY(download(h, h->d_Udot[0], rhs, h->geo.npg, h->geo.nvars));
   return download(h, h->d_U, u, h->geo.npg, h->geo.nvars);
@@ -609,8 +635,10 @@ static int step_single(hpb_solver* h)
     hpbk::apply_bc(h, U);                       // TimeRHSFunctionExplicit.c:46
     TRY(rhs_part_a(h, U, h->d_Udot[s]));
     TRY(rhs_part_b(h, U, h->d_Udot[s]));
+    stage_boundary_flux(h, U, s);               // TimeRK.c:172-177 (BoundaryFlux[s] = StageBoundaryIntegral)
   }
   hpbk::rk_finish(h);                           // TimeRK.c:182-193
+  if (h->cfg.conservation_check) hpbk::step_boundary_integral(h, cons_slot(h, 0), cons_slot(h, CONS_SLOT_STEP));
   h->t += h->cfg.dt;                            // TimePostStep.c:36
   return check_async(h, "TimeStep");
 }
@@ -654,6 +682,73 @@ extern "C" int hpb_dev_StepNormSumSq(hpb_solver* h, double* sumsq_local)
   return check_async(h, "dev_StepNormSumSq");
 }
 
+// ------------------------------------------------------------------------------------ conservation / error diagnostics
+extern "C" int hpb_dev_VolumeIntegral(hpb_solver* h, double* vol_local)
+{
+  TRY(need_device(h));
+  if (!vol_local) return hpb_fail(HPB_ERR_INVALID, "dev_VolumeIntegral: null output");
+  hpbk::volume_integral(h, h->d_u, vol_local);
+  return check_async(h, "dev_VolumeIntegral");
+}
+
+static int cons_download(hpb_solver* h, int slot, double* out, const char* what)
+{
+  TRY(need_device(h));
+  if (!h->cfg.conservation_check || !h->d_cons)
+    return hpb_fail(HPB_ERR_INVALID, "%s: the boundary-flux bookkeeping is off (conservation_check = 0)", what);
+  if (!out) return hpb_fail(HPB_ERR_INVALID, "%s: null output", what);
+  HPB_CUDA(cudaMemcpyAsync(out, cons_slot(h, slot), nbf(h) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return sync_check(h, what);
+}
+extern "C" int hpb_dev_StageBoundaryIntegral(hpb_solver* h, int slot, double* sbi)
+{
+  if (h && (slot < -1 || slot >= h->rk.ns)) return hpb_fail(HPB_ERR_INVALID, "dev_StageBoundaryIntegral: slot %d", slot);
+  return cons_download(h, slot < 0 ? CONS_SLOT_LAST : slot, sbi, "dev_StageBoundaryIntegral");
+}
+extern "C" int hpb_dev_StepBoundaryIntegral(hpb_solver* h, double* step_bi)
+{
+  return cons_download(h, CONS_SLOT_STEP, step_bi, "dev_StepBoundaryIntegral");
+}
+
+// BoundaryIntegral.c:36-48, this rank's part: sum_d (StepBI[2d] + StepBI[2d+1]) dS_d with dS_d the product of the
+// other dimensions' spacings at the block's mid-point index (the reference's uniform-grid assumption). Host code.
+extern "C" int hpb_BoundaryIntegral(const hpb_solver* h, const double* step_bi, double* bi_local)
+{
+  if (!h || !step_bi || !bi_local) return hpb_fail(HPB_ERR_INVALID, "BoundaryIntegral: null argument");
+  const Geom& G = h->geo;
+  for (int v = 0; v < G.nvars; v++) bi_local[v] = 0.0;
+  for (int d = 0; d < G.ndims; d++) for (int v = 0; v < G.nvars; v++) {
+    double dS = 1.0;
+    for (int k = 0; k < G.ndims; k++) if (k != d) dS *= (1.0 / h->dxinv_h[G.xoff[k] + G.g + G.N[k] / 2]);
+    bi_local[v] += step_bi[(2 * d + 0) * G.nvars + v] * dS;
+    bi_local[v] += step_bi[(2 * d + 1) * G.nvars + v] * dS;
+  }
+  return HPB_OK;
+}
+
+// CalculateConservationError.c:24-36
+extern "C" int hpb_CalculateConservationError(int nvars, const double* vol, const double* vol0, const double* tbi, double* err)
+{
+  if (!vol || !vol0 || !tbi || !err || nvars < 1) return hpb_fail(HPB_ERR_INVALID, "CalculateConservationError: bad argument");
+  for (int v = 0; v < nvars; v++) {
+    const double base = (fabs(vol0[v]) > 1.0) ? fabs(vol0[v]) : 1.0;
+    const double e = (vol[v] + tbi[v] - vol0[v]) * (vol[v] + tbi[v] - vol0[v]);
+    err[v] = sqrt(e) / base;
+  }
+  return HPB_OK;
+}
+
+extern "C" int hpb_dev_ErrorSums(hpb_solver* h, const double* uex_host, double* sums)
+{
+  TRY(need_device(h));
+  if (!uex_host || !sums) return hpb_fail(HPB_ERR_INVALID, "dev_ErrorSums: null argument");
+  TRY(tmp(h, 0));
+  TRY(upload(h, uex_host, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  hpbk::diff_norm_sums(h, h->d_tmp[0], nullptr, sums);          // CalculateError.c:68-84 (solution norms)
+  hpbk::diff_norm_sums(h, h->d_tmp[0], h->d_u, sums + 3);      // :87-104 (uex - u)
+  return check_async(h, "dev_ErrorSums");
+}
+
 extern "C" int hpb_dev_RHS(hpb_solver* h, double t, double* rhs_host)
 {
   (void)t;
@@ -663,6 +758,7 @@ extern "C" int hpb_dev_RHS(hpb_solver* h, double t, double* rhs_host)
   hpbk::apply_bc(h, h->d_U);
   TRY(rhs_part_a(h, h->d_U, h->d_Udot[0]));
   TRY(rhs_part_b(h, h->d_U, h->d_Udot[0]));
+  stage_boundary_flux(h, h->d_U, CONS_SLOT_LAST);
   TRY(check_async(h, "dev_RHS"));
   if (rhs_host) return download(h, h->d_Udot[0], rhs_host, h->geo.npg, h->geo.nvars);
   return sync_check(h, "dev_RHS");
@@ -762,6 +858,7 @@ extern "C" int hpb_stage_sweep(hpb_solver* h, int stage, int dir)
   double* rhs = h->d_Udot[stage];
   if (!hpbk::hyperbolic_fused(h, U, rhs, true, true, rhs, fused_visc(h) ? h->d_qd4 : nullptr, dir))
     return hpb_fail(HPB_ERR_CUDA, "stage_sweep: launch failed");
+  stage_boundary_flux(h, U, stage, dir);
   return check_async(h, "stage_sweep");
 }
 
@@ -786,6 +883,7 @@ extern "C" int hpb_stage_rhs_b(hpb_solver* h, int stage)
   TRY(need_device(h));
   if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
   TRY(rhs_part_b(h, h->U_cur ? h->U_cur : h->d_U, h->d_Udot[stage]));
+  stage_boundary_flux(h, h->U_cur ? h->U_cur : h->d_U, stage);
   return check_async(h, "stage_rhs_b");
 }
 
@@ -800,6 +898,7 @@ extern "C" int hpb_step_finish(hpb_solver* h)
 {
   TRY(need_device(h));
   hpbk::rk_finish(h);
+  if (h->cfg.conservation_check) hpbk::step_boundary_integral(h, cons_slot(h, 0), cons_slot(h, CONS_SLOT_STEP));
   h->t += h->cfg.dt;
   return check_async(h, "step_finish");
 }

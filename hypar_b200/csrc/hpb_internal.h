@@ -75,6 +75,12 @@ struct hpb_solver {
   double *d_w = nullptr;           // stored WENO weights of the fine-grained API (all dirs)
   double *d_iface[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // interface scratch (fine-grained API)
   double *d_red = nullptr;         // reduction scratch
+  // conservation diagnostics (cfg.conservation_check): boundary-flux bookkeeping of HyperbolicFunction.c:103-106 /
+  // TimeRK.c:172-193. d_cons = [slot][2*ndims*nvars]: slots 0..3 = BoundaryFlux[stage], 4 = StageBoundaryIntegral of
+  // the last host-facing call, 5 = StepBoundaryIntegral
+  double *d_cons = nullptr;
+  double *d_face = nullptr;        // compact face array of interface fluxes (nvars * largest face)
+  double *d_part = nullptr;        // per-block partials of the deterministic reductions
   double *h_red = nullptr;         // pinned
   // halo buffers per field: send/recv per face
   double *d_send[3][6] = {}, *d_recv[3][6] = {};
@@ -137,6 +143,12 @@ void rk_finish(hpb_solver* h);
 void copy(hpb_solver* h, double* dst, const double* src, long long n);
 void cfl(hpb_solver* h, const double* u, double dt, double* out_host);
 void sumsq_diff(hpb_solver* h, const double* a, const double* b, double* out_host);
+// conservation / error diagnostics (deterministic reductions)
+void boundary_flux(hpb_solver* h, const double* u, int d, double* sbi);
+void step_boundary_integral(hpb_solver* h, const double* bf, double* step_bi);
+void volume_integral(hpb_solver* h, const double* u, double* out_host);
+void diff_norm_sums(hpb_solver* h, const double* a, const double* b, double* out_host);
+int diag_partial_size();
 // fine-grained API kernels
 void flux(hpb_solver* h, const double* u, double* f, int dir);
 void modified_solution(hpb_solver* h, const double* u, double* uC);

@@ -124,14 +124,19 @@ __global__ void k_face_copy(Geom G, double* __restrict__ a, int nv, int d, int o
 template <int MODEL>
 __global__ void __launch_bounds__(TPB)
 k_iface(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict__ gf,
-        const double* __restrict__ gg, int dir, double* __restrict__ fI, double* __restrict__ sI)
+        const double* __restrict__ gg, int dir, double* __restrict__ fI, double* __restrict__ sI, int face)
 {
+  // face < 0: every interface of the sweep. face = 0 / 1: only the interfaces on the block's low / high face
+  // along dir (interface index 0 / N_dir), written compactly (the face box has extent 1 along dir): the
+  // boundary-flux bookkeeping of HyperbolicFunction.c:103-106 evaluates exactly these.
   constexpr int NV = ModelTraits<MODEL>::NV;
-  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
-  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (face >= 0) { if (dir == 0) M0 = 1; else if (dir == 1) M1 = 1; else M2 = 1; }
   if (i0 >= M0) return;
   const long long q = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
   const long long ni = (long long)M0 * M1 * M2;
+  if (face >= 0) { const int at = face ? G.N[dir] : 0; if (dir == 0) i0 = at; else if (dir == 1) i1 = at; else i2 = at; }
   const long long st = G.st[dir];
   const long long pm1 = cell_index(G, i0, i1, i2) - st;      // cell left of the interface
 
@@ -576,6 +581,84 @@ __global__ void k_sumsq_diff(Geom G, const double* __restrict__ a, const double*
 }
 
 // ------------------------------------------------------------------------------------------
+// conservation / error diagnostics. All reductions are DETERMINISTIC: a fixed launch
+// shape, every thread walks its elements in a fixed order, fixed shuffle trees, no atomics -- two runs give the
+// same bits. (The reference sums serially, dim 0 fastest; a parallel sum differs from it by rounding only.)
+constexpr int DIAG_TPB = 256;
+constexpr int DIAG_BLOCKS = 148 * 4;
+
+// StageBoundaryIntegral[(2d+f)*nvars+v] = -/+ sum of the interface flux over the block's low / high face
+// (HyperbolicFunction.c:103-106). face_fI: compact face array written by k_iface in face mode. One block per v.
+__global__ void __launch_bounds__(1024)
+k_face_sum(const double* __restrict__ face_fI, long long nface, double sign, double* __restrict__ out)
+{
+  const int v = blockIdx.x;
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < nface; i += blockDim.x) s += face_fI[v * nface + i];
+  s = block_reduce(s, false);
+  if (threadIdx.x == 0) out[v] = sign * s;
+}
+
+// StepBoundaryIntegral = sum_s (dt b_s) BoundaryFlux[s]   (TimeRK.c:190-193, zeroed by TimePreStep.c:117)
+__global__ void k_step_boundary_integral(const double* __restrict__ bf, int ns, int nbf, RKTableau rk, double dt,
+                                         double* __restrict__ step_bi)
+{
+  const int k = threadIdx.x;
+  if (k >= nbf) return;
+  double acc = 0.0;
+  for (int s = 0; s < ns; s++) acc += (dt * rk.b[s]) * bf[s * nbf + k];
+  step_bi[k] = acc;
+}
+
+// per-block partial results over the interior points, part[ch*nblk + block].
+// MODE 0: channel v = sum a[v,p] * dV(p), dV = prod_d (1/dxinv_d)            (VolumeIntegral.c:33-41)
+// MODE 1: channels (sum |a-b|, sum (a-b)^2, max |a-b|) over all components; b == nullptr: norms of a itself
+//         (ArraySumAbsnD / ArraySumSquarenD / ArrayMaxnD, arrayfunctions.h:486-545; CalculateError.c:68-104)
+template <int MODE>
+__global__ void __launch_bounds__(DIAG_TPB)
+k_diag_partial(Geom G, const double* __restrict__ dxinv, const double* __restrict__ a, const double* __restrict__ b,
+               double* __restrict__ part)
+{
+  const long long nint = (long long)G.N[0] * G.N[1] * G.N[2];
+  double acc[HPB_MAX_NVARS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nint; q += (long long)gridDim.x * blockDim.x) {
+    const int i0 = (int)(q % G.N[0]), i1 = (int)((q / G.N[0]) % G.N[1]), i2 = (int)(q / ((long long)G.N[0] * G.N[1]));
+    const long long p = cell_index(G, i0, i1, i2);
+    if (MODE == 0) {
+      const int idx[3] = { i0, i1, i2 };
+      double dV = 1.0;
+      for (int d = 0; d < G.ndims; d++) dV *= (1.0 / dxinv[G.xoff[d] + G.g + idx[d]]);
+      for (int v = 0; v < G.nvars; v++) acc[v] += a[v * G.npg + p] * dV;
+    } else {
+      for (int v = 0; v < G.nvars; v++) {
+        double e = a[v * G.npg + p];
+        if (b) e -= b[v * G.npg + p];
+        const double m = fabs(e);
+        acc[0] += m; acc[1] += e * e; if (m > acc[2]) acc[2] = m;
+      }
+    }
+  }
+  const int nch = (MODE == 0) ? G.nvars : 3;
+  for (int c = 0; c < nch; c++) {
+    const double r = block_reduce(acc[c], MODE == 1 && c == 2);
+    if (threadIdx.x == 0) part[c * gridDim.x + blockIdx.x] = r;
+    __syncthreads();
+  }
+}
+
+// final pass: one block per channel over the nblk partials; channel `max_ch` is a maximum, the others sums
+__global__ void __launch_bounds__(DIAG_TPB)
+k_diag_final(const double* __restrict__ part, int nblk, int max_ch, double* __restrict__ out)
+{
+  const int c = blockIdx.x;
+  const bool is_max = (c == max_ch);
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) { const double x = part[c * nblk + i]; s = is_max ? fmax(s, x) : s + x; }
+  s = block_reduce(s, is_max);
+  if (threadIdx.x == 0) out[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------
 // fine-grained API kernels (the reference's individual function pointers)
 template <int MODEL>
 __global__ void k_flux(Geom G, Phys ph, const double* __restrict__ u, int dir, double* __restrict__ f)
@@ -869,7 +952,7 @@ void hyperbolic_generic(hpb_solver* h, const double* u, double* out, bool negate
     const int M[3] = { G.N[0] + (d == 0), G.N[1] + (d == 1), G.N[2] + (d == 2) };
     double* sI = (with_source && grav && h->phys.grav[d] != 0.0) ? h->d_sI : nullptr;
     ProfScope ps(h, HPB_PROF_SWEEP_X + d);
-#define CALL(M_) k_iface<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, u, gf, gg, d, h->d_fI, sI)
+#define CALL(M_) k_iface<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, u, gf, gg, d, h->d_fI, sI, -1)
     MODEL_SWITCH(h->cfg.model, CALL)
 #undef CALL
     LAUNCHED(h);
@@ -1036,5 +1119,56 @@ void second_derivative(hpb_solver* h, double* D2f, const double* f, int dir, int
   const Geom& G = h->geo;
   k_second_derivative<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, f, dir, nv, order, D2f); LAUNCHED(h);
 }
+
+
+// boundary-face fluxes of direction d of the state u (ghosts of dimension d valid) -> sbi[(2d+f)*nvars + v].
+// The faces are evaluated by the per-interface kernel whichever path computes the sweep: 2 N^2 of the (N+1) N^2
+// interfaces (0.4 % at 512^3). scratch: h->d_face (nvars * largest face).
+void boundary_flux(hpb_solver* h, const double* u, int d, double* sbi)
+{
+  ProfScope ps(h, HPB_PROF_OTHER);
+  const Geom& G = h->geo;
+  const double* gf = (h->cfg.model == HPB_MODEL_LINEAR_ADR) ? nullptr : h->d_gravf;
+  const double* gg = (h->cfg.model == HPB_MODEL_LINEAR_ADR) ? nullptr : h->d_gravg;
+  int M[3] = { G.N[0], G.N[1], G.N[2] };
+  M[d] = 1;
+  const long long nface = (long long)M[0] * M[1] * M[2];
+  for (int f = 0; f < 2; f++) {
+#define CALL(M_) k_iface<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, u, gf, gg, d, h->d_face, nullptr, f)
+    MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+    LAUNCHED(h);
+    k_face_sum<<<G.nvars, 1024, 0, h->stream>>>(h->d_face, nface, f ? 1.0 : -1.0, sbi + (2 * d + f) * G.nvars); LAUNCHED(h);
+  }
+}
+
+void step_boundary_integral(hpb_solver* h, const double* bf, double* step_bi)
+{
+  const int nbf = 2 * h->geo.ndims * h->geo.nvars;
+  k_step_boundary_integral<<<1, 32, 0, h->stream>>>(bf, h->rk.ns, nbf, h->rk, h->cfg.dt, step_bi); LAUNCHED(h);
+}
+
+// out_host[v] = this rank's part of VolumeIntegral (before the sum over ranks)
+void volume_integral(hpb_solver* h, const double* u, double* out_host)
+{
+  const Geom& G = h->geo;
+  k_diag_partial<0><<<DIAG_BLOCKS, DIAG_TPB, 0, h->stream>>>(G, h->d_dxinv, u, nullptr, h->d_part); LAUNCHED(h);
+  k_diag_final<<<G.nvars, DIAG_TPB, 0, h->stream>>>(h->d_part, DIAG_BLOCKS, -1, h->d_red); LAUNCHED(h);
+  cudaMemcpyAsync(h->h_red, h->d_red, G.nvars * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  for (int v = 0; v < G.nvars; v++) out_host[v] = h->h_red[v];
+}
+
+// out_host = (sum |a-b|, sum (a-b)^2, max |a-b|) over this rank's interior points and all components
+void diff_norm_sums(hpb_solver* h, const double* a, const double* b, double* out_host)
+{
+  const Geom& G = h->geo;
+  k_diag_partial<1><<<DIAG_BLOCKS, DIAG_TPB, 0, h->stream>>>(G, h->d_dxinv, a, b, h->d_part); LAUNCHED(h);
+  k_diag_final<<<3, DIAG_TPB, 0, h->stream>>>(h->d_part, DIAG_BLOCKS, 2, h->d_red); LAUNCHED(h);
+  cudaMemcpyAsync(h->h_red, h->d_red, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  for (int k = 0; k < 3; k++) out_host[k] = h->h_red[k];
+}
+int diag_partial_size() { return DIAG_BLOCKS * HPB_MAX_NVARS; }
 
 } // namespace hpbk

@@ -130,6 +130,7 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     c.x_global = _dp(xg)
     c.device = device
     c.use_fused = int(use_fused)
+    c.conservation_check = int(str(solver.get("conservation_check", "no")) == "yes")
     return c, xg
 
 
@@ -350,6 +351,38 @@ class Solver:
         out = C.c_double()
         self._ck(self.L.hpb_dev_StepNormSumSq(self.h, C.byref(out)))
         return out.value
+
+    # -- conservation / error diagnostics (this rank's parts; see include/hypar_b200.h)
+    def dev_VolumeIntegral(self) -> np.ndarray:
+        out = np.zeros(self.nvars)
+        self._ck(self.L.hpb_dev_VolumeIntegral(self.h, _dp(out)))
+        return out
+
+    def dev_StageBoundaryIntegral(self, slot: int = -1) -> np.ndarray:
+        out = np.zeros(2 * self.ndims * self.nvars)
+        self._ck(self.L.hpb_dev_StageBoundaryIntegral(self.h, slot, _dp(out)))
+        return out
+
+    def dev_StepBoundaryIntegral(self) -> np.ndarray:
+        out = np.zeros(2 * self.ndims * self.nvars)
+        self._ck(self.L.hpb_dev_StepBoundaryIntegral(self.h, _dp(out)))
+        return out
+
+    def BoundaryIntegral(self, step_bi: np.ndarray) -> np.ndarray:
+        out = np.zeros(self.nvars)
+        self._ck(self.L.hpb_BoundaryIntegral(self.h, _dp(np.ascontiguousarray(step_bi, dtype=np.float64)), _dp(out)))
+        return out
+
+    def CalculateConservationError(self, vol, vol0, total_bi) -> np.ndarray:
+        err = np.zeros(self.nvars)
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (vol, vol0, total_bi)]
+        self._ck(self.L.hpb_CalculateConservationError(self.nvars, _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(err)))
+        return err
+
+    def dev_ErrorSums(self, uex: np.ndarray) -> np.ndarray:
+        out = np.zeros(6)
+        self._ck(self.L.hpb_dev_ErrorSums(self.h, _dp(uex), _dp(out)))
+        return out
 
     def synchronize(self) -> None:
         self._ck(self.L.hpb_synchronize(self.h))

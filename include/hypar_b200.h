@@ -114,6 +114,9 @@ typedef struct hpb_config {
   int    use_fused;                    /* 1 (default): fused sweep kernels where available (TMA-fed variant
                                              when the padded row length is even), 2: fused sweeps without
                                              the TMA variant, 0: generic per-interface kernels only */
+  /* --- solver.inp (cont.) --- */
+  int    conservation_check;           /* ConservationCheck "yes": keep the boundary-flux bookkeeping of
+                                          HyperbolicFunction.c:103-106 / TimeRK.c:172-193 on the device       */
 } hpb_config;
 
 typedef struct hpb_solver hpb_solver;
@@ -190,6 +193,28 @@ double hpb_current_time(const hpb_solver* h);
    (returns the LOCAL sum of squares of u - u_prev and the local max CFL; callers all-reduce) */
 int hpb_dev_ComputeCFL(hpb_solver* h, double* cfl_local_max);
 int hpb_dev_StepNormSumSq(hpb_solver* h, double* sumsq_local);
+/* ---- conservation and error diagnostics, evaluated on the device solution; only scalars
+ * cross the bus. Reductions are deterministic (fixed launch shape and summation tree); they differ from the
+ * reference's serial sums by rounding only. Each call returns THIS RANK'S part; the caller sums / maxes over
+ * ranks exactly where the reference calls MPISum_double / MPIMax_double.
+ *   solver->VolumeIntegralFunction   (hypar.h; VolumeIntegral.c:14-48)          hpb_dev_VolumeIntegral
+ *   solver->StageBoundaryIntegral    (HyperbolicFunction.c:65,103-106)          hpb_dev_StageBoundaryIntegral
+ *   solver->StepBoundaryIntegral     (TimePreStep.c:117, TimeRK.c:172-193)      hpb_dev_StepBoundaryIntegral
+ *   solver->BoundaryIntegralFunction (BoundaryIntegral.c:20-60, local part)     hpb_BoundaryIntegral
+ *   solver->CalculateConservationError (CalculateConservationError.c:14-39)     hpb_CalculateConservationError
+ *   CalculateError (CalculateError.c:26-124, the six local sums it all-reduces) hpb_dev_ErrorSums
+ * The boundary-flux bookkeeping needs cfg.conservation_check = 1 (as ConservationCheck "yes" in solver.inp). */
+int hpb_dev_VolumeIntegral(hpb_solver* h, double* vol_local /* [nvars] */);
+/* slot: 0..nstages-1 = BoundaryFlux[stage] of the last step; -1 = StageBoundaryIntegral left by the last
+   hpb_HyperbolicFunction / hpb_RHSFunction / hpb_dev_RHS call. sbi[(2*d+face)*nvars + v], face 0 = low. */
+int hpb_dev_StageBoundaryIntegral(hpb_solver* h, int slot, double* sbi /* [2*ndims*nvars] */);
+int hpb_dev_StepBoundaryIntegral(hpb_solver* h, double* step_bi /* [2*ndims*nvars] */);
+int hpb_BoundaryIntegral(const hpb_solver* h, const double* step_bi, double* bi_local /* [nvars] */);
+int hpb_CalculateConservationError(int nvars, const double* vol, const double* vol_initial,
+                                   const double* total_boundary_integral, double* err /* [nvars] */);
+/* sums[0..2] = (sum |uex|, sum uex^2, max |uex|), sums[3..5] = the same of (u_dev - uex), over this rank's
+   interior points and all components; uex_host: exact solution, HyPar layout (local + ghosts) */
+int hpb_dev_ErrorSums(hpb_solver* h, const double* uex_host, double* sums /* [6] */);
 /* evaluate rhs(u_dev) once into an internal buffer and copy it to the host (HyPar layout) */
 int hpb_dev_RHS(hpb_solver* h, double t, double* rhs_host /* may be NULL */);
 

@@ -77,6 +77,7 @@ def lib():
         _lib.hpo_boundary_integral.argtypes = [cp, dp, dp]
         _lib.hpo_conservation_error.argtypes = [C.c_int, dp, dp, dp, dp]
         _lib.hpo_set_boundary_flux_sink.argtypes = [dp]
+        _lib.hpo_norm_sums.argtypes = [cp, dp, dp, dp]
     return _lib
 
 
@@ -422,6 +423,12 @@ class Oracle:
         self.L.hpo_conservation_error(C.c_int(self.s.nvars), _p(np.ascontiguousarray(vol)), _p(np.ascontiguousarray(vol0)),
                                       _p(np.ascontiguousarray(total_bi)), _p(err))
         return err
+
+    def norm_sums(self, a, b=None):
+        """(sum |a-b|, sum (a-b)^2, max |a-b|) over the interior (CalculateError.c:68-104, this rank's part)"""
+        out = np.zeros(3)
+        self.L.hpo_norm_sums(self.c, _p(a), _p(b) if b is not None else None, _p(out))
+        return out
 
     def pack(self, a, d, side, nvars=None):
         nv = nvars or self.s.nvars

@@ -17,7 +17,8 @@
  *   hypar_ref steps N        -> TimeInitialize + N x (TimePreStep, TimeStep, TimePostStep);
  *                               dumps ref_ufinal.bin (with ghosts) and prints per-step wctime; with
  *                               `conservation_check yes` also the volume / boundary-flux integrals and the
- *                               conservation error of every step
+ *                               conservation error of every step; with an `exact.inp` in the directory also
+ *                               CalculateError's three norms (errors.dat)
  *
  * All dumps: header {int ndims, nvars, ghosts, dim[ndims]} then raw doubles in the
  * reference's own layout (ghost-padded AoS for cell arrays).
@@ -42,6 +43,7 @@
 #include <interpolation.h>
 
 extern "C" int TimeRHSFunctionExplicit(double*, double*, void*, void*, double);
+extern "C" int CalculateError(void*, void*);
 
 static void dump(const char* name, const HyPar* s, const double* a, long n)
 {
@@ -220,6 +222,14 @@ int main(int argc, char** argv)
     }
     printf("TOTAL_WCTIME %.6e NSTEPS %d\n", total, nsteps);
     dump("ref_ufinal.bin", solver, solver->u, nc);
+    { /* CalculateError.c (errors.dat): only when the run directory holds exact.inp */
+      FILE* fe = fopen("exact.inp", "rb");
+      if (fe) {
+        fclose(fe);
+        CalculateError(solver, mpi);
+        printf("ERRORS %.17e %.17e %.17e\n", solver->error[0], solver->error[1], solver->error[2]);
+      }
+    }
     TimeCleanup(&TS);
 
   } else {

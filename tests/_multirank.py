@@ -60,15 +60,21 @@ class MultiRankOracle:
     def local_u0(self):
         return [s.local_u0() for s in self.S]
 
-    def rhs(self, u):
-        """TimeRHSFunctionExplicit on every rank (u modified: BCs + halos). Returns [rhs_r]."""
+    def rhs(self, u, sbi=None):
+        """TimeRHSFunctionExplicit on every rank (u modified: BCs + halos). Returns [rhs_r].
+        sbi: optional list of per-rank arrays receiving StageBoundaryIntegral (HyperbolicFunction.c:103-106)"""
         for r in range(self.nranks):
             self.O[r].apply_bc(u[r])
         self.exchange(u)
         out = []
         pieces = []
         for r in range(self.nranks):
-            hyp, w = self.O[r].hyperbolic(u[r], want_weights=True)
+            if sbi is not None:
+                hpo.lib().hpo_set_boundary_flux_sink(hpo._p(sbi[r]))
+            try:
+                hyp, w = self.O[r].hyperbolic(u[r], want_weights=True)
+            finally:
+                hpo.lib().hpo_set_boundary_flux_sink(None)
             pieces.append((hyp, w))
         par = [o.zeros() for o in self.O]
         if self.viscous:
@@ -106,6 +112,31 @@ class MultiRankOracle:
             for r in range(self.nranks):
                 u[r] += (dt * b[s]) * k[s][r]
         return u
+
+
+    def time_step_cons(self, u, dt, rk_type):
+        """time_step with the boundary-flux bookkeeping of TimeRK.c:172-193; returns [StepBoundaryIntegral_r]"""
+        A, b, c = np.zeros(16), np.zeros(4), np.zeros(4)
+        ns = hpo.lib().hpo_rk_tableau(rk_type, hpo._p(A), hpo._p(b), hpo._p(c))
+        nbf = 2 * self.nd * self.S[0].nvars
+        for r in range(self.nranks):
+            self.O[r].apply_bc(u[r])
+        self.exchange(u)
+        k, bf = [], []
+        for s in range(ns):
+            U = [x.copy() for x in u]
+            for i in range(s):
+                for r in range(self.nranks):
+                    U[r] += (dt * A[s * ns + i]) * k[i][r]
+            sbi = [np.zeros(nbf) for _ in range(self.nranks)]
+            k.append(self.rhs(U, sbi))
+            bf.append(sbi)
+        step = [np.zeros(nbf) for _ in range(self.nranks)]
+        for s in range(ns):
+            for r in range(self.nranks):
+                u[r] += (dt * b[s]) * k[s][r]
+                step[r] += (dt * b[s]) * bf[s][r]
+        return step
 
 
 class LocalRanks:

@@ -141,6 +141,34 @@ def test_oracle_matches_reference_live(case, exe):
     same(S.interior(u), S.interior(o["ufinal"]["data"]), f"{exe} u after 2 steps")
 
 
+@pytest.mark.parametrize("case", [LIVE[0], LIVE[5], LIVE[8]], ids=lambda c: c.name)
+def test_error_norms_match_reference_live(case, tmp_path):
+    """CalculateError.c:26-124 (errors.dat): with exact.inp = the initial solution, the reference's L1/L2/Linf
+    errors after 2 steps equal the ones formed from the oracle's norm sums (same serial summation order)."""
+    import shutil
+    from refrun import ref_available, run_reference
+    if not ref_available("hypar_ref"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    d = str(tmp_path / "run")
+    case.write(d)
+    shutil.copy(os.path.join(d, "initial.inp"), os.path.join(d, "exact.inp"))
+    o = run_reference(case, "steps", [2], keep=d)
+    ref = [float(x) for x in [l for l in o["stdout"].splitlines() if l.startswith("ERRORS")][0].split()[1:]]
+    S = hpo.Setup(case, mpi_semantics=False)
+    O = hpo.Oracle(S)
+    u = S.local_u0()
+    for _ in range(2):
+        O.time_step(u, float(case.solver["dt"]), hpo.RK_TYPES[case.solver["time_scheme_type"]])
+    uex = S.local_u0()
+    npts = float(np.prod(S.dim))
+    n, e = O.norm_sums(uex), O.norm_sums(uex, u)
+    sol = [n[0] / npts, np.sqrt(n[1] / npts), n[2]]
+    err = [e[0] / npts, np.sqrt(e[1] / npts), e[2]]
+    if all(v > 1e-15 for v in sol):
+        err = [a / b for a, b in zip(err, sol)]
+    assert err == ref, f"{err} vs {ref}"
+
+
 # ---- the reference's own unit tests for this path, re-run against the oracle
 def test_first_derivative_polynomial_exactness():
     """tests/FirstDerivative/test_first_derivative.c: the 4th-order central operator differentiates
