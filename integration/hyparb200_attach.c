@@ -1,0 +1,283 @@
+/* hyparb200_attach.c -- the reference-side binding of libhypar_b200.so: plain C99 compiled INTO HyPar
+ * (against HyPar's own headers) and linked with -lhypar_b200. It only uses the C ABI of include/hypar_b200.h.
+ *
+ * HyPar has no plugin loader: its operator API is the set of function pointers in `struct HyPar`
+ * (include/hypar.h:211-359) that InitializeSolvers (src/Simulation/InitializeSolvers.c:71-393) and
+ * <Model>Initialize assign; the reference's own accelerator path (`use_gpu yes`) swaps the same pointers for
+ * gpu... twins. hyparb200_attach() does the same swap, ONE call after InitializePhysicsData
+ * (src/main.cpp:403-420) and before Solve -- no other source change (integration/hypar_b200_main.cpp is
+ * src/main.cpp's single-simulation sequence with that one call added).
+ *
+ * Two modes (environment variable HYPARB200_MODE):
+ *   resident (default)  the solution lives on the GPU; HyPar::TimeIntegrate = one hpb_TimeStep; the host mirror
+ *                       solver->u is refreshed only when HyPar is about to read it (screen norm, file output,
+ *                       CalculateError, the end of the run); CFL, VolumeIntegral and the boundary-flux
+ *                       bookkeeping are device reductions.
+ *   host                every pointer goes through the host-array entry points (H2D, kernels, D2H per call);
+ *                       TimeIntegrate = hpb_TimeIntegrate(u, 1 step). Slower; exercises the fine-grained ABI.
+ * Both give the files HyPar itself writes (op.bin, conservation.dat, errors.dat) with HyPar's own writers.
+ *
+ * One rank per process here (nproc == 1). With MPI, one rank per GPU, the step shim drives the staged calls
+ * (hpb_step_begin ... hpb_step_finish) and moves the face buffers of hpb_halo_buffers with MPI_Isend/Irecv
+ * (tags 1630/1631 as MPIExchangeBoundariesnD.c:95-137) -- INTEGRATION.md section 2; hypar_b200/multigpu.py is
+ * that loop over NCCL.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <basic.h>
+#include <arrayfunctions.h>
+#include <mpivars.h>
+#include <hypar.h>
+#include <simulation_object.h>
+#include <timeintegration.h>
+#include <boundaryconditions.h>
+#include <interpolation.h>
+#include <physicalmodels/linearadr.h>
+#include <physicalmodels/euler1d.h>
+#include <physicalmodels/navierstokes2d.h>
+#include <physicalmodels/navierstokes3d.h>
+#include "hypar_b200.h"
+
+static struct {
+  hpb_solver *h;
+  HyPar      *solver;
+  int         resident;
+  long long   steps;
+} g;
+
+static void die_on_error(const char *where)
+{
+  if (hpb_error_state()) {
+    fprintf(stderr, "hypar_b200 (%s): %s\n", where, hpb_last_error());
+    exit(1);                       /* HyPar drops return values (basic.h:15-23): fail loudly here */
+  }
+}
+
+/* ---- HyPar::ApplyBoundaryConditions (hypar.h:214). Resident mode: the device step applies the boundary
+   conditions to the device solution itself (TimePreStep.c:50 acts on the stale host mirror: nothing to do). */
+static int B200_BC(void *s, void *m, double *u, double *xref, double t)
+{
+  (void)m; (void)xref;
+  if (g.resident && u == ((HyPar*)s)->u) return 0;
+  hpb_ApplyBoundaryConditions(g.h, u, t); die_on_error("ApplyBoundaryConditions");
+  return 0;
+}
+
+/* ---- HyPar::HyperbolicFunction (hypar.h:250-253); the FFunction/Upwind arguments are the model's own, fixed
+   when the hpb_solver was created */
+static int B200_Hyp(double *hyp, double *u, void *s, void *m, double t, int LimFlag,
+                    int (*F)(double*, double*, int, void*, double),
+                    int (*U)(double*, double*, double*, double*, double*, double*, int, void*, double))
+{
+  HyPar *solver = (HyPar*) s;
+  (void)m; (void)F; (void)U;
+  hpb_HyperbolicFunction(g.h, hyp, u, t, LimFlag); die_on_error("HyperbolicFunction");
+  if (!strcmp(solver->ConservationCheck, "yes"))
+    hpb_dev_StageBoundaryIntegral(g.h, -1, solver->StageBoundaryIntegral);
+  return 0;
+}
+static int B200_Par(double *par, double *u, void *s, void *m, double t)
+{ (void)s; (void)m; hpb_ParabolicFunction(g.h, par, u, t); die_on_error("ParabolicFunction"); return 0; }
+static int B200_Src(double *src, double *u, void *s, void *m, double t)
+{ (void)s; (void)m; hpb_SourceFunction(g.h, src, u, t); die_on_error("SourceFunction"); return 0; }
+static int B200_FFunction(double *f, double *u, int dir, void *s, double t)
+{ (void)s; hpb_FFunction(g.h, f, u, dir, t); die_on_error("FFunction"); return 0; }
+static int B200_UFunction(double *uC, double *u, int dir, void *s, void *m, double t)
+{ (void)s; (void)m; hpb_UFunction(g.h, uC, u, dir, t); die_on_error("UFunction"); return 0; }
+static int B200_Upwind(double *fI, double *fL, double *fR, double *uL, double *uR, double *u, int dir, void *s, double t)
+{ (void)s; hpb_Upwind(g.h, fI, fL, fR, uL, uR, u, dir, t); die_on_error("Upwind"); return 0; }
+static int B200_SetInterpLimiterVar(double *fC, double *u, double *x, int dir, void *s, void *m)
+{ (void)x; (void)s; (void)m; hpb_SetInterpLimiterVar(g.h, fC, u, dir); die_on_error("SetInterpLimiterVar"); return 0; }
+static int B200_InterpolateInterfacesHyp(double *fI, double *fC, double *u, double *x, int upw, int dir, void *s, void *m, int uflag)
+{ (void)x; (void)s; (void)m; hpb_InterpolateInterfacesHyp(g.h, fI, fC, u, upw, dir, uflag); die_on_error("InterpolateInterfacesHyp"); return 0; }
+static int B200_FirstDerivativePar(double *Df, double *f, int dir, int bias, void *s, void *m)
+{ (void)s; (void)m; hpb_FirstDerivativePar(g.h, Df, f, dir, bias); die_on_error("FirstDerivativePar"); return 0; }
+static int B200_SecondDerivativePar(double *D2f, double *f, int dir, void *s, void *m)
+{ (void)s; (void)m; hpb_SecondDerivativePar(g.h, D2f, f, dir); die_on_error("SecondDerivativePar"); return 0; }
+
+/* ---- HyPar::ComputeCFL (hypar.h:269), called by TimePreStep.c:93 every screen_op_iter steps */
+static double B200_ComputeCFL(void *s, void *m, double dt, double t)
+{
+  double cfl = -1.0;
+  (void)m;
+  if (g.resident) hpb_dev_ComputeCFL(g.h, &cfl);
+  else            hpb_ComputeCFL(g.h, ((HyPar*)s)->u, dt, t, &cfl);
+  die_on_error("ComputeCFL");
+  return cfl;
+}
+
+/* ---- HyPar::VolumeIntegralFunction (VolumeIntegral.c), called by TimePostStep.c:83 when ConservationCheck = yes */
+static int (*ref_VolumeIntegral)(double*, double*, void*, void*);
+static int B200_VolumeIntegral(double *VolumeIntegral, double *u, void *s, void *m)
+{
+  HyPar *solver = (HyPar*) s;
+  if (g.resident && u == solver->u) {
+    double local[HPB_MAX_NVARS];
+    hpb_dev_VolumeIntegral(g.h, local); die_on_error("VolumeIntegral");
+    return MPISum_double(VolumeIntegral, local, solver->nvars, &((MPIVariables*)m)->world);
+  }
+  return ref_VolumeIntegral(VolumeIntegral, u, s, m);     /* some other host array: HyPar's own host code */
+}
+
+/* ---- HyPar::TimeIntegrate (hypar.h:220) = TimeRK (TimeRK.c:35). */
+static int B200_TimeRK(void *ts)
+{
+  TimeIntegration  *TS  = (TimeIntegration*) ts;
+  SimulationObject *sim = (SimulationObject*) TS->simulation;
+  HyPar *solver = &sim[0].solver;
+  const int cons = !strcmp(solver->ConservationCheck, "yes");
+
+  if (!g.resident) {
+    hpb_TimeIntegrate(g.h, solver->u, 1, TS->waqt); die_on_error("TimeIntegrate");
+  } else {
+    hpb_TimeStep(g.h); die_on_error("TimeStep");
+    /* the host mirror is read by: TimePreStep.c:84 + TimePostStep.c:44-63 (screen norm, steps with
+       (iter+1) % screen_op_iter == 0: the copy is taken BEFORE that step, so the step before it refreshes too),
+       OutputSolution (file_op_iter), CalculateError and the final output */
+    const int it = TS->iter + 1;
+    const int refresh = (it % solver->screen_op_iter == 0) || ((it + 1) % solver->screen_op_iter == 0)
+                     || (it % solver->file_op_iter == 0) || (it == TS->n_iter);
+    if (refresh) { hpb_dev_get_solution(g.h, solver->u); die_on_error("get_solution"); }
+  }
+  if (cons) {    /* TimeRK.c:182-193 leaves the step's flux integrals in solver->StepBoundaryIntegral */
+    hpb_dev_StepBoundaryIntegral(g.h, solver->StepBoundaryIntegral); die_on_error("StepBoundaryIntegral");
+  }
+  g.steps++;
+  return 0;
+}
+
+static int bc_type(const char *name)
+{
+  if (!strcmp(name, _PERIODIC_))    return HPB_BC_PERIODIC;
+  if (!strcmp(name, _EXTRAPOLATE_)) return HPB_BC_EXTRAPOLATE;
+  if (!strcmp(name, _SLIP_WALL_))   return HPB_BC_SLIP_WALL;
+  return -1;
+}
+
+int hyparb200_attach(void *sims, int nsims)
+{
+  SimulationObject *sim = (SimulationObject*) sims;
+  if (nsims != 1) { fprintf(stderr, "hyparb200_attach: ensembles (nsims > 1) are not on the B200 path\n"); return 1; }
+  HyPar *s = &sim[0].solver;
+  MPIVariables *mpi = &sim[0].mpi;
+  if (mpi->nproc != 1) {
+    fprintf(stderr, "hyparb200_attach: this glue drives one rank per process; multi-rank runs use the staged "
+                    "hpb_stage_* calls (INTEGRATION.md section 2)\n");
+    return 1;
+  }
+  if (strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_WENO_) || strcmp(s->time_scheme, _RK_)
+      || strcmp(s->SplitHyperbolicFlux, "no") || s->flag_ib) {
+    fprintf(stderr, "hyparb200_attach: only weno5 + explicit RK without flux splitting / immersed boundaries is on the B200 path\n");
+    return 1;
+  }
+
+  hpb_config c;
+  hpb_config_defaults(&c);
+  c.ndims = s->ndims;  c.nvars = s->nvars;  c.ghosts = s->ghosts;  c.rank = mpi->rank;  c.dt = s->dt;
+  for (int d = 0; d < s->ndims; d++) { c.dim_global[d] = s->dim_global[d]; c.iproc[d] = mpi->iproc[d]; }
+  c.interp_char = !strcmp(s->interp_type, _CHARACTERISTIC_);
+  if      (!strcmp(s->time_scheme_type, _RK_44_))     c.rk_type = HPB_RK_44;
+  else if (!strcmp(s->time_scheme_type, _RK_SSP3_))   c.rk_type = HPB_RK_SSPRK3;
+  else { fprintf(stderr, "hyparb200_attach: rk type %s is not on the B200 path (44, ssprk3)\n", s->time_scheme_type); return 1; }
+  c.par_scheme = atoi(s->spatial_scheme_par);
+  c.conservation_check = !strcmp(s->ConservationCheck, "yes");
+  WENOParameters *w = (WENOParameters*) s->interp;
+  c.weno_type = w->yc ? HPB_WENO_YC : w->borges ? HPB_WENO_Z : w->mapped ? HPB_WENO_M : HPB_WENO_JS;
+  c.no_limiting = w->no_limiting;  c.weno_eps = w->eps;
+
+  if (!strcmp(s->model, _NAVIER_STOKES_3D_)) {
+    NavierStokes3D *p = (NavierStokes3D*) s->physics;
+    c.model = HPB_MODEL_NS3D;  c.gamma = p->gamma;  c.Pr = p->Pr;  c.Minf = p->Minf;
+    c.Re = (p->Re > 0 ? p->Re * p->Minf : p->Re);   /* HyPar already divided Re by Minf (NavierStokes3DInitialize.c:368) */
+    c.upwind = !strcmp(p->upw_choice, _RUSANOV_) ? HPB_UPWIND_RUSANOV : !strcmp(p->upw_choice, _ROE_) ? HPB_UPWIND_ROE : -1;
+    c.gravity[0] = p->grav_x; c.gravity[1] = p->grav_y; c.gravity[2] = p->grav_z;
+    c.rho_ref = p->rho0; c.p_ref = p->p0; c.R = p->R; c.HB = p->HB; c.N_bv = p->N_bv;
+    if (c.Re > 0 && strcmp(s->spatial_type_par, _NC_2STAGE_)) return 1;
+  } else if (!strcmp(s->model, _NAVIER_STOKES_2D_)) {
+    NavierStokes2D *p = (NavierStokes2D*) s->physics;
+    c.model = HPB_MODEL_NS2D;  c.gamma = p->gamma;  c.Pr = p->Pr;  c.Minf = p->Minf;
+    c.Re = (p->Re > 0 ? p->Re * p->Minf : p->Re);   /* NavierStokes2DInitialize.c:205 */
+    c.upwind = !strcmp(p->upw_choice, _RUSANOV_) ? HPB_UPWIND_RUSANOV : !strcmp(p->upw_choice, _ROE_) ? HPB_UPWIND_ROE : -1;
+    if (p->grav_x != 0.0 || p->grav_y != 0.0) { fprintf(stderr, "hyparb200_attach: navierstokes2d with gravity is not on the B200 path\n"); return 1; }
+  } else if (!strcmp(s->model, _EULER_1D_)) {
+    Euler1D *p = (Euler1D*) s->physics;
+    c.model = HPB_MODEL_EULER1D;  c.gamma = p->gamma;
+    c.upwind = !strcmp(p->upw_choice, _RUSANOV_) ? HPB_UPWIND_RUSANOV : !strcmp(p->upw_choice, _ROE_) ? HPB_UPWIND_ROE : -1;
+    if (p->grav != 0.0) { fprintf(stderr, "hyparb200_attach: euler1d with gravity is not on the B200 path\n"); return 1; }
+  } else if (!strcmp(s->model, _LINEAR_ADVECTION_DIFFUSION_REACTION_)) {
+    LinearADR *p = (LinearADR*) s->physics;
+    c.model = HPB_MODEL_LINEAR_ADR;  c.upwind = HPB_UPWIND_DEFAULT;
+    if (!p->constant_advection || strcmp(p->centered_flux, "no")) {
+      fprintf(stderr, "hyparb200_attach: LinearADR needs constant advection and upwinded fluxes on the B200 path\n"); return 1;
+    }
+    for (int i = 0; i < s->ndims * s->nvars; i++) { c.advection[i] = p->a[i]; c.diffusion[i] = p->d[i]; }
+  } else {
+    fprintf(stderr, "hyparb200_attach: model %s is not on the B200 path\n", s->model); return 1;
+  }
+  if (c.upwind < 0) { fprintf(stderr, "hyparb200_attach: upwinding scheme is not on the B200 path (roe, rusanov)\n"); return 1; }
+
+  DomainBoundary *b = (DomainBoundary*) s->boundary;
+  if (s->nBoundaryZones > HPB_MAX_ZONES) return 1;
+  c.nzones = s->nBoundaryZones;
+  for (int n = 0; n < c.nzones; n++) {
+    c.zones[n].type = bc_type(b[n].bctype);
+    if (c.zones[n].type < 0) { fprintf(stderr, "hyparb200_attach: boundary type %s is not on the B200 path\n", b[n].bctype); return 1; }
+    c.zones[n].dim = b[n].dim;  c.zones[n].face = b[n].face;
+    for (int d = 0; d < s->ndims; d++) {
+      c.zones[n].xmin[d] = b[n].xmin[d];  c.zones[n].xmax[d] = b[n].xmax[d];
+      c.zones[n].wall_velocity[d] = (c.zones[n].type == HPB_BC_SLIP_WALL && b[n].FlowVelocity) ? b[n].FlowVelocity[d] : 0.0;
+    }
+  }
+
+  /* global grid, concatenated per dimension as in initial.inp (ReadArray.c:225-256); one rank: the interior part
+     of solver->x (layout include/basic.h:31-36) */
+  int ntot = 0;
+  for (int d = 0; d < s->ndims; d++) ntot += s->dim_global[d];
+  double *xg = (double*) calloc(ntot, sizeof(double));
+  for (int d = 0, off = 0, offg = 0; d < s->ndims; d++) {
+    for (int i = 0; i < s->dim_local[d]; i++) xg[offg + i] = s->x[off + s->ghosts + i];
+    off += s->dim_local[d] + 2 * s->ghosts;  offg += s->dim_global[d];
+  }
+  c.x_global = xg;
+  c.device = getenv("HYPARB200_DEVICE") ? atoi(getenv("HYPARB200_DEVICE")) : 0;   /* as gpu_device_no (default 0) */
+  const char *fz = getenv("HYPARB200_USE_FUSED");
+  if (fz) c.use_fused = atoi(fz);
+  int rc = hpb_create(&c, &g.h);
+  free(xg);
+  if (rc) { fprintf(stderr, "hyparb200_attach: %s\n", hpb_last_error()); return 1; }   /* unsupported choices fail here */
+
+  const char *mode = getenv("HYPARB200_MODE");
+  g.resident = !(mode && !strcmp(mode, "host"));
+  g.solver = s;
+  if (g.resident && hpb_dev_set_solution(g.h, s->u)) { fprintf(stderr, "hyparb200_attach: %s\n", hpb_last_error()); return 1; }
+
+  /* the pointer swap (what InitializeSolvers.c:71-109 / NavierStokes3DInitialize.c:389-446 do for use_gpu) */
+  s->ApplyBoundaryConditions  = B200_BC;
+  s->HyperbolicFunction       = B200_Hyp;
+  s->ParabolicFunction        = B200_Par;
+  s->SourceFunction           = B200_Src;
+  s->FFunction                = B200_FFunction;
+  if (s->UFunction) s->UFunction = B200_UFunction;
+  s->Upwind                   = B200_Upwind;
+  s->SetInterpLimiterVar      = B200_SetInterpLimiterVar;
+  s->InterpolateInterfacesHyp = B200_InterpolateInterfacesHyp;
+  s->FirstDerivativePar       = B200_FirstDerivativePar;
+  s->SecondDerivativePar      = B200_SecondDerivativePar;
+  s->ComputeCFL               = B200_ComputeCFL;
+  ref_VolumeIntegral          = s->VolumeIntegralFunction;
+  s->VolumeIntegralFunction   = B200_VolumeIntegral;
+  s->TimeIntegrate            = B200_TimeRK;        /* picked up by TimeInitialize.c:55 */
+  if (!mpi->rank) printf("hypar_b200 attached: %s, %s mode, device %d\n", hpb_version(), g.resident ? "resident" : "host", c.device);
+  return 0;
+}
+
+int hyparb200_detach(void)
+{
+  if (g.h) {
+    if (!g.solver->my_idx) printf("hypar_b200: %lld steps, %lld kernel launches\n", g.steps, hpb_kernel_launch_count(g.h));
+    hpb_destroy(g.h);
+  }
+  g.h = NULL;
+  return 0;
+}
