@@ -191,3 +191,152 @@ def read_ref_dump(path: str):
         dims = list(struct.unpack(f"{ndims}i", f.read(4 * ndims)))
         a = np.fromfile(f, dtype=np.float64)
     return {"ndims": ndims, "nvars": nvars, "ghosts": ghosts, "dims": dims, "data": a}
+
+
+# --------------------------------------------------------------------------- partitioned ("parallel") and MPI-IO files
+# SURVEY 8f rank 2. The reference's scalable I/O modes (solver.inp: input_mode / output_mode = "parallel n" | "mpi-io n"):
+#   <root>_par.inp.<nnnn>   ReadArrayParallel  (ReadArray.c:293-505), made from <root>.inp by Extras/ParallelInput.c
+#   <root>.bin.<nnnn>       WriteArrayParallel (WriteArray.c:139-323), stitched by Extras/ParallelOutput.c
+#   <root>_mpi.inp          ReadArrayMPI_IO    (ReadArray.c:513-650)
+# One file per I/O group; a file is the concatenation, in rank order, of one block per member rank:
+#   [x_0 (dim_local[0]) | ... | x_{nd-1} | u AoS, no ghosts, dim 0 fastest]            (doubles, no header)
+# With op_overwrite = no every output time appends another round of blocks to the same files.
+# In the reference the group leader receives every member's block over MPI and writes / reads the file alone. Here
+# every rank (= GPU) addresses ITS OWN block with a positional pread / pwrite at the offset the leader would have
+# reached -- the files are byte-identical, no block is gathered through one rank, and all offsets are 64-bit.
+
+def partition1d(nglobal: int, nproc: int, rank: int) -> int:
+    """MPIPartition1D.c: nglobal/nproc points, the remainder on the last rank"""
+    n = nglobal // nproc
+    return nglobal - n * (nproc - 1) if rank == nproc - 1 else n
+
+
+def rank_nd(iproc: Sequence[int], rank: int) -> List[int]:
+    """MPIRanknD.c: rank = ip0 + iproc0*(ip1 + iproc1*ip2)"""
+    ip = []
+    for p in iproc:
+        ip.append(rank % p)
+        rank //= p
+    return ip
+
+
+def local_extent(dim_global: Sequence[int], iproc: Sequence[int], rank: int):
+    """(is, ie) of this rank's block in global indices (MPILocalDomainLimits.c)"""
+    ip = rank_nd(iproc, rank)
+    is_ = [sum(partition1d(dim_global[d], iproc[d], r) for r in range(ip[d])) for d in range(len(iproc))]
+    ie = [is_[d] + partition1d(dim_global[d], iproc[d], ip[d]) for d in range(len(iproc))]
+    return is_, ie
+
+
+def io_group(nproc: int, n_io: int, rank: int):
+    """MPIIOGroups.c:45-72 -> (group index = file index, first rank, one-past-last rank); a rank count that is not a
+    multiple of the number of I/O ranks falls back to ONE group, as the reference does"""
+    if n_io < 1 or nproc % n_io != 0:
+        n_io = 1
+    gs = nproc // n_io
+    g = rank // gs
+    return g, g * gs, (g + 1) * gs
+
+
+def block_doubles(dim_global, iproc, nvars: int, rank: int) -> int:
+    is_, ie = local_extent(dim_global, iproc, rank)
+    n = [b - a for a, b in zip(is_, ie)]
+    return int(sum(n)) + int(nvars) * int(np.prod(n, dtype=np.int64))
+
+
+def _block_offset(dim_global, iproc, nvars, first_rank: int, rank: int) -> int:
+    return sum(block_doubles(dim_global, iproc, nvars, r) for r in range(first_rank, rank))
+
+
+def _pack_block(x_local: Sequence[np.ndarray], u_local: np.ndarray) -> np.ndarray:
+    return np.concatenate([np.ascontiguousarray(v, dtype=np.float64).reshape(-1) for v in list(x_local) + [u_local]])
+
+
+def write_parallel_block(root_ext: str, rank: int, dim_global, iproc, nvars: int, n_io: int,
+                         x_local: Sequence[np.ndarray], u_local: np.ndarray, record: int = 0) -> str:
+    """This rank's block of <root_ext>.<nnnn> (root_ext = "op.bin": WriteArrayParallel's filename_root).
+    record = how many output times are already in the file (op_overwrite = no appends; yes -> always 0).
+    u_local: (N_{nd-1},...,N_0,nvars), no ghosts. Returns the file name."""
+    nproc = int(np.prod(iproc))
+    g, first, last = io_group(nproc, n_io, rank)
+    fname = f"{root_ext}.{g:04d}"
+    buf = _pack_block(x_local, u_local)
+    assert buf.size == block_doubles(dim_global, iproc, nvars, rank), "block size does not match the decomposition"
+    group_total = _block_offset(dim_global, iproc, nvars, first, last)
+    off = 8 * (record * group_total + _block_offset(dim_global, iproc, nvars, first, rank))
+    fd = os.open(fname, os.O_WRONLY | os.O_CREAT, 0o644)
+    try:
+        mv, done = memoryview(buf).cast("B"), 0
+        while done < len(mv):                        # pwrite may be partial beyond 2 GiB
+            done += os.pwrite(fd, mv[done:done + (1 << 30)], off + done)
+    finally:
+        os.close(fd)
+    return fname
+
+
+def _read_block(fname: str, offset_doubles: int, dims: Sequence[int], nvars: int):
+    n = int(sum(dims)) + nvars * int(np.prod(dims, dtype=np.int64))
+    raw = np.fromfile(fname, dtype=np.float64, count=n, offset=8 * offset_doubles)
+    if raw.size != n:
+        raise IOError(f"{fname} contains insufficient data")            # as ReadArrayParallel's error
+    x, o = [], 0
+    for d in dims:
+        x.append(raw[o:o + d].copy())
+        o += d
+    return x, raw[o:].reshape(tuple(reversed(list(dims))) + (nvars,))
+
+
+def read_parallel_block(fname_root: str, rank: int, dim_global, iproc, nvars: int, n_io: int, record: int = 0,
+                        suffix: str = "_par.inp"):
+    """This rank's (x_local, u_local) out of <fname_root>_par.inp.<nnnn> (or, suffix=".bin", an output file)."""
+    nproc = int(np.prod(iproc))
+    g, first, last = io_group(nproc, n_io, rank)
+    is_, ie = local_extent(dim_global, iproc, rank)
+    group_total = _block_offset(dim_global, iproc, nvars, first, last)
+    off = record * group_total + _block_offset(dim_global, iproc, nvars, first, rank)
+    return _read_block(f"{fname_root}{suffix}.{g:04d}", off, [b - a for a, b in zip(is_, ie)], nvars)
+
+
+def read_mpi_io_block(fname_root: str, rank: int, dim_global, iproc, nvars: int):
+    """This rank's block of <fname_root>_mpi.inp: ONE file, the blocks of all ranks in rank order (ReadArray.c:558-572)"""
+    is_, ie = local_extent(dim_global, iproc, rank)
+    off = _block_offset(dim_global, iproc, nvars, 0, rank)
+    return _read_block(f"{fname_root}_mpi.inp", off, [b - a for a, b in zip(is_, ie)], nvars)
+
+
+def serial_to_parallel(path_serial: str, fname_root: str, dim_global, iproc, nvars: int, n_io: int, mpi_io: bool = False):
+    """Extras/ParallelInput.c: split <root>.inp (global, read_initial_bin's layout) into <root>_par.inp.<nnnn>
+    (or the single <root>_mpi.inp). Returns the files written."""
+    x, u = read_initial_bin(path_serial, dim_global, nvars)
+    nproc = int(np.prod(iproc))
+    files = set()
+    for r in range(nproc):
+        is_, ie = local_extent(dim_global, iproc, r)
+        xl = [x[d][is_[d]:ie[d]] for d in range(len(iproc))]
+        ul = u[tuple(slice(is_[d], ie[d]) for d in reversed(range(len(iproc))))]
+        if mpi_io:
+            buf = _pack_block(xl, ul)
+            fname = f"{fname_root}_mpi.inp"
+            with open(fname, "r+b" if fname in files else "wb") as f:
+                f.seek(8 * _block_offset(dim_global, iproc, nvars, 0, r))
+                buf.tofile(f)
+        else:
+            fname = write_parallel_block(f"{fname_root}_par.inp", r, dim_global, iproc, nvars, n_io, xl, ul)
+        files.add(fname)
+    return sorted(files)
+
+
+def parallel_to_serial(root_ext: str, dim_global, iproc, nvars: int, n_io: int, record: int = 0):
+    """Extras/ParallelOutput.c: stitch the blocks of <root_ext>.<nnnn> (one output time) into the global (x, u) that
+    WriteArraySerial would have written (write_op_bin's arguments)."""
+    nd = len(iproc)
+    x = [np.zeros(n) for n in dim_global]
+    u = np.zeros(tuple(reversed(list(dim_global))) + (nvars,))
+    root, ext = root_ext.rsplit(".", 1)
+    for r in range(int(np.prod(iproc))):
+        xl, ul = read_parallel_block(root, r, dim_global, iproc, nvars, n_io, record, suffix="." + ext)
+        is_, ie = local_extent(dim_global, iproc, r)
+        for d in range(nd):
+            x[d][is_[d]:ie[d]] = xl[d]
+        u[tuple(slice(is_[d], ie[d]) for d in reversed(range(nd)))] = ul
+    return x, u

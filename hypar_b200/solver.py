@@ -352,6 +352,40 @@ class Solver:
         self._ck(self.L.hpb_dev_StepNormSumSq(self.h, C.byref(out)))
         return out.value
 
+    # -- partitioned I/O: this rank's block of the reference's parallel / MPI-IO files, addressed
+    #    directly (hypario: no gather through a leader rank, 64-bit offsets)
+    def local_grid(self):
+        x, _ = self.grid()
+        g, out, off = self.ghosts, [], 0
+        for n in self.dim_local:
+            out.append(x[off + g: off + g + n].copy())
+            off += n + 2 * g
+        return out
+
+    def write_solution_parallel(self, root_ext: str = "op.bin", n_io: int = 1, record: int = 0) -> str:
+        """WriteArrayParallel (WriteArray.c:139-323): the device solution of this rank into <root_ext>.<nnnn>"""
+        u = np.ascontiguousarray(self.interior(self.get_solution()))
+        return hypario.write_parallel_block(root_ext, self.rank, self.dim_global, self.iproc, self.nvars, n_io,
+                                            self.local_grid(), u, record)
+
+    def load_solution_parallel(self, fname_root: str = "initial", n_io: int = 1, mode: str = "parallel") -> None:
+        """ReadArrayParallel / ReadArrayMPI_IO (ReadArray.c:293-650): this rank's block of <fname_root>_par.inp.<nnnn>
+        (mode "parallel") or <fname_root>_mpi.inp (mode "mpi-io") onto the device; the grid in the file must be the
+        one the solver was created with"""
+        if mode == "parallel":
+            xl, ul = hypario.read_parallel_block(fname_root, self.rank, self.dim_global, self.iproc, self.nvars, n_io)
+        elif mode == "mpi-io":
+            xl, ul = hypario.read_mpi_io_block(fname_root, self.rank, self.dim_global, self.iproc, self.nvars)
+        else:
+            raise HyParB200Error(f"input mode '{mode}' (parallel, mpi-io)")
+        for a, b in zip(xl, self.local_grid()):
+            if not np.array_equal(a, b):
+                raise HyParB200Error(f"{fname_root}: the grid in the file differs from the solver's grid")
+        g = self.ghosts
+        u = np.zeros(self.shape_g())
+        u[tuple(slice(g, g + n) for n in reversed(self.dim_local))] = ul
+        self.set_solution(np.ascontiguousarray(u).reshape(-1))
+
     # -- conservation / error diagnostics (this rank's parts; see include/hypar_b200.h)
     def dev_VolumeIntegral(self) -> np.ndarray:
         out = np.zeros(self.nvars)
