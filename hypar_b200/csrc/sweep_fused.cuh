@@ -107,36 +107,40 @@ __device__ __forceinline__ double sqrt_fast(double x)
 
 // ------------------------------------------------------------------------------------------
 // Both reconstructions a centred 5-cell stencil serves. X = values the weights are computed from,
-// Y = values that are reconstructed (Y == X for the flux; Y = uC, X = raw u for the solution: Q4).
+// Y = values that are reconstructed (SAME: Y is X -- the flux, and every component of the solution the modified
+// solution leaves unchanged; otherwise Y = uC, X = raw u: Q4).
 // Z (optional) = a second field reconstructed with the same weights (gravity source function: Q5).
 // Returns L = left-biased value at j+1/2, R = right-biased value at j-1/2.
-template <int WT, bool HASZ>
+//
+// The weights of a set sum to one, so a reconstruction is its CENTRAL candidate plus a weighted correction by the
+// two third differences of the stencil, D3a = Y0 - 3 Y1 + 3 Y2 - Y3 and D3b = Y1 - 3 Y2 + 3 Y3 - Y4:
+//   left-biased  candidates (Interp1PrimFifthOrderWENO.c:148-158): fL1 - fL2 =  D3a/3 ,  fL3 - fL2 =  D3b/6
+//   right-biased candidates (mirrored stencil)                   : fR1 - fR2 = -D3a/6 ,  fR3 - fR2 = -D3b/3
+//   L = fL2 + wL1 D3a/3 + wL3 D3b/6 ,   R = fR2 - wR1 D3a/6 - wR3 D3b/3
+// (index k = sub-stencil (j-2,j-1,j), (j-1,j,j+1), (j,j+1,j+2) for both biases). With Y = X the third differences
+// are differences of the second differences the smoothness indicators need anyway. 6 instead of 18 operations for
+// the candidates of a pair; algebraically the reference's formula.
+template <int WT, bool HASZ, bool SAME>
 __device__ __forceinline__ void recon_pair(const double (&X)[5], const double (&Y)[5], const double (&Z)[5],
                                            double eps, double& L, double& R, double& ZL, double& ZR)
 {
   const double s6 = 1.0 / 6.0;
-  // candidate values: left-biased (at j+1/2) and right-biased (at j-1/2); index k = sub-stencil
-  // (j-2,j-1,j), (j-1,j,j+1), (j,j+1,j+2)
-  const double fL1 = (2*s6) * Y[0] + (-7*s6) * Y[1] + (11*s6) * Y[2];
-  const double fL2 = (-s6) * Y[1] + (5*s6) * Y[2] + (2*s6) * Y[3];
-  const double fL3 = (2*s6) * Y[2] + (5*s6) * Y[3] + (-s6) * Y[4];
-  const double fR3 = (2*s6) * Y[4] + (-7*s6) * Y[3] + (11*s6) * Y[2];
-  const double fR2 = (-s6) * Y[3] + (5*s6) * Y[2] + (2*s6) * Y[1];
-  const double fR1 = (2*s6) * Y[2] + (5*s6) * Y[1] + (-s6) * Y[0];
-  double zL1 = 0, zL2 = 0, zL3 = 0, zR1 = 0, zR2 = 0, zR3 = 0;
+  // 6 x the central candidates
+  const double gL = fma(2.0, Y[3], fma(5.0, Y[2], -Y[1]));
+  const double gR = fma(2.0, Y[1], fma(5.0, Y[2], -Y[3]));
+  double zgL = 0, zgR = 0, zDa = 0, zDb = 0;
   if (HASZ) {
-    zL1 = (2*s6) * Z[0] + (-7*s6) * Z[1] + (11*s6) * Z[2];
-    zL2 = (-s6) * Z[1] + (5*s6) * Z[2] + (2*s6) * Z[3];
-    zL3 = (2*s6) * Z[2] + (5*s6) * Z[3] + (-s6) * Z[4];
-    zR3 = (2*s6) * Z[4] + (-7*s6) * Z[3] + (11*s6) * Z[2];
-    zR2 = (-s6) * Z[3] + (5*s6) * Z[2] + (2*s6) * Z[1];
-    zR1 = (2*s6) * Z[2] + (5*s6) * Z[1] + (-s6) * Z[0];
+    zgL = fma(2.0, Z[3], fma(5.0, Z[2], -Z[1]));
+    zgR = fma(2.0, Z[1], fma(5.0, Z[2], -Z[3]));
+    zDa = fma(3.0, Z[2] - Z[1], Z[0] - Z[3]);
+    zDb = fma(3.0, Z[3] - Z[2], Z[1] - Z[4]);
   }
-  const double c1 = 0.1, c2 = 0.6, c3 = 0.3;
   if (WT == WT_NOLIM) {
-    L = c1 * fL1 + c2 * fL2 + c3 * fL3;
-    R = c3 * fR1 + c2 * fR2 + c1 * fR3;     // right-biased: optimal weights mirrored
-    if (HASZ) { ZL = c1 * zL1 + c2 * zL2 + c3 * zL3; ZR = c3 * zR1 + c2 * zR2 + c1 * zR3; }
+    // optimal weights (0.1, 0.6, 0.3), mirrored for the right-biased value
+    const double Da = fma(3.0, Y[2] - Y[1], Y[0] - Y[3]), Db = fma(3.0, Y[3] - Y[2], Y[1] - Y[4]);
+    L = s6 * fma(0.3, Db, fma(0.2, Da, gL));
+    R = s6 * (gR - fma(0.2, Db, 0.3 * Da));
+    if (HASZ) { ZL = s6 * fma(0.3, zDb, fma(0.2, zDa, zgL)); ZR = s6 * (zgR - fma(0.2, zDb, 0.3 * zDa)); }
     return;
   }
   // smoothness indicators of the three sub-stencils (shared by both biases), scaled by 4: b_k = 4 beta_k =
@@ -146,6 +150,8 @@ __device__ __forceinline__ void recon_pair(const double (&X)[5], const double (&
   const double d1 = X[0] - 2*X[1] + X[2], e1 = X[0] - 4*X[1] + 3*X[2];
   const double d2 = X[1] - 2*X[2] + X[3], e2 = X[1] - X[3];
   const double d3 = X[2] - 2*X[3] + X[4], e3 = 3*X[2] - 4*X[3] + X[4];
+  const double Da = SAME ? (d1 - d2) : fma(3.0, Y[2] - Y[1], Y[0] - Y[3]);
+  const double Db = SAME ? (d2 - d3) : fma(3.0, Y[3] - Y[2], Y[1] - Y[4]);
   const double b1 = fma(e1, e1, (t133 * d1) * d1);
   const double b2 = fma(e2, e2, (t133 * d2) * d2);
   const double b3 = fma(e3, e3, (t133 * d3) * d3);
@@ -163,42 +169,45 @@ __device__ __forceinline__ void recon_pair(const double (&X)[5], const double (&
     const double tt = tau * tau;
     h1 = (q1 + tt) * (q2 * q3); h2 = (q2 + tt) * (q1 * q3); h3 = (q3 + tt) * (q1 * q2);
   }
-  // un-normalised nonlinear weights; left-biased: optimal (c1,c2,c3); right-biased: (c3,c2,c1)
-  double nL1 = c1 * h1, n2 = c2 * h2, nL3 = c3 * h3;
-  double nR1 = c3 * h1, nR3 = c1 * h3;
+  // un-normalised nonlinear weights, the common factor 0.1 of the optimal weights dropped:
+  // left-biased (h1, 6 h2, 3 h3), right-biased (3 h1, 6 h2, h3)
+  const double h26 = 6.0 * h2;
+  const double rL = rcp_fast(fma(3.0, h3, h26 + h1)), rR = rcp_fast(fma(3.0, h1, h26 + h3));
   if (WT != HPB_WENO_M) {
-    const double rL = rcp_fast(nL1 + n2 + nL3), rR = rcp_fast(nR1 + n2 + nR3);
-    L = (nL1 * fL1 + n2 * fL2 + nL3 * fL3) * rL;
-    R = (nR1 * fR1 + n2 * fR2 + nR3 * fR3) * rR;
+    // 6 L = gL + rL (2 h1 Da + 3 h3 Db) ; 6 R = gR - rR (3 h1 Da + 2 h3 Db)
+    const double P = h1 * Da, Q = h3 * Db;
+    L = s6 * fma(rL, fma(3.0, Q, 2.0 * P), gL);
+    R = s6 * fma(-rR, fma(3.0, P, 2.0 * Q), gR);
     if (HASZ) {
-      ZL = (nL1 * zL1 + n2 * zL2 + nL3 * zL3) * rL;
-      ZR = (nR1 * zR1 + n2 * zR2 + nR3 * zR3) * rR;
+      const double zP = h1 * zDa, zQ = h3 * zDb;
+      ZL = s6 * fma(rL, fma(3.0, zQ, 2.0 * zP), zgL);
+      ZR = s6 * fma(-rR, fma(3.0, zP, 2.0 * zQ), zgR);
     }
     return;
   }
   // mapped weights (Henrick et al.): w~ = JS weights; alpha_k = w~(c + c^2 - 3 c w~ + w~^2)/(c^2 + w~(1-2c)) = A_k/B_k;
-  // sum_k w_k f_k = (sum_k A_k B_l B_m f_k) / (sum_k A_k B_l B_m)
+  // w_k = A_k B_l B_m / sum_k A_k B_l B_m =: t_k / sum t. The factor 2 of the correction term is folded into the
+  // constants of A (T1 = 2 t1 on the left-biased side, T3 = 2 t3 on the right-biased side).
+  const double c1 = 0.1, c2 = 0.6, c3 = 0.3;
   {
-    const double rL = rcp_fast(nL1 + n2 + nL3);
-    const double w1 = nL1 * rL, w2 = n2 * rL, w3 = nL3 * rL;
-    const double A1 = w1 * (c1 + c1*c1 + w1 * (w1 - 3*c1)), B1 = c1*c1 + w1 * (1.0 - 2*c1);
+    const double w1 = h1 * rL, w2 = h26 * rL, w3 = h3 * (3.0 * rL);
+    const double A1 = w1 * (2*(c1 + c1*c1) + w1 * fma(2.0, w1, -6*c1)), B1 = c1*c1 + w1 * (1.0 - 2*c1);   // 2 A1
     const double A2 = w2 * (c2 + c2*c2 + w2 * (w2 - 3*c2)), B2 = c2*c2 + w2 * (1.0 - 2*c2);
     const double A3 = w3 * (c3 + c3*c3 + w3 * (w3 - 3*c3)), B3 = c3*c3 + w3 * (1.0 - 2*c3);
-    const double t1 = A1 * (B2 * B3), t2 = A2 * (B1 * B3), t3 = A3 * (B1 * B2);
-    const double r = rcp_fast(t1 + t2 + t3);
-    L = (t1 * fL1 + t2 * fL2 + t3 * fL3) * r;
-    if (HASZ) ZL = (t1 * zL1 + t2 * zL2 + t3 * zL3) * r;
+    const double T1 = A1 * (B2 * B3), t2 = A2 * (B1 * B3), t3 = A3 * (B1 * B2);
+    const double r = rcp_fast(fma(0.5, T1, t2) + t3);
+    L = s6 * fma(r, fma(t3, Db, T1 * Da), gL);
+    if (HASZ) ZL = s6 * fma(r, fma(t3, zDb, T1 * zDa), zgL);
   }
   {
-    const double rR = rcp_fast(nR1 + n2 + nR3);
-    const double w1 = nR1 * rR, w2 = n2 * rR, w3 = nR3 * rR;   // optimal weights (c3, c2, c1)
+    const double w1 = h1 * (3.0 * rR), w2 = h26 * rR, w3 = h3 * rR;   // optimal weights (c3, c2, c1)
     const double A1 = w1 * (c3 + c3*c3 + w1 * (w1 - 3*c3)), B1 = c3*c3 + w1 * (1.0 - 2*c3);
     const double A2 = w2 * (c2 + c2*c2 + w2 * (w2 - 3*c2)), B2 = c2*c2 + w2 * (1.0 - 2*c2);
-    const double A3 = w3 * (c1 + c1*c1 + w3 * (w3 - 3*c1)), B3 = c1*c1 + w3 * (1.0 - 2*c1);
-    const double t1 = A1 * (B2 * B3), t2 = A2 * (B1 * B3), t3 = A3 * (B1 * B2);
-    const double r = rcp_fast(t1 + t2 + t3);
-    R = (t1 * fR1 + t2 * fR2 + t3 * fR3) * r;
-    if (HASZ) ZR = (t1 * zR1 + t2 * zR2 + t3 * zR3) * r;
+    const double A3 = w3 * (2*(c1 + c1*c1) + w3 * fma(2.0, w3, -6*c1)), B3 = c1*c1 + w3 * (1.0 - 2*c1);   // 2 A3
+    const double t1 = A1 * (B2 * B3), t2 = A2 * (B1 * B3), T3 = A3 * (B1 * B2);
+    const double r = rcp_fast(fma(0.5, T3, t2) + t1);
+    R = s6 * fma(-r, fma(t1, Da, T3 * Db), gR);
+    if (HASZ) ZR = s6 * fma(-r, fma(t1, zDa, T3 * zDb), zgR);
   }
 }
 
@@ -423,12 +432,12 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const SweepArgs a)
         for (int k = 0; k < 5; k++) X[k] = rec[(RL::F + v) * NREC + cc + (k - 2)];
         const bool zsrc = G3 && a.with_source && (v == dir + 1 || v == NV - 1);
         if (G3 && zsrc) {
-          recon_pair<WT, true>(X, X, Zg, a.ph.eps, L, fRv[v], zl, zr);
+          recon_pair<WT, true, true>(X, X, Zg, a.ph.eps, L, fRv[v], zl, zr);
           const int sidx = (v == NV - 1) ? 1 : 0;
           sR[sidx] = zr;
           exL[(2 * NV + sidx) * NEX + ex] = zl;
         } else {
-          recon_pair<WT, false>(X, X, X, a.ph.eps, L, fRv[v], zl, zr);
+          recon_pair<WT, false, true>(X, X, X, a.ph.eps, L, fRv[v], zl, zr);
         }
         exL[v * NEX + ex] = L;
         // solution: weights from raw u, applied to the modified solution (Q4)
@@ -440,9 +449,9 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const SweepArgs a)
             if (v == NV - 1) Y[k] = rec[RL::V4 * NREC + cc + (k - 2)];
             else Y[k] = X[k] * rec[SL::GFI * NREC + cc + (k - 2)];
           }
-          recon_pair<WT, false>(X, Y, Y, a.ph.eps, L, uRv[v], zl, zr);
+          recon_pair<WT, false, false>(X, Y, Y, a.ph.eps, L, uRv[v], zl, zr);
         } else {
-          recon_pair<WT, false>(X, X, X, a.ph.eps, L, uRv[v], zl, zr);
+          recon_pair<WT, false, true>(X, X, X, a.ph.eps, L, uRv[v], zl, zr);
         }
         exL[(NV + v) * NEX + ex] = L;
       }

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
         double X[5], Y[5], L, R, zl, zr;
 #pragma unroll
         for (int k = 0; k < 5; k++) { X[k] = rec[fx * NREC + cp + (k - 2)]; Y[k] = rec[fy * NREC + cp + (k - 2)]; }
-        recon_pair<WT, false>(X, Y, Y, a.ph.eps, L, R, zl, zr);
+        recon_pair<WT, false, false>(X, Y, Y, a.ph.eps, L, R, zl, zr);
         const int xf = isU ? LY::xU + v : LY::xF + v;
         exL[xf * NEX + xbase + 31 + ce] = L;
         if (ce == 1) exL[xf * NEX + xbase + 1] = R;
@@ -340,12 +340,12 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
           for (int k = 0; k < 5; k++) X[k] = rec[(LY::rF + v) * NREC + cc + (k - 2)];
           const bool zsrc = G3 && a.with_source && (v == dir + 1 || v == NV - 1);
           if (G3 && zsrc) {
-            recon_pair<WT, true>(X, X, Zg, a.ph.eps, L, fRv[v], zl, zr);
+            recon_pair<WT, true, true>(X, X, Zg, a.ph.eps, L, fRv[v], zl, zr);
             const int si = (v == NV - 1) ? 1 : 0;
             sR[si] = zr;
             exL[(LY::xZ + si) * NEX + ex] = zl;
           } else {
-            recon_pair<WT, false>(X, X, X, a.ph.eps, L, fRv[v], zl, zr);
+            recon_pair<WT, false, true>(X, X, X, a.ph.eps, L, fRv[v], zl, zr);
           }
           exL[(LY::xF + v) * NEX + ex] = L;
         }
@@ -358,9 +358,9 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
             if (v == NV - 1) Y[k] = rec[LY::rV4 * NREC + cc + (k - 2)];
             else Y[k] = X[k] * rec[LY::rGF * NREC + cc + (k - 2)];
           }
-          recon_pair<WT, false>(X, Y, Y, a.ph.eps, L, uRv[v], zl, zr);
+          recon_pair<WT, false, false>(X, Y, Y, a.ph.eps, L, uRv[v], zl, zr);
         } else {
-          recon_pair<WT, false>(X, X, X, a.ph.eps, L, uRv[v], zl, zr);
+          recon_pair<WT, false, true>(X, X, X, a.ph.eps, L, uRv[v], zl, zr);
         }
         exL[(LY::xU + v) * NEX + ex] = L;
       }
