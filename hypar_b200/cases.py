@@ -194,7 +194,8 @@ def ns3d_turbulence(n: Sequence[int] = (512, 512, 512), weno: str = "mapped", vi
     phys: Dict[str, object] = {"gamma": gamma, "upwinding": upwinding, "Pr": 0.72, "Minf": Minf}
     phys["Re"] = 333.333333333333333 if viscous else -1.0
     return Case(
-        name=f"c4_turb_{n[0]}x{n[1]}x{n[2]}_{weno}_{'visc' if viscous else 'inv'}",
+        name=f"c4_turb_{n[0]}x{n[1]}x{n[2]}_{weno}_{'visc' if viscous else 'inv'}"
+             + ("" if upwinding == "rusanov" else "_" + upwinding) + ("" if interp == "components" else "_char"),
         solver=_solver(3, 5, n, "navierstokes3d", ts="rk", tstype=tstype, dt=dt, iproc=iproc, interp=interp,
                        par_type="nonconservative-2stage", par_scheme="4"),
         boundary=_zones(3, "periodic", [-1e3] * 3, [1e3] * 3),

@@ -221,6 +221,22 @@ HPB_DEV void ns3d_eigen(double ga, const double* u, int dir, double* lam, double
   }
 }
 
+// eigenvalues only (_Euler1DEigenvalues_, _NavierStokes3DEigenvalues_ navierstokes3d.h:254-278): same ordering as eigen()
+template <int MODEL>
+HPB_DEV void eigenvalues(const Phys& ph, const double* u, int dir, double* lam)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  double rho, vel[3], e, P;
+  flowvar<MODEL>(u, ph.gamma, rho, vel, e, P);
+  const double c = sqrt(ph.gamma * P / rho);
+  if (MODEL == HPB_MODEL_EULER1D) { lam[0] = vel[0]; lam[1] = vel[0] - c; lam[2] = vel[0] + c; }
+  else {
+    const double vn = (dir == 0) ? vel[0] : (dir == 1 ? vel[1] : vel[2]);
+#pragma unroll
+    for (int k = 0; k < NV; k++) lam[k] = (k == dir + 1) ? (vn - c) : ((k == NV - 1) ? (vn + c) : vn);
+  }
+}
+
 template <int MODEL>
 HPB_DEV void eigen(const Phys& ph, const double* u, int dir, double* lam, double* L, double* R)
 {
@@ -261,6 +277,52 @@ HPB_DEV void upwind_fn(const Phys& ph, int dir, const double* fL, const double* 
     const double alpha = kappa * hpb_max3(alphaL, alphaR, alphaavg);
 #pragma unroll
     for (int v = 0; v < NV; v++) fI[v] = 0.5 * (fL[v] + fR[v]) - alpha * udiff[v];
+  } else if (ph.upwind == HPB_UPWIND_RF || ph.upwind == HPB_UPWIND_LLF) {
+    // characteristic-based Roe-fixed / local Lax-Friedrichs: NavierStokes3DUpwind.c:140-237, :244-330;
+    // Euler1DUpwind.c:115-205, :212-286. NavierStokes3D takes the Roe average and the one-sided eigenvalues
+    // from the RECONSTRUCTED interface states uL, uR; Euler1D from the two adjacent cells, with kappa.
+    if (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D) {
+      double eigL[NV], eigC[NV], eigR[NV], L[NV * NV], R[NV * NV], uroe[NV];
+      if (MODEL == HPB_MODEL_NS3D) {
+        roe_average<MODEL>(ph, uL, uR, uroe);
+        eigenvalues<MODEL>(ph, uL, dir, eigL);
+        eigenvalues<MODEL>(ph, uR, dir, eigR);
+      } else {
+#pragma unroll
+        for (int v = 0; v < NV; v++) uroe[v] = uavg[v];
+        eigenvalues<MODEL>(ph, ucL, dir, eigL);
+        eigenvalues<MODEL>(ph, ucR, dir, eigR);
+      }
+      eigen<MODEL>(ph, uroe, dir, eigC, L, R);
+      double wL[NV], wR[NV], gL[NV], gR[NV], fc[NV];
+#pragma unroll
+      for (int i = 0; i < NV; i++) {           // MatVecMult3/5 (matops.h): left to right
+        double a = L[i * NV] * uL[0], b = L[i * NV] * uR[0], c = L[i * NV] * fL[0], d = L[i * NV] * fR[0];
+#pragma unroll
+        for (int j = 1; j < NV; j++) {
+          a += L[i * NV + j] * uL[j]; b += L[i * NV + j] * uR[j];
+          c += L[i * NV + j] * fL[j]; d += L[i * NV + j] * fR[j];
+        }
+        wL[i] = a; wR[i] = b; gL[i] = c; gR[i] = d;
+      }
+#pragma unroll
+      for (int k = 0; k < NV; k++) {
+        if (ph.upwind == HPB_UPWIND_RF && eigL[k] > 0 && eigC[k] > 0 && eigR[k] > 0)      fc[k] = gL[k];
+        else if (ph.upwind == HPB_UPWIND_RF && eigL[k] < 0 && eigC[k] < 0 && eigR[k] < 0) fc[k] = gR[k];
+        else {
+          double alpha = hpb_max3(hpb_abs(eigL[k]), hpb_abs(eigC[k]), hpb_abs(eigR[k]));
+          if (MODEL == HPB_MODEL_EULER1D) alpha = kappa * alpha;
+          fc[k] = 0.5 * (gL[k] + gR[k] + alpha * (wL[k] - wR[k]));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+        double s2 = R[i * NV] * fc[0];
+#pragma unroll
+        for (int j = 1; j < NV; j++) s2 += R[i * NV + j] * fc[j];
+        fI[i] = s2;
+      }
+    }
   } else {
     if (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D) {
       double lam[NV], L[NV * NV], R[NV * NV];

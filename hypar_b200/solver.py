@@ -21,7 +21,7 @@ from . import _lib, hypario
 
 MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3}
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2}
-UPWINDS = {"roe": 1, "rusanov": 2}
+UPWINDS = {"roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 RK_TYPES = {"44": 0, "ssprk3": 1}
 FIELD_U, FIELD_QDERIVX, FIELD_QDERIVY = 0, 1, 2
 
@@ -88,7 +88,7 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     else:
         up = str(ph.get("upwinding", "roe"))
         if up not in UPWINDS:
-            raise HyParB200Error(f"upwinding '{up}' is not on the B200 path (roe, rusanov)")
+            raise HyParB200Error(f"upwinding '{up}' is not on the B200 path (roe, rusanov, rf-char, llf-char)")
         c.upwind = UPWINDS[up]
     c.gamma = float(ph.get("gamma", 1.4))
     c.Re, c.Pr, c.Minf = float(ph.get("Re", -1.0)), float(ph.get("Pr", 0.72)), float(ph.get("Minf", 1.0))

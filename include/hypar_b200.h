@@ -59,6 +59,8 @@ extern "C" {
 #define HPB_UPWIND_DEFAULT 0    /* LinearADRUpwind */
 #define HPB_UPWIND_ROE     1
 #define HPB_UPWIND_RUSANOV 2
+#define HPB_UPWIND_RF      3    /* "rf-char":  characteristic-based Roe-fixed (Euler1D, NavierStokes3D)          */
+#define HPB_UPWIND_LLF     4    /* "llf-char": characteristic-based local Lax-Friedrichs (Euler1D, NavierStokes3D) */
 
 /* boundary.inp zone types implemented on the device (reference: 17 types; the three the
    BASELINE configurations use) */

@@ -147,6 +147,15 @@ static int B200_TimeRK(void *ts)
   return 0;
 }
 
+static int upwind_choice(const char *name)
+{
+  if (!strcmp(name, _RUSANOV_)) return HPB_UPWIND_RUSANOV;
+  if (!strcmp(name, _ROE_))     return HPB_UPWIND_ROE;
+  if (!strcmp(name, _RF_))      return HPB_UPWIND_RF;
+  if (!strcmp(name, _LLF_))     return HPB_UPWIND_LLF;
+  return -1;
+}
+
 static int bc_type(const char *name)
 {
   if (!strcmp(name, _PERIODIC_))    return HPB_BC_PERIODIC;
@@ -190,7 +199,7 @@ int hyparb200_attach(void *sims, int nsims)
     NavierStokes3D *p = (NavierStokes3D*) s->physics;
     c.model = HPB_MODEL_NS3D;  c.gamma = p->gamma;  c.Pr = p->Pr;  c.Minf = p->Minf;
     c.Re = (p->Re > 0 ? p->Re * p->Minf : p->Re);   /* HyPar already divided Re by Minf (NavierStokes3DInitialize.c:368) */
-    c.upwind = !strcmp(p->upw_choice, _RUSANOV_) ? HPB_UPWIND_RUSANOV : !strcmp(p->upw_choice, _ROE_) ? HPB_UPWIND_ROE : -1;
+    c.upwind = upwind_choice(p->upw_choice);
     c.gravity[0] = p->grav_x; c.gravity[1] = p->grav_y; c.gravity[2] = p->grav_z;
     c.rho_ref = p->rho0; c.p_ref = p->p0; c.R = p->R; c.HB = p->HB; c.N_bv = p->N_bv;
     if (c.Re > 0 && strcmp(s->spatial_type_par, _NC_2STAGE_)) return 1;
@@ -203,7 +212,7 @@ int hyparb200_attach(void *sims, int nsims)
   } else if (!strcmp(s->model, _EULER_1D_)) {
     Euler1D *p = (Euler1D*) s->physics;
     c.model = HPB_MODEL_EULER1D;  c.gamma = p->gamma;
-    c.upwind = !strcmp(p->upw_choice, _RUSANOV_) ? HPB_UPWIND_RUSANOV : !strcmp(p->upw_choice, _ROE_) ? HPB_UPWIND_ROE : -1;
+    c.upwind = upwind_choice(p->upw_choice);
     if (p->grav != 0.0) { fprintf(stderr, "hyparb200_attach: euler1d with gravity is not on the B200 path\n"); return 1; }
   } else if (!strcmp(s->model, _LINEAR_ADVECTION_DIFFUSION_REACTION_)) {
     LinearADR *p = (LinearADR*) s->physics;
@@ -215,7 +224,7 @@ int hyparb200_attach(void *sims, int nsims)
   } else {
     fprintf(stderr, "hyparb200_attach: model %s is not on the B200 path\n", s->model); return 1;
   }
-  if (c.upwind < 0) { fprintf(stderr, "hyparb200_attach: upwinding scheme is not on the B200 path (roe, rusanov)\n"); return 1; }
+  if (c.upwind < 0) { fprintf(stderr, "hyparb200_attach: upwinding scheme is not on the B200 path (roe, rusanov, rf-char, llf-char)\n"); return 1; }
 
   DomainBoundary *b = (DomainBoundary*) s->boundary;
   if (s->nBoundaryZones > HPB_MAX_ZONES) return 1;

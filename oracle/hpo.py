@@ -24,7 +24,7 @@ MAXD, MAXV, MAXZ = 3, 5, 16
 
 MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3}
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2}
-UPWINDS = {"default": 0, "roe": 1, "rusanov": 2}
+UPWINDS = {"default": 0, "roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 
 
 class Zone(C.Structure):

@@ -122,7 +122,7 @@ def test_decomposed_setup_neighbors_and_remainders():
     (lambda c: c.solver.__setitem__("ghost", 2), "ghost"),
     (lambda c: c.solver.__setitem__("model", "shallow-water-2d"), "model"),
     (lambda c: c.boundary[0].__setitem__("type", "noslip-wall"), "boundary type"),
-    (lambda c: c.physics.__setitem__("upwinding", "llf-char"), "upwinding"),
+    (lambda c: c.physics.__setitem__("upwinding", "steger-warming"), "upwinding"),
     (lambda c: c.solver.__setitem__("par_space_type", "conservative-1stage"), "nonconservative-2stage"),
 ])
 def test_unsupported_configurations_fail_loudly(mutate, msg):

@@ -44,10 +44,16 @@ def _cases():
     C.append(cases.ns3d_density_wave((16, 12, 10), "js"))                       # C5a
     C.append(cases.ns3d_rising_bubble((12, 16, 10), "yc"))                      # C5b: slip walls + gravity
     C.append(cases.ns3d_rising_bubble((10, 14, 12), "mapped", hb=1))
+    # characteristic-based Roe-fixed / local Lax-Friedrichs upwinding; appended so that the
+    # indices used below (STEP_CASES ...) stay put
     nl = cases.ns3d_density_wave((12, 10, 8), "js")
     nl.weno["no_limiting"] = 1
     nl.name += "_nolimiting"
     C.append(nl)
+    C.append(cases.euler1d_sod(101, "js", upwinding="rf-char"))
+    C.append(cases.euler1d_sod(101, "z", interp="components", upwinding="llf-char"))
+    C.append(cases.ns3d_turbulence((12, 10, 14), "mapped", viscous=False, upwinding="rf-char"))
+    C.append(cases.ns3d_turbulence((10, 12, 8), "yc", viscous=True, interp="characteristic", upwinding="llf-char"))
     return C
 
 
@@ -128,7 +134,7 @@ def test_rhs_parity(need_gpu, case):
     sv.close()
 
 
-STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26]]
+STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CASES[30], CASES[32]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)

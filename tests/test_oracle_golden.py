@@ -40,7 +40,7 @@ def same(a, b, what):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 14
+    assert len(GOLDEN) >= 18
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -115,6 +115,10 @@ def _live_cases():
         cases.ns3d_turbulence((20, 14, 12), "yc"),
         cases.ns3d_turbulence((12, 10, 14), "mapped", viscous=True, interp="characteristic", upwinding="roe"),
         cases.ns3d_rising_bubble((10, 14, 12), "z", hb=3) if False else cases.ns3d_rising_bubble((10, 14, 12), "z"),
+        cases.euler1d_sod(101, "mapped", upwinding="rf-char"),
+        cases.euler1d_sod(101, "js", interp="components", upwinding="llf-char"),
+        cases.ns3d_turbulence((12, 10, 14), "js", viscous=False, upwinding="llf-char"),
+        cases.ns3d_turbulence((10, 12, 8), "z", viscous=True, interp="characteristic", upwinding="rf-char"),
     ]
 
 

@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, built from /root/reference).
 
-    python tools/make_golden.py
+    python tools/make_golden.py [fixture names ...]
 
 Each fixture holds, for one small case of a BASELINE.json configuration family, the outputs of the
 reference's own code on that case's input files:
@@ -36,6 +36,10 @@ GOLDEN = [
     ("c4_turb_mapped_visc", "ns3d_turbulence", dict(n=(10, 8, 8), weno="mapped"), "hypar_ref_mpi1", True),
     ("c4_turb_js_roe_inv", "ns3d_turbulence", dict(n=(12, 10, 14), weno="js", upwinding="roe", viscous=False), "hypar_ref", False),
     ("c4_turb_z_char_inv", "ns3d_turbulence", dict(n=(12, 12, 10), weno="z", interp="characteristic", viscous=False), "hypar_ref", False),
+    ("c2_sod_js_char_rf", "euler1d_sod", dict(n=101, weno="js", upwinding="rf-char"), "hypar_ref", True),
+    ("c2_sod_yc_comp_llf", "euler1d_sod", dict(n=101, weno="yc", interp="components", upwinding="llf-char"), "hypar_ref", False),
+    ("c4_turb_z_rf_inv", "ns3d_turbulence", dict(n=(12, 10, 14), weno="z", upwinding="rf-char", viscous=False), "hypar_ref", False),
+    ("c4_turb_mapped_char_llf_visc", "ns3d_turbulence", dict(n=(10, 8, 8), weno="mapped", interp="characteristic", upwinding="llf-char"), "hypar_ref_mpi1", False),
     ("c5a_denswave_js", "ns3d_density_wave", dict(n=(12, 10, 8), weno="js"), "hypar_ref", False),
     ("c5b_bubble_yc", "ns3d_rising_bubble", dict(n=(12, 16, 10), weno="yc"), "hypar_ref_mpi1", True),
     ("c5b_bubble_mapped_hb1", "ns3d_rising_bubble", dict(n=(10, 12, 14), weno="mapped", hb=1), "hypar_ref", False),
@@ -66,7 +70,10 @@ def build_case(builder, kwargs):
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = set(sys.argv[1:])          # optional: fixture names to (re)generate; default all
     for name, builder, kwargs, exe, pieces in GOLDEN:
+        if only and name not in only:
+            continue
         case = build_case(builder, kwargs)
         data = {}
         o = run_reference(case, "rhs", exe=exe)
