@@ -163,7 +163,7 @@ static void stage_boundary_flux(hpb_solver* h, const double* U, int slot, int on
 static int alloc_main(hpb_solver* h)
 {
   const long long n = ncell(h);
-  TRY(dalloc(&h->d_u, n)); TRY(dalloc(&h->d_uprev, n)); TRY(dalloc(&h->d_U, n));
+  TRY(dalloc(&h->d_u, n)); TRY(dalloc(&h->d_U, n));
   for (int s = 0; s < h->rk.ns; s++) TRY(dalloc(&h->d_Udot[s], n));
   if (fused_visc(h)) TRY(dalloc(&h->d_qd4, 12 * h->geo.npg));
   if (!fused_path(h) || (viscous_on(h) && !fused_visc(h))) TRY(ensure_generic(h));
@@ -230,7 +230,7 @@ extern "C" int hpb_destroy(hpb_solver* h)
 {
   if (!h) return HPB_OK;
   if (h->stream || h->d_x) cudaSetDevice(h->device);
-  double** ptrs[] = { &h->d_x, &h->d_dxinv, &h->d_gravf, &h->d_gravg, &h->d_u, &h->d_uprev, &h->d_U, &h->d_fI, &h->d_sI,
+  double** ptrs[] = { &h->d_x, &h->d_dxinv, &h->d_gravf, &h->d_gravg, &h->d_u, &h->d_U, &h->d_fI, &h->d_sI,
                       &h->d_FV, &h->d_stage_aos, &h->d_w, &h->d_red, &h->d_qd4, &h->d_par, &h->d_src,
                       &h->d_cons, &h->d_face, &h->d_part };
   for (double** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
@@ -626,13 +626,12 @@ static double* stage_U(hpb_solver* h, int s)
 
 static int step_single(hpb_solver* h)
 {
-  const long long n = ncell(h);
-  // TimePreStep.c:50-76: boundary conditions on u; copy for the step norm
+  // TimePreStep.c:50-76: boundary conditions on u (the step norm of TimePostStep is formed from the stage
+  // right-hand sides afterwards: no copy of u is kept)
   hpbk::apply_bc(h, h->d_u);
-  hpbk::copy(h, h->d_uprev, h->d_u, n);
   for (int s = 0; s < h->rk.ns; s++) {
     double* U = stage_U(h, s);                  // TimeRK.c:131-141
-    hpbk::apply_bc(h, U);                       // TimeRHSFunctionExplicit.c:46
+    if (s > 0) hpbk::apply_bc(h, U);            // TimeRHSFunctionExplicit.c:46 (stage 0 is u itself: just done)
     TRY(rhs_part_a(h, U, h->d_Udot[s]));
     TRY(rhs_part_b(h, U, h->d_Udot[s]));
     stage_boundary_flux(h, U, s);               // TimeRK.c:172-177 (BoundaryFlux[s] = StageBoundaryIntegral)
@@ -678,7 +677,7 @@ extern "C" int hpb_dev_ComputeCFL(hpb_solver* h, double* cfl_local_max)
 extern "C" int hpb_dev_StepNormSumSq(hpb_solver* h, double* sumsq_local)
 {
   TRY(need_device(h));
-  hpbk::sumsq_diff(h, h->d_u, h->d_uprev, sumsq_local);
+  hpbk::step_norm_sumsq(h, sumsq_local);
   return check_async(h, "dev_StepNormSumSq");
 }
 
@@ -788,7 +787,6 @@ extern "C" int hpb_step_halo_done(hpb_solver* h)
 {
   TRY(need_device(h));
   hpbk::unpack(h, h->d_u, h->geo.nvars, HPB_FIELD_U);
-  hpbk::copy(h, h->d_uprev, h->d_u, ncell(h));
   return check_async(h, "step_halo_done");
 }
 

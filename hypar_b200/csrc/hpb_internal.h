@@ -59,7 +59,6 @@ struct hpb_solver {
   // device arrays
   double *d_x = nullptr, *d_dxinv = nullptr, *d_gravf = nullptr, *d_gravg = nullptr;
   double *d_u = nullptr;           // solution (SoA, ghosts)
-  double *d_uprev = nullptr;       // u at the start of the step (norm)
   double *d_U = nullptr;           // stage solution
   int interior_stage = -1;         // staged API: stage whose halo-independent work (hpb_stage_interior) is already done
   double *U_cur = nullptr;         // staged API: the array holding the current stage solution (d_u for stage 0)
@@ -143,6 +142,7 @@ void rk_finish(hpb_solver* h);
 void copy(hpb_solver* h, double* dst, const double* src, long long n);
 void cfl(hpb_solver* h, const double* u, double dt, double* out_host);
 void sumsq_diff(hpb_solver* h, const double* a, const double* b, double* out_host);
+void step_norm_sumsq(hpb_solver* h, double* out_host);   // from the stage right-hand sides of the last step
 // conservation / error diagnostics (deterministic reductions)
 void boundary_flux(hpb_solver* h, const double* u, int d, double* sbi);
 void step_boundary_integral(hpb_solver* h, const double* bf, double* step_bi);

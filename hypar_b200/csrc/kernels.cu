@@ -646,6 +646,28 @@ k_diag_partial(Geom G, const double* __restrict__ dxinv, const double* __restric
   }
 }
 
+// TimePostStep.c:44-63: sum over the interior of (u^{n+1} - u^n)^2, evaluated from the stage right-hand sides the step
+// has just combined, u^{n+1} - u^n = sum_s (dt b_s) k_s -- no copy of u^n is kept (2 passes over memory per step
+// saved). It differs from the reference's difference of the two stored solutions by the rounding of the update
+// (relative 1e-16 |u| / |u^{n+1} - u^n| per point).
+__global__ void __launch_bounds__(DIAG_TPB)
+k_step_norm_partial(Geom G, RKArgs args, double* __restrict__ part)
+{
+  const long long nint = (long long)G.N[0] * G.N[1] * G.N[2];
+  double acc = 0.0;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nint; q += (long long)gridDim.x * blockDim.x) {
+    const int i0 = (int)(q % G.N[0]), i1 = (int)((q / G.N[0]) % G.N[1]), i2 = (int)(q / ((long long)G.N[0] * G.N[1]));
+    const long long p = cell_index(G, i0, i1, i2);
+    for (int v = 0; v < G.nvars; v++) {
+      double d = 0.0;
+      for (int s = 0; s < args.n; s++) d += args.a[s] * args.k[s][v * G.npg + p];
+      acc += d * d;
+    }
+  }
+  const double r = block_reduce(acc, false);
+  if (threadIdx.x == 0) part[blockIdx.x] = r;
+}
+
 // final pass: one block per channel over the nblk partials; channel `max_ch` is a maximum, the others sums
 __global__ void __launch_bounds__(DIAG_TPB)
 k_diag_final(const double* __restrict__ part, int nblk, int max_ch, double* __restrict__ out)
@@ -1038,6 +1060,18 @@ void cfl(hpb_solver* h, const double* u, double dt, double* out_host)
   MODEL_SWITCH(h->cfg.model, CALL)
 #undef CALL
   LAUNCHED(h);
+  cudaMemcpyAsync(h->h_red, h->d_red, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  *out_host = h->h_red[0];
+}
+
+void step_norm_sumsq(hpb_solver* h, double* out_host)
+{
+  const Geom& G = h->geo;
+  RKArgs a; a.n = h->rk.ns;
+  for (int s = 0; s < h->rk.ns; s++) { a.k[s] = h->d_Udot[s]; a.a[s] = h->cfg.dt * h->rk.b[s]; }
+  k_step_norm_partial<<<DIAG_BLOCKS, DIAG_TPB, 0, h->stream>>>(G, a, h->d_part); LAUNCHED(h);
+  k_diag_final<<<1, DIAG_TPB, 0, h->stream>>>(h->d_part, DIAG_BLOCKS, -1, h->d_red); LAUNCHED(h);
   cudaMemcpyAsync(h->h_red, h->d_red, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
   cudaStreamSynchronize(h->stream);
   *out_host = h->h_red[0];

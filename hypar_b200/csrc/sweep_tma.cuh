@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
     double dd = 0.0, dxi = 0.0;
     if (V3 && c1 >= -3 && c1 <= N + 2) dd = dxl[c1];
     if (jo >= 0 && jo < N) dxi = dxl[jo];
+    const double dxih = 0.5 * dxi;
 
     mbar_wait(full_bar, (unsigned)(m + 1) & 1u);
 
@@ -255,7 +256,9 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
         rec[LY::rGF * NREC + ci] = gfv; rec[(LY::rGF + 1) * NREC + ci] = ggv;
       }
       const double igm1 = 1.0 / (gamma - 1.0);
-      rec[LY::rV4 * NREC + ci] = G3 ? ((P * igm1) * rcp_fast(ggv) + ke * gfv) : (P * igm1 + ke);
+      // modified solution (NavierStokes3DModifiedSolution.c:65): without gravity its energy P/(gamma-1) + rho|v|^2/2 is
+      // the conserved energy itself (to rounding), like the other components: nothing to store
+      if (G3) rec[LY::rV4 * NREC + ci] = (P * igm1) * rcp_fast(ggv) + ke * gfv;
       const double c2 = gamma * P * rinv;
       rec[LY::rSR * NREC + ci] = sqrt_fast(rho);
 #pragma unroll
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
         const bool isU = pr >= NV - 1;
         const int v = isU ? pr - (NV - 1) : pr + 1;
         const int fx = isU ? LY::rU + v : LY::rF + v;
-        const int fy = (isU && v == NV - 1) ? LY::rV4 : fx;
+        const int fy = (G3 && isU && v == NV - 1) ? LY::rV4 : fx;
         const int cp = rbase + 33 + ce;
         double X[5], Y[5], L, R, zl, zr;
 #pragma unroll
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
         // solution: weights from raw u, applied to the modified solution (Q4)
 #pragma unroll
         for (int k = 0; k < 5; k++) X[k] = rec[(LY::rU + v) * NREC + cc + (k - 2)];
-        if (G3 || v == NV - 1) {
+        if (G3) {
 #pragma unroll
           for (int k = 0; k < 5; k++) {
             if (v == NV - 1) Y[k] = rec[LY::rV4 * NREC + cc + (k - 2)];
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
       for (int v = 0; v < NV; v++) {
         const double uL = exL[(LY::xU + v) * NEX + exl];
         const double fL = (SKIPF0 && v == 0) ? exL[(LY::xU + 1 + dir) * NEX + exl] : exL[(LY::xF + v) * NEX + exl];
-        fh[v] = 0.5 * (fL + fRv[v]) - alpha * (0.5 * (uRv[v] - uL));
+        fh[v] = (fL + fRv[v]) - alpha * (uRv[v] - uL);          // 2 x the interface flux; the factor 1/2 is in dxih
       }
       const int exo = xbase + l + 1;
 #pragma unroll
@@ -422,17 +425,16 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
         const int co = cc - 1;
 #pragma unroll
         for (int v = 0; v < NV; v++) {
-          const double t = dxi * (fh[v] - exF[v * NEX + exl]);
+          const double t = dxih * (fh[v] - exF[v * NEX + exl]);
           res[v] = (a.mode < 2) ? -t : t;
         }
         if (V3) {
           // par_v += dxinv * (FV[j-2] - 8 FV[j-1] + 8 FV[j+1] - FV[j+2]) / 12   (components 1..4)
-          const double s12 = 1.0 / 12.0;
+          const double dxi12 = dxi * (1.0 / 12.0);
 #pragma unroll
           for (int v = 0; v < 4; v++) {
             const double* f = rec + (LY::rFV + v) * NREC + co;
-            const double dfv = (f[-2] - 8 * f[-1] + 8 * f[1] - f[2]) * s12;
-            res[1 + v] += dxi * dfv;
+            res[1 + v] = fma(dxi12, fma(8.0, f[1] - f[-1], f[-2] - f[2]), res[1 + v]);
           }
         }
         if (G3 && a.with_source) {

@@ -192,7 +192,8 @@ int hpb_TimeStep(hpb_solver* h);
 int hpb_TimeSteps(hpb_solver* h, int nsteps);
 double hpb_current_time(const hpb_solver* h);
 /* reductions on the device solution: CFL (ComputeCFL) and the step norm of TimePostStep.c:44-63
-   (returns the LOCAL sum of squares of u - u_prev and the local max CFL; callers all-reduce) */
+   (returns the local max CFL and the LOCAL sum of squares of u^{n+1} - u^n of the last step, formed from the stage
+   right-hand sides the step combined -- valid until the next step starts; callers all-reduce) */
 int hpb_dev_ComputeCFL(hpb_solver* h, double* cfl_local_max);
 int hpb_dev_StepNormSumSq(hpb_solver* h, double* sumsq_local);
 /* ---- conservation and error diagnostics, evaluated on the device solution; only scalars
