@@ -226,6 +226,37 @@ class DistributedSolver:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return float(t.item())
 
+    # conservation diagnostics of TimePostStep.c:81-93 across the ranks: each rank reduces its own block on the device,
+    # the nvars-long partial results are summed where the reference calls MPISum_double (VolumeIntegral.c:44,
+    # BoundaryIntegral.c:52); the flux integrals of internal faces cancel between neighbours
+    def _allreduce_sum(self, a: np.ndarray) -> np.ndarray:
+        import torch.distributed as dist
+        t = self.torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def volume_integral(self) -> np.ndarray:
+        return self._allreduce_sum(self.solver.dev_VolumeIntegral())
+
+    def boundary_integral(self) -> np.ndarray:
+        """global boundary-flux integral of the LAST step (to be added to TotalBoundaryIntegral)"""
+        return self._allreduce_sum(self.solver.BoundaryIntegral(self.solver.dev_StepBoundaryIntegral()))
+
+    def error_norms(self, uex_local: np.ndarray):
+        """CalculateError.c:26-124: (L1, L2, Linf) of u - uex, relative to the norms of uex when those are not tiny"""
+        import torch.distributed as dist
+        s = self.solver.dev_ErrorSums(uex_local)
+        sums = self._allreduce_sum(s[[0, 1, 3, 4]])
+        t = self.torch.as_tensor(s[[2, 5]], device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        mx = t.cpu().numpy()
+        npts = float(np.prod(self.solver.dim_global))
+        sol = [sums[0] / npts, np.sqrt(sums[1] / npts), mx[0]]
+        err = [sums[2] / npts, np.sqrt(sums[3] / npts), mx[1]]
+        if all(v > 1e-15 for v in sol):
+            err = [e / n for e, n in zip(err, sol)]
+        return err
+
     def step_norm(self) -> float:
         import torch.distributed as dist
         t = self.torch.tensor([self.solver.dev_StepNormSumSq()], device=self.device, dtype=self.torch.float64)

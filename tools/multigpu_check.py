@@ -21,6 +21,60 @@ from hypar_b200.multigpu import DistributedSolver
 from oracle import hpo
 
 
+def diagnostics_and_io(rank, world, local, iproc):
+    """conservation bookkeeping summed over the ranks, error norms, partitioned files -- against a single-rank
+    oracle run of the same (inviscid, decomposition-invariant) case"""
+    import tempfile
+    from hypar_b200 import hypario as H
+    case = cases.ns3d_density_wave((26, 24, 28), "js", iproc=iproc)
+    case.solver["conservation_check"] = "yes"
+    one = cases.ns3d_density_wave((26, 24, 28), "js")
+    S1 = hpo.Setup(one)
+    O1 = hpo.Oracle(S1)
+    dt, rk = float(case.solver["dt"]), hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    d = [tempfile.mkdtemp(prefix="hpb_mg_") if rank == 0 else None]
+    dist.broadcast_object_list(d, src=0)
+    os.chdir(d[0])
+    dg, nv = list(case.solver["size"]), 5
+    if rank == 0:
+        H.write_initial_bin("initial.inp", case.x, case.u0)
+        H.serial_to_parallel("initial.inp", "initial", dg, list(iproc), nv, 2 if world % 2 == 0 else 1)
+    dist.barrier()
+    ds = DistributedSolver(case.solver, case.boundary, case.physics, case.weno, case.x, rank=rank, device=local,
+                           use_fused=False)
+    ds.solver.load_solution_parallel("initial", 2 if world % 2 == 0 else 1)
+    vol0 = ds.volume_integral()
+    u1 = S1.local_u0()
+    vol0_ref = O1.volume_integral(u1)
+    ok = bool(np.all(np.abs(vol0 - vol0_ref) <= 1e-13 * np.abs(vol0_ref).max()))
+    tbi, tbi_ref = np.zeros(nv), np.zeros(nv)
+    for step in range(2):
+        sbi_ref = O1.time_step_cons(u1, dt, rk)
+        tbi_ref += O1.boundary_integral(sbi_ref)
+        ds.time_step()
+        tbi += ds.boundary_integral()
+        ds.solver.write_solution_parallel("op.bin", 1, record=step)
+    vol = ds.volume_integral()
+    err = ds.solver.CalculateConservationError(vol, vol0, tbi)
+    uex = MultiRankOracle(case).local_u0()[rank]
+    norms = ds.error_norms(uex)
+    n0, e0 = O1.norm_sums(S1.local_u0()), O1.norm_sums(S1.local_u0(), u1)
+    npts = float(np.prod(dg))
+    norms_ref = [e0[0] / npts / (n0[0] / npts), np.sqrt(e0[1] / npts) / np.sqrt(n0[1] / npts), e0[2] / n0[2]]
+    ok = ok and bool(np.all(err <= 1e-13)) and all(abs(a - b) <= 1e-10 * abs(b) for a, b in zip(norms, norms_ref))
+    dist.barrier()
+    if rank == 0:
+        xs, us = H.parallel_to_serial("op.bin", dg, list(iproc), nv, 1, record=1)
+        same = np.array_equal(us, S1.interior(u1))          # exact path, inviscid: bit-identical to the single-rank run
+        ok = ok and same
+        print(f"[diagnostics, {world} ranks, iproc {iproc}] conservation error {err.max():.2e}, total boundary integral "
+              f"{np.abs(tbi).max():.2e} (ref {np.abs(tbi_ref).max():.2e}), error norms {['%.6e' % v for v in norms]} "
+              f"(ref {['%.6e' % v for v in norms_ref]}), partitioned output == single-rank solution: {same} "
+              f"{'ok' if ok else 'FAIL'}", flush=True)
+    ds.solver.close()
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -64,6 +118,7 @@ def main():
                       f"rhs err/scale {e_rhs:.2e}, u(2 steps) rel err {e_u:.2e}, max CFL {cfl:.4f} {'ok' if good else 'FAIL'}",
                       flush=True)
                 ds.solver.close()
+    ok = diagnostics_and_io(rank, world, local, iprocs[0]) and ok
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
     dist.destroy_process_group()
