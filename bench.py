@@ -204,6 +204,10 @@ def gpu_arm(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    # one process per GPU: keep the host staging buffers on the GPU's own NUMA node (matters for `e2e` at 4-8 GPUs)
+    from hypar_b200.multigpu import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(local_rank) if not args.no_numa_bind else None
+
     size, iproc = weak_grid(args.n, world)
     s, b, ph, w, x = c4_inputs(size, iproc)
     if world == 1:
@@ -359,7 +363,8 @@ def gpu_arm(args):
                    "points_per_gpu": f"{nloc[0]}x{nloc[1]}x{nloc[2]}", "iproc": iproc, "rk_stages_per_step": NSTAGES,
                    "halo": (None if stepper is None else ("NCCL send/recv on a communication stream, overlapped with the "
                             "Q-derivative kernel and the sweeps" if stepper.overlap else "NCCL send/recv, serial")),
-                   "l2": "working set (5.6 GB per array) >> L2, no flush needed"},
+                   "l2": "working set (5.6 GB per array) >> L2, no flush needed",
+                   "host_numa_bind": (f"{len(numa_cpus)} GPU-local CPUs" if numa_cpus else "none")},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                 "api": "hpb_TimeIntegrate(host u, 1 step)" if stepper is None else "DistributedSolver.time_integrate_host"},
@@ -381,6 +386,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=64, help="grid of the cpu_baseline sample")
     ap.add_argument("--ref-n", type=int, default=64, help="grid of the --impl reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA-local CPUs")
     ap.add_argument("--overlap", action="store_true", help="multi-GPU: halo exchange on a communication stream, overlapped "
                     "with the derivative kernel / sweeps (measured slower than the serial schedule on NVLink 5: DESIGN.md)")
     args = ap.parse_args()

@@ -24,6 +24,32 @@ import numpy as np
 from .solver import FIELD_QDERIVX, FIELD_QDERIVY, FIELD_U, Solver
 
 
+def bind_to_gpu_numa(device: int):
+    """Pin this process to the CPUs NVML reports as local to CUDA device `device` (one process per GPU), so that the
+    pinned host buffers it allocates afterwards are placed on that GPU's NUMA node: with 8 ranks staging 11 GB per step
+    each, buffers that all sit on one socket share its memory controllers and the inter-socket link. Returns the CPU
+    set used, or None when the topology is not visible (containers with a restricted CPU set, no NVML)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device), "pci_domain_id", 0)
+        dev_id = torch.cuda.get_device_properties(device).pci_device_id
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev_id:02x}.0".encode())
+        ncpu = os.cpu_count() or 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i * 64 + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        use = cpus & os.sched_getaffinity(0)
+        if not use or use == os.sched_getaffinity(0):
+            return None
+        os.sched_setaffinity(0, use)
+        return sorted(use)
+    except Exception:
+        return None
+
+
 def exchange_ops(neighbors: Sequence[int], dims: Optional[Sequence[int]] = None):
     """The ordered list of point-to-point operations of one face exchange:
     [("send" | "recv", face index 2*d + side, peer rank)], side 0 = low, 1 = high."""

@@ -1,0 +1,219 @@
+"""Parity at BASELINE.json's FULL sizes -- C3 at 1024^2, C4 at 512^3, C5a/C5b at 512^3 per GPU -- where the oracle cannot
+evaluate the whole grid in seconds (C4/C5: the reference itself cannot run 512^3 at all: 32-bit indices, ~300 GB of
+temporaries). Size-independent properties the domain offers:
+
+  * LOCALITY: rhs at a point depends on u within 4 cells (hyperbolic: 3; viscous: 2 + 2), one RK4 step on u within 16.
+    So the CUDA result of the full grid, restricted to a probe box, must equal the ORACLE run on a sub-box around the
+    probe (grid coordinates sliced from the full grid, frozen `extrapolate` faces -- or the real slip wall where the
+    probe touches it) a few cells inside that sub-box. Exact path: bit-identical; production path: <= 1e-12 / 1e-11.
+  * CONSERVATION: on a periodic grid the hyperbolic term is a flux difference: sum over the interior of hyp dV = 0 to
+    rounding of the sum (relative to sum |hyp| dV).
+  * C3 (1024^2) is small enough for the oracle: compared directly, every point.
+Set HPB_FULLSIZE_N (default 512) to run the 3-D cases at another size.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from hypar_b200 import cases
+from hypar_b200.solver import Solver
+from oracle import hpo
+
+pytestmark = pytest.mark.gpu
+N3 = int(os.environ.get("HPB_FULLSIZE_N", "512"))
+EPS = np.finfo(np.float64).eps
+
+
+def _subbox_oracle(full, u_int, lo, ext, walls=()):
+    """Oracle set up on the sub-box [lo, lo+ext) (x, y, z order) of `full`'s grid. u_int: (nz, ny, nx, nv) interior
+    of the full grid (indices wrap: periodic probes may straddle the domain boundary). walls: (dim, face) pairs of the
+    sub-box that coincide with a physical wall of the full problem (they keep the full problem's zone type)."""
+    nd = 3
+    idx = [np.arange(lo[d], lo[d] + ext[d]) for d in range(nd)]
+    x = []
+    for d in range(nd):
+        xf = np.asarray(full.x[d])
+        n = len(xf)
+        h = xf[1] - xf[0]
+        x.append(np.where((idx[d] >= 0) & (idx[d] < n), xf[np.clip(idx[d], 0, n - 1)], xf[0] + idx[d] * h))
+    u = u_int[np.ix_(idx[2] % u_int.shape[0], idx[1] % u_int.shape[1], idx[0] % u_int.shape[2])]
+    kinds = {(d, f): "extrapolate" for d in range(nd) for f in (1, -1)}
+    for d, f in walls:
+        kinds[(d, f)] = [z for z in full.boundary if z["dim"] == d and z["face"] == f][0]["type"]
+    solver = dict(full.solver)
+    solver.update({"size": [int(e) for e in ext], "iproc": [1, 1, 1]})
+    sub = cases.Case(name="subbox", solver=solver,
+                     boundary=cases._zones(nd, kinds, [-1e30] * nd, [1e30] * nd, wall_velocity=[0.0] * nd),
+                     physics=dict(full.physics), weno=dict(full.weno) if full.weno else None, x=x,
+                     u0=np.ascontiguousarray(u))
+    S = hpo.Setup(sub)
+    return S, hpo.Oracle(S)
+
+
+def _core(a4, lo, ext, margin, origin=(0, 0, 0)):
+    """interior-indexed (nz, ny, nx, nv) array -> the probe core: the sub-box shrunk by `margin`"""
+    sl = tuple(slice(lo[d] - origin[d] + margin, lo[d] - origin[d] + ext[d] - margin) for d in (2, 1, 0))
+    return a4[sl]
+
+
+def _c4_case(n):
+    """configuration C4 of bench.py at n^3: inputs of hypar_b200.cases, field synthesised on the GPU"""
+    import torch
+    import bench
+    size, iproc = bench.weak_grid(n, 1)
+    s, b, ph, w, x = bench.c4_inputs(size, iproc)
+    fld = bench.synth_field_torch(x, torch.device("cuda", 0)).cpu().numpy()
+    torch.cuda.empty_cache()
+    return cases.Case(name=f"c4_{n}", solver=s, boundary=b, physics=ph, weno=w, x=x, u0=fld)
+
+
+def _with_ghosts(sv, u_int):
+    g = sv.ghosts
+    u = np.zeros(sv.shape_g())
+    u[g:-g, g:-g, g:-g] = u_int
+    return u.reshape(-1)
+
+
+def test_c3_1024x1024_every_point_against_the_oracle(need_gpu):
+    case = cases.ns2d_vortex((1024, 1024), "mapped")
+    S = hpo.Setup(case)
+    O = hpo.Oracle(S)
+    u_ref = S.local_u0()
+    rhs_ref, hyp_ref, _, _ = O.rhs(u_ref, parts=True)
+    for fused in (False, True):
+        sv = Solver.from_case(case, use_fused=fused)
+        u = S.local_u0()
+        rhs = sv.RHSFunction(u)
+        if not fused:
+            assert np.array_equal(rhs, rhs_ref), f"exact path: max abs diff {np.abs(rhs - rhs_ref).max():.3e}"
+        else:
+            assert np.abs(rhs - rhs_ref).max() <= 1e-12 * np.abs(rhs_ref).max() + 16 * EPS * np.abs(u_ref).max() * 1024 / 10
+            assert sv.tma_launches > 0, "the TMA-fed sweep did not run"
+        hyp = S.interior(sv.HyperbolicFunction(u))
+        assert abs(hyp.sum(axis=(0, 1))).max() <= 1e-13 * np.abs(hyp).sum(axis=(0, 1)).max(), "hyperbolic term not conservative"
+        sv.close()
+
+
+def test_c4_full_size_probes(need_gpu):
+    n = N3
+    case = _c4_case(n)
+    dt = float(case.solver["dt"])
+    rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    m = 8
+    probes = [((n // 2 - 9, n // 3, n // 5), (34, 30, 32)), ((8, n - 42, n // 2), (32, 34, 30))]
+    # a probe that straddles the periodic boundary in all three directions, for the HYPERBOLIC term only: next to the
+    # domain boundary the reference's viscous term is not translation invariant (QDerivZ is never exchanged and is zero
+    # at x/y ghost points), so only a full-domain oracle could check it there
+    wlo, wext = (-14, n - 17, -15), (30, 32, 30)
+    step_lo, step_ext, step_m = (n // 2 - 28, n // 2 - 26, n // 2 - 30), (56, 54, 58), 20
+
+    def cut(a4, lo, ext, margin):                          # probe core out of a full interior array (indices wrap)
+        idx = [np.arange(lo[d] + margin, lo[d] + ext[d] - margin) % n for d in (2, 1, 0)]
+        return a4[np.ix_(*idx)].copy()
+
+    got = {}
+    for fused in (False, True):
+        sv = Solver.from_case(case, use_fused=fused)
+        u = _with_ghosts(sv, case.u0)
+        rhs = sv.interior(sv.RHSFunction(u))
+        got[fused] = [cut(rhs, lo, ext, m) for lo, ext in probes]
+        del rhs
+        hyp = sv.interior(sv.HyperbolicFunction(u))
+        cons = np.abs(hyp.sum(axis=(0, 1, 2))).max() / np.abs(hyp).sum(axis=(0, 1, 2)).max()
+        assert cons <= 1e-13, f"hyperbolic term not conservative at {n}^3: {cons:.3e}"
+        got[fused].append(cut(hyp, wlo, wext, m))
+        del hyp
+        sv.set_solution(u)
+        del u
+        sv.TimeSteps(1)
+        got[fused].append(cut(sv.interior(sv.get_solution()), step_lo, step_ext, step_m))
+        if fused:
+            assert sv.tma_launches > 0
+        sv.close()
+    for k, (lo, ext) in enumerate(probes):
+        S, O = _subbox_oracle(case, case.u0, lo, ext)
+        r_ref = S.interior(O.rhs(S.local_u0()))
+        core_ref = _core(r_ref, lo, ext, m, origin=lo)
+        scale = np.abs(core_ref).max()
+        for fused in (False, True):
+            g = got[fused][k]
+            if not fused:
+                assert np.array_equal(g, core_ref), f"exact path, probe {lo}: max abs diff {np.abs(g - core_ref).max():.3e}"
+            else:
+                # 1e-12 relative + the rounding floor of the dissipation term alpha u dxinv (16 ulp; dxinv = 81 at 512^3):
+                # tests/test_gpu_parity.py::fused_tolerance, DESIGN.md section 2. Measured at 512^3: 1.5e-13 absolute.
+                us = S.local_u0()
+                tol = 1e-12 * scale + 16 * EPS * (O.cfl(us, dt) / dt) * np.abs(us).max()
+                err = np.abs(g - core_ref).max()
+                assert err <= tol, f"probe {lo}: abs err {err:.3e} > {tol:.3e} (rel {err / scale:.3e})"
+                # (at 512^3 the smooth field makes |rhs| ~ 3e-3 a small difference of O(1) x dxinv terms: the error is
+                # 3-4 ulp of those terms, which is also the uncertainty of the reference's own value)
+                rms = np.sqrt(((g - core_ref) ** 2).mean())
+                assert rms <= 0.25 * tol, f"probe {lo}: rms err {rms:.3e}"
+    S, O = _subbox_oracle(case, case.u0, wlo, wext)
+    h_ref = S.interior(O.rhs(S.local_u0(), parts=True)[1])
+    core_ref = _core(h_ref, wlo, wext, m, origin=wlo)
+    for fused in (False, True):
+        # across the periodic boundary the reference's ghost coordinates are extrapolated, the sub-box's are the true
+        # ones: dxinv may differ in the last bit there -> tolerance also on the exact path
+        us = S.local_u0()
+        tol = 1e-12 * np.abs(h_ref).max() + 16 * EPS * (O.cfl(us, dt) / dt) * np.abs(us).max()
+        e = np.abs(got[fused][len(probes)] - core_ref).max()
+        assert e <= tol, f"hyperbolic term across the periodic boundary, fused={fused}: {e:.3e} > {tol:.3e}"
+    # one RK4 step: dependency radius 4 stages x 4 cells
+    S, O = _subbox_oracle(case, case.u0, step_lo, step_ext)
+    us = S.local_u0()
+    O.time_step(us, dt, rk)
+    core_ref = _core(S.interior(us), step_lo, step_ext, step_m, origin=step_lo)
+    assert np.array_equal(got[False][-1], core_ref), \
+        f"exact path, one RK4 step: max abs diff {np.abs(got[False][-1] - core_ref).max():.3e}"
+    assert np.abs(got[True][-1] - core_ref).max() <= 1e-11 * np.abs(core_ref).max()
+
+
+def test_c5_full_size_probes(need_gpu):
+    n = N3
+    # C5a: density sine wave, periodic, inviscid
+    case = cases.ns3d_density_wave((n, n, n), "mapped")
+    sv = Solver.from_case(case, use_fused=True)
+    u = _with_ghosts(sv, case.u0)
+    rhs = sv.interior(sv.RHSFunction(u)).copy()
+    assert sv.tma_launches > 0
+    cons = np.abs(rhs.sum(axis=(0, 1, 2))).max() / np.abs(rhs).sum(axis=(0, 1, 2)).max()
+    assert cons <= 1e-13, f"C5a: rhs not conservative at {n}^3: {cons:.3e}"
+    lo, ext = (n // 4, n // 2 - 15, n - 40), (30, 30, 30)
+    S, O = _subbox_oracle(case, case.u0, lo, ext)
+    r_ref = S.interior(O.rhs(S.local_u0()))
+    got, ref = _core(rhs, lo, ext, 6), _core(r_ref, lo, ext, 6, origin=lo)
+    us = S.local_u0()
+    dt5 = float(case.solver["dt"])
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(r_ref).max() + 16 * EPS * (O.cfl(us, dt5) / dt5) * np.abs(us).max()
+    sv.close()
+    del rhs, u, case
+
+    # C5b: rising thermal bubble, slip walls, gravity: an interior probe through the bubble and one on the bottom wall
+    case = cases.ns3d_rising_bubble((n, n, n), "yc")
+    dt = float(case.solver["dt"])
+    for fused in (False, True):
+        sv = Solver.from_case(case, use_fused=fused)
+        u = _with_ghosts(sv, case.u0)
+        rhs = sv.interior(sv.RHSFunction(u)).copy()
+        sv.close()
+        del u
+        for lo, ext, walls in (((n // 2 - 15, int(0.26 * n) - 15, n // 2 - 15), (30, 30, 30), ()),
+                               ((n // 3, 0, n // 2), (28, 24, 26), ((1, 1),))):
+            S, O = _subbox_oracle(case, case.u0, lo, ext, walls)
+            us = S.local_u0()
+            r_ref, h_ref, _, s_ref = O.rhs(us, parts=True)
+            m = 8
+            sl_full = tuple(slice(lo[d] + (0 if (d, 1) in walls else m), lo[d] + ext[d] - m) for d in (2, 1, 0))
+            sl_sub = tuple(slice((0 if (d, 1) in walls else m), ext[d] - m) for d in (2, 1, 0))
+            got, ref = rhs[sl_full], S.interior(r_ref)[sl_sub]
+            if not fused:
+                assert np.array_equal(got, ref), f"C5b exact path, probe {lo}: max abs diff {np.abs(got - ref).max():.3e}"
+            else:
+                # hydrostatic balance: |rhs| << |terms|; tolerance of tests/test_gpu_parity.py::fused_tolerance
+                scale = max(np.abs(h_ref).max(), np.abs(s_ref).max())
+                tol = 1e-12 * scale + 16 * EPS * (O.cfl(us, dt) / dt) * np.abs(us).max()
+                assert np.abs(got - ref).max() <= tol, f"C5b probe {lo}: {np.abs(got - ref).max():.3e} > {tol:.3e}"
+        del rhs
