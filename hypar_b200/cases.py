@@ -58,19 +58,23 @@ class Case:
 
 def _solver(ndims, nvars, size, model, *, iproc=None, ts="rk", tstype="44", dt=1e-3,
             interp="components", par_type="nonconservative-1stage", par_scheme="2",
-            n_iter=1) -> Dict[str, object]:
+            n_iter=1, scheme="weno5") -> Dict[str, object]:
     return {
         "ndims": ndims, "nvars": nvars, "size": list(size),
         "iproc": list(iproc) if iproc is not None else [1] * ndims,
         "ghost": 3, "n_iter": n_iter, "restart_iter": 0,
         "time_scheme": ts, "time_scheme_type": tstype,
-        "hyp_space_scheme": "weno5", "hyp_flux_split": "no", "hyp_interp_type": interp,
+        "hyp_space_scheme": scheme, "hyp_flux_split": "no", "hyp_interp_type": interp,
         "par_space_type": par_type, "par_space_scheme": par_scheme,
         "dt": float(dt), "conservation_check": "no",
         "screen_op_iter": 1, "file_op_iter": 1000000,
         "ip_file_type": "binary", "input_mode": "serial", "output_mode": "serial",
         "op_file_format": "binary", "op_overwrite": "yes", "model": model,
     }
+
+
+def _sfx(scheme: str) -> str:
+    return "" if scheme == "weno5" else "_" + scheme
 
 
 def weno_inp(kind: str = "js", eps: float = 1e-6, no_limiting: int = 0) -> Dict[str, object]:
@@ -99,22 +103,22 @@ def _zones(ndims, kind_per_face, lo, hi, wall_velocity=None):
 
 # ------------------------------------------------------------------------------------- C1
 def linear_advection_sine(n: int = 1024, weno: str = "js", dt: float = 5e-4,
-                          diffusion: float = 0.0, par_scheme: str = "2") -> Case:
+                          diffusion: float = 0.0, par_scheme: str = "2", scheme: str = "weno5") -> Case:
     x = np.arange(n, dtype=np.float64) / n
     u = np.sin(2.0 * np.pi * x).reshape(n, 1)
     phys: Dict[str, object] = {"advection": 1.0}
     if diffusion != 0.0:
         phys["diffusion"] = float(diffusion)
     return Case(
-        name=f"c1_linadv_{n}_{weno}",
-        solver=_solver(1, 1, [n], "linear-advection-diffusion-reaction", dt=dt, par_scheme=par_scheme),
+        name=f"c1_linadv_{n}_{weno}" + _sfx(scheme),
+        solver=_solver(1, 1, [n], "linear-advection-diffusion-reaction", dt=dt, par_scheme=par_scheme, scheme=scheme),
         boundary=_zones(1, "periodic", [-1e3], [1e3]),
         physics=phys, weno=weno_inp(weno), x=[x], u0=u)
 
 
 # ------------------------------------------------------------------------------------- C2
 def euler1d_sod(n: int = 201, weno: str = "js", interp: str = "characteristic",
-                upwinding: str = "roe", tstype: str = "ssprk3") -> Case:
+                upwinding: str = "roe", tstype: str = "ssprk3", scheme: str = "weno5") -> Case:
     x = np.arange(n, dtype=np.float64) / (n - 1)
     gamma = 1.4
     rho = np.where(x < 0.5, 1.0, 0.125)
@@ -122,16 +126,16 @@ def euler1d_sod(n: int = 201, weno: str = "js", interp: str = "characteristic",
     v = np.zeros_like(x)
     u = np.stack([rho, rho * v, p / (gamma - 1.0) + 0.5 * rho * v * v], axis=-1)
     return Case(
-        name=f"c2_sod_{n}_{weno}_{interp}_{upwinding}",
+        name=f"c2_sod_{n}_{weno}_{interp}_{upwinding}" + _sfx(scheme),
         solver=_solver(1, 3, [n], "euler1d", ts="rk", tstype=tstype, dt=2.5e-3 * (201.0 / n),
-                       interp=interp),
+                       interp=interp, scheme=scheme),
         boundary=_zones(1, "extrapolate", [-1e3], [1e3]),
         physics={"gamma": gamma, "upwinding": upwinding}, weno=weno_inp(weno), x=[x], u0=u)
 
 
 # ------------------------------------------------------------------------------------- C3
 def ns2d_vortex(n: Sequence[int] = (1024, 1024), weno: str = "js", tstype: str = "ssprk3",
-                iproc=None) -> Case:
+                iproc=None, scheme: str = "weno5") -> Case:
     nx, ny = n
     L = 10.0
     x = np.arange(nx, dtype=np.float64) * (L / nx)
@@ -147,9 +151,9 @@ def ns2d_vortex(n: Sequence[int] = (1024, 1024), weno: str = "js", tstype: str =
     p = rho ** gamma
     u = np.stack([rho, rho * vx, rho * vy, p / (gamma - 1.0) + 0.5 * rho * (vx * vx + vy * vy)], axis=-1)
     return Case(
-        name=f"c3_vortex_{nx}x{ny}_{weno}",
+        name=f"c3_vortex_{nx}x{ny}_{weno}" + _sfx(scheme),
         solver=_solver(2, 4, [nx, ny], "navierstokes2d", ts="rk", tstype=tstype, dt=0.005 * 1024.0 / max(nx, ny),
-                       iproc=iproc),
+                       iproc=iproc, scheme=scheme),
         boundary=_zones(2, "periodic", [-1e3, -1e3], [1e3, 1e3]),
         physics={"gamma": gamma, "upwinding": "rusanov"}, weno=weno_inp(weno), x=[x, y], u0=u)
 
@@ -163,7 +167,8 @@ def _grid3(n, L):
 
 def ns3d_turbulence(n: Sequence[int] = (512, 512, 512), weno: str = "mapped", viscous: bool = True,
                     upwinding: str = "rusanov", tstype: str = "44", dt: float = 0.005,
-                    iproc=None, seed: int = 20261017, interp: str = "components") -> Case:
+                    iproc=None, seed: int = 20261017, interp: str = "components",
+                    scheme: str = "weno5") -> Case:
     """Taylor-Green vortex plus 16 solenoidal Fourier modes |k|<=4 (deterministic phases),
     rho = 1, p = 1/gamma, Minf = 0.3: smooth, fully 3-D, every term of the RHS active."""
     gamma, Minf = 1.4, 0.3
@@ -195,16 +200,16 @@ def ns3d_turbulence(n: Sequence[int] = (512, 512, 512), weno: str = "mapped", vi
     phys["Re"] = 333.333333333333333 if viscous else -1.0
     return Case(
         name=f"c4_turb_{n[0]}x{n[1]}x{n[2]}_{weno}_{'visc' if viscous else 'inv'}"
-             + ("" if upwinding == "rusanov" else "_" + upwinding) + ("" if interp == "components" else "_char"),
+             + ("" if upwinding == "rusanov" else "_" + upwinding) + ("" if interp == "components" else "_char") + _sfx(scheme),
         solver=_solver(3, 5, n, "navierstokes3d", ts="rk", tstype=tstype, dt=dt, iproc=iproc, interp=interp,
-                       par_type="nonconservative-2stage", par_scheme="4"),
+                       par_type="nonconservative-2stage", par_scheme="4", scheme=scheme),
         boundary=_zones(3, "periodic", [-1e3] * 3, [1e3] * 3),
         physics=phys, weno=weno_inp(weno), x=xs, u0=u)
 
 
 # ------------------------------------------------------------------------------------- C5a
 def ns3d_density_wave(n: Sequence[int] = (64, 64, 64), weno: str = "js", tstype: str = "44",
-                      dt: float = 1e-3, iproc=None) -> Case:
+                      dt: float = 1e-3, iproc=None, scheme: str = "weno5") -> Case:
     gamma = 1.4
     xs, X, Y, Z = _grid3(n, [1.0] * 3)
     rho = 1.0 + 0.1 * np.sin(2 * np.pi * X) * np.sin(2 * np.pi * Y) * np.sin(2 * np.pi * Z)
@@ -212,16 +217,16 @@ def ns3d_density_wave(n: Sequence[int] = (64, 64, 64), weno: str = "js", tstype:
     p = np.full_like(rho, 1.0 / gamma)
     u = np.stack([rho, rho * v, rho * v, rho * v, p / (gamma - 1.0) + 0.5 * rho * 3.0 * v * v], axis=-1)
     return Case(
-        name=f"c5a_denswave_{n[0]}x{n[1]}x{n[2]}_{weno}",
+        name=f"c5a_denswave_{n[0]}x{n[1]}x{n[2]}_{weno}" + _sfx(scheme),
         solver=_solver(3, 5, n, "navierstokes3d", ts="rk", tstype=tstype, dt=dt, iproc=iproc,
-                       par_type="nonconservative-2stage", par_scheme="4"),
+                       par_type="nonconservative-2stage", par_scheme="4", scheme=scheme),
         boundary=_zones(3, "periodic", [-1e3] * 3, [1e3] * 3),
         physics={"gamma": gamma, "upwinding": "rusanov"}, weno=weno_inp(weno), x=xs, u0=u)
 
 
 # ------------------------------------------------------------------------------------- C5b
 def ns3d_rising_bubble(n: Sequence[int] = (64, 64, 64), weno: str = "yc", tstype: str = "ssprk3",
-                       dt: float = 0.01, iproc=None, hb: int = 2) -> Case:
+                       dt: float = 0.01, iproc=None, hb: int = 2, scheme: str = "weno5") -> Case:
     """Rising thermal bubble: slip walls, gravity (0, 9.8, 0), HB = 2 hydrostatic balance."""
     gamma, R, g = 1.4, 287.058, 9.8
     rho_ref, p_ref = 1.1612055171196529, 100000.0
@@ -241,9 +246,9 @@ def ns3d_rising_bubble(n: Sequence[int] = (64, 64, 64), weno: str = "yc", tstype
     zero = np.zeros_like(rho)
     u = np.stack([rho, zero, zero, zero, E], axis=-1)
     return Case(
-        name=f"c5b_bubble_{n[0]}x{n[1]}x{n[2]}_{weno}",
+        name=f"c5b_bubble_{n[0]}x{n[1]}x{n[2]}_{weno}" + _sfx(scheme),
         solver=_solver(3, 5, n, "navierstokes3d", ts="rk", tstype=tstype, dt=dt, iproc=iproc,
-                       par_type="nonconservative-2stage", par_scheme="4"),
+                       par_type="nonconservative-2stage", par_scheme="4", scheme=scheme),
         boundary=_zones(3, "slip-wall", [0.0] * 3, [L] * 3, wall_velocity=[0.0, 0.0, 0.0]),
         physics={"gamma": gamma, "upwinding": "rusanov", "gravity": [0.0, g, 0.0],
                  "rho_ref": rho_ref, "p_ref": p_ref, "R": R, "HB": hb},

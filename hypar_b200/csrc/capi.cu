@@ -49,6 +49,7 @@ extern "C" void hpb_config_defaults(hpb_config* c)
   c->device = -1;
   c->use_fused = 1;
   c->conservation_check = 0;
+  c->hyp_scheme = HPB_SCHEME_WENO5;
 }
 
 // ------------------------------------------------------------------------------------ helpers
@@ -99,6 +100,8 @@ static int sync_check(hpb_solver* h, const char* what)
   cudaError_t e = cudaStreamSynchronize(h->stream);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return hpb_fail(HPB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  if (h->d_err && hpbk::tridiag_error(h))      // tridiagLU.c returns -1 on a zero pivot
+    return hpb_fail(HPB_ERR_INVALID, "%s: singular tridiagonal system in a compact-scheme solve", what);
   return HPB_OK;
 }
 
@@ -127,10 +130,31 @@ static bool viscous_on(const hpb_solver* h)
 static bool fused_path(const hpb_solver* h) { return hpbk::fused_available(h); }
 static bool fused_visc(const hpb_solver* h) { return fused_path(h) && h->cfg.model == HPB_MODEL_NS3D && viscous_on(h); }
 
+// scratch of the piecewise path (schemes other than WENO5) and of the compact schemes' tridiagonal systems
+static long long woff(const hpb_solver* h, int dir);
+static int ensure_pieces(hpb_solver* h)
+{
+  if (h->cfg.hyp_scheme == HPB_SCHEME_WENO5) return HPB_OK;
+  const long long n = ncell(h);
+  TRY(dalloc(&h->d_fI, nif_max(h) * h->geo.nvars));
+  for (int k = 0; k < 2; k++) TRY(dalloc(&h->d_cell[k], n));
+  for (int k = 0; k < 5; k++) TRY(dalloc(&h->d_iface[k], nif_max(h) * h->geo.nvars));
+  TRY(dalloc(&h->d_w, woff(h, h->geo.ndims)));
+  if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h->cfg.hyp_scheme == HPB_SCHEME_CUPW5) {
+    for (int k = 0; k < 3; k++) TRY(dalloc(&h->d_tri[k], nif_max(h) * h->geo.nvars));
+    if (!h->d_err) {
+      HPB_CUDA(cudaMalloc((void**)&h->d_err, sizeof(int)));
+      HPB_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+    }
+  }
+  return HPB_OK;
+}
+
 // buffers of the exact (generic) kernels; allocated on first use so that a production run does not carry them
 static int ensure_generic(hpb_solver* h)
 {
   const long long n = ncell(h);
+  TRY(ensure_pieces(h));
   TRY(dalloc(&h->d_fI, nif_max(h) * h->geo.nvars));
   if (h->phys.has_grav) { TRY(dalloc(&h->d_sI, nif_max(h) * 2)); TRY(dalloc(&h->d_src, n)); }
   if (viscous_on(h)) {
@@ -237,6 +261,9 @@ extern "C" int hpb_destroy(hpb_solver* h)
   for (int i = 0; i < 4; i++) { if (h->d_Udot[i]) cudaFree(h->d_Udot[i]); if (h->d_tmp[i]) cudaFree(h->d_tmp[i]); }
   for (int i = 0; i < 3; i++) if (h->d_QD[i]) cudaFree(h->d_QD[i]);
   for (int i = 0; i < 5; i++) if (h->d_iface[i]) cudaFree(h->d_iface[i]);
+  for (int i = 0; i < 2; i++) if (h->d_cell[i]) cudaFree(h->d_cell[i]);
+  for (int i = 0; i < 3; i++) if (h->d_tri[i]) cudaFree(h->d_tri[i]);
+  if (h->d_err) cudaFree(h->d_err);
   for (int f = 0; f < 3; f++) for (int k = 0; k < 6; k++) {
     if (h->d_send[f][k]) cudaFree(h->d_send[f][k]);
     if (h->d_recv[f][k]) cudaFree(h->d_recv[f][k]);
@@ -476,7 +503,7 @@ extern "C" int hpb_UFunction(hpb_solver* h, double* uC, const double* u, int dir
   return download(h, h->d_tmp[1], uC, h->geo.npg, h->geo.nvars);
 }
 
-static long long woff(const hpb_solver* h, int dir)
+static long long woff(const hpb_solver* h, int dir)     // declared above ensure_pieces
 {
   long long o = 0;
   for (int d = 0; d < dir; d++) o += 12 * nif(h, d) * h->geo.nvars;
@@ -487,6 +514,8 @@ extern "C" int hpb_SetInterpLimiterVar(hpb_solver* h, const double* fC, const do
 {
   TRY(need_device(h)); TRY(tmp(h, 0)); TRY(tmp(h, 1));
   if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "SetInterpLimiterVar: dir %d", dir);
+  if (h->cfg.hyp_scheme == HPB_SCHEME_CUPW5 || h->cfg.hyp_scheme == HPB_SCHEME_UPW5)
+    return HPB_OK;             // linear schemes: the reference leaves the pointer NULL (InitializeSolvers.c:194)
   TRY(dalloc(&h->d_w, woff(h, h->geo.ndims)));
   TRY(upload(h, fC, h->d_tmp[0], h->geo.npg, h->geo.nvars));
   TRY(upload(h, u, h->d_tmp[1], h->geo.npg, h->geo.nvars));
@@ -513,18 +542,26 @@ extern "C" int hpb_InterpolateInterfacesHyp(hpb_solver* h, double* fI, const dou
   if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "InterpolateInterfacesHyp: dir %d", dir);
   TRY(dalloc(&h->d_w, woff(h, h->geo.ndims)));
   if (!h->w_valid) {
-    // WENOInitialize.c:170-178: weights start at their optimal values
+    // WENOInitialize.c:170-178: weights start at their optimal values (WENOFifthOrderInitializeWeights.c:33-140:
+    // CRWENO5 (0.2,0.5,0.3) except on the two physical-boundary interfaces of every line)
     std::vector<double> w((size_t)woff(h, h->geo.ndims));
     for (int d = 0; d < h->geo.ndims; d++) {
-      const long long n = nif(h, d) * h->geo.nvars;
+      const long long nq = nif(h, d), n = nq * h->geo.nvars;
+      const Geom& G = h->geo;
+      const long long M0 = G.N[0] + (d == 0), M1 = G.N[1] + (d == 1);
       for (int b = 0; b < 4; b++) for (long long i = 0; i < n; i++) {
-        w[(size_t)(woff(h, d) + (3*b+0)*n + i)] = 0.1; w[(size_t)(woff(h, d) + (3*b+1)*n + i)] = 0.6; w[(size_t)(woff(h, d) + (3*b+2)*n + i)] = 0.3;
+        const long long q = i % nq;
+        const long long iI = (d == 0 ? q % M0 : d == 1 ? (q / M0) % M1 : q / (M0 * M1));
+        const bool cr = (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5) && iI != 0 && iI != G.N[d];
+        w[(size_t)(woff(h, d) + (3*b+0)*n + i)] = cr ? 0.2 : 0.1; w[(size_t)(woff(h, d) + (3*b+1)*n + i)] = cr ? 0.5 : 0.6;
+        w[(size_t)(woff(h, d) + (3*b+2)*n + i)] = 0.3;
       }
     }
     HPB_CUDA(cudaMemcpy(h->d_w, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
     h->w_valid = true;
   }
   TRY(dalloc(&h->d_iface[0], nif_max(h) * h->geo.nvars));
+  TRY(ensure_pieces(h));
   TRY(upload(h, fC, h->d_tmp[0], h->geo.npg, h->geo.nvars));
   TRY(upload(h, u, h->d_tmp[1], h->geo.npg, h->geo.nvars));
   hpbk::weno_interp(h, h->d_iface[0], h->d_tmp[0], h->d_tmp[1], h->d_w + woff(h, dir), upw, dir, uflag);

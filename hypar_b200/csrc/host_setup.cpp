@@ -74,6 +74,15 @@ int hpb_setup_host(hpb_solver* h)
     return hpb_fail(HPB_ERR_INVALID, "rusanov upwinding is needed for flows with gravitational forces");
   if (c.model == HPB_MODEL_LINEAR_ADR && c.par_scheme != 2 && c.par_scheme != 4)
     return hpb_fail(HPB_ERR_INVALID, "par_space_scheme %d not supported (2, 4)", c.par_scheme);
+  if (c.hyp_scheme < HPB_SCHEME_WENO5 || c.hyp_scheme > HPB_SCHEME_UPW5)
+    return hpb_fail(HPB_ERR_INVALID, "hyp_space_scheme %d not supported (weno5, crweno5, cupw5, upw5)", c.hyp_scheme);
+  if (c.hyp_scheme != HPB_SCHEME_WENO5 && c.interp_char && c.nvars > 1)
+    return hpb_fail(HPB_ERR_INVALID, "characteristic reconstruction is implemented for weno5 only "
+                    "(the compact schemes would need the block-tridiagonal solver, blocktridiagLU.c)");
+  if (c.hyp_scheme == HPB_SCHEME_CRWENO5 || c.hyp_scheme == HPB_SCHEME_CUPW5)
+    for (int d = 0; d < nd; d++)
+      if (c.iproc[d] != 1)     // tridiagLU.c stages 2-3: reduced system across ranks, iterative by default
+        return hpb_fail(HPB_ERR_INVALID, "compact schemes (crweno5, cupw5) need iproc = 1 along every dimension");
   if (c.nzones > HPB_MAX_ZONES) return hpb_fail(HPB_ERR_INVALID, "too many boundary zones");
   int nranks = 1;
   for (int d = 0; d < nd; d++) {
@@ -190,6 +199,7 @@ int hpb_setup_host(hpb_solver* h)
   P.model = c.model; P.weno = c.weno_type; P.no_limiting = c.no_limiting;
   P.interp_char = (c.interp_char && c.nvars > 1) ? 1 : 0;        // WENOInitialize.c:156
   P.upwind = c.upwind; P.par_scheme = c.par_scheme; P.has_grav = has_grav ? 1 : 0;
+  P.scheme = c.hyp_scheme;
   P.eps = c.weno_eps; P.gamma = c.gamma;
   P.Re = c.Re / c.Minf;                                          // NavierStokes3DInitialize.c:368
   P.Pr = c.Pr;

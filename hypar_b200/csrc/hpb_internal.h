@@ -25,6 +25,7 @@ struct Geom {
 
 struct Phys {
   int model, weno, no_limiting, interp_char, upwind, par_scheme, has_grav;
+  int scheme;                        // HPB_SCHEME_*
   double eps, gamma, Re, Pr, RT;     // Re already / Minf ; RT = p0/rho0
   double grav[3];
   double adv[15], diff[15];
@@ -73,6 +74,12 @@ struct hpb_solver {
   double *d_tmp[4] = {nullptr, nullptr, nullptr, nullptr};   // scratch cell arrays for the fine-grained API
   double *d_w = nullptr;           // stored WENO weights of the fine-grained API (all dirs)
   double *d_iface[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // interface scratch (fine-grained API)
+  // piecewise path of the schemes other than WENO5 (crweno5, cupw5, upw5): cell scratch (flux / source function,
+  // modified solution), tridiagonal rows (sub-diagonal, diagonal, super-diagonal; the right-hand side is solved in
+  // place in the output interface array), pivot-error flag
+  double *d_cell[2] = {nullptr, nullptr};
+  double *d_tri[3] = {nullptr, nullptr, nullptr};
+  int *d_err = nullptr;
   double *d_red = nullptr;         // reduction scratch
   // conservation diagnostics (cfg.conservation_check): boundary-flux bookkeeping of HyperbolicFunction.c:103-106 /
   // TimeRK.c:172-193. d_cons = [slot][2*ndims*nvars]: slots 0..3 = BoundaryFlux[stage], 4 = StageBoundaryIntegral of
@@ -123,6 +130,9 @@ void unpack(hpb_solver* h, double* a, int nv, int field, int only_dim = -1);
 // with_source: gravity-source contribution of each gravity direction is ADDED to src (quirk Q5).
 void hyperbolic(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src);
 void hyperbolic_generic(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src);
+// schemes other than WENO5: the reference's own sequence of pieces (HyperbolicFunction.c:167-222) with stored weights
+void hyperbolic_pieces(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src);
+int  tridiag_error(hpb_solver* h);      // 1 if a tridiagonal solve met a zero pivot since the last call (synchronises)
 // fused sweeps (sweep_fused.cu); qd != nullptr: the NavierStokes3D viscous terms are evaluated inside the sweeps
 bool fused_available(const hpb_solver* h);
 bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src,

@@ -721,6 +721,13 @@ __global__ void k_weights(Geom G, Phys ph, const double* __restrict__ fC, const 
   const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
   if (i0 >= M0) return;
+  // optimal weights: WENO5 (0.1,0.6,0.3); CRWENO5 (0.2,0.5,0.3) except on the two physical-boundary interfaces
+  // (WENOFifthOrderCalculateWeights.c:205-225; compact schemes run with iproc = 1, so these are interfaces 0 and N)
+  double c1 = 0.1, c2 = 0.6, c3 = 0.3;
+  {
+    const int iI = (dir == 0 ? i0 : dir == 1 ? i1 : i2);
+    if (ph.scheme == HPB_SCHEME_CRWENO5 && iI != 0 && iI != G.N[dir]) { c1 = 0.2; c2 = 0.5; c3 = 0.3; }
+  }
   const long long q = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
   const long long ni = (long long)M0 * M1 * M2;
   const long long st = G.st[dir];
@@ -753,12 +760,12 @@ __global__ void k_weights(Geom G, Phys ph, const double* __restrict__ fC, const 
     }
     double ws[4][3];
     if (ph.no_limiting) {
-      for (int b = 0; b < 4; b++) { ws[b][0] = 0.1; ws[b][1] = 0.6; ws[b][2] = 0.3; }
+      for (int b = 0; b < 4; b++) { ws[b][0] = c1; ws[b][1] = c2; ws[b][2] = c3; }
     } else {
-      weno_weights_ref(ph.weno, ph.eps, cF[0], cF[1], cF[2], cF[3], cF[4], ws[0][0], ws[0][1], ws[0][2]);
-      weno_weights_ref(ph.weno, ph.eps, cU[0], cU[1], cU[2], cU[3], cU[4], ws[1][0], ws[1][1], ws[1][2]);
-      weno_weights_ref(ph.weno, ph.eps, cF[5], cF[4], cF[3], cF[2], cF[1], ws[2][0], ws[2][1], ws[2][2]);
-      weno_weights_ref(ph.weno, ph.eps, cU[5], cU[4], cU[3], cU[2], cU[1], ws[3][0], ws[3][1], ws[3][2]);
+      weno_weights_ref_c(ph.weno, ph.eps, c1, c2, c3, cF[0], cF[1], cF[2], cF[3], cF[4], ws[0][0], ws[0][1], ws[0][2]);
+      weno_weights_ref_c(ph.weno, ph.eps, c1, c2, c3, cU[0], cU[1], cU[2], cU[3], cU[4], ws[1][0], ws[1][1], ws[1][2]);
+      weno_weights_ref_c(ph.weno, ph.eps, c1, c2, c3, cF[5], cF[4], cF[3], cF[2], cF[1], ws[2][0], ws[2][1], ws[2][2]);
+      weno_weights_ref_c(ph.weno, ph.eps, c1, c2, c3, cU[5], cU[4], cU[3], cU[2], cU[1], ws[3][0], ws[3][1], ws[3][2]);
     }
     for (int b = 0; b < 4; b++)
       for (int k = 0; k < 3; k++) w[((3 * b + k) * NV + v) * ni + q] = ws[b][k];
@@ -826,6 +833,168 @@ __global__ void k_interp(Geom G, Phys ph, const double* __restrict__ fC, const d
   }
 #pragma unroll
   for (int v = 0; v < NV; v++) fI[v * ni + q] = out[v];
+}
+
+// ------------------------------------------------------------------------------------------
+// Compact schemes, component-wise, one rank along the line:
+// Interp1PrimFifthOrderCRWENO.c:80-237, Interp1PrimFifthOrderCompactUpwind.c:73-228. One tridiagonal system per
+// grid line and component; rows of the two physical-boundary interfaces are the explicit WENO5 / fifth-order
+// upwind value (a = c = 0, b = 1). Row arrays share the interface layout [v*ni + q]; r is solved in place.
+__global__ void k_compact_rows(Geom G, Phys ph, const double* __restrict__ fC, const double* __restrict__ w, int upw,
+                               int dir, int uflag, double* __restrict__ A, double* __restrict__ B,
+                               double* __restrict__ Cc, double* __restrict__ R)
+{
+  const double one_third = 1.0 / 3.0, one_sixth = 1.0 / 6.0;
+  const double thirteen_by_sixty = 13.0 / 60.0, fortyseven_by_sixty = 47.0 / 60.0, twentyseven_by_sixty = 27.0 / 60.0,
+               one_by_twenty = 1.0 / 20.0, one_by_thirty = 1.0 / 30.0, nineteen_by_thirty = 19.0 / 30.0,
+               three_by_ten = 3.0 / 10.0, six_by_ten = 6.0 / 10.0, one_by_ten = 1.0 / 10.0;
+  const int NV = G.nvars;
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= M0) return;
+  const long long q = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
+  const long long ni = (long long)M0 * M1 * M2;
+  const long long st = G.st[dir];
+  const long long pm1 = cell_index(G, i0, i1, i2) - st;
+  const int blk = (upw < 0 ? 2 : 0) + (uflag ? 1 : 0);
+  const int iI = (dir == 0 ? i0 : dir == 1 ? i1 : i2);
+  const bool bnd = (iI == 0) || (iI == G.N[dir]);
+  long long ps[5];
+  for (int k = 0; k < 5; k++) ps[k] = (upw > 0) ? pm1 + (k - 2) * st : pm1 + (3 - k) * st;
+  for (int v = 0; v < NV; v++) {
+    const double fm3 = fC[v * G.npg + ps[0]], fm2 = fC[v * G.npg + ps[1]], fm1 = fC[v * G.npg + ps[2]],
+                 fp1 = fC[v * G.npg + ps[3]], fp2 = fC[v * G.npg + ps[4]];
+    double a, b, c, r;
+    if (ph.scheme == HPB_SCHEME_CRWENO5) {
+      const double w1 = w[((3 * blk + 0) * NV + v) * ni + q], w2 = w[((3 * blk + 1) * NV + v) * ni + q],
+                   w3 = w[((3 * blk + 2) * NV + v) * ni + q];
+      double f1, f2, f3;
+      if (bnd) {
+        f1 = (2 * one_sixth) * fm3 + (-7 * one_sixth) * fm2 + (11 * one_sixth) * fm1;
+        f2 = (-one_sixth) * fm2 + (5 * one_sixth) * fm1 + (2 * one_sixth) * fp1;
+        f3 = (2 * one_sixth) * fm1 + (5 * one_sixth) * fp1 + (-one_sixth) * fp2;
+        a = 0.0; b = 1.0; c = 0.0;
+      } else {
+        f1 = (one_sixth) * fm2 + (5 * one_sixth) * fm1;
+        f2 = (5 * one_sixth) * fm1 + (one_sixth) * fp1;
+        f3 = (one_sixth) * fm1 + (5 * one_sixth) * fp1;
+        const double lo = (2 * one_third) * w1 + (one_third) * w2;
+        const double di = (one_third) * w1 + (2 * one_third) * w2 + (2 * one_third) * w3;
+        const double hi = (one_third) * w3;
+        if (upw > 0) { a = lo; b = di; c = hi; } else { c = lo; b = di; a = hi; }
+      }
+      r = w1 * f1 + w2 * f2 + w3 * f3;
+    } else {
+      if (bnd) {
+        a = 0.0; b = 1.0; c = 0.0;
+        r = one_by_thirty * fm3 - thirteen_by_sixty * fm2 + fortyseven_by_sixty * fm1 + twentyseven_by_sixty * fp1
+          - one_by_twenty * fp2;
+      } else {
+        if (upw > 0) { a = three_by_ten; b = six_by_ten; c = one_by_ten; }
+        else         { c = three_by_ten; b = six_by_ten; a = one_by_ten; }
+        r = one_by_thirty * fm2 + nineteen_by_thirty * fm1 + one_third * fp1;
+      }
+    }
+    A[v * ni + q] = a; B[v * ni + q] = b; Cc[v * ni + q] = c; R[v * ni + q] = r;
+  }
+}
+
+// TridiagLU/tridiagLU.c:84-274 on one rank (stage 1 forward elimination, stage 4 back substitution; stages 2-3 are
+// empty): one thread per system = (grid line, component), the line walked sequentially in the reference's operation
+// order, so the solution carries the reference's bits. Threads of a warp own neighbouring lines (unit stride for the
+// y/z sweeps). The `a*x[0]` products of stage 4 -- the reduced-system coupling of the multi-rank algorithm, zero on
+// one rank -- are kept so that signed zeros come out as in the reference. err: set when a pivot is zero.
+__global__ void k_tridiag(Geom G, int dir, double* __restrict__ A, double* __restrict__ B, const double* __restrict__ Cc,
+                          double* __restrict__ X, int* __restrict__ err)
+{
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  const long long ni = (long long)M0 * M1 * M2;
+  // the two transverse extents (t0 fastest) and the strides of a line in the interface array
+  int T0, T1; long long s0, s1, qs;
+  if (dir == 0)      { T0 = M1; T1 = M2; s0 = M0;  s1 = (long long)M0 * M1; qs = 1; }
+  else if (dir == 1) { T0 = M0; T1 = M2; s0 = 1;   s1 = (long long)M0 * M1; qs = M0; }
+  else               { T0 = M0; T1 = M1; s0 = 1;   s1 = M0;                 qs = (long long)M0 * M1; }
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y, v = blockIdx.z;
+  if (t0 >= T0 || t1 >= T1) return;
+  const int n = G.N[dir] + 1;
+  double* a = A + v * ni + t0 * s0 + t1 * s1;
+  double* b = B + v * ni + t0 * s0 + t1 * s1;
+  const double* c = Cc + v * ni + t0 * s0 + t1 * s1;
+  double* x = X + v * ni + t0 * s0 + t1 * s1;
+  for (int i = 1; i < n; i++) {
+    const double bm = b[(i - 1) * qs];
+    if (bm == 0) { *err = 1; return; }
+    const double factor = a[i * qs] / bm;
+    b[i * qs] -= factor * c[(i - 1) * qs];
+    a[i * qs] = -factor * a[(i - 1) * qs];
+    x[i * qs] -= factor * x[(i - 1) * qs];
+  }
+  const int il = n - 1;
+  if (b[il * qs] == 0) { *err = 1; return; }
+  x[il * qs] = (x[il * qs] - a[il * qs] * x[0] - c[il * qs] * 0.0) / b[il * qs];
+  for (int i = il - 1; i > -1; i--) {
+    if (b[i * qs] == 0) { *err = 1; return; }
+    x[i * qs] = (x[i * qs] - c[i * qs] * x[(i + 1) * qs] - a[i * qs] * x[0]) / b[i * qs];
+  }
+}
+
+// Interp1PrimFifthOrderUpwind.c:60-147 (component-wise)
+__global__ void k_interp_upw5(Geom G, const double* __restrict__ fC, int upw, int dir, double* __restrict__ fI)
+{
+  const double one_by_thirty = 1.0 / 30.0, thirteen_by_sixty = 13.0 / 60.0, fortyseven_by_sixty = 47.0 / 60.0,
+               twentyseven_by_sixty = 27.0 / 60.0, one_by_twenty = 1.0 / 20.0;
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= M0) return;
+  const long long q = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
+  const long long ni = (long long)M0 * M1 * M2;
+  const long long st = G.st[dir];
+  const long long pm1 = cell_index(G, i0, i1, i2) - st;
+  long long ps[5];
+  for (int k = 0; k < 5; k++) ps[k] = (upw > 0) ? pm1 + (k - 2) * st : pm1 + (3 - k) * st;
+  for (int v = 0; v < G.nvars; v++) {
+    const double* f = fC + v * G.npg;
+    fI[v * ni + q] = one_by_thirty * f[ps[0]] - thirteen_by_sixty * f[ps[1]] + fortyseven_by_sixty * f[ps[2]]
+                   + twentyseven_by_sixty * f[ps[3]] - one_by_twenty * f[ps[4]];
+  }
+}
+
+// NavierStokes3DSource.c:124-160: the source function G = g_grav * (0, d_x, d_y, d_z, 1) as a cell array
+__global__ void k_ns3d_source_fn(Geom G, const double* __restrict__ gg, int dir, double* __restrict__ S)
+{
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= G.npg) return;
+  const double g = gg[p];
+  S[p] = 0.0;
+  S[1 * G.npg + p] = g * (dir == 0);
+  S[2 * G.npg + p] = g * (dir == 1);
+  S[3 * G.npg + p] = g * (dir == 2);
+  S[4 * G.npg + p] = g;
+}
+// NavierStokes3DSource.c:174-205: interface value = average of the left- and right-biased reconstructions;
+// only components dir+1 and 4 are consumed (k_ns3d_source)
+__global__ void k_ns3d_source_avg(long long ni, int dir, const double* __restrict__ SL, const double* __restrict__ SR,
+                                  double* __restrict__ sI)
+{
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= ni) return;
+  sI[q]      = 0.5 * (SL[(1 + dir) * ni + q] + SR[(1 + dir) * ni + q]);
+  sI[ni + q] = 0.5 * (SL[4 * ni + q] + SR[4 * ni + q]);
+}
+// boundary-face fluxes from a stored interface array (conservation bookkeeping of the piecewise path)
+__global__ void k_face_from_iface(Geom G, int dir, int face, const double* __restrict__ fI, double* __restrict__ out)
+{
+  int M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
+  int F[3] = { M[0], M[1], M[2] }; F[dir] = 1;
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= F[0]) return;
+  int j[3] = { i0, i1, i2 };
+  const long long qf = i0 + (long long)F[0] * (i1 + (long long)F[1] * i2);
+  const long long nface = (long long)F[0] * F[1] * F[2];
+  j[dir] = face ? G.N[dir] : 0;
+  const long long q = j[0] + (long long)M[0] * (j[1] + (long long)M[1] * j[2]);
+  const long long ni = (long long)M[0] * M[1] * M[2];
+  for (int v = 0; v < G.nvars; v++) out[v * nface + qf] = fI[v * ni + q];
 }
 
 template <int MODEL>
@@ -966,6 +1135,7 @@ void copy(hpb_solver* h, double* dst, const double* src, long long n)
 
 void hyperbolic_generic(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src)
 {
+  if (h->cfg.hyp_scheme != HPB_SCHEME_WENO5) { hyperbolic_pieces(h, u, out, negate, with_source, src); return; }
   const Geom& G = h->geo;
   const bool grav = h->phys.has_grav;
   const double* gf = (h->cfg.model == HPB_MODEL_LINEAR_ADR) ? nullptr : h->d_gravf;
@@ -985,6 +1155,55 @@ void hyperbolic_generic(hpb_solver* h, const double* u, double* out, bool negate
       LAUNCHED(h);
     }
   }
+}
+
+// HyperbolicFunction.c:81-109 + ReconstructHyperbolic :167-222 as the reference sequences them: flux, weights
+// (SetInterpLimiterVar, WENO-type schemes only), modified solution, four InterpolateInterfacesHyp calls, Upwind,
+// flux difference; then NavierStokes3DSource.c:54-101 for a gravity direction, with the same stored flux weights
+// (quirk Q5) and fluxC / fL / fR as scratch like the reference (:54-57).
+void hyperbolic_pieces(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src)
+{
+  const Geom& G = h->geo;
+  const bool grav = h->phys.has_grav;
+  const bool has_w = (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5);
+  double *fC = h->d_cell[0], *uC = h->d_cell[1];
+  double *fL = h->d_iface[1], *fR = h->d_iface[2], *uL = h->d_iface[3], *uR = h->d_iface[4];
+  long long wo = 0;              // the weights of direction d live where the fine-grained API keeps them (capi.cu: woff)
+  for (int d = 0; d < G.ndims; d++) {
+    const int M[3] = { G.N[0] + (d == 0), G.N[1] + (d == 1), G.N[2] + (d == 2) };
+    const long long ni = (long long)M[0] * M[1] * M[2];
+    double* w = h->d_w + wo;
+    wo += 12 * ni * G.nvars;
+    ProfScope ps(h, HPB_PROF_SWEEP_X + d);
+    flux(h, u, fC, d);
+    if (has_w) { weno_weights(h, fC, u, d, w); h->w_valid = true; }
+    modified_solution(h, u, uC);
+    weno_interp(h, uL, uC, u, w,  1, d, 1);
+    weno_interp(h, uR, uC, u, w, -1, d, 1);
+    weno_interp(h, fL, fC, u, w,  1, d, 0);
+    weno_interp(h, fR, fC, u, w, -1, d, 0);
+    upwind(h, h->d_fI, fL, fR, uL, uR, u, d);
+    const int mode = negate ? (d == 0 ? 0 : 1) : (d == 0 ? 2 : 3);
+    k_divergence<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, h->d_dxinv, h->d_fI, d, out, mode); LAUNCHED(h);
+    if (with_source && grav && h->phys.grav[d] != 0.0) {
+      k_ns3d_source_fn<<<(unsigned)((G.npg + 255) / 256), 256, 0, h->stream>>>(G, h->d_gravg, d, fC); LAUNCHED(h);
+      weno_interp(h, fL, fC, u, w,  1, d, 0);
+      weno_interp(h, fR, fC, u, w, -1, d, 0);
+      k_ns3d_source_avg<<<(unsigned)((ni + 255) / 256), 256, 0, h->stream>>>(ni, d, fL, fR, h->d_sI); LAUNCHED(h);
+      k_ns3d_source<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, h->phys, h->d_dxinv, u, h->d_gravf, h->d_sI, d, src);
+      LAUNCHED(h);
+    }
+  }
+}
+
+int tridiag_error(hpb_solver* h)
+{
+  if (!h->d_err) return 0;
+  int e = 0;
+  cudaMemcpyAsync(&e, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  if (e) cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream);
+  return e;
 }
 
 void parabolic_phase1(hpb_solver* h, const double* u)
@@ -1121,6 +1340,21 @@ void weno_interp(hpb_solver* h, double* fI, const double* fC, const double* u, c
 {
   const Geom& G = h->geo;
   const int M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
+  if (h->cfg.hyp_scheme == HPB_SCHEME_UPW5) {
+    k_interp_upw5<<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, fC, upw, dir, fI); LAUNCHED(h);
+    return;
+  }
+  if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h->cfg.hyp_scheme == HPB_SCHEME_CUPW5) {
+    // rows, then one thread per (line, component) system; the solution replaces the right-hand side in fI
+    k_compact_rows<<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, fC, w, upw, dir, uflag,
+                                                                    h->d_tri[0], h->d_tri[1], h->d_tri[2], fI); LAUNCHED(h);
+    int T0, T1;
+    if (dir == 0) { T0 = M[1]; T1 = M[2]; } else if (dir == 1) { T0 = M[0]; T1 = M[2]; } else { T0 = M[0]; T1 = M[1]; }
+    const int tpb = 64;
+    k_tridiag<<<dim3((T0 + tpb - 1) / tpb, T1, G.nvars), tpb, 0, h->stream>>>(G, dir, h->d_tri[0], h->d_tri[1], h->d_tri[2],
+                                                                              fI, h->d_err); LAUNCHED(h);
+    return;
+  }
 #define CALL(M_) k_interp<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, fC, u, w, upw, dir, uflag, fI)
   MODEL_SWITCH(h->cfg.model, CALL)
 #undef CALL
@@ -1167,6 +1401,27 @@ void boundary_flux(hpb_solver* h, const double* u, int d, double* sbi)
   int M[3] = { G.N[0], G.N[1], G.N[2] };
   M[d] = 1;
   const long long nface = (long long)M[0] * M[1] * M[2];
+  if (h->cfg.hyp_scheme != HPB_SCHEME_WENO5) {
+    // compact / linear schemes: the interface fluxes of direction d are re-evaluated by the piecewise sequence
+    // (a boundary value of a compact scheme depends on the whole line) and the two faces are read from them
+    double *fC = h->d_cell[0], *uC = h->d_cell[1];
+    long long wo = 0;
+    for (int k = 0; k < d; k++) wo += 12LL * (G.N[0] + (k == 0)) * (G.N[1] + (k == 1)) * (G.N[2] + (k == 2)) * G.nvars;
+    double* w = h->d_w + wo;
+    flux(h, u, fC, d);
+    if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5) weno_weights(h, fC, u, d, w);
+    modified_solution(h, u, uC);
+    weno_interp(h, h->d_iface[3], uC, u, w,  1, d, 1);
+    weno_interp(h, h->d_iface[4], uC, u, w, -1, d, 1);
+    weno_interp(h, h->d_iface[1], fC, u, w,  1, d, 0);
+    weno_interp(h, h->d_iface[2], fC, u, w, -1, d, 0);
+    upwind(h, h->d_fI, h->d_iface[1], h->d_iface[2], h->d_iface[3], h->d_iface[4], u, d);
+    for (int f = 0; f < 2; f++) {
+      k_face_from_iface<<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, d, f, h->d_fI, h->d_face); LAUNCHED(h);
+      k_face_sum<<<G.nvars, 1024, 0, h->stream>>>(h->d_face, nface, f ? 1.0 : -1.0, sbi + (2 * d + f) * G.nvars); LAUNCHED(h);
+    }
+    return;
+  }
   for (int f = 0; f < 2; f++) {
 #define CALL(M_) k_iface<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, u, gf, gg, d, h->d_face, nullptr, f)
     MODEL_SWITCH(h->cfg.model, CALL)

@@ -21,11 +21,11 @@ HPB_DEV void weno_betas(double m3, double m2, double m1, double p1, double p2, d
 }
 
 // One scalar weight set in the reference's own form (used by the generic path and the
-// fine-grained API): optimal weights (0.1, 0.6, 0.3), p = 2.
-HPB_DEV void weno_weights_ref(int type, double eps, double m3, double m2, double m1, double p1, double p2,
-                              double& w1, double& w2, double& w3)
+// fine-grained API) for the optimal weights (c1, c2, c3), p = 2.
+HPB_DEV void weno_weights_ref_c(int type, double eps, double c1, double c2, double c3,
+                                double m3, double m2, double m1, double p1, double p2,
+                                double& w1, double& w2, double& w3)
 {
-  const double c1 = 0.1, c2 = 0.6, c3 = 0.3;
   double b1, b2, b3, a1, a2, a3;
   weno_betas(m3, m2, m1, p1, p2, b1, b2, b3);
   if (type == HPB_WENO_JS || type == HPB_WENO_M) {
@@ -50,6 +50,13 @@ HPB_DEV void weno_weights_ref(int type, double eps, double m3, double m2, double
     a_sum_inv = 1.0 / (a1 + a2 + a3);
     w1 = a1 * a_sum_inv; w2 = a2 * a_sum_inv; w3 = a3 * a_sum_inv;
   }
+}
+
+// WENO5: optimal weights (0.1, 0.6, 0.3) (interpolation.h:228-232)
+HPB_DEV void weno_weights_ref(int type, double eps, double m3, double m2, double m1, double p1, double p2,
+                              double& w1, double& w2, double& w3)
+{
+  weno_weights_ref_c(type, eps, 0.1, 0.6, 0.3, m3, m2, m1, p1, p2, w1, w2, w3);
 }
 
 // fifth-order interpolant from the three candidate stencils

@@ -23,6 +23,7 @@ MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2}
 UPWINDS = {"roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 RK_TYPES = {"44": 0, "ssprk3": 1}
+SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3}
 FIELD_U, FIELD_QDERIVX, FIELD_QDERIVY = 0, 1, 2
 
 
@@ -56,8 +57,10 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     if model not in MODELS:
         raise HyParB200Error(f"model '{model}' is not on the B200 path (supported: {sorted(MODELS)})")
     c.model = MODELS[model]
-    if str(solver.get("hyp_space_scheme", "1")) != "weno5":
-        raise HyParB200Error(f"hyp_space_scheme '{solver.get('hyp_space_scheme')}' is not on the B200 path (weno5 only)")
+    scheme = str(solver.get("hyp_space_scheme", "1"))
+    if scheme not in SCHEMES:
+        raise HyParB200Error(f"hyp_space_scheme '{scheme}' is not on the B200 path (weno5, crweno5, cupw5, upw5)")
+    c.hyp_scheme = SCHEMES[scheme]
     if str(solver.get("time_scheme", "euler")) != "rk":
         raise HyParB200Error(f"time_scheme '{solver.get('time_scheme')}' is not on the B200 path (rk only)")
     tst = str(solver.get("time_scheme_type", " "))

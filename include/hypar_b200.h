@@ -62,6 +62,15 @@ extern "C" {
 #define HPB_UPWIND_RF      3    /* "rf-char":  characteristic-based Roe-fixed (Euler1D, NavierStokes3D)          */
 #define HPB_UPWIND_LLF     4    /* "llf-char": characteristic-based local Lax-Friedrichs (Euler1D, NavierStokes3D) */
 
+/* solver.inp `hyp_space_scheme` -- reference src/Simulation/InitializeSolvers.c:232-330. The compact schemes
+   solve one tridiagonal system per grid line and component (Interp1PrimFifthOrderCRWENO.c:80,
+   Interp1PrimFifthOrderCompactUpwind.c:73, TridiagLU/tridiagLU.c:84); component-wise, iproc = 1 along every
+   dimension. Anything but WENO5 runs on the reference-exact kernels. */
+#define HPB_SCHEME_WENO5   0    /* "weno5"   */
+#define HPB_SCHEME_CRWENO5 1    /* "crweno5" */
+#define HPB_SCHEME_CUPW5   2    /* "cupw5": fifth-order compact upwind */
+#define HPB_SCHEME_UPW5    3    /* "upw5":  fifth-order upwind         */
+
 /* boundary.inp zone types implemented on the device (reference: 17 types; the three the
    BASELINE configurations use) */
 #define HPB_BC_PERIODIC    0
@@ -119,6 +128,7 @@ typedef struct hpb_config {
   /* --- solver.inp (cont.) --- */
   int    conservation_check;           /* ConservationCheck "yes": keep the boundary-flux bookkeeping of
                                           HyperbolicFunction.c:103-106 / TimeRK.c:172-193 on the device       */
+  int    hyp_scheme;                   /* hyp_space_scheme: HPB_SCHEME_* (default WENO5)                      */
 } hpb_config;
 
 typedef struct hpb_solver hpb_solver;

@@ -175,9 +175,14 @@ int hyparb200_attach(void *sims, int nsims)
                     "hpb_stage_* calls (INTEGRATION.md section 2)\n");
     return 1;
   }
-  if (strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_WENO_) || strcmp(s->time_scheme, _RK_)
-      || strcmp(s->SplitHyperbolicFlux, "no") || s->flag_ib) {
-    fprintf(stderr, "hyparb200_attach: only weno5 + explicit RK without flux splitting / immersed boundaries is on the B200 path\n");
+  int scheme = -1;
+  if      (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_WENO_))           scheme = HPB_SCHEME_WENO5;
+  else if (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_CRWENO_))         scheme = HPB_SCHEME_CRWENO5;
+  else if (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_COMPACT_UPWIND_)) scheme = HPB_SCHEME_CUPW5;
+  else if (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_UPWIND_))         scheme = HPB_SCHEME_UPW5;
+  if (scheme < 0 || strcmp(s->time_scheme, _RK_) || strcmp(s->SplitHyperbolicFlux, "no") || s->flag_ib) {
+    fprintf(stderr, "hyparb200_attach: only weno5 / crweno5 / cupw5 / upw5 + explicit RK without flux splitting / "
+                    "immersed boundaries is on the B200 path\n");
     return 1;
   }
 
@@ -191,9 +196,12 @@ int hyparb200_attach(void *sims, int nsims)
   else { fprintf(stderr, "hyparb200_attach: rk type %s is not on the B200 path (44, ssprk3)\n", s->time_scheme_type); return 1; }
   c.par_scheme = atoi(s->spatial_scheme_par);
   c.conservation_check = !strcmp(s->ConservationCheck, "yes");
-  WENOParameters *w = (WENOParameters*) s->interp;
-  c.weno_type = w->yc ? HPB_WENO_YC : w->borges ? HPB_WENO_Z : w->mapped ? HPB_WENO_M : HPB_WENO_JS;
-  c.no_limiting = w->no_limiting;  c.weno_eps = w->eps;
+  c.hyp_scheme = scheme;
+  if (scheme == HPB_SCHEME_WENO5 || scheme == HPB_SCHEME_CRWENO5) {   /* s->interp is NULL for the linear schemes */
+    WENOParameters *w = (WENOParameters*) s->interp;
+    c.weno_type = w->yc ? HPB_WENO_YC : w->borges ? HPB_WENO_Z : w->mapped ? HPB_WENO_M : HPB_WENO_JS;
+    c.no_limiting = w->no_limiting;  c.weno_eps = w->eps;
+  }
 
   if (!strcmp(s->model, _NAVIER_STOKES_3D_)) {
     NavierStokes3D *p = (NavierStokes3D*) s->physics;
@@ -269,7 +277,7 @@ int hyparb200_attach(void *sims, int nsims)
   s->FFunction                = B200_FFunction;
   if (s->UFunction) s->UFunction = B200_UFunction;
   s->Upwind                   = B200_Upwind;
-  s->SetInterpLimiterVar      = B200_SetInterpLimiterVar;
+  if (s->SetInterpLimiterVar) s->SetInterpLimiterVar = B200_SetInterpLimiterVar;   /* NULL for the linear schemes */
   s->InterpolateInterfacesHyp = B200_InterpolateInterfacesHyp;
   s->FirstDerivativePar       = B200_FirstDerivativePar;
   s->SecondDerivativePar      = B200_SecondDerivativePar;

@@ -25,6 +25,7 @@ MAXD, MAXV, MAXZ = 3, 5, 16
 MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3}
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2}
 UPWINDS = {"default": 0, "roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
+SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3}
 
 
 class Zone(C.Structure):
@@ -46,7 +47,8 @@ class Ctx(C.Structure):
                 ("adv", C.c_double * (MAXD * MAXV)), ("diff", C.c_double * (MAXD * MAXV)),
                 ("zones", Zone * MAXZ),
                 ("x", C.POINTER(C.c_double)), ("dxinv", C.POINTER(C.c_double)),
-                ("grav_f", C.POINTER(C.c_double)), ("grav_g", C.POINTER(C.c_double))]
+                ("grav_f", C.POINTER(C.c_double)), ("grav_g", C.POINTER(C.c_double)),
+                ("scheme", C.c_int)]
 
 
 _lib = None
@@ -261,6 +263,7 @@ class Setup:
         for d in range(self.ndims):
             c.dim[d], c.iproc[d], c.ip[d], c.periodic[d] = self.dim[d], self.iproc[d], self.ip[d], self.periodic[d]
         c.model = MODELS[s["model"]]
+        c.scheme = SCHEMES[str(s.get("hyp_space_scheme", "weno5"))]
         c.weno_type = 3 if int(w.get("yc", 0)) else 2 if int(w.get("borges", 0)) else 1 if int(w.get("mapped", 0)) else 0
         c.no_limiting = int(w.get("no_limiting", 0))
         c.weno_eps = float(w.get("epsilon", 1e-6))

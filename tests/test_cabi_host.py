@@ -116,7 +116,10 @@ def test_decomposed_setup_neighbors_and_remainders():
 
 
 @pytest.mark.parametrize("mutate, msg", [
-    (lambda c: c.solver.__setitem__("hyp_space_scheme", "crweno5"), "weno5"),
+    (lambda c: c.solver.__setitem__("hyp_space_scheme", "hcweno5"), "weno5"),
+    (lambda c: (c.solver.__setitem__("hyp_space_scheme", "crweno5"),
+                c.solver.__setitem__("hyp_interp_type", "characteristic")), "characteristic"),
+    (lambda c: (c.solver.__setitem__("hyp_space_scheme", "cupw5"), c.solver.__setitem__("iproc", [1, 2, 1])), "iproc"),
     (lambda c: c.solver.__setitem__("time_scheme", "glm-gee"), "rk"),
     (lambda c: c.solver.__setitem__("time_scheme_type", "ssprk2"), "ssprk3"),
     (lambda c: c.solver.__setitem__("ghost", 2), "ghost"),
@@ -132,6 +135,19 @@ def test_unsupported_configurations_fail_loudly(mutate, msg):
         Solver.from_case(case)
     assert msg in str(e.value)
     _lib.load().hpb_clear_error()
+
+
+@pytest.mark.parametrize("scheme", ["crweno5", "cupw5", "upw5"])
+def test_compact_and_linear_schemes_are_accepted(scheme):
+    """crweno5 / cupw5 (one rank per line) and upw5 (any decomposition) set up like weno5"""
+    case = cases.ns3d_rising_bubble((12, 12, 12), "yc", scheme=scheme)
+    sv = Solver.from_case(case)
+    assert sv.dim_local == [12, 12, 12]
+    sv.close()
+    if scheme == "upw5":
+        sv = Solver.from_case(cases.ns3d_turbulence((12, 12, 12), "js", iproc=(1, 2, 1), scheme=scheme), rank=1)
+        assert sv.dim_local == [12, 6, 12]
+        sv.close()
 
 
 def test_gravity_needs_rusanov_like_reference():

@@ -43,6 +43,10 @@ CASES = [
     _prep(cases.ns3d_turbulence((16, 14, 12), "mapped"), n_iter=4, cons=False),          # C4: viscous
     _prep(cases.ns3d_density_wave((14, 12, 10), "z"), n_iter=4),                         # C5a
     _prep(cases.ns3d_rising_bubble((12, 16, 10), "yc"), n_iter=4, screen=1),             # C5b: walls + gravity
+    # compact schemes through HyPar's own executable (exact kernels whatever HYPARB200_USE_FUSED says)
+    _prep(cases.ns2d_vortex((32, 24), "mapped", scheme="crweno5")),
+    _prep(cases.ns3d_rising_bubble((12, 16, 10), "yc", scheme="crweno5"), n_iter=4, screen=1),
+    _prep(cases.euler1d_sod(101, "js", interp="components", scheme="cupw5")),
 ]
 
 

@@ -43,6 +43,15 @@ GOLDEN = [
     ("c5a_denswave_js", "ns3d_density_wave", dict(n=(12, 10, 8), weno="js"), "hypar_ref", False),
     ("c5b_bubble_yc", "ns3d_rising_bubble", dict(n=(12, 16, 10), weno="yc"), "hypar_ref_mpi1", True),
     ("c5b_bubble_mapped_hb1", "ns3d_rising_bubble", dict(n=(10, 12, 14), weno="mapped", hb=1), "hypar_ref", False),
+    # compact schemes (one tridiagonal system per line and component) and the linear fifth-order upwind
+    ("c1_linadv_crweno_mapped", "linear_advection_sine", dict(n=64, weno="mapped", scheme="crweno5"), "hypar_ref", True),
+    ("c2_sod_crweno_js_comp_roe", "euler1d_sod", dict(n=101, weno="js", interp="components", scheme="crweno5"), "hypar_ref", False),
+    ("c3_vortex_crweno_z", "ns2d_vortex", dict(n=(20, 16), weno="z", scheme="crweno5"), "hypar_ref_mpi1", True),
+    ("c4_turb_crweno_mapped_visc", "ns3d_turbulence", dict(n=(10, 8, 8), weno="mapped", scheme="crweno5"), "hypar_ref_mpi1", False),
+    ("c5b_bubble_crweno_yc", "ns3d_rising_bubble", dict(n=(12, 16, 10), weno="yc", scheme="crweno5"), "hypar_ref_mpi1", True),
+    ("c5a_denswave_cupw5", "ns3d_density_wave", dict(n=(12, 10, 8), weno="js", scheme="cupw5"), "hypar_ref", True),
+    ("c3_vortex_cupw5", "ns2d_vortex", dict(n=(28, 36), weno="js", scheme="cupw5"), "hypar_ref", False),
+    ("c2_sod_upw5_comp_rusanov", "euler1d_sod", dict(n=101, weno="js", interp="components", upwinding="rusanov", scheme="upw5"), "hypar_ref", True),
 ]
 
 
