@@ -72,7 +72,10 @@ static int dalloc(double** p, long long n)
   if (*p) return HPB_OK;
   cudaError_t e = cudaMalloc((void**)p, (size_t)n * sizeof(double));
   if (e != cudaSuccess) return hpb_fail(HPB_ERR_ALLOC, "cudaMalloc of %lld doubles failed: %s", n, cudaGetErrorString(e));
+  // the solver's stream is non-blocking: a memset on the legacy stream is NOT ordered before later work on it, so
+  // wait for it here (allocation time only) -- otherwise it can land on top of the first data written to the buffer
   e = cudaMemset(*p, 0, (size_t)n * sizeof(double));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
   if (e != cudaSuccess) return hpb_fail(HPB_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
   return HPB_OK;
 }
@@ -145,6 +148,7 @@ static int ensure_pieces(hpb_solver* h)
     if (!h->d_err) {
       HPB_CUDA(cudaMalloc((void**)&h->d_err, sizeof(int)));
       HPB_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+      HPB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     }
   }
   return HPB_OK;
@@ -230,6 +234,7 @@ extern "C" int hpb_create(const hpb_config* cfg, hpb_solver** out)
     cudaMemcpy(h->d_dxinv, h->dxinv_h.data(), nx * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_gravf, h->gravf_h.data(), (size_t)G.npg * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_gravg, h->gravg_h.data(), (size_t)G.npg * sizeof(double), cudaMemcpyHostToDevice);
+    cudaStreamSynchronize(cudaStreamLegacy);   // pageable H2D may still be in flight on return; h->stream is non-blocking
     if (cudaMallocHost((void**)&h->h_red, 8 * sizeof(double)) != cudaSuccess) { hpb_destroy(h); return hpb_fail(HPB_ERR_ALLOC, "pinned alloc"); }
     // halo buffers (only for faces that have a neighbour)
     for (int d = 0; d < G.ndims; d++) {
@@ -558,6 +563,7 @@ extern "C" int hpb_InterpolateInterfacesHyp(hpb_solver* h, double* fI, const dou
       }
     }
     HPB_CUDA(cudaMemcpy(h->d_w, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+    HPB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     h->w_valid = true;
   }
   TRY(dalloc(&h->d_iface[0], nif_max(h) * h->geo.nvars));
