@@ -49,7 +49,7 @@ SYMBOLS = [
     "hpb_ApplyBoundaryConditions", "hpb_HyperbolicFunction", "hpb_ParabolicFunction", "hpb_SourceFunction",
     "hpb_RHSFunction", "hpb_FFunction", "hpb_UFunction", "hpb_SetInterpLimiterVar", "hpb_GetInterpWeights",
     "hpb_InterpolateInterfacesHyp", "hpb_Upwind", "hpb_FirstDerivativePar", "hpb_SecondDerivativePar",
-    "hpb_ComputeCFL", "hpb_TimeIntegrate",
+    "hpb_ComputeCFL", "hpb_TimeIntegrate", "hpb_pipe_upload", "hpb_pipe_download", "hpb_pipe_join", "hpb_pipe_wait", "hpb_TimeIntegrateAsync",
     "hpb_dev_set_solution", "hpb_dev_get_solution", "hpb_dev_fill_solution_from_global", "hpb_TimeStep",
     "hpb_TimeSteps", "hpb_current_time", "hpb_dev_ComputeCFL", "hpb_dev_StepNormSumSq", "hpb_dev_RHS",
     "hpb_halo_buffers", "hpb_step_begin", "hpb_step_halo_done", "hpb_stage_begin", "hpb_stage_halo_done",
@@ -106,6 +106,11 @@ def load():
     L.hpb_SecondDerivativePar.argtypes = [vp, dp, dp, C.c_int]
     L.hpb_ComputeCFL.argtypes = [vp, dp, C.c_double, C.c_double, dp]
     L.hpb_TimeIntegrate.argtypes = [vp, dp, C.c_int, C.c_double]
+    L.hpb_pipe_upload.argtypes = [vp, dp, C.c_double]
+    L.hpb_pipe_download.argtypes = [vp, dp]
+    L.hpb_pipe_wait.argtypes = [vp]
+    L.hpb_pipe_join.argtypes = [vp]
+    L.hpb_TimeIntegrateAsync.argtypes = [vp, dp, dp, C.c_int, C.c_double]
     L.hpb_dev_set_solution.argtypes = [vp, dp]
     L.hpb_dev_get_solution.argtypes = [vp, dp]
     L.hpb_dev_fill_solution_from_global.argtypes = [vp, dp]

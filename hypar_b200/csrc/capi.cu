@@ -269,6 +269,11 @@ extern "C" int hpb_destroy(hpb_solver* h)
   for (int i = 0; i < 2; i++) if (h->d_cell[i]) cudaFree(h->d_cell[i]);
   for (int i = 0; i < 3; i++) if (h->d_tri[i]) cudaFree(h->d_tri[i]);
   if (h->d_err) cudaFree(h->d_err);
+  if (h->d_pipe_in) cudaFree(h->d_pipe_in);
+  if (h->d_pipe_out) cudaFree(h->d_pipe_out);
+  for (int k = 0; k < 4; k++) if (h->ev_pipe[k]) cudaEventDestroy(h->ev_pipe[k]);
+  if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+  if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
   for (int f = 0; f < 3; f++) for (int k = 0; k < 6; k++) {
     if (h->d_send[f][k]) cudaFree(h->d_send[f][k]);
     if (h->d_recv[f][k]) cudaFree(h->d_recv[f][k]);
@@ -708,6 +713,84 @@ extern "C" int hpb_TimeIntegrate(hpb_solver* h, double* u, int nsteps, double t0
   TRY(upload(h, u, h->d_u, h->geo.npg, h->geo.nvars));
   for (int i = 0; i < nsteps; i++) TRY(step_single(h));
   return download(h, h->d_u, u, h->geo.npg, h->geo.nvars);
+}
+
+// ------------------------------------------------------------------------------------ pipelined host-array stepping
+static int ensure_pipe(hpb_solver* h)
+{
+  if (h->s_h2d) return HPB_OK;
+  TRY(dalloc(&h->d_pipe_in, ncell(h)));
+  TRY(dalloc(&h->d_pipe_out, ncell(h)));
+  HPB_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+  for (int k = 0; k < 4; k++) HPB_CUDA(cudaEventCreateWithFlags(&h->ev_pipe[k], cudaEventDisableTiming));
+  HPB_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+  return HPB_OK;
+}
+enum { EV_IN_READY = 0, EV_IN_FREE = 1, EV_OUT_READY = 2, EV_OUT_FREE = 3 };
+
+extern "C" int hpb_pipe_upload(hpb_solver* h, const double* u_in, double t0)
+{
+  TRY(need_device(h));
+  if (!u_in) return hpb_fail(HPB_ERR_INVALID, "pipe_upload: null input");
+  TRY(ensure_pipe(h));
+  const size_t bytes = (size_t)ncell(h) * sizeof(double);
+  // the staging array is free once the previous field has been transposed out of it
+  HPB_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_pipe[EV_IN_FREE], 0));
+  HPB_CUDA(cudaMemcpyAsync(h->d_pipe_in, u_in, bytes, cudaMemcpyHostToDevice, h->s_h2d));
+  HPB_CUDA(cudaEventRecord(h->ev_pipe[EV_IN_READY], h->s_h2d));
+  // on the solver's stream (i.e. after the previous field's steps and its transposition to the outgoing array)
+  HPB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pipe[EV_IN_READY], 0));
+  hpbk::aos_to_soa(h, h->d_pipe_in, h->d_u, h->geo.npg, h->geo.nvars);
+  HPB_CUDA(cudaEventRecord(h->ev_pipe[EV_IN_FREE], h->stream));
+  h->t = t0;
+  return check_async(h, "pipe_upload");
+}
+
+extern "C" int hpb_pipe_download(hpb_solver* h, double* u_out)
+{
+  TRY(need_device(h));
+  if (!u_out) return hpb_fail(HPB_ERR_INVALID, "pipe_download: null output");
+  TRY(ensure_pipe(h));
+  const size_t bytes = (size_t)ncell(h) * sizeof(double);
+  HPB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pipe[EV_OUT_FREE], 0));    // the previous field has left the array
+  hpbk::soa_to_aos(h, h->d_u, h->d_pipe_out, h->geo.npg, h->geo.nvars);
+  HPB_CUDA(cudaEventRecord(h->ev_pipe[EV_OUT_READY], h->stream));
+  HPB_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_pipe[EV_OUT_READY], 0));
+  HPB_CUDA(cudaMemcpyAsync(u_out, h->d_pipe_out, bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+  HPB_CUDA(cudaEventRecord(h->ev_pipe[EV_OUT_FREE], h->s_d2h));
+  return check_async(h, "pipe_download");
+}
+
+extern "C" int hpb_pipe_join(hpb_solver* h)
+{
+  TRY(need_device(h));
+  if (!h->s_h2d) return HPB_OK;
+  // work enqueued on the solver's stream from here on runs after every copy enqueued so far
+  HPB_CUDA(cudaEventRecord(h->ev_pipe[EV_IN_READY], h->s_h2d));
+  HPB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pipe[EV_IN_READY], 0));
+  HPB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pipe[EV_OUT_FREE], 0));
+  return HPB_OK;
+}
+
+extern "C" int hpb_pipe_wait(hpb_solver* h)
+{
+  TRY(need_device(h));
+  if (h->s_h2d) {
+    HPB_CUDA(cudaStreamSynchronize(h->s_h2d));
+    TRY(sync_check(h, "pipe_wait"));
+    HPB_CUDA(cudaStreamSynchronize(h->s_d2h));
+    return HPB_OK;
+  }
+  return sync_check(h, "pipe_wait");
+}
+
+extern "C" int hpb_TimeIntegrateAsync(hpb_solver* h, const double* u_in, double* u_out, int nsteps, double t0)
+{
+  TRY(need_device(h));
+  SINGLE_RANK_ONLY(h, "TimeIntegrateAsync");
+  TRY(hpb_pipe_upload(h, u_in, t0));
+  for (int i = 0; i < nsteps; i++) TRY(step_single(h));
+  return hpb_pipe_download(h, u_out);
 }
 
 extern "C" int hpb_dev_ComputeCFL(hpb_solver* h, double* cfl_local_max)

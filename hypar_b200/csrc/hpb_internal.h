@@ -80,6 +80,11 @@ struct hpb_solver {
   double *d_cell[2] = {nullptr, nullptr};
   double *d_tri[3] = {nullptr, nullptr, nullptr};
   int *d_err = nullptr;
+  // pipelined host-array stepping (hpb_pipe_*): copy streams, AoS staging of the incoming / outgoing field, events
+  // [in ready, in free, out ready, out free]
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  double *d_pipe_in = nullptr, *d_pipe_out = nullptr;
+  cudaEvent_t ev_pipe[4] = {nullptr, nullptr, nullptr, nullptr};
   double *d_red = nullptr;         // reduction scratch
   // conservation diagnostics (cfg.conservation_check): boundary-flux bookkeeping of HyperbolicFunction.c:103-106 /
   // TimeRK.c:172-193. d_cons = [slot][2*ndims*nvars]: slots 0..3 = BoundaryFlux[stage], 4 = StageBoundaryIntegral of

@@ -228,6 +228,14 @@ class DistributedSolver:
                                                            u_host.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double))))
         return u_host
 
+    def time_integrate_host_async(self, u_in: np.ndarray, u_out: np.ndarray, nsteps: int = 1) -> None:
+        """The same for a sequence of independent fields (ensembles): only enqueues -- the H2D copy of this field
+        overlaps the steps of the previous one and the D2H copy of the one before (hpb_pipe_*). Finish with
+        ``solver.pipe_wait()``."""
+        self.solver.pipe_upload(u_in, self.solver.time)
+        self.time_steps(nsteps)
+        self.solver.pipe_download(u_out)
+
     def rhs(self, want: bool = True):
         """One TimeRHSFunctionExplicit of the device solution (stage 0 buffers); returns this rank's rhs."""
         sv, L = self.solver, self.solver.L

@@ -320,6 +320,22 @@ class Solver:
         self._ck(self.L.hpb_TimeIntegrate(self.h, _dp(u), nsteps, t0))
         return u
 
+    # -- pipelined host-array stepping over a sequence of independent fields (ensembles): calls only enqueue
+    def TimeIntegrateAsync(self, u_in: np.ndarray, u_out: np.ndarray, nsteps: int = 1, t0: float = 0.0) -> None:
+        self._ck(self.L.hpb_TimeIntegrateAsync(self.h, _dp(u_in), _dp(u_out), nsteps, t0))
+
+    def pipe_upload(self, u_in: np.ndarray, t0: float = 0.0) -> None:
+        self._ck(self.L.hpb_pipe_upload(self.h, _dp(u_in), t0))
+
+    def pipe_download(self, u_out: np.ndarray) -> None:
+        self._ck(self.L.hpb_pipe_download(self.h, _dp(u_out)))
+
+    def pipe_join(self) -> None:
+        self._ck(self.L.hpb_pipe_join(self.h))
+
+    def pipe_wait(self) -> None:
+        self._ck(self.L.hpb_pipe_wait(self.h))
+
     # -- device-resident path
     def set_solution(self, u: np.ndarray) -> None:
         self._ck(self.L.hpb_dev_set_solution(self.h, _dp(u)))

@@ -192,6 +192,22 @@ int hpb_ComputeCFL(hpb_solver* h, const double* u, double dt, double t, double* 
 /* TimeIntegration::TimeIntegrate = TimeRK (TimeRK.c:35) preceded by TimePreStep's BC/halo
    (TimePreStep.c:50-76): advances host u by nsteps steps of size cfg.dt. Single rank. */
 int hpb_TimeIntegrate(hpb_solver* h, double* u, int nsteps, double t0);
+/* The same for a SEQUENCE of independent fields on one solver -- HyPar's ensemble runs (nsims > 1: Solve.cpp:37-180
+   advances every SimulationObject each step; include/ensemble_simulations.h) or any caller that keeps its fields in
+   host memory: the calls only ENQUEUE work, so the host->device copy of a field overlaps the steps of the previous
+   one and the device->host copy of the one before (two copy streams + the solver's stream, ordered by events).
+     hpb_pipe_upload    H2D of u_in (HyPar layout; pinned memory for a true overlap) + transposition into the device
+                        solution, after the previous field's steps
+     ... steps: hpb_TimeStep / hpb_TimeSteps (single rank) or the staged hpb_step_* / hpb_stage_* sequence ...
+     hpb_pipe_download  transposition + D2H of the device solution into u_out
+     hpb_pipe_wait      blocks until everything enqueued has finished (u_in may be reused after the upload's copy:
+                        conservatively, after hpb_pipe_wait)
+     hpb_TimeIntegrateAsync = upload + nsteps steps + download, single rank. */
+int hpb_pipe_upload(hpb_solver* h, const double* u_in, double t0);
+int hpb_pipe_download(hpb_solver* h, double* u_out);
+int hpb_pipe_join(hpb_solver* h);   /* orders the solver's stream (hpb_stream) after every copy enqueued so far, without blocking */
+int hpb_pipe_wait(hpb_solver* h);
+int hpb_TimeIntegrateAsync(hpb_solver* h, const double* u_in, double* u_out, int nsteps, double t0);
 
 /* ------------------------------------------------------------------ DEVICE-RESIDENT path */
 int hpb_dev_set_solution(hpb_solver* h, const double* u_host);     /* H2D + AoS->SoA */
