@@ -63,6 +63,50 @@ def c4_inputs(size, iproc, dt=0.005):
     return s, b, ph, w, x
 
 
+def c5_inputs(kind, size, iproc):
+    """Configuration C5 (BASELINE.json configs[4]) at an arbitrary size, without materialising the global field:
+    c5a = density sine wave (periodic, inviscid, RK4), c5b = rising thermal bubble (slip walls, gravity, HB 2, yc
+    weights, SSPRK3) -- the dictionaries of hypar_b200.cases.ns3d_density_wave / ns3d_rising_bubble, dt scaled with
+    the grid spacing (same CFL as the 64^3 cases)."""
+    from hypar_b200 import cases
+    import numpy as np
+    small = (cases.ns3d_density_wave if kind == "c5a" else cases.ns3d_rising_bubble)((8, 8, 8))
+    s = dict(small.solver)
+    s["size"], s["iproc"] = list(size), list(iproc)
+    s["dt"] = (1e-3 if kind == "c5a" else 0.01) * 64.0 / max(size)
+    if kind == "c5a":
+        x = [np.arange(size[d], dtype=np.float64) / size[d] for d in range(3)]
+    else:
+        x = [np.arange(size[d], dtype=np.float64) * (1000.0 / (size[d] - 1)) for d in range(3)]
+    return s, small.boundary, small.physics, small.weno, x
+
+
+def synth_field_c5(kind, x_loc, device):
+    """This rank's block of the C5 initial fields (hypar_b200.cases: DensitySineWave exact.C:54-81,
+    RisingThermalBubble_Config1 init.c:108-133), evaluated on the GPU. Returns (nz, ny, nx, 5) float64."""
+    import math
+    import torch
+    gamma = 1.4
+    X = torch.as_tensor(x_loc[0], device=device)[None, None, :]
+    Y = torch.as_tensor(x_loc[1], device=device)[None, :, None]
+    Z = torch.as_tensor(x_loc[2], device=device)[:, None, None]
+    if kind == "c5a":
+        rho = 1.0 + 0.1 * torch.sin(2 * math.pi * X) * torch.sin(2 * math.pi * Y) * torch.sin(2 * math.pi * Z)
+        e = (1.0 / gamma) / (gamma - 1.0) + 0.5 * rho * 3.0
+        return torch.stack([rho, rho, rho, rho, e], dim=-1)
+    R, g, rho_ref, p_ref = 287.058, 9.8, 1.1612055171196529, 100000.0
+    T_ref = p_ref / (R * rho_ref)
+    Cp = gamma / (gamma - 1.0) * R
+    r = torch.sqrt((X - 500.0) ** 2 + (Y - 260.0) ** 2 + (Z - 500.0) ** 2)
+    dtheta = torch.where(r > 250.0, torch.zeros_like(r), 0.5 * (1.0 + torch.cos(math.pi * r / 250.0)))
+    theta = T_ref + dtheta
+    Pexner = (1.0 - (g / (Cp * T_ref)) * Y).expand_as(theta)
+    rho = (p_ref / (R * theta)) * Pexner ** (1.0 / (gamma - 1.0))
+    E = rho * (R / (gamma - 1.0)) * theta * Pexner
+    zero = torch.zeros_like(rho)
+    return torch.stack([rho, zero, zero, zero, E], dim=-1)
+
+
 def synth_field_torch(x_loc, device, seed=20261017):
     """The C4 synthetic field of hypar_b200.cases.ns3d_turbulence evaluated on this rank's block, on the
     GPU (torch is plumbing here: it only creates the input). Returns (nz, ny, nx, 5) float64."""
@@ -209,7 +253,15 @@ def gpu_arm(args):
     numa_cpus = bind_to_gpu_numa(local_rank) if not args.no_numa_bind else None
 
     size, iproc = weak_grid(args.n, world)
-    s, b, ph, w, x = c4_inputs(size, iproc)
+    if args.workload == "c4":
+        s, b, ph, w, x = c4_inputs(size, iproc)
+        wl_label = "C4 NavierStokes3D WENO5(mapped)+Rusanov+viscous RK4"
+        wl_bc = "periodic"
+    else:
+        s, b, ph, w, x = c5_inputs(args.workload, size, iproc)
+        wl_label = ("C5a NavierStokes3D density sine wave, WENO5(JS)+Rusanov, inviscid, RK4" if args.workload == "c5a" else
+                    "C5b NavierStokes3D rising thermal bubble, WENO5(YC)+Rusanov, gravity (HB 2) source, SSPRK3")
+        wl_bc = "periodic" if args.workload == "c5a" else "slip walls"
     if world == 1:
         sv = Solver(s, b, ph, w, x, rank=0, device=local_rank)
         stepper = None
@@ -224,7 +276,7 @@ def gpu_arm(args):
     # synthetic input, created on the device, staged into a pinned host array in HyPar's own layout
     u_host_t = torch.zeros(sv.npoints_local_wghosts * 5, dtype=torch.float64).pin_memory()
     u_host = u_host_t.numpy()
-    fld = synth_field_torch(x_loc, dev)
+    fld = synth_field_torch(x_loc, dev) if args.workload == "c4" else synth_field_c5(args.workload, x_loc, dev)
     u_host_t.view(nloc[2] + 2 * g, nloc[1] + 2 * g, nloc[0] + 2 * g, 5)[g:-g, g:-g, g:-g, :].copy_(fld)
     del fld
     torch.cuda.empty_cache()
@@ -232,6 +284,7 @@ def gpu_arm(args):
 
     stream = torch.cuda.ExternalStream(sv.stream, device=dev)
     npts_global = float(size[0]) * size[1] * size[2]
+    nstages = sv.nstages
 
     def barrier():
         torch.cuda.synchronize()
@@ -275,7 +328,7 @@ def gpu_arm(args):
     prof = sv.profile_query()
     sv.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
-    value = npts_global * NSTAGES * args.steps / (ms * 1e-3) / 1e6
+    value = npts_global * nstages * args.steps / (ms * 1e-3) / 1e6
 
     # sanity: the field must still be finite after the timed steps
     cfl = sv.dev_ComputeCFL()
@@ -289,67 +342,70 @@ def gpu_arm(args):
     # (an ensemble: every step takes a field from pinned host memory and returns its result to pinned host memory) --
     # the H2D copy of field k+1 and the D2H copy of field k-1 run on copy streams under the step of field k.
     nbytes = u_host.nbytes
-    sync_steps = max(1, min(args.steps, 3))
+    e2e_val = ms_e2e = sync_val = ms_sync = None
+    e2e_steps = sync_steps = 0
+    if not args.no_e2e:
+        sync_steps = max(1, min(args.steps, 3))
 
-    def e2e_step():
-        if stepper is None:
-            sv.TimeIntegrate(u_host, 1, sv.time)
-        else:
-            stepper.time_integrate_host(u_host, 1)
+        def e2e_step():
+            if stepper is None:
+                sv.TimeIntegrate(u_host, 1, sv.time)
+            else:
+                stepper.time_integrate_host(u_host, 1)
 
-    u_in_t = torch.empty_like(u_host_t).pin_memory()     # the synthetic input, kept: every pipelined step consumes it
-    u_in_t.copy_(u_host_t)
-    u_in = u_in_t.numpy()
-    e2e_step()
-    ms_sync = timed(e2e_step, sync_steps)
-    sync_val = npts_global * NSTAGES * sync_steps / (ms_sync * 1e-3) / 1e6
-    if not np.isfinite(u_host).all():
-        raise RuntimeError("non-finite values in the host solution after the end-to-end steps")
+        u_in_t = torch.empty_like(u_host_t).pin_memory()     # the synthetic input, kept: every pipelined step consumes it
+        u_in_t.copy_(u_host_t)
+        u_in = u_in_t.numpy()
+        e2e_step()
+        ms_sync = timed(e2e_step, sync_steps)
+        sync_val = npts_global * nstages * sync_steps / (ms_sync * 1e-3) / 1e6
+        if not np.isfinite(u_host).all():
+            raise RuntimeError("non-finite values in the host solution after the end-to-end steps")
 
-    e2e_steps = max(args.steps, 16)
-    u_out = u_host                               # results land in the first pinned array
+        e2e_steps = max(args.steps, 16)
+        u_out = u_host                               # results land in the first pinned array
 
-    def e2e_submit():
-        if stepper is None:
-            sv.TimeIntegrateAsync(u_in, u_out, 1, 0.0)
-        else:
-            stepper.time_integrate_host_async(u_in, u_out, 1)
+        def e2e_submit():
+            if stepper is None:
+                sv.TimeIntegrateAsync(u_in, u_out, 1, 0.0)
+            else:
+                stepper.time_integrate_host_async(u_in, u_out, 1)
 
-    def e2e_all():
-        for _ in range(e2e_steps):
-            e2e_submit()
-        sv.pipe_join()                           # the closing event (on the solver's stream) comes after the last D2H
+        def e2e_all():
+            for _ in range(e2e_steps):
+                e2e_submit()
+            sv.pipe_join()                           # the closing event (on the solver's stream) comes after the last D2H
 
-    # the pipelined result must be the blocking call's result for the same input, bit for bit
-    u_host_t.copy_(u_in_t)
-    e2e_step()
-    u_chk = sv.interior(u_host).copy()
-    u_host_t.zero_()
-    e2e_submit(); e2e_submit()
-    sv.pipe_wait()
-    if not np.array_equal(sv.interior(u_out), u_chk):
-        raise RuntimeError("pipelined end-to-end step differs from the blocking hpb_TimeIntegrate result")
-    del u_chk
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    e2e_all()
-    e1.record(stream)
-    sv.pipe_wait()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if dist is not None:
-        tt = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_e2e = float(tt.item())
-    e2e_val = npts_global * NSTAGES * e2e_steps / (ms_e2e * 1e-3) / 1e6
-    if not np.isfinite(u_out).all():
-        raise RuntimeError("non-finite values in the host solution after the pipelined end-to-end steps")
-
-    if rank != 0:
+        # the pipelined result must be the blocking call's result for the same input, bit for bit
+        u_host_t.copy_(u_in_t)
+        e2e_step()
+        u_chk = sv.interior(u_host).copy()
+        u_host_t.zero_()
+        e2e_submit(); e2e_submit()
+        sv.pipe_wait()
+        if not np.array_equal(sv.interior(u_out), u_chk):
+            raise RuntimeError("pipelined end-to-end step differs from the blocking hpb_TimeIntegrate result")
+        del u_chk
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        e2e_all()
+        e1.record(stream)
+        sv.pipe_wait()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
         if dist is not None:
-            dist.destroy_process_group()
-        return
+            tt = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_e2e = float(tt.item())
+        e2e_val = npts_global * nstages * e2e_steps / (ms_e2e * 1e-3) / 1e6
+        if not np.isfinite(u_out).all():
+            raise RuntimeError("non-finite values in the host solution after the pipelined end-to-end steps")
+
+        if rank != 0:
+            if dist is not None:
+                dist.destroy_process_group()
+            return
 
     # ---- roofline of the dominant kernel (per-launch CUDA-event time, this rank)
     peaks = {}
@@ -383,8 +439,8 @@ def gpu_arm(args):
         "bytes_per_point": SWEEP_BYTES[dom],
         "share_of_step": {k: (v[0] / total_prof if total_prof > 0 else None) for k, v in prof.items() if v[1] > 0},
         "whole_stage": {"bytes_per_point_stage": STAGE_BYTES,
-                        "achieved": STAGE_BYTES * npts_local * NSTAGES * args.steps / (ms * 1e-3) / 1e9,
-                        "frac": STAGE_BYTES * npts_local * NSTAGES * args.steps / (ms * 1e-3) / 1e9 / peak},
+                        "achieved": STAGE_BYTES * npts_local * nstages * args.steps / (ms * 1e-3) / 1e9,
+                        "frac": STAGE_BYTES * npts_local * nstages * args.steps / (ms * 1e-3) / 1e9 / peak},
         "note": "FP64-issue-bound kernel (DESIGN.md): the HBM fraction is reported as the metric demands; the FP64 pipe "
                 "is the binding unit (fp64_pipe_active_pct_ncu); traffic exceeds the algorithmic bytes by the 8 "
                 "derivative scalars (64 B/point) the viscous flux reads",
@@ -392,7 +448,7 @@ def gpu_arm(args):
 
     # ---- CPU baseline: the reference itself on a bounded sample
     cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable"}
-    if not args.no_cpu:
+    if not args.no_cpu and args.workload == "c4":
         try:
             threads = os.cpu_count() or 1
             v, sec = run_reference_cpu(args.cpu_n, 2, 1, threads)
@@ -406,18 +462,18 @@ def gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C4 NavierStokes3D WENO5(mapped)+Rusanov+viscous RK4, {size[0]}x{size[1]}x{size[2]} periodic",
-                   "points_per_gpu": f"{nloc[0]}x{nloc[1]}x{nloc[2]}", "iproc": iproc, "rk_stages_per_step": NSTAGES,
+        "config": {"workload": f"{wl_label}, {size[0]}x{size[1]}x{size[2]} {wl_bc}",
+                   "points_per_gpu": f"{nloc[0]}x{nloc[1]}x{nloc[2]}", "iproc": iproc, "rk_stages_per_step": nstages,
                    "halo": (None if stepper is None else ("NCCL send/recv on a communication stream, overlapped with the "
                             "Q-derivative kernel and the sweeps" if stepper.overlap else "NCCL send/recv, serial")),
                    "l2": "working set (5.6 GB per array) >> L2, no flush needed",
                    "host_numa_bind": (f"{len(numa_cpus)} GPU-local CPUs" if numa_cpus else "none")},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                "ms_per_step": (ms_e2e / e2e_steps if e2e_steps else None), "steps": e2e_steps,
                 "api": ("hpb_TimeIntegrateAsync(pinned host u_in -> pinned host u_out, 1 step)" if stepper is None
                         else "DistributedSolver.time_integrate_host_async") + ", one call per step over a sequence of "
                        "independent fields; the copies of neighbouring steps overlap the step (copy streams)",
-                "sync": {"value": sync_val, "ms_per_step": ms_sync / sync_steps, "steps": sync_steps,
+                "sync": {"value": sync_val, "ms_per_step": (ms_sync / sync_steps if sync_steps else None), "steps": sync_steps,
                          "api": "hpb_TimeIntegrate(host u, 1 step), blocking: copy, step, copy in sequence"
                                 if stepper is None else "DistributedSolver.time_integrate_host, blocking"}},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -437,7 +493,11 @@ def main():
     ap.add_argument("--n", type=int, default=512, help="points per dimension per GPU")
     ap.add_argument("--cpu-n", type=int, default=64, help="grid of the cpu_baseline sample")
     ap.add_argument("--ref-n", type=int, default=64, help="grid of the --impl reference sample")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5a", "c5b"],
+                    help="c4 (default): the configuration BASELINE.json's metric is quoted on; c5a / c5b: configs[4] "
+                         "(density sine wave / rising thermal bubble with gravity), 1024^3 at 8 GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end legs (profiler runs of the device loop only)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA-local CPUs")
     ap.add_argument("--overlap", action="store_true", help="multi-GPU: halo exchange on a communication stream, overlapped "
                     "with the derivative kernel / sweeps (measured slower than the serial schedule on NVLink 5: DESIGN.md)")

@@ -73,6 +73,15 @@ def _solver(ndims, nvars, size, model, *, iproc=None, ts="rk", tstype="44", dt=1
     }
 
 
+def with_time_scheme(case: "Case", time_scheme: str, tstype: str = " ") -> "Case":
+    """the same case with another time integrator (solver.inp time_scheme / time_scheme_type)"""
+    case.solver["time_scheme"], case.solver["time_scheme_type"] = time_scheme, tstype
+    if time_scheme == "euler":
+        del case.solver["time_scheme_type"]          # no type keyword for forward Euler (ReadInputs.c:131)
+    case.name += f"_{time_scheme}{'' if time_scheme == 'euler' else tstype}"
+    return case
+
+
 def _sfx(scheme: str) -> str:
     return "" if scheme == "weno5" else "_" + scheme
 

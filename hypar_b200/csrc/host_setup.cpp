@@ -59,8 +59,8 @@ int hpb_setup_host(hpb_solver* h)
                     model_nv[c.model], nd, c.nvars);
   if (c.nvars < 1 || c.nvars > HPB_MAX_NVARS) return hpb_fail(HPB_ERR_INVALID, "nvars = %d not supported", c.nvars);
   if (c.weno_type < 0 || c.weno_type > 3) return hpb_fail(HPB_ERR_INVALID, "unknown WENO weight type %d", c.weno_type);
-  if (c.rk_type != HPB_RK_44 && c.rk_type != HPB_RK_SSPRK3)
-    return hpb_fail(HPB_ERR_INVALID, "time_scheme_type %d not supported (rk 44, ssprk3)", c.rk_type);
+  if (c.rk_type < HPB_RK_44 || c.rk_type > HPB_RK_33)
+    return hpb_fail(HPB_ERR_INVALID, "time_scheme_type %d not supported (rk 1fe, 22, 33, 44, ssprk3)", c.rk_type);
   if (c.model == HPB_MODEL_NS2D && c.upwind != HPB_UPWIND_RUSANOV)
     return hpb_fail(HPB_ERR_INVALID, "navierstokes2d: only rusanov upwinding is implemented on the device");
   if ((c.model == HPB_MODEL_NS3D || c.model == HPB_MODEL_EULER1D) && (c.upwind < HPB_UPWIND_ROE || c.upwind > HPB_UPWIND_LLF))
@@ -258,11 +258,23 @@ int hpb_setup_host(hpb_solver* h)
     T.A[4] = 0.5; T.A[9] = 0.5; T.A[14] = 1.0;
     T.c[0] = 0.0; T.c[1] = T.c[2] = 0.5; T.c[3] = 1.0;
     T.b[0] = T.b[3] = 1.0/6.0; T.b[1] = T.b[2] = 1.0/3.0;
-  } else {
+  } else if (c.rk_type == HPB_RK_SSPRK3) {
     T.ns = 3;
     T.A[3] = 1.0; T.A[6] = 0.25; T.A[7] = 0.25;
     T.c[1] = 1.0; T.c[2] = 0.5; T.c[0] = 0.0;
     T.b[0] = T.b[1] = 1.0/6.0; T.b[2] = 2.0/3.0;
+  } else if (c.rk_type == HPB_RK_1FE) {         // TimeExplicitRKInitialize.c:27-36
+    T.ns = 1;
+    T.b[0] = 1.0;
+  } else if (c.rk_type == HPB_RK_22) {          // :37-48
+    T.ns = 2;
+    T.A[2] = 1.0; T.c[1] = 1.0;
+    T.b[0] = T.b[1] = 0.5;
+  } else {                                      // HPB_RK_33, :49-60
+    T.ns = 3;
+    T.A[3] = 2.0/3.0; T.A[6] = 2.0/3.0-1.0/4.0; T.A[7] = 1.0/4.0;
+    T.c[1] = 2.0/3.0; T.c[2] = 2.0/3.0;
+    T.b[0] = 1.0/4.0; T.b[1] = -1.0/4.0; T.b[2] = 1.0;
   }
   return HPB_OK;
 }

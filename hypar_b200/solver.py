@@ -22,7 +22,7 @@ from . import _lib, hypario
 MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3}
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2}
 UPWINDS = {"roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
-RK_TYPES = {"44": 0, "ssprk3": 1}
+RK_TYPES = {"44": 0, "ssprk3": 1, "tvdrk3": 1, "1fe": 2, "22": 3, "33": 4}
 SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3}
 FIELD_U, FIELD_QDERIVX, FIELD_QDERIVY = 0, 1, 2
 
@@ -61,11 +61,12 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     if scheme not in SCHEMES:
         raise HyParB200Error(f"hyp_space_scheme '{scheme}' is not on the B200 path (weno5, crweno5, cupw5, upw5)")
     c.hyp_scheme = SCHEMES[scheme]
-    if str(solver.get("time_scheme", "euler")) != "rk":
-        raise HyParB200Error(f"time_scheme '{solver.get('time_scheme')}' is not on the B200 path (rk only)")
-    tst = str(solver.get("time_scheme_type", " "))
+    ts = str(solver.get("time_scheme", "euler"))
+    if ts not in ("rk", "euler"):
+        raise HyParB200Error(f"time_scheme '{ts}' is not on the B200 path (rk, euler)")
+    tst = str(solver.get("time_scheme_type", " ")) if ts == "rk" else "1fe"     # TimeForwardEuler.c = RK "1fe"
     if tst not in RK_TYPES:
-        raise HyParB200Error(f"time_scheme_type '{tst}' is not on the B200 path (44, ssprk3)")
+        raise HyParB200Error(f"time_scheme_type '{tst}' is not on the B200 path (1fe, 22, 33, 44, ssprk3, tvdrk3)")
     c.rk_type = RK_TYPES[tst]
     if str(solver.get("hyp_flux_split", "no")) != "no":
         raise HyParB200Error("hyp_flux_split yes is not on the B200 path")

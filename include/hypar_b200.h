@@ -79,7 +79,10 @@ extern "C" {
 
 /* time_scheme_type for time_scheme "rk" -- reference TimeExplicitRKInitialize.c:58-79 */
 #define HPB_RK_44     0
-#define HPB_RK_SSPRK3 1
+#define HPB_RK_SSPRK3 1   /* "ssprk3" = "tvdrk3" */
+#define HPB_RK_1FE    2   /* "1fe"; also time_scheme "euler" (TimeForwardEuler.c: the same update) */
+#define HPB_RK_22     3
+#define HPB_RK_33     4
 
 /* fields that have a halo exchange (reference MPIExchangeBoundariesnD call sites) */
 #define HPB_FIELD_U       0   /* TimeRHSFunctionExplicit.c:60, TimePreStep.c:71         */

@@ -192,7 +192,10 @@ int hyparb200_attach(void *sims, int nsims)
   for (int d = 0; d < s->ndims; d++) { c.dim_global[d] = s->dim_global[d]; c.iproc[d] = mpi->iproc[d]; }
   c.interp_char = !strcmp(s->interp_type, _CHARACTERISTIC_);
   if      (!strcmp(s->time_scheme_type, _RK_44_))     c.rk_type = HPB_RK_44;
-  else if (!strcmp(s->time_scheme_type, _RK_SSP3_))   c.rk_type = HPB_RK_SSPRK3;
+  else if (!strcmp(s->time_scheme_type, _RK_SSP3_) || !strcmp(s->time_scheme_type, _RK_TVD3_)) c.rk_type = HPB_RK_SSPRK3;
+  else if (!strcmp(s->time_scheme_type, _RK_1FE_))    c.rk_type = HPB_RK_1FE;
+  else if (!strcmp(s->time_scheme_type, _RK_22_))     c.rk_type = HPB_RK_22;
+  else if (!strcmp(s->time_scheme_type, _RK_33_))     c.rk_type = HPB_RK_33;
   else { fprintf(stderr, "hyparb200_attach: rk type %s is not on the B200 path (44, ssprk3)\n", s->time_scheme_type); return 1; }
   c.par_scheme = atoi(s->spatial_scheme_par);
   c.conservation_check = !strcmp(s->ConservationCheck, "yes");

@@ -444,4 +444,11 @@ class Oracle:
         self.L.hpo_unpack(self.c, _p(a), C.c_int(nv), C.c_int(d), C.c_int(side), _p(buf)); return a
 
 
-RK_TYPES = {"44": 0, "ssprk3": 1}
+RK_TYPES = {"44": 0, "ssprk3": 1, "tvdrk3": 1, "1fe": 2, "22": 3, "33": 4}
+
+
+def rk_type_of(case) -> int:
+    """oracle tableau id of a case's time integrator; time_scheme "euler" (TimeForwardEuler.c) is RK "1fe" """
+    if str(case.solver.get("time_scheme", "rk")) == "euler":
+        return RK_TYPES["1fe"]
+    return RK_TYPES[str(case.solver["time_scheme_type"])]

@@ -78,6 +78,12 @@ def test_host_setup_matches_oracle_setup(case):
     assert np.array_equal(f, S.grav_f) and np.array_equal(g, S.grav_g)
     assert sv.neighbors == [-1] * (2 * S.ndims)
     assert sv.nstages == (4 if case.solver["time_scheme_type"] == "44" else 3)
+    if case is ALL_CASES[0]:
+        for ts, tst, ns in (("rk", "1fe", 1), ("rk", "22", 2), ("rk", "33", 3), ("rk", "tvdrk3", 3), ("euler", " ", 1)):
+            c2 = cases.with_time_scheme(cases.linear_advection_sine(64, "js"), ts, tst)
+            s2 = Solver.from_case(c2)
+            assert s2.nstages == ns
+            s2.close()
     for d in range(S.ndims):
         assert sv.ninterfaces(d) == S.ninterfaces(d)
     sv.close()

@@ -51,7 +51,7 @@ def test_decomposed_rhs_and_steps(need_gpu, case, fused):
                 f"rank {r}: rhs abs err {np.abs(rhs[r] - rhs_ref[r]).max():.3e} > {tol:.3e}"
     # two full time steps
     dt = float(case.solver["dt"])
-    rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    rk = hpo.rk_type_of(case)
     u_ref = MO.local_u0()
     for _ in range(2):
         MO.time_step(u_ref, dt, rk)

@@ -97,7 +97,7 @@ def test_conservation_over_steps(need_gpu, case):
     VolumeIntegral, the local BoundaryIntegral and the conservation error of every step."""
     S = hpo.Setup(case)
     O = hpo.Oracle(S)
-    dt, rk = float(case.solver["dt"]), hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    dt, rk = float(case.solver["dt"]), hpo.rk_type_of(case)
     sv = Solver.from_case(case, use_fused=False)
     u_ref = S.local_u0()
     sv.set_solution(S.local_u0())
@@ -172,7 +172,7 @@ def test_error_sums(need_gpu, case):
     S = hpo.Setup(case)
     O = hpo.Oracle(S)
     u = S.local_u0()
-    dt, rk = float(case.solver["dt"]), hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    dt, rk = float(case.solver["dt"]), hpo.rk_type_of(case)
     for _ in range(2):
         O.time_step(u, dt, rk)
     uex = S.local_u0()
@@ -214,7 +214,7 @@ def test_decomposed_boundary_integral(need_gpu, case, sweepwise):
     if sweepwise and case.solver["model"] != "navierstokes3d":
         pytest.skip("sweep-wise schedule: NavierStokes3D production path")
     MO = MultiRankOracle(case)
-    dt, rk = float(case.solver["dt"]), hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    dt, rk = float(case.solver["dt"]), hpo.rk_type_of(case)
     LR = LocalRanks(case, use_fused=True, sweepwise=sweepwise)
     LR.set_solution(MO.local_u0())
     LR.time_step()

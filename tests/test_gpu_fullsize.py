@@ -99,7 +99,7 @@ def test_c4_full_size_probes(need_gpu):
     n = N3
     case = _c4_case(n)
     dt = float(case.solver["dt"])
-    rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    rk = hpo.rk_type_of(case)
     m = 8
     probes = [((n // 2 - 9, n // 3, n // 5), (34, 30, 32)), ((8, n - 42, n // 2), (32, 34, 30))]
     # a probe that straddles the periodic boundary in all three directions, for the HYPERBOLIC term only: next to the

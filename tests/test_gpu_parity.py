@@ -70,6 +70,12 @@ def _cases():
     C.append(cases.ns3d_rising_bubble((10, 14, 12), "js", scheme="cupw5"))
     C.append(cases.euler1d_sod(101, "js", interp="components", upwinding="llf-char", scheme="upw5"))
     C.append(cases.ns3d_turbulence((14, 10, 12), "js", scheme="upw5"))
+    # the other explicit RK tableaux and forward Euler
+    C.append(cases.with_time_scheme(cases.linear_advection_sine(96, "js"), "rk", "1fe"))
+    C.append(cases.with_time_scheme(cases.euler1d_sod(101, "mapped"), "rk", "22"))
+    C.append(cases.with_time_scheme(cases.ns2d_vortex((40, 28), "yc"), "rk", "33"))
+    C.append(cases.with_time_scheme(cases.ns3d_rising_bubble((12, 16, 10), "z"), "rk", "tvdrk3"))
+    C.append(cases.with_time_scheme(cases.ns3d_turbulence((16, 12, 10), "mapped"), "euler"))
     return C
 
 
@@ -151,7 +157,8 @@ def test_rhs_parity(need_gpu, case):
 
 
 STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CASES[30], CASES[32],
-              CASES[34], CASES[36], CASES[37], CASES[38], CASES[40], CASES[41], CASES[43], CASES[45]]
+              CASES[34], CASES[36], CASES[37], CASES[38], CASES[40], CASES[41], CASES[43], CASES[45],
+              CASES[46], CASES[47], CASES[48], CASES[49], CASES[50]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)
@@ -162,7 +169,7 @@ def test_time_steps_exact_path_bit_identical(need_gpu, case):
     O = hpo.Oracle(S)
     u_ref = S.local_u0()
     dt = float(case.solver["dt"])
-    rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    rk = hpo.rk_type_of(case)
     for _ in range(5):
         O.time_step(u_ref, dt, rk)
     sv = Solver.from_case(case, use_fused=False)
@@ -186,7 +193,7 @@ def test_time_steps_parity(need_gpu, case):
     O = hpo.Oracle(S)
     u_ref = S.local_u0()
     dt = float(case.solver["dt"])
-    rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    rk = hpo.rk_type_of(case)
     for _ in range(5):
         u_prev = u_ref.copy()
         O.time_step(u_ref, dt, rk)

@@ -88,7 +88,7 @@ def test_tma_sweep_time_steps(need_gpu, case):
     O = hpo.Oracle(S)
     u_ref = S.local_u0()
     dt = float(case.solver["dt"])
-    rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    rk = hpo.rk_type_of(case)
     for _ in range(3):
         O.time_step(u_ref, dt, rk)
     sv = Solver.from_case(case)

@@ -59,7 +59,7 @@ def test_oracle_matches_reference_golden(path):
     same(rhs, z["rhs_rhs"], "rhs")
     # three steps of the reference's own time loop
     u = S.local_u0()
-    rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    rk = hpo.rk_type_of(case)
     for _ in range(3):
         O.time_step(u, float(case.solver["dt"]), rk)
     same(S.interior(u), S.interior(z["steps3_u"]), "u after 3 steps")
@@ -129,6 +129,12 @@ def _live_cases():
         cases.ns3d_rising_bubble((10, 14, 12), "js", scheme="cupw5"),
         cases.euler1d_sod(101, "js", interp="components", upwinding="llf-char", scheme="cupw5"),
         cases.ns3d_turbulence((12, 10, 14), "js", viscous=False, upwinding="roe", scheme="upw5"),
+        # the other explicit RK tableaux (TimeExplicitRKInitialize.c:27-79) and forward Euler (TimeForwardEuler.c)
+        cases.with_time_scheme(cases.linear_advection_sine(96, "js"), "rk", "1fe"),
+        cases.with_time_scheme(cases.euler1d_sod(101, "mapped"), "rk", "22"),
+        cases.with_time_scheme(cases.ns2d_vortex((24, 40), "yc"), "rk", "33"),
+        cases.with_time_scheme(cases.ns3d_rising_bubble((10, 14, 12), "z"), "rk", "tvdrk3"),
+        cases.with_time_scheme(cases.ns3d_turbulence((12, 10, 14), "mapped"), "euler"),
     ]
 
 
@@ -151,7 +157,7 @@ def test_oracle_matches_reference_live(case, exe):
     o = run_reference(case, "steps", [2], exe=exe)
     u = S.local_u0()
     for _ in range(2):
-        O.time_step(u, float(case.solver["dt"]), hpo.RK_TYPES[case.solver["time_scheme_type"]])
+        O.time_step(u, float(case.solver["dt"]), hpo.rk_type_of(case))
     same(S.interior(u), S.interior(o["ufinal"]["data"]), f"{exe} u after 2 steps")
 
 
@@ -172,7 +178,7 @@ def test_error_norms_match_reference_live(case, tmp_path):
     O = hpo.Oracle(S)
     u = S.local_u0()
     for _ in range(2):
-        O.time_step(u, float(case.solver["dt"]), hpo.RK_TYPES[case.solver["time_scheme_type"]])
+        O.time_step(u, float(case.solver["dt"]), hpo.rk_type_of(case))
     uex = S.local_u0()
     npts = float(np.prod(S.dim))
     n, e = O.norm_sums(uex), O.norm_sums(uex, u)

@@ -10,7 +10,7 @@ from oracle import hpo
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 for case in (cases.euler1d_sod(101, "js"), cases.ns3d_turbulence((16, 12, 10), "js", viscous=False, upwinding="roe")):
     S = hpo.Setup(case); O = hpo.Oracle(S)
-    dt = float(case.solver["dt"]); rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    dt = float(case.solver["dt"]); rk = hpo.rk_type_of(case)
     u_ref = S.local_u0()
     for _ in range(5):
         O.time_step(u_ref, dt, rk)

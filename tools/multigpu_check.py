@@ -31,7 +31,7 @@ def diagnostics_and_io(rank, world, local, iproc):
     one = cases.ns3d_density_wave((26, 24, 28), "js")
     S1 = hpo.Setup(one)
     O1 = hpo.Oracle(S1)
-    dt, rk = float(case.solver["dt"]), hpo.RK_TYPES[case.solver["time_scheme_type"]]
+    dt, rk = float(case.solver["dt"]), hpo.rk_type_of(case)
     d = [tempfile.mkdtemp(prefix="hpb_mg_") if rank == 0 else None]
     dist.broadcast_object_list(d, src=0)
     os.chdir(d[0])
@@ -96,7 +96,7 @@ def main():
                 scale = max(np.abs(r).max() for r in rhs_ref)
                 e_rhs = np.abs(rhs - rhs_ref[rank]).max() / scale
                 dt = float(case.solver["dt"])
-                rk = hpo.RK_TYPES[case.solver["time_scheme_type"]]
+                rk = hpo.rk_type_of(case)
                 u_ref = MO.local_u0()
                 for _ in range(2):
                     MO.time_step(u_ref, dt, rk)
