@@ -144,7 +144,7 @@ def euler1d_sod(n: int = 201, weno: str = "js", interp: str = "characteristic",
 
 # ------------------------------------------------------------------------------------- C3
 def ns2d_vortex(n: Sequence[int] = (1024, 1024), weno: str = "js", tstype: str = "ssprk3",
-                iproc=None, scheme: str = "weno5") -> Case:
+                iproc=None, scheme: str = "weno5", upwinding: str = "rusanov", interp: str = "components") -> Case:
     nx, ny = n
     L = 10.0
     x = np.arange(nx, dtype=np.float64) * (L / nx)
@@ -160,11 +160,12 @@ def ns2d_vortex(n: Sequence[int] = (1024, 1024), weno: str = "js", tstype: str =
     p = rho ** gamma
     u = np.stack([rho, rho * vx, rho * vy, p / (gamma - 1.0) + 0.5 * rho * (vx * vx + vy * vy)], axis=-1)
     return Case(
-        name=f"c3_vortex_{nx}x{ny}_{weno}" + _sfx(scheme),
+        name=f"c3_vortex_{nx}x{ny}_{weno}" + ("" if upwinding == "rusanov" else "_" + upwinding)
+             + ("" if interp == "components" else "_char") + _sfx(scheme),
         solver=_solver(2, 4, [nx, ny], "navierstokes2d", ts="rk", tstype=tstype, dt=0.005 * 1024.0 / max(nx, ny),
-                       iproc=iproc, scheme=scheme),
+                       iproc=iproc, scheme=scheme, interp=interp),
         boundary=_zones(2, "periodic", [-1e3, -1e3], [1e3, 1e3]),
-        physics={"gamma": gamma, "upwinding": "rusanov"}, weno=weno_inp(weno), x=[x, y], u0=u)
+        physics={"gamma": gamma, "upwinding": upwinding}, weno=weno_inp(weno), x=[x, y], u0=u)
 
 
 # ------------------------------------------------------------------------------------- C4

@@ -61,12 +61,9 @@ int hpb_setup_host(hpb_solver* h)
   if (c.weno_type < 0 || c.weno_type > 3) return hpb_fail(HPB_ERR_INVALID, "unknown WENO weight type %d", c.weno_type);
   if (c.rk_type < HPB_RK_44 || c.rk_type > HPB_RK_33)
     return hpb_fail(HPB_ERR_INVALID, "time_scheme_type %d not supported (rk 1fe, 22, 33, 44, ssprk3)", c.rk_type);
-  if (c.model == HPB_MODEL_NS2D && c.upwind != HPB_UPWIND_RUSANOV)
-    return hpb_fail(HPB_ERR_INVALID, "navierstokes2d: only rusanov upwinding is implemented on the device");
-  if ((c.model == HPB_MODEL_NS3D || c.model == HPB_MODEL_EULER1D) && (c.upwind < HPB_UPWIND_ROE || c.upwind > HPB_UPWIND_LLF))
+  if ((c.model == HPB_MODEL_NS3D || c.model == HPB_MODEL_NS2D || c.model == HPB_MODEL_EULER1D) &&
+      (c.upwind < HPB_UPWIND_ROE || c.upwind > HPB_UPWIND_LLF))
     return hpb_fail(HPB_ERR_INVALID, "upwinding %d not implemented (roe, rusanov, rf-char, llf-char)", c.upwind);
-  if (c.model == HPB_MODEL_NS2D && c.interp_char)
-    return hpb_fail(HPB_ERR_INVALID, "navierstokes2d: characteristic WENO5 is not implemented on the device");
   const bool has_grav = (c.gravity[0] != 0.0 || c.gravity[1] != 0.0 || c.gravity[2] != 0.0);
   if (has_grav && c.model != HPB_MODEL_NS3D)
     return hpb_fail(HPB_ERR_INVALID, "gravity is implemented for navierstokes3d only");

@@ -156,7 +156,7 @@ k_iface(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict_
 
   double fL[NV], fR[NV], uL[NV], uR[NV];
   double wLF[NV][3], wRF[NV][3];
-  const bool use_char = ph.interp_char && (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D);
+  const bool use_char = ph.interp_char && (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS2D || MODEL == HPB_MODEL_NS3D);
 
   if (!use_char) {
 #pragma unroll
@@ -739,7 +739,7 @@ __global__ void k_weights(Geom G, Phys ph, const double* __restrict__ fC, const 
 #pragma unroll
     for (int v = 0; v < NV; v++) { U[k][v] = u[v * G.npg + p]; F[k][v] = fC[v * G.npg + p]; }
   }
-  const bool use_char = ph.interp_char && (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D);
+  const bool use_char = ph.interp_char && (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS2D || MODEL == HPB_MODEL_NS3D);
   double L[NV * NV];
   if (use_char) {
     double uavg[NV], lam[NV], R[NV * NV];
@@ -794,7 +794,7 @@ __global__ void k_interp(Geom G, Phys ph, const double* __restrict__ fC, const d
   for (int k = 0; k < 5; k++)
 #pragma unroll
     for (int v = 0; v < NV; v++) S[k][v] = fC[v * G.npg + ps[k]];
-  const bool use_char = ph.interp_char && (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D);
+  const bool use_char = ph.interp_char && (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS2D || MODEL == HPB_MODEL_NS3D);
   double out[NV];
   if (!use_char) {
 #pragma unroll

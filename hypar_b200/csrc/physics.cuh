@@ -221,6 +221,68 @@ HPB_DEV void ns3d_eigen(double ga, const double* u, int dir, double* lam, double
   }
 }
 
+// NS2D: navierstokes2d.h:213-400 (_NavierStokes2DEigenvalues_ / LeftEigenvectors_ / RightEigenvectors_), written out
+// with the reference's nx, ny so that every entry rounds as there. Ordering: x: (v-a, v+a, shear, entropy);
+// y: (v-a, shear, v+a, entropy).
+HPB_DEV void ns2d_eigen(double ga, const double* u, int dir, double* lam, double* L, double* R)
+{
+  const double ga_minus_one = ga - 1.0;
+  const double rho = u[0], vx = u[1] / rho, vy = u[2] / rho, e = u[3];
+  const double vsq = (vx * vx) + (vy * vy);
+  const double P = (e - 0.5 * rho * vsq) * (ga - 1.0);
+  const double ek = 0.5 * (vx * vx + vy * vy);
+  const double a = sqrt(ga * P / rho);
+  const double h0 = a * a / ga_minus_one + ek;
+  double nx = 0, ny = 0, un;
+  if (dir == 0) {
+    un = vx; nx = 1.0;
+    lam[0] = un - a; lam[1] = un + a; lam[2] = un; lam[3] = un;
+    L[0]  = (ga_minus_one * ek + a * un) / (2 * a * a);
+    L[1]  = ((-ga_minus_one) * vx - a * nx) / (2 * a * a);
+    L[2]  = ((-ga_minus_one) * vy - a * ny) / (2 * a * a);
+    L[3]  = ga_minus_one / (2 * a * a);
+    L[12] = (a * a - ga_minus_one * ek) / (a * a);
+    L[13] = (ga_minus_one * vx) / (a * a);
+    L[14] = (ga_minus_one * vy) / (a * a);
+    L[15] = (-ga_minus_one) / (a * a);
+    L[4]  = (ga_minus_one * ek - a * un) / (2 * a * a);
+    L[5]  = ((-ga_minus_one) * vx + a * nx) / (2 * a * a);
+    L[6]  = ((-ga_minus_one) * vy + a * ny) / (2 * a * a);
+    L[7]  = ga_minus_one / (2 * a * a);
+    L[8]  = (vy - un * ny) / nx;
+    L[9]  = ny;
+    L[10] = (ny * ny - 1.0) / nx;
+    L[11] = 0.0;
+    R[0] = 1.0; R[4] = vx - a * nx; R[8]  = vy - a * ny; R[12] = h0 - a * un;
+    R[3] = 1.0; R[7] = vx;          R[11] = vy;          R[15] = ek;
+    R[1] = 1.0; R[5] = vx + a * nx; R[9]  = vy + a * ny; R[13] = h0 + a * un;
+    R[2] = 0.0; R[6] = ny;          R[10] = -nx;         R[14] = vx * ny - vy * nx;
+  } else {
+    un = vy; ny = 1.0;
+    lam[0] = un - a; lam[1] = un; lam[2] = un + a; lam[3] = un;
+    L[0]  = (ga_minus_one * ek + a * un) / (2 * a * a);
+    L[1]  = ((1.0 - ga) * vx - a * nx) / (2 * a * a);
+    L[2]  = ((1.0 - ga) * vy - a * ny) / (2 * a * a);
+    L[3]  = ga_minus_one / (2 * a * a);
+    L[12] = (a * a - ga_minus_one * ek) / (a * a);
+    L[13] = ga_minus_one * vx / (a * a);
+    L[14] = ga_minus_one * vy / (a * a);
+    L[15] = (1.0 - ga) / (a * a);
+    L[8]  = (ga_minus_one * ek - a * un) / (2 * a * a);
+    L[9]  = ((1.0 - ga) * vx + a * nx) / (2 * a * a);
+    L[10] = ((1.0 - ga) * vy + a * ny) / (2 * a * a);
+    L[11] = ga_minus_one / (2 * a * a);
+    L[4]  = (un * nx - vx) / ny;
+    L[5]  = (1.0 - nx * nx) / ny;
+    L[6]  = -nx;
+    L[7]  = 0;
+    R[0] = 1.0; R[4] = vx - a * nx; R[8]  = vy - a * ny; R[12] = h0 - a * un;
+    R[3] = 1.0; R[7] = vx;          R[11] = vy;          R[15] = ek;
+    R[2] = 1.0; R[6] = vx + a * nx; R[10] = vy + a * ny; R[14] = h0 + a * un;
+    R[1] = 0;   R[5] = ny;          R[9]  = -nx;         R[13] = vx * ny - vy * nx;
+  }
+}
+
 // eigenvalues only (_Euler1DEigenvalues_, _NavierStokes3DEigenvalues_ navierstokes3d.h:254-278): same ordering as eigen()
 template <int MODEL>
 HPB_DEV void eigenvalues(const Phys& ph, const double* u, int dir, double* lam)
@@ -230,7 +292,10 @@ HPB_DEV void eigenvalues(const Phys& ph, const double* u, int dir, double* lam)
   flowvar<MODEL>(u, ph.gamma, rho, vel, e, P);
   const double c = sqrt(ph.gamma * P / rho);
   if (MODEL == HPB_MODEL_EULER1D) { lam[0] = vel[0]; lam[1] = vel[0] - c; lam[2] = vel[0] + c; }
-  else {
+  else if (MODEL == HPB_MODEL_NS2D) {          // navierstokes2d.h:213-240
+    const double vn = (dir == 0) ? vel[0] : vel[1];
+    lam[0] = vn - c; lam[1] = (dir == 0) ? vn + c : vn; lam[2] = (dir == 0) ? vn : vn + c; lam[3] = vn;
+  } else {
     const double vn = (dir == 0) ? vel[0] : (dir == 1 ? vel[1] : vel[2]);
 #pragma unroll
     for (int k = 0; k < NV; k++) lam[k] = (k == dir + 1) ? (vn - c) : ((k == NV - 1) ? (vn + c) : vn);
@@ -242,6 +307,7 @@ HPB_DEV void eigen(const Phys& ph, const double* u, int dir, double* lam, double
 {
   if (MODEL == HPB_MODEL_EULER1D) e1d_eigen(ph.gamma, u, lam, L, R);
   else if (MODEL == HPB_MODEL_NS3D) ns3d_eigen(ph.gamma, u, dir, lam, L, R);
+  else if (MODEL == HPB_MODEL_NS2D) ns2d_eigen(ph.gamma, u, dir, lam, L, R);
 }
 
 // ---- Upwind. Inputs: reconstructed fL,fR,uL,uR at the interface, raw u of the two adjacent cells,
@@ -281,9 +347,11 @@ HPB_DEV void upwind_fn(const Phys& ph, int dir, const double* fL, const double* 
     // characteristic-based Roe-fixed / local Lax-Friedrichs: NavierStokes3DUpwind.c:140-237, :244-330;
     // Euler1DUpwind.c:115-205, :212-286. NavierStokes3D takes the Roe average and the one-sided eigenvalues
     // from the RECONSTRUCTED interface states uL, uR; Euler1D from the two adjacent cells, with kappa.
-    if (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D) {
+    // NavierStokes2D (NavierStokes2DUpwind.c:120-196, :223-300): RF like NavierStokes3D (interface states, no kappa);
+    // LLF from the two adjacent cells, kappa on the FIRST characteristic field only (sic).
+    if (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D || MODEL == HPB_MODEL_NS2D) {
       double eigL[NV], eigC[NV], eigR[NV], L[NV * NV], R[NV * NV], uroe[NV];
-      if (MODEL == HPB_MODEL_NS3D) {
+      if (MODEL == HPB_MODEL_NS3D || (MODEL == HPB_MODEL_NS2D && ph.upwind == HPB_UPWIND_RF)) {
         roe_average<MODEL>(ph, uL, uR, uroe);
         eigenvalues<MODEL>(ph, uL, dir, eigL);
         eigenvalues<MODEL>(ph, uR, dir, eigR);
@@ -312,6 +380,7 @@ HPB_DEV void upwind_fn(const Phys& ph, int dir, const double* fL, const double* 
         else {
           double alpha = hpb_max3(hpb_abs(eigL[k]), hpb_abs(eigC[k]), hpb_abs(eigR[k]));
           if (MODEL == HPB_MODEL_EULER1D) alpha = kappa * alpha;
+          if (MODEL == HPB_MODEL_NS2D && ph.upwind == HPB_UPWIND_LLF && k == 0) alpha = kappa * alpha;
           fc[k] = 0.5 * (gL[k] + gR[k] + alpha * (wL[k] - wR[k]));
         }
       }
@@ -324,7 +393,7 @@ HPB_DEV void upwind_fn(const Phys& ph, int dir, const double* fL, const double* 
       }
     }
   } else {
-    if (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D) {
+    if (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS3D || MODEL == HPB_MODEL_NS2D) {
       double lam[NV], L[NV * NV], R[NV * NV];
       eigen<MODEL>(ph, uavg, dir, lam, L, R);
       if (MODEL == HPB_MODEL_EULER1D) {
@@ -333,8 +402,10 @@ HPB_DEV void upwind_fn(const Phys& ph, int dir, const double* fL, const double* 
       } else {
         const double delta = 0.000001, delta2 = delta * delta;
 #pragma unroll
-        for (int k = 0; k < NV; k++)
+        for (int k = 0; k < NV; k++) {
           lam[k] = (hpb_abs(lam[k]) < delta ? (lam[k] * lam[k] + delta2) / (2 * delta) : hpb_abs(lam[k]));
+          if (MODEL == HPB_MODEL_NS2D) lam[k] = kappa * lam[k];        // NavierStokes2DUpwind.c:86-91
+        }
       }
       // udiss = (R (|D| L)) udiff, multiplied out in the reference's own order (MatMult, MatMult, MatVecMult:
       // NavierStokes3DUpwind.c:104-106, Euler1DUpwind.c:84-86) so that the result carries its rounding

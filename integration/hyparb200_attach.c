@@ -218,7 +218,7 @@ int hyparb200_attach(void *sims, int nsims)
     NavierStokes2D *p = (NavierStokes2D*) s->physics;
     c.model = HPB_MODEL_NS2D;  c.gamma = p->gamma;  c.Pr = p->Pr;  c.Minf = p->Minf;
     c.Re = (p->Re > 0 ? p->Re * p->Minf : p->Re);   /* NavierStokes2DInitialize.c:205 */
-    c.upwind = !strcmp(p->upw_choice, _RUSANOV_) ? HPB_UPWIND_RUSANOV : !strcmp(p->upw_choice, _ROE_) ? HPB_UPWIND_ROE : -1;
+    c.upwind = upwind_choice(p->upw_choice);
     if (p->grav_x != 0.0 || p->grav_y != 0.0) { fprintf(stderr, "hyparb200_attach: navierstokes2d with gravity is not on the B200 path\n"); return 1; }
   } else if (!strcmp(s->model, _EULER_1D_)) {
     Euler1D *p = (Euler1D*) s->physics;

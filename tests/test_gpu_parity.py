@@ -76,6 +76,12 @@ def _cases():
     C.append(cases.with_time_scheme(cases.ns2d_vortex((40, 28), "yc"), "rk", "33"))
     C.append(cases.with_time_scheme(cases.ns3d_rising_bubble((12, 16, 10), "z"), "rk", "tvdrk3"))
     C.append(cases.with_time_scheme(cases.ns3d_turbulence((16, 12, 10), "mapped"), "euler"))
+    # NavierStokes2D Roe / rf-char / llf-char upwinding and characteristic reconstruction
+    C.append(cases.ns2d_vortex((40, 28), "yc", upwinding="roe"))
+    C.append(cases.ns2d_vortex((28, 40), "js", upwinding="rf-char"))
+    C.append(cases.ns2d_vortex((32, 24), "mapped", upwinding="llf-char", interp="characteristic"))
+    C.append(cases.ns2d_vortex((24, 32), "z", upwinding="rusanov", interp="characteristic"))
+    C.append(cases.ns2d_vortex((24, 20), "js", upwinding="roe", scheme="crweno5"))
     return C
 
 
@@ -158,7 +164,7 @@ def test_rhs_parity(need_gpu, case):
 
 STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CASES[30], CASES[32],
               CASES[34], CASES[36], CASES[37], CASES[38], CASES[40], CASES[41], CASES[43], CASES[45],
-              CASES[46], CASES[47], CASES[48], CASES[49], CASES[50]]
+              CASES[46], CASES[47], CASES[48], CASES[49], CASES[50], CASES[51], CASES[53]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)
@@ -215,7 +221,8 @@ def test_time_steps_parity(need_gpu, case):
 
 
 @pytest.mark.parametrize("case", [CASES[4], CASES[12], CASES[16], CASES[20], CASES[26],
-                                  CASES[35], CASES[37], CASES[40], CASES[42], CASES[44]], ids=lambda c: c.name)
+                                  CASES[35], CASES[37], CASES[40], CASES[42], CASES[44], CASES[51], CASES[52], CASES[53]],
+                         ids=lambda c: c.name)
 def test_function_pointer_pieces(need_gpu, case):
     """FFunction, UFunction, SetInterpLimiterVar, InterpolateInterfacesHyp, Upwind,
     FirstDerivativePar, SecondDerivativePar, ComputeCFL -- one by one against the oracle."""

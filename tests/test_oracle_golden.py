@@ -40,7 +40,7 @@ def same(a, b, what):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 26
+    assert len(GOLDEN) >= 29
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -129,6 +129,12 @@ def _live_cases():
         cases.ns3d_rising_bubble((10, 14, 12), "js", scheme="cupw5"),
         cases.euler1d_sod(101, "js", interp="components", upwinding="llf-char", scheme="cupw5"),
         cases.ns3d_turbulence((12, 10, 14), "js", viscous=False, upwinding="roe", scheme="upw5"),
+        # NavierStokes2D Roe / rf-char / llf-char upwinding and characteristic reconstruction
+        cases.ns2d_vortex((24, 40), "yc", upwinding="roe"),
+        cases.ns2d_vortex((24, 20), "js", upwinding="rf-char"),
+        cases.ns2d_vortex((20, 24), "mapped", upwinding="llf-char", interp="characteristic"),
+        cases.ns2d_vortex((24, 20), "z", upwinding="rusanov", interp="characteristic"),
+        cases.ns2d_vortex((24, 20), "js", upwinding="roe", scheme="crweno5"),
         # the other explicit RK tableaux (TimeExplicitRKInitialize.c:27-79) and forward Euler (TimeForwardEuler.c)
         cases.with_time_scheme(cases.linear_advection_sine(96, "js"), "rk", "1fe"),
         cases.with_time_scheme(cases.euler1d_sod(101, "mapped"), "rk", "22"),

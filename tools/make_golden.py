@@ -51,6 +51,10 @@ GOLDEN = [
     ("c5b_bubble_crweno_yc", "ns3d_rising_bubble", dict(n=(12, 16, 10), weno="yc", scheme="crweno5"), "hypar_ref_mpi1", True),
     ("c5a_denswave_cupw5", "ns3d_density_wave", dict(n=(12, 10, 8), weno="js", scheme="cupw5"), "hypar_ref", True),
     ("c3_vortex_cupw5", "ns2d_vortex", dict(n=(28, 36), weno="js", scheme="cupw5"), "hypar_ref", False),
+    # NavierStokes2D: Roe (+ Harten fix), characteristic Roe-fixed / local Lax-Friedrichs, characteristic WENO5
+    ("c3_vortex_js_roe", "ns2d_vortex", dict(n=(20, 16), weno="js", upwinding="roe"), "hypar_ref", True),
+    ("c3_vortex_mapped_char_rf", "ns2d_vortex", dict(n=(24, 20), weno="mapped", upwinding="rf-char", interp="characteristic"), "hypar_ref_mpi1", True),
+    ("c3_vortex_z_llf", "ns2d_vortex", dict(n=(20, 24), weno="z", upwinding="llf-char"), "hypar_ref", False),
     ("c2_sod_upw5_comp_rusanov", "euler1d_sod", dict(n=101, weno="js", interp="components", upwinding="rusanov", scheme="upw5"), "hypar_ref", True),
 ]
 
