@@ -168,6 +168,38 @@ def ns2d_vortex(n: Sequence[int] = (1024, 1024), weno: str = "js", tstype: str =
         physics={"gamma": gamma, "upwinding": upwinding}, weno=weno_inp(weno), x=[x, y], u0=u)
 
 
+def ns2d_rising_bubble(n: Sequence[int] = (64, 64), weno: str = "js", tstype: str = "ssprk3", dt: float = 0.01,
+                       iproc=None, hb: int = 2, upwinding: str = "rusanov", scheme: str = "weno5",
+                       interp: str = "components") -> Case:
+    """2-D rising thermal bubble (Examples/2D/NavierStokes2D/RisingThermalBubble/aux/init.c:80-115): slip walls,
+    gravity (0, 9.8), HB = 2 hydrostatic balance, well-balanced source term."""
+    gamma, R, g = 1.4, 287.058, 9.8
+    rho_ref, p_ref = 1.1612055171196529, 100000.0
+    L = 1000.0
+    xs = [np.arange(n[d], dtype=np.float64) * (L / (n[d] - 1)) for d in range(2)]
+    X, Y = np.meshgrid(xs[0], xs[1], indexing="xy")          # shape (ny, nx): dim 0 fastest
+    T_ref = p_ref / (R * rho_ref)
+    Cp = gamma / (gamma - 1.0) * R
+    tc, xc, yc, rc = 0.5, 500.0, 350.0, 250.0
+    r = np.sqrt((X - xc) ** 2 + (Y - yc) ** 2)
+    dtheta = np.where(r > rc, 0.0, 0.5 * tc * (1.0 + np.cos(np.pi * r / rc)))
+    theta = T_ref + dtheta
+    Pexner = 1.0 - (g * Y) / (Cp * T_ref)
+    rho = (p_ref / (R * theta)) * Pexner ** (1.0 / (gamma - 1.0))
+    E = rho * (R / (gamma - 1.0)) * theta * Pexner
+    zero = np.zeros_like(rho)
+    u = np.stack([rho, zero, zero, E], axis=-1)
+    return Case(
+        name=f"c3g_bubble2d_{n[0]}x{n[1]}_{weno}_hb{hb}" + ("" if upwinding == "rusanov" else "_" + upwinding)
+             + ("" if interp == "components" else "_char") + _sfx(scheme),
+        solver=_solver(2, 4, n, "navierstokes2d", ts="rk", tstype=tstype, dt=dt, iproc=iproc,
+                       par_type="nonconservative-2stage", par_scheme="4", scheme=scheme, interp=interp),
+        boundary=_zones(2, "slip-wall", [0.0] * 2, [L] * 2, wall_velocity=[0.0, 0.0]),
+        physics={"gamma": gamma, "upwinding": upwinding, "gravity": [0.0, g],
+                 "rho_ref": rho_ref, "p_ref": p_ref, "R": R, "HB": hb},
+        weno=weno_inp(weno), x=xs, u0=u)
+
+
 # ------------------------------------------------------------------------------------- C4
 def _grid3(n, L):
     xs = [np.arange(n[d], dtype=np.float64) * (L[d] / n[d]) for d in range(3)]

@@ -65,10 +65,15 @@ int hpb_setup_host(hpb_solver* h)
       (c.upwind < HPB_UPWIND_ROE || c.upwind > HPB_UPWIND_LLF))
     return hpb_fail(HPB_ERR_INVALID, "upwinding %d not implemented (roe, rusanov, rf-char, llf-char)", c.upwind);
   const bool has_grav = (c.gravity[0] != 0.0 || c.gravity[1] != 0.0 || c.gravity[2] != 0.0);
-  if (has_grav && c.model != HPB_MODEL_NS3D)
-    return hpb_fail(HPB_ERR_INVALID, "gravity is implemented for navierstokes3d only");
-  if (has_grav && c.upwind != HPB_UPWIND_RUSANOV)      // NavierStokes3DInitialize.c:371-378
+  if (has_grav && c.model != HPB_MODEL_NS3D && c.model != HPB_MODEL_NS2D)
+    return hpb_fail(HPB_ERR_INVALID, "gravity is implemented for navierstokes2d and navierstokes3d only");
+  if (has_grav && c.model == HPB_MODEL_NS3D && c.upwind != HPB_UPWIND_RUSANOV)      // NavierStokes3DInitialize.c:371-378
     return hpb_fail(HPB_ERR_INVALID, "rusanov upwinding is needed for flows with gravitational forces");
+  if (has_grav && c.model == HPB_MODEL_NS2D && c.upwind != HPB_UPWIND_RUSANOV && c.upwind != HPB_UPWIND_ROE &&
+      c.upwind != HPB_UPWIND_LLF)                                                   // NavierStokes2DInitialize.c:207-216
+    return hpb_fail(HPB_ERR_INVALID, "llf-char, roe or rusanov upwinding is needed for flows with gravitational forces");
+  if (c.model == HPB_MODEL_NS2D && c.gravity[2] != 0.0)
+    return hpb_fail(HPB_ERR_INVALID, "navierstokes2d: gravity has two components");
   if (c.model == HPB_MODEL_LINEAR_ADR && c.par_scheme != 2 && c.par_scheme != 4)
     return hpb_fail(HPB_ERR_INVALID, "par_space_scheme %d not supported (2, 4)", c.par_scheme);
   if (c.hyp_scheme < HPB_SCHEME_WENO5 || c.hyp_scheme > HPB_SCHEME_UPW5)
@@ -204,34 +209,41 @@ int hpb_setup_host(hpb_solver* h)
   for (int d = 0; d < 3; d++) P.grav[d] = c.gravity[d];
   for (int i = 0; i < 15; i++) { P.adv[i] = c.advection[i]; P.diff[i] = c.diffusion[i]; }
 
-  // ---- gravity field (NS3D); 1.0 everywhere for the other models
+  // ---- gravity field (NavierStokes3DGravityField.c:33-152; NavierStokes2DGravityField.c:33-150 is the same with
+  // (gx x + gy y) and y as the vertical of HB 3); 1.0 everywhere for the other models
   h->gravf_h.assign((size_t)G.npg, 1.0);
   h->gravg_h.assign((size_t)G.npg, 1.0);
-  if (c.model == HPB_MODEL_NS3D) {
+  if (c.model == HPB_MODEL_NS3D || c.model == HPB_MODEL_NS2D) {
+    const bool is3 = (c.model == HPB_MODEL_NS3D);
     double p0 = c.p_ref, rho0 = c.rho_ref, RT = p0 / rho0, gamma = c.gamma, R = c.R;
     double Cp = gamma * R / (gamma - 1.0), T0 = p0 / (rho0 * R);
     double gx = c.gravity[0], gy = c.gravity[1], gz = c.gravity[2], Nbv = c.N_bv;
-    if (c.HB == 3 && (gx != 0 || gy != 0))
+    if (c.HB == 3 && is3 && (gx != 0 || gy != 0))
       return hpb_fail(HPB_ERR_INVALID, "HB = 3 is implemented only for gravity force along the z-coordinate");
+    if (c.HB == 3 && !is3 && gx != 0)
+      return hpb_fail(HPB_ERR_INVALID, "HB = 3 is implemented only for gravity force along the y-coordinate");
+    const double gv = is3 ? gz : gy;          // vertical component
     const double* X = h->x_h.data();
     for (int k = 0; k < G.P[2]; k++) for (int j = 0; j < G.P[1]; j++) for (int i = 0; i < G.P[0]; i++) {
       size_t p = i + (size_t)G.P[0] * (j + (size_t)G.P[1] * k);
-      double xc = X[G.xoff[0] + i], yc = X[G.xoff[1] + j], zc = X[G.xoff[2] + k];
+      double xc = X[G.xoff[0] + i], yc = X[G.xoff[1] + j], zc = is3 ? X[G.xoff[2] + k] : 0.0;
+      const double phi = is3 ? (gx*xc+gy*yc+gz*zc) : (gx*xc+gy*yc);
+      const double vc = is3 ? zc : yc;
       double f, gg;
       if (c.HB == 1) {
-        f  = exp( (gx*xc+gy*yc+gz*zc)/RT);
-        gg = exp(-(gx*xc+gy*yc+gz*zc)/RT);
+        f  = exp( phi/RT);
+        gg = exp(-phi/RT);
       } else if (c.HB == 2) {
-        f  = raiseto((1.0-(gx*xc+gy*yc+gz*zc)/(Cp*T0)), (-1.0 /(gamma-1.0)));
-        gg = raiseto((1.0-(gx*xc+gy*yc+gz*zc)/(Cp*T0)), (gamma/(gamma-1.0)));
+        f  = raiseto((1.0-phi/(Cp*T0)), (-1.0 /(gamma-1.0)));
+        gg = raiseto((1.0-phi/(Cp*T0)), (gamma/(gamma-1.0)));
       } else if (c.HB == 3) {
-        double Pexner = 1 + ((gz*gz)/(Cp*T0*Nbv*Nbv)) * (exp(-(Nbv*Nbv/gz)*zc)-1.0);
-        f  = raiseto(Pexner, (-1.0 /(gamma-1.0))) * exp(Nbv*Nbv*zc/gz);
+        double Pexner = 1 + ((gv*gv)/(Cp*T0*Nbv*Nbv)) * (exp(-(Nbv*Nbv/gv)*vc)-1.0);
+        f  = raiseto(Pexner, (-1.0 /(gamma-1.0))) * exp(Nbv*Nbv*vc/gv);
         gg = raiseto(Pexner, (gamma/(gamma-1.0)));
       } else { f = gg = 1.0; }
       h->gravf_h[p] = f; h->gravg_h[p] = gg;
     }
-    for (int d = 0; d < 3; d++) for (int side = 0; side < 2; side++) {
+    for (int d = 0; d < G.ndims; d++) for (int side = 0; side < 2; side++) {
       if (side == 0 && h->ip[d] != 0) continue;
       if (side == 1 && h->ip[d] != c.iproc[d] - 1) continue;
       int b[3] = { G.N[0], G.N[1], G.N[2] };
@@ -240,8 +252,9 @@ int hpb_setup_host(hpb_solver* h)
         int ib[3] = { i, j, k }, i1[3] = { i, j, k }, i2[3] = { i, j, k };
         if (side == 0) { i1[d] = ib[d] - g;        i2[d] = g - 1 - ib[d]; }
         else           { i1[d] = ib[d] + G.N[d];   i2[d] = G.N[d] - 1 - ib[d]; }
-        size_t p1 = (i1[0]+g) + (size_t)G.P[0] * ((i1[1]+g) + (size_t)G.P[1] * (i1[2]+g));
-        size_t p2 = (i2[0]+g) + (size_t)G.P[0] * ((i2[1]+g) + (size_t)G.P[1] * (i2[2]+g));
+        const int g2 = (G.ndims > 2) ? g : 0;     // no ghost layers along an unused third dimension
+        size_t p1 = (i1[0]+g) + (size_t)G.P[0] * ((i1[1]+g) + (size_t)G.P[1] * (i1[2]+g2));
+        size_t p2 = (i2[0]+g) + (size_t)G.P[0] * ((i2[1]+g) + (size_t)G.P[1] * (i2[2]+g2));
         h->gravf_h[p1] = h->gravf_h[p2]; h->gravg_h[p1] = h->gravg_h[p2];
       }
     }

@@ -225,7 +225,7 @@ k_iface(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict_
 #pragma unroll
   for (int v = 0; v < NV; v++) fI[v * ni + q] = fhat[v];
 
-  if (MODEL == HPB_MODEL_NS3D && sI != nullptr) {
+  if ((MODEL == HPB_MODEL_NS3D || MODEL == HPB_MODEL_NS2D) && sI != nullptr) {
     // source function G_j = g_grav_j * (0, d_x, d_y, d_z, 1): only components dir+1 and 4 are non-zero
     const int vm = dir + 1;
     const double sLm = weno_combine(wLF[vm][0], wLF[vm][1], wLF[vm][2], GG[0], GG[1], GG[2], GG[3], GG[4]);
@@ -280,7 +280,7 @@ __global__ void k_ns3d_source(Geom G, Phys ph, const double* __restrict__ dxinv,
   const double f = gf[p];
   const double tm = rho * ph.RT, te = rho * ph.RT * vd;
   out[(1 + dir) * G.npg + p] += ((tm * f) * (sI[q1 + qs] - sI[q1]) * dxi);
-  out[4 * G.npg + p]         += ((te * f) * (sI[ni + q1 + qs] - sI[ni + q1]) * dxi);
+  out[(long long)(G.nvars - 1) * G.npg + p] += ((te * f) * (sI[ni + q1 + qs] - sI[ni + q1]) * dxi);   // energy: last component
 }
 
 // ------------------------------------------------------------------------------------------
@@ -966,20 +966,18 @@ __global__ void k_ns3d_source_fn(Geom G, const double* __restrict__ gg, int dir,
   if (p >= G.npg) return;
   const double g = gg[p];
   S[p] = 0.0;
-  S[1 * G.npg + p] = g * (dir == 0);
-  S[2 * G.npg + p] = g * (dir == 1);
-  S[3 * G.npg + p] = g * (dir == 2);
-  S[4 * G.npg + p] = g;
+  for (int k = 0; k < G.ndims; k++) S[(long long)(1 + k) * G.npg + p] = g * (dir == k);
+  S[(long long)(G.nvars - 1) * G.npg + p] = g;
 }
 // NavierStokes3DSource.c:174-205: interface value = average of the left- and right-biased reconstructions;
 // only components dir+1 and 4 are consumed (k_ns3d_source)
-__global__ void k_ns3d_source_avg(long long ni, int dir, const double* __restrict__ SL, const double* __restrict__ SR,
+__global__ void k_ns3d_source_avg(long long ni, int dir, int ve, const double* __restrict__ SL, const double* __restrict__ SR,
                                   double* __restrict__ sI)
 {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= ni) return;
   sI[q]      = 0.5 * (SL[(1 + dir) * ni + q] + SR[(1 + dir) * ni + q]);
-  sI[ni + q] = 0.5 * (SL[4 * ni + q] + SR[4 * ni + q]);
+  sI[ni + q] = 0.5 * (SL[ve * ni + q] + SR[ve * ni + q]);          // ve: the energy component
 }
 // boundary-face fluxes from a stored interface array (conservation bookkeeping of the piecewise path)
 __global__ void k_face_from_iface(Geom G, int dir, int face, const double* __restrict__ fI, double* __restrict__ out)
@@ -1189,7 +1187,7 @@ void hyperbolic_pieces(hpb_solver* h, const double* u, double* out, bool negate,
       k_ns3d_source_fn<<<(unsigned)((G.npg + 255) / 256), 256, 0, h->stream>>>(G, h->d_gravg, d, fC); LAUNCHED(h);
       weno_interp(h, fL, fC, u, w,  1, d, 0);
       weno_interp(h, fR, fC, u, w, -1, d, 0);
-      k_ns3d_source_avg<<<(unsigned)((ni + 255) / 256), 256, 0, h->stream>>>(ni, d, fL, fR, h->d_sI); LAUNCHED(h);
+      k_ns3d_source_avg<<<(unsigned)((ni + 255) / 256), 256, 0, h->stream>>>(ni, d, G.nvars - 1, fL, fR, h->d_sI); LAUNCHED(h);
       k_ns3d_source<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, h->phys, h->d_dxinv, u, h->d_gravf, h->d_sI, d, src);
       LAUNCHED(h);
     }

@@ -92,6 +92,7 @@ bool fused_available(const hpb_solver* h)
   if (c.model == HPB_MODEL_EULER1D) return false;
   if ((c.model == HPB_MODEL_NS2D || c.model == HPB_MODEL_NS3D) && c.upwind != HPB_UPWIND_RUSANOV) return false;
   if (c.model == HPB_MODEL_LINEAR_ADR && c.nvars != 1) return false;
+  if (c.model == HPB_MODEL_NS2D && h->phys.has_grav) return false;   // 2-D gravity source: reference-exact kernels only
   return true;
 }
 

@@ -34,6 +34,10 @@ def write_keyword_file(path: str, entries: Dict[str, object]) -> None:
     with open(path, "w") as f:
         f.write("begin\n")
         for k, v in entries.items():
+            if k == "N_bv":
+                continue            # written with HB 3 (NavierStokes3DInitialize.c:176-180: "HB 3 <N_bv>")
+            if k == "HB" and int(v) == 3:
+                v = [3, float(entries.get("N_bv", 0.0))]
             if isinstance(v, (list, tuple, np.ndarray)):
                 v = " ".join(_fmt(x) for x in v)
             else:
@@ -71,7 +75,10 @@ def read_keyword_file(path: str, ndims_hint: int | None = None,
         n = vector_keys.get(key)
         if n is None and key in _VECTOR_KEYS and ndims_hint is not None:
             n = ndims_hint
-        if n is None:
+        if key == "HB" and words[i] == "3":      # "HB 3 <N_bv>"
+            out["HB"], out["N_bv"] = "3", words[i + 1]
+            i += 2
+        elif n is None:
             out[key] = words[i]
             i += 1
         else:

@@ -101,8 +101,7 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     grav = ph.get("gravity", [0.0] * 3)
     grav = list(grav) if isinstance(grav, (list, tuple)) else [grav]
     if c.model == 2:
-        if any(float(v) != 0.0 for v in grav):
-            raise HyParB200Error("navierstokes2d with gravity is not on the B200 path")
+        grav = (grav + [0.0, 0.0])[:2] + [0.0]
     elif c.model == 1:
         if float(ph.get("gravity", 0.0) if not isinstance(ph.get("gravity", 0.0), (list, tuple)) else 0.0) != 0.0:
             raise HyParB200Error("euler1d with gravity is not on the B200 path")

@@ -219,7 +219,8 @@ int hyparb200_attach(void *sims, int nsims)
     c.model = HPB_MODEL_NS2D;  c.gamma = p->gamma;  c.Pr = p->Pr;  c.Minf = p->Minf;
     c.Re = (p->Re > 0 ? p->Re * p->Minf : p->Re);   /* NavierStokes2DInitialize.c:205 */
     c.upwind = upwind_choice(p->upw_choice);
-    if (p->grav_x != 0.0 || p->grav_y != 0.0) { fprintf(stderr, "hyparb200_attach: navierstokes2d with gravity is not on the B200 path\n"); return 1; }
+    c.gravity[0] = p->grav_x; c.gravity[1] = p->grav_y;
+    c.rho_ref = p->rho0; c.p_ref = p->p0; c.R = p->R; c.HB = p->HB; c.N_bv = p->N_bv;
   } else if (!strcmp(s->model, _EULER_1D_)) {
     Euler1D *p = (Euler1D*) s->physics;
     c.model = HPB_MODEL_EULER1D;  c.gamma = p->gamma;

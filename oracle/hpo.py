@@ -301,7 +301,7 @@ class Setup:
         n = self.npoints_g
         self.grav_f, self.grav_g = np.ones(n), np.ones(n)
         c.grav_f, c.grav_g = _p(self.grav_f), _p(self.grav_g)
-        if c.model == 3:
+        if c.model in (2, 3):       # NavierStokes2D / 3D gravity field (identical to 1 without gravity, HB 1)
             lib().hpo_ns3d_gravity_field(C.byref(c), _p(self.grav_f), _p(self.grav_g))
         return c
 
@@ -378,7 +378,7 @@ class Oracle:
 
     def source(self, u, w):
         src = self.zeros()
-        if self.s.ctx.model == 3:
+        if self.s.ctx.model in (2, 3):
             self.L.hpo_ns3d_source(self.c, _p(src), _p(u), _p(w))
         return src
 

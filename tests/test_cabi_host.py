@@ -59,6 +59,8 @@ ALL_CASES = [
     cases.ns3d_turbulence((20, 14, 12), "mapped"),
     cases.ns3d_rising_bubble((12, 16, 10), "yc"),
     cases.ns3d_rising_bubble((10, 14, 12), "mapped", hb=1),
+    cases.ns2d_rising_bubble((20, 24), "js"),                      # 2-D gravity field (HB 2) and slip walls
+    cases.ns2d_rising_bubble((24, 20), "z", hb=1, upwinding="roe"),
 ]
 
 

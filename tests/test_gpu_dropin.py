@@ -48,6 +48,7 @@ CASES = [
     _prep(cases.ns3d_rising_bubble((12, 16, 10), "yc", scheme="crweno5"), n_iter=4, screen=1),
     _prep(cases.euler1d_sod(101, "js", interp="components", scheme="cupw5")),
     _prep(cases.ns2d_vortex((32, 24), "js", upwinding="roe", interp="characteristic")),       # NavierStokes2D char + Roe
+    _prep(cases.ns2d_rising_bubble((24, 28), "yc"), n_iter=4, screen=1),                      # NavierStokes2D + gravity
 ]
 
 

@@ -82,6 +82,14 @@ def _cases():
     C.append(cases.ns2d_vortex((32, 24), "mapped", upwinding="llf-char", interp="characteristic"))
     C.append(cases.ns2d_vortex((24, 32), "z", upwinding="rusanov", interp="characteristic"))
     C.append(cases.ns2d_vortex((24, 20), "js", upwinding="roe", scheme="crweno5"))
+    # NavierStokes2D with gravity (exact kernels only)
+    C.append(cases.ns2d_rising_bubble((28, 24), "mapped"))
+    C.append(cases.ns2d_rising_bubble((24, 28), "z", hb=1, upwinding="roe"))
+    hb3 = cases.ns2d_rising_bubble((24, 24), "js", hb=3, upwinding="llf-char")
+    hb3.physics["N_bv"] = 0.01
+    hb3.name += "_nbv"
+    C.append(hb3)
+    C.append(cases.ns2d_rising_bubble((20, 24), "yc", scheme="crweno5"))
     return C
 
 
@@ -164,7 +172,8 @@ def test_rhs_parity(need_gpu, case):
 
 STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CASES[30], CASES[32],
               CASES[34], CASES[36], CASES[37], CASES[38], CASES[40], CASES[41], CASES[43], CASES[45],
-              CASES[46], CASES[47], CASES[48], CASES[49], CASES[50], CASES[51], CASES[53]]
+              CASES[46], CASES[47], CASES[48], CASES[49], CASES[50], CASES[51], CASES[53],
+              CASES[56], CASES[57], CASES[58], CASES[59]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)
@@ -221,7 +230,8 @@ def test_time_steps_parity(need_gpu, case):
 
 
 @pytest.mark.parametrize("case", [CASES[4], CASES[12], CASES[16], CASES[20], CASES[26],
-                                  CASES[35], CASES[37], CASES[40], CASES[42], CASES[44], CASES[51], CASES[52], CASES[53]],
+                                  CASES[35], CASES[37], CASES[40], CASES[42], CASES[44], CASES[51], CASES[52], CASES[53],
+                                  CASES[56], CASES[58]],
                          ids=lambda c: c.name)
 def test_function_pointer_pieces(need_gpu, case):
     """FFunction, UFunction, SetInterpLimiterVar, InterpolateInterfacesHyp, Upwind,

@@ -40,7 +40,7 @@ def same(a, b, what):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 29
+    assert len(GOLDEN) >= 32
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -105,6 +105,16 @@ def test_oracle_matches_reference_golden(path):
 
 
 # ---- live reference (only where oracle/_ref was built: this container, or the GPU box via gpurun)
+def _hb3(case, vertical=1):
+    """stratified atmosphere (HB 3 <N_bv>): gravity along the vertical coordinate only"""
+    case.physics["N_bv"] = 0.01
+    g = [0.0] * case.ndims
+    g[vertical] = 9.8
+    case.physics["gravity"] = g
+    case.name += "_hb3"
+    return case
+
+
 def _live_cases():
     return [
         cases.linear_advection_sine(96, "z"),
@@ -135,6 +145,12 @@ def _live_cases():
         cases.ns2d_vortex((20, 24), "mapped", upwinding="llf-char", interp="characteristic"),
         cases.ns2d_vortex((24, 20), "z", upwinding="rusanov", interp="characteristic"),
         cases.ns2d_vortex((24, 20), "js", upwinding="roe", scheme="crweno5"),
+        # NavierStokes2D with gravity (well-balanced source term; HB 1, 2, 3)
+        cases.ns2d_rising_bubble((20, 24), "mapped"),
+        cases.ns2d_rising_bubble((24, 20), "z", hb=1, upwinding="roe"),
+        _hb3(cases.ns2d_rising_bubble((20, 24), "js", hb=3, upwinding="llf-char")),
+        _hb3(cases.ns3d_rising_bubble((10, 12, 14), "js", hb=3), vertical=2),
+        cases.ns2d_rising_bubble((20, 20), "yc", upwinding="llf-char", interp="characteristic"),
         # the other explicit RK tableaux (TimeExplicitRKInitialize.c:27-79) and forward Euler (TimeForwardEuler.c)
         cases.with_time_scheme(cases.linear_advection_sine(96, "js"), "rk", "1fe"),
         cases.with_time_scheme(cases.euler1d_sod(101, "mapped"), "rk", "22"),

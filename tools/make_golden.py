@@ -55,6 +55,10 @@ GOLDEN = [
     ("c3_vortex_js_roe", "ns2d_vortex", dict(n=(20, 16), weno="js", upwinding="roe"), "hypar_ref", True),
     ("c3_vortex_mapped_char_rf", "ns2d_vortex", dict(n=(24, 20), weno="mapped", upwinding="rf-char", interp="characteristic"), "hypar_ref_mpi1", True),
     ("c3_vortex_z_llf", "ns2d_vortex", dict(n=(20, 24), weno="z", upwinding="llf-char"), "hypar_ref", False),
+    # NavierStokes2D with gravity: well-balanced source, HB 2 / HB 3, Rusanov / llf-char / Roe
+    ("c3g_bubble2d_js_hb2", "ns2d_rising_bubble", dict(n=(20, 24), weno="js"), "hypar_ref_mpi1", True),
+    ("c3g_bubble2d_yc_hb1_llf", "ns2d_rising_bubble", dict(n=(24, 20), weno="yc", hb=1, upwinding="llf-char"), "hypar_ref", False),
+    ("c3g_bubble2d_mapped_roe_crweno", "ns2d_rising_bubble", dict(n=(20, 20), weno="mapped", upwinding="roe", scheme="crweno5"), "hypar_ref", False),
     ("c2_sod_upw5_comp_rusanov", "euler1d_sod", dict(n=101, weno="js", interp="components", upwinding="rusanov", scheme="upw5"), "hypar_ref", True),
 ]
 
