@@ -17,7 +17,8 @@ MAX_NDIMS, MAX_NVARS, MAX_ZONES = 3, 5, 16
 class BoundaryZone(C.Structure):
     _fields_ = [("type", C.c_int), ("dim", C.c_int), ("face", C.c_int),
                 ("xmin", C.c_double * MAX_NDIMS), ("xmax", C.c_double * MAX_NDIMS),
-                ("wall_velocity", C.c_double * MAX_NDIMS)]
+                ("wall_velocity", C.c_double * MAX_NDIMS),
+                ("flow_density", C.c_double), ("flow_pressure", C.c_double), ("dirichlet", C.c_double * MAX_NVARS)]
 
 
 class Config(C.Structure):

@@ -200,6 +200,79 @@ def ns2d_rising_bubble(n: Sequence[int] = (64, 64), weno: str = "js", tstype: st
         weno=weno_inp(weno), x=xs, u0=u)
 
 
+# ------------------------------------------------------------------------------------- open / wall boundaries
+def _flow_zone(kind, ndims, d, face, lo, hi, rho, vel, p, nvars, gamma):
+    """one boundary.inp zone of the given type with the data InitializeBoundaries.c:107-175 reads for it"""
+    z = {"type": kind, "dim": d, "face": face,
+         "xmin": [0.0 if k == d else float(lo[k]) for k in range(ndims)],
+         "xmax": [0.0 if k == d else float(hi[k]) for k in range(ndims)]}
+    if kind in ("slip-wall", "noslip-wall"):
+        z["wall_velocity"] = [0.0] * ndims
+    elif kind == "dirichlet":
+        z["values"] = [rho] + [rho * v for v in vel] + [p / (gamma - 1.0) + 0.5 * rho * sum(v * v for v in vel)]
+    elif kind == "subsonic-inflow":
+        z["density"], z["velocity"] = rho, list(vel)
+    elif kind == "subsonic-outflow":
+        z["pressure"] = p
+    elif kind in ("subsonic-ambivalent", "supersonic-inflow"):
+        z["density"], z["velocity"], z["pressure"] = rho, list(vel), p
+    return z
+
+
+BC_SETS = {
+    "sup": {(0, 1): "supersonic-inflow", (0, -1): "supersonic-outflow", (1, 1): "dirichlet", (1, -1): "extrapolate"},
+    "amb2": {(0, 1): "subsonic-ambivalent", (0, -1): "subsonic-ambivalent", (1, 1): "subsonic-ambivalent",
+             (1, -1): "subsonic-ambivalent"},
+    "sup3": {(0, 1): "supersonic-inflow", (0, -1): "supersonic-outflow", (1, 1): "dirichlet", (1, -1): "extrapolate",
+             (2, 1): "subsonic-ambivalent", (2, -1): "subsonic-ambivalent"},
+    "amb3": {(2, 1): "subsonic-ambivalent", (2, -1): "noslip-wall"},
+}
+
+
+def ns_channel(n: Sequence[int] = (32, 24), weno: str = "js", bcs: Optional[Dict] = None, mach: float = 0.5,
+               upwinding: str = "rusanov", tstype: str = "ssprk3", viscous: bool = False, iproc=None,
+               scheme: str = "weno5") -> Case:
+    """Uniform stream (Mach `mach` along x, a small cross flow) with a smooth pressure / velocity disturbance in a box
+    [0,1]^nd, 2-D (navierstokes2d) or 3-D (navierstokes3d) by len(n). `bcs` maps (dim, face) to a boundary type among
+    slip-wall, noslip-wall, dirichlet, extrapolate, subsonic-inflow, subsonic-outflow, subsonic-ambivalent,
+    supersonic-inflow, supersonic-outflow; default: inflow / outflow along x, walls on the other faces."""
+    nd = len(n)
+    if isinstance(bcs, str):            # named sets (fixtures store their arguments as JSON)
+        bcs = BC_SETS[bcs]
+    gamma = 1.4
+    rho0, p0 = 1.0, 1.0 / gamma
+    vel0 = [mach, 0.05 * mach, -0.03 * mach][:nd]
+    xs = [(np.arange(n[d], dtype=np.float64) + 0.5) / n[d] for d in range(nd)]
+    grids = np.meshgrid(*[xs[d] for d in reversed(range(nd))], indexing="ij")     # slowest dimension first
+    X = list(reversed(grids))
+    bump = np.ones_like(X[0])
+    for d in range(nd):
+        bump = bump * np.sin(np.pi * X[d]) ** 2
+    rho = rho0 * (1.0 + 0.05 * bump)
+    p = p0 * (1.0 + 0.08 * bump)
+    vel = [vel0[d] * (1.0 + 0.1 * bump * np.cos(2.0 * np.pi * X[(d + 1) % nd])) for d in range(nd)]
+    ke = 0.5 * rho * sum(v * v for v in vel)
+    u = np.stack([rho] + [rho * v for v in vel] + [p / (gamma - 1.0) + ke], axis=-1)
+    default = {(0, 1): "subsonic-inflow", (0, -1): "subsonic-outflow"}
+    for d in range(1, nd):
+        default[(d, 1)], default[(d, -1)] = "noslip-wall", "slip-wall"
+    kinds = dict(default)
+    kinds.update(bcs or {})
+    zones = [_flow_zone(kinds[(d, f)], nd, d, f, [0.0] * nd, [1.0] * nd, rho0, vel0, p0, nd + 2, gamma)
+             for d in range(nd) for f in (1, -1)]
+    tag = "-".join(kinds[(d, f)].replace("subsonic-", "sub").replace("supersonic-", "sup")[:8] for d in range(nd) for f in (1, -1))
+    phys = {"gamma": gamma, "upwinding": upwinding}
+    if viscous:
+        phys.update({"Pr": 0.72, "Minf": mach, "Re": 100.0})
+    return Case(
+        name=f"chan{nd}d_{'x'.join(str(v) for v in n)}_{weno}_{tag}" + ("" if upwinding == "rusanov" else "_" + upwinding)
+             + ("_visc" if viscous else "") + _sfx(scheme),
+        solver=_solver(nd, nd + 2, n, "navierstokes2d" if nd == 2 else "navierstokes3d", ts="rk", tstype=tstype,
+                       dt=0.2 / max(n) / (1.0 + mach), iproc=iproc, par_type="nonconservative-2stage", par_scheme="4",
+                       scheme=scheme),
+        boundary=zones, physics=phys, weno=weno_inp(weno), x=xs, u0=u)
+
+
 # ------------------------------------------------------------------------------------- C4
 def _grid3(n, L):
     xs = [np.arange(n[d], dtype=np.float64) * (L[d] / n[d]) for d in range(3)]

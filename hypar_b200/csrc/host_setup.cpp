@@ -118,10 +118,13 @@ int hpb_setup_host(hpb_solver* h)
     const hpb_boundary_zone& z = c.zones[n];
     if (z.dim < 0 || z.dim >= nd) return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: dim %d is invalid (ndims = %d)", n, z.dim, nd);
     if (z.face != 1 && z.face != -1) return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: face must be +1/-1", n);
-    if (z.type < 0 || z.type > HPB_BC_SLIP_WALL)
-      return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: type %d not implemented (periodic, extrapolate, slip-wall)", n, z.type);
+    if (z.type < 0 || z.type > HPB_BC_SUPERSONIC_OUTFLOW)
+      return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: boundary type %d not implemented", n, z.type);
     if (z.type == HPB_BC_SLIP_WALL && c.model == HPB_MODEL_LINEAR_ADR)
       return hpb_fail(HPB_ERR_INVALID, "slip-wall needs an Euler/Navier-Stokes model");
+    if ((z.type == HPB_BC_NOSLIP_WALL || z.type >= HPB_BC_SUBSONIC_INFLOW) &&
+        c.model != HPB_MODEL_NS2D && c.model != HPB_MODEL_NS3D)      // the reference has 2-D and 3-D branches only
+      return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: boundary type %d needs a 2-D or 3-D Navier-Stokes model", n, z.type);
     if (z.type == HPB_BC_PERIODIC && c.iproc[z.dim] > 1) h->bcperiodic[z.dim] = 1;
   }
   for (int d = 0; d < 3; d++) h->neighbor[2*d] = h->neighbor[2*d+1] = -1;
@@ -177,6 +180,8 @@ int hpb_setup_host(hpb_solver* h)
     ZoneDev zd; memset(&zd, 0, sizeof(zd));
     zd.type = z.type; zd.dim = z.dim; zd.face = z.face; zd.on = 0;
     for (int d = 0; d < 3; d++) { zd.is[d] = 0; zd.ie[d] = 1; zd.wall[d] = z.wall_velocity[d]; }
+    zd.rho = z.flow_density; zd.pressure = z.flow_pressure;
+    for (int v = 0; v < HPB_MAX_NVARS; v++) zd.val[v] = z.dirichlet[v];
     const bool edge = (z.face == 1) ? (h->ip[z.dim] == 0) : (h->ip[z.dim] == c.iproc[z.dim] - 1);
     if (edge) {
       zd.on = 1;

@@ -34,7 +34,9 @@ struct Phys {
 struct ZoneDev {
   int type, dim, face, on;
   int is[3], ie[3];
-  double wall[3];
+  double wall[3];                 // wall / inflow velocity
+  double rho, pressure;           // inflow density, inflow / outflow pressure
+  double val[HPB_MAX_NVARS];      // Dirichlet values
 };
 
 struct RKTableau { int ns; double A[16], b[4], c[4]; };

@@ -67,8 +67,63 @@ __global__ void k_bc_zone(Geom G, ZoneDev z, double gamma, double* __restrict__ 
   }
   const long long p1 = cell_index(G, i1[0], i1[1], i1[2]);
   const long long p2 = cell_index(G, i2[0], i2[1], i2[2]);
-  if (z.type != HPB_BC_SLIP_WALL) {
+  if (z.type == HPB_BC_PERIODIC || z.type == HPB_BC_EXTRAPOLATE) {
     for (int v = 0; v < nv; v++) phi[v * G.npg + p1] = phi[v * G.npg + p2];
+    return;
+  }
+  if (z.type == HPB_BC_DIRICHLET) {                 // BCDirichlet.c:20-38
+    for (int v = 0; v < nv; v++) phi[v * G.npg + p1] = z.val[v];
+    return;
+  }
+  if (z.type != HPB_BC_SLIP_WALL) {
+    // BCNoslipWall.c, BCSubsonicInflow.c, BCSubsonicOutflow.c, BCSubsonicAmbivalent.c, BCSupersonicInflow.c,
+    // BCSupersonicOutflow.c (2-D and 3-D branches): density, velocity and pressure of the ghost point come from the
+    // mirrored interior point or from the zone's data; the energy is recomputed. 2-D: _Euler2DGetFlowVar_ (no
+    // rho == 0 guard); 3-D: _NavierStokes3DGetFlowVar_.
+    const int nd = G.ndims;
+    const double inv_gamma_m1 = 1.0 / (gamma - 1.0);
+    const double rho = phi[p2];
+    double vel[3] = { 0.0, 0.0, 0.0 };
+    for (int k = 0; k < nd; k++) vel[k] = (nd == 3 && rho == 0) ? 0.0 : phi[(1 + k) * G.npg + p2] / rho;
+    const double energy = phi[(nv - 1) * G.npg + p2];
+    const double vsq = (nd == 2) ? (vel[0] * vel[0]) + (vel[1] * vel[1]) : (vel[0] * vel[0]) + (vel[1] * vel[1]) + (vel[2] * vel[2]);
+    const double pressure = (energy - 0.5 * rho * vsq) * (gamma - 1.0);
+    bool inflow = (z.type == HPB_BC_SUBSONIC_INFLOW), outflow = (z.type == HPB_BC_SUBSONIC_OUTFLOW);
+    if (z.type == HPB_BC_SUBSONIC_AMBIVALENT) {
+      // face velocity by 2nd-order extrapolation from the two interior points next to the boundary, dotted with the
+      // inward normal (BCSubsonicAmbivalent.c:66-92)
+      int j1[3] = { i1[0], i1[1], i1[2] }, j2[3] = { i1[0], i1[1], i1[2] };
+      if (z.face == 1) { j1[dim] = 0; j2[dim] = 1; } else { j1[dim] = G.N[dim] - 1; j2[dim] = G.N[dim] - 2; }
+      const long long q1 = cell_index(G, j1[0], j1[1], j1[2]), q2 = cell_index(G, j2[0], j2[1], j2[2]);
+      const double r1 = phi[q1], r2 = phi[q2];
+      double vb[3] = { 0.0, 0.0, 0.0 };
+      for (int k = 0; k < nd; k++) {
+        const double a1 = (nd == 3 && r1 == 0) ? 0.0 : phi[(1 + k) * G.npg + q1] / r1;
+        const double a2 = (nd == 3 && r2 == 0) ? 0.0 : phi[(1 + k) * G.npg + q2] / r2;
+        vb[k] = 1.5 * a1 - 0.5 * a2;
+      }
+      double nrm[3] = { dim == 0 ? 1.0 : 0.0, dim == 1 ? 1.0 : 0.0, dim == 2 ? 1.0 : 0.0 };
+      for (int k = 0; k < 3; k++) nrm[k] *= (double) z.face;
+      const double vn = (nd == 2) ? vb[0] * nrm[0] + vb[1] * nrm[1] : vb[0] * nrm[0] + vb[1] * nrm[1] + vb[2] * nrm[2];
+      if (vn > 0) inflow = true; else outflow = true;
+    }
+    double rho_gpt = rho, pressure_gpt = pressure, vg[3] = { vel[0], vel[1], vel[2] };
+    if (z.type == HPB_BC_NOSLIP_WALL) {
+      for (int k = 0; k < nd; k++) vg[k] = 2.0 * z.wall[k] - vel[k];
+    } else if (inflow) {
+      rho_gpt = z.rho;
+      for (int k = 0; k < nd; k++) vg[k] = z.wall[k];
+    } else if (outflow) {
+      pressure_gpt = z.pressure;
+    } else if (z.type == HPB_BC_SUPERSONIC_INFLOW) {
+      rho_gpt = z.rho; pressure_gpt = z.pressure;
+      for (int k = 0; k < nd; k++) vg[k] = z.wall[k];
+    }
+    const double vgsq = (nd == 2) ? vg[0] * vg[0] + vg[1] * vg[1] : vg[0] * vg[0] + vg[1] * vg[1] + vg[2] * vg[2];
+    const double energy_gpt = inv_gamma_m1 * pressure_gpt + 0.5 * rho_gpt * vgsq;
+    phi[p1] = rho_gpt;
+    for (int k = 0; k < nd; k++) phi[(1 + k) * G.npg + p1] = rho_gpt * vg[k];
+    phi[(nv - 1) * G.npg + p1] = energy_gpt;
     return;
   }
   // slip wall: rho, p copied; normal velocity 2*v_wall - v; energy recomputed

@@ -121,8 +121,18 @@ def write_boundary_inp(path: str, zones: Sequence[dict]) -> None:
         for z in zones:
             ext = "  ".join(f"{a!r} {b!r}" for a, b in zip(z["xmin"], z["xmax"]))
             f.write(f"{z['type']}  {z['dim']}  {z['face']}  {ext}\n")
-            if z["type"] in ("slip-wall", "noslip-wall"):
+            # type-specific data, InitializeBoundaries.c:107-175
+            t = z["type"]
+            if t in ("slip-wall", "noslip-wall"):
                 f.write(" ".join(repr(float(v)) for v in z["wall_velocity"]) + "\n")
+            elif t in ("dirichlet", "sponge"):
+                f.write(" ".join(repr(float(v)) for v in z["values"]) + "\n")
+            elif t == "subsonic-inflow":
+                f.write(" ".join(repr(float(v)) for v in [z["density"], *z["velocity"]]) + "\n")
+            elif t == "subsonic-outflow":
+                f.write(repr(float(z["pressure"])) + "\n")
+            elif t in ("subsonic-ambivalent", "supersonic-inflow"):
+                f.write(" ".join(repr(float(v)) for v in [z["density"], *z["velocity"], z["pressure"]]) + "\n")
 
 
 def read_boundary_inp(path: str, ndims: int, nvars: int) -> List[dict]:
@@ -143,6 +153,16 @@ def read_boundary_inp(path: str, ndims: int, nvars: int) -> List[dict]:
         elif z["type"] in ("dirichlet", "sponge"):
             z["values"] = [float(x) for x in w[i:i + nvars]]
             i += nvars
+        elif z["type"] == "subsonic-inflow":
+            z["density"], z["velocity"] = float(w[i]), [float(x) for x in w[i + 1:i + 1 + ndims]]
+            i += 1 + ndims
+        elif z["type"] == "subsonic-outflow":
+            z["pressure"] = float(w[i])
+            i += 1
+        elif z["type"] in ("subsonic-ambivalent", "supersonic-inflow"):
+            z["density"], z["velocity"] = float(w[i]), [float(x) for x in w[i + 1:i + 1 + ndims]]
+            z["pressure"] = float(w[i + 1 + ndims])
+            i += 2 + ndims
         zones.append(z)
     return zones
 

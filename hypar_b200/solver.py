@@ -20,7 +20,8 @@ import numpy as np
 from . import _lib, hypario
 
 MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3}
-BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2}
+BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "dirichlet": 4, "subsonic-inflow": 5,
+           "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9}
 UPWINDS = {"roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 RK_TYPES = {"44": 0, "ssprk3": 1, "tvdrk3": 1, "1fe": 2, "22": 3, "33": 4}
 SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3}
@@ -123,12 +124,15 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     c.nzones = len(boundary)
     for n, z in enumerate(boundary):
         if z["type"] not in BCTYPES:
-            raise HyParB200Error(f"boundary type '{z['type']}' is not on the B200 path (periodic, extrapolate, slip-wall)")
+            raise HyParB200Error(f"boundary type '{z['type']}' is not on the B200 path ({', '.join(BCTYPES)})")
         cz = c.zones[n]
         cz.type, cz.dim, cz.face = BCTYPES[z["type"]], int(z["dim"]), int(z["face"])
         for d in range(nd):
             cz.xmin[d], cz.xmax[d] = float(z["xmin"][d]), float(z["xmax"][d])
-            cz.wall_velocity[d] = float(z.get("wall_velocity", [0.0] * nd)[d])
+            cz.wall_velocity[d] = float(z.get("wall_velocity", z.get("velocity", [0.0] * nd))[d])
+        cz.flow_density, cz.flow_pressure = float(z.get("density", 0.0)), float(z.get("pressure", 0.0))
+        for v, val in enumerate(z.get("values", [])):
+            cz.dirichlet[v] = float(val)
     xg = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in x]))
     c.x_global = _dp(xg)
     c.device = device

@@ -71,11 +71,19 @@ extern "C" {
 #define HPB_SCHEME_CUPW5   2    /* "cupw5": fifth-order compact upwind */
 #define HPB_SCHEME_UPW5    3    /* "upw5":  fifth-order upwind         */
 
-/* boundary.inp zone types implemented on the device (reference: 17 types; the three the
-   BASELINE configurations use) */
-#define HPB_BC_PERIODIC    0
-#define HPB_BC_EXTRAPOLATE 1
-#define HPB_BC_SLIP_WALL   2
+/* boundary.inp zone types implemented on the device (reference: 17 types, src/BoundaryConditions/BCInitialize.c; the first
+   three are the ones the BASELINE configurations use, the others cover the reference's Navier-Stokes examples;
+   types 3, 5-9 exist for 2-D and 3-D models only, as in the reference) */
+#define HPB_BC_PERIODIC            0
+#define HPB_BC_EXTRAPOLATE         1
+#define HPB_BC_SLIP_WALL           2
+#define HPB_BC_NOSLIP_WALL         3   /* BCNoslipWall.c: wall_velocity                                  */
+#define HPB_BC_DIRICHLET           4   /* BCDirichlet.c: dirichlet[nvars]                                */
+#define HPB_BC_SUBSONIC_INFLOW     5   /* BCSubsonicInflow.c: flow_density, wall_velocity = flow velocity */
+#define HPB_BC_SUBSONIC_OUTFLOW    6   /* BCSubsonicOutflow.c: flow_pressure                             */
+#define HPB_BC_SUBSONIC_AMBIVALENT 7   /* BCSubsonicAmbivalent.c: density, velocity, pressure            */
+#define HPB_BC_SUPERSONIC_INFLOW   8   /* BCSupersonicInflow.c: density, velocity, pressure              */
+#define HPB_BC_SUPERSONIC_OUTFLOW  9   /* BCSupersonicOutflow.c                                          */
 
 /* time_scheme_type for time_scheme "rk" -- reference TimeExplicitRKInitialize.c:58-79 */
 #define HPB_RK_44     0
@@ -93,7 +101,10 @@ typedef struct hpb_boundary_zone {
   int    type;                         /* HPB_BC_*                                       */
   int    dim, face;                    /* face = +1 (low side) / -1 (high side)          */
   double xmin[HPB_MAX_NDIMS], xmax[HPB_MAX_NDIMS];
-  double wall_velocity[HPB_MAX_NDIMS]; /* slip-wall only                                 */
+  double wall_velocity[HPB_MAX_NDIMS]; /* DomainBoundary::FlowVelocity: wall velocity (slip / no-slip wall) or the
+                                          flow velocity of an inflow zone                  */
+  double flow_density, flow_pressure;  /* DomainBoundary::FlowDensity, FlowPressure      */
+  double dirichlet[HPB_MAX_NVARS];     /* DomainBoundary::DirichletValue                 */
 } hpb_boundary_zone;
 
 typedef struct hpb_config {

@@ -161,6 +161,13 @@ static int bc_type(const char *name)
   if (!strcmp(name, _PERIODIC_))    return HPB_BC_PERIODIC;
   if (!strcmp(name, _EXTRAPOLATE_)) return HPB_BC_EXTRAPOLATE;
   if (!strcmp(name, _SLIP_WALL_))   return HPB_BC_SLIP_WALL;
+  if (!strcmp(name, _NOSLIP_WALL_))          return HPB_BC_NOSLIP_WALL;
+  if (!strcmp(name, _DIRICHLET_))            return HPB_BC_DIRICHLET;
+  if (!strcmp(name, _SUBSONIC_INFLOW_))      return HPB_BC_SUBSONIC_INFLOW;
+  if (!strcmp(name, _SUBSONIC_OUTFLOW_))     return HPB_BC_SUBSONIC_OUTFLOW;
+  if (!strcmp(name, _SUBSONIC_AMBIVALENT_))  return HPB_BC_SUBSONIC_AMBIVALENT;
+  if (!strcmp(name, _SUPERSONIC_INFLOW_))    return HPB_BC_SUPERSONIC_INFLOW;
+  if (!strcmp(name, _SUPERSONIC_OUTFLOW_))   return HPB_BC_SUPERSONIC_OUTFLOW;
   return -1;
 }
 
@@ -247,8 +254,10 @@ int hyparb200_attach(void *sims, int nsims)
     c.zones[n].dim = b[n].dim;  c.zones[n].face = b[n].face;
     for (int d = 0; d < s->ndims; d++) {
       c.zones[n].xmin[d] = b[n].xmin[d];  c.zones[n].xmax[d] = b[n].xmax[d];
-      c.zones[n].wall_velocity[d] = (c.zones[n].type == HPB_BC_SLIP_WALL && b[n].FlowVelocity) ? b[n].FlowVelocity[d] : 0.0;
+      c.zones[n].wall_velocity[d] = b[n].FlowVelocity ? b[n].FlowVelocity[d] : 0.0;   /* allocated only where read */
     }
+    c.zones[n].flow_density = b[n].FlowDensity;  c.zones[n].flow_pressure = b[n].FlowPressure;
+    if (b[n].DirichletValue) for (int v = 0; v < s->nvars; v++) c.zones[n].dirichlet[v] = b[n].DirichletValue[v];
   }
 
   /* global grid, concatenated per dimension as in initial.inp (ReadArray.c:225-256); one rank: the interior part

@@ -23,7 +23,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 MAXD, MAXV, MAXZ = 3, 5, 16
 
 MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3}
-BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2}
+BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "dirichlet": 4, "subsonic-inflow": 5,
+           "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9}
 UPWINDS = {"default": 0, "roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3}
 
@@ -31,7 +32,8 @@ SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3}
 class Zone(C.Structure):
     _fields_ = [("type", C.c_int), ("dim", C.c_int), ("face", C.c_int),
                 ("is_", C.c_int * MAXD), ("ie", C.c_int * MAXD), ("on_this_proc", C.c_int),
-                ("wall_vel", C.c_double * MAXD)]
+                ("wall_vel", C.c_double * MAXD), ("rho", C.c_double), ("pressure", C.c_double),
+                ("values", C.c_double * MAXV)]
 
 
 class Ctx(C.Structure):
@@ -210,7 +212,9 @@ class Setup:
         for z in case.boundary:
             dim, face = int(z["dim"]), int(z["face"])
             zi = {"type": z["type"], "dim": dim, "face": face, "is": [0] * nd, "ie": [0] * nd,
-                  "on": 0, "wall_vel": list(z.get("wall_velocity", [0.0] * nd))}
+                  "on": 0, "wall_vel": list(z.get("wall_velocity", z.get("velocity", [0.0] * nd))),
+                  "rho": float(z.get("density", 0.0)), "pressure": float(z.get("pressure", 0.0)),
+                  "values": list(z.get("values", []))}
             edge = (self.ip[dim] == 0) if face == 1 else (self.ip[dim] == self.iproc[dim] - 1)
             if edge:
                 zi["on"] = 1
@@ -296,6 +300,9 @@ class Setup:
             cz.type, cz.dim, cz.face, cz.on_this_proc = BCTYPES[z["type"]], z["dim"], z["face"], z["on"]
             for d in range(self.ndims):
                 cz.is_[d], cz.ie[d], cz.wall_vel[d] = z["is"][d], z["ie"][d], z["wall_vel"][d]
+            cz.rho, cz.pressure = z["rho"], z["pressure"]
+            for v, val in enumerate(z["values"]):
+                cz.values[v] = float(val)
         c.x, c.dxinv = _p(self.x), _p(self.dxinv)
         # gravity field
         n = self.npoints_g

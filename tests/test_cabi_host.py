@@ -61,6 +61,8 @@ ALL_CASES = [
     cases.ns3d_rising_bubble((10, 14, 12), "mapped", hb=1),
     cases.ns2d_rising_bubble((20, 24), "js"),                      # 2-D gravity field (HB 2) and slip walls
     cases.ns2d_rising_bubble((24, 20), "z", hb=1, upwinding="roe"),
+    cases.ns_channel((24, 20), "js"),                               # inflow / outflow / no-slip / slip zones
+    cases.ns_channel((10, 12, 10), "js", bcs={(1, 1): "dirichlet", (1, -1): "subsonic-ambivalent"}),
 ]
 
 
@@ -132,7 +134,7 @@ def test_decomposed_setup_neighbors_and_remainders():
     (lambda c: c.solver.__setitem__("time_scheme_type", "ssprk2"), "ssprk3"),
     (lambda c: c.solver.__setitem__("ghost", 2), "ghost"),
     (lambda c: c.solver.__setitem__("model", "shallow-water-2d"), "model"),
-    (lambda c: c.boundary[0].__setitem__("type", "noslip-wall"), "boundary type"),
+    (lambda c: c.boundary[0].__setitem__("type", "sponge"), "boundary type"),
     (lambda c: c.physics.__setitem__("upwinding", "steger-warming"), "upwinding"),
     (lambda c: c.solver.__setitem__("par_space_type", "conservative-1stage"), "nonconservative-2stage"),
 ])

@@ -90,6 +90,14 @@ def _cases():
     hb3.name += "_nbv"
     C.append(hb3)
     C.append(cases.ns2d_rising_bubble((20, 24), "yc", scheme="crweno5"))
+    # inflow / outflow / wall / Dirichlet boundary zones
+    C.append(cases.ns_channel((32, 24), "mapped"))
+    C.append(cases.ns_channel((24, 28), "js", bcs="sup", mach=1.6))
+    C.append(cases.ns_channel((28, 24), "z", bcs="amb2", upwinding="roe"))
+    C.append(cases.ns_channel((24, 24), "yc", viscous=True))
+    C.append(cases.ns_channel((16, 12, 14), "js"))
+    C.append(cases.ns_channel((12, 14, 12), "mapped", bcs="sup3", mach=1.4))
+    C.append(cases.ns_channel((14, 12, 12), "z", viscous=True, bcs="amb3"))
     return C
 
 
@@ -173,7 +181,8 @@ def test_rhs_parity(need_gpu, case):
 STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CASES[30], CASES[32],
               CASES[34], CASES[36], CASES[37], CASES[38], CASES[40], CASES[41], CASES[43], CASES[45],
               CASES[46], CASES[47], CASES[48], CASES[49], CASES[50], CASES[51], CASES[53],
-              CASES[56], CASES[57], CASES[58], CASES[59]]
+              CASES[56], CASES[57], CASES[58], CASES[59], CASES[60], CASES[61], CASES[62], CASES[63], CASES[64],
+              CASES[65], CASES[66]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)

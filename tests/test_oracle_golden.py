@@ -40,7 +40,7 @@ def same(a, b, what):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 32
+    assert len(GOLDEN) >= 35
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -151,6 +151,14 @@ def _live_cases():
         _hb3(cases.ns2d_rising_bubble((20, 24), "js", hb=3, upwinding="llf-char")),
         _hb3(cases.ns3d_rising_bubble((10, 12, 14), "js", hb=3), vertical=2),
         cases.ns2d_rising_bubble((20, 20), "yc", upwinding="llf-char", interp="characteristic"),
+        # inflow / outflow / wall / Dirichlet boundary zones (BCNoslipWall.c, BCDirichlet.c, BCSub*/BCSuper*.c)
+        cases.ns_channel((24, 20), "mapped", upwinding="roe"),
+        cases.ns_channel((20, 24), "js", bcs="sup", mach=1.6),
+        cases.ns_channel((24, 20), "z", bcs="amb2", upwinding="llf-char"),
+        cases.ns_channel((20, 20), "yc", viscous=True),
+        cases.ns_channel((12, 10, 14), "js"),
+        cases.ns_channel((10, 12, 10), "mapped", bcs="sup3", mach=1.4),
+        cases.ns_channel((12, 10, 10), "z", viscous=True, bcs="amb3"),
         # the other explicit RK tableaux (TimeExplicitRKInitialize.c:27-79) and forward Euler (TimeForwardEuler.c)
         cases.with_time_scheme(cases.linear_advection_sine(96, "js"), "rk", "1fe"),
         cases.with_time_scheme(cases.euler1d_sod(101, "mapped"), "rk", "22"),

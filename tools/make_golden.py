@@ -59,6 +59,10 @@ GOLDEN = [
     ("c3g_bubble2d_js_hb2", "ns2d_rising_bubble", dict(n=(20, 24), weno="js"), "hypar_ref_mpi1", True),
     ("c3g_bubble2d_yc_hb1_llf", "ns2d_rising_bubble", dict(n=(24, 20), weno="yc", hb=1, upwinding="llf-char"), "hypar_ref", False),
     ("c3g_bubble2d_mapped_roe_crweno", "ns2d_rising_bubble", dict(n=(20, 20), weno="mapped", upwinding="roe", scheme="crweno5"), "hypar_ref", False),
+    # inflow / outflow / wall / Dirichlet boundary zones
+    ("chan2d_js_inflow_outflow_walls", "ns_channel", dict(n=(24, 20), weno="js"), "hypar_ref", False),
+    ("chan2d_mapped_supersonic_dirichlet", "ns_channel", dict(n=(20, 24), weno="mapped", mach=1.6, bcs="sup"), "hypar_ref_mpi1", False),
+    ("chan3d_z_ambivalent_visc", "ns_channel", dict(n=(12, 10, 10), weno="z", viscous=True, bcs="amb3"), "hypar_ref_mpi1", False),
     ("c2_sod_upw5_comp_rusanov", "euler1d_sod", dict(n=101, weno="js", interp="components", upwinding="rusanov", scheme="upw5"), "hypar_ref", True),
 ]
 
