@@ -524,7 +524,7 @@ extern "C" int hpb_SetInterpLimiterVar(hpb_solver* h, const double* fC, const do
 {
   TRY(need_device(h)); TRY(tmp(h, 0)); TRY(tmp(h, 1));
   if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "SetInterpLimiterVar: dir %d", dir);
-  if (h->cfg.hyp_scheme == HPB_SCHEME_CUPW5 || h->cfg.hyp_scheme == HPB_SCHEME_UPW5)
+  if (h->cfg.hyp_scheme != HPB_SCHEME_WENO5 && h->cfg.hyp_scheme != HPB_SCHEME_CRWENO5)
     return HPB_OK;             // linear schemes: the reference leaves the pointer NULL (InitializeSolvers.c:194)
   TRY(dalloc(&h->d_w, woff(h, h->geo.ndims)));
   TRY(upload(h, fC, h->d_tmp[0], h->geo.npg, h->geo.nvars));

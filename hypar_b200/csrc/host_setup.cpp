@@ -76,8 +76,8 @@ int hpb_setup_host(hpb_solver* h)
     return hpb_fail(HPB_ERR_INVALID, "navierstokes2d: gravity has two components");
   if (c.model == HPB_MODEL_LINEAR_ADR && c.par_scheme != 2 && c.par_scheme != 4)
     return hpb_fail(HPB_ERR_INVALID, "par_space_scheme %d not supported (2, 4)", c.par_scheme);
-  if (c.hyp_scheme < HPB_SCHEME_WENO5 || c.hyp_scheme > HPB_SCHEME_UPW5)
-    return hpb_fail(HPB_ERR_INVALID, "hyp_space_scheme %d not supported (weno5, crweno5, cupw5, upw5)", c.hyp_scheme);
+  if (c.hyp_scheme < HPB_SCHEME_WENO5 || c.hyp_scheme > HPB_SCHEME_FOURTH)
+    return hpb_fail(HPB_ERR_INVALID, "hyp_space_scheme %d not supported (weno5, crweno5, cupw5, upw5, 1, 2, 4)", c.hyp_scheme);
   if (c.hyp_scheme != HPB_SCHEME_WENO5 && c.interp_char && c.nvars > 1)
     return hpb_fail(HPB_ERR_INVALID, "characteristic reconstruction is implemented for weno5 only "
                     "(the compact schemes would need the block-tridiagonal solver, blocktridiagLU.c)");

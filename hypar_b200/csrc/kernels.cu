@@ -993,9 +993,11 @@ __global__ void k_tridiag(Geom G, int dir, double* __restrict__ A, double* __res
   }
 }
 
-// Interp1PrimFifthOrderUpwind.c:60-147 (component-wise)
-__global__ void k_interp_upw5(Geom G, const double* __restrict__ fC, int upw, int dir, double* __restrict__ fI)
+// the linear schemes, component-wise: Interp1PrimFifthOrderUpwind.c:60-147, Interp1PrimFirstOrderUpwind.c:78-84,
+// Interp1PrimSecondOrderCentral.c:80-88, Interp1PrimFourthOrderCentral.c:96-120
+__global__ void k_interp_upw5(Geom G, int scheme, const double* __restrict__ fC, int upw, int dir, double* __restrict__ fI)
 {
+  const double c1 = 7.0 / 12.0, c2 = -1.0 / 12.0;
   const double one_by_thirty = 1.0 / 30.0, thirteen_by_sixty = 13.0 / 60.0, fortyseven_by_sixty = 47.0 / 60.0,
                twentyseven_by_sixty = 27.0 / 60.0, one_by_twenty = 1.0 / 20.0;
   const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
@@ -1007,10 +1009,16 @@ __global__ void k_interp_upw5(Geom G, const double* __restrict__ fC, int upw, in
   const long long pm1 = cell_index(G, i0, i1, i2) - st;
   long long ps[5];
   for (int k = 0; k < 5; k++) ps[k] = (upw > 0) ? pm1 + (k - 2) * st : pm1 + (3 - k) * st;
+  const long long qL = pm1, qR = pm1 + st;          // cells left / right of the interface whatever the bias
   for (int v = 0; v < G.nvars; v++) {
     const double* f = fC + v * G.npg;
-    fI[v * ni + q] = one_by_thirty * f[ps[0]] - thirteen_by_sixty * f[ps[1]] + fortyseven_by_sixty * f[ps[2]]
-                   + twentyseven_by_sixty * f[ps[3]] - one_by_twenty * f[ps[4]];
+    double r;
+    if (scheme == HPB_SCHEME_FIRST)       r = f[ps[2]];
+    else if (scheme == HPB_SCHEME_SECOND) r = 0.5 * (f[qL] + f[qR]);
+    else if (scheme == HPB_SCHEME_FOURTH) r = c2 * f[qL - st] + c1 * f[qL] + c1 * f[qR] + c2 * f[qR + st];
+    else r = one_by_thirty * f[ps[0]] - thirteen_by_sixty * f[ps[1]] + fortyseven_by_sixty * f[ps[2]]
+           + twentyseven_by_sixty * f[ps[3]] - one_by_twenty * f[ps[4]];
+    fI[v * ni + q] = r;
   }
 }
 
@@ -1393,8 +1401,8 @@ void weno_interp(hpb_solver* h, double* fI, const double* fC, const double* u, c
 {
   const Geom& G = h->geo;
   const int M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
-  if (h->cfg.hyp_scheme == HPB_SCHEME_UPW5) {
-    k_interp_upw5<<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, fC, upw, dir, fI); LAUNCHED(h);
+  if (h->cfg.hyp_scheme >= HPB_SCHEME_UPW5) {
+    k_interp_upw5<<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->cfg.hyp_scheme, fC, upw, dir, fI); LAUNCHED(h);
     return;
   }
   if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h->cfg.hyp_scheme == HPB_SCHEME_CUPW5) {

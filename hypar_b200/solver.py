@@ -24,7 +24,7 @@ BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "d
            "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9}
 UPWINDS = {"roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 RK_TYPES = {"44": 0, "ssprk3": 1, "tvdrk3": 1, "1fe": 2, "22": 3, "33": 4}
-SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3}
+SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6}
 FIELD_U, FIELD_QDERIVX, FIELD_QDERIVY = 0, 1, 2
 
 
@@ -60,7 +60,7 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     c.model = MODELS[model]
     scheme = str(solver.get("hyp_space_scheme", "1"))
     if scheme not in SCHEMES:
-        raise HyParB200Error(f"hyp_space_scheme '{scheme}' is not on the B200 path (weno5, crweno5, cupw5, upw5)")
+        raise HyParB200Error(f"hyp_space_scheme '{scheme}' is not on the B200 path (weno5, crweno5, cupw5, upw5, 1, 2, 4)")
     c.hyp_scheme = SCHEMES[scheme]
     ts = str(solver.get("time_scheme", "euler"))
     if ts not in ("rk", "euler"):

@@ -70,6 +70,9 @@ extern "C" {
 #define HPB_SCHEME_CRWENO5 1    /* "crweno5" */
 #define HPB_SCHEME_CUPW5   2    /* "cupw5": fifth-order compact upwind */
 #define HPB_SCHEME_UPW5    3    /* "upw5":  fifth-order upwind         */
+#define HPB_SCHEME_FIRST   4    /* "1": first-order upwind  (Interp1PrimFirstOrderUpwind.c)   */
+#define HPB_SCHEME_SECOND  5    /* "2": second-order central (Interp1PrimSecondOrderCentral.c) */
+#define HPB_SCHEME_FOURTH  6    /* "4": fourth-order central (Interp1PrimFourthOrderCentral.c) */
 
 /* boundary.inp zone types implemented on the device (reference: 17 types, src/BoundaryConditions/BCInitialize.c; the first
    three are the ones the BASELINE configurations use, the others cover the reference's Navier-Stokes examples;

@@ -187,6 +187,9 @@ int hyparb200_attach(void *sims, int nsims)
   else if (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_CRWENO_))         scheme = HPB_SCHEME_CRWENO5;
   else if (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_COMPACT_UPWIND_)) scheme = HPB_SCHEME_CUPW5;
   else if (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_UPWIND_))         scheme = HPB_SCHEME_UPW5;
+  else if (!strcmp(s->spatial_scheme_hyp, _FIRST_ORDER_UPWIND_))         scheme = HPB_SCHEME_FIRST;
+  else if (!strcmp(s->spatial_scheme_hyp, _SECOND_ORDER_CENTRAL_))       scheme = HPB_SCHEME_SECOND;
+  else if (!strcmp(s->spatial_scheme_hyp, _FOURTH_ORDER_CENTRAL_))       scheme = HPB_SCHEME_FOURTH;
   if (scheme < 0 || strcmp(s->time_scheme, _RK_) || strcmp(s->SplitHyperbolicFlux, "no") || s->flag_ib) {
     fprintf(stderr, "hyparb200_attach: only weno5 / crweno5 / cupw5 / upw5 + explicit RK without flux splitting / "
                     "immersed boundaries is on the B200 path\n");

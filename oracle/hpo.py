@@ -26,7 +26,7 @@ MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "dirichlet": 4, "subsonic-inflow": 5,
            "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9}
 UPWINDS = {"default": 0, "roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
-SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3}
+SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6}
 
 
 class Zone(C.Structure):

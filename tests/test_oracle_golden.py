@@ -159,6 +159,12 @@ def _live_cases():
         cases.ns_channel((12, 10, 14), "js"),
         cases.ns_channel((10, 12, 10), "mapped", bcs="sup3", mach=1.4),
         cases.ns_channel((12, 10, 10), "z", viscous=True, bcs="amb3"),
+        # the low-order linear schemes "1", "2", "4"
+        cases.linear_advection_sine(96, "js", diffusion=0.01, scheme="1"),
+        cases.euler1d_sod(101, "js", interp="components", upwinding="rusanov", scheme="1"),
+        cases.ns2d_vortex((24, 20), "js", scheme="2"),
+        cases.ns3d_rising_bubble((10, 14, 12), "js", scheme="4"),
+        cases.ns_channel((12, 10, 14), "js", viscous=True, scheme="1"),
         # the other explicit RK tableaux (TimeExplicitRKInitialize.c:27-79) and forward Euler (TimeForwardEuler.c)
         cases.with_time_scheme(cases.linear_advection_sine(96, "js"), "rk", "1fe"),
         cases.with_time_scheme(cases.euler1d_sod(101, "mapped"), "rk", "22"),
