@@ -37,7 +37,7 @@ class Config(C.Structure):
         ("nzones", C.c_int), ("zones", BoundaryZone * MAX_ZONES),
         ("x_global", C.POINTER(C.c_double)),
         ("device", C.c_int), ("use_fused", C.c_int), ("conservation_check", C.c_int),
-        ("hyp_scheme", C.c_int),
+        ("hyp_scheme", C.c_int), ("muscl_limiter", C.c_int), ("muscl_eps", C.c_double),
     ]
 
 

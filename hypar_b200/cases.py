@@ -33,6 +33,7 @@ class Case:
     weno: Optional[Dict[str, object]]
     x: List[np.ndarray]            # global coordinates per dimension
     u0: np.ndarray                 # shape (N_{nd-1}, ..., N_0, nvars)
+    muscl: Optional[Dict[str, object]] = None      # muscl.inp (epsilon, limiter) for muscl2 / muscl3
 
     @property
     def ndims(self) -> int:
@@ -53,6 +54,8 @@ class Case:
         hypario.write_keyword_file(os.path.join(d, "physics.inp"), self.physics)
         if self.weno is not None:
             hypario.write_keyword_file(os.path.join(d, "weno.inp"), self.weno)
+        if self.muscl is not None:
+            hypario.write_keyword_file(os.path.join(d, "muscl.inp"), self.muscl)
         hypario.write_initial_bin(os.path.join(d, "initial.inp"), self.x, self.u0)
 
 
@@ -79,6 +82,14 @@ def with_time_scheme(case: "Case", time_scheme: str, tstype: str = " ") -> "Case
     if time_scheme == "euler":
         del case.solver["time_scheme_type"]          # no type keyword for forward Euler (ReadInputs.c:131)
     case.name += f"_{time_scheme}{'' if time_scheme == 'euler' else tstype}"
+    return case
+
+
+def with_muscl(case: "Case", scheme: str, epsilon: float = 1e-3, limiter: str = "gmm") -> "Case":
+    """the same case with a MUSCL reconstruction (muscl2: limiter; muscl3: epsilon) and its muscl.inp"""
+    case.solver["hyp_space_scheme"] = scheme
+    case.muscl = {"epsilon": float(epsilon), "limiter": limiter}
+    case.name += f"_{scheme}_{limiter if scheme == 'muscl2' else epsilon}"
     return case
 
 

@@ -50,6 +50,7 @@ extern "C" void hpb_config_defaults(hpb_config* c)
   c->use_fused = 1;
   c->conservation_check = 0;
   c->hyp_scheme = HPB_SCHEME_WENO5;
+  c->muscl_limiter = HPB_LIMITER_GMM; c->muscl_eps = 1e-3;     // MUSCLInitialize.c:26-27
 }
 
 // ------------------------------------------------------------------------------------ helpers

@@ -76,8 +76,11 @@ int hpb_setup_host(hpb_solver* h)
     return hpb_fail(HPB_ERR_INVALID, "navierstokes2d: gravity has two components");
   if (c.model == HPB_MODEL_LINEAR_ADR && c.par_scheme != 2 && c.par_scheme != 4)
     return hpb_fail(HPB_ERR_INVALID, "par_space_scheme %d not supported (2, 4)", c.par_scheme);
-  if (c.hyp_scheme < HPB_SCHEME_WENO5 || c.hyp_scheme > HPB_SCHEME_FOURTH)
-    return hpb_fail(HPB_ERR_INVALID, "hyp_space_scheme %d not supported (weno5, crweno5, cupw5, upw5, 1, 2, 4)", c.hyp_scheme);
+  if (c.hyp_scheme < HPB_SCHEME_WENO5 || c.hyp_scheme > HPB_SCHEME_MUSCL3)
+    return hpb_fail(HPB_ERR_INVALID, "hyp_space_scheme %d not supported (weno5, crweno5, cupw5, upw5, 1, 2, 4, muscl2, muscl3)",
+                    c.hyp_scheme);
+  if (c.muscl_limiter < HPB_LIMITER_GMM || c.muscl_limiter > HPB_LIMITER_SUPERBEE)
+    return hpb_fail(HPB_ERR_INVALID, "muscl limiter %d not supported (gmm, minmod, vanleer, superbee)", c.muscl_limiter);
   if (c.hyp_scheme != HPB_SCHEME_WENO5 && c.interp_char && c.nvars > 1)
     return hpb_fail(HPB_ERR_INVALID, "characteristic reconstruction is implemented for weno5 only "
                     "(the compact schemes would need the block-tridiagonal solver, blocktridiagLU.c)");
@@ -206,7 +209,7 @@ int hpb_setup_host(hpb_solver* h)
   P.model = c.model; P.weno = c.weno_type; P.no_limiting = c.no_limiting;
   P.interp_char = (c.interp_char && c.nvars > 1) ? 1 : 0;        // WENOInitialize.c:156
   P.upwind = c.upwind; P.par_scheme = c.par_scheme; P.has_grav = has_grav ? 1 : 0;
-  P.scheme = c.hyp_scheme;
+  P.scheme = c.hyp_scheme; P.muscl_limiter = c.muscl_limiter; P.muscl_eps = c.muscl_eps;
   P.eps = c.weno_eps; P.gamma = c.gamma;
   P.Re = c.Re / c.Minf;                                          // NavierStokes3DInitialize.c:368
   P.Pr = c.Pr;

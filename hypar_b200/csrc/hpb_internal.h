@@ -26,6 +26,8 @@ struct Geom {
 struct Phys {
   int model, weno, no_limiting, interp_char, upwind, par_scheme, has_grav;
   int scheme;                        // HPB_SCHEME_*
+  int muscl_limiter;                 // HPB_LIMITER_* (muscl2)
+  double muscl_eps;                  // muscl3
   double eps, gamma, Re, Pr, RT;     // Re already / Minf ; RT = p0/rho0
   double grav[3];
   double adv[15], diff[15];

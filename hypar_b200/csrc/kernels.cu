@@ -995,7 +995,17 @@ __global__ void k_tridiag(Geom G, int dir, double* __restrict__ A, double* __res
 
 // the linear schemes, component-wise: Interp1PrimFifthOrderUpwind.c:60-147, Interp1PrimFirstOrderUpwind.c:78-84,
 // Interp1PrimSecondOrderCentral.c:80-88, Interp1PrimFourthOrderCentral.c:96-120
-__global__ void k_interp_upw5(Geom G, int scheme, const double* __restrict__ fC, int upw, int dir, double* __restrict__ fI)
+// ... and the MUSCL schemes: Interp1PrimSecondOrderMUSCL.c:118-156 (limiters of src/LimiterFunctions/),
+// Interp1PrimThirdOrderMUSCL.c:118-160 (Koren's limiter with the epsilon of muscl.inp)
+__device__ __forceinline__ double muscl_limiter_fn(int type, double r)
+{
+  if (type == HPB_LIMITER_MINMOD)   return fmax(0.0, fmin(1.0, r));
+  if (type == HPB_LIMITER_VANLEER)  return (r + fabs(r)) / (1.0 + fabs(r));
+  if (type == HPB_LIMITER_SUPERBEE) return fmax(fmax(0.0, fmin(2 * r, 1.0)), fmin(r, 2.0));
+  return fmax(0.0, fmin(fmin(r, 0.5 * (1.0 + r)), 1.0));          // generalised minmod, theta = 1
+}
+__global__ void k_interp_upw5(Geom G, int scheme, int limiter, double meps, const double* __restrict__ fC, int upw, int dir,
+                              double* __restrict__ fI)
 {
   const double c1 = 7.0 / 12.0, c2 = -1.0 / 12.0;
   const double one_by_thirty = 1.0 / 30.0, thirteen_by_sixty = 13.0 / 60.0, fortyseven_by_sixty = 47.0 / 60.0,
@@ -1013,7 +1023,31 @@ __global__ void k_interp_upw5(Geom G, int scheme, const double* __restrict__ fC,
   for (int v = 0; v < G.nvars; v++) {
     const double* f = fC + v * G.npg;
     double r;
-    if (scheme == HPB_SCHEME_FIRST)       r = f[ps[2]];
+    if (scheme == HPB_SCHEME_MUSCL3 || scheme == HPB_SCHEME_MUSCL2) {
+      // biased numbering: ps[1], ps[2], ps[3] = the two cells on the upwind side and the one beyond the interface
+      const double a2 = f[ps[1]], a1 = f[ps[2]], b1 = f[ps[3]];
+      if (scheme == HPB_SCHEME_MUSCL3) {
+        const double one_third = 1.0 / 3.0, one_sixth = 1.0 / 6.0;
+        if (upw > 0) {
+          const double fdiff = b1 - a1, bdiff = a1 - a2;
+          const double limit = (3 * fdiff * bdiff + meps) / (2 * (fdiff - bdiff) * (fdiff - bdiff) + 3 * fdiff * bdiff + meps);
+          r = a1 + limit * (one_third * fdiff + one_sixth * bdiff);
+        } else {          // reference names: m1 = b1, p1 = a1, p2 = a2
+          const double fdiff = a2 - a1, bdiff = a1 - b1;
+          const double limit = (3 * fdiff * bdiff + meps) / (2 * (fdiff - bdiff) * (fdiff - bdiff) + 3 * fdiff * bdiff + meps);
+          r = a1 - limit * (one_third * fdiff + one_sixth * bdiff);
+        }
+      } else {
+        if (upw > 0) {
+          const double slope_ratio = (a1 - a2) / ((b1 - a1) + 1e-40);
+          r = a1 + 0.5 * muscl_limiter_fn(limiter, slope_ratio) * (b1 - a1);
+        } else {
+          const double slope_ratio = (a1 - b1) / ((a2 - a1) + 1e-40);
+          r = a1 + 0.5 * muscl_limiter_fn(limiter, slope_ratio) * (a1 - a2);
+        }
+      }
+    }
+    else if (scheme == HPB_SCHEME_FIRST)  r = f[ps[2]];
     else if (scheme == HPB_SCHEME_SECOND) r = 0.5 * (f[qL] + f[qR]);
     else if (scheme == HPB_SCHEME_FOURTH) r = c2 * f[qL - st] + c1 * f[qL] + c1 * f[qR] + c2 * f[qR + st];
     else r = one_by_thirty * f[ps[0]] - thirteen_by_sixty * f[ps[1]] + fortyseven_by_sixty * f[ps[2]]
@@ -1402,7 +1436,8 @@ void weno_interp(hpb_solver* h, double* fI, const double* fC, const double* u, c
   const Geom& G = h->geo;
   const int M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
   if (h->cfg.hyp_scheme >= HPB_SCHEME_UPW5) {
-    k_interp_upw5<<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->cfg.hyp_scheme, fC, upw, dir, fI); LAUNCHED(h);
+    k_interp_upw5<<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->cfg.hyp_scheme, h->phys.muscl_limiter, h->phys.muscl_eps,
+                                                                   fC, upw, dir, fI); LAUNCHED(h);
     return;
   }
   if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h->cfg.hyp_scheme == HPB_SCHEME_CUPW5) {

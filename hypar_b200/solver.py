@@ -24,7 +24,8 @@ BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "d
            "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9}
 UPWINDS = {"roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 RK_TYPES = {"44": 0, "ssprk3": 1, "tvdrk3": 1, "1fe": 2, "22": 3, "33": 4}
-SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6}
+SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6, "muscl2": 7, "muscl3": 8}
+LIMITERS = {"gmm": 0, "minmod": 1, "vanleer": 2, "superbee": 3}
 FIELD_U, FIELD_QDERIVX, FIELD_QDERIVY = 0, 1, 2
 
 
@@ -40,8 +41,8 @@ def _dp(a: np.ndarray):
 
 def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], physics: Dict[str, object],
                        weno: Optional[Dict[str, object]], x: Sequence[np.ndarray], rank: int = 0,
-                       device: int = -1, use_fused: bool = True):
-    """Translate the contents of solver.inp / boundary.inp / physics.inp / weno.inp (as parsed
+                       device: int = -1, use_fused: bool = True, muscl: Optional[Dict[str, object]] = None):
+    """Translate the contents of solver.inp / boundary.inp / physics.inp / weno.inp / muscl.inp (as parsed
     dictionaries) into an ``hpb_config``. Unsupported choices raise here or in ``hpb_create``."""
     L = _lib.load()
     c = _lib.Config()
@@ -60,8 +61,11 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     c.model = MODELS[model]
     scheme = str(solver.get("hyp_space_scheme", "1"))
     if scheme not in SCHEMES:
-        raise HyParB200Error(f"hyp_space_scheme '{scheme}' is not on the B200 path (weno5, crweno5, cupw5, upw5, 1, 2, 4)")
+        raise HyParB200Error(f"hyp_space_scheme '{scheme}' is not on the B200 path (weno5, crweno5, cupw5, upw5, 1, 2, 4, muscl2, muscl3)")
     c.hyp_scheme = SCHEMES[scheme]
+    mu = muscl or {}
+    c.muscl_eps = float(mu.get("epsilon", 1e-3))                         # MUSCLInitialize.c:26-27
+    c.muscl_limiter = LIMITERS.get(str(mu.get("limiter", "gmm")), 0)     # :72-75: unknown names fall back to gmm
     ts = str(solver.get("time_scheme", "euler"))
     if ts not in ("rk", "euler"):
         raise HyParB200Error(f"time_scheme '{ts}' is not on the B200 path (rk, euler)")
@@ -145,10 +149,10 @@ class Solver:
     """One rank of the B200 explicit-RHS path."""
 
     def __init__(self, solver: Dict[str, object], boundary, physics, weno, x, rank: int = 0,
-                 device: int = -1, use_fused: bool = True):
+                 device: int = -1, use_fused: bool = True, muscl=None):
         self.L = _lib.load()
-        self.inputs = {"solver": solver, "boundary": boundary, "physics": physics, "weno": weno}
-        cfg, self._xg = config_from_inputs(solver, boundary, physics, weno, x, rank, device, use_fused)
+        self.inputs = {"solver": solver, "boundary": boundary, "physics": physics, "weno": weno, "muscl": muscl}
+        cfg, self._xg = config_from_inputs(solver, boundary, physics, weno, x, rank, device, use_fused, muscl)
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.hpb_create(C.byref(cfg), C.byref(self.h))
@@ -171,7 +175,8 @@ class Solver:
     # -- construction helpers
     @classmethod
     def from_case(cls, case, rank: int = 0, device: int = -1, use_fused: bool = True) -> "Solver":
-        return cls(case.solver, case.boundary, case.physics, case.weno, case.x, rank, device, use_fused)
+        return cls(case.solver, case.boundary, case.physics, case.weno, case.x, rank, device, use_fused,
+                   muscl=getattr(case, "muscl", None))
 
     @classmethod
     def from_directory(cls, path: str, rank: int = 0, device: int = -1, use_fused: bool = True) -> "Solver":
@@ -192,7 +197,9 @@ class Solver:
         if str(s.get("ip_file_type", "ascii")) not in ("binary", "bin"):
             raise HyParB200Error("only binary initial.inp is read by the B200 host layer")
         x, u0 = hypario.read_initial_bin(os.path.join(path, "initial.inp"), s["size"], nv)
-        obj = cls(s, b, ph, w, x, rank, device, use_fused)
+        mf = os.path.join(path, "muscl.inp")
+        mu = hypario.read_keyword_file(mf) if os.path.exists(mf) else None
+        obj = cls(s, b, ph, w, x, rank, device, use_fused, muscl=mu)
         obj.u0_global = u0
         return obj
 

@@ -73,6 +73,13 @@ extern "C" {
 #define HPB_SCHEME_FIRST   4    /* "1": first-order upwind  (Interp1PrimFirstOrderUpwind.c)   */
 #define HPB_SCHEME_SECOND  5    /* "2": second-order central (Interp1PrimSecondOrderCentral.c) */
 #define HPB_SCHEME_FOURTH  6    /* "4": fourth-order central (Interp1PrimFourthOrderCentral.c) */
+#define HPB_SCHEME_MUSCL2  7    /* "muscl2": Interp1PrimSecondOrderMUSCL.c, limiter from muscl.inp */
+#define HPB_SCHEME_MUSCL3  8    /* "muscl3": Interp1PrimThirdOrderMUSCL.c (Koren), epsilon from muscl.inp */
+/* muscl.inp `limiter` -- MUSCLInitialize.c:62-75, src/LimiterFunctions/ */
+#define HPB_LIMITER_GMM      0
+#define HPB_LIMITER_MINMOD   1
+#define HPB_LIMITER_VANLEER  2
+#define HPB_LIMITER_SUPERBEE 3
 
 /* boundary.inp zone types implemented on the device (reference: 17 types, src/BoundaryConditions/BCInitialize.c; the first
    three are the ones the BASELINE configurations use, the others cover the reference's Navier-Stokes examples;
@@ -146,6 +153,9 @@ typedef struct hpb_config {
   int    conservation_check;           /* ConservationCheck "yes": keep the boundary-flux bookkeeping of
                                           HyperbolicFunction.c:103-106 / TimeRK.c:172-193 on the device       */
   int    hyp_scheme;                   /* hyp_space_scheme: HPB_SCHEME_* (default WENO5)                      */
+  /* --- muscl.inp --- */
+  int    muscl_limiter;                /* HPB_LIMITER_* (default gmm)                                         */
+  double muscl_eps;                    /* default 1e-3                                                        */
 } hpb_config;
 
 typedef struct hpb_solver hpb_solver;

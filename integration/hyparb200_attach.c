@@ -33,6 +33,7 @@
 #include <timeintegration.h>
 #include <boundaryconditions.h>
 #include <interpolation.h>
+#include <limiters.h>
 #include <physicalmodels/linearadr.h>
 #include <physicalmodels/euler1d.h>
 #include <physicalmodels/navierstokes2d.h>
@@ -190,6 +191,8 @@ int hyparb200_attach(void *sims, int nsims)
   else if (!strcmp(s->spatial_scheme_hyp, _FIRST_ORDER_UPWIND_))         scheme = HPB_SCHEME_FIRST;
   else if (!strcmp(s->spatial_scheme_hyp, _SECOND_ORDER_CENTRAL_))       scheme = HPB_SCHEME_SECOND;
   else if (!strcmp(s->spatial_scheme_hyp, _FOURTH_ORDER_CENTRAL_))       scheme = HPB_SCHEME_FOURTH;
+  else if (!strcmp(s->spatial_scheme_hyp, _SECOND_ORDER_MUSCL_))         scheme = HPB_SCHEME_MUSCL2;
+  else if (!strcmp(s->spatial_scheme_hyp, _THIRD_ORDER_MUSCL_))          scheme = HPB_SCHEME_MUSCL3;
   if (scheme < 0 || strcmp(s->time_scheme, _RK_) || strcmp(s->SplitHyperbolicFlux, "no") || s->flag_ib) {
     fprintf(stderr, "hyparb200_attach: only weno5 / crweno5 / cupw5 / upw5 + explicit RK without flux splitting / "
                     "immersed boundaries is on the B200 path\n");
@@ -210,6 +213,12 @@ int hyparb200_attach(void *sims, int nsims)
   c.par_scheme = atoi(s->spatial_scheme_par);
   c.conservation_check = !strcmp(s->ConservationCheck, "yes");
   c.hyp_scheme = scheme;
+  if (scheme == HPB_SCHEME_MUSCL2 || scheme == HPB_SCHEME_MUSCL3) {
+    MUSCLParameters *mp = (MUSCLParameters*) s->interp;
+    c.muscl_eps = mp->eps;
+    c.muscl_limiter = !strcmp(mp->limiter_type, _LIM_MM_) ? HPB_LIMITER_MINMOD : !strcmp(mp->limiter_type, _LIM_VANLEER_) ? HPB_LIMITER_VANLEER
+                    : !strcmp(mp->limiter_type, _LIM_SUPERBEE_) ? HPB_LIMITER_SUPERBEE : HPB_LIMITER_GMM;
+  }
   if (scheme == HPB_SCHEME_WENO5 || scheme == HPB_SCHEME_CRWENO5) {   /* s->interp is NULL for the linear schemes */
     WENOParameters *w = (WENOParameters*) s->interp;
     c.weno_type = w->yc ? HPB_WENO_YC : w->borges ? HPB_WENO_Z : w->mapped ? HPB_WENO_M : HPB_WENO_JS;

@@ -26,7 +26,8 @@ MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "dirichlet": 4, "subsonic-inflow": 5,
            "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9}
 UPWINDS = {"default": 0, "roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
-SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6}
+SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6, "muscl2": 7, "muscl3": 8}
+LIMITERS = {"gmm": 0, "minmod": 1, "vanleer": 2, "superbee": 3}
 
 
 class Zone(C.Structure):
@@ -50,7 +51,7 @@ class Ctx(C.Structure):
                 ("zones", Zone * MAXZ),
                 ("x", C.POINTER(C.c_double)), ("dxinv", C.POINTER(C.c_double)),
                 ("grav_f", C.POINTER(C.c_double)), ("grav_g", C.POINTER(C.c_double)),
-                ("scheme", C.c_int)]
+                ("scheme", C.c_int), ("muscl_limiter", C.c_int), ("muscl_eps", C.c_double)]
 
 
 _lib = None
@@ -268,6 +269,9 @@ class Setup:
             c.dim[d], c.iproc[d], c.ip[d], c.periodic[d] = self.dim[d], self.iproc[d], self.ip[d], self.periodic[d]
         c.model = MODELS[s["model"]]
         c.scheme = SCHEMES[str(s.get("hyp_space_scheme", "weno5"))]
+        mu = getattr(case, "muscl", None) or {}
+        c.muscl_eps = float(mu.get("epsilon", 1e-3))                       # MUSCLInitialize.c:26-27 defaults
+        c.muscl_limiter = LIMITERS.get(str(mu.get("limiter", "gmm")), 0)   # :72-75: unknown names fall back to gmm
         c.weno_type = 3 if int(w.get("yc", 0)) else 2 if int(w.get("borges", 0)) else 1 if int(w.get("mapped", 0)) else 0
         c.no_limiting = int(w.get("no_limiting", 0))
         c.weno_eps = float(w.get("epsilon", 1e-6))

@@ -147,14 +147,14 @@ def test_unsupported_configurations_fail_loudly(mutate, msg):
     _lib.load().hpb_clear_error()
 
 
-@pytest.mark.parametrize("scheme", ["crweno5", "cupw5", "upw5", "1", "2", "4"])
+@pytest.mark.parametrize("scheme", ["crweno5", "cupw5", "upw5", "1", "2", "4", "muscl2", "muscl3"])
 def test_compact_and_linear_schemes_are_accepted(scheme):
     """crweno5 / cupw5 (one rank per line) and upw5 (any decomposition) set up like weno5"""
     case = cases.ns3d_rising_bubble((12, 12, 12), "yc", scheme=scheme)
     sv = Solver.from_case(case)
     assert sv.dim_local == [12, 12, 12]
     sv.close()
-    if scheme in ("upw5", "1", "2", "4"):
+    if scheme in ("upw5", "1", "2", "4", "muscl2", "muscl3"):
         sv = Solver.from_case(cases.ns3d_turbulence((12, 12, 12), "js", iproc=(1, 2, 1), scheme=scheme), rank=1)
         assert sv.dim_local == [12, 6, 12]
         sv.close()

@@ -103,6 +103,12 @@ def _cases():
     C.append(cases.ns2d_vortex((28, 24), "js", scheme="2"))
     C.append(cases.ns3d_rising_bubble((12, 14, 10), "js", scheme="4"))
     C.append(cases.ns_channel((16, 12, 14), "js", scheme="1"))
+    # MUSCL reconstructions
+    C.append(cases.with_muscl(cases.euler1d_sod(101, "js", interp="components", upwinding="rusanov"), "muscl2", limiter="vanleer"))
+    C.append(cases.with_muscl(cases.ns2d_vortex((28, 24), "js", upwinding="roe"), "muscl2", limiter="superbee"))
+    C.append(cases.with_muscl(cases.ns2d_vortex((24, 28), "js"), "muscl2", limiter="minmod"))
+    C.append(cases.with_muscl(cases.ns3d_rising_bubble((12, 14, 10), "js"), "muscl3", epsilon=1e-6))
+    C.append(cases.with_muscl(cases.ns_channel((16, 12, 14), "js"), "muscl2"))
     return C
 
 
@@ -187,7 +193,8 @@ STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CA
               CASES[34], CASES[36], CASES[37], CASES[38], CASES[40], CASES[41], CASES[43], CASES[45],
               CASES[46], CASES[47], CASES[48], CASES[49], CASES[50], CASES[51], CASES[53],
               CASES[56], CASES[57], CASES[58], CASES[59], CASES[60], CASES[61], CASES[62], CASES[63], CASES[64],
-              CASES[65], CASES[66], CASES[67], CASES[68], CASES[69], CASES[70]]
+              CASES[65], CASES[66], CASES[67], CASES[68], CASES[69], CASES[70],
+              CASES[71], CASES[72], CASES[73], CASES[74], CASES[75]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)
@@ -246,7 +253,7 @@ def test_time_steps_parity(need_gpu, case):
 
 @pytest.mark.parametrize("case", [CASES[4], CASES[12], CASES[16], CASES[20], CASES[26],
                                   CASES[35], CASES[37], CASES[40], CASES[42], CASES[44], CASES[51], CASES[52], CASES[53],
-                                  CASES[56], CASES[58], CASES[60], CASES[65], CASES[69]],
+                                  CASES[56], CASES[58], CASES[60], CASES[65], CASES[69], CASES[72], CASES[74]],
                          ids=lambda c: c.name)
 def test_function_pointer_pieces(need_gpu, case):
     """FFunction, UFunction, SetInterpLimiterVar, InterpolateInterfacesHyp, Upwind,

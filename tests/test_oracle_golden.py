@@ -165,6 +165,13 @@ def _live_cases():
         cases.ns2d_vortex((24, 20), "js", scheme="2"),
         cases.ns3d_rising_bubble((10, 14, 12), "js", scheme="4"),
         cases.ns_channel((12, 10, 14), "js", viscous=True, scheme="1"),
+        # MUSCL reconstructions (muscl.inp: limiter of muscl2, epsilon of muscl3)
+        cases.with_muscl(cases.linear_advection_sine(96, "js"), "muscl3"),
+        cases.with_muscl(cases.euler1d_sod(101, "js", interp="components", upwinding="rusanov"), "muscl2", limiter="vanleer"),
+        cases.with_muscl(cases.ns2d_vortex((24, 20), "js", upwinding="roe"), "muscl2", limiter="superbee"),
+        cases.with_muscl(cases.ns2d_vortex((20, 24), "js"), "muscl2", limiter="minmod"),
+        cases.with_muscl(cases.ns3d_rising_bubble((10, 14, 12), "js"), "muscl3", epsilon=1e-6),
+        cases.with_muscl(cases.ns_channel((12, 10, 14), "js", viscous=True), "muscl2"),
         # the other explicit RK tableaux (TimeExplicitRKInitialize.c:27-79) and forward Euler (TimeForwardEuler.c)
         cases.with_time_scheme(cases.linear_advection_sine(96, "js"), "rk", "1fe"),
         cases.with_time_scheme(cases.euler1d_sod(101, "mapped"), "rk", "22"),
