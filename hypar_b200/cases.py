@@ -138,7 +138,8 @@ def linear_advection_sine(n: int = 1024, weno: str = "js", dt: float = 5e-4,
 
 # ------------------------------------------------------------------------------------- C2
 def euler1d_sod(n: int = 201, weno: str = "js", interp: str = "characteristic",
-                upwinding: str = "roe", tstype: str = "ssprk3", scheme: str = "weno5") -> Case:
+                upwinding: str = "roe", tstype: str = "ssprk3", scheme: str = "weno5",
+                gravity: float = 0.0, gravity_type: int = 0) -> Case:
     x = np.arange(n, dtype=np.float64) / (n - 1)
     gamma = 1.4
     rho = np.where(x < 0.5, 1.0, 0.125)
@@ -146,11 +147,14 @@ def euler1d_sod(n: int = 201, weno: str = "js", interp: str = "characteristic",
     v = np.zeros_like(x)
     u = np.stack([rho, rho * v, p / (gamma - 1.0) + 0.5 * rho * v * v], axis=-1)
     return Case(
-        name=f"c2_sod_{n}_{weno}_{interp}_{upwinding}" + _sfx(scheme),
+        name=f"c2_sod_{n}_{weno}_{interp}_{upwinding}" + _sfx(scheme)
+             + (f"_grav{gravity_type}" if gravity != 0.0 else ""),
         solver=_solver(1, 3, [n], "euler1d", ts="rk", tstype=tstype, dt=2.5e-3 * (201.0 / n),
                        interp=interp, scheme=scheme),
         boundary=_zones(1, "extrapolate", [-1e3], [1e3]),
-        physics={"gamma": gamma, "upwinding": upwinding}, weno=weno_inp(weno), x=[x], u0=u)
+        physics=({"gamma": gamma, "upwinding": upwinding} if gravity == 0.0 else
+                 {"gamma": gamma, "upwinding": upwinding, "gravity": float(gravity), "gravity_type": int(gravity_type)}),
+        weno=weno_inp(weno), x=[x], u0=u)
 
 
 # ------------------------------------------------------------------------------------- C3

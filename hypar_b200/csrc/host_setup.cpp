@@ -65,8 +65,12 @@ int hpb_setup_host(hpb_solver* h)
       (c.upwind < HPB_UPWIND_ROE || c.upwind > HPB_UPWIND_LLF))
     return hpb_fail(HPB_ERR_INVALID, "upwinding %d not implemented (roe, rusanov, rf-char, llf-char)", c.upwind);
   const bool has_grav = (c.gravity[0] != 0.0 || c.gravity[1] != 0.0 || c.gravity[2] != 0.0);
-  if (has_grav && c.model != HPB_MODEL_NS3D && c.model != HPB_MODEL_NS2D)
-    return hpb_fail(HPB_ERR_INVALID, "gravity is implemented for navierstokes2d and navierstokes3d only");
+  if (has_grav && c.model == HPB_MODEL_LINEAR_ADR)
+    return hpb_fail(HPB_ERR_INVALID, "gravity needs an Euler / Navier-Stokes model");
+  if (has_grav && c.model == HPB_MODEL_EULER1D && c.upwind != HPB_UPWIND_LLF && c.upwind != HPB_UPWIND_ROE)   // Euler1DInitialize.c:144-149
+    return hpb_fail(HPB_ERR_INVALID, "llf-char or roe upwinding is needed for flows with gravitational forces");
+  if (c.model == HPB_MODEL_EULER1D && (c.gravity[1] != 0.0 || c.gravity[2] != 0.0 || c.gravity_type < 0 || c.gravity_type > 1))
+    return hpb_fail(HPB_ERR_INVALID, "euler1d: one gravity component, gravity_type 0 or 1");
   if (has_grav && c.model == HPB_MODEL_NS3D && c.upwind != HPB_UPWIND_RUSANOV)      // NavierStokes3DInitialize.c:371-378
     return hpb_fail(HPB_ERR_INVALID, "rusanov upwinding is needed for flows with gravitational forces");
   if (has_grav && c.model == HPB_MODEL_NS2D && c.upwind != HPB_UPWIND_RUSANOV && c.upwind != HPB_UPWIND_ROE &&
@@ -266,6 +270,24 @@ int hpb_setup_host(hpb_solver* h)
         h->gravf_h[p1] = h->gravf_h[p2]; h->gravg_h[p1] = h->gravg_h[p2];
       }
     }
+  }
+
+  if (c.model == HPB_MODEL_EULER1D) {
+    // Euler1DGravityField.c:25-95: ONE field S, used as both grav_f and grav_g here; type 0 exp(-g x) with mirror copies into
+    // the ghosts of physical faces, type 1 exp(sin(2 pi x) / (2 pi)) without
+    const double* X = h->x_h.data();
+    const int n = G.N[0];
+    for (int i = 0; i < G.P[0]; i++) {
+      double S = 1.0;
+      if (c.gravity_type == 0) S = exp(-c.gravity[0] * X[i]);
+      else { const double pi = 4.0 * atan(1.0); const double phi = -sin(2 * pi * X[i]) / (2 * pi); S = exp(-phi); }
+      h->gravf_h[i] = S;
+    }
+    if (c.gravity_type != 1) {
+      if (h->ip[0] == 0)              for (int k = 0; k < g; k++) h->gravf_h[k] = h->gravf_h[g + (g - 1 - k)];
+      if (h->ip[0] == c.iproc[0] - 1) for (int k = 0; k < g; k++) h->gravf_h[g + n + k] = h->gravf_h[g + (n - 1 - k)];
+    }
+    for (int i = 0; i < G.P[0]; i++) h->gravg_h[i] = h->gravf_h[i];
   }
 
   // ---- RK tableau

@@ -280,7 +280,8 @@ k_iface(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict_
 #pragma unroll
   for (int v = 0; v < NV; v++) fI[v * ni + q] = fhat[v];
 
-  if ((MODEL == HPB_MODEL_NS3D || MODEL == HPB_MODEL_NS2D) && sI != nullptr) {
+  if ((MODEL == HPB_MODEL_NS3D || MODEL == HPB_MODEL_NS2D || MODEL == HPB_MODEL_EULER1D) && sI != nullptr) {
+    // Euler1D (Euler1DSource.c:90-123): G = S (0, 1, 1) with the one field S = grav_field -- the same two components
     // source function G_j = g_grav_j * (0, d_x, d_y, d_z, 1): only components dir+1 and 4 are non-zero
     const int vm = dir + 1;
     const double sLm = weno_combine(wLF[vm][0], wLF[vm][1], wLF[vm][2], GG[0], GG[1], GG[2], GG[3], GG[4]);
@@ -331,9 +332,11 @@ __global__ void k_ns3d_source(Geom G, Phys ph, const double* __restrict__ dxinv,
   const int idx = (dir == 0 ? i0 : dir == 1 ? i1 : i2);
   const double dxi = dxinv[G.xoff[dir] + G.g + idx];
   const double rho = u[p];
-  const double vd = (rho == 0) ? 0.0 : u[(1 + dir) * G.npg + p] / rho;
-  const double f = gf[p];
-  const double tm = rho * ph.RT, te = rho * ph.RT * vd;
+  const double vd = (rho == 0 && ph.model != HPB_MODEL_EULER1D) ? 0.0 : u[(1 + dir) * G.npg + p] / rho;
+  // Navier-Stokes: term = rho RT (1, v_dir), factor f_grav; Euler1D (Euler1DSource.c:62-66): term = rho (1, v), factor 1 / S
+  const bool e1d = (ph.model == HPB_MODEL_EULER1D);
+  const double f = e1d ? (1.0 / gf[p]) : gf[p];
+  const double tm = e1d ? rho : rho * ph.RT, te = e1d ? rho * vd : rho * ph.RT * vd;
   out[(1 + dir) * G.npg + p] += ((tm * f) * (sI[q1 + qs] - sI[q1]) * dxi);
   out[(long long)(G.nvars - 1) * G.npg + p] += ((te * f) * (sI[ni + q1 + qs] - sI[ni + q1]) * dxi);   // energy: last component
 }

@@ -108,9 +108,9 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     if c.model == 2:
         grav = (grav + [0.0, 0.0])[:2] + [0.0]
     elif c.model == 1:
-        if float(ph.get("gravity", 0.0) if not isinstance(ph.get("gravity", 0.0), (list, tuple)) else 0.0) != 0.0:
-            raise HyParB200Error("euler1d with gravity is not on the B200 path")
-        grav = [0.0] * 3
+        g1 = ph.get("gravity", 0.0)
+        grav = [float(g1[0] if isinstance(g1, (list, tuple)) else g1), 0.0, 0.0]
+        c.gravity_type = int(ph.get("gravity_type", 0))
     for d in range(min(3, len(grav))):
         c.gravity[d] = float(grav[d])
     c.rho_ref, c.p_ref, c.R = float(ph.get("rho_ref", 1.0)), float(ph.get("p_ref", 1.0)), float(ph.get("R", 1.0))

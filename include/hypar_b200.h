@@ -156,6 +156,9 @@ typedef struct hpb_config {
   /* --- muscl.inp --- */
   int    muscl_limiter;                /* HPB_LIMITER_* (default gmm)                                         */
   double muscl_eps;                    /* default 1e-3                                                        */
+  /* --- physics.inp (cont.) --- */
+  int    gravity_type;                 /* Euler1D `gravity_type` (Euler1DGravityField.c:44-52): 0 exp(-g x), 1 sinusoidal
+                                          potential; the 1-D gravity is gravity[0]                             */
 } hpb_config;
 
 typedef struct hpb_solver hpb_solver;

@@ -244,7 +244,7 @@ int hyparb200_attach(void *sims, int nsims)
     Euler1D *p = (Euler1D*) s->physics;
     c.model = HPB_MODEL_EULER1D;  c.gamma = p->gamma;
     c.upwind = upwind_choice(p->upw_choice);
-    if (p->grav != 0.0) { fprintf(stderr, "hyparb200_attach: euler1d with gravity is not on the B200 path\n"); return 1; }
+    c.gravity[0] = p->grav;  c.gravity_type = p->grav_type;
   } else if (!strcmp(s->model, _LINEAR_ADVECTION_DIFFUSION_REACTION_)) {
     LinearADR *p = (LinearADR*) s->physics;
     c.model = HPB_MODEL_LINEAR_ADR;  c.upwind = HPB_UPWIND_DEFAULT;

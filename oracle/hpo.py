@@ -51,7 +51,7 @@ class Ctx(C.Structure):
                 ("zones", Zone * MAXZ),
                 ("x", C.POINTER(C.c_double)), ("dxinv", C.POINTER(C.c_double)),
                 ("grav_f", C.POINTER(C.c_double)), ("grav_g", C.POINTER(C.c_double)),
-                ("scheme", C.c_int), ("muscl_limiter", C.c_int), ("muscl_eps", C.c_double)]
+                ("scheme", C.c_int), ("muscl_limiter", C.c_int), ("muscl_eps", C.c_double), ("grav_type", C.c_int)]
 
 
 _lib = None
@@ -312,8 +312,11 @@ class Setup:
         n = self.npoints_g
         self.grav_f, self.grav_g = np.ones(n), np.ones(n)
         c.grav_f, c.grav_g = _p(self.grav_f), _p(self.grav_g)
+        c.grav_type = int(ph.get("gravity_type", 0))
         if c.model in (2, 3):       # NavierStokes2D / 3D gravity field (identical to 1 without gravity, HB 1)
             lib().hpo_ns3d_gravity_field(C.byref(c), _p(self.grav_f), _p(self.grav_g))
+        elif c.model == 1:          # Euler1D: one field (exp(0) = 1 without gravity)
+            lib().hpo_e1d_gravity_field(C.byref(c), _p(self.grav_f), _p(self.grav_g))
         return c
 
 
@@ -389,7 +392,7 @@ class Oracle:
 
     def source(self, u, w):
         src = self.zeros()
-        if self.s.ctx.model in (2, 3):
+        if self.s.ctx.model in (1, 2, 3):
             self.L.hpo_ns3d_source(self.c, _p(src), _p(u), _p(w))
         return src
 

@@ -109,6 +109,11 @@ def _cases():
     C.append(cases.with_muscl(cases.ns2d_vortex((24, 28), "js"), "muscl2", limiter="minmod"))
     C.append(cases.with_muscl(cases.ns3d_rising_bubble((12, 14, 10), "js"), "muscl3", epsilon=1e-6))
     C.append(cases.with_muscl(cases.ns_channel((16, 12, 14), "js"), "muscl2"))
+    # Euler1D with gravity
+    C.append(cases.euler1d_sod(101, "js", gravity=1.0))
+    C.append(cases.euler1d_sod(101, "mapped", interp="components", upwinding="llf-char", gravity=1.0))
+    C.append(cases.euler1d_sod(101, "z", upwinding="roe", gravity=1.0, gravity_type=1))
+    C.append(cases.euler1d_sod(101, "yc", interp="components", upwinding="llf-char", gravity=0.5, scheme="crweno5"))
     return C
 
 
@@ -194,7 +199,7 @@ STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CA
               CASES[46], CASES[47], CASES[48], CASES[49], CASES[50], CASES[51], CASES[53],
               CASES[56], CASES[57], CASES[58], CASES[59], CASES[60], CASES[61], CASES[62], CASES[63], CASES[64],
               CASES[65], CASES[66], CASES[67], CASES[68], CASES[69], CASES[70],
-              CASES[71], CASES[72], CASES[73], CASES[74], CASES[75]]
+              CASES[71], CASES[72], CASES[73], CASES[74], CASES[75], CASES[76], CASES[77], CASES[78], CASES[79]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)
@@ -253,7 +258,7 @@ def test_time_steps_parity(need_gpu, case):
 
 @pytest.mark.parametrize("case", [CASES[4], CASES[12], CASES[16], CASES[20], CASES[26],
                                   CASES[35], CASES[37], CASES[40], CASES[42], CASES[44], CASES[51], CASES[52], CASES[53],
-                                  CASES[56], CASES[58], CASES[60], CASES[65], CASES[69], CASES[72], CASES[74]],
+                                  CASES[56], CASES[58], CASES[60], CASES[65], CASES[69], CASES[72], CASES[74], CASES[76], CASES[79]],
                          ids=lambda c: c.name)
 def test_function_pointer_pieces(need_gpu, case):
     """FFunction, UFunction, SetInterpLimiterVar, InterpolateInterfacesHyp, Upwind,

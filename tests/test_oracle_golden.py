@@ -40,7 +40,7 @@ def same(a, b, what):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 35
+    assert len(GOLDEN) >= 36
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -172,6 +172,11 @@ def _live_cases():
         cases.with_muscl(cases.ns2d_vortex((20, 24), "js"), "muscl2", limiter="minmod"),
         cases.with_muscl(cases.ns3d_rising_bubble((10, 14, 12), "js"), "muscl3", epsilon=1e-6),
         cases.with_muscl(cases.ns_channel((12, 10, 14), "js", viscous=True), "muscl2"),
+        # Euler1D with gravity (Euler1DGravityField.c, Euler1DSource.c)
+        cases.euler1d_sod(101, "js", gravity=1.0),
+        cases.euler1d_sod(101, "mapped", interp="components", upwinding="llf-char", gravity=1.0),
+        cases.euler1d_sod(101, "z", upwinding="roe", gravity=1.0, gravity_type=1),
+        cases.euler1d_sod(101, "yc", interp="components", upwinding="llf-char", gravity=0.5, scheme="crweno5"),
         # the other explicit RK tableaux (TimeExplicitRKInitialize.c:27-79) and forward Euler (TimeForwardEuler.c)
         cases.with_time_scheme(cases.linear_advection_sine(96, "js"), "rk", "1fe"),
         cases.with_time_scheme(cases.euler1d_sod(101, "mapped"), "rk", "22"),
