@@ -85,6 +85,13 @@ def with_time_scheme(case: "Case", time_scheme: str, tstype: str = " ") -> "Case
     return case
 
 
+def with_characteristic(case: "Case") -> "Case":
+    """the same case with characteristic-based reconstruction (solver.inp hyp_interp_type)"""
+    case.solver["hyp_interp_type"] = "characteristic"
+    case.name += "_char"
+    return case
+
+
 def with_muscl(case: "Case", scheme: str, epsilon: float = 1e-3, limiter: str = "gmm") -> "Case":
     """the same case with a MUSCL reconstruction (muscl2: limiter; muscl3: epsilon) and its muscl.inp"""
     case.solver["hyp_space_scheme"] = scheme

@@ -211,6 +211,7 @@ k_iface(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict_
 
   double fL[NV], fR[NV], uL[NV], uR[NV];
   double wLF[NV][3], wRF[NV][3];
+  double srcL[2] = { 0.0, 0.0 }, srcR[2] = { 0.0, 0.0 };      // characteristic reconstruction of the source function
   const bool use_char = ph.interp_char && (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS2D || MODEL == HPB_MODEL_NS3D);
 
   if (!use_char) {
@@ -236,19 +237,24 @@ k_iface(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict_
     roe_average<MODEL>(ph, U[2], U[3], uavg);
     eigen<MODEL>(ph, uavg, dir, lam, L, R);
     double fLc[NV], fRc[NV], uLc[NV], uRc[NV];
+    double sLc[NV], sRc[NV];          // gravity-source function in characteristic space (only when sI != nullptr)
 #pragma unroll
     for (int v = 0; v < NV; v++) {
-      double cF[6], cU[6], cV[6];
+      double cF[6], cU[6], cV[6], cG[6];
 #pragma unroll
       for (int k = 0; k < 6; k++) {
-        double sF = 0.0, sU = 0.0, sV = 0.0;
+        double sF = 0.0, sU = 0.0, sV = 0.0, sG = 0.0;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
           sF += L[v * NV + j] * F[k][j];
           sU += L[v * NV + j] * U[k][j];
           sV += L[v * NV + j] * V[k][j];
+          // source function G_k = g_k (0, d_x, d_y, d_z, 1) (Euler1D: S (0, 1, 1)), projected like the flux
+          // (Interp1PrimFifthOrderWENOChar.c:160-176 applied to SourceC, NavierStokes3DSource.c:77-78)
+          const double Gj = (j == 0) ? 0.0 : ((j == NV - 1) ? GG[k] : GG[k] * (dir == j - 1));
+          sG += L[v * NV + j] * Gj;
         }
-        cF[k] = sF; cU[k] = sU; cV[k] = sV;
+        cF[k] = sF; cU[k] = sU; cV[k] = sV; cG[k] = sG;
       }
       double w1, w2, w3;
       if (ph.no_limiting) { w1 = 0.1; w2 = 0.6; w3 = 0.3; }
@@ -258,6 +264,8 @@ k_iface(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict_
       if (!ph.no_limiting) weno_weights_ref(ph.weno, ph.eps, cF[5], cF[4], cF[3], cF[2], cF[1], w1, w2, w3);
       wRF[v][0] = w1; wRF[v][1] = w2; wRF[v][2] = w3;
       fRc[v] = weno_combine(w1, w2, w3, cF[5], cF[4], cF[3], cF[2], cF[1]);
+      sLc[v] = weno_combine(wLF[v][0], wLF[v][1], wLF[v][2], cG[0], cG[1], cG[2], cG[3], cG[4]);
+      sRc[v] = weno_combine(wRF[v][0], wRF[v][1], wRF[v][2], cG[5], cG[4], cG[3], cG[2], cG[1]);
       if (!ph.no_limiting) weno_weights_ref(ph.weno, ph.eps, cU[0], cU[1], cU[2], cU[3], cU[4], w1, w2, w3);
       uLc[v] = weno_combine(w1, w2, w3, cV[0], cV[1], cV[2], cV[3], cV[4]);
       if (!ph.no_limiting) weno_weights_ref(ph.weno, ph.eps, cU[5], cU[4], cU[3], cU[2], cU[1], w1, w2, w3);
@@ -273,6 +281,17 @@ k_iface(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict_
       }
       fL[i] = a; fR[i] = b; uL[i] = c; uR[i] = d;
     }
+    if (sI != nullptr) {
+      // back-projection of the source function; only components dir+1 and NV-1 are consumed
+      const int rows[2] = { dir + 1, NV - 1 };
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int j = 0; j < NV; j++) { a += R[rows[r] * NV + j] * sLc[j]; b += R[rows[r] * NV + j] * sRc[j]; }
+        srcL[r] = a; srcR[r] = b;
+      }
+    }
   }
 
   double fhat[NV];
@@ -284,10 +303,14 @@ k_iface(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict_
     // Euler1D (Euler1DSource.c:90-123): G = S (0, 1, 1) with the one field S = grav_field -- the same two components
     // source function G_j = g_grav_j * (0, d_x, d_y, d_z, 1): only components dir+1 and 4 are non-zero
     const int vm = dir + 1;
-    const double sLm = weno_combine(wLF[vm][0], wLF[vm][1], wLF[vm][2], GG[0], GG[1], GG[2], GG[3], GG[4]);
-    const double sRm = weno_combine(wRF[vm][0], wRF[vm][1], wRF[vm][2], GG[5], GG[4], GG[3], GG[2], GG[1]);
-    const double sLe = weno_combine(wLF[NV-1][0], wLF[NV-1][1], wLF[NV-1][2], GG[0], GG[1], GG[2], GG[3], GG[4]);
-    const double sRe = weno_combine(wRF[NV-1][0], wRF[NV-1][1], wRF[NV-1][2], GG[5], GG[4], GG[3], GG[2], GG[1]);
+    double sLm, sRm, sLe, sRe;
+    if (use_char) { sLm = srcL[0]; sRm = srcR[0]; sLe = srcL[1]; sRe = srcR[1]; }
+    else {
+      sLm = weno_combine(wLF[vm][0], wLF[vm][1], wLF[vm][2], GG[0], GG[1], GG[2], GG[3], GG[4]);
+      sRm = weno_combine(wRF[vm][0], wRF[vm][1], wRF[vm][2], GG[5], GG[4], GG[3], GG[2], GG[1]);
+      sLe = weno_combine(wLF[NV-1][0], wLF[NV-1][1], wLF[NV-1][2], GG[0], GG[1], GG[2], GG[3], GG[4]);
+      sRe = weno_combine(wRF[NV-1][0], wRF[NV-1][1], wRF[NV-1][2], GG[5], GG[4], GG[3], GG[2], GG[1]);
+    }
     sI[q]      = 0.5 * (sLm + sRm);
     sI[ni + q] = 0.5 * (sLe + sRe);
   }

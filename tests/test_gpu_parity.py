@@ -114,6 +114,9 @@ def _cases():
     C.append(cases.euler1d_sod(101, "mapped", interp="components", upwinding="llf-char", gravity=1.0))
     C.append(cases.euler1d_sod(101, "z", upwinding="roe", gravity=1.0, gravity_type=1))
     C.append(cases.euler1d_sod(101, "yc", interp="components", upwinding="llf-char", gravity=0.5, scheme="crweno5"))
+    # gravity source reconstructed characteristic-wise
+    C.append(cases.with_characteristic(cases.ns3d_rising_bubble((12, 14, 10), "js")))
+    C.append(cases.with_characteristic(cases.ns2d_rising_bubble((24, 20), "mapped", upwinding="roe")))
     return C
 
 
@@ -199,7 +202,8 @@ STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CA
               CASES[46], CASES[47], CASES[48], CASES[49], CASES[50], CASES[51], CASES[53],
               CASES[56], CASES[57], CASES[58], CASES[59], CASES[60], CASES[61], CASES[62], CASES[63], CASES[64],
               CASES[65], CASES[66], CASES[67], CASES[68], CASES[69], CASES[70],
-              CASES[71], CASES[72], CASES[73], CASES[74], CASES[75], CASES[76], CASES[77], CASES[78], CASES[79]]
+              CASES[71], CASES[72], CASES[73], CASES[74], CASES[75], CASES[76], CASES[77], CASES[78], CASES[79],
+              CASES[80], CASES[81]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)

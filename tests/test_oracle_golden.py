@@ -172,6 +172,10 @@ def _live_cases():
         cases.with_muscl(cases.ns2d_vortex((20, 24), "js"), "muscl2", limiter="minmod"),
         cases.with_muscl(cases.ns3d_rising_bubble((10, 14, 12), "js"), "muscl3", epsilon=1e-6),
         cases.with_muscl(cases.ns_channel((12, 10, 14), "js", viscous=True), "muscl2"),
+        # gravity source reconstructed characteristic-wise (the source function goes through the same
+        # InterpolateInterfacesHyp as the flux: NavierStokes3DSource.c:77-78)
+        cases.with_characteristic(cases.ns3d_rising_bubble((10, 14, 12), "js")),
+        cases.with_characteristic(cases.ns2d_rising_bubble((20, 24), "mapped", upwinding="roe")),
         # Euler1D with gravity (Euler1DGravityField.c, Euler1DSource.c)
         cases.euler1d_sod(101, "js", gravity=1.0),
         cases.euler1d_sod(101, "mapped", interp="components", upwinding="llf-char", gravity=1.0),
