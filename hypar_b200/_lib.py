@@ -45,7 +45,7 @@ class Config(C.Structure):
 # every symbol include/hypar_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "hpb_config_defaults", "hpb_create", "hpb_destroy", "hpb_last_error", "hpb_error_state", "hpb_clear_error",
-    "hpb_device_count", "hpb_version",
+    "hpb_device_count", "hpb_version", "hpb_sizeof_config",
     "hpb_partition1d", "hpb_rank1d", "hpb_ranknd", "hpb_get_local_dims", "hpb_npoints_local_wghosts",
     "hpb_ninterfaces", "hpb_get_grid", "hpb_get_neighbors", "hpb_get_zone_extent", "hpb_get_gravity_field",
     "hpb_ApplyBoundaryConditions", "hpb_HyperbolicFunction", "hpb_ParabolicFunction", "hpb_SourceFunction",
@@ -75,6 +75,10 @@ def load():
                            "(or __graft_entry__.build()); hypar_b200 has no fallback path")
     L = C.CDLL(LIB_PATH)
     dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    L.hpb_sizeof_config.restype = C.c_size_t
+    if L.hpb_sizeof_config() != C.sizeof(Config):
+        raise RuntimeError(f"hpb_config layout mismatch: library {L.hpb_sizeof_config()} bytes, binding {C.sizeof(Config)} "
+                           "(rebuild hypar_b200/libhypar_b200.so: make -C hypar_b200/csrc)")
     L.hpb_last_error.restype = C.c_char_p
     L.hpb_version.restype = C.c_char_p
     L.hpb_config_defaults.argtypes = [C.POINTER(Config)]

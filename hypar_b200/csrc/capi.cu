@@ -27,6 +27,8 @@ extern "C" int hpb_error_state(void) { return g_err_state; }
 extern "C" void hpb_clear_error(void) { g_err_state = 0; g_err[0] = 0; }
 extern "C" const char* hpb_version(void) { return "hypar_b200 0.1 (sm_100a)"; }
 
+extern "C" size_t hpb_sizeof_config(void) { return sizeof(hpb_config); }
+
 extern "C" int hpb_device_count(void)
 {
   int n = 0;

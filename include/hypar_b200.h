@@ -172,6 +172,7 @@ int         hpb_error_state(void);
 void        hpb_clear_error(void);
 int         hpb_device_count(void);                 /* 0 when no CUDA device is visible  */
 const char* hpb_version(void);
+size_t      hpb_sizeof_config(void);                /* sizeof(hpb_config) of the library: bindings check their own layout */
 
 /* ------------------------------------------------------------------ host set-up queries
  * (pure host code, usable without a GPU: partitioning as MPIPartition1D.c / MPIRanknD.c, ghost

@@ -200,6 +200,10 @@ int hyparb200_attach(void *sims, int nsims)
   }
 
   hpb_config c;
+  if (hpb_sizeof_config() != sizeof(hpb_config)) {
+    fprintf(stderr, "hyparb200_attach: include/hypar_b200.h does not match libhypar_b200.so (hpb_config layout)\n");
+    return 1;
+  }
   hpb_config_defaults(&c);
   c.ndims = s->ndims;  c.nvars = s->nvars;  c.ghosts = s->ghosts;  c.rank = mpi->rank;  c.dt = s->dt;
   for (int d = 0; d < s->ndims; d++) { c.dim_global[d] = s->dim_global[d]; c.iproc[d] = mpi->iproc[d]; }
