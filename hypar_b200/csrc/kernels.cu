@@ -1030,55 +1030,100 @@ __device__ __forceinline__ double muscl_limiter_fn(int type, double r)
   if (type == HPB_LIMITER_SUPERBEE) return fmax(fmax(0.0, fmin(2 * r, 1.0)), fmin(r, 2.0));
   return fmax(0.0, fmin(fmin(r, 0.5 * (1.0 + r)), 1.0));          // generalised minmod, theta = 1
 }
-__global__ void k_interp_upw5(Geom G, int scheme, int limiter, double meps, const double* __restrict__ fC, int upw, int dir,
-                              double* __restrict__ fI)
+// one interface value from the six cells around it, s[0..5] = cells i-3 .. i+2 (interface between cells i-1 and i)
+__device__ __forceinline__ double linear_scheme_value(int scheme, int limiter, double meps, int upw, const double* s)
 {
   const double c1 = 7.0 / 12.0, c2 = -1.0 / 12.0;
   const double one_by_thirty = 1.0 / 30.0, thirteen_by_sixty = 13.0 / 60.0, fortyseven_by_sixty = 47.0 / 60.0,
                twentyseven_by_sixty = 27.0 / 60.0, one_by_twenty = 1.0 / 20.0;
+  // biased numbering (m3, m2, m1, p1, p2)
+  const double fm3 = (upw > 0 ? s[0] : s[5]), fm2 = (upw > 0 ? s[1] : s[4]), fm1 = (upw > 0 ? s[2] : s[3]),
+               fp1 = (upw > 0 ? s[3] : s[2]), fp2 = (upw > 0 ? s[4] : s[1]);
+  if (scheme == HPB_SCHEME_MUSCL3) {
+    const double one_third = 1.0 / 3.0, one_sixth = 1.0 / 6.0;
+    if (upw > 0) {
+      const double m2 = s[1], m1 = s[2], p1 = s[3];
+      const double fdiff = p1 - m1, bdiff = m1 - m2;
+      const double limit = (3 * fdiff * bdiff + meps) / (2 * (fdiff - bdiff) * (fdiff - bdiff) + 3 * fdiff * bdiff + meps);
+      return m1 + limit * (one_third * fdiff + one_sixth * bdiff);
+    } else {
+      const double m1 = s[2], p1 = s[3], p2 = s[4];
+      const double fdiff = p2 - p1, bdiff = p1 - m1;
+      const double limit = (3 * fdiff * bdiff + meps) / (2 * (fdiff - bdiff) * (fdiff - bdiff) + 3 * fdiff * bdiff + meps);
+      return p1 - limit * (one_third * fdiff + one_sixth * bdiff);
+    }
+  }
+  if (scheme == HPB_SCHEME_MUSCL2) {
+    if (upw > 0) {
+      const double m2 = s[1], m1 = s[2], p1 = s[3];
+      const double slope_ratio = (m1 - m2) / ((p1 - m1) + 1e-40);
+      return m1 + 0.5 * muscl_limiter_fn(limiter, slope_ratio) * (p1 - m1);
+    } else {
+      const double m1 = s[2], p1 = s[3], p2 = s[4];
+      const double slope_ratio = (p1 - m1) / ((p2 - p1) + 1e-40);
+      return p1 + 0.5 * muscl_limiter_fn(limiter, slope_ratio) * (p1 - p2);
+    }
+  }
+  if (scheme == HPB_SCHEME_FIRST)  return fm1;
+  if (scheme == HPB_SCHEME_SECOND) return 0.5 * (s[2] + s[3]);
+  if (scheme == HPB_SCHEME_FOURTH) return c2 * s[1] + c1 * s[2] + c1 * s[3] + c2 * s[4];
+  return one_by_thirty * fm3 - thirteen_by_sixty * fm2 + fortyseven_by_sixty * fm1 + twentyseven_by_sixty * fp1 - one_by_twenty * fp2;
+}
+
+// component-wise, or characteristic-wise like the reference's Interp1Prim...Char.c twins: averaged state of the two cells
+// next to the interface, its left eigenvectors applied to every stencil point, the scalar scheme per characteristic
+// field, the right eigenvectors applied to the result
+template <int MODEL>
+__global__ void k_interp_upw5(Geom G, Phys ph, const double* __restrict__ fC, const double* __restrict__ u, int upw, int dir,
+                              double* __restrict__ fI)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
   const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
   if (i0 >= M0) return;
   const long long q = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
   const long long ni = (long long)M0 * M1 * M2;
   const long long st = G.st[dir];
-  const long long pm1 = cell_index(G, i0, i1, i2) - st;
-  long long ps[5];
-  for (int k = 0; k < 5; k++) ps[k] = (upw > 0) ? pm1 + (k - 2) * st : pm1 + (3 - k) * st;
-  const long long qL = pm1, qR = pm1 + st;          // cells left / right of the interface whatever the bias
-  for (int v = 0; v < G.nvars; v++) {
-    const double* f = fC + v * G.npg;
-    double r;
-    if (scheme == HPB_SCHEME_MUSCL3 || scheme == HPB_SCHEME_MUSCL2) {
-      // biased numbering: ps[1], ps[2], ps[3] = the two cells on the upwind side and the one beyond the interface
-      const double a2 = f[ps[1]], a1 = f[ps[2]], b1 = f[ps[3]];
-      if (scheme == HPB_SCHEME_MUSCL3) {
-        const double one_third = 1.0 / 3.0, one_sixth = 1.0 / 6.0;
-        if (upw > 0) {
-          const double fdiff = b1 - a1, bdiff = a1 - a2;
-          const double limit = (3 * fdiff * bdiff + meps) / (2 * (fdiff - bdiff) * (fdiff - bdiff) + 3 * fdiff * bdiff + meps);
-          r = a1 + limit * (one_third * fdiff + one_sixth * bdiff);
-        } else {          // reference names: m1 = b1, p1 = a1, p2 = a2
-          const double fdiff = a2 - a1, bdiff = a1 - b1;
-          const double limit = (3 * fdiff * bdiff + meps) / (2 * (fdiff - bdiff) * (fdiff - bdiff) + 3 * fdiff * bdiff + meps);
-          r = a1 - limit * (one_third * fdiff + one_sixth * bdiff);
-        }
-      } else {
-        if (upw > 0) {
-          const double slope_ratio = (a1 - a2) / ((b1 - a1) + 1e-40);
-          r = a1 + 0.5 * muscl_limiter_fn(limiter, slope_ratio) * (b1 - a1);
-        } else {
-          const double slope_ratio = (a1 - b1) / ((a2 - a1) + 1e-40);
-          r = a1 + 0.5 * muscl_limiter_fn(limiter, slope_ratio) * (a1 - a2);
-        }
-      }
+  const long long pm1 = cell_index(G, i0, i1, i2) - st;      // cell i-1
+  const bool use_char = ph.interp_char && (MODEL == HPB_MODEL_EULER1D || MODEL == HPB_MODEL_NS2D || MODEL == HPB_MODEL_NS3D);
+  double S[6][NV];
+#pragma unroll
+  for (int k = 0; k < 6; k++)
+#pragma unroll
+    for (int v = 0; v < NV; v++) S[k][v] = fC[v * G.npg + pm1 + (k - 2) * st];
+  if (!use_char) {
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      double s[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) s[k] = S[k][v];
+      fI[v * ni + q] = linear_scheme_value(ph.scheme, ph.muscl_limiter, ph.muscl_eps, upw, s);
     }
-    else if (scheme == HPB_SCHEME_FIRST)  r = f[ps[2]];
-    else if (scheme == HPB_SCHEME_SECOND) r = 0.5 * (f[qL] + f[qR]);
-    else if (scheme == HPB_SCHEME_FOURTH) r = c2 * f[qL - st] + c1 * f[qL] + c1 * f[qR] + c2 * f[qR + st];
-    else r = one_by_thirty * f[ps[0]] - thirteen_by_sixty * f[ps[1]] + fortyseven_by_sixty * f[ps[2]]
-           + twentyseven_by_sixty * f[ps[3]] - one_by_twenty * f[ps[4]];
-    fI[v * ni + q] = r;
+    return;
+  }
+  double UL[NV], UR[NV], uavg[NV], lam[NV], L[NV * NV], R[NV * NV], fc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) { UL[v] = u[v * G.npg + pm1]; UR[v] = u[v * G.npg + pm1 + st]; }
+  roe_average<MODEL>(ph, UL, UR, uavg);
+  eigen<MODEL>(ph, uavg, dir, lam, L, R);
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    double s[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      double a = 0.0;
+#pragma unroll
+      for (int j = 0; j < NV; j++) a += L[v * NV + j] * S[k][j];
+      s[k] = a;
+    }
+    fc[v] = linear_scheme_value(ph.scheme, ph.muscl_limiter, ph.muscl_eps, upw, s);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    double a = 0.0;
+#pragma unroll
+    for (int j = 0; j < NV; j++) a += R[i * NV + j] * fc[j];
+    fI[i * ni + q] = a;
   }
 }
 
@@ -1462,8 +1507,10 @@ void weno_interp(hpb_solver* h, double* fI, const double* fC, const double* u, c
   const Geom& G = h->geo;
   const int M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
   if (h->cfg.hyp_scheme >= HPB_SCHEME_UPW5) {
-    k_interp_upw5<<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->cfg.hyp_scheme, h->phys.muscl_limiter, h->phys.muscl_eps,
-                                                                   fC, upw, dir, fI); LAUNCHED(h);
+#define CALL(M_) k_interp_upw5<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, fC, u, upw, dir, fI)
+    MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+    LAUNCHED(h);
     return;
   }
   if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h->cfg.hyp_scheme == HPB_SCHEME_CUPW5) {

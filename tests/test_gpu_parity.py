@@ -117,6 +117,13 @@ def _cases():
     # gravity source reconstructed characteristic-wise
     C.append(cases.with_characteristic(cases.ns3d_rising_bubble((12, 14, 10), "js")))
     C.append(cases.with_characteristic(cases.ns2d_rising_bubble((24, 20), "mapped", upwinding="roe")))
+    # the linear / MUSCL schemes characteristic-wise
+    C.append(cases.euler1d_sod(101, "js", scheme="upw5"))
+    C.append(cases.euler1d_sod(101, "js", scheme="2", upwinding="llf-char"))
+    C.append(cases.with_muscl(cases.euler1d_sod(101, "js", gravity=1.0), "muscl3"))
+    C.append(cases.with_muscl(cases.ns2d_vortex((24, 28), "js", upwinding="rf-char", interp="characteristic"), "muscl2", limiter="vanleer"))
+    C.append(cases.with_characteristic(cases.ns3d_turbulence((12, 14, 10), "js", viscous=False, upwinding="roe", scheme="4")))
+    C.append(cases.with_characteristic(cases.ns_channel((14, 12, 12), "js", scheme="upw5")))
     return C
 
 
@@ -203,7 +210,7 @@ STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CA
               CASES[56], CASES[57], CASES[58], CASES[59], CASES[60], CASES[61], CASES[62], CASES[63], CASES[64],
               CASES[65], CASES[66], CASES[67], CASES[68], CASES[69], CASES[70],
               CASES[71], CASES[72], CASES[73], CASES[74], CASES[75], CASES[76], CASES[77], CASES[78], CASES[79],
-              CASES[80], CASES[81]]
+              CASES[80], CASES[81], CASES[82], CASES[83], CASES[84], CASES[85], CASES[86], CASES[87]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)
@@ -262,7 +269,7 @@ def test_time_steps_parity(need_gpu, case):
 
 @pytest.mark.parametrize("case", [CASES[4], CASES[12], CASES[16], CASES[20], CASES[26],
                                   CASES[35], CASES[37], CASES[40], CASES[42], CASES[44], CASES[51], CASES[52], CASES[53],
-                                  CASES[56], CASES[58], CASES[60], CASES[65], CASES[69], CASES[72], CASES[74], CASES[76], CASES[79]],
+                                  CASES[56], CASES[58], CASES[60], CASES[65], CASES[69], CASES[72], CASES[74], CASES[76], CASES[79], CASES[82], CASES[85], CASES[87]],
                          ids=lambda c: c.name)
 def test_function_pointer_pieces(need_gpu, case):
     """FFunction, UFunction, SetInterpLimiterVar, InterpolateInterfacesHyp, Upwind,

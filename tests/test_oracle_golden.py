@@ -176,6 +176,13 @@ def _live_cases():
         # InterpolateInterfacesHyp as the flux: NavierStokes3DSource.c:77-78)
         cases.with_characteristic(cases.ns3d_rising_bubble((10, 14, 12), "js")),
         cases.with_characteristic(cases.ns2d_rising_bubble((20, 24), "mapped", upwinding="roe")),
+        # the linear / MUSCL schemes characteristic-wise (Interp1Prim...Char.c)
+        cases.euler1d_sod(101, "js", scheme="upw5"),
+        cases.euler1d_sod(101, "js", scheme="2", upwinding="llf-char"),
+        cases.with_muscl(cases.euler1d_sod(101, "js", gravity=1.0), "muscl3"),
+        cases.with_muscl(cases.ns2d_vortex((20, 24), "js", upwinding="rf-char", interp="characteristic"), "muscl2", limiter="vanleer"),
+        cases.with_characteristic(cases.ns3d_turbulence((12, 10, 14), "js", viscous=False, upwinding="roe", scheme="4")),
+        cases.with_characteristic(cases.ns_channel((12, 10, 14), "js", viscous=True, scheme="upw5")),
         # Euler1D with gravity (Euler1DGravityField.c, Euler1DSource.c)
         cases.euler1d_sod(101, "js", gravity=1.0),
         cases.euler1d_sod(101, "mapped", interp="components", upwinding="llf-char", gravity=1.0),
