@@ -119,7 +119,8 @@ def _cases():
     C.append(cases.with_characteristic(cases.ns2d_rising_bubble((24, 20), "mapped", upwinding="roe")))
     # the linear / MUSCL schemes characteristic-wise
     C.append(cases.euler1d_sod(101, "js", scheme="upw5"))
-    C.append(cases.euler1d_sod(101, "js", scheme="2", upwinding="llf-char"))
+    # (central scheme: a smooth flow -- on the Sod tube it produces NaNs within a few steps, in the reference too)
+    C.append(cases.ns2d_vortex((28, 24), "js", upwinding="llf-char", interp="characteristic", scheme="2"))
     C.append(cases.with_muscl(cases.euler1d_sod(101, "js", gravity=1.0), "muscl3"))
     C.append(cases.with_muscl(cases.ns2d_vortex((24, 28), "js", upwinding="rf-char", interp="characteristic"), "muscl2", limiter="vanleer"))
     C.append(cases.with_characteristic(cases.ns3d_turbulence((12, 14, 10), "js", viscous=False, upwinding="roe", scheme="4")))

@@ -178,7 +178,7 @@ def _live_cases():
         cases.with_characteristic(cases.ns2d_rising_bubble((20, 24), "mapped", upwinding="roe")),
         # the linear / MUSCL schemes characteristic-wise (Interp1Prim...Char.c)
         cases.euler1d_sod(101, "js", scheme="upw5"),
-        cases.euler1d_sod(101, "js", scheme="2", upwinding="llf-char"),
+        cases.ns2d_vortex((24, 20), "js", upwinding="llf-char", interp="characteristic", scheme="2"),
         cases.with_muscl(cases.euler1d_sod(101, "js", gravity=1.0), "muscl3"),
         cases.with_muscl(cases.ns2d_vortex((20, 24), "js", upwinding="rf-char", interp="characteristic"), "muscl2", limiter="vanleer"),
         cases.with_characteristic(cases.ns3d_turbulence((12, 10, 14), "js", viscous=False, upwinding="roe", scheme="4")),
