@@ -143,6 +143,27 @@ def linear_advection_sine(n: int = 1024, weno: str = "js", dt: float = 5e-4,
         physics=phys, weno=weno_inp(weno), x=[x], u0=u)
 
 
+def linear_advection_nd(n: Sequence[int] = (32, 24), weno: str = "js", advection=None, diffusion=None,
+                        par_scheme: str = "2", tstype: str = "44", scheme: str = "weno5", iproc=None) -> Case:
+    """Scalar linear advection(-diffusion) of a smooth periodic field in 2-D or 3-D
+    (Examples/2D/LinearAdvection/SineWave, Examples/3D/LinearAdvection): u = prod_d sin(2 pi x_d) + 0.5."""
+    nd = len(n)
+    xs = [np.arange(n[d], dtype=np.float64) / n[d] for d in range(nd)]
+    grids = np.meshgrid(*[xs[d] for d in reversed(range(nd))], indexing="ij")
+    X = list(reversed(grids))
+    u = 0.5 + np.prod([np.sin(2.0 * np.pi * X[d] + 0.3 * d) for d in range(nd)], axis=0)
+    adv = list(advection) if advection is not None else [1.0, -0.5, 0.25][:nd]
+    phys: Dict[str, object] = {"advection": adv}
+    if diffusion is not None:
+        phys["diffusion"] = list(diffusion)
+    return Case(
+        name=f"linadv{nd}d_{'x'.join(str(v) for v in n)}_{weno}" + ("_diff" if diffusion is not None else "") + _sfx(scheme),
+        solver=_solver(nd, 1, n, "linear-advection-diffusion-reaction", ts="rk", tstype=tstype, dt=0.2 / max(n),
+                       par_scheme=par_scheme, scheme=scheme, iproc=iproc),
+        boundary=_zones(nd, "periodic", [-1e3] * nd, [1e3] * nd),
+        physics=phys, weno=weno_inp(weno), x=xs, u0=u[..., None])
+
+
 # ------------------------------------------------------------------------------------- C2
 def euler1d_sod(n: int = 201, weno: str = "js", interp: str = "characteristic",
                 upwinding: str = "roe", tstype: str = "ssprk3", scheme: str = "weno5",

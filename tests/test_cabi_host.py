@@ -61,6 +61,8 @@ ALL_CASES = [
     cases.ns3d_rising_bubble((10, 14, 12), "mapped", hb=1),
     cases.ns2d_rising_bubble((20, 24), "js"),                      # 2-D gravity field (HB 2) and slip walls
     cases.ns2d_rising_bubble((24, 20), "z", hb=1, upwinding="roe"),
+    cases.linear_advection_nd((24, 20), "js"),
+    cases.linear_advection_nd((12, 10, 14), "js", diffusion=[0.01, 0.0, 0.02]),
     cases.euler1d_sod(101, "js", gravity=1.0),                      # 1-D gravity field, mirrored at the physical faces
     cases.euler1d_sod(101, "z", gravity=1.0, gravity_type=1),
     cases.ns_channel((24, 20), "js"),                               # inflow / outflow / no-slip / slip zones

@@ -125,6 +125,12 @@ def _cases():
     C.append(cases.with_muscl(cases.ns2d_vortex((24, 28), "js", upwinding="rf-char", interp="characteristic"), "muscl2", limiter="vanleer"))
     C.append(cases.with_characteristic(cases.ns3d_turbulence((12, 14, 10), "js", viscous=False, upwinding="roe", scheme="4")))
     C.append(cases.with_characteristic(cases.ns_channel((14, 12, 12), "js", scheme="upw5")))
+    # LinearADR in 2-D / 3-D
+    C.append(cases.linear_advection_nd((32, 24), "mapped"))
+    C.append(cases.linear_advection_nd((24, 28), "z", diffusion=[0.01, 0.02], par_scheme="4"))
+    C.append(cases.linear_advection_nd((16, 12, 14), "js", diffusion=[0.01, 0.0, 0.02]))
+    C.append(cases.linear_advection_nd((12, 14, 10), "yc", scheme="crweno5", advection=[-1.0, 0.5, 0.3]))
+    C.append(cases.linear_advection_nd((33, 24), "js"))          # odd row length
     return C
 
 
@@ -211,7 +217,8 @@ STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CA
               CASES[56], CASES[57], CASES[58], CASES[59], CASES[60], CASES[61], CASES[62], CASES[63], CASES[64],
               CASES[65], CASES[66], CASES[67], CASES[68], CASES[69], CASES[70],
               CASES[71], CASES[72], CASES[73], CASES[74], CASES[75], CASES[76], CASES[77], CASES[78], CASES[79],
-              CASES[80], CASES[81], CASES[82], CASES[83], CASES[84], CASES[85], CASES[86], CASES[87]]
+              CASES[80], CASES[81], CASES[82], CASES[83], CASES[84], CASES[85], CASES[86], CASES[87],
+              CASES[88], CASES[89], CASES[90], CASES[91], CASES[92]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)

@@ -183,6 +183,11 @@ def _live_cases():
         cases.with_muscl(cases.ns2d_vortex((20, 24), "js", upwinding="rf-char", interp="characteristic"), "muscl2", limiter="vanleer"),
         cases.with_characteristic(cases.ns3d_turbulence((12, 10, 14), "js", viscous=False, upwinding="roe", scheme="4")),
         cases.with_characteristic(cases.ns_channel((12, 10, 14), "js", viscous=True, scheme="upw5")),
+        # LinearADR in 2-D / 3-D (Examples/2D/LinearAdvection, Examples/3D/LinearAdvection)
+        cases.linear_advection_nd((24, 20), "mapped"),
+        cases.linear_advection_nd((20, 24), "z", diffusion=[0.01, 0.02], par_scheme="4"),
+        cases.linear_advection_nd((12, 10, 14), "js", diffusion=[0.01, 0.0, 0.02]),
+        cases.linear_advection_nd((10, 12, 10), "yc", scheme="crweno5", advection=[-1.0, 0.5, 0.3]),
         # Euler1D with gravity (Euler1DGravityField.c, Euler1DSource.c)
         cases.euler1d_sod(101, "js", gravity=1.0),
         cases.euler1d_sod(101, "mapped", interp="components", upwinding="llf-char", gravity=1.0),
