@@ -100,6 +100,19 @@ def with_muscl(case: "Case", scheme: str, epsilon: float = 1e-3, limiter: str = 
     return case
 
 
+def with_sponge(case: "Case", dim: int, face: int, xstart: float, xend: float, values) -> "Case":
+    """the same case with a sponge zone (BCSponge.c): an interior box spanning [xstart, xend] along `dim` (the whole
+    domain in the other dimensions) in which the solution is relaxed towards `values`"""
+    nd = case.ndims
+    z = {"type": "sponge", "dim": dim, "face": face,
+         "xmin": [float(xstart) if k == dim else -1e3 for k in range(nd)],
+         "xmax": [float(xend) if k == dim else 1e3 for k in range(nd)],
+         "values": [float(v) for v in values]}
+    case.boundary = list(case.boundary) + [z]
+    case.name += f"_sponge{dim}{'p' if face > 0 else 'm'}"
+    return case
+
+
 def _sfx(scheme: str) -> str:
     return "" if scheme == "weno5" else "_" + scheme
 

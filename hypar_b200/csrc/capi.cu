@@ -164,6 +164,7 @@ static int ensure_generic(hpb_solver* h)
   TRY(ensure_pieces(h));
   TRY(dalloc(&h->d_fI, nif_max(h) * h->geo.nvars));
   if (h->phys.has_grav) { TRY(dalloc(&h->d_sI, nif_max(h) * 2)); TRY(dalloc(&h->d_src, n)); }
+  if (hpbk::has_sponge(h)) TRY(dalloc(&h->d_src, n));
   if (viscous_on(h)) {
     for (int d = 0; d < h->geo.ndims; d++) TRY(dalloc(&h->d_QD[d], n));
     TRY(dalloc(&h->d_FV, h->geo.npg * (h->geo.nvars - 1)));
@@ -395,6 +396,7 @@ static int rhs_part_a(hpb_solver* h, const double* U, double* rhs)
   TRY(ensure_generic(h));
   if (h->d_src) hpbk::set_zero(h, h->d_src, ncell(h));
   hpbk::hyperbolic_generic(h, U, rhs, /*negate=*/true, /*with_source=*/true, h->d_src);
+  if (hpbk::has_sponge(h)) hpbk::sponge_source(h, U, h->d_src);      // SourceFunction.c:52-75: after the model's source
   if (viscous_on(h)) hpbk::parabolic_phase1(h, U);
   return HPB_OK;
 }
@@ -404,12 +406,14 @@ static int rhs_part_b(hpb_solver* h, const double* U, double* rhs)
     if (fused_visc(h)) hpbk::hyperbolic_fused(h, U, rhs, true, true, rhs, h->d_qd4);
     else if (viscous_on(h)) hpbk::parabolic_phase2(h, U, rhs, /*accumulate=*/true);
     else if (h->cfg.model == HPB_MODEL_LINEAR_ADR) hpbk::parabolic_nc1(h, U, rhs, true);
+    if (hpbk::has_sponge(h)) hpbk::sponge_source(h, U, rhs);        // production path: straight into the right-hand side
     return HPB_OK;
   }
   const double* par = nullptr;
   if (viscous_on(h)) { hpbk::parabolic_phase2(h, U, h->d_par, /*accumulate=*/false); par = h->d_par; }
   else if (h->cfg.model == HPB_MODEL_LINEAR_ADR) { hpbk::parabolic_nc1(h, U, h->d_par, false); par = h->d_par; }
-  if (par || (h->d_src && h->phys.has_grav)) hpbk::combine_rhs(h, rhs, par, h->phys.has_grav ? h->d_src : nullptr);
+  const bool src_on = h->d_src && (h->phys.has_grav || hpbk::has_sponge(h));
+  if (par || src_on) hpbk::combine_rhs(h, rhs, par, src_on ? h->d_src : nullptr);
   return HPB_OK;
 }
 static bool multi_rank(const hpb_solver* h)
@@ -476,6 +480,7 @@ extern "C" int hpb_SourceFunction(hpb_solver* h, double* source, const double* u
   // re-evaluated here with the source enabled; its hyperbolic output goes to scratch
   TRY(ensure_generic(h));
   if (h->phys.has_grav) hpbk::hyperbolic_generic(h, h->d_tmp[0], h->d_tmp[2], false, true, h->d_tmp[1]);
+  if (hpbk::has_sponge(h)) hpbk::sponge_source(h, h->d_tmp[0], h->d_tmp[1]);
   TRY(check_async(h, "SourceFunction"));
   return download(h, h->d_tmp[1], source, h->geo.npg, h->geo.nvars);
 }
@@ -954,6 +959,7 @@ extern "C" int hpb_stage_halo_done_dim(hpb_solver* h, int field, int dim)
 extern "C" int hpb_stage_overlap_supported(const hpb_solver* h)
 {
   if (!fused_path(h)) return 0;
+  if (hpbk::has_sponge(h)) return 0;          // the sponge source is added after the last sweep by hpb_stage_rhs_b
   if (viscous_on(h) && !fused_visc(h)) return 0;
   if (h->cfg.model == HPB_MODEL_LINEAR_ADR) return 0;
   return 1;

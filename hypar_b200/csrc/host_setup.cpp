@@ -125,11 +125,11 @@ int hpb_setup_host(hpb_solver* h)
     const hpb_boundary_zone& z = c.zones[n];
     if (z.dim < 0 || z.dim >= nd) return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: dim %d is invalid (ndims = %d)", n, z.dim, nd);
     if (z.face != 1 && z.face != -1) return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: face must be +1/-1", n);
-    if (z.type < 0 || z.type > HPB_BC_SUPERSONIC_OUTFLOW)
+    if (z.type < 0 || z.type > HPB_BC_SPONGE)
       return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: boundary type %d not implemented", n, z.type);
     if (z.type == HPB_BC_SLIP_WALL && c.model == HPB_MODEL_LINEAR_ADR)
       return hpb_fail(HPB_ERR_INVALID, "slip-wall needs an Euler/Navier-Stokes model");
-    if ((z.type == HPB_BC_NOSLIP_WALL || z.type >= HPB_BC_SUBSONIC_INFLOW) &&
+    if ((z.type == HPB_BC_NOSLIP_WALL || (z.type >= HPB_BC_SUBSONIC_INFLOW && z.type <= HPB_BC_SUPERSONIC_OUTFLOW)) &&
         c.model != HPB_MODEL_NS2D && c.model != HPB_MODEL_NS3D)      // the reference has 2-D and 3-D branches only
       return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: boundary type %d needs a 2-D or 3-D Navier-Stokes model", n, z.type);
     if (z.type == HPB_BC_PERIODIC && c.iproc[z.dim] > 1) h->bcperiodic[z.dim] = 1;
@@ -189,8 +189,17 @@ int hpb_setup_host(hpb_solver* h)
     for (int d = 0; d < 3; d++) { zd.is[d] = 0; zd.ie[d] = 1; zd.wall[d] = z.wall_velocity[d]; }
     zd.rho = z.flow_density; zd.pressure = z.flow_pressure;
     for (int v = 0; v < HPB_MAX_NVARS; v++) zd.val[v] = z.dirichlet[v];
+    zd.xs = z.xmin[z.dim]; zd.xe = z.xmax[z.dim];
     const bool edge = (z.face == 1) ? (h->ip[z.dim] == 0) : (h->ip[z.dim] == c.iproc[z.dim] - 1);
-    if (edge) {
+    if (z.type == HPB_BC_SPONGE) {            // InitializeBoundaries.c:381-395: an interior box on every rank it overlaps
+      zd.on = 1;
+      for (int d = 0; d < nd; d++) {
+        int is, ie;
+        find_interval(z.xmin[d], z.xmax[d], h->x_h.data() + G.xoff[d] + g, G.N[d], &is, &ie);
+        zd.is[d] = is; zd.ie[d] = ie;
+        if ((ie - is) <= 0) zd.on = 0;
+      }
+    } else if (edge) {
       zd.on = 1;
       for (int d = 0; d < nd; d++) {
         if (d == z.dim) {

@@ -38,7 +38,8 @@ struct ZoneDev {
   int is[3], ie[3];
   double wall[3];                 // wall / inflow velocity
   double rho, pressure;           // inflow density, inflow / outflow pressure
-  double val[HPB_MAX_NVARS];      // Dirichlet values
+  double val[HPB_MAX_NVARS];      // Dirichlet / sponge values
+  double xs, xe;                  // sponge: start and end coordinate along dim
 };
 
 struct RKTableau { int ns; double A[16], b[4], c[4]; };
@@ -132,6 +133,9 @@ namespace hpbk {
 void aos_to_soa(hpb_solver* h, const double* aos, double* soa, long long npts, int nv);
 void soa_to_aos(hpb_solver* h, const double* soa, double* aos, long long npts, int nv);
 void apply_bc(hpb_solver* h, double* u);
+// sponge zones (BCSponge.c): out -= sigma (u - u_ref) inside every sponge box; true if the configuration has one
+bool has_sponge(const hpb_solver* h);
+void sponge_source(hpb_solver* h, const double* u, double* out);
 void pack(hpb_solver* h, const double* a, int nv, int field);
 void unpack(hpb_solver* h, double* a, int nv, int field, int only_dim = -1);
 // hyperbolic term. negate=true: out = -sum_d dxinv*(fhat_{j+1}-fhat_j) (the first direction overwrites the

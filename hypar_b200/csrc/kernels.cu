@@ -151,6 +151,21 @@ __global__ void k_bc_zone(Geom G, ZoneDev z, double gamma, double* __restrict__ 
   phi[(nv - 1) * G.npg + p1] = energy_gpt;
 }
 
+// BCSponge.c:25-75 (BCSpongeSource): out -= sigma (u - u_ref) inside the zone box, sigma rising linearly from 0 at the
+// zone's start to 1 at its end (x = the cell's coordinate along the zone's dimension)
+__global__ void k_sponge(Geom G, ZoneDev z, const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ out)
+{
+  const int b0 = z.ie[0] - z.is[0], b1 = (G.ndims > 1 ? z.ie[1] - z.is[1] : 1), b2 = (G.ndims > 2 ? z.ie[2] - z.is[2] : 1);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)b0 * b1 * b2) return;
+  const int t0 = (int)(t % b0), t1 = (int)((t / b0) % b1), t2 = (int)(t / ((long long)b0 * b1));
+  const int i1[3] = { t0 + z.is[0], t1 + (G.ndims > 1 ? z.is[1] : 0), t2 + (G.ndims > 2 ? z.is[2] : 0) };
+  const double xc = x[G.xoff[z.dim] + G.g + i1[z.dim]];
+  const double sigma = (z.face > 0) ? (xc - z.xs) / (z.xe - z.xs) : (xc - z.xe) / (z.xs - z.xe);
+  const long long p = cell_index(G, i1[0], i1[1], i1[2]);
+  for (int v = 0; v < G.nvars; v++) out[v * G.npg + p] -= (sigma * (u[v * G.npg + p] - z.val[v]));
+}
+
 // ------------------------------------------------------------------------------------------
 // halo pack / unpack (MPIExchangeBoundariesnD.c:42-173). Face box: bounds[d] = g, other dims N.
 // Buffer layout: component-major, then the face box with dim 0 fastest.
@@ -1252,9 +1267,27 @@ void apply_bc(hpb_solver* h, double* u)
   for (const ZoneDev& z : h->zones) {
     if (!z.on) continue;
     if (z.type == HPB_BC_PERIODIC && h->cfg.iproc[z.dim] != 1) continue;
+    if (z.type == HPB_BC_SPONGE) continue;                     // BCSpongeUDummy: a source term, no ghost fill
     const int b0 = z.ie[0] - z.is[0], b1 = (G.ndims > 1 ? z.ie[1] - z.is[1] : 1), b2 = (G.ndims > 2 ? z.ie[2] - z.is[2] : 1);
     if (b0 <= 0 || b1 <= 0 || b2 <= 0) continue;
     k_bc_zone<<<(unsigned)(((long long)b0 * b1 * b2 + TPB - 1) / TPB), TPB, 0, h->stream>>>(G, z, h->phys.gamma, u); LAUNCHED(h);
+  }
+}
+
+bool has_sponge(const hpb_solver* h)
+{
+  for (int n = 0; n < h->cfg.nzones; n++) if (h->cfg.zones[n].type == HPB_BC_SPONGE) return true;
+  return false;
+}
+
+void sponge_source(hpb_solver* h, const double* u, double* out)
+{
+  const Geom& G = h->geo;
+  for (const ZoneDev& z : h->zones) {
+    if (!z.on || z.type != HPB_BC_SPONGE) continue;
+    const int b0 = z.ie[0] - z.is[0], b1 = (G.ndims > 1 ? z.ie[1] - z.is[1] : 1), b2 = (G.ndims > 2 ? z.ie[2] - z.is[2] : 1);
+    if (b0 <= 0 || b1 <= 0 || b2 <= 0) continue;
+    k_sponge<<<(unsigned)(((long long)b0 * b1 * b2 + TPB - 1) / TPB), TPB, 0, h->stream>>>(G, z, h->d_x, u, out); LAUNCHED(h);
   }
 }
 

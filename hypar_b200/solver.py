@@ -21,7 +21,7 @@ from . import _lib, hypario
 
 MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3}
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "dirichlet": 4, "subsonic-inflow": 5,
-           "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9}
+           "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9, "sponge": 10}
 UPWINDS = {"roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 RK_TYPES = {"44": 0, "ssprk3": 1, "tvdrk3": 1, "1fe": 2, "22": 3, "33": 4}
 SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6, "muscl2": 7, "muscl3": 8}

@@ -94,6 +94,8 @@ extern "C" {
 #define HPB_BC_SUBSONIC_AMBIVALENT 7   /* BCSubsonicAmbivalent.c: density, velocity, pressure            */
 #define HPB_BC_SUPERSONIC_INFLOW   8   /* BCSupersonicInflow.c: density, velocity, pressure              */
 #define HPB_BC_SUPERSONIC_OUTFLOW  9   /* BCSupersonicOutflow.c                                          */
+#define HPB_BC_SPONGE             10   /* BCSponge.c: an interior box [xmin, xmax] in which the solution is relaxed towards
+                                          dirichlet[] (SpongeValue) by a source term, SourceFunction.c:52-75; no ghost fill */
 
 /* time_scheme_type for time_scheme "rk" -- reference TimeExplicitRKInitialize.c:58-79 */
 #define HPB_RK_44     0

@@ -169,6 +169,7 @@ static int bc_type(const char *name)
   if (!strcmp(name, _SUBSONIC_AMBIVALENT_))  return HPB_BC_SUBSONIC_AMBIVALENT;
   if (!strcmp(name, _SUPERSONIC_INFLOW_))    return HPB_BC_SUPERSONIC_INFLOW;
   if (!strcmp(name, _SUPERSONIC_OUTFLOW_))   return HPB_BC_SUPERSONIC_OUTFLOW;
+  if (!strcmp(name, _SPONGE_))               return HPB_BC_SPONGE;
   return -1;
 }
 
@@ -274,6 +275,7 @@ int hyparb200_attach(void *sims, int nsims)
     }
     c.zones[n].flow_density = b[n].FlowDensity;  c.zones[n].flow_pressure = b[n].FlowPressure;
     if (b[n].DirichletValue) for (int v = 0; v < s->nvars; v++) c.zones[n].dirichlet[v] = b[n].DirichletValue[v];
+    if (b[n].SpongeValue)    for (int v = 0; v < s->nvars; v++) c.zones[n].dirichlet[v] = b[n].SpongeValue[v];
   }
 
   /* global grid, concatenated per dimension as in initial.inp (ReadArray.c:225-256); one rank: the interior part

@@ -24,7 +24,7 @@ MAXD, MAXV, MAXZ = 3, 5, 16
 
 MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3}
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "dirichlet": 4, "subsonic-inflow": 5,
-           "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9}
+           "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9, "sponge": 10}
 UPWINDS = {"default": 0, "roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6, "muscl2": 7, "muscl3": 8}
 LIMITERS = {"gmm": 0, "minmod": 1, "vanleer": 2, "superbee": 3}
@@ -34,7 +34,7 @@ class Zone(C.Structure):
     _fields_ = [("type", C.c_int), ("dim", C.c_int), ("face", C.c_int),
                 ("is_", C.c_int * MAXD), ("ie", C.c_int * MAXD), ("on_this_proc", C.c_int),
                 ("wall_vel", C.c_double * MAXD), ("rho", C.c_double), ("pressure", C.c_double),
-                ("values", C.c_double * MAXV)]
+                ("values", C.c_double * MAXV), ("xstart", C.c_double), ("xend", C.c_double)]
 
 
 class Ctx(C.Structure):
@@ -216,8 +216,16 @@ class Setup:
                   "on": 0, "wall_vel": list(z.get("wall_velocity", z.get("velocity", [0.0] * nd))),
                   "rho": float(z.get("density", 0.0)), "pressure": float(z.get("pressure", 0.0)),
                   "values": list(z.get("values", []))}
+            zi["xstart"], zi["xend"] = float(z["xmin"][dim]), float(z["xmax"][dim])
             edge = (self.ip[dim] == 0) if face == 1 else (self.ip[dim] == self.iproc[dim] - 1)
-            if edge:
+            if z["type"] == "sponge":       # InitializeBoundaries.c:381-395: an interior box, FindInterval in every dimension
+                zi["on"] = 1
+                for d in range(nd):
+                    a, b = find_interval(z["xmin"][d], z["xmax"][d], xs[d][g:g + self.dim[d]])
+                    zi["is"][d], zi["ie"][d] = a, b
+                    if b - a <= 0:
+                        zi["on"] = 0
+            elif edge:
                 zi["on"] = 1
                 for d in range(nd):
                     if d == dim:
@@ -305,6 +313,7 @@ class Setup:
             for d in range(self.ndims):
                 cz.is_[d], cz.ie[d], cz.wall_vel[d] = z["is"][d], z["ie"][d], z["wall_vel"][d]
             cz.rho, cz.pressure = z["rho"], z["pressure"]
+            cz.xstart, cz.xend = z["xstart"], z["xend"]
             for v, val in enumerate(z["values"]):
                 cz.values[v] = float(val)
         c.x, c.dxinv = _p(self.x), _p(self.dxinv)
@@ -394,6 +403,7 @@ class Oracle:
         src = self.zeros()
         if self.s.ctx.model in (1, 2, 3):
             self.L.hpo_ns3d_source(self.c, _p(src), _p(u), _p(w))
+        self.L.hpo_sponge_source(self.c, _p(src), _p(u))
         return src
 
     def rhs(self, u, parts=False, mpi_semantics=None):

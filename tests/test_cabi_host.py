@@ -62,6 +62,7 @@ ALL_CASES = [
     cases.ns2d_rising_bubble((20, 24), "js"),                      # 2-D gravity field (HB 2) and slip walls
     cases.ns2d_rising_bubble((24, 20), "z", hb=1, upwinding="roe"),
     cases.linear_advection_nd((24, 20), "js"),
+    cases.with_sponge(cases.ns_channel((24, 20), "js"), 0, 1, 0.7, 1.0, [1.0, 0.5, 0.0, 2.0]),    # interior sponge box
     cases.linear_advection_nd((12, 10, 14), "js", diffusion=[0.01, 0.0, 0.02]),
     cases.euler1d_sod(101, "js", gravity=1.0),                      # 1-D gravity field, mirrored at the physical faces
     cases.euler1d_sod(101, "z", gravity=1.0, gravity_type=1),
@@ -138,7 +139,7 @@ def test_decomposed_setup_neighbors_and_remainders():
     (lambda c: c.solver.__setitem__("time_scheme_type", "ssprk2"), "ssprk3"),
     (lambda c: c.solver.__setitem__("ghost", 2), "ghost"),
     (lambda c: c.solver.__setitem__("model", "shallow-water-2d"), "model"),
-    (lambda c: c.boundary[0].__setitem__("type", "sponge"), "boundary type"),
+    (lambda c: c.boundary[0].__setitem__("type", "thermal-slip-wall"), "boundary type"),
     (lambda c: c.physics.__setitem__("upwinding", "steger-warming"), "upwinding"),
     (lambda c: c.solver.__setitem__("par_space_type", "conservative-1stage"), "nonconservative-2stage"),
 ])

@@ -53,6 +53,7 @@ CASES = [
     _prep(cases.ns_channel((12, 14, 12), "mapped", bcs="sup3", mach=1.4), n_iter=4),          # supersonic / Dirichlet / ambivalent
     _prep(cases.with_muscl(cases.ns2d_vortex((32, 24), "js", upwinding="roe"), "muscl3")),    # muscl.inp through HyPar's reader
     _prep(cases.euler1d_sod(101, "mapped", gravity=1.0)),                                     # Euler1D + gravity
+    _prep(cases.with_sponge(cases.linear_advection_nd((28, 24), "js"), 0, -1, 0.0, 0.4, [0.5])),   # sponge zone
 ]
 
 

@@ -131,6 +131,12 @@ def _cases():
     C.append(cases.linear_advection_nd((16, 12, 14), "js", diffusion=[0.01, 0.0, 0.02]))
     C.append(cases.linear_advection_nd((12, 14, 10), "yc", scheme="crweno5", advection=[-1.0, 0.5, 0.3]))
     C.append(cases.linear_advection_nd((33, 24), "js"))          # odd row length
+    # sponge zones
+    C.append(cases.with_sponge(cases.linear_advection_sine(96, "js"), 0, 1, 0.6, 0.9, [0.1]))
+    C.append(cases.with_sponge(cases.linear_advection_nd((24, 20), "mapped"), 1, -1, 0.1, 0.5, [0.5]))
+    C.append(cases.with_sponge(cases.ns_channel((28, 24), "js"), 0, 1, 0.7, 1.0, [1.0, 0.5, 0.0, 2.0]))
+    C.append(cases.with_sponge(cases.ns3d_rising_bubble((12, 14, 10), "yc"), 1, 1, 700.0, 1000.0, [1.0, 0.0, 0.0, 0.0, 2.0e5]))
+    C.append(cases.with_sponge(cases.ns3d_turbulence((16, 12, 14), "mapped"), 2, -1, 0.0, 3.0, [1.0, 0.1, 0.0, 0.0, 1.8]))
     return C
 
 
@@ -218,7 +224,7 @@ STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CA
               CASES[65], CASES[66], CASES[67], CASES[68], CASES[69], CASES[70],
               CASES[71], CASES[72], CASES[73], CASES[74], CASES[75], CASES[76], CASES[77], CASES[78], CASES[79],
               CASES[80], CASES[81], CASES[82], CASES[83], CASES[84], CASES[85], CASES[86], CASES[87],
-              CASES[88], CASES[89], CASES[90], CASES[91], CASES[92]]
+              CASES[88], CASES[89], CASES[90], CASES[91], CASES[92], CASES[93], CASES[94], CASES[95], CASES[96], CASES[97]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)

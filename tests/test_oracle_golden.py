@@ -188,6 +188,11 @@ def _live_cases():
         cases.linear_advection_nd((20, 24), "z", diffusion=[0.01, 0.02], par_scheme="4"),
         cases.linear_advection_nd((12, 10, 14), "js", diffusion=[0.01, 0.0, 0.02]),
         cases.linear_advection_nd((10, 12, 10), "yc", scheme="crweno5", advection=[-1.0, 0.5, 0.3]),
+        # sponge zones (BCSponge.c through SourceFunction.c)
+        cases.with_sponge(cases.linear_advection_sine(96, "js"), 0, 1, 0.6, 0.9, [0.1]),
+        cases.with_sponge(cases.linear_advection_nd((24, 20), "mapped"), 1, -1, 0.1, 0.5, [0.5]),
+        cases.with_sponge(cases.ns_channel((24, 20), "js"), 0, 1, 0.7, 1.0, [1.0, 0.5, 0.0, 2.0]),
+        cases.with_sponge(cases.ns3d_rising_bubble((10, 14, 12), "yc"), 1, 1, 700.0, 1000.0, [1.0, 0.0, 0.0, 0.0, 2.0e5]),
         # Euler1D with gravity (Euler1DGravityField.c, Euler1DSource.c)
         cases.euler1d_sod(101, "js", gravity=1.0),
         cases.euler1d_sod(101, "mapped", interp="components", upwinding="llf-char", gravity=1.0),
