@@ -147,7 +147,10 @@ static int ensure_pieces(hpb_solver* h)
   for (int k = 0; k < 5; k++) TRY(dalloc(&h->d_iface[k], nif_max(h) * h->geo.nvars));
   TRY(dalloc(&h->d_w, woff(h, h->geo.ndims)));
   if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h->cfg.hyp_scheme == HPB_SCHEME_CUPW5) {
-    for (int k = 0; k < 3; k++) TRY(dalloc(&h->d_tri[k], nif_max(h) * h->geo.nvars));
+    // component-wise: one scalar row per interface and component; characteristic: one nvars x nvars block per interface
+    const long long blk = (h->phys.interp_char ? (long long)h->geo.nvars * h->geo.nvars : h->geo.nvars);
+    for (int k = 0; k < 3; k++) TRY(dalloc(&h->d_tri[k], nif_max(h) * blk));
+    if (h->phys.interp_char) TRY(dalloc(&h->d_bx, nif_max(h) * h->geo.nvars));
     if (!h->d_err) {
       HPB_CUDA(cudaMalloc((void**)&h->d_err, sizeof(int)));
       HPB_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
@@ -273,6 +276,7 @@ extern "C" int hpb_destroy(hpb_solver* h)
   for (int i = 0; i < 2; i++) if (h->d_cell[i]) cudaFree(h->d_cell[i]);
   for (int i = 0; i < 3; i++) if (h->d_tri[i]) cudaFree(h->d_tri[i]);
   if (h->d_err) cudaFree(h->d_err);
+  if (h->d_bx) cudaFree(h->d_bx);
   if (h->d_pipe_in) cudaFree(h->d_pipe_in);
   if (h->d_pipe_out) cudaFree(h->d_pipe_out);
   for (int k = 0; k < 4; k++) if (h->ev_pipe[k]) cudaEventDestroy(h->ev_pipe[k]);

@@ -85,9 +85,6 @@ int hpb_setup_host(hpb_solver* h)
                     c.hyp_scheme);
   if (c.muscl_limiter < HPB_LIMITER_GMM || c.muscl_limiter > HPB_LIMITER_SUPERBEE)
     return hpb_fail(HPB_ERR_INVALID, "muscl limiter %d not supported (gmm, minmod, vanleer, superbee)", c.muscl_limiter);
-  if ((c.hyp_scheme == HPB_SCHEME_CRWENO5 || c.hyp_scheme == HPB_SCHEME_CUPW5) && c.interp_char && c.nvars > 1)
-    return hpb_fail(HPB_ERR_INVALID, "characteristic reconstruction is not implemented for the compact schemes "
-                    "(they would need the block-tridiagonal solver, blocktridiagLU.c)");
   if (c.hyp_scheme == HPB_SCHEME_CRWENO5 || c.hyp_scheme == HPB_SCHEME_CUPW5)
     for (int d = 0; d < nd; d++)
       if (c.iproc[d] != 1)     // tridiagLU.c stages 2-3: reduced system across ranks, iterative by default

@@ -84,6 +84,7 @@ struct hpb_solver {
   // place in the output interface array), pivot-error flag
   double *d_cell[2] = {nullptr, nullptr};
   double *d_tri[3] = {nullptr, nullptr, nullptr};
+  double *d_bx = nullptr;          // characteristic compact schemes: right-hand side / solution of the block systems
   int *d_err = nullptr;
   // pipelined host-array stepping (hpb_pipe_*): copy streams, AoS staging of the incoming / outgoing field, events
   // [in ready, in free, out ready, out free]

@@ -1034,6 +1034,215 @@ __global__ void k_tridiag(Geom G, int dir, double* __restrict__ A, double* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Compact schemes on characteristic variables (Interp1PrimFifthOrderCRWENOChar.c:95-277,
+// Interp1PrimFifthOrderCompactUpwindChar.c:85-264): one BLOCK tridiagonal system per grid line. Row blocks are
+// (coefficient) x L(uavg), the right-hand side is the characteristic candidate combination, the unknown is the
+// interface value itself. Block storage: element e of block i of system `sys` at [(i*NV*NV + e)*Nsys + sys], vector
+// component at [(i*NV + v)*Nsys + sys] (neighbouring threads = neighbouring systems). sys = t0 + T0*t1 over the two
+// transverse indices in increasing dimension order.
+__device__ __forceinline__ void compact_sys_index(int dir, int i0, int i1, int i2, int M0, int M1, int M2, int& iI, long long& sys, long long& Nsys)
+{
+  if (dir == 0)      { iI = i0; sys = i1 + (long long)M1 * i2; Nsys = (long long)M1 * M2; }
+  else if (dir == 1) { iI = i1; sys = i0 + (long long)M0 * i2; Nsys = (long long)M0 * M2; }
+  else               { iI = i2; sys = i0 + (long long)M0 * i1; Nsys = (long long)M0 * M1; }
+}
+
+template <int MODEL>
+__global__ void k_compact_rows_char(Geom G, Phys ph, const double* __restrict__ fC, const double* __restrict__ u,
+                                    const double* __restrict__ w, int upw, int dir, int uflag, double* __restrict__ A,
+                                    double* __restrict__ B, double* __restrict__ Cc, double* __restrict__ F)
+{
+  constexpr int NV = ModelTraits<MODEL>::NV;
+  const double one_third = 1.0 / 3.0, one_sixth = 1.0 / 6.0;
+  const double thirteen_by_sixty = 13.0 / 60.0, fortyseven_by_sixty = 47.0 / 60.0, twentyseven_by_sixty = 27.0 / 60.0,
+               one_by_twenty = 1.0 / 20.0, one_by_thirty = 1.0 / 30.0, nineteen_by_thirty = 19.0 / 30.0,
+               three_by_ten = 3.0 / 10.0, six_by_ten = 6.0 / 10.0, one_by_ten = 1.0 / 10.0;
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+  if (i0 >= M0) return;
+  const long long q = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
+  const long long ni = (long long)M0 * M1 * M2;
+  const long long st = G.st[dir];
+  const long long pm1 = cell_index(G, i0, i1, i2) - st;
+  const int blk = (upw < 0 ? 2 : 0) + (uflag ? 1 : 0);
+  int iI; long long sys, Nsys;
+  compact_sys_index(dir, i0, i1, i2, M0, M1, M2, iI, sys, Nsys);
+  const bool bnd = (iI == 0) || (iI == G.N[dir]);
+  long long ps[5];
+  for (int k = 0; k < 5; k++) ps[k] = (upw > 0) ? pm1 + (k - 2) * st : pm1 + (3 - k) * st;
+  double UL[NV], UR[NV], uavg[NV], lam[NV], L[NV * NV], R[NV * NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) { UL[v] = u[v * G.npg + pm1]; UR[v] = u[v * G.npg + pm1 + st]; }
+  roe_average<MODEL>(ph, UL, UR, uavg);
+  eigen<MODEL>(ph, uavg, dir, lam, L, R);
+  double S[5][NV];
+#pragma unroll
+  for (int k = 0; k < 5; k++)
+#pragma unroll
+    for (int v = 0; v < NV; v++) S[k][v] = fC[v * G.npg + ps[k]];
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    double c[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NV; j++) s += L[v * NV + j] * S[k][j];
+      c[k] = s;
+    }
+    const double fm3 = c[0], fm2 = c[1], fm1 = c[2], fp1 = c[3], fp2 = c[4];
+    double lo, di, hi, f;
+    if (ph.scheme == HPB_SCHEME_CRWENO5) {
+      const double w1 = w[((3 * blk + 0) * NV + v) * ni + q], w2 = w[((3 * blk + 1) * NV + v) * ni + q],
+                   w3 = w[((3 * blk + 2) * NV + v) * ni + q];
+      double f1, f2, f3;
+      if (bnd) {
+        f1 = (2 * one_sixth) * fm3 - (7.0 * one_sixth) * fm2 + (11.0 * one_sixth) * fm1;
+        f2 = (-one_sixth) * fm2 + (5.0 * one_sixth) * fm1 + (2 * one_sixth) * fp1;
+        f3 = (2 * one_sixth) * fm1 + (5 * one_sixth) * fp1 - (one_sixth) * fp2;
+      } else {
+        f1 = (one_sixth) * (fm2 + 5 * fm1);
+        f2 = (one_sixth) * (5 * fm1 + fp1);
+        f3 = (one_sixth) * (fm1 + 5 * fp1);
+      }
+      lo = ((2 * one_third) * w1 + (one_third) * w2);
+      di = ((one_third) * w1 + (2 * one_third) * (w2 + w3));
+      hi = ((one_third) * w3);
+      f = w1 * f1 + w2 * f2 + w3 * f3;
+    } else {
+      lo = three_by_ten; di = six_by_ten; hi = one_by_ten;
+      if (bnd) f = one_by_thirty * fm3 - thirteen_by_sixty * fm2 + fortyseven_by_sixty * fm1 + twentyseven_by_sixty * fp1
+                 - one_by_twenty * fp2;
+      else     f = one_by_thirty * fm2 + nineteen_by_thirty * fm1 + one_third * fp1;
+    }
+    F[((long long)iI * NV + v) * Nsys + sys] = f;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      double a, b, cc;
+      if (bnd) { a = 0.0; cc = 0.0; b = L[v * NV + k]; }
+      else if (upw > 0) { a = lo * L[v * NV + k]; b = di * L[v * NV + k]; cc = hi * L[v * NV + k]; }
+      else              { cc = lo * L[v * NV + k]; b = di * L[v * NV + k]; a = hi * L[v * NV + k]; }
+      const long long e = ((long long)iI * NV * NV + v * NV + k) * Nsys + sys;
+      A[e] = a; B[e] = b; Cc[e] = cc;
+    }
+  }
+}
+
+// include/matops.h in its own operation order (row-major N x N)
+template <int N> __device__ __forceinline__ void bt_invert(const double* A, double* B)      // _MatrixInvert_ :93-127
+{
+  double Ac[N * N];
+  for (int i = 0; i < N * N; i++) { Ac[i] = A[i]; B[i] = 0.0; }
+  for (int i = 0; i < N; i++) B[i * N + i] = 1.0;
+  for (int i = 0; i < N - 1; i++)
+    for (int j = i + 1; j < N; j++) {
+      const double factor = Ac[j * N + i] / Ac[i * N + i];
+      for (int k = i + 1; k < N; k++) Ac[j * N + k] -= (factor * Ac[i * N + k]);
+      for (int k = 0; k < j; k++) B[j * N + k] -= (factor * B[i * N + k]);
+    }
+  for (int i = N - 1; i >= 0; i--)
+    for (int k = 0; k < N; k++) {
+      double sum = 0.0;
+      for (int j = i + 1; j < N; j++) sum += (Ac[i * N + j] * B[j * N + k]);
+      B[i * N + k] = (B[i * N + k] - sum) / Ac[i * N + i];
+    }
+}
+template <int N> __device__ __forceinline__ void bt_mul(const double* A, const double* B, double* C)
+{
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) {
+    double s = 0;
+    for (int k = 0; k < N; k++) s += (A[i * N + k] * B[k * N + j]);
+    C[i * N + j] = s;
+  }
+}
+template <int N> __device__ __forceinline__ void bt_mul_sub(double* C, const double* A, const double* B)
+{
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) {
+    double s = C[i * N + j];
+    for (int k = 0; k < N; k++) s -= (A[i * N + k] * B[k * N + j]);
+    C[i * N + j] = s;
+  }
+}
+// y -= A x, element by element in place like _MatVecMultiplySubtract_ (:81-86): y and x may be the same array (row 0
+// of the back substitution), and then the macro's in-place semantics are reproduced
+template <int N> __device__ __forceinline__ void bt_matvec_sub(double* y, const double* A, const double* x)
+{
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) y[i] -= (A[i * N + j] * x[j]);
+}
+template <int N> __device__ __forceinline__ void bt_load(const double* __restrict__ M, long long row, long long Nsys, long long sys, double* blk)
+{
+  for (int e = 0; e < N * N; e++) blk[e] = M[(row * N * N + e) * Nsys + sys];
+}
+template <int N> __device__ __forceinline__ void bt_store(double* __restrict__ M, long long row, long long Nsys, long long sys, const double* blk)
+{
+  for (int e = 0; e < N * N; e++) M[(row * N * N + e) * Nsys + sys] = blk[e];
+}
+
+// TridiagLU/blocktridiagLU.c:103-320 on one rank: block forward elimination from row 1 on, block back substitution, one
+// thread per system in the reference's operation order; the solution is written to the interface array fI.
+template <int MODEL>
+__global__ void k_block_tridiag(Geom G, int dir, double* __restrict__ A, double* __restrict__ B, const double* __restrict__ Cc,
+                                double* __restrict__ X, double* __restrict__ fI)
+{
+  constexpr int N = ModelTraits<MODEL>::NV;
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  const long long ni = (long long)M0 * M1 * M2;
+  int T0, T1; long long s0, s1, qs;
+  if (dir == 0)      { T0 = M1; T1 = M2; s0 = M0;  s1 = (long long)M0 * M1; qs = 1; }
+  else if (dir == 1) { T0 = M0; T1 = M2; s0 = 1;   s1 = (long long)M0 * M1; qs = M0; }
+  else               { T0 = M0; T1 = M1; s0 = 1;   s1 = M0;                 qs = (long long)M0 * M1; }
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y;
+  if (t0 >= T0 || t1 >= T1) return;
+  const long long Nsys = (long long)T0 * T1, sys = t0 + (long long)T0 * t1;
+  const int n = G.N[dir] + 1;
+  double bprev[N * N], cprev[N * N], aprev[N * N], xprev[N], binv[N * N], factor[N * N], a[N * N], b[N * N], x[N];
+  bt_load<N>(B, 0, Nsys, sys, bprev); bt_load<N>(Cc, 0, Nsys, sys, cprev); bt_load<N>(A, 0, Nsys, sys, aprev);
+  for (int v = 0; v < N; v++) xprev[v] = X[((long long)0 * N + v) * Nsys + sys];
+  for (int i = 1; i < n; i++) {
+    bt_load<N>(A, i, Nsys, sys, a); bt_load<N>(B, i, Nsys, sys, b);
+    for (int v = 0; v < N; v++) x[v] = X[((long long)i * N + v) * Nsys + sys];
+    bt_invert<N>(bprev, binv);
+    bt_mul<N>(a, binv, factor);
+    bt_mul_sub<N>(b, factor, cprev);
+    for (int e = 0; e < N * N; e++) a[e] = 0.0;
+    bt_mul_sub<N>(a, factor, aprev);
+    bt_matvec_sub<N>(x, factor, xprev);
+    bt_store<N>(A, i, Nsys, sys, a); bt_store<N>(B, i, Nsys, sys, b);
+    for (int v = 0; v < N; v++) X[((long long)i * N + v) * Nsys + sys] = x[v];
+    for (int e = 0; e < N * N; e++) { bprev[e] = b[e]; aprev[e] = a[e]; }
+    bt_load<N>(Cc, i, Nsys, sys, cprev);
+    for (int v = 0; v < N; v++) xprev[v] = x[v];
+  }
+  // back substitution; x0 = row 0 of the system as it stands (the reduced-system coupling of the multi-rank algorithm)
+  double x0[N], xnext[N], xt[N], zero[N];
+  for (int v = 0; v < N; v++) { x0[v] = X[((long long)0 * N + v) * Nsys + sys]; zero[v] = 0.0; }
+  {
+    const int i = n - 1;
+    bt_load<N>(B, i, Nsys, sys, b); bt_load<N>(A, i, Nsys, sys, a); bt_load<N>(Cc, i, Nsys, sys, cprev);
+    for (int v = 0; v < N; v++) x[v] = X[((long long)i * N + v) * Nsys + sys];
+    bt_invert<N>(b, binv);
+    bt_matvec_sub<N>(x, a, x0);
+    bt_matvec_sub<N>(x, cprev, zero);
+    for (int r = 0; r < N; r++) { double s = 0; for (int j = 0; j < N; j++) s += (binv[r * N + j] * x[j]); xt[r] = s; }
+    for (int v = 0; v < N; v++) { X[((long long)i * N + v) * Nsys + sys] = xt[v]; xnext[v] = xt[v]; }
+  }
+  for (int i = n - 2; i > -1; i--) {
+    bt_load<N>(B, i, Nsys, sys, b); bt_load<N>(A, i, Nsys, sys, a); bt_load<N>(Cc, i, Nsys, sys, cprev);
+    for (int v = 0; v < N; v++) x[v] = X[((long long)i * N + v) * Nsys + sys];
+    bt_invert<N>(b, binv);
+    bt_matvec_sub<N>(x, cprev, xnext);
+    if (i > 0) bt_matvec_sub<N>(x, a, x0);
+    else       bt_matvec_sub<N>(x, a, x);           // row 0: the reference's x + d*bs IS this row
+    for (int r = 0; r < N; r++) { double s = 0; for (int j = 0; j < N; j++) s += (binv[r * N + j] * x[j]); xt[r] = s; }
+    for (int v = 0; v < N; v++) { X[((long long)i * N + v) * Nsys + sys] = xt[v]; xnext[v] = xt[v]; }
+  }
+  // the solution in the interface layout
+  const long long qbase = t0 * s0 + t1 * s1;
+  for (int i = 0; i < n; i++)
+    for (int v = 0; v < N; v++) fI[v * ni + qbase + i * qs] = X[((long long)i * N + v) * Nsys + sys];
+}
+
 // the linear schemes, component-wise: Interp1PrimFifthOrderUpwind.c:60-147, Interp1PrimFirstOrderUpwind.c:78-84,
 // Interp1PrimSecondOrderCentral.c:80-88, Interp1PrimFourthOrderCentral.c:96-120
 // ... and the MUSCL schemes: Interp1PrimSecondOrderMUSCL.c:118-156 (limiters of src/LimiterFunctions/),
@@ -1544,6 +1753,20 @@ void weno_interp(hpb_solver* h, double* fI, const double* fC, const double* u, c
     MODEL_SWITCH(h->cfg.model, CALL)
 #undef CALL
     LAUNCHED(h);
+    return;
+  }
+  if ((h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h->cfg.hyp_scheme == HPB_SCHEME_CUPW5) && h->phys.interp_char) {
+    // characteristic variant: block rows, then one thread per grid line (block tridiagonal system)
+    int T0, T1;
+    if (dir == 0) { T0 = M[1]; T1 = M[2]; } else if (dir == 1) { T0 = M[0]; T1 = M[2]; } else { T0 = M[0]; T1 = M[1]; }
+    const int tpb = 64;
+#define CALL(M_) { k_compact_rows_char<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, fC, u, w, upw, dir, uflag, \
+                       h->d_tri[0], h->d_tri[1], h->d_tri[2], h->d_bx); \
+                   k_block_tridiag<M_><<<dim3((T0 + tpb - 1) / tpb, T1, 1), tpb, 0, h->stream>>>(G, dir, h->d_tri[0], h->d_tri[1], \
+                       h->d_tri[2], h->d_bx, fI); }
+    MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+    LAUNCHED(h); LAUNCHED(h);
     return;
   }
   if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h->cfg.hyp_scheme == HPB_SCHEME_CUPW5) {

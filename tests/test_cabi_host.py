@@ -132,8 +132,6 @@ def test_decomposed_setup_neighbors_and_remainders():
 
 @pytest.mark.parametrize("mutate, msg", [
     (lambda c: c.solver.__setitem__("hyp_space_scheme", "hcweno5"), "weno5"),
-    (lambda c: (c.solver.__setitem__("hyp_space_scheme", "crweno5"),
-                c.solver.__setitem__("hyp_interp_type", "characteristic")), "characteristic"),
     (lambda c: (c.solver.__setitem__("hyp_space_scheme", "cupw5"), c.solver.__setitem__("iproc", [1, 2, 1])), "iproc"),
     (lambda c: c.solver.__setitem__("time_scheme", "glm-gee"), "rk"),
     (lambda c: c.solver.__setitem__("time_scheme_type", "ssprk2"), "ssprk3"),

@@ -64,6 +64,8 @@ GOLDEN = [
     ("chan2d_mapped_supersonic_dirichlet", "ns_channel", dict(n=(20, 24), weno="mapped", mach=1.6, bcs="sup"), "hypar_ref_mpi1", False),
     ("chan3d_z_ambivalent_visc", "ns_channel", dict(n=(12, 10, 10), weno="z", viscous=True, bcs="amb3"), "hypar_ref_mpi1", False),
     ("c2_sod_js_char_roe_gravity", "euler1d_sod", dict(n=101, weno="js", gravity=1.0), "hypar_ref", True),
+    ("c2_sod_crweno_js_char_roe", "euler1d_sod", dict(n=101, weno="js", scheme="crweno5"), "hypar_ref", True),
+    ("c3_vortex_crweno_z_char_roe", "ns2d_vortex", dict(n=(20, 16), weno="z", upwinding="roe", interp="characteristic", scheme="crweno5"), "hypar_ref_mpi1", False),
     ("c2_sod_upw5_comp_rusanov", "euler1d_sod", dict(n=101, weno="js", interp="components", upwinding="rusanov", scheme="upw5"), "hypar_ref", True),
 ]
 
