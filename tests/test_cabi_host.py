@@ -130,6 +130,24 @@ def test_decomposed_setup_neighbors_and_remainders():
     sv.close()
 
 
+def test_decomposed_zone_extents_of_open_boundaries_and_sponges():
+    """every rank's zone boxes (edge zones: only on the ranks that own the face; sponge: an interior box on every rank it
+    overlaps, InitializeBoundaries.c:381-440) against the independent numpy set-up"""
+    for case in (cases.with_sponge(cases.ns_channel((24, 20), "js", iproc=(2, 2)), 0, 1, 0.4, 1.0, [1.0, 0.5, 0.0, 2.0]),
+                 cases.with_sponge(cases.ns_channel((12, 10, 14), "js", iproc=(2, 1, 2), bcs="sup3"), 2, -1, 0.0, 0.6,
+                                   [1, 0, 0, 0, 2]),
+                 cases.with_sponge(cases.linear_advection_nd((24, 21), "js", iproc=(3, 2)), 1, 1, 0.2, 0.8, [0.5])):
+        for r in range(int(np.prod(case.solver["iproc"]))):
+            S = hpo.Setup(case, rank=r)
+            sv = Solver.from_case(case, rank=r)
+            for n, z in enumerate(S.zones):
+                a, b, on = sv.zone_extent(n)
+                assert on == z["on"], (case.name, r, n)
+                if on:
+                    assert a == z["is"] and b == z["ie"], (case.name, r, n)
+            sv.close()
+
+
 @pytest.mark.parametrize("mutate, msg", [
     (lambda c: c.solver.__setitem__("hyp_space_scheme", "hcweno5"), "weno5"),
     (lambda c: (c.solver.__setitem__("hyp_space_scheme", "cupw5"), c.solver.__setitem__("iproc", [1, 2, 1])), "iproc"),
