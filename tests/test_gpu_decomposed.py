@@ -25,6 +25,14 @@ DECOMP = [
 ]
 DECOMP[-2].solver["iproc"] = [2]
 DECOMP[-1].solver["iproc"] = [3]
+DECOMP += [
+    # open / wall boundary zones and a sponge box across ranks; NavierStokes2D gravity; characteristic + Roe in 2-D
+    cases.with_sponge(cases.ns_channel((28, 24), "js", iproc=(2, 2)), 0, 1, 0.4, 1.0, [1.0, 0.5, 0.0, 2.0]),
+    cases.ns_channel((14, 12, 16), "mapped", viscous=True, bcs="amb3", iproc=(2, 1, 2)),
+    cases.ns2d_rising_bubble((24, 28), "yc", iproc=(2, 2)),
+    cases.ns2d_vortex((28, 24), "z", upwinding="roe", interp="characteristic", iproc=(2, 1)),
+    cases.with_muscl(cases.linear_advection_nd((24, 21), "js", iproc=(3, 2)), "muscl3"),
+]
 for c in DECOMP:
     c.name += "_iproc" + "x".join(str(v) for v in c.solver["iproc"])
 
