@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from _multirank import LocalRanks, MultiRankOracle
-from conftest import rel_linf
+from conftest import assert_exact, rel_linf
 from hypar_b200 import cases
 from oracle import hpo
 
@@ -50,8 +50,8 @@ def test_decomposed_rhs_and_steps(need_gpu, case, fused):
     for r in range(MO.nranks):
         assert np.isfinite(rhs[r]).all()
         if not fused:
-            assert np.array_equal(rhs[r], rhs_ref[r]), \
-                f"rank {r}: rhs not bit-identical (max abs diff {np.abs(rhs[r] - rhs_ref[r]).max():.3e})"
+            ulp = case.name.startswith("chan") and float(case.physics.get("Re", -1.0)) > 0
+            assert_exact(rhs[r], rhs_ref[r], f"rank {r}: rhs", libm_ulp=ulp)
         else:
             lam = MO.O[r].cfl(u_ref[r], float(case.solver["dt"])) / float(case.solver["dt"])
             tol = 1e-12 * scale + 16 * np.finfo(np.float64).eps * lam * np.abs(u_ref[r]).max()
@@ -70,7 +70,9 @@ def test_decomposed_rhs_and_steps(need_gpu, case, fused):
     for r in range(MO.nranks):
         a, b = MO.S[r].interior(u[r]), MO.S[r].interior(u_ref[r])
         if not fused:
-            assert np.array_equal(a, b), f"rank {r}: u after 2 steps not bit-identical ({np.abs(a - b).max():.3e})"
+            # viscous channel case: temperatures on which CUDA's and glibc's exp / log differ by an ulp (conftest.assert_exact)
+            ulp = case.name.startswith("chan") and float(case.physics.get("Re", -1.0)) > 0
+            assert_exact(a, b, f"rank {r}: u after 2 steps", libm_ulp=ulp)
         else:
             assert rel_linf(a, b) <= 1e-11, f"rank {r}: u after 2 steps rel err {rel_linf(a, b):.3e}"
     LR.close()
