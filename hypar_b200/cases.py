@@ -177,6 +177,21 @@ def linear_advection_nd(n: Sequence[int] = (32, 24), weno: str = "js", advection
         physics=phys, weno=weno_inp(weno), x=xs, u0=u[..., None])
 
 
+def burgers_nd(n: Sequence[int] = (64,), weno: str = "js", tstype: str = "ssprk3", scheme: str = "weno5", iproc=None) -> Case:
+    """Inviscid Burgers equation (model `burgers`, Examples/1D/Burgers/SineWave, Examples/2D/Burgers, 3D/Burgers): a
+    periodic sine field with sign changes (both upwind branches and the local Lax-Friedrichs one are taken)."""
+    nd = len(n)
+    xs = [np.arange(n[d], dtype=np.float64) / n[d] for d in range(nd)]
+    grids = np.meshgrid(*[xs[d] for d in reversed(range(nd))], indexing="ij")
+    X = list(reversed(grids))
+    u = 0.2 + np.prod([np.sin(2.0 * np.pi * X[d] + 0.4 * d) for d in range(nd)], axis=0)
+    return Case(
+        name=f"burgers{nd}d_{'x'.join(str(v) for v in n)}_{weno}" + _sfx(scheme),
+        solver=_solver(nd, 1, n, "burgers", ts="rk", tstype=tstype, dt=0.2 / max(n), scheme=scheme, iproc=iproc),
+        boundary=_zones(nd, "periodic", [-1e3] * nd, [1e3] * nd),
+        physics={}, weno=weno_inp(weno), x=xs, u0=u[..., None])
+
+
 # ------------------------------------------------------------------------------------- C2
 def euler1d_sod(n: int = 201, weno: str = "js", interp: str = "characteristic",
                 upwinding: str = "roe", tstype: str = "ssprk3", scheme: str = "weno5",

@@ -52,9 +52,10 @@ int hpb_setup_host(hpb_solver* h)
   // ---- validation: what the device path implements (anything else fails loudly)
   if (nd < 1 || nd > 3) return hpb_fail(HPB_ERR_INVALID, "ndims = %d not supported (1..3)", nd);
   if (g != HPB_G) return hpb_fail(HPB_ERR_INVALID, "ghost = %d: the WENO5 device path needs exactly %d ghost layers", g, HPB_G);
-  static const int model_nv[4] = { -1, 3, 4, 5 }, model_nd[4] = { -1, 1, 2, 3 };
-  if (c.model < 0 || c.model > 3) return hpb_fail(HPB_ERR_INVALID, "unknown model id %d", c.model);
-  if (c.model != HPB_MODEL_LINEAR_ADR && (c.nvars != model_nv[c.model] || nd != model_nd[c.model]))
+  static const int model_nv[5] = { -1, 3, 4, 5, -1 }, model_nd[5] = { -1, 1, 2, 3, -1 };
+  if (c.model < 0 || c.model > HPB_MODEL_BURGERS) return hpb_fail(HPB_ERR_INVALID, "unknown model id %d", c.model);
+  if (c.model == HPB_MODEL_BURGERS && c.nvars != 1) return hpb_fail(HPB_ERR_INVALID, "burgers: nvars must be 1");
+  if (c.model != HPB_MODEL_LINEAR_ADR && c.model != HPB_MODEL_BURGERS && (c.nvars != model_nv[c.model] || nd != model_nd[c.model]))
     return hpb_fail(HPB_ERR_INVALID, "model %d needs ndims=%d nvars=%d (got %d, %d)", c.model, model_nd[c.model],
                     model_nv[c.model], nd, c.nvars);
   if (c.nvars < 1 || c.nvars > HPB_MAX_NVARS) return hpb_fail(HPB_ERR_INVALID, "nvars = %d not supported", c.nvars);
@@ -65,7 +66,7 @@ int hpb_setup_host(hpb_solver* h)
       (c.upwind < HPB_UPWIND_ROE || c.upwind > HPB_UPWIND_LLF))
     return hpb_fail(HPB_ERR_INVALID, "upwinding %d not implemented (roe, rusanov, rf-char, llf-char)", c.upwind);
   const bool has_grav = (c.gravity[0] != 0.0 || c.gravity[1] != 0.0 || c.gravity[2] != 0.0);
-  if (has_grav && c.model == HPB_MODEL_LINEAR_ADR)
+  if (has_grav && (c.model == HPB_MODEL_LINEAR_ADR || c.model == HPB_MODEL_BURGERS))
     return hpb_fail(HPB_ERR_INVALID, "gravity needs an Euler / Navier-Stokes model");
   if (has_grav && c.model == HPB_MODEL_EULER1D && c.upwind != HPB_UPWIND_LLF && c.upwind != HPB_UPWIND_ROE)   // Euler1DInitialize.c:144-149
     return hpb_fail(HPB_ERR_INVALID, "llf-char or roe upwinding is needed for flows with gravitational forces");
@@ -124,7 +125,7 @@ int hpb_setup_host(hpb_solver* h)
     if (z.face != 1 && z.face != -1) return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: face must be +1/-1", n);
     if (z.type < 0 || z.type > HPB_BC_SPONGE)
       return hpb_fail(HPB_ERR_INVALID, "boundary zone %d: boundary type %d not implemented", n, z.type);
-    if (z.type == HPB_BC_SLIP_WALL && c.model == HPB_MODEL_LINEAR_ADR)
+    if (z.type == HPB_BC_SLIP_WALL && (c.model == HPB_MODEL_LINEAR_ADR || c.model == HPB_MODEL_BURGERS))
       return hpb_fail(HPB_ERR_INVALID, "slip-wall needs an Euler/Navier-Stokes model");
     if ((z.type == HPB_BC_NOSLIP_WALL || (z.type >= HPB_BC_SUBSONIC_INFLOW && z.type <= HPB_BC_SUPERSONIC_OUTFLOW)) &&
         c.model != HPB_MODEL_NS2D && c.model != HPB_MODEL_NS3D)      // the reference has 2-D and 3-D branches only

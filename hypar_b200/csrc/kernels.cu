@@ -16,6 +16,7 @@ constexpr int TPB = 128;
     case HPB_MODEL_LINEAR_ADR: { CALL(HPB_MODEL_LINEAR_ADR); } break;        \
     case HPB_MODEL_EULER1D:    { CALL(HPB_MODEL_EULER1D); } break;           \
     case HPB_MODEL_NS2D:       { CALL(HPB_MODEL_NS2D); } break;              \
+    case HPB_MODEL_BURGERS:    { CALL(HPB_MODEL_BURGERS); } break;           \
     default:                   { CALL(HPB_MODEL_NS3D); } break;              \
   }
 
@@ -645,6 +646,12 @@ __global__ void k_cfl(Geom G, Phys ph, const double* __restrict__ dxinv, const d
     if (MODEL == HPB_MODEL_LINEAR_ADR) {
       for (int d = 0; d < G.ndims; d++) {
         const double c = ph.adv[G.nvars * d] * dt * dxinv[G.xoff[d] + G.g + idx[d]];
+        if (c > m) m = c;
+      }
+    } else if (MODEL == HPB_MODEL_BURGERS) {      // BurgersComputeCFL.c:14-48: u dt / dx (sic: no absolute value)
+      const double uu = u[cell_index(G, i0, i1, i2)];
+      for (int d = 0; d < G.ndims; d++) {
+        const double c = uu * dt * dxinv[G.xoff[d] + G.g + idx[d]];
         if (c > m) m = c;
       }
     } else {

@@ -10,6 +10,7 @@ template <> struct ModelTraits<HPB_MODEL_LINEAR_ADR> { static constexpr int NV =
 template <> struct ModelTraits<HPB_MODEL_EULER1D>    { static constexpr int NV = 3; static constexpr int ND = 1; };
 template <> struct ModelTraits<HPB_MODEL_NS2D>       { static constexpr int NV = 4; static constexpr int ND = 2; };
 template <> struct ModelTraits<HPB_MODEL_NS3D>       { static constexpr int NV = 5; static constexpr int ND = 3; };
+template <> struct ModelTraits<HPB_MODEL_BURGERS>    { static constexpr int NV = 1; static constexpr int ND = 1; };
 
 HPB_DEV double hpb_abs(double a) { return fabs(a); }
 HPB_DEV double hpb_max3(double a, double b, double c) { return fmax(fmax(a, b), c); }
@@ -46,6 +47,8 @@ HPB_DEV void flux_fn(const Phys& ph, const double* u, int dir, double* f)
   constexpr int NV = ModelTraits<MODEL>::NV;
   if (MODEL == HPB_MODEL_LINEAR_ADR) {
     f[0] = ph.adv[dir] * u[0];
+  } else if (MODEL == HPB_MODEL_BURGERS) {        // BurgersAdvection.c:17-49: the same flux in every direction
+    f[0] = 0.5 * u[0] * u[0];
   } else {
     constexpr int NDV = NV - 2;
     double rho, vel[3], e, P;
@@ -70,7 +73,7 @@ template <int MODEL>
 HPB_DEV void modified_fn(const Phys& ph, const double* u, double gf, double gg, double* uC)
 {
   constexpr int NV = ModelTraits<MODEL>::NV;
-  if (MODEL == HPB_MODEL_LINEAR_ADR) {
+  if (MODEL == HPB_MODEL_LINEAR_ADR || MODEL == HPB_MODEL_BURGERS) {
     uC[0] = u[0];
   } else if (MODEL == HPB_MODEL_EULER1D) {
     const double a = 1.0 / gf;
@@ -322,6 +325,16 @@ HPB_DEV void upwind_fn(const Phys& ph, int dir, const double* fL, const double* 
   constexpr int NV = ModelTraits<MODEL>::NV;
   if (MODEL == HPB_MODEL_LINEAR_ADR) {
     fI[0] = (ph.adv[dir] > 0 ? fL[0] : fR[0]);
+    return;
+  }
+  if (MODEL == HPB_MODEL_BURGERS) {               // BurgersUpwind.c:17-70: the wave speed is u itself
+    const double eigL = ucL[0], eigR = ucR[0];
+    if ((eigL > 0) && (eigR > 0))      fI[0] = fL[0];
+    else if ((eigL < 0) && (eigR < 0)) fI[0] = fR[0];
+    else {
+      const double alpha = fmax(hpb_abs(eigL), hpb_abs(eigR));
+      fI[0] = 0.5 * (fL[0] + fR[0] - alpha * (uR[0] - uL[0]));
+    }
     return;
   }
   double udiff[NV], uavg[NV];

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib, hypario
 
-MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3}
+MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3, "burgers": 4}
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "dirichlet": 4, "subsonic-inflow": 5,
            "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9, "sponge": 10}
 UPWINDS = {"roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
@@ -94,6 +94,10 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
             raise HyParB200Error("LinearADR spatially-varying advection is not on the B200 path")
         if c.nvars != 1:
             raise HyParB200Error("LinearADR: nvars must be 1 on the B200 path")
+    elif c.model == 4:
+        c.upwind = 0                 # BurgersUpwind: the model's only upwinding
+        if c.nvars != 1:
+            raise HyParB200Error("burgers: nvars must be 1")
     else:
         up = str(ph.get("upwinding", "roe"))
         if up not in UPWINDS:

@@ -48,6 +48,7 @@ extern "C" {
 #define HPB_MODEL_EULER1D    1  /* "euler1d"        */
 #define HPB_MODEL_NS2D       2  /* "navierstokes2d" */
 #define HPB_MODEL_NS3D       3  /* "navierstokes3d" */
+#define HPB_MODEL_BURGERS    4  /* "burgers": inviscid Burgers equation, nvars = 1, 1-3 dimensions (src/PhysicalModels/Burgers) */
 
 /* weno.inp -- reference src/InterpolationFunctions/WENOFifthOrderCalculateWeights.c:40-61 */
 #define HPB_WENO_JS 0

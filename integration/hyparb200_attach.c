@@ -250,6 +250,8 @@ int hyparb200_attach(void *sims, int nsims)
     c.model = HPB_MODEL_EULER1D;  c.gamma = p->gamma;
     c.upwind = upwind_choice(p->upw_choice);
     c.gravity[0] = p->grav;  c.gravity_type = p->grav_type;
+  } else if (!strcmp(s->model, "burgers")) {            /* _BURGERS_ (physicalmodels/burgers.h): no parameters */
+    c.model = HPB_MODEL_BURGERS;  c.upwind = HPB_UPWIND_DEFAULT;
   } else if (!strcmp(s->model, _LINEAR_ADVECTION_DIFFUSION_REACTION_)) {
     LinearADR *p = (LinearADR*) s->physics;
     c.model = HPB_MODEL_LINEAR_ADR;  c.upwind = HPB_UPWIND_DEFAULT;

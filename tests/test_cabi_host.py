@@ -62,6 +62,7 @@ ALL_CASES = [
     cases.ns2d_rising_bubble((20, 24), "js"),                      # 2-D gravity field (HB 2) and slip walls
     cases.ns2d_rising_bubble((24, 20), "z", hb=1, upwinding="roe"),
     cases.linear_advection_nd((24, 20), "js"),
+    cases.burgers_nd((24, 20), "js"),
     cases.with_sponge(cases.ns_channel((24, 20), "js"), 0, 1, 0.7, 1.0, [1.0, 0.5, 0.0, 2.0]),    # interior sponge box
     cases.linear_advection_nd((12, 10, 14), "js", diffusion=[0.01, 0.0, 0.02]),
     cases.euler1d_sod(101, "js", gravity=1.0),                      # 1-D gravity field, mirrored at the physical faces

@@ -40,7 +40,7 @@ def same(a, b, what):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 38
+    assert len(GOLDEN) >= 39
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -201,6 +201,12 @@ def _live_cases():
         cases.ns2d_vortex((20, 24), "js", upwinding="rf-char", interp="characteristic", scheme="cupw5"),
         cases.with_characteristic(cases.ns3d_turbulence((12, 10, 14), "mapped", viscous=True, upwinding="roe", scheme="crweno5")),
         cases.with_characteristic(cases.ns_channel((12, 10, 14), "js", scheme="cupw5")),
+        # inviscid Burgers equation (src/PhysicalModels/Burgers)
+        cases.burgers_nd((96,), "mapped"),
+        cases.burgers_nd((24, 20), "z"),
+        cases.burgers_nd((12, 10, 14), "js"),
+        cases.burgers_nd((20, 24), "yc", scheme="crweno5"),
+        cases.with_muscl(cases.burgers_nd((80,), "js"), "muscl3"),
         # Euler1D with gravity (Euler1DGravityField.c, Euler1DSource.c)
         cases.euler1d_sod(101, "js", gravity=1.0),
         cases.euler1d_sod(101, "mapped", interp="components", upwinding="llf-char", gravity=1.0),

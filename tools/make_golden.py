@@ -66,6 +66,7 @@ GOLDEN = [
     ("c2_sod_js_char_roe_gravity", "euler1d_sod", dict(n=101, weno="js", gravity=1.0), "hypar_ref", True),
     ("c2_sod_crweno_js_char_roe", "euler1d_sod", dict(n=101, weno="js", scheme="crweno5"), "hypar_ref", True),
     ("c3_vortex_crweno_z_char_roe", "ns2d_vortex", dict(n=(20, 16), weno="z", upwinding="roe", interp="characteristic", scheme="crweno5"), "hypar_ref_mpi1", False),
+    ("burgers2d_z", "burgers_nd", dict(n=(24, 20), weno="z"), "hypar_ref", True),
     ("c2_sod_upw5_comp_rusanov", "euler1d_sod", dict(n=101, weno="js", interp="components", upwinding="rusanov", scheme="upw5"), "hypar_ref", True),
 ]
 
