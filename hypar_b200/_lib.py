@@ -38,7 +38,7 @@ class Config(C.Structure):
         ("x_global", C.POINTER(C.c_double)),
         ("device", C.c_int), ("use_fused", C.c_int), ("conservation_check", C.c_int),
         ("hyp_scheme", C.c_int), ("muscl_limiter", C.c_int), ("muscl_eps", C.c_double),
-        ("gravity_type", C.c_int),
+        ("gravity_type", C.c_int), ("advection_field", C.POINTER(C.c_double)),
     ]
 
 
@@ -48,6 +48,7 @@ SYMBOLS = [
     "hpb_device_count", "hpb_version", "hpb_sizeof_config",
     "hpb_partition1d", "hpb_rank1d", "hpb_ranknd", "hpb_get_local_dims", "hpb_npoints_local_wghosts",
     "hpb_ninterfaces", "hpb_get_grid", "hpb_get_neighbors", "hpb_get_zone_extent", "hpb_get_gravity_field",
+    "hpb_get_advection_field",
     "hpb_ApplyBoundaryConditions", "hpb_HyperbolicFunction", "hpb_ParabolicFunction", "hpb_SourceFunction",
     "hpb_RHSFunction", "hpb_FFunction", "hpb_UFunction", "hpb_SetInterpLimiterVar", "hpb_GetInterpWeights",
     "hpb_InterpolateInterfacesHyp", "hpb_Upwind", "hpb_FirstDerivativePar", "hpb_SecondDerivativePar",
@@ -97,6 +98,7 @@ def load():
     L.hpb_get_neighbors.argtypes = [vp, ip]
     L.hpb_get_zone_extent.argtypes = [vp, C.c_int, ip, ip, ip]
     L.hpb_get_gravity_field.argtypes = [vp, dp, dp]
+    L.hpb_get_advection_field.argtypes = [vp, dp]
     L.hpb_ApplyBoundaryConditions.argtypes = [vp, dp, C.c_double]
     L.hpb_HyperbolicFunction.argtypes = [vp, dp, dp, C.c_double, C.c_int]
     L.hpb_ParabolicFunction.argtypes = [vp, dp, dp, C.c_double]

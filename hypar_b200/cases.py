@@ -34,6 +34,7 @@ class Case:
     x: List[np.ndarray]            # global coordinates per dimension
     u0: np.ndarray                 # shape (N_{nd-1}, ..., N_0, nvars)
     muscl: Optional[Dict[str, object]] = None      # muscl.inp (epsilon, limiter) for muscl2 / muscl3
+    advection_field: Optional[np.ndarray] = None   # LinearADR `advection_filename advection`: shape (N_{nd-1},...,N_0, ndims*nvars)
 
     @property
     def ndims(self) -> int:
@@ -56,6 +57,8 @@ class Case:
             hypario.write_keyword_file(os.path.join(d, "weno.inp"), self.weno)
         if self.muscl is not None:
             hypario.write_keyword_file(os.path.join(d, "muscl.inp"), self.muscl)
+        if self.advection_field is not None:           # same binary layout as initial.inp (ReadArray.c:225-256)
+            hypario.write_initial_bin(os.path.join(d, "advection.inp"), self.x, self.advection_field)
         hypario.write_initial_bin(os.path.join(d, "initial.inp"), self.x, self.u0)
 
 
@@ -175,6 +178,31 @@ def linear_advection_nd(n: Sequence[int] = (32, 24), weno: str = "js", advection
                        par_scheme=par_scheme, scheme=scheme, iproc=iproc),
         boundary=_zones(nd, "periodic", [-1e3] * nd, [1e3] * nd),
         physics=phys, weno=weno_inp(weno), x=xs, u0=u[..., None])
+
+
+def linear_advection_varying(n: Sequence[int] = (96,), weno: str = "js", tstype: str = "44", scheme: str = "weno5",
+                             iproc=None, periodic: bool = True) -> Case:
+    """Scalar advection by a spatially varying velocity field read from a file (physics.inp `advection_filename`,
+    Examples/1D/LinearAdvection/SineWave_NonConstantAdvection, Examples/2D/.../SineWave_NonConstantAdvection): the field
+    changes sign, so LinearADRUpwind.c:56-82 takes all three of its branches."""
+    base = linear_advection_nd(n, weno, tstype=tstype, scheme=scheme, iproc=iproc) if len(n) > 1 else None
+    nd = len(n)
+    xs = [np.arange(n[d], dtype=np.float64) / n[d] for d in range(nd)]
+    grids = np.meshgrid(*[xs[d] for d in reversed(range(nd))], indexing="ij")
+    X = list(reversed(grids))
+    u = 0.5 + np.prod([np.sin(2.0 * np.pi * X[d] + 0.3 * d) for d in range(nd)], axis=0)
+    a = np.stack([0.3 + np.cos(2.0 * np.pi * X[d] + 0.7 * d) * np.prod([np.cos(2.0 * np.pi * X[k]) for k in range(nd) if k != d] or [1.0], axis=0)
+                  for d in range(nd)], axis=-1)
+    kind = "periodic" if periodic else "extrapolate"
+    case = Case(
+        name=f"linadvvar{nd}d_{'x'.join(str(v) for v in n)}_{weno}_{kind[:3]}" + _sfx(scheme),
+        solver=_solver(nd, 1, n, "linear-advection-diffusion-reaction", ts="rk", tstype=tstype, dt=0.1 / max(n),
+                       scheme=scheme, iproc=iproc),
+        boundary=_zones(nd, kind, [-1e3] * nd, [1e3] * nd),
+        physics={"advection_filename": "advection"}, weno=weno_inp(weno), x=xs, u0=u[..., None])
+    case.advection_field = np.ascontiguousarray(a)
+    del base
+    return case
 
 
 def burgers_nd(n: Sequence[int] = (64,), weno: str = "js", tstype: str = "ssprk3", scheme: str = "weno5", iproc=None) -> Case:

@@ -241,6 +241,12 @@ extern "C" int hpb_create(const hpb_config* cfg, hpb_solver** out)
     cudaMemcpy(h->d_dxinv, h->dxinv_h.data(), nx * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_gravf, h->gravf_h.data(), (size_t)G.npg * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_gravg, h->gravg_h.data(), (size_t)G.npg * sizeof(double), cudaMemcpyHostToDevice);
+    h->phys.advf = nullptr; h->phys.advf_npg = G.npg;
+    if (!h->advf_h.empty()) {
+      rc = dalloc(&h->d_advf, (long long)h->advf_h.size());   if (rc) { hpb_destroy(h); return rc; }
+      cudaMemcpy(h->d_advf, h->advf_h.data(), h->advf_h.size() * sizeof(double), cudaMemcpyHostToDevice);
+      h->phys.advf = h->d_advf;
+    }
     cudaStreamSynchronize(cudaStreamLegacy);   // pageable H2D may still be in flight on return; h->stream is non-blocking
     if (cudaMallocHost((void**)&h->h_red, 8 * sizeof(double)) != cudaSuccess) { hpb_destroy(h); return hpb_fail(HPB_ERR_ALLOC, "pinned alloc"); }
     // halo buffers (only for faces that have a neighbour)
@@ -277,6 +283,7 @@ extern "C" int hpb_destroy(hpb_solver* h)
   for (int i = 0; i < 3; i++) if (h->d_tri[i]) cudaFree(h->d_tri[i]);
   if (h->d_err) cudaFree(h->d_err);
   if (h->d_bx) cudaFree(h->d_bx);
+  if (h->d_advf) cudaFree(h->d_advf);
   if (h->d_pipe_in) cudaFree(h->d_pipe_in);
   if (h->d_pipe_out) cudaFree(h->d_pipe_out);
   for (int k = 0; k < 4; k++) if (h->ev_pipe[k]) cudaEventDestroy(h->ev_pipe[k]);
@@ -324,6 +331,14 @@ extern "C" int hpb_get_gravity_field(const hpb_solver* h, double* f, double* g)
 {
   if (f) memcpy(f, h->gravf_h.data(), h->gravf_h.size() * sizeof(double));
   if (g) memcpy(g, h->gravg_h.data(), h->gravg_h.size() * sizeof(double));
+  return HPB_OK;
+}
+extern "C" int hpb_get_advection_field(const hpb_solver* h, double* a)
+{
+  if (h->advf_h.empty() || !a) return hpb_fail(HPB_ERR_INVALID, "no spatially varying advection field");
+  const int nd = h->cfg.ndims;
+  const size_t npg = h->advf_h.size() / nd;
+  for (size_t p = 0; p < npg; p++) for (int d = 0; d < nd; d++) a[p * nd + d] = h->advf_h[(size_t)d * npg + p];
   return HPB_OK;
 }
 extern "C" long long hpb_kernel_launch_count(const hpb_solver* h) { return h->launches; }

@@ -279,6 +279,52 @@ int hpb_setup_host(hpb_solver* h)
     }
   }
 
+  // ---- LinearADR spatially varying advection (LinearADRAdvectionField.c:25-193): this rank's block with ghosts. Interior
+  // from the global field; internal faces from the neighbour's interior (= the global field); physical faces: periodic copy
+  // (one rank along the dimension) or mirror extrapolation; edges and corners are never filled (zero).
+  h->advf_h.clear();
+  if (c.advection_field) {
+    if (c.model != HPB_MODEL_LINEAR_ADR || c.nvars != 1)
+      return hpb_fail(HPB_ERR_INVALID, "advection_field: linear-advection-diffusion-reaction with nvars = 1 only");
+    const int NG[3] = { c.dim_global[0], nd > 1 ? c.dim_global[1] : 1, nd > 2 ? c.dim_global[2] : 1 };
+    h->advf_h.assign((size_t)nd * G.npg, 0.0);
+    bool dper[3] = { false, false, false };
+    for (int n = 0; n < c.nzones; n++) if (c.zones[n].type == HPB_BC_PERIODIC) dper[c.zones[n].dim] = true;
+    auto gidx = [&](int i0, int i1, int i2) { return (size_t)i0 + (size_t)NG[0] * ((size_t)i1 + (size_t)NG[1] * (size_t)i2); };
+    auto lidx = [&](int i0, int i1, int i2) {        // local indices, may be ghosts
+      size_t p = (size_t)(i0 + g);
+      if (nd > 1) p += (size_t)G.P[0] * (size_t)(i1 + g);
+      if (nd > 2) p += (size_t)G.P[0] * (size_t)G.P[1] * (size_t)(i2 + g);
+      return p; };
+    // interior + ghost layers along ONE dimension at a time (the transverse indices stay interior)
+    for (int dd = -1; dd < nd; dd++) {
+      int lo[3] = { 0, 0, 0 }, hi[3] = { G.N[0], G.N[1], G.N[2] };
+      for (int pass = 0; pass < (dd < 0 ? 1 : 2); pass++) {
+        if (dd >= 0) { lo[dd] = pass ? G.N[dd] : -g; hi[dd] = pass ? G.N[dd] + g : 0; }
+        for (int k = lo[2]; k < hi[2]; k++) for (int j = lo[1]; j < hi[1]; j++) for (int i = lo[0]; i < hi[0]; i++) {
+          int li[3] = { i, j, k }, gi[3];
+          bool ok = true;
+          for (int d = 0; d < 3; d++) gi[d] = (d < nd ? h->is_global[d] + li[d] : 0);
+          if (dd >= 0) {
+            const int d = dd, n = G.N[d];
+            const bool low = (li[d] < 0);
+            const bool internal = low ? (h->ip[d] > 0) : (h->ip[d] < c.iproc[d] - 1);
+            // (sic) a periodic dimension split among ranks: the exchange wraps the end ranks' outer ghosts, and the
+            // else-branch of LinearADRAdvectionField.c:142-189 then overwrites them with the mirror image
+            if (internal) { /* neighbour's interior: the global index as it is */ }
+            else if (dper[d] && c.iproc[d] == 1) gi[d] = h->is_global[d] + (low ? li[d] + n : li[d] - n);   // periodic copy
+            else gi[d] = h->is_global[d] + (low ? (-1 - li[d]) : (2 * n - 1 - li[d]));                      // mirror
+            ok = (gi[d] >= 0 && gi[d] < NG[d]);
+          }
+          if (!ok) continue;
+          const size_t p = lidx(li[0], li[1], li[2]), q = gidx(gi[0], gi[1], gi[2]);
+          for (int d = 0; d < nd; d++) h->advf_h[(size_t)d * G.npg + p] = c.advection_field[q * nd + d];
+        }
+        if (dd >= 0) { lo[dd] = 0; hi[dd] = G.N[dd]; }
+      }
+    }
+  }
+
   if (c.model == HPB_MODEL_EULER1D) {
     // Euler1DGravityField.c:25-95: ONE field S, used as both grav_f and grav_g here; type 0 exp(-g x) with mirror copies into
     // the ghosts of physical faces, type 1 exp(sin(2 pi x) / (2 pi)) without

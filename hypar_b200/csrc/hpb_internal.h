@@ -31,6 +31,8 @@ struct Phys {
   double eps, gamma, Re, Pr, RT;     // Re already / Minf ; RT = p0/rho0
   double grav[3];
   double adv[15], diff[15];
+  const double* advf;                // LinearADR spatially varying advection on the device, [dir*advf_npg + p]; nullptr = constant
+  long long advf_npg;
 };
 
 struct ZoneDev {
@@ -55,6 +57,8 @@ struct hpb_solver {
   int bcperiodic[3];               // mpi->bcperiodic: periodic AND iproc>1
   std::vector<ZoneDev> zones;
   std::vector<double> x_h, dxinv_h, gravf_h, gravg_h;   // host copies (set-up products)
+  std::vector<double> advf_h;      // LinearADR varying advection field of this rank, ghost-padded, [dir*npg + p]
+  double* d_advf = nullptr;
   bool device_ready = false;
   int device = 0;
   cudaStream_t stream = nullptr;

@@ -219,11 +219,13 @@ k_iface(Geom G, Phys ph, const double* __restrict__ u, const double* __restrict_
     for (int v = 0; v < NV; v++) U[k][v] = u[v * G.npg + p];
     const double gfk = gf ? gf[p] : 1.0;
     GG[k] = gg ? gg[p] : 1.0;
-    flux_fn<MODEL>(ph, U[k], dir, F[k]);
+    flux_fn<MODEL>(ph, U[k], dir, F[k], p);
     modified_fn<MODEL>(ph, U[k], gfk, GG[k], V[k]);
   }
-  const double kL = (MODEL == HPB_MODEL_EULER1D) ? (gf ? gf[pm1] : 1.0) : GG[2];
-  const double kR = (MODEL == HPB_MODEL_EULER1D) ? (gf ? gf[pm1 + st] : 1.0) : GG[3];
+  // kappa sources of the upwinding (grav fields); LinearADR with a varying advection field: the speeds of the two cells
+  const bool lin_var = (MODEL == HPB_MODEL_LINEAR_ADR) && ph.advf != nullptr;
+  const double kL = lin_var ? ph.advf[dir * ph.advf_npg + pm1] : (MODEL == HPB_MODEL_EULER1D) ? (gf ? gf[pm1] : 1.0) : GG[2];
+  const double kR = lin_var ? ph.advf[dir * ph.advf_npg + pm1 + st] : (MODEL == HPB_MODEL_EULER1D) ? (gf ? gf[pm1 + st] : 1.0) : GG[3];
 
   double fL[NV], fR[NV], uL[NV], uR[NV];
   double wLF[NV][3], wRF[NV][3];
@@ -643,7 +645,15 @@ __global__ void k_cfl(Geom G, Phys ph, const double* __restrict__ dxinv, const d
   double m = 0.0;
   if (i0 < G.N[0]) {
     const int idx[3] = { i0, i1, i2 };
-    if (MODEL == HPB_MODEL_LINEAR_ADR) {
+    if (MODEL == HPB_MODEL_LINEAR_ADR && ph.advf != nullptr) {
+      // LinearADRComputeCFL.c:41-58 (sic: the spacing of dimension 0 for every direction)
+      const long long p = cell_index(G, i0, i1, i2);
+      const double dxi = dxinv[G.xoff[0] + G.g + idx[0]];
+      for (int d = 0; d < G.ndims; d++) {
+        const double c = ph.advf[d * ph.advf_npg + p] * dt * dxi;
+        if (c > m) m = c;
+      }
+    } else if (MODEL == HPB_MODEL_LINEAR_ADR) {
       for (int d = 0; d < G.ndims; d++) {
         const double c = ph.adv[G.nvars * d] * dt * dxinv[G.xoff[d] + G.g + idx[d]];
         if (c > m) m = c;
@@ -794,7 +804,7 @@ __global__ void k_flux(Geom G, Phys ph, const double* __restrict__ u, int dir, d
   double uu[NV], ff[NV];
 #pragma unroll
   for (int v = 0; v < NV; v++) uu[v] = u[v * G.npg + p];
-  flux_fn<MODEL>(ph, uu, dir, ff);
+  flux_fn<MODEL>(ph, uu, dir, ff, p);
 #pragma unroll
   for (int v = 0; v < NV; v++) f[v * G.npg + p] = ff[v];
 }
@@ -1414,7 +1424,9 @@ __global__ void k_upwind(Geom G, Phys ph, const double* __restrict__ fL, const d
     cl[v] = u[v * G.npg + pL]; cr[v] = u[v * G.npg + pR];
   }
   const double* kk = (MODEL == HPB_MODEL_EULER1D) ? gf : gg;
-  upwind_fn<MODEL>(ph, dir, a, b, c, d, cl, cr, kk ? kk[pL] : 1.0, kk ? kk[pR] : 1.0, out);
+  double kLv = kk ? kk[pL] : 1.0, kRv = kk ? kk[pR] : 1.0;
+  if (MODEL == HPB_MODEL_LINEAR_ADR && ph.advf != nullptr) { kLv = ph.advf[dir * ph.advf_npg + pL]; kRv = ph.advf[dir * ph.advf_npg + pR]; }
+  upwind_fn<MODEL>(ph, dir, a, b, c, d, cl, cr, kLv, kRv, out);
 #pragma unroll
   for (int v = 0; v < NV; v++) fI[v * ni + q] = out[v];
 }

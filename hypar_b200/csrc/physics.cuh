@@ -42,11 +42,13 @@ HPB_DEV void flowvar(const double* u, double gamma, double& rho, double* vel, do
 // ---- FFunction: NavierStokes3DFlux.c:24 (_NavierStokes3DSetFlux_ navierstokes3d.h:114-139),
 // NavierStokes2DFlux.c:21, Euler1DFlux.c:16, LinearADRAdvection.c:37
 template <int MODEL>
-HPB_DEV void flux_fn(const Phys& ph, const double* u, int dir, double* f)
+HPB_DEV void flux_fn(const Phys& ph, const double* u, int dir, double* f, long long p = -1)
 {
   constexpr int NV = ModelTraits<MODEL>::NV;
   if (MODEL == HPB_MODEL_LINEAR_ADR) {
-    f[0] = ph.adv[dir] * u[0];
+    // p: the cell (with ghosts) -- only the spatially varying advection field needs it (LinearADRAdvection.c:72-80)
+    const double a = (ph.advf != nullptr && p >= 0) ? ph.advf[dir * ph.advf_npg + p] : ph.adv[dir];
+    f[0] = a * u[0];
   } else if (MODEL == HPB_MODEL_BURGERS) {        // BurgersAdvection.c:17-49: the same flux in every direction
     f[0] = 0.5 * u[0] * u[0];
   } else {
@@ -324,6 +326,16 @@ HPB_DEV void upwind_fn(const Phys& ph, int dir, const double* fL, const double* 
 {
   constexpr int NV = ModelTraits<MODEL>::NV;
   if (MODEL == HPB_MODEL_LINEAR_ADR) {
+    if (ph.advf != nullptr) {       // LinearADRUpwind.c:56-82; kL, kR carry the advection speed of the two adjacent cells
+      const double eigL = kL, eigR = kR;
+      if ((eigL > 0) && (eigR > 0))      fI[0] = fL[0];
+      else if ((eigL < 0) && (eigR < 0)) fI[0] = fR[0];
+      else {
+        const double alpha = fmax(hpb_abs(eigL), hpb_abs(eigR));
+        fI[0] = 0.5 * (fL[0] + fR[0] - alpha * (uR[0] - uL[0]));
+      }
+      return;
+    }
     fI[0] = (ph.adv[dir] > 0 ? fL[0] : fR[0]);
     return;
   }

@@ -89,6 +89,7 @@ bool fused_available(const hpb_solver* h)
   if (!c.use_fused) return false;
   if (c.hyp_scheme != HPB_SCHEME_WENO5) return false;       // compact / linear schemes: reference-exact kernels only
   if (c.model == HPB_MODEL_BURGERS) return false;
+  if (h->phys.advf != nullptr || c.advection_field != nullptr) return false;     // spatially varying advection: exact kernels
   if (h->phys.interp_char) return false;
   if (c.model == HPB_MODEL_EULER1D) return false;
   if ((c.model == HPB_MODEL_NS2D || c.model == HPB_MODEL_NS3D) && c.upwind != HPB_UPWIND_RUSANOV) return false;

@@ -126,11 +126,11 @@ class DistributedSolver:
     """
 
     def __init__(self, solver_inp, boundary, physics, weno, x, rank: int, device: int, group=None,
-                 use_fused: bool = True, overlap: bool = False, muscl=None):
+                 use_fused: bool = True, overlap: bool = False, muscl=None, advection_field=None):
         import torch
         self.torch = torch
         self.solver = Solver(solver_inp, boundary, physics, weno, x, rank=rank, device=device, use_fused=use_fused,
-                             muscl=muscl)
+                             muscl=muscl, advection_field=advection_field)
         sv = self.solver
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.ExternalStream(sv.stream, device=self.device)

@@ -41,7 +41,8 @@ def _dp(a: np.ndarray):
 
 def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], physics: Dict[str, object],
                        weno: Optional[Dict[str, object]], x: Sequence[np.ndarray], rank: int = 0,
-                       device: int = -1, use_fused: bool = True, muscl: Optional[Dict[str, object]] = None):
+                       device: int = -1, use_fused: bool = True, muscl: Optional[Dict[str, object]] = None,
+                       advection_field: Optional[np.ndarray] = None):
     """Translate the contents of solver.inp / boundary.inp / physics.inp / weno.inp / muscl.inp (as parsed
     dictionaries) into an ``hpb_config``. Unsupported choices raise here or in ``hpb_create``."""
     L = _lib.load()
@@ -90,10 +91,21 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
         c.upwind = 0
         if str(ph.get("centered_flux", "no")) != "no":
             raise HyParB200Error("LinearADR centered_flux is not on the B200 path")
-        if "advection_filename" in ph:
-            raise HyParB200Error("LinearADR spatially-varying advection is not on the B200 path")
         if c.nvars != 1:
             raise HyParB200Error("LinearADR: nvars must be 1 on the B200 path")
+        if "advection_filename" in ph:
+            # LinearADRInitialize.c:98-124: `advection` and `advection_filename` exclude each other; a field file that is
+            # not there leaves the field at zero (LinearADRAdvectionField.c:117-120)
+            if "advection" in ph:
+                raise HyParB200Error("LinearADR: both advection and advection_filename are specified")
+            if str(ph["advection_filename"]) != "none":
+                npts = int(np.prod([int(v) for v in size[:nd]]))
+                af = (np.zeros(npts * nd * c.nvars) if advection_field is None
+                      else np.ascontiguousarray(advection_field, dtype=np.float64).reshape(-1))
+                if af.size != npts * nd * c.nvars:
+                    raise HyParB200Error("LinearADR: the advection field must have ndims*nvars components on the global grid")
+                c.advection_field = _dp(af)
+                c._advf_keep = af
     elif c.model == 4:
         c.upwind = 0                 # BurgersUpwind: the model's only upwinding
         if c.nvars != 1:
@@ -153,10 +165,12 @@ class Solver:
     """One rank of the B200 explicit-RHS path."""
 
     def __init__(self, solver: Dict[str, object], boundary, physics, weno, x, rank: int = 0,
-                 device: int = -1, use_fused: bool = True, muscl=None):
+                 device: int = -1, use_fused: bool = True, muscl=None, advection_field=None):
         self.L = _lib.load()
-        self.inputs = {"solver": solver, "boundary": boundary, "physics": physics, "weno": weno, "muscl": muscl}
-        cfg, self._xg = config_from_inputs(solver, boundary, physics, weno, x, rank, device, use_fused, muscl)
+        self.inputs = {"solver": solver, "boundary": boundary, "physics": physics, "weno": weno, "muscl": muscl,
+                       "advection_field": advection_field}
+        cfg, self._xg = config_from_inputs(solver, boundary, physics, weno, x, rank, device, use_fused, muscl,
+                                           advection_field)
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.hpb_create(C.byref(cfg), C.byref(self.h))
@@ -180,7 +194,7 @@ class Solver:
     @classmethod
     def from_case(cls, case, rank: int = 0, device: int = -1, use_fused: bool = True) -> "Solver":
         return cls(case.solver, case.boundary, case.physics, case.weno, case.x, rank, device, use_fused,
-                   muscl=getattr(case, "muscl", None))
+                   muscl=getattr(case, "muscl", None), advection_field=getattr(case, "advection_field", None))
 
     @classmethod
     def from_directory(cls, path: str, rank: int = 0, device: int = -1, use_fused: bool = True) -> "Solver":
@@ -203,7 +217,12 @@ class Solver:
         x, u0 = hypario.read_initial_bin(os.path.join(path, "initial.inp"), s["size"], nv)
         mf = os.path.join(path, "muscl.inp")
         mu = hypario.read_keyword_file(mf) if os.path.exists(mf) else None
-        obj = cls(s, b, ph, w, x, rank, device, use_fused, muscl=mu)
+        af = None
+        if str(ph.get("advection_filename", "none")) != "none":        # same binary layout as initial.inp (ReadArray.c)
+            fn = os.path.join(path, str(ph["advection_filename"]) + ".inp")
+            if os.path.exists(fn):
+                af = hypario.read_initial_bin(fn, s["size"], nd * nv)[1]
+        obj = cls(s, b, ph, w, x, rank, device, use_fused, muscl=mu, advection_field=af)
         obj.u0_global = u0
         return obj
 
@@ -253,6 +272,12 @@ class Solver:
         f, g = np.zeros(self.npoints_local_wghosts), np.zeros(self.npoints_local_wghosts)
         self.L.hpb_get_gravity_field(self.h, _dp(f), _dp(g))
         return f, g
+
+    def advection_field(self) -> np.ndarray:
+        """LinearADR::a of a spatially varying advection: [point with ghosts][ndims*nvars]."""
+        a = np.zeros(self.npoints_local_wghosts * self.ndims * self.nvars)
+        self._ck(self.L.hpb_get_advection_field(self.h, _dp(a)))
+        return a
 
     def local_from_global(self, ug: np.ndarray) -> np.ndarray:
         """This rank's ghost-padded AoS block (ghosts zero) out of a global (N_{nd-1},...,N_0,nvars) array."""

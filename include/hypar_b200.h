@@ -162,6 +162,10 @@ typedef struct hpb_config {
   /* --- physics.inp (cont.) --- */
   int    gravity_type;                 /* Euler1D `gravity_type` (Euler1DGravityField.c:44-52): 0 exp(-g x), 1 sinusoidal
                                           potential; the 1-D gravity is gravity[0]                             */
+  const double* advection_field;       /* LinearADR `advection_filename` (LinearADRAdvectionField.c): the spatially varying
+                                          advection field on the GLOBAL grid, [point][ndims*nvars], points ordered like the
+                                          solution in initial.inp (no ghosts); NULL = constant advection[]. Copied by
+                                          hpb_create.                                                          */
 } hpb_config;
 
 typedef struct hpb_solver hpb_solver;
@@ -191,6 +195,9 @@ int  hpb_get_grid(const hpb_solver* h, double* x_wghosts, double* dxinv_wghosts)
 int  hpb_get_neighbors(const hpb_solver* h, int* neighbor_rank /* [2*ndims], -1 = none */);
 int  hpb_get_zone_extent(const hpb_solver* h, int zone, int* is, int* ie, int* on_this_proc);
 int  hpb_get_gravity_field(const hpb_solver* h, double* grav_f, double* grav_g);
+/* LinearADR varying advection field of this rank (LinearADR::a after LinearADRAdvectionField.c), HyPar layout
+   [point with ghosts][ndims*nvars]; HPB_ERR_INVALID when the advection is constant */
+int  hpb_get_advection_field(const hpb_solver* h, double* a);
 
 /* ------------------------------------------------------------------ HOST entry points
  * (the reference's function-pointer surface; arrays = host, HyPar layout, local + ghosts) */

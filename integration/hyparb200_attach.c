@@ -201,6 +201,7 @@ int hyparb200_attach(void *sims, int nsims)
   }
 
   hpb_config c;
+  double *advf = NULL;              /* LinearADR varying advection field, global, freed after hpb_create */
   if (hpb_sizeof_config() != sizeof(hpb_config)) {
     fprintf(stderr, "hyparb200_attach: include/hypar_b200.h does not match libhypar_b200.so (hpb_config layout)\n");
     return 1;
@@ -255,10 +256,26 @@ int hyparb200_attach(void *sims, int nsims)
   } else if (!strcmp(s->model, _LINEAR_ADVECTION_DIFFUSION_REACTION_)) {
     LinearADR *p = (LinearADR*) s->physics;
     c.model = HPB_MODEL_LINEAR_ADR;  c.upwind = HPB_UPWIND_DEFAULT;
-    if (!p->constant_advection || strcmp(p->centered_flux, "no")) {
-      fprintf(stderr, "hyparb200_attach: LinearADR needs constant advection and upwinded fluxes on the B200 path\n"); return 1;
+    if (strcmp(p->centered_flux, "no") || s->nvars != 1) {
+      fprintf(stderr, "hyparb200_attach: LinearADR needs upwinded fluxes and nvars = 1 on the B200 path\n"); return 1;
     }
-    for (int i = 0; i < s->ndims * s->nvars; i++) { c.advection[i] = p->a[i]; c.diffusion[i] = p->d[i]; }
+    for (int i = 0; i < s->ndims * s->nvars; i++) c.diffusion[i] = p->d[i];
+    if (p->constant_advection == 1) {
+      for (int i = 0; i < s->ndims * s->nvars; i++) c.advection[i] = p->a[i];
+    } else if (p->constant_advection == 0) {
+      /* spatially varying field (LinearADRAdvectionField.c): p->a is this rank's ghost-padded block, [point][ndims*nvars];
+         one rank, so its interior IS the global field the C-ABI takes (hpb_create rebuilds the ghosts) */
+      const int nc = s->ndims * s->nvars;
+      advf = (double*) calloc((size_t) s->npoints_global * nc, sizeof(double));
+      int idx[3] = {0, 0, 0}, done = 0;  long q = 0;
+      while (!done) {
+        int pg; _ArrayIndex1D_(s->ndims, s->dim_local, idx, s->ghosts, pg);
+        for (int k = 0; k < nc; k++) advf[q * nc + k] = p->a[(long) pg * nc + k];
+        q++;
+        _ArrayIncrementIndex_(s->ndims, s->dim_local, idx, done);
+      }
+      c.advection_field = advf;
+    }
   } else {
     fprintf(stderr, "hyparb200_attach: model %s is not on the B200 path\n", s->model); return 1;
   }
@@ -295,6 +312,7 @@ int hyparb200_attach(void *sims, int nsims)
   if (fz) c.use_fused = atoi(fz);
   int rc = hpb_create(&c, &g.h);
   free(xg);
+  if (advf) free(advf);
   if (rc) { fprintf(stderr, "hyparb200_attach: %s\n", hpb_last_error()); return 1; }   /* unsupported choices fail here */
 
   const char *mode = getenv("HYPARB200_MODE");

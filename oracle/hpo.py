@@ -51,7 +51,8 @@ class Ctx(C.Structure):
                 ("zones", Zone * MAXZ),
                 ("x", C.POINTER(C.c_double)), ("dxinv", C.POINTER(C.c_double)),
                 ("grav_f", C.POINTER(C.c_double)), ("grav_g", C.POINTER(C.c_double)),
-                ("scheme", C.c_int), ("muscl_limiter", C.c_int), ("muscl_eps", C.c_double), ("grav_type", C.c_int)]
+                ("scheme", C.c_int), ("muscl_limiter", C.c_int), ("muscl_eps", C.c_double), ("grav_type", C.c_int),
+                ("adv_field", C.POINTER(C.c_double))]
 
 
 _lib = None
@@ -268,6 +269,57 @@ class Setup:
         u[dst] = self.case.u0[src]
         return np.ascontiguousarray(u).reshape(-1)
 
+    def _local_adv_field(self, af: np.ndarray) -> np.ndarray:
+        nd, g, nc = self.ndims, self.ghosts, self.ndims * self.nvars
+        shp = tuple(n + 2 * g for n in reversed(self.dim)) + (nc,)
+        a = np.zeros(shp)
+        axis = lambda d: nd - 1 - d                                        # numpy axis of dimension d
+        inner = [slice(g, g + self.dim[d]) for d in range(nd)]            # per dimension
+        glob = [slice(self.is_[d], self.is_[d] + self.dim[d]) for d in range(nd)]
+        put = lambda loc, gl: a.__setitem__(tuple(loc[d] for d in reversed(range(nd))),
+                                            af[tuple(gl[d] for d in reversed(range(nd)))])
+        put(inner, glob)
+        # internal (MPI) faces, periodic wrap included when iproc > 1
+        for d in range(nd):
+            N, n, i0 = self.dim_global[d], self.dim[d], self.is_[d]
+            for side in (0, 1):
+                if side == 0:
+                    has = self.ip[d] > 0 or (self.periodic[d] and self.iproc[d] > 1)
+                    gidx = [(i0 - g + k) % N for k in range(g)]
+                    loc_sl = slice(0, g)
+                else:
+                    has = self.ip[d] < self.iproc[d] - 1 or (self.periodic[d] and self.iproc[d] > 1)
+                    gidx = [(i0 + n + k) % N for k in range(g)]
+                    loc_sl = slice(g + n, g + n + g)
+                if not has:
+                    continue
+                loc = list(inner); loc[d] = loc_sl
+                gl = list(glob); gl[d] = gidx
+                put(loc, gl)
+        # physical faces (LinearADRAdvectionField.c:118-190), dimension by dimension
+        per = {int(z["dim"]) for z in self.case.boundary if z["type"] == "periodic"}
+        for d in range(nd):
+            n = self.dim[d]
+            ax = axis(d)
+            def view(lo, hi, rev=False):
+                idx = [slice(g, g + self.dim[k]) for k in reversed(range(nd))] + [slice(None)]
+                idx[ax] = slice(lo, hi)
+                v = a[tuple(idx)]
+                return np.flip(v, axis=ax) if rev else v
+            def assign(lo, hi, val):
+                idx = [slice(g, g + self.dim[k]) for k in reversed(range(nd))] + [slice(None)]
+                idx[ax] = slice(lo, hi)
+                a[tuple(idx)] = val
+            if d in per and self.iproc[d] == 1:
+                assign(0, g, view(n, n + g).copy())              # left ghosts <- last g interior
+                assign(g + n, g + n + g, view(g, 2 * g).copy())  # right ghosts <- first g interior
+            else:
+                if self.ip[d] == 0:
+                    assign(0, g, view(g, 2 * g, rev=True).copy())                 # mirror: ghost -1-k <- interior k
+                if self.ip[d] == self.iproc[d] - 1:
+                    assign(g + n, g + n + g, view(n, n + g, rev=True).copy())
+        return np.ascontiguousarray(a).reshape(-1)
+
     def _make_ctx(self) -> Ctx:
         case, s, ph = self.case, self.case.solver, self.case.physics
         w = case.weno or {}
@@ -322,6 +374,15 @@ class Setup:
         self.grav_f, self.grav_g = np.ones(n), np.ones(n)
         c.grav_f, c.grav_g = _p(self.grav_f), _p(self.grav_g)
         c.grav_type = int(ph.get("gravity_type", 0))
+        # LinearADR spatially varying advection (LinearADRAdvectionField.c:25-193): this rank's block of the field with
+        # ghosts -- interior from the file; internal faces from the neighbour (MPIExchangeBoundariesnD = the global field,
+        # wrapped where the dimension is periodic and split); physical faces: periodic copy (one rank along the dimension)
+        # or mirror extrapolation; edges / corners stay zero
+        self.adv_field = None
+        af = getattr(case, "advection_field", None)
+        if c.model == 0 and af is not None:
+            self.adv_field = self._local_adv_field(np.asarray(af, dtype=np.float64))
+            c.adv_field = _p(self.adv_field)
         if c.model in (2, 3):       # NavierStokes2D / 3D gravity field (identical to 1 without gravity, HB 1)
             lib().hpo_ns3d_gravity_field(C.byref(c), _p(self.grav_f), _p(self.grav_g))
         elif c.model == 1:          # Euler1D: one field (exp(0) = 1 without gravity)

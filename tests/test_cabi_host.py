@@ -63,6 +63,8 @@ ALL_CASES = [
     cases.ns2d_rising_bubble((24, 20), "z", hb=1, upwinding="roe"),
     cases.linear_advection_nd((24, 20), "js"),
     cases.burgers_nd((24, 20), "js"),
+    cases.linear_advection_varying((24, 20), "js"),                 # advection field from a file: periodic copies
+    cases.linear_advection_varying((12, 10, 14), "z", periodic=False),   # ... and mirrored at open faces
     cases.with_sponge(cases.ns_channel((24, 20), "js"), 0, 1, 0.7, 1.0, [1.0, 0.5, 0.0, 2.0]),    # interior sponge box
     cases.linear_advection_nd((12, 10, 14), "js", diffusion=[0.01, 0.0, 0.02]),
     cases.euler1d_sod(101, "js", gravity=1.0),                      # 1-D gravity field, mirrored at the physical faces
@@ -86,6 +88,8 @@ def test_host_setup_matches_oracle_setup(case):
             assert a == z["is"] and b == z["ie"]
     f, g = sv.gravity_field()
     assert np.array_equal(f, S.grav_f) and np.array_equal(g, S.grav_g)
+    if S.adv_field is not None:
+        assert np.array_equal(sv.advection_field(), S.adv_field)
     assert sv.neighbors == [-1] * (2 * S.ndims)
     assert sv.nstages == (4 if case.solver["time_scheme_type"] == "44" else 3)
     if case is ALL_CASES[0]:
@@ -129,6 +133,32 @@ def test_decomposed_setup_neighbors_and_remainders():
     sv = Solver.from_case(case, rank=0)
     assert sv.neighbors == [-1, 1, -1, 2, -1, -1]
     sv.close()
+
+
+def test_decomposed_advection_field_blocks():
+    """LinearADRAdvectionField.c:122-190 on every rank of a split domain: neighbours' interiors on internal faces, the
+    periodic copy only where one rank spans the dimension, the mirror image at the end ranks otherwise (sic: also in a
+    periodic dimension split among ranks), zero edges / corners."""
+    for n, iproc, per in (((26, 21), (2, 3), True), ((26, 21), (3, 1), True), ((13, 11, 14), (2, 1, 2), False),
+                          ((50,), (3,), True), ((50,), (2,), False)):
+        case = cases.linear_advection_varying(n, "js", iproc=iproc, periodic=per)
+        for r in range(int(np.prod(iproc))):
+            S = hpo.Setup(case, rank=r)
+            sv = Solver.from_case(case, rank=r)
+            a = sv.advection_field()
+            assert np.array_equal(a, S.adv_field), (n, iproc, per, r)
+            sv.close()
+    # the interior of every block is the file's field
+    case = cases.linear_advection_varying((26, 21), "js", iproc=(2, 3))
+    for r in range(6):
+        sv = Solver.from_case(case, rank=r)
+        a = sv.advection_field().reshape(sv.shape_g()[:-1] + (2,))
+        g = sv.ghosts
+        blk = a[g:-g, g:-g]
+        i0, j0 = sv.is_global
+        assert np.array_equal(blk, case.advection_field[j0:j0 + blk.shape[0], i0:i0 + blk.shape[1]])
+        assert not a[:g, :g].any() and not a[-g:, -g:].any()
+        sv.close()
 
 
 def test_decomposed_zone_extents_of_open_boundaries_and_sponges():

@@ -32,6 +32,9 @@ DECOMP += [
     cases.ns2d_rising_bubble((24, 28), "yc", iproc=(2, 2)),
     cases.ns2d_vortex((28, 24), "z", upwinding="roe", interp="characteristic", iproc=(2, 1)),
     cases.with_muscl(cases.linear_advection_nd((24, 21), "js", iproc=(3, 2)), "muscl3"),
+    # spatially varying advection field: every rank's block with the neighbours' values / mirror images in its ghosts
+    cases.linear_advection_varying((26, 21), "js", iproc=(2, 3)),
+    cases.linear_advection_varying((24, 20), "z", iproc=(2, 1), periodic=False),
 ]
 for c in DECOMP:
     c.name += "_iproc" + "x".join(str(v) for v in c.solver["iproc"])

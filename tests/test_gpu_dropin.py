@@ -56,6 +56,7 @@ CASES = [
     _prep(cases.with_sponge(cases.linear_advection_nd((28, 24), "js"), 0, -1, 0.0, 0.4, [0.5])),   # sponge zone
     _prep(cases.ns2d_vortex((32, 24), "mapped", upwinding="roe", interp="characteristic", scheme="crweno5")),   # char CRWENO5
     _prep(cases.burgers_nd((32, 24), "js")),                                                  # model burgers
+    _prep(cases.linear_advection_varying((32, 24), "js")),                                    # advection.inp through HyPar's reader
 ]
 
 

@@ -150,6 +150,13 @@ def _cases():
     C.append(cases.burgers_nd((14, 12, 16), "js"))
     C.append(cases.burgers_nd((24, 28), "yc", scheme="crweno5"))
     C.append(cases.with_muscl(cases.burgers_nd((80,), "js"), "muscl3"))
+    # LinearADR with a spatially varying advection field (sign changes: all three branches of LinearADRUpwind.c:56-82)
+    C.append(cases.linear_advection_varying((96,), "js"))
+    C.append(cases.linear_advection_varying((28, 24), "z"))
+    C.append(cases.linear_advection_varying((24, 28), "mapped", periodic=False))
+    C.append(cases.linear_advection_varying((14, 12, 16), "yc"))
+    C.append(cases.linear_advection_varying((24, 28), "js", scheme="crweno5"))
+    C.append(cases.linear_advection_varying((80,), "js", scheme="muscl3", periodic=False))
     return C
 
 
@@ -239,7 +246,8 @@ STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CA
               CASES[80], CASES[81], CASES[82], CASES[83], CASES[84], CASES[85], CASES[86], CASES[87],
               CASES[88], CASES[89], CASES[90], CASES[91], CASES[92], CASES[93], CASES[94], CASES[95], CASES[96], CASES[97],
               CASES[98], CASES[99], CASES[100], CASES[101], CASES[102], CASES[103],
-              CASES[104], CASES[105], CASES[106], CASES[107], CASES[108]]
+              CASES[104], CASES[105], CASES[106], CASES[107], CASES[108],
+              CASES[109], CASES[110], CASES[111], CASES[112], CASES[113], CASES[114]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)
@@ -298,7 +306,7 @@ def test_time_steps_parity(need_gpu, case):
 
 @pytest.mark.parametrize("case", [CASES[4], CASES[12], CASES[16], CASES[20], CASES[26],
                                   CASES[35], CASES[37], CASES[40], CASES[42], CASES[44], CASES[51], CASES[52], CASES[53],
-                                  CASES[56], CASES[58], CASES[60], CASES[65], CASES[69], CASES[72], CASES[74], CASES[76], CASES[79], CASES[82], CASES[85], CASES[87], CASES[98], CASES[100], CASES[102], CASES[104], CASES[105]],
+                                  CASES[56], CASES[58], CASES[60], CASES[65], CASES[69], CASES[72], CASES[74], CASES[76], CASES[79], CASES[82], CASES[85], CASES[87], CASES[98], CASES[100], CASES[102], CASES[104], CASES[105], CASES[109], CASES[110], CASES[111]],
                          ids=lambda c: c.name)
 def test_function_pointer_pieces(need_gpu, case):
     """FFunction, UFunction, SetInterpLimiterVar, InterpolateInterfacesHyp, Upwind,

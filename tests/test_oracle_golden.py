@@ -40,7 +40,7 @@ def same(a, b, what):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 39
+    assert len(GOLDEN) >= 41
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -207,6 +207,14 @@ def _live_cases():
         cases.burgers_nd((12, 10, 14), "js"),
         cases.burgers_nd((20, 24), "yc", scheme="crweno5"),
         cases.with_muscl(cases.burgers_nd((80,), "js"), "muscl3"),
+        # LinearADR with a spatially varying advection field read from a file (LinearADRAdvectionField.c, LinearADRUpwind.c:56-82)
+        cases.linear_advection_varying((96,), "js"),
+        cases.linear_advection_varying((80,), "mapped", periodic=False, tstype="ssprk3"),
+        cases.linear_advection_varying((24, 20), "z"),
+        cases.linear_advection_varying((20, 24), "js", periodic=False),
+        cases.linear_advection_varying((12, 10, 14), "yc"),
+        cases.linear_advection_varying((20, 24), "js", scheme="crweno5"),
+        cases.linear_advection_varying((64,), "js", scheme="muscl3"),
         # Euler1D with gravity (Euler1DGravityField.c, Euler1DSource.c)
         cases.euler1d_sod(101, "js", gravity=1.0),
         cases.euler1d_sod(101, "mapped", interp="components", upwinding="llf-char", gravity=1.0),

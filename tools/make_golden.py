@@ -67,6 +67,8 @@ GOLDEN = [
     ("c2_sod_crweno_js_char_roe", "euler1d_sod", dict(n=101, weno="js", scheme="crweno5"), "hypar_ref", True),
     ("c3_vortex_crweno_z_char_roe", "ns2d_vortex", dict(n=(20, 16), weno="z", upwinding="roe", interp="characteristic", scheme="crweno5"), "hypar_ref_mpi1", False),
     ("burgers2d_z", "burgers_nd", dict(n=(24, 20), weno="z"), "hypar_ref", True),
+    ("linadvvar2d_js", "linear_advection_varying", dict(n=(24, 20), weno="js"), "hypar_ref", True),
+    ("linadvvar1d_mapped_ext", "linear_advection_varying", dict(n=(80,), weno="mapped", periodic=False, tstype="ssprk3"), "hypar_ref_mpi1", True),
     ("c2_sod_upw5_comp_rusanov", "euler1d_sod", dict(n=101, weno="js", interp="components", upwinding="rusanov", scheme="upw5"), "hypar_ref", True),
 ]
 
