@@ -108,7 +108,7 @@ int hpb_setup_host(hpb_solver* h)
   int xo = 0;
   for (int d = 0; d < nd; d++) {
     G.N[d] = hpb_partition1d(c.dim_global[d], c.iproc[d], h->ip[d]);
-    if (G.N[d] < 2 * g) return hpb_fail(HPB_ERR_INVALID, "local size %d along dim %d is smaller than 2*ghosts", G.N[d], d);
+    if (G.N[d] < g) return hpb_fail(HPB_ERR_INVALID, "local size %d along dim %d is smaller than the number of ghost layers", G.N[d], d);   // quasi-1-D runs (size 3, ghost 3) are in the reference's Examples
     h->is_global[d] = (c.dim_global[d] / c.iproc[d]) * h->ip[d];
     G.P[d] = G.N[d] + 2 * g;
     G.xoff[d] = xo;

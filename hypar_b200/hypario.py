@@ -78,6 +78,10 @@ def read_keyword_file(path: str, ndims_hint: int | None = None,
         if key == "HB" and words[i] == "3":      # "HB 3 <N_bv>"
             out["HB"], out["N_bv"] = "3", words[i + 1]
             i += 2
+        elif key in ("input_mode", "output_mode") and words[i] != "serial":
+            # ReadInputs.c:358-366: "parallel" / "mpi-io" are followed by the number of I/O ranks
+            out[key], out["n_io_ranks"] = words[i], words[i + 1]
+            i += 2
         elif n is None:
             out[key] = words[i]
             i += 1
@@ -136,33 +140,46 @@ def write_boundary_inp(path: str, zones: Sequence[dict]) -> None:
 
 
 def read_boundary_inp(path: str, ndims: int, nvars: int) -> List[dict]:
+    """boundary.inp the way InitializeBoundaries.c:85-200 scans it: type, dim, face and the extents must be there; the
+    zone-specific values are read with unchecked fscanf("%lf") calls, so a value that is missing (the next token is the
+    next zone's type, or the file ends) stays 0 and consumes nothing -- the reference's own Examples rely on that
+    (NavierStokes2D/1DSodShockTubeWithGravity gives one wall velocity in 2-D, FlatPlateSupersonic no outflow pressure)."""
     with open(path) as f:
         w = f.read().split()
     n = int(w[0])
-    i = 1
+    pos = [1]
+
+    def lf() -> float:
+        if pos[0] < len(w):
+            try:
+                v = float(w[pos[0]])
+            except ValueError:
+                return 0.0
+            pos[0] += 1
+            return v
+        return 0.0
+
     zones = []
     for _ in range(n):
+        i = pos[0]
         z = {"type": w[i], "dim": int(w[i + 1]), "face": int(w[i + 2])}
         i += 3
         z["xmin"] = [float(w[i + 2 * d]) for d in range(ndims)]
         z["xmax"] = [float(w[i + 2 * d + 1]) for d in range(ndims)]
-        i += 2 * ndims
+        pos[0] = i + 2 * ndims
         if z["type"] in ("slip-wall", "noslip-wall"):
-            z["wall_velocity"] = [float(x) for x in w[i:i + ndims]]
-            i += ndims
+            z["wall_velocity"] = [lf() for _ in range(ndims)]
         elif z["type"] in ("dirichlet", "sponge"):
-            z["values"] = [float(x) for x in w[i:i + nvars]]
-            i += nvars
+            z["values"] = [lf() for _ in range(nvars)]
         elif z["type"] == "subsonic-inflow":
-            z["density"], z["velocity"] = float(w[i]), [float(x) for x in w[i + 1:i + 1 + ndims]]
-            i += 1 + ndims
+            z["density"] = lf()
+            z["velocity"] = [lf() for _ in range(ndims)]
         elif z["type"] == "subsonic-outflow":
-            z["pressure"] = float(w[i])
-            i += 1
+            z["pressure"] = lf()
         elif z["type"] in ("subsonic-ambivalent", "supersonic-inflow"):
-            z["density"], z["velocity"] = float(w[i]), [float(x) for x in w[i + 1:i + 1 + ndims]]
-            z["pressure"] = float(w[i + 1 + ndims])
-            i += 2 + ndims
+            z["density"] = lf()
+            z["velocity"] = [lf() for _ in range(ndims)]
+            z["pressure"] = lf()
         zones.append(z)
     return zones
 

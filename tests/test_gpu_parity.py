@@ -157,6 +157,16 @@ def _cases():
     C.append(cases.linear_advection_varying((14, 12, 16), "yc"))
     C.append(cases.linear_advection_varying((24, 28), "js", scheme="crweno5"))
     C.append(cases.linear_advection_varying((80,), "js", scheme="muscl3", periodic=False))
+    # quasi-1-D grids: 3 cells = the number of ghost layers along one dimension (Examples/2D/NavierStokes2D/1DHydrostaticBalance,
+    # 1DSodShockTubeWithGravity, 3D/NavierStokes3D/2D_RisingThermalBubble): ghosts filled from ghosts-wide interiors
+    C.append(cases.ns2d_vortex((32, 3), "js"))
+    C.append(cases.ns2d_rising_bubble((3, 28), "yc"))
+    C.append(cases.ns2d_rising_bubble((24, 3), "z", hb=1, upwinding="roe"))
+    C.append(cases.ns3d_rising_bubble((12, 16, 3), "mapped"))
+    C.append(cases.ns3d_turbulence((3, 14, 12), "js"))
+    C.append(cases.ns_channel((28, 3), "js"))
+    C.append(cases.ns2d_vortex((3, 24), "mapped", scheme="crweno5"))
+    C.append(cases.linear_advection_nd((3, 20), "js", diffusion=[0.01, 0.02]))
     return C
 
 
@@ -247,7 +257,8 @@ STEP_CASES = [CASES[0], CASES[7], CASES[15], CASES[19], CASES[25], CASES[26], CA
               CASES[88], CASES[89], CASES[90], CASES[91], CASES[92], CASES[93], CASES[94], CASES[95], CASES[96], CASES[97],
               CASES[98], CASES[99], CASES[100], CASES[101], CASES[102], CASES[103],
               CASES[104], CASES[105], CASES[106], CASES[107], CASES[108],
-              CASES[109], CASES[110], CASES[111], CASES[112], CASES[113], CASES[114]]
+              CASES[109], CASES[110], CASES[111], CASES[112], CASES[113], CASES[114],
+              CASES[115], CASES[116], CASES[117], CASES[118], CASES[119], CASES[120], CASES[121], CASES[122]]
 
 
 @pytest.mark.parametrize("case", STEP_CASES, ids=lambda c: c.name)
@@ -306,7 +317,7 @@ def test_time_steps_parity(need_gpu, case):
 
 @pytest.mark.parametrize("case", [CASES[4], CASES[12], CASES[16], CASES[20], CASES[26],
                                   CASES[35], CASES[37], CASES[40], CASES[42], CASES[44], CASES[51], CASES[52], CASES[53],
-                                  CASES[56], CASES[58], CASES[60], CASES[65], CASES[69], CASES[72], CASES[74], CASES[76], CASES[79], CASES[82], CASES[85], CASES[87], CASES[98], CASES[100], CASES[102], CASES[104], CASES[105], CASES[109], CASES[110], CASES[111]],
+                                  CASES[56], CASES[58], CASES[60], CASES[65], CASES[69], CASES[72], CASES[74], CASES[76], CASES[79], CASES[82], CASES[85], CASES[87], CASES[98], CASES[100], CASES[102], CASES[104], CASES[105], CASES[109], CASES[110], CASES[111], CASES[115], CASES[118]],
                          ids=lambda c: c.name)
 def test_function_pointer_pieces(need_gpu, case):
     """FFunction, UFunction, SetInterpLimiterVar, InterpolateInterfacesHyp, Upwind,

@@ -215,6 +215,12 @@ def _live_cases():
         cases.linear_advection_varying((12, 10, 14), "yc"),
         cases.linear_advection_varying((20, 24), "js", scheme="crweno5"),
         cases.linear_advection_varying((64,), "js", scheme="muscl3"),
+        # quasi-1-D grids (3 cells = ghosts along one dimension, as the reference's 1DHydrostaticBalance / 2D_RisingThermalBubble)
+        cases.ns2d_vortex((32, 3), "js"),
+        cases.ns2d_rising_bubble((3, 28), "yc"),
+        cases.ns3d_rising_bubble((12, 16, 3), "mapped"),
+        cases.ns3d_turbulence((3, 14, 12), "js"),
+        cases.ns_channel((28, 3), "js"),
         # Euler1D with gravity (Euler1DGravityField.c, Euler1DSource.c)
         cases.euler1d_sod(101, "js", gravity=1.0),
         cases.euler1d_sod(101, "mapped", interp="components", upwinding="llf-char", gravity=1.0),
