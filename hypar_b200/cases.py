@@ -57,9 +57,57 @@ class Case:
             hypario.write_keyword_file(os.path.join(d, "weno.inp"), self.weno)
         if self.muscl is not None:
             hypario.write_keyword_file(os.path.join(d, "muscl.inp"), self.muscl)
-        if self.advection_field is not None:           # same binary layout as initial.inp (ReadArray.c:225-256)
-            hypario.write_initial_bin(os.path.join(d, "advection.inp"), self.x, self.advection_field)
-        hypario.write_initial_bin(os.path.join(d, "initial.inp"), self.x, self.u0)
+        ipt = str(self.solver.get("ip_file_type", "binary"))
+        if self.advection_field is not None:           # same layout and flavour as initial.inp (ReadArray.c:173-256)
+            hypario.write_initial(os.path.join(d, "advection.inp"), self.x, self.advection_field, ipt)
+        hypario.write_initial(os.path.join(d, "initial.inp"), self.x, self.u0, ipt)
+
+
+def write_ensemble(d: str, sims: Sequence[Case]) -> None:
+    """A run directory of the reference's ensemble driver (simulation.inp + one solver.inp whose size / iproc hold one vector
+    per simulation, initial_<n>.inp, shared boundary / physics / weno files; InitialSolution.c:36-43)."""
+    os.makedirs(d, exist_ok=True)
+    nsims = len(sims)
+    width = len(str(nsims - 1)) if nsims > 1 else 1       # (int) log10(nsims) + 1 digits
+    s = dict(sims[0].solver)
+    s["size"] = [int(v) for c in sims for v in c.solver["size"]]
+    s["iproc"] = [int(v) for c in sims for v in c.solver.get("iproc", [1] * c.ndims)]
+    hypario.write_keyword_file(os.path.join(d, "simulation.inp"), {"nsims": nsims})
+    hypario.write_keyword_file(os.path.join(d, "solver.inp"), s)
+    hypario.write_boundary_inp(os.path.join(d, "boundary.inp"), sims[0].boundary)
+    hypario.write_keyword_file(os.path.join(d, "physics.inp"), sims[0].physics)
+    if sims[0].weno is not None:
+        hypario.write_keyword_file(os.path.join(d, "weno.inp"), sims[0].weno)
+    if sims[0].muscl is not None:
+        hypario.write_keyword_file(os.path.join(d, "muscl.inp"), sims[0].muscl)
+    ipt = str(s.get("ip_file_type", "binary"))
+    for n, c in enumerate(sims):
+        tag = f"_{n:0{width}d}" if nsims > 1 else ""
+        hypario.write_initial(os.path.join(d, f"initial{tag}.inp"), c.x, c.u0, ipt)
+        if c.advection_field is not None:
+            hypario.write_initial(os.path.join(d, f"advection{tag}.inp"), c.x, c.advection_field, ipt)
+
+
+def ensemble(name: str, n_iter: int = 4) -> List[Case]:
+    """Named ensembles (the reference's Examples/*_Ensemble and LaSDI/*/training_data): the same equations on several grids,
+    one time step for all -- simulation 0's (ReadInputs.c:321)."""
+    if name == "vortex3":
+        sims = [ns2d_vortex((32, 16), "js"), ns2d_vortex((16, 32), "js"), ns2d_vortex((24, 24), "js")]
+    elif name == "burgers2":
+        sims = [burgers_nd((96,), "mapped"), burgers_nd((64,), "mapped")]
+    elif name == "linadvvar2":
+        sims = [linear_advection_varying((24, 20), "z"), linear_advection_varying((16, 28), "z")]
+    elif name == "sod2":
+        sims = [euler1d_sod(101, "js"), euler1d_sod(81, "js")]
+    elif name == "turb12":                # 12 simulations: two-digit file indices
+        sims = [ns3d_turbulence((8 + (k % 3) * 2, 8, 8 + (k % 2) * 2), "mapped") for k in range(12)]
+    else:
+        raise KeyError(name)
+    for c in sims:
+        c.solver.update({"dt": sims[0].solver["dt"], "n_iter": n_iter, "screen_op_iter": 2, "file_op_iter": n_iter,
+                         "op_overwrite": "yes", "op_file_format": "binary"})
+        c.name = f"ens_{name}_" + c.name
+    return sims
 
 
 def _solver(ndims, nvars, size, model, *, iproc=None, ts="rk", tstype="44", dt=1e-3,

@@ -53,7 +53,7 @@ def _fmt(x) -> str:
 
 
 def read_keyword_file(path: str, ndims_hint: int | None = None,
-                      vector_keys: Dict[str, int] | None = None) -> Dict[str, object]:
+                      vector_keys: Dict[str, int] | None = None, nsims: int = 1) -> Dict[str, object]:
     """Parse a ``begin ... end`` file into {key: str | [str,...]}.
 
     ``vector_keys`` maps a key to the number of values that follow it
@@ -74,7 +74,7 @@ def read_keyword_file(path: str, ndims_hint: int | None = None,
             ndims_hint = int(words[i])
         n = vector_keys.get(key)
         if n is None and key in _VECTOR_KEYS and ndims_hint is not None:
-            n = ndims_hint
+            n = ndims_hint * nsims          # ensembles: one vector per simulation, in order (ReadInputs.c:186-250)
         if key == "HB" and words[i] == "3":      # "HB 3 <N_bv>"
             out["HB"], out["N_bv"] = "3", words[i + 1]
             i += 2
@@ -91,8 +91,35 @@ def read_keyword_file(path: str, ndims_hint: int | None = None,
     return out
 
 
-def read_solver_inp(path: str) -> Dict[str, object]:
+def read_simulation_inp(path: str) -> int:
+    """simulation.inp (src/main.cpp:181-240): ``nsims`` > 1 selects the ensemble driver. 1 when the file is absent."""
+    if not os.path.exists(path):
+        return 1
     raw = read_keyword_file(path)
+    return int(raw.get("nsims", 1))
+
+
+def read_ensemble_solver_inp(path: str, nsims: int) -> List[Dict[str, object]]:
+    """solver.inp of an ensemble run: ``size`` / ``iproc`` / ``size_exact`` hold one vector per simulation, everything else is
+    shared (ReadInputs.c:176-410 copies sim[0]'s value to the others)."""
+    raw = read_keyword_file(path, nsims=nsims)
+    nd = int(raw.get("ndims", 1))
+    out = []
+    for n in range(nsims):
+        one = dict(raw)
+        for k in _VECTOR_KEYS:
+            if k in raw:
+                one[k] = raw[k][n * nd:(n + 1) * nd]
+        cfg = _solver_cfg(one)
+        out.append(cfg)
+    return out
+
+
+def read_solver_inp(path: str) -> Dict[str, object]:
+    return _solver_cfg(read_keyword_file(path))
+
+
+def _solver_cfg(raw: Dict[str, object]) -> Dict[str, object]:
     ndims = int(raw.get("ndims", 1))
     cfg: Dict[str, object] = {
         # defaults of src/Simulation/ReadInputs.c:112-146
@@ -204,6 +231,48 @@ def read_initial_bin(path: str, dims: Sequence[int], nvars: int):
         off += d
     u = raw[off:off + n].reshape(tuple(reversed(list(dims))) + (nvars,)).copy()
     return x, u
+
+
+def write_initial_ascii(path: str, x: Sequence[np.ndarray], u: np.ndarray) -> None:
+    """The text flavour of initial.inp (``ip_file_type ascii``, ReadArray.c:173-217): the grid, dimension by dimension, then the
+    field ONE VARIABLE AFTER THE OTHER, each over the whole grid with dimension 0 fastest. Written with repr(): 17
+    significant digits, so the reference's fscanf("%lf") gets the same doubles back."""
+    nvars = u.shape[-1]
+    with open(path, "w") as f:
+        for xd in x:
+            f.write(" ".join(repr(float(v)) for v in np.asarray(xd, dtype=np.float64)) + "\n")
+        flat = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, nvars)
+        for v in range(nvars):
+            f.write(" ".join(repr(float(t)) for t in flat[:, v]) + "\n")
+
+
+def read_initial_ascii(path: str, dims: Sequence[int], nvars: int):
+    dims = [int(d) for d in dims]
+    sz, npts = int(np.sum(dims)), int(np.prod(dims))
+    with open(path) as f:
+        raw = np.array(f.read().split(), dtype=np.float64)
+    if raw.size < sz + npts * nvars:
+        raise ValueError(f"Error in ReadArraySerial(): unable to read data ({path}: {raw.size} values, "
+                         f"{sz + npts * nvars} expected)")
+    x, off = [], 0
+    for d in dims:
+        x.append(raw[off:off + d].copy())
+        off += d
+    u = np.ascontiguousarray(raw[off:off + npts * nvars].reshape(nvars, npts).T)
+    return x, u.reshape(tuple(reversed(dims)) + (nvars,))
+
+
+def read_initial(path: str, dims: Sequence[int], nvars: int, ip_file_type: str = "binary"):
+    """initial.inp (or any array file of that layout) in the flavour solver.inp names (ReadArray.c:173, :218)."""
+    if str(ip_file_type) == "ascii":
+        return read_initial_ascii(path, dims, nvars)
+    if str(ip_file_type) in ("bin", "binary"):
+        return read_initial_bin(path, dims, nvars)
+    raise ValueError(f"ip_file_type '{ip_file_type}' is neither ascii nor binary")
+
+
+def write_initial(path: str, x: Sequence[np.ndarray], u: np.ndarray, ip_file_type: str = "binary") -> None:
+    (write_initial_ascii if str(ip_file_type) == "ascii" else write_initial_bin)(path, x, u)
 
 
 def write_op_bin(path: str, x: Sequence[np.ndarray], u: np.ndarray) -> None:

@@ -212,16 +212,17 @@ class Solver:
                 ph[k] = [float(v) for v in ph[k]]
         wf = os.path.join(path, "weno.inp")
         w = hypario.read_keyword_file(wf) if os.path.exists(wf) else None
-        if str(s.get("ip_file_type", "ascii")) not in ("binary", "bin"):
-            raise HyParB200Error("only binary initial.inp is read by the B200 host layer")
-        x, u0 = hypario.read_initial_bin(os.path.join(path, "initial.inp"), s["size"], nv)
+        ipt = str(s.get("ip_file_type", "ascii"))
+        if ipt not in ("ascii", "binary", "bin"):
+            raise HyParB200Error(f"ip_file_type '{ipt}' is neither ascii nor binary")
+        x, u0 = hypario.read_initial(os.path.join(path, "initial.inp"), s["size"], nv, ipt)
         mf = os.path.join(path, "muscl.inp")
         mu = hypario.read_keyword_file(mf) if os.path.exists(mf) else None
         af = None
-        if str(ph.get("advection_filename", "none")) != "none":        # same binary layout as initial.inp (ReadArray.c)
+        if str(ph.get("advection_filename", "none")) != "none":        # same layout and flavour as initial.inp (ReadArray.c)
             fn = os.path.join(path, str(ph["advection_filename"]) + ".inp")
             if os.path.exists(fn):
-                af = hypario.read_initial_bin(fn, s["size"], nd * nv)[1]
+                af = hypario.read_initial(fn, s["size"], nd * nv, ipt)[1]
         obj = cls(s, b, ph, w, x, rank, device, use_fused, muscl=mu, advection_field=af)
         obj.u0_global = u0
         return obj

@@ -4,8 +4,9 @@
 
 Every directory's solver.inp / boundary.inp / physics.inp / weno.inp / muscl.inp are read with the package's own readers
 and handed to config_from_inputs + hpb_create (host set-up only, no device needed) on a coarsened grid -- the same
-accept / reject decisions a user's run would meet. Directories that need another driver of the reference (sparse grids,
-ensembles) or an immersed body are rejected here, since those inputs never reach the library. Prints one line per
+accept / reject decisions a user's run would meet. Ensemble directories (simulation.inp) are read the way
+hypar_b200.ensemble does. Directories that need the sparse-grids driver or an immersed body are rejected here, since those
+inputs never reach the library. Prints one line per
 directory and the totals by reason; DESIGN.md section 1 quotes the totals.
 """
 import collections
@@ -21,14 +22,14 @@ from hypar_b200.solver import MODELS, HyParB200Error, Solver  # noqa: E402
 
 
 def classify(d):
-    s = hypario.read_solver_inp(os.path.join(d, "solver.inp"))
+    nsims = hypario.read_simulation_inp(os.path.join(d, "simulation.inp"))
+    # ensembles: per-simulation size / iproc vectors; the simulations differ in size only, the first one decides
+    s = hypario.read_ensemble_solver_inp(os.path.join(d, "solver.inp"), nsims)[0]
     model = str(s.get("model", "none"))
     if model not in MODELS:
         return f"model {model}"
     if os.path.exists(os.path.join(d, "sparse_grids.inp")):
         return "sparse-grids driver"
-    if os.path.exists(os.path.join(d, "simulation.inp")):
-        return "ensemble driver"
     if str(s.get("immersed_body", "none")) != "none":
         return "immersed boundary"
     nd, nv = int(s["ndims"]), int(s["nvars"])
