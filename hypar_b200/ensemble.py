@@ -140,22 +140,12 @@ class Ensemble:
         return float(sum(s.dev_StepNormSumSq() for s in self.sims))
 
     # -- output in the reference's naming
-    def write_solutions(self, path: str, iteration: Optional[int] = None) -> List[str]:
-        """``op_<n>.bin`` (op_overwrite yes) or ``op_<n>_<iter>.bin`` with the whole local block of every simulation
-        (one rank per simulation), WriteBinary.c layout."""
-        names = []
+    def write_solutions(self, path: str, index: Optional[int] = None) -> List[str]:
+        """Every simulation's solution file in the reference's naming (OutputSolution.cpp:52-60: root ``op_<n>``), format and
+        ``op_overwrite`` from solver.inp; ``index`` overrides the running file index of ``op_overwrite no``."""
         nsims = len(self.sims)
+        names = []
         for n, s in enumerate(self.sims):
-            if any(p != 1 for p in s.iproc):
-                raise HyParB200Error("write_solutions gathers nothing: one rank per simulation (use write_solution_parallel)")
-            tag = "_" + index_string(n, nsims) if nsims > 1 else ""
-            name = f"op{tag}.bin" if iteration is None else f"op{tag}_{iteration:05d}.bin"
-            x, _ = s.grid()
-            g = s.ghosts
-            xs, off = [], 0
-            for d in range(s.ndims):
-                xs.append(x[off + g: off + g + s.dim_local[d]].copy())
-                off += s.dim_local[d] + 2 * g
-            hypario.write_op_bin(os.path.join(path, name), xs, s.interior(s.get_solution()))
-            names.append(name)
+            root = "op" + ("_" + index_string(n, nsims) if nsims > 1 else "")
+            names.append(s.write_solution(path, 0 if index is None else index, root))
         return names

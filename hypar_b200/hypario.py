@@ -288,6 +288,86 @@ def write_op_bin(path: str, x: Sequence[np.ndarray], u: np.ndarray) -> None:
         np.ascontiguousarray(u, dtype=np.float64).tofile(f)
 
 
+def _point_table(x: Sequence[np.ndarray], u: np.ndarray):
+    """Rows of WriteText.c:54-66: the ndims indices, the ndims coordinates, the nvars values; points with dimension 0 fastest."""
+    dims = [len(xd) for xd in x]
+    nd, nvars = len(dims), u.shape[-1]
+    grids = np.meshgrid(*[np.arange(n) for n in reversed(dims)], indexing="ij")      # axes: dim nd-1 ... dim 0
+    idx = [grids[nd - 1 - d].reshape(-1) for d in range(nd)]
+    cols = [i.astype(np.float64) for i in idx] + [np.asarray(x[d], dtype=np.float64)[idx[d]] for d in range(nd)]
+    tab = np.column_stack(cols + [np.ascontiguousarray(u, dtype=np.float64).reshape(-1, nvars)])
+    fmt = "%4d " * nd + "%+1.16E " * (nd + nvars)
+    return tab, fmt
+
+
+def write_op_text(path: str, x: Sequence[np.ndarray], u: np.ndarray) -> None:
+    """``op_file_format text`` (WriteText.c:27-69): one line per grid point -- indices ``%4d``, coordinates and values
+    ``%+1.16E``, each followed by a blank. Byte-identical to the reference's file for finite values."""
+    tab, fmt = _point_table(x, u)
+    with open(path, "w") as f:
+        np.savetxt(f, tab, fmt=fmt, newline="\n")
+
+
+def write_op_tecplot(path: str, x: Sequence[np.ndarray], u: np.ndarray) -> None:
+    """``op_file_format tecplot2d`` / ``tecplot3d`` (WriteTecplot2D.c:48-72, WriteTecplot3D.c:49-73): the text rows under a
+    Tecplot POINT-format header; variables are named "00", "01", ..."""
+    dims = [len(xd) for xd in x]
+    nd, nvars = len(dims), u.shape[-1]
+    if nd not in (2, 3):
+        raise ValueError(f"Error in WriteTecplot{nd}D(): hardcoded for 2- and 3-dimensional problems only")
+    tab, fmt = _point_table(x, u)
+    names = ["I", "J", "K"][:nd] + ["X", "Y", "Z"][:nd] + [f"{v // 10}{v % 10}" for v in range(nvars)]
+    with open(path, "w") as f:
+        f.write("VARIABLES=" + "".join(f'"{n}",' for n in names) + "\n")
+        f.write("ZONE " + ",".join(f"{a}={n}" for a, n in zip("IJK", dims)) + ",F=POINT\n")
+        np.savetxt(f, tab, fmt=fmt, newline="\n")
+
+
+def read_op_text(path: str, ndims: int, nvars: int):
+    """Back from a text / tecplot solution file: (x per dimension, u of shape (N_{nd-1}, ..., N_0, nvars))."""
+    rows = []
+    with open(path) as f:
+        for ln in f:
+            if ln.startswith(("VARIABLES", "ZONE")):
+                continue
+            rows.append(ln.split())
+    a = np.array(rows, dtype=np.float64)
+    idx = a[:, :ndims].astype(np.int64)
+    dims = [int(idx[:, d].max()) + 1 for d in range(ndims)]
+    x = []
+    for d in range(ndims):
+        xd = np.zeros(dims[d])
+        xd[idx[:, d]] = a[:, ndims + d]
+        x.append(xd)
+    return x, a[:, 2 * ndims:].reshape(tuple(reversed(dims)) + (nvars,))
+
+
+def solution_file_name(op_file_format: str, overwrite: bool, index: int = 0, root: str = "op", index_length: int = 5) -> str:
+    """``<root>[_<index>].<dat|bin>`` as OutputSolution.cpp:100-118 / InitializeSolvers.c:416-431 form it."""
+    fmt = str(op_file_format)
+    if fmt in ("binary", "bin"):
+        ext = ".bin"
+    elif fmt in ("text", "tecplot2d", "tecplot3d"):
+        ext = ".dat"
+    else:
+        raise ValueError(f"op_file_format '{fmt}' writes no file")
+    return root + ("" if overwrite else f"_{index:0{index_length}d}") + ext
+
+
+def write_solution(path: str, x: Sequence[np.ndarray], u: np.ndarray, op_file_format: str = "binary") -> None:
+    fmt = str(op_file_format)
+    if fmt in ("binary", "bin"):
+        write_op_bin(path, x, u)
+    elif fmt == "text":
+        write_op_text(path, x, u)
+    elif fmt in ("tecplot2d", "tecplot3d"):
+        if len(x) != int(fmt[7]):
+            raise ValueError(f"Error in WriteTecplot{fmt[7]}D(): hardcoded for {fmt[7]}-dimensional problems only")
+        write_op_tecplot(path, x, u)
+    else:
+        raise ValueError(f"op_file_format '{fmt}' writes no file")
+
+
 def read_op_bin(path: str):
     with open(path, "rb") as f:
         ndims, nvars = struct.unpack("2i", f.read(8))

@@ -386,6 +386,27 @@ class Solver:
         self._ck(self.L.hpb_dev_get_solution(self.h, _dp(u)))
         return u
 
+    def interior_grid(self) -> List[np.ndarray]:
+        """This rank's coordinates without ghosts, one array per dimension."""
+        x, _ = self.grid()
+        g, out, off = self.ghosts, [], 0
+        for d in range(self.ndims):
+            out.append(x[off + g: off + g + self.dim_local[d]].copy())
+            off += self.dim_local[d] + 2 * g
+        return out
+
+    def write_solution(self, directory: str, index: int = 0, root: str = "op") -> str:
+        """The device solution as the reference's OutputSolution would write it on one rank: ``op_file_format`` text /
+        tecplot2d / tecplot3d / binary and ``op_overwrite`` of solver.inp decide format and name (hypario.write_solution:
+        byte-identical to WriteText.c / WriteTecplot*.c / WriteBinary.c). Decomposed runs use write_solution_parallel."""
+        if any(p != 1 for p in self.iproc):
+            raise HyParB200Error("write_solution gathers nothing: one rank only (use write_solution_parallel)")
+        s = self.inputs["solver"]
+        fmt = str(s.get("op_file_format", "text"))
+        name = hypario.solution_file_name(fmt, str(s.get("op_overwrite", "no")) == "yes", index, root)
+        hypario.write_solution(os.path.join(directory, name), self.interior_grid(), self.interior(self.get_solution()), fmt)
+        return name
+
     def TimeStep(self) -> None:
         self._ck(self.L.hpb_TimeStep(self.h))
 

@@ -132,3 +132,69 @@ def test_solver_inp_io_modes_with_rank_count(tmp_path):
     s = hypario.read_solver_inp(os.path.join(d, "solver.inp"))
     assert s["input_mode"] == "parallel" and s["output_mode"] == "parallel" and int(s["n_io_ranks"]) == 4
     assert s["model"] == "navierstokes3d" and s["size"] == [8, 8, 8]
+
+
+# ---------------------------------------------------------------------------------------------------------------- output
+# the text and Tecplot solution files (WriteText.c, WriteTecplot2D.c, WriteTecplot3D.c) next to the binary one.
+def _ref_main(case, d):
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "hypar_ref_main")
+    if not os.access(exe, os.X_OK):
+        pytest.skip("oracle/_ref/hypar_ref_main not built (needs /root/reference)")
+    case.write(d)
+    p = subprocess.run([exe], cwd=d, capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS="1"), timeout=600)
+    assert p.returncode == 0 and "Finished." in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+def _fmt_case(case, fmt, overwrite):
+    case.solver.update({"n_iter": 2, "file_op_iter": 1, "screen_op_iter": 1, "op_file_format": fmt,
+                        "op_overwrite": "yes" if overwrite else "no"})
+    return case
+
+
+FORMATS = [
+    (cases.linear_advection_sine(48, "js"), "text", False),
+    (cases.euler1d_sod(61, "js"), "text", True),
+    (cases.ns2d_vortex((14, 12), "z"), "text", False),
+    (cases.ns2d_vortex((14, 12), "z"), "tecplot2d", False),
+    (cases.ns3d_density_wave((6, 8, 10), "js"), "tecplot3d", True),
+    (cases.ns3d_density_wave((6, 8, 10), "js"), "text", True),
+    (cases.ns3d_density_wave((6, 8, 10), "js"), "binary", False),
+]
+
+
+@pytest.mark.parametrize("case,fmt,overwrite", FORMATS, ids=[f"{c.name}-{f}-{'ow' if o else 'idx'}" for c, f, o in FORMATS])
+def test_solution_files_byte_identical_to_the_reference_writers(case, fmt, overwrite, tmp_path):
+    """The reference's own main writes op*.dat / op*.bin after 0, 1 and 2 steps; the oracle's solutions (bit-identical to the
+    reference's) through OUR writers give the same BYTES, under the same file names."""
+    import filecmp
+    case = _fmt_case(case, fmt, overwrite)
+    dref, dnew = str(tmp_path / "ref"), str(tmp_path / "new")
+    _ref_main(case, dref)
+    os.makedirs(dnew)
+    S = hpo.Setup(case, mpi_semantics=True)
+    O = hpo.Oracle(S)
+    u = S.local_u0()
+    names = []
+    for it in range(3):
+        if it:
+            O.time_step(u, float(case.solver["dt"]), hpo.rk_type_of(case))
+        nm = hypario.solution_file_name(fmt, overwrite, it)
+        hypario.write_solution(os.path.join(dnew, nm), case.x, S.interior(u), fmt)
+        names.append(nm)
+        if not overwrite or it == 2:
+            assert os.path.exists(os.path.join(dref, nm)), (nm, sorted(os.listdir(dref)))
+            assert filecmp.cmp(os.path.join(dref, nm), os.path.join(dnew, nm), shallow=False), f"{nm}: bytes differ"
+    assert len(set(names)) == (1 if overwrite else 3)
+    if fmt != "binary":
+        x, v = hypario.read_op_text(os.path.join(dnew, names[-1]), case.ndims, case.nvars)
+        assert np.array_equal(v, S.interior(u)) and all(np.array_equal(a, b) for a, b in zip(x, case.x))
+
+
+def test_tecplot_writers_are_dimension_specific(tmp_path):
+    c = cases.linear_advection_sine(16, "js")
+    with pytest.raises(ValueError, match="WriteTecplot2D"):
+        hypario.write_solution(str(tmp_path / "a.dat"), c.x, c.u0, "tecplot2d")
+    with pytest.raises(ValueError, match="writes no file"):
+        hypario.write_solution(str(tmp_path / "a.dat"), c.x, c.u0, "none")
