@@ -81,6 +81,12 @@ int hpb_setup_host(hpb_solver* h)
     return hpb_fail(HPB_ERR_INVALID, "navierstokes2d: gravity has two components");
   if (c.model == HPB_MODEL_LINEAR_ADR && c.par_scheme != 2 && c.par_scheme != 4)
     return hpb_fail(HPB_ERR_INVALID, "par_space_scheme %d not supported (2, 4)", c.par_scheme);
+  if (c.par_space_type < HPB_PAR_NC_1STAGE || c.par_space_type > HPB_PAR_CONS_1STAGE)
+    return hpb_fail(HPB_ERR_INVALID, "unknown par_space_type %d", c.par_space_type);
+  if (c.model == HPB_MODEL_LINEAR_ADR && c.par_space_type != HPB_PAR_NC_1STAGE)
+    for (int i = 0; i < nd * c.nvars; i++)
+      if (c.diffusion[i] != 0.0)       // LinearADR installs GFunction AND HFunction: every form is a different discretisation
+        return hpb_fail(HPB_ERR_INVALID, "LinearADR diffusion is on the B200 path as par_space_type nonconservative-1stage only");
   if (c.hyp_scheme < HPB_SCHEME_WENO5 || c.hyp_scheme > HPB_SCHEME_MUSCL3)
     return hpb_fail(HPB_ERR_INVALID, "hyp_space_scheme %d not supported (weno5, crweno5, cupw5, upw5, 1, 2, 4, muscl2, muscl3)",
                     c.hyp_scheme);

@@ -22,6 +22,7 @@ from . import _lib, hypario
 MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2d": 2, "navierstokes3d": 3, "burgers": 4}
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "dirichlet": 4, "subsonic-inflow": 5,
            "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9, "sponge": 10}
+PAR_TYPES = {"nonconservative-1stage": 0, "nonconservative-1.5stage": 1, "nonconservative-2stage": 2, "conservative-1stage": 3}
 UPWINDS = {"roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 RK_TYPES = {"44": 0, "ssprk3": 1, "tvdrk3": 1, "1fe": 2, "22": 3, "33": 4}
 SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6, "muscl2": 7, "muscl3": 8}
@@ -81,6 +82,10 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
         raise HyParB200Error(f"{it} is not a supported interpolation type")
     c.interp_char = int(it == "characteristic")
     c.par_scheme = int(solver.get("par_space_scheme", "2"))
+    pst = str(solver.get("par_space_type", "nonconservative-1stage"))
+    if pst not in PAR_TYPES:          # InitializeSolvers.c:177-181
+        raise HyParB200Error(f"{pst} is not a supported spatial discretization type for the parabolic terms")
+    c.par_space_type = PAR_TYPES[pst]
     c.dt = float(solver.get("dt", 0.0))
     w = weno or {}
     c.weno_type = 3 if int(w.get("yc", 0)) else 2 if int(w.get("borges", 0)) else 1 if int(w.get("mapped", 0)) else 0

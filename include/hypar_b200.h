@@ -105,6 +105,12 @@ extern "C" {
 #define HPB_RK_22     3
 #define HPB_RK_33     4
 
+/* par_space_type -- reference InitializeSolvers.c:107-176 (the form of the parabolic term) */
+#define HPB_PAR_NC_1STAGE   0   /* "nonconservative-1stage" (default, ReadInputs.c:134): ParabolicFunctionNC1Stage  */
+#define HPB_PAR_NC_1_5STAGE 1   /* "nonconservative-1.5stage"                                                        */
+#define HPB_PAR_NC_2STAGE   2   /* "nonconservative-2stage": what the Navier-Stokes models need                      */
+#define HPB_PAR_CONS_1STAGE 3   /* "conservative-1stage"                                                             */
+
 /* fields that have a halo exchange (reference MPIExchangeBoundariesnD call sites) */
 #define HPB_FIELD_U       0   /* TimeRHSFunctionExplicit.c:60, TimePreStep.c:71         */
 #define HPB_FIELD_QDERIVX 1   /* NavierStokes3DParabolicFunction.c:125                  */
@@ -166,6 +172,9 @@ typedef struct hpb_config {
                                           advection field on the GLOBAL grid, [point][ndims*nvars], points ordered like the
                                           solution in initial.inp (no ghosts); NULL = constant advection[]. Copied by
                                           hpb_create.                                                          */
+  int    par_space_type;               /* HPB_PAR_*: LinearADR with a non-zero diffusion coefficient is on the device only
+                                          as nonconservative-1stage -- the other forms are different arithmetic
+                                          (ParabolicFunctionNC2Stage.c / NC1_5Stage / Cons1Stage) and fail in hpb_create */
 } hpb_config;
 
 typedef struct hpb_solver hpb_solver;

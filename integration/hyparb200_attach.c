@@ -217,6 +217,8 @@ int hyparb200_attach(void *sims, int nsims)
   else if (!strcmp(s->time_scheme_type, _RK_33_))     c.rk_type = HPB_RK_33;
   else { fprintf(stderr, "hyparb200_attach: rk type %s is not on the B200 path (44, ssprk3)\n", s->time_scheme_type); return 1; }
   c.par_scheme = atoi(s->spatial_scheme_par);
+  c.par_space_type = !strcmp(s->spatial_type_par, _NC_1STAGE_) ? HPB_PAR_NC_1STAGE : !strcmp(s->spatial_type_par, _NC_1_5STAGE_) ? HPB_PAR_NC_1_5STAGE
+                   : !strcmp(s->spatial_type_par, _NC_2STAGE_) ? HPB_PAR_NC_2STAGE : HPB_PAR_CONS_1STAGE;
   c.conservation_check = !strcmp(s->ConservationCheck, "yes");
   c.hyp_scheme = scheme;
   if (scheme == HPB_SCHEME_MUSCL2 || scheme == HPB_SCHEME_MUSCL3) {

@@ -355,6 +355,9 @@ class Setup:
         for i, a in enumerate(adv):
             c.adv[i] = float(a)
         dif = ph.get("diffusion", [])
+        if c.model == 0 and str(s.get("par_space_type", "nonconservative-1stage")) != "nonconservative-1stage" and \
+                any(float(v) != 0.0 for v in (dif if isinstance(dif, (list, tuple)) else [dif])):
+            raise NotImplementedError("oracle: LinearADR diffusion is restated as ParabolicFunctionNC1Stage only")
         dif = list(dif) if isinstance(dif, (list, tuple)) else [dif]
         for i, a in enumerate(dif):
             c.diff[i] = float(a)

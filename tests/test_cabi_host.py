@@ -199,6 +199,24 @@ def test_unsupported_configurations_fail_loudly(mutate, msg):
     _lib.load().hpb_clear_error()
 
 
+@pytest.mark.parametrize("pst", ["nonconservative-2stage", "nonconservative-1.5stage", "conservative-1stage"])
+def test_linear_diffusion_in_another_form_fails_loudly(pst):
+    """LinearADR installs GFunction and HFunction (LinearADRInitialize.c:190-191), so every par_space_type is a different
+    discretisation of the diffusion term (InitializeSolvers.c:107-176); the device has nonconservative-1stage. Without
+    diffusion every form is identically zero and is accepted."""
+    case = cases.linear_advection_sine(64, "js", diffusion=0.02)
+    case.solver["par_space_type"] = pst
+    with pytest.raises(HyParB200Error, match="nonconservative-1stage only"):
+        Solver.from_case(case)
+    _lib.load().hpb_clear_error()
+    case = cases.linear_advection_sine(64, "js")
+    case.solver["par_space_type"] = pst
+    Solver.from_case(case).close()
+    case.solver["par_space_type"] = "conservative-2stage"
+    with pytest.raises(HyParB200Error, match="not a supported spatial discretization type"):
+        Solver.from_case(case)
+
+
 @pytest.mark.parametrize("scheme", ["crweno5", "cupw5", "upw5", "1", "2", "4", "muscl2", "muscl3"])
 def test_compact_and_linear_schemes_are_accepted(scheme):
     """crweno5 / cupw5 (one rank per line) and upw5 (any decomposition) set up like weno5"""
