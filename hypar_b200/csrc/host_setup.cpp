@@ -81,6 +81,10 @@ int hpb_setup_host(hpb_solver* h)
     return hpb_fail(HPB_ERR_INVALID, "navierstokes2d: gravity has two components");
   if (c.model == HPB_MODEL_LINEAR_ADR && c.par_scheme != 2 && c.par_scheme != 4)
     return hpb_fail(HPB_ERR_INVALID, "par_space_scheme %d not supported (2, 4)", c.par_scheme);
+  if ((c.model == HPB_MODEL_NS2D || c.model == HPB_MODEL_NS3D) && c.Re > 0 && c.par_scheme != 4)
+    // InitializeSolvers.c:128-141: par_space_scheme 2 makes FirstDerivativePar the FIRST-order difference; the device's viscous
+    // kernels are FirstDerivativeFourthOrderCentral
+    return hpb_fail(HPB_ERR_INVALID, "viscous terms are on the B200 path with par_space_scheme 4 only (got %d)", c.par_scheme);
   if (c.par_space_type < HPB_PAR_NC_1STAGE || c.par_space_type > HPB_PAR_CONS_1STAGE)
     return hpb_fail(HPB_ERR_INVALID, "unknown par_space_type %d", c.par_space_type);
   if (c.model == HPB_MODEL_LINEAR_ADR && c.par_space_type != HPB_PAR_NC_1STAGE)

@@ -75,6 +75,8 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     if tst not in RK_TYPES:
         raise HyParB200Error(f"time_scheme_type '{tst}' is not on the B200 path (1fe, 22, 33, 44, ssprk3, tvdrk3)")
     c.rk_type = RK_TYPES[tst]
+    if str(solver.get("immersed_body", "none")) != "none":
+        raise HyParB200Error("immersed bodies are not on the B200 path")
     if str(solver.get("hyp_flux_split", "no")) != "no":
         raise HyParB200Error("hyp_flux_split yes is not on the B200 path")
     it = str(solver.get("hyp_interp_type", "characteristic"))

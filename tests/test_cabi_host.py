@@ -189,6 +189,8 @@ def test_decomposed_zone_extents_of_open_boundaries_and_sponges():
     (lambda c: c.boundary[0].__setitem__("type", "thermal-slip-wall"), "boundary type"),
     (lambda c: c.physics.__setitem__("upwinding", "steger-warming"), "upwinding"),
     (lambda c: c.solver.__setitem__("par_space_type", "conservative-1stage"), "nonconservative-2stage"),
+    (lambda c: c.solver.__setitem__("par_space_scheme", "2"), "par_space_scheme 4 only"),
+    (lambda c: c.solver.__setitem__("immersed_body", "sphere.stl"), "immersed"),
 ])
 def test_unsupported_configurations_fail_loudly(mutate, msg):
     case = cases.ns3d_turbulence((12, 12, 12), "js")
