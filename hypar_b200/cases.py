@@ -63,6 +63,32 @@ class Case:
         hypario.write_initial(os.path.join(d, "initial.inp"), self.x, self.u0, ipt)
 
 
+def from_directory(path: str) -> Case:
+    """An existing HyPar run directory (solver.inp, boundary.inp, [physics.inp], [weno.inp], [muscl.inp], initial.inp in the
+    flavour solver.inp names, [<advection_filename>.inp]) as a Case -- the same reading Solver.from_directory does."""
+    s = hypario.read_solver_inp(os.path.join(path, "solver.inp"))
+    nd, nv = int(s["ndims"]), int(s["nvars"])
+    b = hypario.read_boundary_inp(os.path.join(path, "boundary.inp"), nd, nv)
+    vk = {"gravity": 3 if s["model"] == "navierstokes3d" else 2 if s["model"] == "navierstokes2d" else 1,
+          "advection": nd * nv, "diffusion": nd * nv}
+    pf = os.path.join(path, "physics.inp")
+    ph = hypario.read_keyword_file(pf, vector_keys=vk) if os.path.exists(pf) else {}
+    for k in ("advection", "diffusion", "gravity"):
+        if k in ph:
+            ph[k] = [float(v) for v in (ph[k] if isinstance(ph[k], (list, tuple)) else [ph[k]])]
+    wf, mf = os.path.join(path, "weno.inp"), os.path.join(path, "muscl.inp")
+    w = hypario.read_keyword_file(wf) if os.path.exists(wf) else None
+    mu = hypario.read_keyword_file(mf) if os.path.exists(mf) else None
+    ipt = str(s.get("ip_file_type", "ascii"))
+    x, u0 = hypario.read_initial(os.path.join(path, "initial.inp"), s["size"], nv, ipt)
+    case = Case(name=os.path.basename(os.path.normpath(path)), solver=s, boundary=b, physics=ph, weno=w, x=x, u0=u0, muscl=mu)
+    if str(ph.get("advection_filename", "none")) != "none":
+        fn = os.path.join(path, str(ph["advection_filename"]) + ".inp")
+        if os.path.exists(fn):
+            case.advection_field = hypario.read_initial(fn, s["size"], nd * nv, ipt)[1]
+    return case
+
+
 def write_ensemble(d: str, sims: Sequence[Case]) -> None:
     """A run directory of the reference's ensemble driver (simulation.inp + one solver.inp whose size / iproc hold one vector
     per simulation, initial_<n>.inp, shared boundary / physics / weno files; InitialSolution.c:36-43)."""
