@@ -1492,13 +1492,16 @@ void apply_bc(hpb_solver* h, double* u)
 {
   ProfScope ps(h, HPB_PROF_BC);
   const Geom& G = h->geo;
+  // Euler1DInitialize.c never sets boundary[n].gamma (NavierStokes2D/3DInitialize.c do): the reference's 1-D branches of the
+  // boundary functions run with the calloc-ed 0, i.e. energy_gpt = -(-(e - K)) + K
+  const double bc_gamma = (h->cfg.model == HPB_MODEL_EULER1D) ? 0.0 : h->phys.gamma;
   for (const ZoneDev& z : h->zones) {
     if (!z.on) continue;
     if (z.type == HPB_BC_PERIODIC && h->cfg.iproc[z.dim] != 1) continue;
     if (z.type == HPB_BC_SPONGE) continue;                     // BCSpongeUDummy: a source term, no ghost fill
     const int b0 = z.ie[0] - z.is[0], b1 = (G.ndims > 1 ? z.ie[1] - z.is[1] : 1), b2 = (G.ndims > 2 ? z.ie[2] - z.is[2] : 1);
     if (b0 <= 0 || b1 <= 0 || b2 <= 0) continue;
-    k_bc_zone<<<(unsigned)(((long long)b0 * b1 * b2 + TPB - 1) / TPB), TPB, 0, h->stream>>>(G, z, h->phys.gamma, u); LAUNCHED(h);
+    k_bc_zone<<<(unsigned)(((long long)b0 * b1 * b2 + TPB - 1) / TPB), TPB, 0, h->stream>>>(G, z, bc_gamma, u); LAUNCHED(h);
   }
 }
 
