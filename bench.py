@@ -230,10 +230,113 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+STRONG_IPROC = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}   # configs[3]: 512^3 over 1/2/4/8 GPUs
+
+
+def workload_inputs(workload, size, iproc):
+    if workload == "c4":
+        s, b, ph, w, x = c4_inputs(size, iproc)
+        return s, b, ph, w, x, "C4 NavierStokes3D WENO5(mapped)+Rusanov+viscous RK4", "periodic"
+    s, b, ph, w, x = c5_inputs(workload, size, iproc)
+    label = ("C5a NavierStokes3D density sine wave, WENO5(JS)+Rusanov, inviscid, RK4" if workload == "c5a" else
+             "C5b NavierStokes3D rising thermal bubble, WENO5(YC)+Rusanov, gravity (HB 2) source, SSPRK3")
+    return s, b, ph, w, x, label, ("periodic" if workload == "c5a" else "slip walls")
+
+
+class Run:
+    """one workload on this rank's GPU: solver (+ NCCL transport when decomposed), synthetic field, device-timed steps"""
+
+    def __init__(self, workload, size, iproc, rank, local_rank, world, overlap=True):
+        import torch
+        from hypar_b200.solver import Solver
+        self.torch, self.world, self.rank = torch, world, rank
+        self.dev = torch.device("cuda", local_rank)
+        self.size, self.iproc, self.workload = list(size), list(iproc), workload
+        s, b, ph, w, x, self.label, self.bc = workload_inputs(workload, size, iproc)
+        if world == 1:
+            self.sv, self.stepper = Solver(s, b, ph, w, x, rank=0, device=local_rank), None
+        else:
+            from hypar_b200.multigpu import DistributedSolver
+            self.stepper = DistributedSolver(s, b, ph, w, x, rank=rank, device=local_rank, overlap=overlap)
+            self.sv = self.stepper.solver
+        sv = self.sv
+        self.g, self.nloc = sv.ghosts, sv.dim_local
+        x_loc = [x[d][sv.is_global[d]:sv.is_global[d] + self.nloc[d]] for d in range(3)]
+        # synthetic input, created on the device, staged into a pinned host array in HyPar's own layout
+        self.u_host_t = torch.zeros(sv.npoints_local_wghosts * 5, dtype=torch.float64).pin_memory()
+        self.u_host = self.u_host_t.numpy()
+        fld = synth_field_torch(x_loc, self.dev) if workload == "c4" else synth_field_c5(workload, x_loc, self.dev)
+        g, n = self.g, self.nloc
+        self.u_host_t.view(n[2] + 2 * g, n[1] + 2 * g, n[0] + 2 * g, 5)[g:-g, g:-g, g:-g, :].copy_(fld)
+        del fld
+        torch.cuda.empty_cache()
+        sv.set_solution(self.u_host)
+        self.stream = torch.cuda.ExternalStream(sv.stream, device=self.dev)
+        self.npts_global = float(size[0]) * size[1] * size[2]
+        self.nstages = sv.nstages
+
+    def barrier(self):
+        torch = self.torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(self):
+        if self.stepper is None:
+            self.sv.TimeStep()
+        else:
+            self.stepper.time_step()
+
+    def timed(self, fn, nsteps):
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(nsteps):
+            fn()
+        e1.record(self.stream)
+        self.sv.synchronize()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def device_loop(self, steps, warmup):
+        """W untimed + K timed device-resident steps; returns (ms total, Mpoint-RK-stage/s, CFL afterwards)"""
+        import numpy as np
+        for _ in range(warmup):
+            self.one_step()
+        self.sv.synchronize()
+        ms = self.timed(self.one_step, steps)
+        cfl = self.sv.dev_ComputeCFL()
+        if not np.isfinite(cfl) or cfl <= 0 or cfl > 10:
+            raise RuntimeError(f"solution blew up during the bench of {self.workload} (CFL = {cfl})")
+        return ms, self.npts_global * self.nstages * steps / (ms * 1e-3) / 1e6, cfl
+
+    def close(self):
+        self.sv.close()
+        del self.u_host, self.u_host_t
+        self.torch.cuda.empty_cache()
+
+
+def sub_record(workload, size, iproc, rank, local_rank, world, steps, warmup, overlap):
+    """a second workload measured in the same process after the main one (device-resident loop only)"""
+    R = Run(workload, size, iproc, rank, local_rank, world, overlap=overlap)
+    ms, val, cfl = R.device_loop(steps, warmup)
+    rec = {"workload": f"{R.label}, {size[0]}x{size[1]}x{size[2]} {R.bc}", "iproc": list(iproc),
+           "points_per_gpu": "x".join(str(v) for v in R.nloc), "value": val, "unit": UNIT, "ms_per_step": ms / steps,
+           "steps": steps, "warmup": warmup, "rk_stages_per_step": R.nstages, "cfl": cfl}
+    R.close()
+    return rec
+
+
 def gpu_arm(args):
     import numpy as np
     import torch
-    from hypar_b200.solver import Solver
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -252,67 +355,15 @@ def gpu_arm(args):
     from hypar_b200.multigpu import bind_to_gpu_numa
     numa_cpus = bind_to_gpu_numa(local_rank) if not args.no_numa_bind else None
 
+    overlap = not args.serial_halo
     size, iproc = weak_grid(args.n, world)
-    if args.workload == "c4":
-        s, b, ph, w, x = c4_inputs(size, iproc)
-        wl_label = "C4 NavierStokes3D WENO5(mapped)+Rusanov+viscous RK4"
-        wl_bc = "periodic"
-    else:
-        s, b, ph, w, x = c5_inputs(args.workload, size, iproc)
-        wl_label = ("C5a NavierStokes3D density sine wave, WENO5(JS)+Rusanov, inviscid, RK4" if args.workload == "c5a" else
-                    "C5b NavierStokes3D rising thermal bubble, WENO5(YC)+Rusanov, gravity (HB 2) source, SSPRK3")
-        wl_bc = "periodic" if args.workload == "c5a" else "slip walls"
-    if world == 1:
-        sv = Solver(s, b, ph, w, x, rank=0, device=local_rank)
-        stepper = None
-    else:
-        from hypar_b200.multigpu import DistributedSolver
-        stepper = DistributedSolver(s, b, ph, w, x, rank=rank, device=local_rank, overlap=args.overlap)
-        sv = stepper.solver
-    g = sv.ghosts
-    nloc = sv.dim_local
-    x_loc = [x[d][sv.is_global[d]:sv.is_global[d] + nloc[d]] for d in range(3)]
-
-    # synthetic input, created on the device, staged into a pinned host array in HyPar's own layout
-    u_host_t = torch.zeros(sv.npoints_local_wghosts * 5, dtype=torch.float64).pin_memory()
-    u_host = u_host_t.numpy()
-    fld = synth_field_torch(x_loc, dev) if args.workload == "c4" else synth_field_c5(args.workload, x_loc, dev)
-    u_host_t.view(nloc[2] + 2 * g, nloc[1] + 2 * g, nloc[0] + 2 * g, 5)[g:-g, g:-g, g:-g, :].copy_(fld)
-    del fld
-    torch.cuda.empty_cache()
-    sv.set_solution(u_host)
-
-    stream = torch.cuda.ExternalStream(sv.stream, device=dev)
-    npts_global = float(size[0]) * size[1] * size[2]
-    nstages = sv.nstages
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def one_step():
-        if stepper is None:
-            sv.TimeStep()
-        else:
-            stepper.time_step()
-
-    def timed(fn, nsteps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(nsteps):
-            fn()
-        e1.record(stream)
-        sv.synchronize()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+    R = Run(args.workload, size, iproc, rank, local_rank, world, overlap=overlap)
+    sv, stepper = R.sv, R.stepper
+    wl_label, wl_bc = R.label, R.bc
+    g, nloc = R.g, R.nloc
+    u_host_t, u_host = R.u_host_t, R.u_host
+    stream, npts_global, nstages = R.stream, R.npts_global, R.nstages
+    barrier, one_step, timed = R.barrier, R.one_step, R.timed
 
     # ---- device-resident loop
     for _ in range(args.warmup):
@@ -402,10 +453,33 @@ def gpu_arm(args):
         if not np.isfinite(u_out).all():
             raise RuntimeError("non-finite values in the host solution after the pipelined end-to-end steps")
 
-        if rank != 0:
-            if dist is not None:
-                dist.destroy_process_group()
-            return
+    # ---- sub-records (device-resident loop only), measured by all ranks after the main workload has released its memory:
+    #   strong : configs[3] as BASELINE.json states it -- C4 at 512^3 GLOBAL, split over the N GPUs like HyPar would
+    #            (iproc (1,1,2) / (1,2,2) / (2,2,2), Initialize.c:66-98, MPIPartition1D.c) -- with its efficiency against
+    #            the 1-GPU rate of this run's per-GPU block size
+    #   c5b    : configs[4] -- rising thermal bubble with the gravity source, WENO5-YC, SSPRK3, 512^3 per GPU (1024^3 at 8)
+    tma_launches = sv.tma_launches
+    comm_msgs, comm_bytes = sv.comm_stats() if stepper is not None else (0, 0)
+    sub = {}
+    if not args.no_sub and args.workload == "c4":
+        R.close()
+        del u_host_t, u_host
+        if not args.no_e2e:
+            del u_in_t, u_in, u_out
+        torch.cuda.empty_cache()
+        if world > 1:
+            sub["strong"] = sub_record("c4", [args.n] * 3, STRONG_IPROC[world], rank, local_rank, world,
+                                       max(args.steps, 10), args.warmup, overlap)
+            sub["strong"]["scaling"] = "strong"
+            sub["strong"]["note"] = (f"{args.n}^3 global on {world} GPUs; compare value with the N=1 line's (same global grid): "
+                                     "strong-scaling efficiency = value / (N x value at N=1)")
+        sub["c5b"] = sub_record("c5b", size, iproc, rank, local_rank, world, args.steps, args.warmup, overlap)
+        sub["c5b"]["scaling"] = "weak"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     # ---- roofline of the dominant kernel (per-launch CUDA-event time, this rank)
     peaks = {}
@@ -425,7 +499,7 @@ def gpu_arm(args):
     traffic, fp64_pct, ncu_src = None, None, None
     try:
         prof_ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_sweep_512.json")))
-        if tuple(nloc) == (512, 512, 512) and dom in prof_ncu and sv.tma_launches > 0:
+        if tuple(nloc) == (512, 512, 512) and dom in prof_ncu and tma_launches > 0:
             traffic = float(prof_ncu[dom]["dram_bytes_read"] + prof_ncu[dom]["dram_bytes_write"]) / 1e9
             fp64_pct = prof_ncu[dom]["fp64_pipe_active_pct"]
             ncu_src = "profiles/ncu_sweep_512.json"
@@ -464,8 +538,10 @@ def gpu_arm(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{wl_label}, {size[0]}x{size[1]}x{size[2]} {wl_bc}",
                    "points_per_gpu": f"{nloc[0]}x{nloc[1]}x{nloc[2]}", "iproc": iproc, "rk_stages_per_step": nstages,
-                   "halo": (None if stepper is None else ("NCCL send/recv on a communication stream, overlapped with the "
-                            "Q-derivative kernel and the sweeps" if stepper.overlap else "NCCL send/recv, serial")),
+                   "halo": (None if stepper is None else (
+                       "in-library ncclSend/ncclRecv on a communication stream, overlapped: u faces under the full-array RK "
+                       "update, Q-derivative faces of dims 1.. under the x-sweep (hpb_TimeStepsDistributed, no Python in the step)"
+                       if stepper.overlap else "in-library ncclSend/ncclRecv, serial (hpb_TimeStepsDistributed)")),
                    "l2": "working set (5.6 GB per array) >> L2, no flush needed",
                    "host_numa_bind": (f"{len(numa_cpus)} GPU-local CPUs" if numa_cpus else "none")},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
@@ -478,6 +554,8 @@ def gpu_arm(args):
                                 if stepper is None else "DistributedSolver.time_integrate_host, blocking"}},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "cfl": cfl,
+        "halo_traffic": (None if stepper is None else {"messages_sent_rank0": comm_msgs, "bytes_sent_rank0": comm_bytes}),
+        "strong": sub.get("strong"), "c5b": sub.get("c5b"),
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -499,8 +577,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end legs (profiler runs of the device loop only)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA-local CPUs")
-    ap.add_argument("--overlap", action="store_true", help="multi-GPU: halo exchange on a communication stream, overlapped "
-                    "with the derivative kernel / sweeps (measured slower than the serial schedule on NVLink 5: DESIGN.md)")
+    ap.add_argument("--serial-halo", action="store_true", help="multi-GPU: pack - exchange - unpack in sequence instead of "
+                    "the overlapped schedule (hpb_set_overlap 0); same results bit for bit")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (C4 512^3 strong scaling at N > 1, C5b)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -56,9 +56,11 @@ SYMBOLS = [
     "hpb_ComputeCFL", "hpb_TimeIntegrate", "hpb_pipe_upload", "hpb_pipe_download", "hpb_pipe_join", "hpb_pipe_wait", "hpb_TimeIntegrateAsync",
     "hpb_dev_set_solution", "hpb_dev_get_solution", "hpb_dev_fill_solution_from_global", "hpb_TimeStep",
     "hpb_TimeSteps", "hpb_current_time", "hpb_dev_ComputeCFL", "hpb_dev_StepNormSumSq", "hpb_dev_RHS",
-    "hpb_halo_buffers", "hpb_step_begin", "hpb_step_halo_done", "hpb_stage_begin", "hpb_stage_halo_done",
-    "hpb_stage_rhs_a", "hpb_stage_rhs_b", "hpb_step_finish", "hpb_stage_overlap_supported", "hpb_stage_interior",
-    "hpb_stage_halo_done_dim", "hpb_stage_sweep", "hpb_dev_get_stage_rhs", "hpb_nstages", "hpb_needs_viscous_exchange",
+    "hpb_comm_get_unique_id", "hpb_comm_nccl_version", "hpb_comm_init_nccl", "hpb_comm_init_local", "hpb_comm_finalize",
+    "hpb_comm_kind", "hpb_comm_allreduce", "hpb_comm_stats", "hpb_exchange_plan", "hpb_ExchangeBoundariesnD",
+    "hpb_TimeStepDistributed", "hpb_TimeStepsDistributed", "hpb_RHSFunctionDistributed", "hpb_TimeStepsLocal",
+    "hpb_RHSFunctionLocal", "hpb_set_overlap", "hpb_stage_overlap_supported",
+    "hpb_dev_get_stage_rhs", "hpb_nstages", "hpb_needs_viscous_exchange",
     "hpb_dev_VolumeIntegral", "hpb_dev_StageBoundaryIntegral", "hpb_dev_StepBoundaryIntegral", "hpb_BoundaryIntegral",
     "hpb_CalculateConservationError", "hpb_dev_ErrorSums",
     "hpb_stream", "hpb_synchronize", "hpb_kernel_launch_count", "hpb_tma_launch_count", "hpb_profile_enable", "hpb_profile_query",
@@ -130,15 +132,20 @@ def load():
     L.hpb_dev_ComputeCFL.argtypes = [vp, dp]
     L.hpb_dev_StepNormSumSq.argtypes = [vp, dp]
     L.hpb_dev_RHS.argtypes = [vp, C.c_double, dp]
-    L.hpb_halo_buffers.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
-    for name in ("hpb_step_begin", "hpb_step_halo_done", "hpb_step_finish", "hpb_nstages",
-                 "hpb_needs_viscous_exchange", "hpb_synchronize"):
+    for name in ("hpb_nstages", "hpb_needs_viscous_exchange", "hpb_synchronize", "hpb_comm_finalize", "hpb_comm_kind",
+                 "hpb_ExchangeBoundariesnD", "hpb_TimeStepDistributed", "hpb_RHSFunctionDistributed",
+                 "hpb_stage_overlap_supported"):
         getattr(L, name).argtypes = [vp]
-    for name in ("hpb_stage_begin", "hpb_stage_halo_done", "hpb_stage_rhs_a", "hpb_stage_rhs_b", "hpb_stage_interior"):
-        getattr(L, name).argtypes = [vp, C.c_int]
-    L.hpb_stage_overlap_supported.argtypes = [vp]
-    L.hpb_stage_halo_done_dim.argtypes = [vp, C.c_int, C.c_int]
-    L.hpb_stage_sweep.argtypes = [vp, C.c_int, C.c_int]
+    L.hpb_comm_get_unique_id.argtypes = [C.c_char_p]
+    L.hpb_comm_init_nccl.argtypes = [vp, C.c_char_p, C.c_int]
+    L.hpb_comm_init_local.argtypes = [C.POINTER(vp), C.c_int]
+    L.hpb_comm_allreduce.argtypes = [vp, dp, C.c_int, C.c_int]
+    L.hpb_comm_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.hpb_exchange_plan.argtypes = [vp, C.c_int, ip, C.POINTER(C.c_longlong), ip]
+    L.hpb_TimeStepsDistributed.argtypes = [vp, C.c_int]
+    L.hpb_TimeStepsLocal.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    L.hpb_RHSFunctionLocal.argtypes = [C.POINTER(vp), C.c_int]
+    L.hpb_set_overlap.argtypes = [vp, C.c_int]
     L.hpb_dev_get_stage_rhs.argtypes = [vp, C.c_int, dp]
     L.hpb_dev_VolumeIntegral.argtypes = [vp, dp]
     L.hpb_dev_StageBoundaryIntegral.argtypes = [vp, C.c_int, dp]

@@ -10,7 +10,7 @@
 
 // ------------------------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
-static int g_err_state = 0;
+static thread_local int g_err_state = 0;   // per host thread, like the message (one thread per GPU must not see another's failure)
 
 int hpb_fail(int code, const char* fmt, ...)
 {
@@ -272,6 +272,7 @@ extern "C" int hpb_destroy(hpb_solver* h)
 {
   if (!h) return HPB_OK;
   if (h->stream || h->d_x) cudaSetDevice(h->device);
+  hpbc::comm_free(h);          // before the halo buffers go (it frees them itself when NCCL allocated them)
   double** ptrs[] = { &h->d_x, &h->d_dxinv, &h->d_gravf, &h->d_gravg, &h->d_u, &h->d_U, &h->d_fI, &h->d_sI,
                       &h->d_FV, &h->d_stage_aos, &h->d_w, &h->d_red, &h->d_qd4, &h->d_par, &h->d_src,
                       &h->d_cons, &h->d_face, &h->d_part };
@@ -403,11 +404,10 @@ static int rhs_part_a(hpb_solver* h, const double* U, double* rhs)
 {
   if (fused_path(h)) {
     if (fused_visc(h)) {
-      // part 2 when hpb_stage_interior already did the halo-independent part of this stage
-      hpbk::qderiv_fused(h, U, h->interior_stage >= 0 ? 2 : 0);
-      h->interior_stage = -1;
+      TRY(hpbk::qderiv_fused(h, U));
     } else {
-      hpbk::hyperbolic_fused(h, U, rhs, /*negate=*/true, /*with_source=*/true, rhs, nullptr);
+      if (!hpbk::hyperbolic_fused(h, U, rhs, /*negate=*/true, /*with_source=*/true, rhs, nullptr))
+        return hpb_fail(HPB_ERR_CUDA, "right-hand side: the fused sweep refused the launch");
       if (viscous_on(h)) hpbk::parabolic_phase1(h, U);          // NavierStokes2D viscous terms: generic kernels
     }
     return HPB_OK;
@@ -422,7 +422,10 @@ static int rhs_part_a(hpb_solver* h, const double* U, double* rhs)
 static int rhs_part_b(hpb_solver* h, const double* U, double* rhs)
 {
   if (fused_path(h)) {
-    if (fused_visc(h)) hpbk::hyperbolic_fused(h, U, rhs, true, true, rhs, h->d_qd4);
+    if (fused_visc(h)) {
+      if (!hpbk::hyperbolic_fused(h, U, rhs, true, true, rhs, h->d_qd4))
+        return hpb_fail(HPB_ERR_CUDA, "right-hand side: the fused sweep refused the launch");
+    }
     else if (viscous_on(h)) hpbk::parabolic_phase2(h, U, rhs, /*accumulate=*/true);
     else if (h->cfg.model == HPB_MODEL_LINEAR_ADR) hpbk::parabolic_nc1(h, U, rhs, true);
     if (hpbk::has_sponge(h)) hpbk::sponge_source(h, U, rhs);        // production path: straight into the right-hand side
@@ -435,13 +438,14 @@ static int rhs_part_b(hpb_solver* h, const double* U, double* rhs)
   if (par || src_on) hpbk::combine_rhs(h, rhs, par, src_on ? h->d_src : nullptr);
   return HPB_OK;
 }
+extern "C" int hpb_stage_overlap_supported(const hpb_solver* h);
 static bool multi_rank(const hpb_solver* h)
 {
   for (int k = 0; k < 6; k++) if (h->neighbor[k] >= 0) return true;
   return false;
 }
 #define SINGLE_RANK_ONLY(h, name) do { if (multi_rank(h)) return hpb_fail(HPB_ERR_INVALID, \
-  name ": this rank has neighbours; drive the step with the staged hpb_stage_* calls and exchange the halo buffers"); } while (0)
+  name ": this rank has neighbours; use hpb_TimeStepsDistributed / hpb_RHSFunctionDistributed (include/hypar_b200.h)"); } while (0)
 
 // ------------------------------------------------------------------------------------ HOST entry points
 static int tmp(hpb_solver* h, int k) { return dalloc(&h->d_tmp[k], ncell(h)); }
@@ -662,6 +666,7 @@ extern "C" int hpb_dev_set_solution(hpb_solver* h, const double* u_host)
 {
   TRY(need_device(h));
   TRY(upload(h, u_host, h->d_u, h->geo.npg, h->geo.nvars));
+  h->u_halo_valid = false;
   return sync_check(h, "dev_set_solution");
 }
 
@@ -768,6 +773,7 @@ extern "C" int hpb_pipe_upload(hpb_solver* h, const double* u_in, double t0)
   // on the solver's stream (i.e. after the previous field's steps and its transposition to the outgoing array)
   HPB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pipe[EV_IN_READY], 0));
   hpbk::aos_to_soa(h, h->d_pipe_in, h->d_u, h->geo.npg, h->geo.nvars);
+  h->u_halo_valid = false;
   HPB_CUDA(cudaEventRecord(h->ev_pipe[EV_IN_FREE], h->stream));
   h->t = t0;
   return check_async(h, "pipe_upload");
@@ -916,127 +922,242 @@ extern "C" int hpb_dev_RHS(hpb_solver* h, double t, double* rhs_host)
   return sync_check(h, "dev_RHS");
 }
 
-// ------------------------------------------------------------------------------------ staged multi-GPU step
-extern "C" int hpb_halo_buffers(hpb_solver* h, int field, void** send, void** recv, size_t* bytes)
+// ------------------------------------------------------------------------------------ distributed step
+// One time step of a domain-decomposed run, entirely inside the library: TimePreStep.c:50-76 (boundary conditions +
+// halo of u), TimeRK.c:126-195 with TimeRHSFunctionExplicit.c:46-92 per stage (boundary conditions + halo of the stage
+// solution, NavierStokes3DParabolicFunction.c:125-130: halo of QDerivX / QDerivY), and the step completion. The transport
+// is comm.cu's (NCCL send/recv on a communication stream, or device-to-device copies between in-process ranks).
+//
+// The step is written once for a GROUP of solvers: one element with NCCL (one process per GPU), every rank of the
+// decomposition with the in-process transport, which therefore advances in lock step.
+//
+// Overlapped schedule (h->overlap, the default), per stage s >= 1:
+//     k_rk_faces      U_s on the face layers, straight into the send buffers
+//     exchange of u   on the communication stream           ||  k_rk_combine: U_s on the whole block, physical BCs
+//     unpack (one launch)
+//     k_qderiv_*      (viscous) ; pack (one launch per slot)
+//     exchange of the Q-derivatives, dimension 0, then dimensions 1.. as a second group
+//     unpack dim 0 ; sweep x                                 ||  exchange of dimensions 1..
+//     unpack dims 1.. ; sweep y ; sweep z
+// and at the end of the step the same for u itself (faces of u + dt sum b_s k_s first, exchange under the full update):
+// that exchange IS the TimePreStep exchange of the next step, so stage 0 (whose stage solution is u) starts at once.
+// The exchange of the stage-0 solution the reference repeats (TimeRHSFunctionExplicit.c:60 right after TimePreStep.c:57
+// on the same values) is not issued: 4 exchanges of u per RK4 step instead of 5. The serial schedule (h->overlap = 0)
+// runs pack - exchange - unpack where the reference has its MPIExchangeBoundariesnD calls; results are bit-identical
+// (tests/test_gpu_decomposed.py).
+struct Grp { hpb_solver** hs; int n; };
+#define EACH(h) for (int r_ = 0; r_ < G.n; r_++) if (hpb_solver* h = G.hs[r_])
+
+static hpbc::RKCoef stage_coef(const hpb_solver* h, int stage)
 {
-  if (field < 0 || field > 2) return hpb_fail(HPB_ERR_INVALID, "halo_buffers: field %d", field);
-  for (int k = 0; k < 2 * h->geo.ndims; k++) {
-    send[k] = h->d_send[field][k]; recv[k] = h->d_recv[field][k];
-    bytes[k] = (h->neighbor[k] >= 0) ? h->face_bytes[k] : 0;
-    if (field != HPB_FIELD_U && fused_visc(h)) bytes[k] = bytes[k] / h->geo.nvars * 4;   // (u,v,w,T) derivatives only
+  hpbc::RKCoef a; a.n = 0;
+  for (int i = 0; i < stage; i++) {                       // the coefficients of hpbk::rk_stage
+    const double c = h->cfg.dt * h->rk.A[stage * h->rk.ns + i];
+    if (c == 0.0) continue;
+    a.k[a.n] = h->d_Udot[i]; a.a[a.n] = c; a.n++;
+  }
+  return a;
+}
+static hpbc::RKCoef finish_coef(const hpb_solver* h)
+{
+  hpbc::RKCoef a; a.n = h->rk.ns;                         // hpbk::rk_finish
+  for (int s = 0; s < h->rk.ns; s++) { a.k[s] = h->d_Udot[s]; a.a[s] = h->cfg.dt * h->rk.b[s]; }
+  return a;
+}
+
+// serial exchange of a solution array: pack - exchange - wait - unpack
+static int exchange_u_serial(Grp& G, bool stage_solution)
+{
+  TRY(hpbc::fill_begin(G.hs, G.n, hpbc::SLOT_U));
+  EACH(h) { TRY(need_device(h)); hpbc::pack_faces(h, hpbc::SLOT_U, stage_solution ? h->U_cur : h->d_u); }
+  TRY(hpbc::xchg_start(G.hs, G.n, hpbc::SLOT_U));
+  TRY(hpbc::xchg_wait(G.hs, G.n, hpbc::SLOT_U));
+  EACH(h) { TRY(need_device(h)); hpbc::unpack_faces(h, hpbc::SLOT_U, stage_solution ? h->U_cur : h->d_u); }
+  return HPB_OK;
+}
+
+static int dist_prestep(Grp& G)
+{
+  bool valid = true;
+  EACH(h) { TRY(need_device(h)); hpbk::apply_bc(h, h->d_u); valid = valid && h->u_halo_valid; }     // TimePreStep.c:50-56
+  if (!valid) {
+    TRY(exchange_u_serial(G, false));                                                                 // TimePreStep.c:57-76
+    EACH(h) h->u_halo_valid = true;
   }
   return HPB_OK;
 }
 
-extern "C" int hpb_step_begin(hpb_solver* h)
+static int dist_stage(Grp& G, int s)
 {
-  TRY(need_device(h));
-  hpbk::apply_bc(h, h->d_u);                          // TimePreStep.c:50-70
-  hpbk::pack(h, h->d_u, h->geo.nvars, HPB_FIELD_U);
-  return check_async(h, "step_begin");
+  const bool overlap = G.hs[0]->overlap != 0;
+  // ---- stage solution with boundary conditions and halo (TimeRK.c:131-141, TimeRHSFunctionExplicit.c:46-60)
+  if (s == 0) {
+    EACH(h) h->U_cur = h->d_u;                 // TimePreStep has just filled its ghosts
+  } else if (overlap) {
+    TRY(hpbc::fill_begin(G.hs, G.n, hpbc::SLOT_U));
+    EACH(h) { TRY(need_device(h)); hpbc::rk_faces(h, h->d_u, stage_coef(h, s)); }
+    TRY(hpbc::xchg_start(G.hs, G.n, hpbc::SLOT_U));
+    EACH(h) { TRY(need_device(h)); h->U_cur = stage_U(h, s); hpbk::apply_bc(h, h->U_cur); }
+    TRY(hpbc::xchg_wait(G.hs, G.n, hpbc::SLOT_U));
+    EACH(h) { TRY(need_device(h)); hpbc::unpack_faces(h, hpbc::SLOT_U, h->U_cur); }
+  } else {
+    EACH(h) { TRY(need_device(h)); h->U_cur = stage_U(h, s); hpbk::apply_bc(h, h->U_cur); }
+    TRY(exchange_u_serial(G, true));
+  }
+  // ---- right-hand side
+  const bool visc = viscous_on(G.hs[0]);
+  if (overlap && hpb_stage_overlap_supported(G.hs[0])) {
+    const bool fv = fused_visc(G.hs[0]);
+    const int nd = G.hs[0]->geo.ndims;
+    if (fv) {
+      EACH(h) { TRY(need_device(h)); TRY(hpbk::qderiv_fused(h, h->U_cur)); }
+      for (int slot = hpbc::SLOT_Q0; slot <= hpbc::SLOT_Q12; slot++) {
+        TRY(hpbc::fill_begin(G.hs, G.n, slot));
+        EACH(h) { TRY(need_device(h)); hpbc::pack_faces(h, slot, nullptr); }
+        TRY(hpbc::xchg_start(G.hs, G.n, slot));
+      }
+    }
+    for (int d = 0; d < nd; d++) {
+      if (fv && d < 2) {
+        const int slot = d == 0 ? hpbc::SLOT_Q0 : hpbc::SLOT_Q12;
+        TRY(hpbc::xchg_wait(G.hs, G.n, slot));
+        EACH(h) { TRY(need_device(h)); hpbc::unpack_faces(h, slot, nullptr); }
+      }
+      EACH(h) {
+        TRY(need_device(h));
+        double* rhs = h->d_Udot[s];
+        if (!hpbk::hyperbolic_fused(h, h->U_cur, rhs, true, true, rhs, fv ? h->d_qd4 : nullptr, d))
+          return hpb_fail(HPB_ERR_CUDA, "distributed step: fused sweep of direction %d refused the launch", d);
+        stage_boundary_flux(h, h->U_cur, s, d);
+      }
+    }
+  } else {
+    EACH(h) { TRY(need_device(h)); TRY(rhs_part_a(h, h->U_cur, h->d_Udot[s])); }
+    if (visc) {
+      for (int slot = hpbc::SLOT_Q0; slot <= hpbc::SLOT_Q12; slot++) {
+        TRY(hpbc::fill_begin(G.hs, G.n, slot));
+        EACH(h) { TRY(need_device(h)); hpbc::pack_faces(h, slot, nullptr); }
+        TRY(hpbc::xchg_start(G.hs, G.n, slot));
+      }
+      for (int slot = hpbc::SLOT_Q0; slot <= hpbc::SLOT_Q12; slot++) {
+        TRY(hpbc::xchg_wait(G.hs, G.n, slot));
+        EACH(h) { TRY(need_device(h)); hpbc::unpack_faces(h, slot, nullptr); }
+      }
+    }
+    EACH(h) { TRY(need_device(h)); TRY(rhs_part_b(h, h->U_cur, h->d_Udot[s])); stage_boundary_flux(h, h->U_cur, s); }
+  }
+  EACH(h) TRY(check_async(h, "distributed stage"));
+  return HPB_OK;
 }
 
-extern "C" int hpb_step_halo_done(hpb_solver* h)
+static int dist_finish(Grp& G)
 {
-  TRY(need_device(h));
-  hpbk::unpack(h, h->d_u, h->geo.nvars, HPB_FIELD_U);
-  return check_async(h, "step_halo_done");
+  const bool overlap = G.hs[0]->overlap != 0;
+  if (overlap) {
+    // u^{n+1} on the face layers first (reads the old u), its exchange under the full update
+    TRY(hpbc::fill_begin(G.hs, G.n, hpbc::SLOT_U));
+    EACH(h) { TRY(need_device(h)); hpbc::rk_faces(h, h->d_u, finish_coef(h)); }
+    TRY(hpbc::xchg_start(G.hs, G.n, hpbc::SLOT_U));
+  }
+  EACH(h) {
+    TRY(need_device(h));
+    hpbk::rk_finish(h);                                                                   // TimeRK.c:182-193
+    if (h->cfg.conservation_check) hpbk::step_boundary_integral(h, cons_slot(h, 0), cons_slot(h, CONS_SLOT_STEP));
+    h->t += h->cfg.dt;                                                                    // TimePostStep.c:36
+    h->u_halo_valid = false;
+  }
+  if (overlap) {
+    TRY(hpbc::xchg_wait(G.hs, G.n, hpbc::SLOT_U));
+    EACH(h) { TRY(need_device(h)); hpbc::unpack_faces(h, hpbc::SLOT_U, h->d_u); h->u_halo_valid = true; }
+  }
+  EACH(h) TRY(check_async(h, "distributed step"));
+  return HPB_OK;
 }
 
-extern "C" int hpb_stage_begin(hpb_solver* h, int stage)
+static int dist_check(Grp& G, const char* what, int want_kind)
 {
-  TRY(need_device(h));
-  if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
-  double* U = stage_U(h, stage);
-  h->U_cur = U;
-  hpbk::apply_bc(h, U);
-  hpbk::pack(h, U, h->geo.nvars, HPB_FIELD_U);
-  return check_async(h, "stage_begin");
+  if (!G.hs || G.n < 1) return hpb_fail(HPB_ERR_INVALID, "%s: no solver", what);
+  EACH(h) {
+    TRY(need_device(h));
+    if (!hpbc::comm_ready(h)) {
+      if (multi_rank(h)) return hpb_fail(HPB_ERR_INVALID, "%s: this rank has neighbours but no transport "
+                                         "(hpb_comm_init_nccl / hpb_comm_init_local)", what);
+    } else if (hpb_comm_kind(h) != want_kind)
+      return hpb_fail(HPB_ERR_INVALID, "%s: the solver's transport is of the other kind (NCCL: hpb_*Distributed, in-process: hpb_*Local)", what);
+    if (h->overlap != G.hs[0]->overlap) return hpb_fail(HPB_ERR_INVALID, "%s: the ranks disagree on the schedule", what);
+  }
+  return HPB_OK;
 }
 
-static int halo_done(hpb_solver* h, int field, int dim)
+static int dist_steps(Grp& G, int nsteps)
 {
-  TRY(need_device(h));
-  if (dim >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "stage_halo_done: dimension %d", dim);
-  if (field == HPB_FIELD_U) hpbk::unpack(h, h->U_cur ? h->U_cur : h->d_U, h->geo.nvars, HPB_FIELD_U, dim);
-  else if (field == HPB_FIELD_QDERIVX || field == HPB_FIELD_QDERIVY) {
-    if (!viscous_on(h)) return hpb_fail(HPB_ERR_INVALID, "stage_halo_done: no viscous exchange in this configuration");
-    if (fused_visc(h)) hpbk::unpack_qd4(h, field, dim);
-    else hpbk::unpack(h, h->d_QD[field - 1], h->geo.nvars, field, dim);
-  } else return hpb_fail(HPB_ERR_INVALID, "stage_halo_done: field %d", field);
-  return check_async(h, "stage_halo_done");
+  for (int i = 0; i < nsteps; i++) {
+    TRY(dist_prestep(G));
+    for (int s = 0; s < G.hs[0]->rk.ns; s++) TRY(dist_stage(G, s));
+    TRY(dist_finish(G));
+  }
+  return HPB_OK;
 }
-extern "C" int hpb_stage_halo_done(hpb_solver* h, int field) { return halo_done(h, field, -1); }
-extern "C" int hpb_stage_halo_done_dim(hpb_solver* h, int field, int dim)
+static int dist_rhs(Grp& G)
 {
-  if (dim < 0) return hpb_fail(HPB_ERR_INVALID, "stage_halo_done_dim: dimension %d", dim);
-  return halo_done(h, field, dim);
+  TRY(dist_prestep(G));
+  return dist_stage(G, 0);
 }
 
-// 1 when the production path of this configuration can be driven sweep by sweep (hpb_stage_interior /
-// hpb_stage_sweep): fused sweeps with everything but the Q-derivatives inside them
+// NCCL transport: this rank's part; only enqueues (no host synchronisation: hpb_synchronize when the result is needed)
+extern "C" int hpb_TimeStepsDistributed(hpb_solver* h, int nsteps)
+{
+  Grp G{ &h, 1 };
+  TRY(dist_check(G, "TimeStepsDistributed", 1));
+  return dist_steps(G, nsteps);
+}
+extern "C" int hpb_TimeStepDistributed(hpb_solver* h) { return hpb_TimeStepsDistributed(h, 1); }
+extern "C" int hpb_RHSFunctionDistributed(hpb_solver* h)
+{
+  Grp G{ &h, 1 };
+  TRY(dist_check(G, "RHSFunctionDistributed", 1));
+  return dist_rhs(G);
+}
+// in-process transport: all ranks
+extern "C" int hpb_TimeStepsLocal(hpb_solver** hs, int nranks, int nsteps)
+{
+  Grp G{ hs, nranks };
+  TRY(dist_check(G, "TimeStepsLocal", 2));
+  return dist_steps(G, nsteps);
+}
+extern "C" int hpb_RHSFunctionLocal(hpb_solver** hs, int nranks)
+{
+  Grp G{ hs, nranks };
+  TRY(dist_check(G, "RHSFunctionLocal", 2));
+  return dist_rhs(G);
+}
+
+// MPIExchangeBoundariesnD on the device solution (ghost faces of u <- the neighbours' interior layers), blocking
+extern "C" int hpb_ExchangeBoundariesnD(hpb_solver* h)
+{
+  Grp G{ &h, 1 };
+  TRY(dist_check(G, "ExchangeBoundariesnD", 1));
+  TRY(exchange_u_serial(G, false));
+  h->u_halo_valid = true;
+  return sync_check(h, "ExchangeBoundariesnD");
+}
+
+extern "C" int hpb_set_overlap(hpb_solver* h, int on)
+{
+  if (!h) return hpb_fail(HPB_ERR_INVALID, "set_overlap: null solver");
+  h->overlap = on ? 1 : 0;
+  return HPB_OK;
+}
+
+// 1 when the production path of this configuration is driven sweep by sweep in the overlapped schedule (fused sweeps
+// with everything but the Q-derivatives inside them)
 extern "C" int hpb_stage_overlap_supported(const hpb_solver* h)
 {
   if (!fused_path(h)) return 0;
-  if (hpbk::has_sponge(h)) return 0;          // the sponge source is added after the last sweep by hpb_stage_rhs_b
+  if (hpbk::has_sponge(h)) return 0;          // the sponge source is added after the last sweep (rhs_part_b)
   if (viscous_on(h) && !fused_visc(h)) return 0;
   if (h->cfg.model == HPB_MODEL_LINEAR_ADR) return 0;
   return 1;
-}
-
-// the part of stage `stage` that reads no ghost cell of the stage solution: may be issued while the exchange of
-// FIELD_U is in flight (viscous production path: Q-derivatives of the deep interior; otherwise nothing)
-extern "C" int hpb_stage_interior(hpb_solver* h, int stage)
-{
-  TRY(need_device(h));
-  if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
-  if (!hpb_stage_overlap_supported(h)) return hpb_fail(HPB_ERR_INVALID, "stage_interior: configuration is not driven sweep by sweep");
-  if (fused_visc(h)) {
-    hpbk::qderiv_fused(h, h->U_cur ? h->U_cur : h->d_U, 1);
-    h->interior_stage = stage;
-  }
-  return check_async(h, "stage_interior");
-}
-
-// one directional sweep of stage `stage` (needs the FIELD_U halo of dimension `dir` and, with viscous terms, the
-// Q-derivative halos of dimension `dir` only); dir = 0 must come first (it overwrites Udot[stage])
-extern "C" int hpb_stage_sweep(hpb_solver* h, int stage, int dir)
-{
-  TRY(need_device(h));
-  if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
-  if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "stage_sweep: direction %d", dir);
-  if (!hpb_stage_overlap_supported(h)) return hpb_fail(HPB_ERR_INVALID, "stage_sweep: configuration is not driven sweep by sweep");
-  double* U = h->U_cur ? h->U_cur : h->d_U;
-  double* rhs = h->d_Udot[stage];
-  if (!hpbk::hyperbolic_fused(h, U, rhs, true, true, rhs, fused_visc(h) ? h->d_qd4 : nullptr, dir))
-    return hpb_fail(HPB_ERR_CUDA, "stage_sweep: launch failed");
-  stage_boundary_flux(h, U, stage, dir);
-  return check_async(h, "stage_sweep");
-}
-
-extern "C" int hpb_stage_rhs_a(hpb_solver* h, int stage)
-{
-  TRY(need_device(h));
-  if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
-  TRY(rhs_part_a(h, h->U_cur ? h->U_cur : h->d_U, h->d_Udot[stage]));
-  if (viscous_on(h)) {
-    // NavierStokes3DParabolicFunction.c:125-130: QDerivX and QDerivY are exchanged, QDerivZ is not (Q1)
-    if (fused_visc(h)) { hpbk::pack_qd4(h, HPB_FIELD_QDERIVX); hpbk::pack_qd4(h, HPB_FIELD_QDERIVY); }
-    else {
-      hpbk::pack(h, h->d_QD[0], h->geo.nvars, HPB_FIELD_QDERIVX);
-      hpbk::pack(h, h->d_QD[1], h->geo.nvars, HPB_FIELD_QDERIVY);
-    }
-  }
-  return check_async(h, "stage_rhs_a");
-}
-
-extern "C" int hpb_stage_rhs_b(hpb_solver* h, int stage)
-{
-  TRY(need_device(h));
-  if (stage < 0 || stage >= h->rk.ns) return hpb_fail(HPB_ERR_INVALID, "stage %d", stage);
-  TRY(rhs_part_b(h, h->U_cur ? h->U_cur : h->d_U, h->d_Udot[stage]));
-  stage_boundary_flux(h, h->U_cur ? h->U_cur : h->d_U, stage);
-  return check_async(h, "stage_rhs_b");
 }
 
 extern "C" int hpb_dev_get_stage_rhs(hpb_solver* h, int stage, double* rhs_host)
@@ -1044,13 +1165,4 @@ extern "C" int hpb_dev_get_stage_rhs(hpb_solver* h, int stage, double* rhs_host)
   TRY(need_device(h));
   if (stage < 0 || stage >= h->rk.ns || !rhs_host) return hpb_fail(HPB_ERR_INVALID, "dev_get_stage_rhs: stage %d", stage);
   return download(h, h->d_Udot[stage], rhs_host, h->geo.npg, h->geo.nvars);
-}
-
-extern "C" int hpb_step_finish(hpb_solver* h)
-{
-  TRY(need_device(h));
-  hpbk::rk_finish(h);
-  if (h->cfg.conservation_check) hpbk::step_boundary_integral(h, cons_slot(h, 0), cons_slot(h, CONS_SLOT_STEP));
-  h->t += h->cfg.dt;
-  return check_async(h, "step_finish");
 }

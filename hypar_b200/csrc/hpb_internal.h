@@ -70,8 +70,7 @@ struct hpb_solver {
   double *d_x = nullptr, *d_dxinv = nullptr, *d_gravf = nullptr, *d_gravg = nullptr;
   double *d_u = nullptr;           // solution (SoA, ghosts)
   double *d_U = nullptr;           // stage solution
-  int interior_stage = -1;         // staged API: stage whose halo-independent work (hpb_stage_interior) is already done
-  double *U_cur = nullptr;         // staged API: the array holding the current stage solution (d_u for stage 0)
+  double *U_cur = nullptr;         // distributed step: the array holding the current stage solution (d_u for stage 0)
   double *d_Udot[4] = {nullptr, nullptr, nullptr, nullptr};
   double *d_fI = nullptr;          // interface flux (generic path), max over dirs
   double *d_sI = nullptr;          // interface gravity-source function (generic path)
@@ -106,6 +105,15 @@ struct hpb_solver {
   // halo buffers per field: send/recv per face
   double *d_send[3][6] = {}, *d_recv[3][6] = {};
   size_t face_bytes[6] = {};
+  bool halo_nccl_mem = false;      // the halo buffers were re-allocated with ncclMemAlloc (comm.cu)
+  // in-library halo exchange (comm.cu): transport, communication stream, one event pair per exchange slot
+  // ([0] = send buffers filled, recorded on `stream`; [1] = receive buffers filled, recorded on `s_comm`)
+  struct HpbComm* comm = nullptr;
+  cudaStream_t s_comm = nullptr;
+  cudaEvent_t ev_x[3][2] = {};
+  bool u_halo_valid = false;       // the face ghosts of d_u already hold the neighbours' values of the current u
+  int overlap = 1;                 // distributed step: 1 = exchanges hidden behind producers / sweeps, 0 = serial
+  long long xchg_count = 0, xchg_bytes = 0;   // messages sent / bytes sent by this rank (instrumentation)
   bool w_valid = false;
   // optional per-category device timing (hpb_profile_*): CUDA event pairs on h->stream
   bool prof_on = false;
@@ -141,8 +149,6 @@ void apply_bc(hpb_solver* h, double* u);
 // sponge zones (BCSponge.c): out -= sigma (u - u_ref) inside every sponge box; true if the configuration has one
 bool has_sponge(const hpb_solver* h);
 void sponge_source(hpb_solver* h, const double* u, double* out);
-void pack(hpb_solver* h, const double* a, int nv, int field);
-void unpack(hpb_solver* h, double* a, int nv, int field, int only_dim = -1);
 // hyperbolic term. negate=true: out = -sum_d dxinv*(fhat_{j+1}-fhat_j) (the first direction overwrites the
 // interior, i.e. includes the zeroing of TimeRHSFunctionExplicit.c:89); negate=false: out = +hyp.
 // with_source: gravity-source contribution of each gravity direction is ADDED to src (quirk Q5).
@@ -156,9 +162,7 @@ bool fused_available(const hpb_solver* h);
 bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src,
                       const double* qd, int only_dir = -1);
 // fused viscous path (viscous_fused.cu)
-void qderiv_fused(hpb_solver* h, const double* u, int part = 0);
-void pack_qd4(hpb_solver* h, int field);
-void unpack_qd4(hpb_solver* h, int field, int only_dim = -1);
+int qderiv_fused(hpb_solver* h, const double* u, int part = 0);
 // exact path: rhs = (rhs + par) + src in the reference's order (TimeRHSFunctionExplicit.c:89-92)
 void combine_rhs(hpb_solver* h, double* rhs, const double* par, const double* src);
 void parabolic_phase1(hpb_solver* h, const double* u);
@@ -186,4 +190,28 @@ void upwind(hpb_solver* h, double* fI, const double* fL, const double* fR, const
             const double* u, int dir);
 void first_derivative(hpb_solver* h, double* Df, const double* f, int dir, int nv);
 void second_derivative(hpb_solver* h, double* D2f, const double* f, int dir, int nv, int order);
+}
+
+// in-library halo exchange (comm.cu). The primitives act on a GROUP of solvers: one element with the NCCL transport
+// (one process per GPU), every rank of the decomposition with the in-process transport (all ranks in one process:
+// tests on one GPU, or one process driving several GPUs) -- the step is written once, each primitive loops over the
+// group, so that the in-process ranks advance in lock step.
+namespace hpbc {
+enum { BUF_U = 0, BUF_QD = 1 };                 // what travels: the solution / the Q-derivative arrays of the viscous term
+enum { SLOT_U = 0, SLOT_Q0 = 1, SLOT_Q12 = 2 }; // exchange slots: u (all dimensions), Q-derivatives of dimension 0 / of the others
+struct RKCoef { const double* k[4]; double a[4]; int n; };
+int  slot_bufset(int slot);
+int  slot_dimmask(const hpb_solver* h, int slot);
+// before the send buffers of `slot` are rewritten (in-process transport: the neighbours' copies out of them must be done)
+int  fill_begin(hpb_solver** hs, int n, int slot);
+// send buffers <- face layers of array `a` (BUF_U: nvars components x g layers; BUF_QD: see comm.cu)
+void pack_faces(hpb_solver* h, int slot, const double* a);
+// send buffers of SLOT_U <- u + sum a_s k_s on the face layers (the stage vector / the step completion, TimeRK.c:131-141,
+// :182-193, evaluated where it is sent from: the exchange then runs under the full-array update)
+void rk_faces(hpb_solver* h, const double* u, const RKCoef& c);
+int  xchg_start(hpb_solver** hs, int n, int slot);   // after the fill: exchange on the communication stream
+int  xchg_wait(hpb_solver** hs, int n, int slot);    // the compute stream waits for the receive buffers
+void unpack_faces(hpb_solver* h, int slot, double* a);
+int  comm_free(hpb_solver* h);
+bool comm_ready(const hpb_solver* h);
 }

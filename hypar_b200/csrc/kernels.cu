@@ -168,23 +168,6 @@ __global__ void k_sponge(Geom G, ZoneDev z, const double* __restrict__ x, const 
 }
 
 // ------------------------------------------------------------------------------------------
-// halo pack / unpack (MPIExchangeBoundariesnD.c:42-173). Face box: bounds[d] = g, other dims N.
-// Buffer layout: component-major, then the face box with dim 0 fastest.
-__global__ void k_face_copy(Geom G, double* __restrict__ a, int nv, int d, int off_d, double* __restrict__ buf, int to_buf)
-{
-  int b[3] = { G.N[0], G.N[1], G.N[2] };
-  b[d] = G.g;
-  const long long nface = (long long)b[0] * b[1] * b[2];
-  const long long p2 = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // linear over the face box, dim 0 fastest
-  if (p2 >= nface) return;
-  int s[3] = { (int)(p2 % b[0]), (int)((p2 / b[0]) % b[1]), (int)(p2 / ((long long)b[0] * b[1])) };
-  s[d] += off_d;
-  const long long p1 = cell_index(G, s[0], s[1], s[2]);
-  if (to_buf) for (int v = 0; v < nv; v++) buf[v * nface + p2] = a[v * G.npg + p1];
-  else        for (int v = 0; v < nv; v++) a[v * G.npg + p1] = buf[v * nface + p2];
-}
-
-// ------------------------------------------------------------------------------------------
 // GENERIC hyperbolic kernel: one thread per interface. Restates ReconstructHyperbolic
 // (HyperbolicFunction.c:167-222) without materialising fluxC, uC, the 12 weight arrays or
 // uL/uR/fL/fR: flux + modified solution of the six stencil cells, the four weight sets
@@ -1519,34 +1502,6 @@ void sponge_source(hpb_solver* h, const double* u, double* out)
     const int b0 = z.ie[0] - z.is[0], b1 = (G.ndims > 1 ? z.ie[1] - z.is[1] : 1), b2 = (G.ndims > 2 ? z.ie[2] - z.is[2] : 1);
     if (b0 <= 0 || b1 <= 0 || b2 <= 0) continue;
     k_sponge<<<(unsigned)(((long long)b0 * b1 * b2 + TPB - 1) / TPB), TPB, 0, h->stream>>>(G, z, h->d_x, u, out); LAUNCHED(h);
-  }
-}
-
-static void face_launch(hpb_solver* h, double* a, int nv, int d, int off_d, double* buf, int to_buf)
-{
-  const Geom& G = h->geo;
-  int b[3] = { G.N[0], G.N[1], G.N[2] };
-  b[d] = G.g;
-  k_face_copy<<<(unsigned)(((long long)b[0] * b[1] * b[2] + TPB - 1) / TPB), TPB, 0, h->stream>>>(G, a, nv, d, off_d, buf, to_buf); LAUNCHED(h);
-}
-
-void pack(hpb_solver* h, const double* a, int nv, int field)
-{
-  ProfScope ps(h, HPB_PROF_HALO);
-  const Geom& G = h->geo;
-  for (int d = 0; d < G.ndims; d++) {
-    if (h->neighbor[2*d] >= 0)   face_launch(h, (double*)a, nv, d, 0, h->d_send[field][2*d], 1);
-    if (h->neighbor[2*d+1] >= 0) face_launch(h, (double*)a, nv, d, G.N[d] - G.g, h->d_send[field][2*d+1], 1);
-  }
-}
-void unpack(hpb_solver* h, double* a, int nv, int field, int only_dim)
-{
-  ProfScope ps(h, HPB_PROF_HALO);
-  const Geom& G = h->geo;
-  for (int d = 0; d < G.ndims; d++) {
-    if (only_dim >= 0 && d != only_dim) continue;
-    if (h->neighbor[2*d] >= 0)   face_launch(h, a, nv, d, -G.g, h->d_recv[field][2*d], 0);
-    if (h->neighbor[2*d+1] >= 0) face_launch(h, a, nv, d, G.N[d], h->d_recv[field][2*d+1], 0);
   }
 }
 

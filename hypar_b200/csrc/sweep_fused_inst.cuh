@@ -10,14 +10,17 @@ template <int MODEL, int WT, bool MAPX, bool GRAV, bool VISC>
 static bool launch_one(hpb_solver* h, const SweepArgs& a)
 {
   constexpr size_t smem = SweepLayout<MODEL, GRAV, VISC>::smem_bytes;
-  static bool configured = false;
+  // the shared-memory opt-in is a per-device attribute: one bit per device ordinal (one process may hold solvers on
+  // several GPUs)
+  static unsigned long long configured = 0ull;
   auto kern = k_sweep<MODEL, WT, MAPX, GRAV, VISC>;
-  if (!configured) {
+  const unsigned long long dbit = 1ull << (h->device & 63);
+  if (!(configured & dbit)) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
-    configured = true;
+    configured |= dbit;
   }
   dim3 grid((a.nlines + TW - 1) / TW, 1, 1);
   kern<<<grid, NT, smem, h->stream>>>(a);
@@ -38,14 +41,15 @@ static bool launch_one_tma(hpb_solver* h, const SweepArgs& a)
   if (XS == accumulate) return false;
   TmaMaps tm;
   if (!tma_maps_for(h, a, XS, GRAV, VISC, &tm)) return false;
-  static bool configured = false;
+  static unsigned long long configured = 0ull;        // per device ordinal, as above
   auto kern = k_sweep_tma<MODEL, WT, XS, GRAV, VISC>;
-  if (!configured) {
+  const unsigned long long dbit = 1ull << (h->device & 63);
+  if (!(configured & dbit)) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
-    configured = true;
+    configured |= dbit;
   }
   const Geom& G = a.G;
   long long nblk;

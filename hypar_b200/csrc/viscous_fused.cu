@@ -282,116 +282,49 @@ __global__ void __launch_bounds__(QTX * QTY, Q_MINB) k_qderiv_int(const QD3Args 
   }
 }
 
-// pack / unpack of one 4-component derivative array face (same face boxes as the solution exchange)
-__global__ void k_face4(Geom G, double* __restrict__ a, int d, int off_d, double* __restrict__ buf, int to_buf)
-{
-  int b[3] = { G.N[0], G.N[1], G.N[2] };
-  b[d] = G.g;
-  const long long nface = (long long)b[0] * b[1] * b[2];
-  const long long p2 = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // linear over the face box, dim 0 fastest
-  if (p2 >= nface) return;
-  int s[3] = { (int)(p2 % b[0]), (int)((p2 / b[0]) % b[1]), (int)(p2 / ((long long)b[0] * b[1])) };
-  s[d] += off_d;
-  const long long p1 = (s[0] + G.g) + (long long)G.P[0] * ((s[1] + G.g) + (long long)G.P[1] * (s[2] + G.g));
-  if (to_buf) for (int v = 0; v < 4; v++) buf[v * nface + p2] = a[v * G.npg + p1];
-  else        for (int v = 0; v < 4; v++) a[v * G.npg + p1] = buf[v * nface + p2];
-}
-
 } // namespace
 
 namespace hpbk {
 
-// part 0: everything. part 1: only the interior points at least 2 cells away from every face (they read no
-// ghost cell: may run while the halo exchange of u is in flight). part 2: the rest (the 2-cell shell of the
-// interior with the per-point kernel, and the ghost slabs).
-void qderiv_fused(hpb_solver* h, const double* u, int part)
+// All Q-derivatives of one stage: the interior in one tiled launch, the six ghost slabs (normal derivative only; the
+// outermost layer is skipped inside the kernel) with the per-point kernel.
+int qderiv_fused(hpb_solver* h, const double* u, int part)
 {
+  (void)part;
   ProfScope ps(h, HPB_PROF_VISCOUS);
   const Geom& G = h->geo;
-  static bool configured = false;
-  if (!configured) {
+  // the shared-memory opt-in is a per-device attribute: one bit per device ordinal
+  static unsigned long long configured = 0ull;
+  const unsigned long long dbit = 1ull << (h->device & 63);
+  if (!(configured & dbit)) {
     if (cudaFuncSetAttribute(k_qderiv_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QSMEM) != cudaSuccess) {
-      hpb_fail(HPB_ERR_CUDA, "k_qderiv_int: cannot reserve %zu bytes of shared memory", QSMEM);
-      return;
+      cudaGetLastError();
+      return hpb_fail(HPB_ERR_CUDA, "k_qderiv_int: cannot reserve %zu bytes of shared memory", QSMEM);
     }
-    configured = true;
+    configured |= dbit;
   }
   QD3Args a; a.G = G; a.gamma = h->phys.gamma; a.inv_Re = 1.0 / h->phys.Re; a.u = u; a.dxinv = h->d_dxinv; a.qd = h->d_qd4;
   a.zchunk = Q_ZCHUNK;
-  auto box_points = [&](const int lo[3], const int ext[3]) {
-    for (int d = 0; d < 3; d++) { a.lo[d] = lo[d]; a.ext[d] = ext[d]; }
-    const long long n = (long long)ext[0] * ext[1] * ext[2];
-    if (n <= 0) return;
-    k_qderiv3<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a);
-    h->launches++;
-  };
-  const bool splittable = G.N[0] > 2 * QH && G.N[1] > 2 * QH && G.N[2] > 2 * QH;
-  if (part == 1 && !splittable) return;
-  if (part == 2 && !splittable) part = 0;
-  auto box_tiled = [&](const int lo[3], const int ext[3]) {
-    for (int d = 0; d < 3; d++) { a.lo[d] = lo[d]; a.ext[d] = ext[d]; }
-    if (ext[0] <= 0 || ext[1] <= 0 || ext[2] <= 0) return;
-    dim3 grid((ext[0] + QTX - 1) / QTX, (ext[1] + QTY - 1) / QTY, (ext[2] + a.zchunk - 1) / a.zchunk);
+  {
+    for (int d = 0; d < 3; d++) { a.lo[d] = 0; a.ext[d] = G.N[d]; }
+    dim3 grid((G.N[0] + QTX - 1) / QTX, (G.N[1] + QTY - 1) / QTY, (G.N[2] + a.zchunk - 1) / a.zchunk);
     k_qderiv_int<<<grid, dim3(QTX, QTY, 1), QSMEM, h->stream>>>(a);
     h->launches++;
-  };
-  if (part == 0 || part == 1) {
-    const int sh = (part == 1) ? QH : 0;
-    const int lo[3] = { sh, sh, sh }, ext[3] = { G.N[0] - 2 * sh, G.N[1] - 2 * sh, G.N[2] - 2 * sh };
-    box_tiled(lo, ext);
-    if (part == 1) return;
   }
-  if (part == 2) {
-    // the 2-cell shell of the interior as six disjoint boxes, same kernel (thin boxes waste most of a tile, but the
-    // shell is ~2 % of the points)
-    const int N0 = G.N[0], N1 = G.N[1], N2 = G.N[2];
-    const int boxes[6][6] = {
-      { 0, 0, 0, N0, N1, QH }, { 0, 0, N2 - QH, N0, N1, QH },
-      { 0, 0, QH, N0, QH, N2 - 2 * QH }, { 0, N1 - QH, QH, N0, QH, N2 - 2 * QH },
-      { 0, QH, QH, QH, N1 - 2 * QH, N2 - 2 * QH }, { N0 - QH, QH, QH, QH, N1 - 2 * QH, N2 - 2 * QH } };
-    for (int b = 0; b < 6; b++) box_tiled(&boxes[b][0], &boxes[b][3]);
-  }
-  // the six ghost slabs (normal derivative only; the outermost layer is skipped inside the kernel)
   for (int d = 0; d < 3; d++) {
     for (int f = 0; f < 2; f++) {
-      int lo[3] = { 0, 0, 0 }, ext[3] = { G.N[0], G.N[1], G.N[2] };
-      lo[d] = f ? G.N[d] : -G.g;
-      ext[d] = G.g;
-      box_points(lo, ext);
+      for (int k = 0; k < 3; k++) { a.lo[k] = 0; a.ext[k] = G.N[k]; }
+      a.lo[d] = f ? G.N[d] : -G.g;
+      a.ext[d] = G.g;
+      const long long n = (long long)a.ext[0] * a.ext[1] * a.ext[2];
+      if (n <= 0) continue;
+      k_qderiv3<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a);
+      h->launches++;
     }
   }
-}
-
-static void face4(hpb_solver* h, double* a, int d, int off_d, double* buf, int to_buf)
-{
-  const Geom& G = h->geo;
-  int b[3] = { G.N[0], G.N[1], G.N[2] };
-  b[d] = G.g;
-  k_face4<<<(unsigned)(((long long)b[0] * b[1] * b[2] + 127) / 128), 128, 0, h->stream>>>(G, a, d, off_d, buf, to_buf);
-  h->launches++;
-}
-
-// field = HPB_FIELD_QDERIVX / HPB_FIELD_QDERIVY of the fused path: 4-component arrays inside d_qd4
-void pack_qd4(hpb_solver* h, int field)
-{
-  ProfScope ps(h, HPB_PROF_HALO);
-  const Geom& G = h->geo;
-  double* a = h->d_qd4 + (long long)(field - 1) * 4 * G.npg;
-  for (int d = 0; d < G.ndims; d++) {
-    if (h->neighbor[2*d] >= 0)   face4(h, a, d, 0, h->d_send[field][2*d], 1);
-    if (h->neighbor[2*d+1] >= 0) face4(h, a, d, G.N[d] - G.g, h->d_send[field][2*d+1], 1);
-  }
-}
-void unpack_qd4(hpb_solver* h, int field, int only_dim)
-{
-  ProfScope ps(h, HPB_PROF_HALO);
-  const Geom& G = h->geo;
-  double* a = h->d_qd4 + (long long)(field - 1) * 4 * G.npg;
-  for (int d = 0; d < G.ndims; d++) {
-    if (only_dim >= 0 && d != only_dim) continue;
-    if (h->neighbor[2*d] >= 0)   face4(h, a, d, -G.g, h->d_recv[field][2*d], 0);
-    if (h->neighbor[2*d+1] >= 0) face4(h, a, d, G.N[d], h->d_recv[field][2*d+1], 0);
-  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return hpb_fail(HPB_ERR_CUDA, "Q-derivative kernels: launch failed: %s", cudaGetErrorString(e));
+  return HPB_OK;
 }
 
 } // namespace hpbk

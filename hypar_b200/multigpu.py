@@ -1,19 +1,20 @@
-"""One rank of a domain-decomposed run: the halo exchange of MPIExchangeBoundariesnD
-(reference src/MPIFunctions/MPIExchangeBoundariesnD.c:42-173) over torch.distributed (NCCL on the
-GPUs of one NVSwitch box; gloo in the CPU tests), wrapped around the staged C-ABI step
-(``hpb_step_begin`` ... ``hpb_step_finish``, include/hypar_b200.h).
+"""One rank of a domain-decomposed run (one process per GPU).
+
+The halo exchange of MPIExchangeBoundariesnD (reference src/MPIFunctions/MPIExchangeBoundariesnD.c:42-173) and the
+whole time step around it run INSIDE the library (csrc/comm.cu, csrc/capi.cu: hpb_comm_init_nccl,
+hpb_TimeStepsDistributed): pack kernels, ncclSend / ncclRecv on the library's communication stream, unpack kernels,
+ordered by CUDA events -- no Python and no host synchronisation between the stages. This module only brings the
+communicator up (the ncclUniqueId travels over torch.distributed, as it would over MPI_Bcast in HyPar) and offers the
+scalar reductions of TimePreStep / TimePostStep.
 
 Decomposition = HyPar's: ``iproc[d]`` blocks per dimension, remainder on the last block, rank =
 ip0 + iproc0*(ip1 + iproc1*ip2); faces only (edges/corners are never exchanged, as in the reference).
-The path has exactly one real exchange step per field -- no other collective is on the data path;
-CFL / norm reductions are scalar all-reduces outside the hot loop.
 
-Message matching. NCCL point-to-point has no tags: between one pair of ranks, sends and receives
-match in issue order. The reference distinguishes the two messages of a pair with tags 1630/1631
-(:95-100, :132-137); they matter when iproc[d] == 2 with periodic boundaries, where the left and the
-right neighbour are the same peer. Here every rank issues, per dimension, ``send(low face)``,
-``send(high face)`` and ``recv(high ghost)``, ``recv(low ghost)`` -- the peer's low-face send is the
-first message it sends us and lands in our high ghost, its high-face send is the second.
+Message matching. NCCL point-to-point has no tags: between one pair of ranks, sends and receives match in issue
+order. The reference distinguishes the two messages of a pair with tags 1630/1631 (:95-100, :132-137); they matter
+when iproc[d] == 2 with periodic boundaries, where the left and the right neighbour are the same peer. The library
+issues, per dimension, ``send(low face)``, ``send(high face)``, ``recv(high ghost)``, ``recv(low ghost)``
+(``hpb_exchange_plan``; tests/test_multigpu_gloo.py runs that plan over gloo on the CPU).
 """
 from __future__ import annotations
 
@@ -21,7 +22,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from .solver import FIELD_QDERIVX, FIELD_QDERIVY, FIELD_U, Solver
+from .solver import Solver, comm_unique_id
 
 
 def bind_to_gpu_numa(device: int):
@@ -51,8 +52,9 @@ def bind_to_gpu_numa(device: int):
 
 
 def exchange_ops(neighbors: Sequence[int], dims: Optional[Sequence[int]] = None):
-    """The ordered list of point-to-point operations of one face exchange:
-    [("send" | "recv", face index 2*d + side, peer rank)], side 0 = low, 1 = high."""
+    """The ordered list of point-to-point operations of one face exchange, as csrc/comm.cu issues them
+    (``Solver.exchange_plan`` returns the library's own list for a solver; this is the same rule for a bare
+    neighbour table): [("send" | "recv", face index 2*d + side, peer rank)], side 0 = low, 1 = high."""
     nd = len(neighbors) // 2
     ops = []
     for d in (range(nd) if dims is None else dims):
@@ -69,15 +71,20 @@ def exchange_ops(neighbors: Sequence[int], dims: Optional[Sequence[int]] = None)
 
 
 class HaloExchanger:
-    """Face exchange between persistent send/receive buffers (torch tensors: CUDA for NCCL, CPU for gloo)."""
+    """A face exchange over torch.distributed between host (gloo) or device (NCCL) tensors, following a plan of
+    (kind, face, peer) operations. TEST HELPER of the N > 1 path on the CPU (tests/test_multigpu_gloo.py): the product
+    exchanges inside the library (hpb_TimeStepsDistributed)."""
 
-    def __init__(self, neighbors: Sequence[int], send: Sequence, recv: Sequence, group=None):
+    def __init__(self, neighbors: Sequence[int], send: Sequence, recv: Sequence, group=None, plan=None):
         self.neighbors, self.send, self.recv, self.group = list(neighbors), list(send), list(recv), group
+        self.plan = plan
 
     def start(self, dims: Optional[Sequence[int]] = None):
         import torch.distributed as dist
         p2p = []
-        for kind, face, peer in exchange_ops(self.neighbors, dims):
+        plan = self.plan if (self.plan is not None and dims is None) else exchange_ops(self.neighbors, dims)
+        for op in plan:
+            kind, face, peer = op[0], op[1], op[2]
             if kind == "send":
                 p2p.append(dist.P2POp(dist.isend, self.send[face], peer, self.group))
             else:
@@ -93,41 +100,20 @@ class HaloExchanger:
         self.finish(self.start(dims))
 
 
-class _DevBuf:
-    """a raw device allocation seen through __cuda_array_interface__ (no copy, no ownership)"""
-
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (int(ptr), False),
-                                         "version": 2, "strides": None}
-
-
 class DistributedSolver:
-    """Drives the staged step of one rank and exchanges its halo buffers.
+    """One rank of a decomposed run: a Solver whose NCCL transport is up (``hpb_comm_init_nccl``); the steps are
+    ``hpb_TimeStepsDistributed`` -- the stage loop, the pack / unpack kernels and the ncclSend / ncclRecv calls all
+    live in the library.
 
-    The library's kernels run on the solver's own CUDA stream. Serial schedule (``overlap=False``, the default, and
-    every configuration the library cannot drive sweep by sweep): that stream is made torch's current stream
-    around every exchange, so NCCL's send/recv are ordered after the pack kernels and before the unpack kernels
-    without any host synchronisation. Overlapped schedule (``overlap=True``): the exchanges are issued on a second
-    (communication) stream, dimension by dimension, ordered against the compute stream with CUDA events only:
-
-      u halos (all dimensions)            ||  Q-derivatives of the deep interior        (viscous)
-      Q-derivative halos of dimension d+1 ||  sweep d
-      u halos of dimension d+1            ||  sweep d                                   (inviscid)
-
-    Sweep d reads the halos of dimension d only (faces, never edges/corners: MPIExchangeBoundariesnD.c:60-76),
-    so the result is identical to the serial schedule (tests/test_gpu_decomposed.py: bit for bit).
-
-    Measured on 8 B200 (C4, 512^3 per GPU, 2x2x2; profiles/r01f_bench8*.json): serial 193.0 ms/step (95.5 % of the
-    single-GPU rate), overlapped 201.6 ms/step. The exchange itself is ~1 ms of a 48 ms stage (NVLink 5), the
-    pack/unpack kernels another ~0.9 ms; splitting the derivative kernel into deep interior + six thin shell
-    boxes and running NCCL's copy kernels next to FP64-saturated SMs costs more than the ~1 ms it hides. The
-    overlapped schedule is kept for slower links / smaller blocks; the serial one is the default because it is
-    faster here.
+    ``overlap`` selects the library's schedule (``hpb_set_overlap``): True (default) = the exchange of u travels under
+    the full-array RK update (face layers of the stage vector first, straight into the send buffers), the Q-derivative
+    exchange of dimensions 1.. under the x-sweep; False = pack - exchange - unpack in sequence. Bit-identical results.
     """
 
     def __init__(self, solver_inp, boundary, physics, weno, x, rank: int, device: int, group=None,
-                 use_fused: bool = True, overlap: bool = False, muscl=None, advection_field=None):
+                 use_fused: bool = True, overlap: bool = True, muscl=None, advection_field=None):
         import torch
+        import torch.distributed as dist
         self.torch = torch
         self.solver = Solver(solver_inp, boundary, physics, weno, x, rank=rank, device=device, use_fused=use_fused,
                              muscl=muscl, advection_field=advection_field)
@@ -135,91 +121,24 @@ class DistributedSolver:
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.ExternalStream(sv.stream, device=self.device)
         self.viscous = bool(sv.L.hpb_needs_viscous_exchange(sv.h))
-        self.ex = {}
-        fields = [FIELD_U] + ([FIELD_QDERIVX, FIELD_QDERIVY] if self.viscous else [])
-        for f in fields:
-            send, recv, nbytes = sv.halo_buffers(f)
-            st = [torch.as_tensor(_DevBuf(p, n), device=self.device) if (p and n) else None for p, n in zip(send, nbytes)]
-            rt = [torch.as_tensor(_DevBuf(p, n), device=self.device) if (p and n) else None for p, n in zip(recv, nbytes)]
-            self.ex[f] = HaloExchanger(sv.neighbors, st, rt, group)
         self.group = group
-        self.overlap = bool(overlap) and bool(sv.L.hpb_stage_overlap_supported(sv.h))
-        if self.overlap:
-            self.comm_stream = torch.cuda.Stream(device=self.device)
-            self._ev = [torch.cuda.Event() for _ in range(8)]
-
-    # ---- overlapped schedule -------------------------------------------------------------------------------
-    def _exchange_async(self, fields, dims, ev_ready, ev_done) -> None:
-        """issue the exchange of `fields` restricted to `dims` on the communication stream: it starts when the compute
-        stream has reached `ev_ready` (already recorded) and records ev_done[d] after the messages of dimension d"""
-        torch = self.torch
-        self.comm_stream.wait_event(ev_ready)
-        with torch.cuda.stream(self.comm_stream):
-            for d in dims:
-                works = []
-                for f in fields:
-                    works += self.ex[f].start([d])
-                HaloExchanger.finish(works)
-                ev_done[d].record(self.comm_stream)
-
-    def _stage_overlapped(self, s: int) -> None:
-        sv, L = self.solver, self.solver.L
-        nd = sv.ndims
-        dims = list(range(nd))
-        ev_pack, ev_pack2, ev_dim = self._ev[0], self._ev[1], self._ev[2:2 + nd]
-        sv._ck(L.hpb_stage_begin(sv.h, s))                       # stage vector, BCs, pack u
-        ev_pack.record(self.stream)
-        if self.viscous:
-            self._exchange_async([FIELD_U], dims, ev_pack, ev_dim)
-            sv._ck(L.hpb_stage_interior(sv.h, s))                # || exchange of u
-            self.stream.wait_event(ev_dim[nd - 1])
-            sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_U))
-            sv._ck(L.hpb_stage_rhs_a(sv.h, s))                   # shell + ghost slabs of the Q-derivatives, pack
-            ev_pack2.record(self.stream)
-            self._exchange_async([FIELD_QDERIVX, FIELD_QDERIVY], dims, ev_pack2, ev_dim)
-            for d in dims:
-                self.stream.wait_event(ev_dim[d])
-                sv._ck(L.hpb_stage_halo_done_dim(sv.h, FIELD_QDERIVX, d))
-                sv._ck(L.hpb_stage_halo_done_dim(sv.h, FIELD_QDERIVY, d))
-                sv._ck(L.hpb_stage_sweep(sv.h, s, d))            # || exchange of dimensions d+1..
-        else:
-            self._exchange_async([FIELD_U], dims, ev_pack, ev_dim)
-            for d in dims:
-                self.stream.wait_event(ev_dim[d])
-                sv._ck(L.hpb_stage_halo_done_dim(sv.h, FIELD_U, d))
-                sv._ck(L.hpb_stage_sweep(sv.h, s, d))
-
-    def _exchange(self, fields) -> None:
-        with self.torch.cuda.stream(self.stream):
-            works = []
-            for f in fields:
-                works += self.ex[f].start()
-            HaloExchanger.finish(works)
+        nranks = int(np.prod(sv.iproc))
+        if dist.get_world_size(group) != nranks:
+            raise RuntimeError(f"iproc {sv.iproc} needs {nranks} ranks, the process group has {dist.get_world_size(group)}")
+        # ncclUniqueId: made by rank 0 of the group through the library, broadcast as it would be over MPI_Bcast
+        uid = [comm_unique_id() if dist.get_rank(group) == 0 else None]
+        dist.broadcast_object_list(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        sv.comm_init_nccl(uid[0], nranks)
+        sv.set_overlap(overlap)
+        self.overlap = bool(overlap)
+        self.sweepwise = self.overlap and bool(sv.L.hpb_stage_overlap_supported(sv.h))
 
     def time_step(self) -> None:
-        """TimePreStep (BCs + halo on u) and TimeRK (TimeRK.c:126-195), one step."""
-        sv, L = self.solver, self.solver.L
-        sv._ck(L.hpb_step_begin(sv.h))
-        self._exchange([FIELD_U])
-        sv._ck(L.hpb_step_halo_done(sv.h))
-        for s in range(sv.nstages):
-            if self.overlap:
-                self._stage_overlapped(s)
-                continue
-            sv._ck(L.hpb_stage_begin(sv.h, s))
-            self._exchange([FIELD_U])
-            sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_U))
-            sv._ck(L.hpb_stage_rhs_a(sv.h, s))
-            if self.viscous:
-                self._exchange([FIELD_QDERIVX, FIELD_QDERIVY])
-                sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_QDERIVX))
-                sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_QDERIVY))
-            sv._ck(L.hpb_stage_rhs_b(sv.h, s))
-        sv._ck(L.hpb_step_finish(sv.h))
+        """TimePreStep (BCs + halo on u) and TimeRK (TimeRK.c:126-195), one step; only enqueues."""
+        self.solver.TimeStepsDistributed(1)
 
     def time_steps(self, n: int) -> None:
-        for _ in range(n):
-            self.time_step()
+        self.solver.TimeStepsDistributed(n)
 
     def time_integrate_host(self, u_host: np.ndarray, nsteps: int = 1) -> np.ndarray:
         """TimeIntegrate on a host array in HyPar's layout (this rank's block with ghosts): H2D, steps, D2H."""
@@ -239,20 +158,8 @@ class DistributedSolver:
 
     def rhs(self, want: bool = True):
         """One TimeRHSFunctionExplicit of the device solution (stage 0 buffers); returns this rank's rhs."""
-        sv, L = self.solver, self.solver.L
-        if self.overlap:
-            self._stage_overlapped(0)
-            return sv.get_stage_rhs(0) if want else None
-        sv._ck(L.hpb_stage_begin(sv.h, 0))
-        self._exchange([FIELD_U])
-        sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_U))
-        sv._ck(L.hpb_stage_rhs_a(sv.h, 0))
-        if self.viscous:
-            self._exchange([FIELD_QDERIVX, FIELD_QDERIVY])
-            sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_QDERIVX))
-            sv._ck(L.hpb_stage_halo_done(sv.h, FIELD_QDERIVY))
-        sv._ck(L.hpb_stage_rhs_b(sv.h, 0))
-        return sv.get_stage_rhs(0) if want else None
+        self.solver.RHSFunctionDistributed()
+        return self.solver.get_stage_rhs(0) if want else None
 
     # scalar reductions of TimePreStep.c:81-107 / TimePostStep.c:44-63
     def max_cfl(self) -> float:

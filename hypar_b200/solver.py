@@ -544,8 +544,48 @@ class Solver:
             out[name] = (ms.value, n.value)
         return out
 
-    def halo_buffers(self, field: int):
-        n = 2 * self.ndims
-        send, recv, nbytes = (C.c_void_p * 6)(), (C.c_void_p * 6)(), (C.c_size_t * 6)()
-        self._ck(self.L.hpb_halo_buffers(self.h, field, send, recv, nbytes))
-        return [send[k] for k in range(n)], [recv[k] for k in range(n)], [nbytes[k] for k in range(n)]
+    # ---- in-library halo exchange (include/hypar_b200.h: hpb_comm_*, hpb_*Distributed)
+    def exchange_plan(self, slot: int = 0):
+        """[("send" | "recv", face 2*d + side, peer rank, doubles)] in issue order (host logic: needs no device)"""
+        ops, counts, n = (C.c_int * 72)(), (C.c_longlong * 24)(), C.c_int()
+        self._ck(self.L.hpb_exchange_plan(self.h, slot, ops, counts, C.byref(n)))
+        return [("recv" if ops[3 * i] else "send", ops[3 * i + 1], ops[3 * i + 2], counts[i]) for i in range(n.value)]
+
+    def comm_init_nccl(self, unique_id: bytes, nranks: int) -> None:
+        self._ck(self.L.hpb_comm_init_nccl(self.h, unique_id, nranks))
+
+    def set_overlap(self, on: bool) -> None:
+        self._ck(self.L.hpb_set_overlap(self.h, int(bool(on))))
+
+    def TimeStepsDistributed(self, n: int = 1) -> None:
+        self._ck(self.L.hpb_TimeStepsDistributed(self.h, n))
+
+    def RHSFunctionDistributed(self) -> None:
+        self._ck(self.L.hpb_RHSFunctionDistributed(self.h))
+
+    def comm_allreduce(self, values, op: str = "sum") -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.float64).copy()
+        self._ck(self.L.hpb_comm_allreduce(self.h, _dp(v), v.size, 1 if op == "max" else 0))
+        return v
+
+    def comm_stats(self):
+        m, b = C.c_longlong(), C.c_longlong()
+        self._ck(self.L.hpb_comm_stats(self.h, C.byref(m), C.byref(b)))
+        return m.value, b.value
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and broadcasts the 128 bytes)"""
+    L = _lib.load()
+    buf = C.create_string_buffer(128)
+    if L.hpb_comm_get_unique_id(buf) != 0:
+        raise HyParB200Error(L.hpb_last_error().decode())
+    return buf.raw
+
+
+def comm_init_local(solvers) -> None:
+    """in-process transport: `solvers` = every rank of the decomposition, indexed by rank"""
+    L = _lib.load()
+    arr = (C.c_void_p * len(solvers))(*[sv.h for sv in solvers])
+    if L.hpb_comm_init_local(arr, len(solvers)) != 0:
+        raise HyParB200Error(L.hpb_last_error().decode())

@@ -248,7 +248,7 @@ int hpb_TimeIntegrate(hpb_solver* h, double* u, int nsteps, double t0);
    one and the device->host copy of the one before (two copy streams + the solver's stream, ordered by events).
      hpb_pipe_upload    H2D of u_in (HyPar layout; pinned memory for a true overlap) + transposition into the device
                         solution, after the previous field's steps
-     ... steps: hpb_TimeStep / hpb_TimeSteps (single rank) or the staged hpb_step_* / hpb_stage_* sequence ...
+     ... steps: hpb_TimeStep / hpb_TimeSteps (single rank) or hpb_TimeStepsDistributed (decomposed) ...
      hpb_pipe_download  transposition + D2H of the device solution into u_out
      hpb_pipe_wait      blocks until everything enqueued has finished (u_in may be reused after the upload's copy:
                         conservatively, after hpb_pipe_wait)
@@ -297,40 +297,57 @@ int hpb_dev_ErrorSums(hpb_solver* h, const double* uex_host, double* sums /* [6]
 /* evaluate rhs(u_dev) once into an internal buffer and copy it to the host (HyPar layout) */
 int hpb_dev_RHS(hpb_solver* h, double t, double* rhs_host /* may be NULL */);
 
-/* ---- multi-GPU: one solver per rank; the host (torch.distributed / NCCL) moves the buffers.
- * A time step is driven stage by stage so that the exchange overlaps the interior sweeps:
- *   hpb_stage_begin(s)            U_s = u + dt*sum a_si*Udot_i ; BCs ; pack u halos
- *   [exchange FIELD_U]            (on a comm stream; hpb_stage_interior may run meanwhile)
- *   hpb_stage_halo_done(FIELD_U)  unpack
- *   hpb_stage_rhs_a(s)            hyperbolic sweeps (+source), viscous phase 1, pack QDerivX/Y
- *   [exchange FIELD_QDERIVX, FIELD_QDERIVY]
- *   hpb_stage_halo_done(...)      unpack
- *   hpb_stage_rhs_b(s)            viscous phase 2 ; Udot_s complete
- *   hpb_step_finish()             u += dt*sum b_s*Udot_s ; t += dt
- */
-int hpb_halo_buffers(hpb_solver* h, int field, void** send /*[2*ndims]*/, void** recv /*[2*ndims]*/,
-                     size_t* bytes /*[2*ndims]*/);     /* device pointers; face 2*d = low, 2*d+1 = high */
-int hpb_step_begin(hpb_solver* h);                    /* TimePreStep: BCs on u + pack (exchange FIELD_U follows) */
-int hpb_step_halo_done(hpb_solver* h);                /* unpack into u */
-int hpb_stage_begin(hpb_solver* h, int stage);
-int hpb_stage_halo_done(hpb_solver* h, int field);
-int hpb_stage_rhs_a(hpb_solver* h, int stage);
-int hpb_stage_rhs_b(hpb_solver* h, int stage);
-int hpb_step_finish(hpb_solver* h);
-/* Overlapped variant (production path of NavierStokes2D/3D; hpb_stage_overlap_supported() == 1): the exchange runs
- * on a communication stream, dimension by dimension, while this rank computes:
- *   hpb_stage_begin(s)
- *   [exchange FIELD_U]                         || hpb_stage_interior(s)   Q-derivatives that read no ghost cell
- *   hpb_stage_halo_done(FIELD_U)
- *   hpb_stage_rhs_a(s)                         remaining Q-derivatives, pack QDerivX/Y   (viscous only)
- *   for d = 0..ndims-1:
- *     [exchange dimension d of QDerivX/Y, or of FIELD_U when inviscid]   || sweep d-1
- *     hpb_stage_halo_done_dim(field, d) ; hpb_stage_sweep(s, d)          sweep d needs the halos of dimension d only
- * (faces only, no edges/corners, as MPIExchangeBoundariesnD.c: the dimensions are independent).            */
-int hpb_stage_overlap_supported(const hpb_solver* h);
-int hpb_stage_interior(hpb_solver* h, int stage);
-int hpb_stage_halo_done_dim(hpb_solver* h, int field, int dim);
-int hpb_stage_sweep(hpb_solver* h, int stage, int dir);
+/* ---- multi-GPU: one solver per rank / GPU, HyPar's Cartesian blocks. The halo exchange lives inside the
+ * library (csrc/comm.cu): it replaces
+ *   MPIExchangeBoundariesnD            src/MPIFunctions/MPIExchangeBoundariesnD.c:42-173
+ *   gpuMPIExchangeBoundariesnD         src/MPIFunctions/MPIExchangeBoundariesnD_GPU.cu:435-558
+ * at their call sites on the explicit path: TimePreStep.c:57-76 (u), TimeRHSFunctionExplicit.c:60 (stage solution),
+ * NavierStokes3DParabolicFunction.c:125-130 (QDerivX, QDerivY; QDerivZ is not exchanged there, nor here).
+ * Transport: NCCL point-to-point over NVLink (ncclSend / ncclRecv, grouped, on a communication stream of the library;
+ * libnccl.so.2 is dlopen'ed, there is no link-time dependency), or an in-process transport when one process owns every
+ * rank (device-to-device copies; the single-GPU tests, or one process driving several GPUs).
+ *
+ *   rank 0:  hpb_comm_get_unique_id(id)  ->  the caller broadcasts the 128 bytes (HyPar: MPI_Bcast on mpi.world)
+ *   all:     hpb_comm_init_nccl(h, id, nranks)          collective (ncclCommInitRank; rank = cfg.rank)
+ *            hpb_dev_set_solution(h, u) ... hpb_TimeStepsDistributed(h, n) ... hpb_dev_get_solution(h, u)
+ *            hpb_comm_allreduce(h, v, n, op)            MPISum_double / MPIMax_double for CFL, norms, integrals
+ *            hpb_comm_finalize(h)                       (hpb_destroy does it too)
+ * hpb_TimeStepsDistributed only ENQUEUES (no host synchronisation between stages or steps: compute and communication
+ * streams are ordered by CUDA events); hpb_synchronize / any download waits for it. */
+#define HPB_COMM_ID_BYTES 128
+#define HPB_SLOT_U   0   /* exchange of the solution, all dimensions */
+#define HPB_SLOT_Q0  1   /* exchange of the Q-derivatives across the faces of dimension 0 */
+#define HPB_SLOT_Q12 2   /* ... of the other dimensions */
+int hpb_comm_get_unique_id(void* id /* [HPB_COMM_ID_BYTES] */);
+int hpb_comm_nccl_version(void);                          /* e.g. 22809; 0 = libnccl could not be loaded */
+int hpb_comm_init_nccl(hpb_solver* h, const void* id, int nranks);
+int hpb_comm_init_local(hpb_solver** ranks, int nranks);  /* every rank of the decomposition, indexed by rank, one process */
+int hpb_comm_finalize(hpb_solver* h);
+int hpb_comm_kind(const hpb_solver* h);                   /* 0 none, 1 NCCL, 2 in-process */
+int hpb_comm_allreduce(hpb_solver* h, double* v, int n /* <= 8 */, int op /* 0 sum, 1 max */);
+int hpb_comm_stats(const hpb_solver* h, long long* messages_sent, long long* bytes_sent);
+/* the ordered point-to-point operations of one exchange on this rank (host logic, needs no device): ops[3*i] = 0 send /
+   1 recv, ops[3*i+1] = face 2*d + side (side 0 = low), ops[3*i+2] = peer rank, counts[i] = doubles; at most 24 entries.
+   Per dimension: send(low), send(high), recv(high), recv(low) -- between one pair of ranks messages match in issue order
+   (the role of the reference's tags 1630 / 1631 when both neighbours are the same rank). */
+int hpb_exchange_plan(const hpb_solver* h, int slot, int* ops, long long* counts, int* nops);
+/* MPIExchangeBoundariesnD on the device solution: ghost faces of u <- the neighbours' interior layers. Blocking. */
+int hpb_ExchangeBoundariesnD(hpb_solver* h);
+/* TimePreStep (BCs + halo of u) + TimeRK + step completion, nsteps times; this rank's part (NCCL transport) */
+int hpb_TimeStepDistributed(hpb_solver* h);
+int hpb_TimeStepsDistributed(hpb_solver* h, int nsteps);
+/* one TimeRHSFunctionExplicit of the device solution into the stage-0 right-hand side (hpb_dev_get_stage_rhs(h, 0, .)) */
+int hpb_RHSFunctionDistributed(hpb_solver* h);
+/* the same for in-process ranks: all of them advance in lock step */
+int hpb_TimeStepsLocal(hpb_solver** ranks, int nranks, int nsteps);
+int hpb_RHSFunctionLocal(hpb_solver** ranks, int nranks);
+/* Schedule of the distributed step. 1 (default): the exchange of u travels under the full-array RK update (the face
+ * layers of the stage vector are evaluated first, straight into the send buffers; the step completion does the same,
+ * which makes the TimePreStep exchange of the next step free), the Q-derivative exchange of dimensions 1.. travels
+ * under the x-sweep (sweep d reads the halos of dimension d only: faces, never edges or corners). 0: pack - exchange -
+ * unpack in sequence at the reference's call sites. Results are bit-identical. */
+int hpb_set_overlap(hpb_solver* h, int on);
+int hpb_stage_overlap_supported(const hpb_solver* h);     /* 1: this configuration is driven sweep by sweep when overlapped */
 int hpb_dev_get_stage_rhs(hpb_solver* h, int stage, double* rhs_host);   /* Udot[stage] -> host (HyPar layout) */
 int hpb_nstages(const hpb_solver* h);
 int hpb_needs_viscous_exchange(const hpb_solver* h);

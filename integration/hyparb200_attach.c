@@ -235,16 +235,21 @@ int hyparb200_attach(void *sims, int nsims)
 
   if (!strcmp(s->model, _NAVIER_STOKES_3D_)) {
     NavierStokes3D *p = (NavierStokes3D*) s->physics;
-    c.model = HPB_MODEL_NS3D;  c.gamma = p->gamma;  c.Pr = p->Pr;  c.Minf = p->Minf;
-    c.Re = (p->Re > 0 ? p->Re * p->Minf : p->Re);   /* HyPar already divided Re by Minf (NavierStokes3DInitialize.c:368) */
+    /* HyPar already divided Re by Minf (NavierStokes3DInitialize.c:368); Minf enters the path only through that quotient:
+       pass the scaled value with Minf = 1 so that it is not multiplied and divided again (1 ulp when Minf is not 2^k) */
+    c.model = HPB_MODEL_NS3D;  c.gamma = p->gamma;  c.Pr = p->Pr;  c.Minf = 1.0;
+    c.Re = p->Re;
     c.upwind = upwind_choice(p->upw_choice);
     c.gravity[0] = p->grav_x; c.gravity[1] = p->grav_y; c.gravity[2] = p->grav_z;
     c.rho_ref = p->rho0; c.p_ref = p->p0; c.R = p->R; c.HB = p->HB; c.N_bv = p->N_bv;
-    if (c.Re > 0 && strcmp(s->spatial_type_par, _NC_2STAGE_)) return 1;
+    if (c.Re > 0 && strcmp(s->spatial_type_par, _NC_2STAGE_)) {
+      fprintf(stderr, "hyparb200_attach: viscous NavierStokes3D needs par_space_type %s (got %s)\n", _NC_2STAGE_, s->spatial_type_par);
+      return 1;
+    }
   } else if (!strcmp(s->model, _NAVIER_STOKES_2D_)) {
     NavierStokes2D *p = (NavierStokes2D*) s->physics;
-    c.model = HPB_MODEL_NS2D;  c.gamma = p->gamma;  c.Pr = p->Pr;  c.Minf = p->Minf;
-    c.Re = (p->Re > 0 ? p->Re * p->Minf : p->Re);   /* NavierStokes2DInitialize.c:205 */
+    c.model = HPB_MODEL_NS2D;  c.gamma = p->gamma;  c.Pr = p->Pr;  c.Minf = 1.0;
+    c.Re = p->Re;                                   /* already / Minf: NavierStokes2DInitialize.c:205 */
     c.upwind = upwind_choice(p->upw_choice);
     c.gravity[0] = p->grav_x; c.gravity[1] = p->grav_y;
     c.rho_ref = p->rho0; c.p_ref = p->p0; c.R = p->R; c.HB = p->HB; c.N_bv = p->N_bv;

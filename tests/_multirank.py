@@ -141,96 +141,43 @@ class MultiRankOracle:
 
 class LocalRanks:
     def __init__(self, case, use_fused=True, device=0, sweepwise=False):
-        """sweepwise: drive the stages with the call sequence of the overlapped schedule (hpb_stage_interior,
-        hpb_stage_halo_done_dim, hpb_stage_sweep) -- same order of calls as DistributedSolver._stage_overlapped."""
-        import torch
-        from hypar_b200.multigpu import _DevBuf
-        self.torch = torch
+        """All ranks of a decomposed case in this process on one GPU, advanced in lock step by the library's own
+        distributed step (hpb_TimeStepsLocal / hpb_RHSFunctionLocal) over the in-process transport: pack / unpack kernels,
+        face-layer RK kernels, event ordering and schedule are the ones the NCCL run uses; only the copy between the ranks'
+        buffers differs (cudaMemcpyAsync instead of ncclSend / ncclRecv).
+        sweepwise: the overlapped schedule (hpb_set_overlap 1); otherwise the serial one."""
+        import ctypes as C
+        from hypar_b200.solver import comm_init_local
         self.nranks = int(np.prod(case.solver["iproc"]))
         self.sv = [Solver.from_case(case, rank=r, device=device, use_fused=use_fused) for r in range(self.nranks)]
         self.viscous = bool(self.sv[0].L.hpb_needs_viscous_exchange(self.sv[0].h))
         self.sweepwise = bool(sweepwise)
-        if self.sweepwise:
-            assert all(sv.L.hpb_stage_overlap_supported(sv.h) for sv in self.sv), "configuration is not driven sweep by sweep"
-        dev = torch.device("cuda", device)
-        self.buf = {}
-        for f in [FIELD_U] + ([FIELD_QDERIVX, FIELD_QDERIVY] if self.viscous else []):
-            for r, sv in enumerate(self.sv):
-                send, recv, nbytes = sv.halo_buffers(f)
-                for k in range(2 * sv.ndims):
-                    if nbytes[k]:
-                        self.buf[(f, r, k, "s")] = torch.as_tensor(_DevBuf(send[k], nbytes[k]), device=dev)
-                        self.buf[(f, r, k, "r")] = torch.as_tensor(_DevBuf(recv[k], nbytes[k]), device=dev)
+        comm_init_local(self.sv)
+        for sv in self.sv:
+            sv.set_overlap(self.sweepwise)
+        self._arr = (C.c_void_p * self.nranks)(*[sv.h for sv in self.sv])
 
     def _sync(self):
         for sv in self.sv:
             sv.synchronize()
-        self.torch.cuda.synchronize()
-
-    def exchange(self, fields):
-        self._sync()
-        for f in fields:
-            for r, sv in enumerate(self.sv):
-                for k in range(2 * sv.ndims):
-                    peer = sv.neighbors[k]
-                    if peer >= 0:
-                        self.buf[(f, r, k, "r")].copy_(self.buf[(f, peer, k ^ 1, "s")])
-        self.torch.cuda.synchronize()
-
-    def _all(self, name, *args):
-        for sv in self.sv:
-            sv._ck(getattr(sv.L, name)(sv.h, *args))
 
     def set_solution(self, u):
         for sv, x in zip(self.sv, u):
             sv.set_solution(x)
 
     def get_solution(self):
+        self._sync()
         return [sv.get_solution() for sv in self.sv]
 
-    def _stage_sweepwise(self, s):
-        nd = self.sv[0].ndims
-        self._all("hpb_stage_begin", s)
-        if self.viscous:
-            self._all("hpb_stage_interior", s)          # before the halos of u have arrived
-            self.exchange([FIELD_U])
-            self._all("hpb_stage_halo_done", FIELD_U)
-            self._all("hpb_stage_rhs_a", s)
-            self.exchange([FIELD_QDERIVX, FIELD_QDERIVY])
-            for d in range(nd):
-                self._all("hpb_stage_halo_done_dim", FIELD_QDERIVX, d)
-                self._all("hpb_stage_halo_done_dim", FIELD_QDERIVY, d)
-                self._all("hpb_stage_sweep", s, d)
-        else:
-            self.exchange([FIELD_U])
-            for d in range(nd):
-                self._all("hpb_stage_halo_done_dim", FIELD_U, d)
-                self._all("hpb_stage_sweep", s, d)
-
-    def _stage(self, s):
-        if self.sweepwise:
-            return self._stage_sweepwise(s)
-        self._all("hpb_stage_begin", s)
-        self.exchange([FIELD_U])
-        self._all("hpb_stage_halo_done", FIELD_U)
-        self._all("hpb_stage_rhs_a", s)
-        if self.viscous:
-            self.exchange([FIELD_QDERIVX, FIELD_QDERIVY])
-            self._all("hpb_stage_halo_done", FIELD_QDERIVX)
-            self._all("hpb_stage_halo_done", FIELD_QDERIVY)
-        self._all("hpb_stage_rhs_b", s)
-
     def rhs(self):
-        self._stage(0)
+        sv = self.sv[0]
+        sv._ck(sv.L.hpb_RHSFunctionLocal(self._arr, self.nranks))
+        self._sync()
         return [sv.get_stage_rhs(0) for sv in self.sv]
 
-    def time_step(self):
-        self._all("hpb_step_begin")
-        self.exchange([FIELD_U])
-        self._all("hpb_step_halo_done")
-        for s in range(self.sv[0].nstages):
-            self._stage(s)
-        self._all("hpb_step_finish")
+    def time_step(self, n=1):
+        sv = self.sv[0]
+        sv._ck(sv.L.hpb_TimeStepsLocal(self._arr, self.nranks, n))
 
     def close(self):
         for sv in self.sv:

@@ -1,8 +1,9 @@
 """Domain-decomposed runs: every rank's CUDA result against an oracle run WITH THE SAME iproc (the viscous
 term depends on the decomposition: SURVEY.md Q1/Q2). All ranks live in one process on one GPU
-(tests/_multirank.py): the staged C-ABI step, the pack/unpack kernels and the face-buffer plumbing are the
-ones the NCCL run uses; only the transport (device-to-device copy vs ncclSend/Recv) differs, and that one is
-covered by tests/test_multigpu_gloo.py and the 2-GPU check in tools/multigpu_check.py."""
+(tests/_multirank.py) and are advanced by the library's own distributed step (hpb_TimeStepsLocal): schedule, pack /
+unpack / face-layer RK kernels and event ordering are the ones the NCCL run uses; only the transport (device-to-device
+copy vs ncclSend/Recv) differs, and that one is covered by tests/test_multigpu_gloo.py (the library's message plan over
+gloo) and the multi-GPU check in tools/multigpu_check.py."""
 import numpy as np
 import pytest
 
@@ -42,11 +43,12 @@ for c in DECOMP:
 
 @pytest.mark.parametrize("case", DECOMP, ids=[c.name for c in DECOMP])
 @pytest.mark.parametrize("fused", [False, True], ids=["exact", "fused"])
-def test_decomposed_rhs_and_steps(need_gpu, case, fused):
+@pytest.mark.parametrize("overlap", [False, True], ids=["serial", "overlap"])
+def test_decomposed_rhs_and_steps(need_gpu, case, fused, overlap):
     MO = MultiRankOracle(case)
     u_ref = MO.local_u0()
     rhs_ref = MO.rhs(u_ref)
-    LR = LocalRanks(case, use_fused=fused)
+    LR = LocalRanks(case, use_fused=fused, sweepwise=overlap)
     LR.set_solution(MO.local_u0())
     rhs = LR.rhs()
     scale = max(np.abs(r).max() for r in rhs_ref)
@@ -67,8 +69,7 @@ def test_decomposed_rhs_and_steps(need_gpu, case, fused):
     for _ in range(2):
         MO.time_step(u_ref, dt, rk)
     LR.set_solution(MO.local_u0())
-    for _ in range(2):
-        LR.time_step()
+    LR.time_step(2)
     u = LR.get_solution()
     for r in range(MO.nranks):
         a, b = MO.S[r].interior(u[r]), MO.S[r].interior(u_ref[r])
@@ -111,9 +112,10 @@ SWEEPWISE = [cases.ns3d_turbulence((26, 24, 22), "mapped", iproc=(2, 2, 2)),
 
 @pytest.mark.parametrize("case", SWEEPWISE, ids=lambda c: c.name + "_" + "x".join(str(v) for v in c.solver["iproc"]))
 def test_overlapped_call_sequence_is_identical(need_gpu, case):
-    """The overlapped multi-GPU schedule (Q-derivatives of the deep interior before the halos of u arrive, then one
-    sweep per dimension as soon as that dimension's halos are unpacked) gives bit-identical results to the serial
-    sequence, and both agree with the multi-rank oracle."""
+    """The overlapped multi-GPU schedule (face layers of the stage vector first, their exchange under the full-array RK
+    update; the step completion likewise, which serves the next step's TimePreStep; one sweep per dimension as soon as
+    that dimension's Q-derivative halos are unpacked) gives bit-identical results to the serial sequence, and both agree
+    with the multi-rank oracle."""
     MO = MultiRankOracle(case)
     A = LocalRanks(case, use_fused=True, sweepwise=False)
     B = LocalRanks(case, use_fused=True, sweepwise=True)

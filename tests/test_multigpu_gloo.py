@@ -1,5 +1,5 @@
-"""N > 1 path on CPU: world_size-2 (and 4) gloo process groups drive hypar_b200.multigpu.HaloExchanger --
-the same message plan (exchange_ops) the NCCL run uses -- on host buffers packed/unpacked by the oracle.
+"""N > 1 path on CPU: world_size-2 (and 4) gloo process groups execute the message plan the library issues through
+NCCL (hpb_exchange_plan, csrc/comm.cu) on host buffers packed/unpacked by the oracle.
 Checked: every rank's ghost faces equal the neighbour's interior layers of the GLOBAL array, including the
 same-peer case (iproc = 2 with periodic boundaries: two messages each way between one pair of ranks, matched
 by issue order -- the reference needs tags 1630/1631 for this, MPIExchangeBoundariesnD.c:95-137), remainder
@@ -62,8 +62,13 @@ def _worker(rank, world, port, builder, kwargs, q):
                 if sv.neighbors[2 * d + side] >= 0:
                     send[2 * d + side] = torch.from_numpy(O.pack(u, d, side))
                     recv[2 * d + side] = torch.zeros_like(send[2 * d + side])
-        ex = HaloExchanger(sv.neighbors, send, recv)
+        # the plan under test is the LIBRARY's (hpb_exchange_plan: what hpb_TimeStepsDistributed issues through NCCL)
+        plan = sv.exchange_plan(0)
         ops = exchange_ops(sv.neighbors)
+        assert [p[:3] for p in plan] == ops, f"library plan {plan} != {ops}"
+        for kind, face, peer, count in plan:
+            assert count == send[face].numel(), f"face {face}: the library sends {count} doubles, the oracle packs {send[face].numel()}"
+        ex = HaloExchanger(sv.neighbors, send, recv, plan=plan)
         ex.exchange()
         for d in range(nd):
             for side in (0, 1):

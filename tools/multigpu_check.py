@@ -85,12 +85,13 @@ def main():
     for iproc in iprocs:
         for name, case in (("visc", cases.ns3d_turbulence((26, 25, 27), "mapped", iproc=iproc)),
                            ("bubble", cases.ns3d_rising_bubble((26, 24, 28), "yc", iproc=iproc))):
-            for fused in (False, True):
+            keep = {}
+            for fused, overlap in ((False, False), (False, True), (True, False), (True, True)):
                 MO = MultiRankOracle(case)
                 u_ref = MO.local_u0()
                 rhs_ref = MO.rhs(u_ref)
                 ds = DistributedSolver(case.solver, case.boundary, case.physics, case.weno, case.x, rank=rank,
-                                       device=local, use_fused=fused)
+                                       device=local, use_fused=fused, overlap=overlap)
                 ds.solver.set_solution(MO.local_u0()[rank])
                 rhs = ds.rhs()
                 scale = max(np.abs(r).max() for r in rhs_ref)
@@ -113,8 +114,14 @@ def main():
                 lam = MO.O[rank].cfl(MO.local_u0()[rank], dt) / dt
                 tol = 1e-12 + 16 * np.finfo(np.float64).eps * lam * np.abs(MO.local_u0()[rank]).max() / scale
                 good = (e_rhs == 0 and e_u == 0) if not fused else (e_rhs <= tol and e_u <= 1e-11)
+                # the two schedules of the library's step must agree bit for bit
+                if overlap:
+                    good = good and np.array_equal(keep[fused][0], rhs) and np.array_equal(keep[fused][1], u)
+                else:
+                    keep[fused] = (rhs.copy(), u.copy())
                 ok = ok and good
-                print(f"[rank {rank}/{world}] iproc {iproc} {name:6s} {'fused' if fused else 'exact'}: "
+                print(f"[rank {rank}/{world}] iproc {iproc} {name:6s} {'fused' if fused else 'exact'} "
+                      f"{'overlapped' if overlap else 'serial    '}: "
                       f"rhs err/scale {e_rhs:.2e}, u(2 steps) rel err {e_u:.2e}, max CFL {cfl:.4f} {'ok' if good else 'FAIL'}",
                       flush=True)
                 ds.solver.close()
