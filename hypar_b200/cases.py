@@ -497,7 +497,7 @@ def ns3d_turbulence(n: Sequence[int] = (512, 512, 512), weno: str = "mapped", vi
 
 # ------------------------------------------------------------------------------------- C5a
 def ns3d_density_wave(n: Sequence[int] = (64, 64, 64), weno: str = "js", tstype: str = "44",
-                      dt: float = 1e-3, iproc=None, scheme: str = "weno5") -> Case:
+                      dt: float = 1e-3, iproc=None, scheme: str = "weno5", upwinding: str = "rusanov") -> Case:
     gamma = 1.4
     xs, X, Y, Z = _grid3(n, [1.0] * 3)
     rho = 1.0 + 0.1 * np.sin(2 * np.pi * X) * np.sin(2 * np.pi * Y) * np.sin(2 * np.pi * Z)
@@ -509,12 +509,13 @@ def ns3d_density_wave(n: Sequence[int] = (64, 64, 64), weno: str = "js", tstype:
         solver=_solver(3, 5, n, "navierstokes3d", ts="rk", tstype=tstype, dt=dt, iproc=iproc,
                        par_type="nonconservative-2stage", par_scheme="4", scheme=scheme),
         boundary=_zones(3, "periodic", [-1e3] * 3, [1e3] * 3),
-        physics={"gamma": gamma, "upwinding": "rusanov"}, weno=weno_inp(weno), x=xs, u0=u)
+        physics={"gamma": gamma, "upwinding": upwinding}, weno=weno_inp(weno), x=xs, u0=u)
 
 
 # ------------------------------------------------------------------------------------- C5b
 def ns3d_rising_bubble(n: Sequence[int] = (64, 64, 64), weno: str = "yc", tstype: str = "ssprk3",
-                       dt: float = 0.01, iproc=None, hb: int = 2, scheme: str = "weno5") -> Case:
+                       dt: float = 0.01, iproc=None, hb: int = 2, scheme: str = "weno5",
+                       upwinding: str = "rusanov") -> Case:
     """Rising thermal bubble: slip walls, gravity (0, 9.8, 0), HB = 2 hydrostatic balance."""
     gamma, R, g = 1.4, 287.058, 9.8
     rho_ref, p_ref = 1.1612055171196529, 100000.0
@@ -538,6 +539,6 @@ def ns3d_rising_bubble(n: Sequence[int] = (64, 64, 64), weno: str = "yc", tstype
         solver=_solver(3, 5, n, "navierstokes3d", ts="rk", tstype=tstype, dt=dt, iproc=iproc,
                        par_type="nonconservative-2stage", par_scheme="4", scheme=scheme),
         boundary=_zones(3, "slip-wall", [0.0] * 3, [L] * 3, wall_velocity=[0.0, 0.0, 0.0]),
-        physics={"gamma": gamma, "upwinding": "rusanov", "gravity": [0.0, g, 0.0],
+        physics={"gamma": gamma, "upwinding": upwinding, "gravity": [0.0, g, 0.0],
                  "rho_ref": rho_ref, "p_ref": p_ref, "R": R, "HB": hb},
         weno=weno_inp(weno), x=xs, u0=u)

@@ -1,7 +1,7 @@
 // sweep_fused.cu -- dispatch of the fused directional sweep kernels (sweep_fused.cuh).
 // Covered: component-wise WENO5 (all weight types, no_limiting) for LinearADR, NavierStokes2D and
-// NavierStokes3D with Rusanov upwinding (with or without gravity). Everything else (characteristic
-// reconstruction, Roe upwinding, Euler1D) is served by the generic per-interface kernels.
+// NavierStokes3D with Rusanov or Roe upwinding (with or without gravity). Everything else (characteristic
+// reconstruction, rf-char / llf-char upwinding, Euler1D) is served by the generic per-interface kernels.
 #include "sweep_fused.cuh"
 #include "sweep_tma.cuh"
 #include <cstdlib>
@@ -92,7 +92,7 @@ bool fused_available(const hpb_solver* h)
   if (h->phys.advf != nullptr || c.advection_field != nullptr) return false;     // spatially varying advection: exact kernels
   if (h->phys.interp_char) return false;
   if (c.model == HPB_MODEL_EULER1D) return false;
-  if ((c.model == HPB_MODEL_NS2D || c.model == HPB_MODEL_NS3D) && c.upwind != HPB_UPWIND_RUSANOV) return false;
+  if ((c.model == HPB_MODEL_NS2D || c.model == HPB_MODEL_NS3D) && c.upwind != HPB_UPWIND_RUSANOV && c.upwind != HPB_UPWIND_ROE) return false;
   if (c.model == HPB_MODEL_LINEAR_ADR && c.nvars != 1) return false;
   if (c.model == HPB_MODEL_NS2D && h->phys.has_grav) return false;   // 2-D gravity source: reference-exact kernels only
   return true;
@@ -113,6 +113,7 @@ bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, 
     a.mode = negate ? (d == 0 ? 0 : 1) : (d == 0 ? 2 : 3);
     a.with_source = (with_source && h->phys.has_grav && h->phys.grav[d] != 0.0 && src != nullptr) ? 1 : 0;
     a.qd = qd;
+    a.upw = (h->cfg.upwind == HPB_UPWIND_ROE) ? 1 : 0;
     {
       static const int tab[3][8] = { { 0, 1, 2, 3, 4, 5, 8, 10 }, { 4, 5, 6, 7, 0, 1, 9, 10 }, { 8, 9, 10, 11, 0, 2, 5, 6 } };
       for (int k = 0; k < 8; k++) a.qidx[k] = tab[d][k];

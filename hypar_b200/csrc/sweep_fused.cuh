@@ -76,6 +76,7 @@ struct SweepArgs {
   int with_source;       // add the gravity source of this direction to src
   int nlines;            // number of grid lines along dir
   const double* qd;      // VISC: (mu/Re) x first differences of (u,v,w,T): qd[(dir*4 + comp) * npg + p] (viscous_fused.cu)
+  int upw;               // fluid models: 0 = Rusanov, 1 = Roe with Harten's entropy fix
   int qidx[8];           // VISC: the 8 derivative scalars the viscous flux of `dir` needs (indices dir*4+comp into qd):
                          //   dir 0: ux vx wx Tx | uy vy | uz wz   dir 1: uy vy wy Ty | ux vx | vz wz   dir 2: uz vz wz Tz | ux wx | vy wy
 };
@@ -103,6 +104,62 @@ __device__ __forceinline__ double sqrt_fast(double x)
   g = fma(g, r, g); h = fma(h, r, h);
   r = fma(-h, g, 0.5);
   return fma(g, r, g);
+}
+
+// ------------------------------------------------------------------------------------------
+// Roe dissipation R |Lambda| L (uR - uL) of NavierStokes3DUpwind.c:40-125 / NavierStokes2DUpwind.c (Roe), in closed form.
+// The reference multiplies the three 5x5 matrices out (MatMult5, MatMult5, MatVecMult5: 275 multiply-adds per interface);
+// with the eigenvectors of navierstokes3d.h:288-470 the product collapses to the wave decomposition
+//   beta = (gamma-1) (ek drho - v.dm + dE),   dn = vn drho - dm_n
+//   w0 = drho - beta / a^2                      entropy wave, speed vn,       r0 = (1, v, ek)
+//   w-+ = (beta +- a dn) / (2 a^2)              acoustic waves, speeds vn -+ a, r-+ = (1, v -+ a n, h0 -+ a vn)
+//   s_t = dm_t - v_t drho                       shear waves (t != n), speed vn, r_t = (0, e_t, v_t)
+// (the signs of the reference's shear rows and columns cancel in the product), ~60 operations. |lambda| carries Harten's
+// fix with delta = 1e-6 (:95-101). The Roe-averaged state comes from the sqrt(rho)-weighted cell records the Rusanov
+// flux uses too; a^2 = (gamma-1)(H - ek) is what _NavierStokes3DRoeAverage_ + GetFlowVar return to rounding.
+// Input du = uR - uL (TWICE the reference's udiff: the caller's flux accumulates 2 x the interface flux).
+__device__ __forceinline__ double harten_abs(double lam)
+{
+  const double delta = 0.000001;
+  const double al = fabs(lam);
+  return (al < delta) ? (lam * lam + delta * delta) * (0.5 / delta) : al;
+}
+template <int NV>
+__device__ __forceinline__ void roe_dissipation(const double (&du)[NV], const double (&vh)[3], double vn, double vsq, double H,
+                                                double gamma, int dir, double (&diss)[NV])
+{
+  constexpr int NDV = NV - 2;
+  const double gm1 = gamma - 1.0;
+  const double ek = 0.5 * vsq;
+  const double a2 = gm1 * (H - ek);
+  double a = sqrt_fast(a2);
+  const double ia2 = rcp_fast(a2);
+  double vdm = 0.0;
+#pragma unroll
+  for (int k = 0; k < NDV; k++) vdm = fma(vh[k], du[1 + k], vdm);
+  const double beta = gm1 * (fma(ek, du[0], du[NV - 1]) - vdm);
+  double dmn = 0.0;
+#pragma unroll
+  for (int k = 0; k < NDV; k++) if (k == dir) dmn = du[1 + k];
+  const double dn = fma(vn, du[0], -dmn);
+  const double l0 = harten_abs(vn), lm = harten_abs(vn - a), lp = harten_abs(vn + a);
+  const double c0 = l0 * fma(-beta, ia2, du[0]);
+  const double hi = 0.5 * ia2;
+  const double cm = lm * (hi * fma(a, dn, beta));
+  const double cp = lp * (hi * fma(-a, dn, beta));
+  const double csum = c0 + cm + cp, cdif = a * (cp - cm);
+  diss[0] = csum;
+  double shear_e = 0.0;
+#pragma unroll
+  for (int k = 0; k < NDV; k++) {
+    if (k == dir) diss[1 + k] = fma(vh[k], csum, cdif);
+    else {
+      const double st = l0 * fma(-vh[k], du[0], du[1 + k]);
+      diss[1 + k] = fma(vh[k], csum, st);
+      shear_e = fma(vh[k], st, shear_e);
+    }
+  }
+  diss[NV - 1] = fma(ek, c0, fma(H, cm + cp, fma(vn, cdif, shear_e)));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -472,14 +529,23 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const SweepArgs a)
         const int cL = cc - 1, cR = cc;
         const double tL = rec[RL::SR * NREC + cL], tR = rec[RL::SR * NREC + cR];
         const double rs = 1.0 / (tL + tR);
-        double vsq = 0.0, vn = 0.0;
+        double vsq = 0.0, vn = 0.0, vhat[3] = { 0.0, 0.0, 0.0 };
 #pragma unroll
         for (int k = 0; k < NDV; k++) {
           const double v = (tL * rec[(RL::VEL + k) * NREC + cL] + tR * rec[(RL::VEL + k) * NREC + cR]) * rs;
           vsq += v * v;
+          vhat[k] = v;
           if (k == dir) vn = v;
         }
         const double H = (tL * rec[RL::H * NREC + cL] + tR * rec[RL::H * NREC + cR]) * rs;
+        if (a.upw == 1) {
+          double du[NV], diss[NV];
+#pragma unroll
+          for (int v = 0; v < NV; v++) du[v] = uRv[v] - exL[(NV + v) * NEX + exl];
+          roe_dissipation<NV>(du, vhat, vn, vsq, H, gamma, dir, diss);
+#pragma unroll
+          for (int v = 0; v < NV; v++) fh[v] = 0.5 * ((exL[v * NEX + exl] + fRv[v]) - diss[v]);
+        } else {
         const double cavg = sqrt((gamma - 1.0) * (H - 0.5 * vsq));
         const double aavg = cavg + fabs(vn);
         double alpha = fmax(fmax(rec[RL::A * NREC + cL], rec[RL::A * NREC + cR]), aavg);
@@ -488,6 +554,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep(const SweepArgs a)
         for (int v = 0; v < NV; v++) {
           const double fL = exL[v * NEX + exl], uL = exL[(NV + v) * NEX + exl];
           fh[v] = 0.5 * (fL + fRv[v]) - alpha * (0.5 * (uRv[v] - uL));
+        }
         }
       }
       const int exo = xbase + l + 1;

@@ -381,23 +381,37 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
       const int cL = cc - 1, cR = cc;
       const double tL = rec[LY::rSR * NREC + cL], tR = rec[LY::rSR * NREC + cR];
       const double rs = rcp_fast(tL + tR);
-      double vsq = 0.0, vn = 0.0;
+      double vsq = 0.0, vn = 0.0, vhat[3] = { 0.0, 0.0, 0.0 };
 #pragma unroll
       for (int k = 0; k < NDV; k++) {
         const double v = (tL * rec[(LY::rVEL + k) * NREC + cL] + tR * rec[(LY::rVEL + k) * NREC + cR]) * rs;
         vsq += v * v;
+        vhat[k] = v;
         if (k == dir) vn = v;
       }
       const double H = (tL * rec[LY::rH * NREC + cL] + tR * rec[LY::rH * NREC + cR]) * rs;
-      const double cavg = sqrt_fast((gamma - 1.0) * (H - 0.5 * vsq));
-      const double aavg = cavg + fabs(vn);
-      double alpha = fmax(fmax(rec[LY::rA * NREC + cL], rec[LY::rA * NREC + cR]), aavg);
-      if (G3) alpha *= fmax(rec[(LY::rGF + 1) * NREC + cL], rec[(LY::rGF + 1) * NREC + cR]);
+      if (a.upw == 1) {
+        // Roe (NavierStokes3DUpwind.c:40-125): 2 x the interface flux = (fL + fR) - R |Lambda| L (uR - uL)
+        double du[NV], diss[NV];
 #pragma unroll
-      for (int v = 0; v < NV; v++) {
-        const double uL = exL[(LY::xU + v) * NEX + exl];
-        const double fL = (SKIPF0 && v == 0) ? exL[(LY::xU + 1 + dir) * NEX + exl] : exL[(LY::xF + v) * NEX + exl];
-        fh[v] = (fL + fRv[v]) - alpha * (uRv[v] - uL);          // 2 x the interface flux; the factor 1/2 is in dxih
+        for (int v = 0; v < NV; v++) du[v] = uRv[v] - exL[(LY::xU + v) * NEX + exl];
+        roe_dissipation<NV>(du, vhat, vn, vsq, H, gamma, dir, diss);
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          const double fL = (SKIPF0 && v == 0) ? exL[(LY::xU + 1 + dir) * NEX + exl] : exL[(LY::xF + v) * NEX + exl];
+          fh[v] = (fL + fRv[v]) - diss[v];
+        }
+      } else {
+        const double cavg = sqrt_fast((gamma - 1.0) * (H - 0.5 * vsq));
+        const double aavg = cavg + fabs(vn);
+        double alpha = fmax(fmax(rec[LY::rA * NREC + cL], rec[LY::rA * NREC + cR]), aavg);
+        if (G3) alpha *= fmax(rec[(LY::rGF + 1) * NREC + cL], rec[(LY::rGF + 1) * NREC + cR]);
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          const double uL = exL[(LY::xU + v) * NEX + exl];
+          const double fL = (SKIPF0 && v == 0) ? exL[(LY::xU + 1 + dir) * NEX + exl] : exL[(LY::xF + v) * NEX + exl];
+          fh[v] = (fL + fRv[v]) - alpha * (uRv[v] - uL);          // 2 x the interface flux; the factor 1/2 is in dxih
+        }
       }
       const int exo = xbase + l + 1;
 #pragma unroll
