@@ -24,9 +24,12 @@ extern "C" int hyparb200_detach(void);
 
 class B200Simulation : public SingleSimulation {
   public:
-#ifndef HYPARB200_NO_ATTACH
     int attach() { return hyparb200_attach((void*) m_sim, 1); }
-#endif
+};
+/* ensembles (simulation.inp present: src/main.cpp:278-318): every SimulationObject gets its own library solver */
+class B200Ensemble : public EnsembleSimulation {
+  public:
+    int attach() { return hyparb200_attach((void*) m_sims.data(), m_nsims); }
 };
 
 int main(int argc, char** argv)
@@ -41,7 +44,16 @@ int main(int argc, char** argv)
   MPI_Comm_size(MPI_COMM_WORLD, &nproc);
 #endif
   gettimeofday(&main_start, NULL);
-  B200Simulation* sim = new B200Simulation;
+  /* single or ensemble simulation, chosen as src/main.cpp:273-318 does (sparse grids are not on this path) */
+  int ensemble = 0;
+  if (!rank) { FILE* f = fopen(_ENSEMBLE_SIM_INP_FNAME_, "r"); if (f) { ensemble = 1; fclose(f); } }
+#ifndef serial
+  MPI_Bcast(&ensemble, 1, MPI_INT, 0, MPI_COMM_WORLD);
+#endif
+  B200Simulation* single = ensemble ? NULL : new B200Simulation;
+  B200Ensemble*   many   = ensemble ? new B200Ensemble : NULL;
+  Simulation* sim = ensemble ? (Simulation*) many : (Simulation*) single;
+  if (ensemble && !rank) printf("-- Ensemble Simulation --\n");
   ierr = sim->define(rank, nproc);                 if (ierr) return ierr;
 #ifndef serial
   ierr = sim->mpiCommDup();                        if (ierr) return ierr;
@@ -57,7 +69,7 @@ int main(int argc, char** argv)
   ierr = sim->InitializationWrapup();              if (ierr) return ierr;
 
 #ifndef HYPARB200_NO_ATTACH
-  ierr = sim->attach();                            /* <-- the one added call */
+  ierr = ensemble ? many->attach() : single->attach();     /* <-- the one added call */
   if (ierr) { fprintf(stderr, "hyparb200_attach failed on process %d\n", rank); return ierr; }
 #endif
 

@@ -17,10 +17,17 @@
  *                       TimeIntegrate = hpb_TimeIntegrate(u, 1 step). Slower; exercises the fine-grained ABI.
  * Both give the files HyPar itself writes (op.bin, conservation.dat, errors.dat) with HyPar's own writers.
  *
- * One rank per process here (nproc == 1). With MPI, one rank per GPU, the step shim drives the staged calls
- * (hpb_step_begin ... hpb_step_finish) and moves the face buffers of hpb_halo_buffers with MPI_Isend/Irecv
- * (tags 1630/1631 as MPIExchangeBoundariesnD.c:95-137) -- INTEGRATION.md section 2; hypar_b200/multigpu.py is
- * that loop over NCCL.
+ * Several ranks (one GPU per rank, resident mode): rank 0 asks the library for an ncclUniqueId, HyPar's own
+ * MPIBroadcast_character carries it over mpi->world, hpb_comm_init_nccl brings the library's NCCL transport up and
+ * HyPar::TimeIntegrate becomes hpb_TimeStepsDistributed -- the halo exchange (MPIExchangeBoundariesnD's job) happens
+ * inside the library, device to device over NVLink. Ensembles (nsims > 1, TimeRK.c:50-93): one hpb_solver per
+ * SimulationObject.
+ *
+ * Resident mode keeps HyPar's host code off the hot path: solver->PreStep (NavierStokes3DPreStep.c:55-99 rebuilds a
+ * 3 x 25-double Jacobian per point that the explicit path never reads) is cleared, and the direct call of
+ * MPIExchangeBoundariesnD on the stale host mirror in TimePreStep.c:57-76 is answered by
+ * __wrap_MPIExchangeBoundariesnD below (link with -Wl,--wrap=MPIExchangeBoundariesnD; a maintainer would rather put
+ * `if (solver->use_b200) return 0;` at the top of that call site).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -40,12 +47,28 @@
 #include <physicalmodels/navierstokes3d.h>
 #include "hypar_b200.h"
 
+#define B200_MAXSIM 256
+typedef struct { hpb_solver *h; HyPar *solver; MPIVariables *mpi; } B200Sim;
 static struct {
-  hpb_solver *h;
-  HyPar      *solver;
+  int         nsims;
+  B200Sim     sim[B200_MAXSIM];
   int         resident;
   long long   steps;
 } g;
+
+/* the library solver behind a HyPar solver object (the `void *s` every function pointer receives) */
+static hpb_solver* H(void *s)
+{
+  for (int n = 0; n < g.nsims; n++) if ((void*) g.sim[n].solver == s) return g.sim[n].h;
+  fprintf(stderr, "hypar_b200: called with a solver object that was not attached\n");
+  exit(1);
+}
+static int is_resident_solution(const double *u)
+{
+  if (!g.resident) return 0;
+  for (int n = 0; n < g.nsims; n++) if (u == g.sim[n].solver->u) return 1;
+  return 0;
+}
 
 static void die_on_error(const char *where)
 {
@@ -61,8 +84,18 @@ static int B200_BC(void *s, void *m, double *u, double *xref, double t)
 {
   (void)m; (void)xref;
   if (g.resident && u == ((HyPar*)s)->u) return 0;
-  hpb_ApplyBoundaryConditions(g.h, u, t); die_on_error("ApplyBoundaryConditions");
+  hpb_ApplyBoundaryConditions(H(s), u, t); die_on_error("ApplyBoundaryConditions");
   return 0;
+}
+
+/* ---- TimePreStep.c:57-76 calls MPIExchangeBoundariesnD directly (no function pointer). In resident mode the array it
+   names is the stale host mirror: the device step exchanges the device solution itself (hpb_TimeStepsDistributed).
+   -Wl,--wrap=MPIExchangeBoundariesnD routes the call here; every other array goes to the reference's function. */
+int __real_MPIExchangeBoundariesnD(int, int, int*, int, void*, double*);
+int __wrap_MPIExchangeBoundariesnD(int ndims, int nvars, int *dim, int ghosts, void *m, double *var)
+{
+  if (is_resident_solution(var)) return 0;
+  return __real_MPIExchangeBoundariesnD(ndims, nvars, dim, ghosts, m, var);
 }
 
 /* ---- HyPar::HyperbolicFunction (hypar.h:250-253); the FFunction/Upwind arguments are the model's own, fixed
@@ -73,37 +106,37 @@ static int B200_Hyp(double *hyp, double *u, void *s, void *m, double t, int LimF
 {
   HyPar *solver = (HyPar*) s;
   (void)m; (void)F; (void)U;
-  hpb_HyperbolicFunction(g.h, hyp, u, t, LimFlag); die_on_error("HyperbolicFunction");
+  hpb_HyperbolicFunction(H(s), hyp, u, t, LimFlag); die_on_error("HyperbolicFunction");
   if (!strcmp(solver->ConservationCheck, "yes"))
-    hpb_dev_StageBoundaryIntegral(g.h, -1, solver->StageBoundaryIntegral);
+    hpb_dev_StageBoundaryIntegral(H(s), -1, solver->StageBoundaryIntegral);
   return 0;
 }
 static int B200_Par(double *par, double *u, void *s, void *m, double t)
-{ (void)s; (void)m; hpb_ParabolicFunction(g.h, par, u, t); die_on_error("ParabolicFunction"); return 0; }
+{ (void)s; (void)m; hpb_ParabolicFunction(H(s), par, u, t); die_on_error("ParabolicFunction"); return 0; }
 static int B200_Src(double *src, double *u, void *s, void *m, double t)
-{ (void)s; (void)m; hpb_SourceFunction(g.h, src, u, t); die_on_error("SourceFunction"); return 0; }
+{ (void)s; (void)m; hpb_SourceFunction(H(s), src, u, t); die_on_error("SourceFunction"); return 0; }
 static int B200_FFunction(double *f, double *u, int dir, void *s, double t)
-{ (void)s; hpb_FFunction(g.h, f, u, dir, t); die_on_error("FFunction"); return 0; }
+{ (void)s; hpb_FFunction(H(s), f, u, dir, t); die_on_error("FFunction"); return 0; }
 static int B200_UFunction(double *uC, double *u, int dir, void *s, void *m, double t)
-{ (void)s; (void)m; hpb_UFunction(g.h, uC, u, dir, t); die_on_error("UFunction"); return 0; }
+{ (void)s; (void)m; hpb_UFunction(H(s), uC, u, dir, t); die_on_error("UFunction"); return 0; }
 static int B200_Upwind(double *fI, double *fL, double *fR, double *uL, double *uR, double *u, int dir, void *s, double t)
-{ (void)s; hpb_Upwind(g.h, fI, fL, fR, uL, uR, u, dir, t); die_on_error("Upwind"); return 0; }
+{ (void)s; hpb_Upwind(H(s), fI, fL, fR, uL, uR, u, dir, t); die_on_error("Upwind"); return 0; }
 static int B200_SetInterpLimiterVar(double *fC, double *u, double *x, int dir, void *s, void *m)
-{ (void)x; (void)s; (void)m; hpb_SetInterpLimiterVar(g.h, fC, u, dir); die_on_error("SetInterpLimiterVar"); return 0; }
+{ (void)x; (void)s; (void)m; hpb_SetInterpLimiterVar(H(s), fC, u, dir); die_on_error("SetInterpLimiterVar"); return 0; }
 static int B200_InterpolateInterfacesHyp(double *fI, double *fC, double *u, double *x, int upw, int dir, void *s, void *m, int uflag)
-{ (void)x; (void)s; (void)m; hpb_InterpolateInterfacesHyp(g.h, fI, fC, u, upw, dir, uflag); die_on_error("InterpolateInterfacesHyp"); return 0; }
+{ (void)x; (void)s; (void)m; hpb_InterpolateInterfacesHyp(H(s), fI, fC, u, upw, dir, uflag); die_on_error("InterpolateInterfacesHyp"); return 0; }
 static int B200_FirstDerivativePar(double *Df, double *f, int dir, int bias, void *s, void *m)
-{ (void)s; (void)m; hpb_FirstDerivativePar(g.h, Df, f, dir, bias); die_on_error("FirstDerivativePar"); return 0; }
+{ (void)s; (void)m; hpb_FirstDerivativePar(H(s), Df, f, dir, bias); die_on_error("FirstDerivativePar"); return 0; }
 static int B200_SecondDerivativePar(double *D2f, double *f, int dir, void *s, void *m)
-{ (void)s; (void)m; hpb_SecondDerivativePar(g.h, D2f, f, dir); die_on_error("SecondDerivativePar"); return 0; }
+{ (void)s; (void)m; hpb_SecondDerivativePar(H(s), D2f, f, dir); die_on_error("SecondDerivativePar"); return 0; }
 
 /* ---- HyPar::ComputeCFL (hypar.h:269), called by TimePreStep.c:93 every screen_op_iter steps */
 static double B200_ComputeCFL(void *s, void *m, double dt, double t)
 {
   double cfl = -1.0;
   (void)m;
-  if (g.resident) hpb_dev_ComputeCFL(g.h, &cfl);
-  else            hpb_ComputeCFL(g.h, ((HyPar*)s)->u, dt, t, &cfl);
+  if (g.resident) hpb_dev_ComputeCFL(H(s), &cfl);
+  else            hpb_ComputeCFL(H(s), ((HyPar*)s)->u, dt, t, &cfl);
   die_on_error("ComputeCFL");
   return cfl;
 }
@@ -115,34 +148,38 @@ static int B200_VolumeIntegral(double *VolumeIntegral, double *u, void *s, void 
   HyPar *solver = (HyPar*) s;
   if (g.resident && u == solver->u) {
     double local[HPB_MAX_NVARS];
-    hpb_dev_VolumeIntegral(g.h, local); die_on_error("VolumeIntegral");
+    hpb_dev_VolumeIntegral(H(s), local); die_on_error("VolumeIntegral");
     return MPISum_double(VolumeIntegral, local, solver->nvars, &((MPIVariables*)m)->world);
   }
   return ref_VolumeIntegral(VolumeIntegral, u, s, m);     /* some other host array: HyPar's own host code */
 }
 
-/* ---- HyPar::TimeIntegrate (hypar.h:220) = TimeRK (TimeRK.c:35). */
+/* ---- HyPar::TimeIntegrate (hypar.h:220) = TimeRK (TimeRK.c:35): every simulation of the ensemble advances by one step
+   (with explicit RK they never exchange data: TimeRK.c:50-93 walks one concatenated vector, simulation after simulation) */
 static int B200_TimeRK(void *ts)
 {
   TimeIntegration  *TS  = (TimeIntegration*) ts;
   SimulationObject *sim = (SimulationObject*) TS->simulation;
-  HyPar *solver = &sim[0].solver;
-  const int cons = !strcmp(solver->ConservationCheck, "yes");
-
-  if (!g.resident) {
-    hpb_TimeIntegrate(g.h, solver->u, 1, TS->waqt); die_on_error("TimeIntegrate");
-  } else {
-    hpb_TimeStep(g.h); die_on_error("TimeStep");
-    /* the host mirror is read by: TimePreStep.c:84 + TimePostStep.c:44-63 (screen norm, steps with
-       (iter+1) % screen_op_iter == 0: the copy is taken BEFORE that step, so the step before it refreshes too),
-       OutputSolution (file_op_iter), CalculateError and the final output */
-    const int it = TS->iter + 1;
-    const int refresh = (it % solver->screen_op_iter == 0) || ((it + 1) % solver->screen_op_iter == 0)
-                     || (it % solver->file_op_iter == 0) || (it == TS->n_iter);
-    if (refresh) { hpb_dev_get_solution(g.h, solver->u); die_on_error("get_solution"); }
-  }
-  if (cons) {    /* TimeRK.c:182-193 leaves the step's flux integrals in solver->StepBoundaryIntegral */
-    hpb_dev_StepBoundaryIntegral(g.h, solver->StepBoundaryIntegral); die_on_error("StepBoundaryIntegral");
+  for (int ns = 0; ns < g.nsims; ns++) {
+    HyPar *solver = &sim[ns].solver;
+    hpb_solver *h = H(solver);
+    const int cons = !strcmp(solver->ConservationCheck, "yes");
+    if (!g.resident) {
+      hpb_TimeIntegrate(h, solver->u, 1, TS->waqt); die_on_error("TimeIntegrate");
+    } else {
+      if (sim[ns].mpi.nproc > 1) { hpb_TimeStepsDistributed(h, 1); die_on_error("TimeStepsDistributed"); }
+      else                       { hpb_TimeStep(h); die_on_error("TimeStep"); }
+      /* the host mirror is read by: TimePreStep.c:84 + TimePostStep.c:44-63 (screen norm, steps with
+         (iter+1) % screen_op_iter == 0: the copy is taken BEFORE that step, so the step before it refreshes too),
+         OutputSolution (file_op_iter), CalculateError and the final output */
+      const int it = TS->iter + 1;
+      const int refresh = (it % solver->screen_op_iter == 0) || ((it + 1) % solver->screen_op_iter == 0)
+                       || (it % solver->file_op_iter == 0) || (it == TS->n_iter);
+      if (refresh) { hpb_dev_get_solution(h, solver->u); die_on_error("get_solution"); }
+    }
+    if (cons) {    /* TimeRK.c:182-193 leaves the step's flux integrals in solver->StepBoundaryIntegral */
+      hpb_dev_StepBoundaryIntegral(h, solver->StepBoundaryIntegral); die_on_error("StepBoundaryIntegral");
+    }
   }
   g.steps++;
   return 0;
@@ -173,15 +210,13 @@ static int bc_type(const char *name)
   return -1;
 }
 
-int hyparb200_attach(void *sims, int nsims)
+static int attach_one(SimulationObject *sim, int n)
 {
-  SimulationObject *sim = (SimulationObject*) sims;
-  if (nsims != 1) { fprintf(stderr, "hyparb200_attach: ensembles (nsims > 1) are not on the B200 path\n"); return 1; }
-  HyPar *s = &sim[0].solver;
-  MPIVariables *mpi = &sim[0].mpi;
-  if (mpi->nproc != 1) {
-    fprintf(stderr, "hyparb200_attach: this glue drives one rank per process; multi-rank runs use the staged "
-                    "hpb_stage_* calls (INTEGRATION.md section 2)\n");
+  HyPar *s = &sim[n].solver;
+  MPIVariables *mpi = &sim[n].mpi;
+  hpb_solver *h = NULL;
+  if (mpi->nproc != 1 && !g.resident) {
+    fprintf(stderr, "hyparb200_attach: several ranks need the resident mode (the host-array entry points are single-rank)\n");
     return 1;
   }
   int scheme = -1;
@@ -269,6 +304,9 @@ int hyparb200_attach(void *sims, int nsims)
     for (int i = 0; i < s->ndims * s->nvars; i++) c.diffusion[i] = p->d[i];
     if (p->constant_advection == 1) {
       for (int i = 0; i < s->ndims * s->nvars; i++) c.advection[i] = p->a[i];
+    } else if (p->constant_advection == 0 && mpi->nproc != 1) {
+      fprintf(stderr, "hyparb200_attach: a spatially varying advection field with several ranks is not wired up in this glue\n");
+      return 1;
     } else if (p->constant_advection == 0) {
       /* spatially varying field (LinearADRAdvectionField.c): p->a is this rank's ghost-padded block, [point][ndims*nvars];
          one rank, so its interior IS the global field the C-ABI takes (hpb_create rebuilds the ghosts) */
@@ -304,28 +342,44 @@ int hyparb200_attach(void *sims, int nsims)
     if (b[n].SpongeValue)    for (int v = 0; v < s->nvars; v++) c.zones[n].dirichlet[v] = b[n].SpongeValue[v];
   }
 
-  /* global grid, concatenated per dimension as in initial.inp (ReadArray.c:225-256); one rank: the interior part
-     of solver->x (layout include/basic.h:31-36) */
+  /* global grid, concatenated per dimension as in initial.inp (ReadArray.c:225-256): the interior parts of the ranks'
+     solver->x (layout include/basic.h:31-36), gathered on rank 0 and broadcast with HyPar's own helpers */
   int ntot = 0;
   for (int d = 0; d < s->ndims; d++) ntot += s->dim_global[d];
   double *xg = (double*) calloc(ntot, sizeof(double));
   for (int d = 0, off = 0, offg = 0; d < s->ndims; d++) {
-    for (int i = 0; i < s->dim_local[d]; i++) xg[offg + i] = s->x[off + s->ghosts + i];
+    if (mpi->nproc == 1) {
+      for (int i = 0; i < s->dim_local[d]; i++) xg[offg + i] = s->x[off + s->ghosts + i];
+    } else {
+      MPIGatherArray1D(mpi, (mpi->rank ? NULL : xg + offg), s->x + off, mpi->is[d], mpi->ie[d], s->dim_local[d], s->ghosts);
+      MPIBroadcast_double(xg + offg, s->dim_global[d], 0, &mpi->world);
+    }
     off += s->dim_local[d] + 2 * s->ghosts;  offg += s->dim_global[d];
   }
   c.x_global = xg;
-  c.device = getenv("HYPARB200_DEVICE") ? atoi(getenv("HYPARB200_DEVICE")) : 0;   /* as gpu_device_no (default 0) */
+  /* one GPU per rank (as the reference's gpu_device_no + rank would); HYPARB200_DEVICE pins a device for one-rank runs */
+  const int ndev = hpb_device_count();
+  c.device = getenv("HYPARB200_DEVICE") ? atoi(getenv("HYPARB200_DEVICE")) : (ndev > 0 ? mpi->rank % ndev : 0);
   const char *fz = getenv("HYPARB200_USE_FUSED");
   if (fz) c.use_fused = atoi(fz);
-  int rc = hpb_create(&c, &g.h);
+  int rc = hpb_create(&c, &h);
   free(xg);
   if (advf) free(advf);
   if (rc) { fprintf(stderr, "hyparb200_attach: %s\n", hpb_last_error()); return 1; }   /* unsupported choices fail here */
 
-  const char *mode = getenv("HYPARB200_MODE");
-  g.resident = !(mode && !strcmp(mode, "host"));
-  g.solver = s;
-  if (g.resident && hpb_dev_set_solution(g.h, s->u)) { fprintf(stderr, "hyparb200_attach: %s\n", hpb_last_error()); return 1; }
+  if (mpi->nproc > 1) {
+    /* the library's NCCL transport: the communicator id travels over HyPar's own MPI world */
+    char id[HPB_COMM_ID_BYTES];
+    memset(id, 0, sizeof(id));
+    if (!mpi->rank && hpb_comm_get_unique_id(id)) { fprintf(stderr, "hyparb200_attach: %s\n", hpb_last_error()); return 1; }
+    MPIBroadcast_character(id, HPB_COMM_ID_BYTES, 0, &mpi->world);
+    if (hpb_comm_init_nccl(h, id, mpi->nproc)) { fprintf(stderr, "hyparb200_attach: %s\n", hpb_last_error()); return 1; }
+    const char *ov = getenv("HYPARB200_OVERLAP");
+    if (ov) hpb_set_overlap(h, atoi(ov));
+  }
+  g.sim[n].h = h;  g.sim[n].solver = s;  g.sim[n].mpi = mpi;
+  if (g.resident && hpb_dev_set_solution(h, s->u)) { fprintf(stderr, "hyparb200_attach: %s\n", hpb_last_error()); return 1; }
+  if (g.resident) s->PreStep = NULL;     /* see the header comment: host work on the stale mirror that nothing reads */
 
   /* the pointer swap (what InitializeSolvers.c:71-109 / NavierStokes3DInitialize.c:389-446 do for use_gpu) */
   s->ApplyBoundaryConditions  = B200_BC;
@@ -343,16 +397,32 @@ int hyparb200_attach(void *sims, int nsims)
   ref_VolumeIntegral          = s->VolumeIntegralFunction;
   s->VolumeIntegralFunction   = B200_VolumeIntegral;
   s->TimeIntegrate            = B200_TimeRK;        /* picked up by TimeInitialize.c:55 */
-  if (!mpi->rank) printf("hypar_b200 attached: %s, %s mode, device %d\n", hpb_version(), g.resident ? "resident" : "host", c.device);
+  if (!mpi->rank) printf("hypar_b200 attached%s: %s, %s mode, device %d%s\n", (g.nsims > 1 ? " (one solver per simulation)" : ""),
+                         hpb_version(), g.resident ? "resident" : "host", c.device,
+                         mpi->nproc > 1 ? ", in-library NCCL halo exchange" : "");
+  return 0;
+}
+
+int hyparb200_attach(void *sims, int nsims)
+{
+  SimulationObject *sim = (SimulationObject*) sims;
+  if (nsims < 1 || nsims > B200_MAXSIM) { fprintf(stderr, "hyparb200_attach: %d simulations (1..%d)\n", nsims, B200_MAXSIM); return 1; }
+  const char *mode = getenv("HYPARB200_MODE");
+  g.resident = !(mode && !strcmp(mode, "host"));
+  g.nsims = 0;
+  for (int n = 0; n < nsims; n++) {
+    if (attach_one(sim, n)) return 1;
+    g.nsims = n + 1;
+  }
   return 0;
 }
 
 int hyparb200_detach(void)
 {
-  if (g.h) {
-    if (!g.solver->my_idx) printf("hypar_b200: %lld steps, %lld kernel launches\n", g.steps, hpb_kernel_launch_count(g.h));
-    hpb_destroy(g.h);
-  }
-  g.h = NULL;
+  long long launches = 0;
+  for (int n = 0; n < g.nsims; n++) if (g.sim[n].h) launches += hpb_kernel_launch_count(g.sim[n].h);
+  if (g.nsims && !g.sim[0].mpi->rank) printf("hypar_b200: %lld steps, %lld kernel launches\n", g.steps, launches);
+  for (int n = 0; n < g.nsims; n++) { if (g.sim[n].h) hpb_destroy(g.sim[n].h); g.sim[n].h = NULL; }
+  g.nsims = 0;
   return 0;
 }

@@ -45,8 +45,15 @@
 extern "C" int TimeRHSFunctionExplicit(double*, double*, void*, void*, double);
 extern "C" int CalculateError(void*, void*);
 
-static void dump(const char* name, const HyPar* s, const double* a, long n)
+static int g_rank = 0, g_nproc = 1;
+static void dump(const char* name_in, const HyPar* s, const double* a, long n)
 {
+  /* several ranks (the multi-process shim): ref_<what>.bin -> ref_<what>.r<rank>.bin, every rank dumps its own block */
+  char name[512];
+  if (g_nproc > 1) {
+    const char* dot = strrchr(name_in, '.');
+    snprintf(name, sizeof(name), "%.*s.r%04d%s", (int)(dot - name_in), name_in, g_rank, dot);
+  } else snprintf(name, sizeof(name), "%s", name_in);
   FILE* f = fopen(name, "wb");
   if (!f) { fprintf(stderr, "cannot write %s\n", name); exit(2); }
   int hdr[3] = { s->ndims, s->nvars, s->ghosts };
@@ -79,6 +86,7 @@ int main(int argc, char** argv)
   MPI_Comm_rank(MPI_COMM_WORLD, &rank);
   MPI_Comm_size(MPI_COMM_WORLD, &nproc);
 #endif
+  g_rank = rank; g_nproc = nproc;
 
   SimulationObject* sim = new SimulationObject;
   memset(sim, 0, sizeof(SimulationObject));
@@ -206,7 +214,7 @@ int main(int argc, char** argv)
       TimePreStep(&TS);
       TimeStep(&TS);
       TimePostStep(&TS);
-      printf("STEP %d wctime %.6e norm %.17e maxcfl %.17e\n", TS.iter+1, TS.iter_wctime, TS.norm, TS.max_cfl);
+      if (!rank) printf("STEP %d wctime %.6e norm %.17e maxcfl %.17e\n", TS.iter+1, TS.iter_wctime, TS.norm, TS.max_cfl);
       if (!strcmp(solver->ConservationCheck, "yes")) {
         /* conservation diagnostics of TimePostStep.c:81-93 (VolumeIntegral.c, BoundaryIntegral.c,
            CalculateConservationError.c) and the per-face flux integrals TimeRK.c:182-193 accumulates */

@@ -134,6 +134,9 @@ def test_overlapped_call_sequence_is_identical(need_gpu, case):
         B.time_step()
     ua, ub = A.get_solution(), B.get_solution()
     for r in range(MO.nranks):
-        assert np.array_equal(ua[r], ub[r]), f"rank {r}: u after 2 steps differs between the schedules"
+        # interiors: the overlapped schedule has already exchanged the face ghosts of u for the NEXT step's TimePreStep
+        # (they hold the neighbours' new values), the serial one leaves the previous step's there, as the reference does
+        a, b = MO.S[r].interior(ua[r]), MO.S[r].interior(ub[r])
+        assert np.array_equal(a, b), f"rank {r}: u after 2 steps differs between the schedules"
     A.close()
     B.close()

@@ -151,3 +151,78 @@ def test_hypar_executable_with_library_attached(need_exes, case, variant, tmp_pa
         for k in range(len(ca) - nv, len(ca)):
             assert abs(ca[k] - cb[k]) <= 1e-9 * abs(ca[k]) + 1e-14 * scale + 1e-12, \
                 f"conservation.dat column {k}: {ca[k]!r} vs {cb[k]!r} (integral scale {scale:.2e})"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ensembles (nsims > 1, TimeRK.c:50-93) through the glue: one library solver per SimulationObject
+REF_MAIN = os.path.join(ROOT, "oracle", "_ref", "hypar_ref_main")
+
+
+@pytest.mark.parametrize("name", ["vortex3", "sod2", "turb12"])
+@pytest.mark.parametrize("path", ["exact", "fused"])
+def test_ensemble_through_the_glue(need_exes, name, path, tmp_path):
+    if not os.access(REF_MAIN, os.X_OK):
+        pytest.fail(f"{REF_MAIN} is missing (make -C oracle ref)")
+    sims = cases.ensemble(name, n_iter=4)
+    dref, dnew = str(tmp_path / "ref"), str(tmp_path / "b200")
+    cases.write_ensemble(dref, sims)
+    cases.write_ensemble(dnew, sims)
+    _run(REF_MAIN, dref)
+    out_new = _run(B200_EXE, dnew, {"HYPARB200_USE_FUSED": "0" if path == "exact" else "1"})
+    assert "one solver per simulation" in out_new
+    files = sorted(os.path.basename(f) for f in glob.glob(os.path.join(dref, "op_*.bin")))
+    assert len(files) == len(sims), files
+    assert files == sorted(os.path.basename(f) for f in glob.glob(os.path.join(dnew, "op_*.bin")))
+    for f in files:
+        a, b = os.path.join(dref, f), os.path.join(dnew, f)
+        if path == "exact":
+            assert filecmp.cmp(a, b, shallow=False), f"{f}: not byte-identical to the reference's file"
+        else:
+            ua, ub = hypario.read_op_bin(a)[1], hypario.read_op_bin(b)[1]
+            assert np.abs(ua - ub).max() <= 1e-11 * np.abs(ua).max()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# several ranks: HyPar's executable, one GPU per rank, the halo exchange inside the library over NCCL; the ranks are
+# forked by the multi-process MPI shim (oracle/mpishim/mpishim_mp.c). Reference = the unmodified reference with the same
+# number of ranks on the CPU. Needs as many GPUs as ranks (NCCL refuses two ranks on one device).
+REF_MP = os.path.join(ROOT, "oracle", "_ref", "hypar_main_mp")
+B200_MP = os.path.join(ROOT, "oracle", "_ref", "hypar_b200_dropin_mp")
+MP_CASES = [
+    _prep(cases.ns3d_turbulence((26, 25, 27), "mapped", iproc=(1, 1, 2)), n_iter=4, cons=False),
+    _prep(cases.ns3d_rising_bubble((14, 26, 12), "yc", iproc=(1, 2, 1)), n_iter=4, screen=1),
+    _prep(cases.ns2d_vortex((40, 27), "mapped", iproc=(2, 1))),
+]
+
+
+@pytest.mark.parametrize("case", MP_CASES, ids=[c.name for c in MP_CASES])
+@pytest.mark.parametrize("path", ["exact", "fused"])
+def test_multirank_executable_with_library_attached(need_exes, case, path, tmp_path):
+    import ctypes
+    from hypar_b200 import _lib
+    nr = int(np.prod(case.solver["iproc"]))
+    if _lib.load().hpb_device_count() < nr:
+        pytest.skip(f"needs {nr} GPUs (one rank per GPU)")
+    for exe in (REF_MP, B200_MP):
+        if not os.access(exe, os.X_OK):
+            pytest.fail(f"{exe} is missing (make -C oracle refmp && make -C integration)")
+    dref, dnew = str(tmp_path / "ref"), str(tmp_path / "b200")
+    case.write(dref)
+    case.write(dnew)
+    env = {"HPB_MPI_NP": str(nr)}
+    out_ref = _run(REF_MP, dref, env)
+    out_new = _run(B200_MP, dnew, dict(env, HYPARB200_USE_FUSED="0" if path == "exact" else "1"))
+    assert "in-library NCCL halo exchange" in out_new
+    files = sorted(os.path.basename(f) for f in glob.glob(os.path.join(dref, "op_*.bin")))
+    assert len(files) >= 2 and files == sorted(os.path.basename(f) for f in glob.glob(os.path.join(dnew, "op_*.bin")))
+    for f in files:
+        a, b = os.path.join(dref, f), os.path.join(dnew, f)
+        if path == "exact":
+            assert filecmp.cmp(a, b, shallow=False), f"{f}: not byte-identical to the {nr}-rank reference's file"
+        else:
+            ua, ub = hypario.read_op_bin(a)[1], hypario.read_op_bin(b)[1]
+            assert np.abs(ua - ub).max() <= 1e-11 * np.abs(ua).max()
+    ra, rb = _screen_rows(out_ref), _screen_rows(out_new)
+    assert len(ra) == len(rb) and len(ra) >= 1
+    for x, y in zip(ra, rb):
+        assert abs(x["CFL"] - y["CFL"]) <= 2e-3 * x["CFL"] and abs(x["norm"] - y["norm"]) <= 2e-4 * x["norm"] + 1e-300

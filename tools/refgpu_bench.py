@@ -77,17 +77,26 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--upwinding", default="rusanov")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--prepare", default=None, help="only write the run directory of the first --n here (for `ncu ... hypar_ref_gpu`)")
+    ap.add_argument("--tstype", default="44", help="RK type: 44 (C4) or ssprk3 (the reference's DNS example)")
     args = ap.parse_args()
+    if args.prepare:
+        n = args.n[0]
+        c = cases.ns3d_turbulence((n, n, n), "mapped", upwinding=args.upwinding, tstype=args.tstype)
+        c.solver.update({"n_iter": args.steps, "screen_op_iter": 1, "file_op_iter": args.steps, "use_gpu": "yes", "gpu_device_no": 0,
+                         "op_overwrite": "yes"})
+        c.write(args.prepare)
+        return
     if not os.access(EXE, os.X_OK):
         raise SystemExit(f"{EXE} is missing (make -C oracle refgpu, where /root/reference exists)")
     recs = []
     for n in args.n:
-        case = cases.ns3d_turbulence((n, n, n), "mapped", upwinding=args.upwinding)
-        nst = 4
+        case = cases.ns3d_turbulence((n, n, n), "mapped", upwinding=args.upwinding, tstype=args.tstype)
+        nst = 4 if args.tstype == "44" else 3
         r = run_ref_gpu(case, args.steps)
         w = r["wctime"][2:] if len(r["wctime"]) > 4 else r["wctime"]       # HyPar's own per-iteration wall clock, first two dropped
         sec_ref = float(np.median(w))
-        rec = {"grid": f"{n}^3", "upwinding": args.upwinding, "steps": args.steps, "rk_stages": nst,
+        rec = {"grid": f"{n}^3", "upwinding": args.upwinding, "rk": args.tstype, "steps": args.steps, "rk_stages": nst,
                "ref_gpu_s_per_step": sec_ref, "ref_gpu_mpoint_rk_stage_per_s": n ** 3 * nst / sec_ref / 1e6,
                "ref_gpu_wall_s": r["wall_s"]}
         try:
