@@ -50,14 +50,14 @@ def weak_grid(n: int, ngpus: int):
     return [n * iproc[0], n * iproc[1], n * iproc[2]], list(iproc)
 
 
-def c4_inputs(size, iproc, dt=0.005):
+def c4_inputs(size, iproc, dt=0.005, upwinding="rusanov", tstype="44"):
     """solver.inp / boundary.inp / physics.inp / weno.inp of configuration C4 (hypar_b200.cases)."""
     from hypar_b200 import cases
     import numpy as np
-    s = cases._solver(3, 5, size, "navierstokes3d", ts="rk", tstype="44", dt=dt, iproc=iproc,
+    s = cases._solver(3, 5, size, "navierstokes3d", ts="rk", tstype=tstype, dt=dt, iproc=iproc,
                       par_type="nonconservative-2stage", par_scheme="4")
     b = cases._zones(3, "periodic", [-1e3] * 3, [1e3] * 3)
-    ph = {"gamma": 1.4, "upwinding": "rusanov", "Pr": 0.72, "Minf": 0.3, "Re": 333.333333333333333}
+    ph = {"gamma": 1.4, "upwinding": upwinding, "Pr": 0.72, "Minf": 0.3, "Re": 333.333333333333333}
     w = cases.weno_inp("mapped")
     x = [np.arange(size[d], dtype=np.float64) * (2.0 * np.pi / size[d]) for d in range(3)]
     return s, b, ph, w, x
@@ -237,6 +237,11 @@ def workload_inputs(workload, size, iproc):
     if workload == "c4":
         s, b, ph, w, x = c4_inputs(size, iproc)
         return s, b, ph, w, x, "C4 NavierStokes3D WENO5(mapped)+Rusanov+viscous RK4", "periodic"
+    if workload == "c4roe":
+        # the configuration of the reference's own flagship CUDA run (Examples/3D/NavierStokes3D/DNS_IsotropicTurbulenceDecay_CUDA:
+        # weno5 mapped, components, Roe, viscous, SSPRK3; its out.log: 256^3 on 64 V100, 82 ms per step)
+        s, b, ph, w, x = c4_inputs(size, iproc, upwinding="roe", tstype="ssprk3")
+        return s, b, ph, w, x, "C4-Roe NavierStokes3D WENO5(mapped)+Roe+viscous SSPRK3 (the reference's DNS_IsotropicTurbulenceDecay_CUDA setup)", "periodic"
     s, b, ph, w, x = c5_inputs(workload, size, iproc)
     label = ("C5a NavierStokes3D density sine wave, WENO5(JS)+Rusanov, inviscid, RK4" if workload == "c5a" else
              "C5b NavierStokes3D rising thermal bubble, WENO5(YC)+Rusanov, gravity (HB 2) source, SSPRK3")
@@ -265,7 +270,7 @@ class Run:
         # synthetic input, created on the device, staged into a pinned host array in HyPar's own layout
         self.u_host_t = torch.zeros(sv.npoints_local_wghosts * 5, dtype=torch.float64).pin_memory()
         self.u_host = self.u_host_t.numpy()
-        fld = synth_field_torch(x_loc, self.dev) if workload == "c4" else synth_field_c5(workload, x_loc, self.dev)
+        fld = synth_field_torch(x_loc, self.dev) if workload in ("c4", "c4roe") else synth_field_c5(workload, x_loc, self.dev)
         g, n = self.g, self.nloc
         self.u_host_t.view(n[2] + 2 * g, n[1] + 2 * g, n[0] + 2 * g, 5)[g:-g, g:-g, g:-g, :].copy_(fld)
         del fld
@@ -475,6 +480,8 @@ def gpu_arm(args):
                                      "strong-scaling efficiency = value / (N x value at N=1)")
         sub["c5b"] = sub_record("c5b", size, iproc, rank, local_rank, world, args.steps, args.warmup, overlap)
         sub["c5b"]["scaling"] = "weak"
+        if world == 1:
+            sub["c4roe"] = sub_record("c4roe", size, iproc, rank, local_rank, world, args.steps, args.warmup, overlap)
 
     if rank != 0:
         if dist is not None:
@@ -555,7 +562,7 @@ def gpu_arm(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "cfl": cfl,
         "halo_traffic": (None if stepper is None else {"messages_sent_rank0": comm_msgs, "bytes_sent_rank0": comm_bytes}),
-        "strong": sub.get("strong"), "c5b": sub.get("c5b"),
+        "strong": sub.get("strong"), "c5b": sub.get("c5b"), "c4roe": sub.get("c4roe"),
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -571,7 +578,7 @@ def main():
     ap.add_argument("--n", type=int, default=512, help="points per dimension per GPU")
     ap.add_argument("--cpu-n", type=int, default=64, help="grid of the cpu_baseline sample")
     ap.add_argument("--ref-n", type=int, default=64, help="grid of the --impl reference sample")
-    ap.add_argument("--workload", default="c4", choices=["c4", "c5a", "c5b"],
+    ap.add_argument("--workload", default="c4", choices=["c4", "c4roe", "c5a", "c5b"],
                     help="c4 (default): the configuration BASELINE.json's metric is quoted on; c5a / c5b: configs[4] "
                          "(density sine wave / rising thermal bubble with gravity), 1024^3 at 8 GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -210,7 +210,7 @@ static int bc_type(const char *name)
   return -1;
 }
 
-static int attach_one(SimulationObject *sim, int n)
+static int attach_one(SimulationObject *sim, int n, int nsims)
 {
   HyPar *s = &sim[n].solver;
   MPIVariables *mpi = &sim[n].mpi;
@@ -397,7 +397,7 @@ static int attach_one(SimulationObject *sim, int n)
   ref_VolumeIntegral          = s->VolumeIntegralFunction;
   s->VolumeIntegralFunction   = B200_VolumeIntegral;
   s->TimeIntegrate            = B200_TimeRK;        /* picked up by TimeInitialize.c:55 */
-  if (!mpi->rank) printf("hypar_b200 attached%s: %s, %s mode, device %d%s\n", (g.nsims > 1 ? " (one solver per simulation)" : ""),
+  if (!mpi->rank) printf("hypar_b200 attached%s: %s, %s mode, device %d%s\n", (nsims > 1 ? " (one solver per simulation)" : ""),
                          hpb_version(), g.resident ? "resident" : "host", c.device,
                          mpi->nproc > 1 ? ", in-library NCCL halo exchange" : "");
   return 0;
@@ -411,7 +411,7 @@ int hyparb200_attach(void *sims, int nsims)
   g.resident = !(mode && !strcmp(mode, "host"));
   g.nsims = 0;
   for (int n = 0; n < nsims; n++) {
-    if (attach_one(sim, n)) return 1;
+    if (attach_one(sim, n, nsims)) return 1;
     g.nsims = n + 1;
   }
   return 0;
