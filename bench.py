@@ -50,12 +50,12 @@ def weak_grid(n: int, ngpus: int):
     return [n * iproc[0], n * iproc[1], n * iproc[2]], list(iproc)
 
 
-def c4_inputs(size, iproc, dt=0.005, upwinding="rusanov", tstype="44"):
+def c4_inputs(size, iproc, dt=0.005, upwinding="rusanov", tstype="44", interp="components"):
     """solver.inp / boundary.inp / physics.inp / weno.inp of configuration C4 (hypar_b200.cases)."""
     from hypar_b200 import cases
     import numpy as np
     s = cases._solver(3, 5, size, "navierstokes3d", ts="rk", tstype=tstype, dt=dt, iproc=iproc,
-                      par_type="nonconservative-2stage", par_scheme="4")
+                      par_type="nonconservative-2stage", par_scheme="4", interp=interp)
     b = cases._zones(3, "periodic", [-1e3] * 3, [1e3] * 3)
     ph = {"gamma": 1.4, "upwinding": upwinding, "Pr": 0.72, "Minf": 0.3, "Re": 333.333333333333333}
     w = cases.weno_inp("mapped")
@@ -242,6 +242,10 @@ def workload_inputs(workload, size, iproc):
         # weno5 mapped, components, Roe, viscous, SSPRK3; its out.log: 256^3 on 64 V100, 82 ms per step)
         s, b, ph, w, x = c4_inputs(size, iproc, upwinding="roe", tstype="ssprk3")
         return s, b, ph, w, x, "C4-Roe NavierStokes3D WENO5(mapped)+Roe+viscous SSPRK3 (the reference's DNS_IsotropicTurbulenceDecay_CUDA setup)", "periodic"
+    if workload == "c4char":
+        # the same with characteristic-wise reconstruction (HyPar's default hyp_interp_type, ReadInputs.c:136)
+        s, b, ph, w, x = c4_inputs(size, iproc, upwinding="roe", tstype="ssprk3", interp="characteristic")
+        return s, b, ph, w, x, "C4-char NavierStokes3D characteristic WENO5(mapped)+Roe+viscous SSPRK3", "periodic"
     s, b, ph, w, x = c5_inputs(workload, size, iproc)
     label = ("C5a NavierStokes3D density sine wave, WENO5(JS)+Rusanov, inviscid, RK4" if workload == "c5a" else
              "C5b NavierStokes3D rising thermal bubble, WENO5(YC)+Rusanov, gravity (HB 2) source, SSPRK3")
@@ -270,7 +274,7 @@ class Run:
         # synthetic input, created on the device, staged into a pinned host array in HyPar's own layout
         self.u_host_t = torch.zeros(sv.npoints_local_wghosts * 5, dtype=torch.float64).pin_memory()
         self.u_host = self.u_host_t.numpy()
-        fld = synth_field_torch(x_loc, self.dev) if workload in ("c4", "c4roe") else synth_field_c5(workload, x_loc, self.dev)
+        fld = synth_field_torch(x_loc, self.dev) if workload in ("c4", "c4roe", "c4char") else synth_field_c5(workload, x_loc, self.dev)
         g, n = self.g, self.nloc
         self.u_host_t.view(n[2] + 2 * g, n[1] + 2 * g, n[0] + 2 * g, 5)[g:-g, g:-g, g:-g, :].copy_(fld)
         del fld
@@ -482,6 +486,7 @@ def gpu_arm(args):
         sub["c5b"]["scaling"] = "weak"
         if world == 1:
             sub["c4roe"] = sub_record("c4roe", size, iproc, rank, local_rank, world, args.steps, args.warmup, overlap)
+            sub["c4char"] = sub_record("c4char", size, iproc, rank, local_rank, world, args.steps, args.warmup, overlap)
 
     if rank != 0:
         if dist is not None:
@@ -539,6 +544,26 @@ def gpu_arm(args):
         except Exception as ex:  # the baseline is a report, not a dependency of the GPU number
             cpu["sample"] = f"failed: {ex}"
 
+    # ---- second baseline: the reference's OWN CUDA path (its *_GPU.cu kernels, unmodified, re-targeted from sm_70 to
+    # sm_100a: oracle/Makefile `refgpu`) on this GPU, HyPar's own per-iteration wall clock; 128^3 (its weight arrays alone
+    # are 12 x 3 x 5 doubles per point: 512^3 does not fit one GPU, and its 32-bit indices overflow beyond ~329^3)
+    ref_gpu = None
+    if not args.no_cpu and args.workload == "c4" and world == 1 and sub:
+        try:
+            import numpy as _np
+            from hypar_b200 import cases as _cases
+            from refgpu_bench import EXE as _REFGPU, run_ref_gpu
+            if os.access(_REFGPU, os.X_OK):
+                n_rg = args.ref_gpu_n
+                rr = run_ref_gpu(_cases.ns3d_turbulence((n_rg, n_rg, n_rg), "mapped"), 8, timeout=600)
+                w = rr["wctime"][2:] if len(rr["wctime"]) > 4 else rr["wctime"]
+                sec_rg = float(_np.median(w))
+                ref_gpu = {"value": n_rg ** 3 * NSTAGES / sec_rg / 1e6, "unit": UNIT, "grid": f"{n_rg}^3", "s_per_step": sec_rg,
+                           "kind": "reference CUDA path (use_gpu yes; unmodified sources built with -DHAVE_CUDA for sm_100a, "
+                                   "oracle/_ref/hypar_ref_gpu), same physics and scheme, HyPar's own wctime, median of 6 steps"}
+        except Exception as ex:
+            ref_gpu = {"value": None, "error": str(ex)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -562,7 +587,7 @@ def gpu_arm(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "cfl": cfl,
         "halo_traffic": (None if stepper is None else {"messages_sent_rank0": comm_msgs, "bytes_sent_rank0": comm_bytes}),
-        "strong": sub.get("strong"), "c5b": sub.get("c5b"), "c4roe": sub.get("c4roe"),
+        "strong": sub.get("strong"), "c5b": sub.get("c5b"), "c4roe": sub.get("c4roe"), "c4char": sub.get("c4char"), "ref_gpu_baseline": ref_gpu,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -578,7 +603,8 @@ def main():
     ap.add_argument("--n", type=int, default=512, help="points per dimension per GPU")
     ap.add_argument("--cpu-n", type=int, default=64, help="grid of the cpu_baseline sample")
     ap.add_argument("--ref-n", type=int, default=64, help="grid of the --impl reference sample")
-    ap.add_argument("--workload", default="c4", choices=["c4", "c4roe", "c5a", "c5b"],
+    ap.add_argument("--ref-gpu-n", type=int, default=128, help="grid of the ref_gpu_baseline run (the reference's own CUDA path)")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c4roe", "c4char", "c5a", "c5b"],
                     help="c4 (default): the configuration BASELINE.json's metric is quoted on; c5a / c5b: configs[4] "
                          "(density sine wave / rising thermal bubble with gravity), 1024^3 at 8 GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -1,7 +1,8 @@
 // sweep_fused.cu -- dispatch of the fused directional sweep kernels (sweep_fused.cuh).
 // Covered: component-wise WENO5 (all weight types, no_limiting) for LinearADR, NavierStokes2D and
-// NavierStokes3D with Rusanov or Roe upwinding (with or without gravity). Everything else (characteristic
-// reconstruction, rf-char / llf-char upwinding, Euler1D) is served by the generic per-interface kernels.
+// NavierStokes3D with Rusanov or Roe upwinding (with or without gravity), and characteristic-wise WENO5 for
+// NavierStokes2D / 3D without gravity. Everything else (rf-char / llf-char upwinding, Euler1D, characteristic
+// reconstruction with gravity) is served by the generic per-interface kernels.
 #include "sweep_fused.cuh"
 #include "sweep_tma.cuh"
 #include <cstdlib>
@@ -61,6 +62,8 @@ static bool get_map(hpb_solver* h, const void* ptr, int nf, int boxf, int kind, 
   return true;
 }
 
+bool tma_available() { return encode_fn() != nullptr; }
+
 bool tma_maps_for(hpb_solver* h, const SweepArgs& a, bool xs, bool grav, bool visc, TmaMaps* tm)
 {
   static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
@@ -90,8 +93,15 @@ bool fused_available(const hpb_solver* h)
   if (c.hyp_scheme != HPB_SCHEME_WENO5) return false;       // compact / linear schemes: reference-exact kernels only
   if (c.model == HPB_MODEL_BURGERS) return false;
   if (h->phys.advf != nullptr || c.advection_field != nullptr) return false;     // spatially varying advection: exact kernels
-  if (h->phys.interp_char) return false;
   if (c.model == HPB_MODEL_EULER1D) return false;
+  if (h->phys.interp_char) {
+    // characteristic-wise WENO5: NavierStokes2D / 3D without gravity, Roe or Rusanov, on the TMA-fed kernel only (even padded
+    // row length, 2-D or 3-D, driver entry point available)
+    if (c.model != HPB_MODEL_NS2D && c.model != HPB_MODEL_NS3D) return false;
+    if (h->phys.has_grav || c.use_fused == 2) return false;
+    if (c.upwind != HPB_UPWIND_RUSANOV && c.upwind != HPB_UPWIND_ROE) return false;
+    if ((h->geo.P[0] & 1) || h->geo.ndims < 2 || h->geo.g != HPB_G || !hpbf::tma_available()) return false;
+  }
   if ((c.model == HPB_MODEL_NS2D || c.model == HPB_MODEL_NS3D) && c.upwind != HPB_UPWIND_RUSANOV && c.upwind != HPB_UPWIND_ROE) return false;
   if (c.model == HPB_MODEL_LINEAR_ADR && c.nvars != 1) return false;
   if (c.model == HPB_MODEL_NS2D && h->phys.has_grav) return false;   // 2-D gravity source: reference-exact kernels only

@@ -31,7 +31,7 @@ static bool launch_one(hpb_solver* h, const SweepArgs& a)
 // TMA variant (sweep_tma.cuh): NavierStokes2D/3D, even padded row length, x-sweep overwriting / y-,z-sweeps
 // accumulating (what hyperbolic_fused always asks for). Returns false when not applicable: the caller then
 // launches k_sweep.
-template <int MODEL, int WT, bool XS, bool GRAV, bool VISC>
+template <int MODEL, int WT, bool XS, bool GRAV, bool VISC, bool CHR = false>
 static bool launch_one_tma(hpb_solver* h, const SweepArgs& a)
 {
   using LY = TmaLayout<MODEL, GRAV, VISC>;
@@ -42,7 +42,7 @@ static bool launch_one_tma(hpb_solver* h, const SweepArgs& a)
   TmaMaps tm;
   if (!tma_maps_for(h, a, XS, GRAV, VISC, &tm)) return false;
   static unsigned long long configured = 0ull;        // per device ordinal, as above
-  auto kern = k_sweep_tma<MODEL, WT, XS, GRAV, VISC>;
+  auto kern = k_sweep_tma<MODEL, WT, XS, GRAV, VISC, CHR>;
   const unsigned long long dbit = 1ull << (h->device & 63);
   if (!(configured & dbit)) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -65,6 +65,12 @@ static bool launch_one_tma(hpb_solver* h, const SweepArgs& a)
 template <int MODEL, int WT, bool MAPX, bool GRAV, bool VISC>
 static bool launch_pick(hpb_solver* h, const SweepArgs& a)
 {
+  if (MODEL != HPB_MODEL_LINEAR_ADR && h->phys.interp_char) {
+    // characteristic-wise reconstruction: the TMA-fed kernel only (fused_available has checked that it applies), no gravity
+    constexpr int M2 = (MODEL == HPB_MODEL_LINEAR_ADR) ? HPB_MODEL_NS3D : MODEL;
+    if (GRAV) return false;
+    return launch_one_tma<M2, WT, MAPX, false, VISC, true>(h, a);
+  }
   if (MODEL != HPB_MODEL_LINEAR_ADR && h->cfg.use_fused != 2) {
     constexpr int M2 = (MODEL == HPB_MODEL_LINEAR_ADR) ? HPB_MODEL_NS3D : MODEL;   // never instantiated for LinearADR
     if (launch_one_tma<M2, WT, MAPX, GRAV, VISC>(h, a)) return true;

@@ -43,6 +43,7 @@ struct TmaMaps {
 // host (sweep_fused.cu): descriptors for the arrays of one launch; false when the TMA path does not apply
 // (driver entry point missing, odd padded row length, misaligned array)
 bool tma_maps_for(hpb_solver* h, const SweepArgs& a, bool xs, bool grav, bool visc, TmaMaps* tm);
+bool tma_available();      // the driver's cuTensorMapEncodeTiled entry point was found (and HPB_NO_TMA is not set)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
@@ -117,7 +118,19 @@ struct TmaLayout {
   static constexpr size_t smem_bytes = sizeof(double) * (size_t)(o_sync + 4);
 };
 
-template <int MODEL, int WT, bool XS, bool GRAV, bool VISC>
+// CHR: characteristic-wise reconstruction (Interp1PrimFifthOrderWENOChar.c:86-198 with the weights of
+// WENOFifthOrderCalculateWeights.c:760-1440). The lane owns an INTERFACE instead of a centred stencil: the six cells
+// around it are projected on the left eigenvectors of the Roe average of the two adjacent cells, every characteristic
+// field is reconstructed from both sides (flux with flux weights, solution with solution weights), and the upwind flux is
+// formed in characteristic space -- 1/2 (fL + fR) - 1/2 |lambda| (uR - uL) per field (Roe; alpha instead of |lambda| for
+// Rusanov) -- so that ONE multiplication by the right eigenvectors returns the interface flux (the reference multiplies
+// fL, fR, uL, uR back one by one and Roe's scheme projects uR - uL again: the same numbers, L R = I). The eigenvectors
+// are applied in closed form (see roe_dissipation): with beta = (gamma-1)(ek q0 - v.qm + qE) and dn = vn q0 - q_n the
+// five amplitudes of a vector q are q0 - beta/a^2, (beta +- a dn)/(2 a^2) and q_t - v_t q0 -- the reference's rows up to
+// the sign of the shear rows, which cancels against the sign of the matching column (WENO is odd in its data and its
+// weights are even). Only (q0, beta, dn) of the six cells are kept in registers; the shear fields re-read their
+// component. No gravity in this variant.
+template <int MODEL, int WT, bool XS, bool GRAV, bool VISC, bool CHR = false>
 __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __grid_constant__ TmaMaps tm)
 {
   using LY = TmaLayout<MODEL, GRAV, VISC>;
@@ -292,9 +305,121 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
       }
     }
 
+    const int cc = rbase + l + 3;
+    double fh[NV], Sh[2] = { 0.0, 0.0 };
+#pragma unroll
+    for (int v = 0; v < NV; v++) fh[v] = 0.0;
+    if constexpr (CHR) {
+    // ---------------- P2+P3 (characteristic-wise): interface j-1/2 between cells jo = j-1 (position l+2) and j (l+3);
+    // stencil cells jo-2 .. jo+3 = positions l .. l+5
+    const bool if_ok = line_ok && j >= 0 && j <= N;
+    if (if_ok) {
+      const int cL = cc - 1, cR = cc;
+      const int p0 = rbase + l;
+      const double gm1 = gamma - 1.0;
+      const double tL = rec[LY::rSR * NREC + cL], tR = rec[LY::rSR * NREC + cR];
+      const double rs = rcp_fast(tL + tR);
+      double vsq = 0.0, vn = 0.0, vhat[3] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+      for (int k = 0; k < NDV; k++) {
+        const double v = (tL * rec[(LY::rVEL + k) * NREC + cL] + tR * rec[(LY::rVEL + k) * NREC + cR]) * rs;
+        vsq += v * v;
+        vhat[k] = v;
+        if (k == dir) vn = v;
+      }
+      const double H = (tL * rec[LY::rH * NREC + cL] + tR * rec[LY::rH * NREC + cR]) * rs;
+      const double ek = 0.5 * vsq;
+      const double a2 = gm1 * (H - ek);
+      const double aa = sqrt_fast(a2);
+      const double ia2 = rcp_fast(a2), hia2 = 0.5 * ia2;
+      // dissipation speed per field: Roe |lambda| with Harten's fix, or the Rusanov alpha for all of them
+      double lam0, lamm, lamp;
+      if (a.upw == 1) { lam0 = harten_abs(vn); lamm = harten_abs(vn - aa); lamp = harten_abs(vn + aa); }
+      else {
+        const double alpha = fmax(fmax(rec[LY::rA * NREC + cL], rec[LY::rA * NREC + cR]), aa + fabs(vn));
+        lam0 = lamm = lamp = alpha;
+      }
+      // Two passes over the six cells, flux first, then the solution (one pass keeps (q0, beta, dn) of the six cells in
+      // registers: 18 doubles; both at once would spill under the 128-register cap of two CTAs per SM). Per field k the
+      // pass returns fL + fR (flux) or uR - uL (solution); g[k] = (fL + fR) - lam_k (uR - uL) = 2 x the upwind amplitude.
+      // Field order: entropy, vn - a, vn + a, then the shear wave of every tangential component.
+      double g[5] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+      auto pass = [&](const bool isU) {
+        const int rQ = isU ? LY::rU : LY::rF;
+        double Q0[6], QB[6], QD[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          const int pc = p0 + c;
+          double qm[3] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+          for (int k = 0; k < NDV; k++) qm[k] = rec[(rQ + 1 + k) * NREC + pc];
+          // without gravity the mass flux is the normal momentum component itself (no record field for it)
+          const double q0 = (!isU && SKIPF0) ? rec[(LY::rU + 1 + dir) * NREC + pc] : rec[rQ * NREC + pc];
+          const double qE = rec[(rQ + NV - 1) * NREC + pc];
+          double vq = 0.0;
+#pragma unroll
+          for (int k = 0; k < NDV; k++) vq = fma(vhat[k], qm[k], vq);
+          double qn = 0.0;
+#pragma unroll
+          for (int k = 0; k < NDV; k++) if (k == dir) qn = qm[k];
+          Q0[c] = q0; QB[c] = gm1 * (fma(ek, q0, qE) - vq); QD[c] = fma(vn, q0, -qn);
+        }
+        auto both = [&](const double (&X)[6]) -> double {
+          double vL, vR, d0, d1, d2;
+          const double XL[5] = { X[0], X[1], X[2], X[3], X[4] }, XR[5] = { X[1], X[2], X[3], X[4], X[5] };
+          recon_pair<WT, false, true>(XL, XL, XL, a.ph.eps, vL, d0, d1, d2);    // left-biased value of the stencil centred on jo
+          recon_pair<WT, false, true>(XR, XR, XR, a.ph.eps, d0, vR, d1, d2);    // right-biased value of the stencil centred on j
+          return isU ? (vR - vL) : (vL + vR);
+        };
+        auto put = [&](int k, double val, double lam) { g[k] = isU ? fma(-lam, val, g[k]) : val; };
+        double X[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) X[c] = fma(-QB[c], ia2, Q0[c]);
+        put(0, both(X), lam0);
+#pragma unroll
+        for (int c = 0; c < 6; c++) X[c] = hia2 * fma(aa, QD[c], QB[c]);
+        put(1, both(X), lamm);
+#pragma unroll
+        for (int c = 0; c < 6; c++) X[c] = hia2 * fma(-aa, QD[c], QB[c]);
+        put(2, both(X), lamp);
+        int kf = 3;
+#pragma unroll
+        for (int k = 0; k < NDV; k++) {
+          if (k == dir) continue;
+#pragma unroll
+          for (int c = 0; c < 6; c++) X[c] = fma(-vhat[k], Q0[c], rec[(rQ + 1 + k) * NREC + p0 + c]);
+          put(kf, both(X), lam0);
+          kf++;
+        }
+      };
+      pass(false);
+      pass(true);
+      // back to conserved variables: one multiplication by the right eigenvectors
+      const double g0 = g[0], gm = g[1], gp = g[2];
+      const double gsum = g0 + gm + gp, gdif = aa * (gp - gm);
+      fh[0] = gsum;
+      double shear_e = 0.0;
+      {
+        int kf = 3;
+#pragma unroll
+        for (int k = 0; k < NDV; k++) {
+          if (k == dir) fh[1 + k] = fma(vhat[k], gsum, gdif);
+          else {
+            fh[1 + k] = fma(vhat[k], gsum, g[kf]);
+            shear_e = fma(vhat[k], g[kf], shear_e);
+            kf++;
+          }
+        }
+      }
+      fh[NV - 1] = fma(ek, g0, fma(H, gm + gp, fma(vn, gdif, shear_e)));
+      const int exo = xbase + l + 1;
+#pragma unroll
+      for (int v = 0; v < NV; v++) exF[v * NEX + exo] = fh[v];
+    }
+    __syncwarp();
+    } else {
     // ---------------- P2: both reconstructions of the centred stencil of cell j = 32m+1+l (position l+3)
     const bool rc_ok = line_ok && j >= -1 && j <= N;
-    const int cc = rbase + l + 3;
     double fRv[NV], uRv[NV], sR[2] = { 0.0, 0.0 };
 #pragma unroll
     for (int v = 0; v < NV; v++) { fRv[v] = 0.0; uRv[v] = 0.0; }
@@ -373,9 +498,6 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
 
     // ---------------- P3: interface j-1/2 (between cells j-1 and j): Rusanov flux
     const bool if_ok = line_ok && j >= 0 && j <= N;
-    double fh[NV], Sh[2] = { 0.0, 0.0 };
-#pragma unroll
-    for (int v = 0; v < NV; v++) fh[v] = 0.0;
     if (if_ok) {
       const int exl = xbase + l;              // left-biased values of cell j-1 (slot 0: carry)
       const int cL = cc - 1, cR = cc;
@@ -427,6 +549,8 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
     // carry of the left-biased values (slot 32 -> slot 0)
     if (l < LY::NFL) exL[l * NEX + xbase] = exL[l * NEX + xbase + TL];
     __syncwarp();
+
+    }
 
     // ---------------- P4: cell jo = j-1 = 32m+l (position l+2): interfaces j-1/2 (own) and j-3/2 (neighbour / carry)
     if (m >= 0) {
