@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhypar_b200.so")
+# HYPAR_B200_LIB: another build of the same library (kernel-variant A/B measurements: make -C hypar_b200/csrc OUT=... BUILD=...)
+LIB_PATH = os.environ.get("HYPAR_B200_LIB") or os.path.join(HERE, "libhypar_b200.so")
 
 MAX_NDIMS, MAX_NVARS, MAX_ZONES = 3, 5, 16
 

@@ -35,6 +35,16 @@
 #include <cuda.h>
 #include "sweep_fused.cuh"
 
+// x-sweep result stores: plain (default) or streaming (-DHPB_XS_STCS=1; measured in profiles/r02f_variants.txt)
+#ifndef HPB_XS_STCS
+#define HPB_XS_STCS 0
+#endif
+#if HPB_XS_STCS
+#define XS_STORE(ptr, val) __stcs((ptr), (val))
+#else
+#define XS_STORE(ptr, val) (*(ptr) = (val))
+#endif
+
 namespace hpbf {
 
 struct TmaMaps {
@@ -591,7 +601,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
         // first direction: overwrite; the warp's 32 cells are contiguous
         if (out_ok) {
 #pragma unroll
-          for (int v = 0; v < NV; v++) a.out[v * npg + pline + jo] = res[v];
+          for (int v = 0; v < NV; v++) XS_STORE(a.out + v * npg + pline + jo, res[v]);
         }
       } else {
         if (m >= 1) mbar_wait(free_bar, (unsigned)(m - 1) & 1u);     // the reduce of step m-1 has read the tile

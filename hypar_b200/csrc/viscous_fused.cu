@@ -155,6 +155,14 @@ __global__ void __launch_bounds__(128) k_qderiv3(const QD3Args a)
 #ifndef Q_MINB
 #define Q_MINB 1
 #endif
+#ifndef Q_STCS
+#define Q_STCS 0       // streaming stores measured no faster (profiles/r02f_variants.txt: 18.7 vs 18.3 ms per step)
+#endif
+#if Q_STCS
+#define QD_STORE(ptr, val) __stcs((ptr), (val))
+#else
+#define QD_STORE(ptr, val) (*(ptr) = (val))
+#endif
 constexpr int QTX = 32, QTY = Q_TY, QH = 2;
 constexpr int QSX = QTX + 2 * QH + 1;      // padded row (37): conflict-free column access is not needed, rows are read along x
 constexpr int QSY = QTY + 2 * QH;
@@ -274,9 +282,10 @@ __global__ void __launch_bounds__(QTX * QTY, Q_MINB) k_qderiv_int(const QD3Args 
         const double dx = central4(r[-2], r[-1], r[1], r[2]);
         const double dy = central4(r[-2 * QSX], r[-QSX], r[QSX], r[2 * QSX]);
         const double dz = central4(w[0][c], w[1][c], w[3][c], w[4][c]);
-        a.qd[(long long)(0 * 4 + c) * npg + p] = __dmul_rn(dx, muRe);
-        a.qd[(long long)(1 * 4 + c) * npg + p] = __dmul_rn(dy, muRe);
-        a.qd[(long long)(2 * 4 + c) * npg + p] = __dmul_rn(dz, muRe);
+        // streaming stores: 12 output streams per CTA that nothing re-reads before the whole array has passed through L2
+        QD_STORE(a.qd + (long long)(0 * 4 + c) * npg + p, __dmul_rn(dx, muRe));
+        QD_STORE(a.qd + (long long)(1 * 4 + c) * npg + p, __dmul_rn(dy, muRe));
+        QD_STORE(a.qd + (long long)(2 * 4 + c) * npg + p, __dmul_rn(dz, muRe));
       }
     }
   }

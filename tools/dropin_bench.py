@@ -30,7 +30,10 @@ def main():
     recs = []
     for n in args.n:
         case = cases.ns3d_turbulence((n, n, n), "mapped")
-        case.solver.update({"n_iter": args.steps, "screen_op_iter": args.steps, "file_op_iter": 10 * args.steps, "op_overwrite": "yes"})
+        # no screen / file output inside the timed steps: on a screen-output step HyPar itself copies u, forms u - u_prev and sums
+        # its squares on the host (TimePreStep.c:84, TimePostStep.c:44-63: ~0.5 s at 256^3, single-threaded index arithmetic) --
+        # the reference's own use_gpu path skips that norm altogether (TimePostStep.c:38-40 sets it to -1)
+        case.solver.update({"n_iter": args.steps, "screen_op_iter": 1000 * args.steps, "file_op_iter": 1000 * args.steps, "op_overwrite": "yes"})
         d = tempfile.mkdtemp(prefix="hpbdropin_")
         try:
             case.write(d)
