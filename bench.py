@@ -255,7 +255,7 @@ def workload_inputs(workload, size, iproc):
 class Run:
     """one workload on this rank's GPU: solver (+ NCCL transport when decomposed), synthetic field, device-timed steps"""
 
-    def __init__(self, workload, size, iproc, rank, local_rank, world, overlap=True):
+    def __init__(self, workload, size, iproc, rank, local_rank, world, overlap=True, use_fused=True):
         import torch
         from hypar_b200.solver import Solver
         self.torch, self.world, self.rank = torch, world, rank
@@ -263,10 +263,10 @@ class Run:
         self.size, self.iproc, self.workload = list(size), list(iproc), workload
         s, b, ph, w, x, self.label, self.bc = workload_inputs(workload, size, iproc)
         if world == 1:
-            self.sv, self.stepper = Solver(s, b, ph, w, x, rank=0, device=local_rank), None
+            self.sv, self.stepper = Solver(s, b, ph, w, x, rank=0, device=local_rank, use_fused=use_fused), None
         else:
             from hypar_b200.multigpu import DistributedSolver
-            self.stepper = DistributedSolver(s, b, ph, w, x, rank=rank, device=local_rank, overlap=overlap)
+            self.stepper = DistributedSolver(s, b, ph, w, x, rank=rank, device=local_rank, overlap=overlap, use_fused=use_fused)
             self.sv = self.stepper.solver
         sv = self.sv
         self.g, self.nloc = sv.ghosts, sv.dim_local
@@ -332,9 +332,9 @@ class Run:
         self.torch.cuda.empty_cache()
 
 
-def sub_record(workload, size, iproc, rank, local_rank, world, steps, warmup, overlap):
+def sub_record(workload, size, iproc, rank, local_rank, world, steps, warmup, overlap, use_fused=True):
     """a second workload measured in the same process after the main one (device-resident loop only)"""
-    R = Run(workload, size, iproc, rank, local_rank, world, overlap=overlap)
+    R = Run(workload, size, iproc, rank, local_rank, world, overlap=overlap, use_fused=use_fused)
     ms, val, cfl = R.device_loop(steps, warmup)
     rec = {"workload": f"{R.label}, {size[0]}x{size[1]}x{size[2]} {R.bc}", "iproc": list(iproc),
            "points_per_gpu": "x".join(str(v) for v in R.nloc), "value": val, "unit": UNIT, "ms_per_step": ms / steps,
@@ -487,6 +487,9 @@ def gpu_arm(args):
         if world == 1:
             sub["c4roe"] = sub_record("c4roe", size, iproc, rank, local_rank, world, args.steps, args.warmup, overlap)
             sub["c4char"] = sub_record("c4char", size, iproc, rank, local_rank, world, args.steps, args.warmup, overlap)
+            # the reference-exact path (use_fused = 0: one thread per interface, no FMA contraction, bit-identical to the
+            # reference) on the same physics, 256^3 (its interface / weight scratch is sized for parity runs, not for 512^3)
+            sub["c4_exact_path"] = sub_record("c4", [256] * 3, iproc, rank, local_rank, world, 3, 2, overlap, use_fused=False)
 
     if rank != 0:
         if dist is not None:
@@ -587,7 +590,7 @@ def gpu_arm(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "cfl": cfl,
         "halo_traffic": (None if stepper is None else {"messages_sent_rank0": comm_msgs, "bytes_sent_rank0": comm_bytes}),
-        "strong": sub.get("strong"), "c5b": sub.get("c5b"), "c4roe": sub.get("c4roe"), "c4char": sub.get("c4char"), "ref_gpu_baseline": ref_gpu,
+        "strong": sub.get("strong"), "c5b": sub.get("c5b"), "c4roe": sub.get("c4roe"), "c4char": sub.get("c4char"), "c4_exact_path": sub.get("c4_exact_path"), "ref_gpu_baseline": ref_gpu,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

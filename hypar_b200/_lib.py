@@ -58,7 +58,7 @@ SYMBOLS = [
     "hpb_dev_set_solution", "hpb_dev_get_solution", "hpb_dev_fill_solution_from_global", "hpb_TimeStep",
     "hpb_TimeSteps", "hpb_current_time", "hpb_dev_ComputeCFL", "hpb_dev_StepNormSumSq", "hpb_dev_RHS",
     "hpb_comm_get_unique_id", "hpb_comm_nccl_version", "hpb_comm_init_nccl", "hpb_comm_init_local", "hpb_comm_finalize",
-    "hpb_comm_kind", "hpb_comm_allreduce", "hpb_comm_stats", "hpb_exchange_plan", "hpb_ExchangeBoundariesnD",
+    "hpb_comm_kind", "hpb_comm_allreduce", "hpb_comm_stats", "hpb_exchange_plan", "hpb_ExchangeBoundariesnD", "hpb_ExchangeBoundariesLocal",
     "hpb_TimeStepDistributed", "hpb_TimeStepsDistributed", "hpb_RHSFunctionDistributed", "hpb_TimeStepsLocal",
     "hpb_RHSFunctionLocal", "hpb_set_overlap", "hpb_stage_overlap_supported",
     "hpb_dev_get_stage_rhs", "hpb_nstages", "hpb_needs_viscous_exchange",
@@ -146,6 +146,7 @@ def load():
     L.hpb_TimeStepsDistributed.argtypes = [vp, C.c_int]
     L.hpb_TimeStepsLocal.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
     L.hpb_RHSFunctionLocal.argtypes = [C.POINTER(vp), C.c_int]
+    L.hpb_ExchangeBoundariesLocal.argtypes = [C.POINTER(vp), C.c_int]
     L.hpb_set_overlap.argtypes = [vp, C.c_int]
     L.hpb_dev_get_stage_rhs.argtypes = [vp, C.c_int, dp]
     L.hpb_dev_VolumeIntegral.argtypes = [vp, dp]

@@ -593,7 +593,8 @@ extern "C" int hpb_InterpolateInterfacesHyp(hpb_solver* h, double* fI, const dou
       for (int b = 0; b < 4; b++) for (long long i = 0; i < n; i++) {
         const long long q = i % nq;
         const long long iI = (d == 0 ? q % M0 : d == 1 ? (q / M0) % M1 : q / (M0 * M1));
-        const bool cr = (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5) && iI != 0 && iI != G.N[d];
+        const bool bnd = (iI == 0 && G.lo_phys[d]) || (iI == G.N[d] && G.hi_phys[d]);
+        const bool cr = (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5) && !bnd;
         w[(size_t)(woff(h, d) + (3*b+0)*n + i)] = cr ? 0.2 : 0.1; w[(size_t)(woff(h, d) + (3*b+1)*n + i)] = cr ? 0.5 : 0.6;
         w[(size_t)(woff(h, d) + (3*b+2)*n + i)] = 0.3;
       }
@@ -1032,7 +1033,27 @@ static int dist_stage(Grp& G, int s)
       }
     }
   } else {
-    EACH(h) { TRY(need_device(h)); TRY(rhs_part_a(h, h->U_cur, h->d_Udot[s])); }
+    const hpb_solver* h0 = G.hs[0];
+    bool split_compact = false;       // a compact scheme whose grid lines are split among ranks: the reconstructions couple the ranks
+    if (h0->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h0->cfg.hyp_scheme == HPB_SCHEME_CUPW5)
+      for (int d = 0; d < h0->geo.ndims; d++) split_compact = split_compact || h0->cfg.iproc[d] > 1;
+    if (split_compact) {
+      std::vector<const double*> U(G.n);
+      std::vector<double*> out(G.n), src(G.n);
+      EACH(h) {
+        TRY(need_device(h)); TRY(ensure_generic(h));
+        if (h->d_src) hpbk::set_zero(h, h->d_src, ncell(h));
+        U[r_] = h->U_cur; out[r_] = h->d_Udot[s]; src[r_] = h->d_src;
+      }
+      TRY(hpbk::hyperbolic_pieces_group(G.hs, G.n, U.data(), out.data(), /*negate=*/true, /*with_source=*/true, src.data()));
+      EACH(h) {
+        TRY(need_device(h));
+        if (hpbk::has_sponge(h)) hpbk::sponge_source(h, h->U_cur, h->d_src);
+        if (viscous_on(h)) hpbk::parabolic_phase1(h, h->U_cur);
+      }
+    } else {
+      EACH(h) { TRY(need_device(h)); TRY(rhs_part_a(h, h->U_cur, h->d_Udot[s])); }
+    }
     if (visc) {
       for (int slot = hpbc::SLOT_Q0; slot <= hpbc::SLOT_Q12; slot++) {
         TRY(hpbc::fill_begin(G.hs, G.n, slot));
@@ -1140,6 +1161,15 @@ extern "C" int hpb_ExchangeBoundariesnD(hpb_solver* h)
   TRY(exchange_u_serial(G, false));
   h->u_halo_valid = true;
   return sync_check(h, "ExchangeBoundariesnD");
+}
+
+extern "C" int hpb_ExchangeBoundariesLocal(hpb_solver** hs, int nranks)
+{
+  Grp G{ hs, nranks };
+  TRY(dist_check(G, "ExchangeBoundariesLocal", 2));
+  TRY(exchange_u_serial(G, false));
+  EACH(h) { h->u_halo_valid = true; TRY(sync_check(h, "ExchangeBoundariesLocal")); }
+  return HPB_OK;
 }
 
 extern "C" int hpb_set_overlap(hpb_solver* h, int on)

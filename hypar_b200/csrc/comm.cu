@@ -394,6 +394,100 @@ int xchg_wait(hpb_solver** hs, int n, int slot)
   return HPB_OK;
 }
 
+// ---- small messages along one dimension's line of ranks (compact schemes across ranks). They run on the COMPUTE
+// streams: the solve they serve is a chain of tiny dependent steps. In-process transport: all streams are
+// synchronised around the copies (this is the reference-exact path: simplicity over speed).
+int line_rank(const hpb_solver* h, int dir, int k)
+{
+  int ip[3] = { h->ip[0], h->ip[1], h->ip[2] };
+  ip[dir] = k;
+  return hpb_rank1d(h->geo.ndims, h->cfg.iproc, ip);
+}
+
+static int local_sync_all(hpb_solver** hs, int n)
+{
+  for (int r = 0; r < n; r++) {
+    HPB_CUDA(cudaSetDevice(hs[r]->device));
+    HPB_CUDA(cudaStreamSynchronize(hs[r]->stream));
+  }
+  return HPB_OK;
+}
+
+int line_swap(hpb_solver** hs, int n, int dir, double* const* send_lo, double* const* send_hi, double* const* recv_lo,
+              double* const* recv_hi, const long long* counts, const int* active)
+{
+  if (n < 1 || !hs[0]->comm) return hpb_fail(HPB_ERR_INVALID, "line exchange: no transport");
+  const int kind = hs[0]->comm->kind;
+  if (kind == 2) { int rc = local_sync_all(hs, n); if (rc) return rc; }
+  for (int r = 0; r < n; r++) {
+    hpb_solver* h = hs[r];
+    if (active && !active[r]) continue;
+    HPB_CUDA(cudaSetDevice(h->device));
+    const int ip = h->ip[dir], np = h->cfg.iproc[dir];
+    const int lo = ip > 0 ? line_rank(h, dir, ip - 1) : -1, hi = ip < np - 1 ? line_rank(h, dir, ip + 1) : -1;
+    const size_t count = (size_t)counts[r];          // the members of one line share their transverse extents
+    if (kind == 1) {
+      HPB_NCCL(g_nccl.GroupStart());
+      if (lo >= 0 && send_lo && send_lo[r]) HPB_NCCL(g_nccl.Send(send_lo[r], count, NCCL_FLOAT64, lo, h->comm->nccl, h->stream));
+      if (hi >= 0 && send_hi && send_hi[r]) HPB_NCCL(g_nccl.Send(send_hi[r], count, NCCL_FLOAT64, hi, h->comm->nccl, h->stream));
+      if (lo >= 0 && recv_lo && recv_lo[r]) HPB_NCCL(g_nccl.Recv(recv_lo[r], count, NCCL_FLOAT64, lo, h->comm->nccl, h->stream));
+      if (hi >= 0 && recv_hi && recv_hi[r]) HPB_NCCL(g_nccl.Recv(recv_hi[r], count, NCCL_FLOAT64, hi, h->comm->nccl, h->stream));
+      HPB_NCCL(g_nccl.GroupEnd());
+    } else {
+      // pull: my recv_lo <- the low neighbour's send_hi, my recv_hi <- the high neighbour's send_lo
+      if (lo >= 0 && recv_lo && recv_lo[r] && send_hi && send_hi[lo])
+        HPB_CUDA(cudaMemcpyAsync(recv_lo[r], send_hi[lo], count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      if (hi >= 0 && recv_hi && recv_hi[r] && send_lo && send_lo[hi])
+        HPB_CUDA(cudaMemcpyAsync(recv_hi[r], send_lo[hi], count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->xchg_count += (lo >= 0 && send_lo ? 1 : 0) + (hi >= 0 && send_hi ? 1 : 0);
+  }
+  if (kind == 2) { int rc = local_sync_all(hs, n); if (rc) return rc; }
+  return HPB_OK;
+}
+
+int line_shift(hpb_solver** hs, int n, int dir, int step, double* const* send, double* const* recv, const long long* counts, const int* active)
+{
+  // step +1: to the high neighbour (received from the low one); step -1: to the low neighbour
+  if (step > 0) return line_swap(hs, n, dir, nullptr, send, recv, nullptr, counts, active);
+  return line_swap(hs, n, dir, send, nullptr, nullptr, recv, counts, active);
+}
+
+int line_gather(hpb_solver** hs, int n, int dir, double* const* d_val, double* const* d_scratch, double (*h_out)[64], const int* active)
+{
+  if (n < 1 || !hs[0]->comm) return hpb_fail(HPB_ERR_INVALID, "line gather: no transport");
+  const int kind = hs[0]->comm->kind;
+  if (kind == 2) {
+    int rc = local_sync_all(hs, n); if (rc) return rc;
+    for (int r = 0; r < n; r++) {
+      if (active && !active[r]) continue;
+      hpb_solver* h = hs[r];
+      for (int k = 0; k < h->cfg.iproc[dir]; k++) {
+        hpb_solver* m = hs[line_rank(h, dir, k)];
+        HPB_CUDA(cudaSetDevice(m->device));
+        HPB_CUDA(cudaMemcpy(&h_out[r][k], d_val[line_rank(h, dir, k)], sizeof(double), cudaMemcpyDeviceToHost));
+      }
+    }
+    return HPB_OK;
+  }
+  hpb_solver* h = hs[0];
+  if (active && !active[0]) return HPB_OK;
+  HPB_CUDA(cudaSetDevice(h->device));
+  const int np = h->cfg.iproc[dir], me = h->ip[dir];
+  HPB_NCCL(g_nccl.GroupStart());
+  for (int k = 0; k < np; k++) if (k != me) {
+    const int peer = line_rank(h, dir, k);
+    HPB_NCCL(g_nccl.Send(d_val[0], 1, NCCL_FLOAT64, peer, h->comm->nccl, h->stream));
+    HPB_NCCL(g_nccl.Recv(d_scratch[0] + k, 1, NCCL_FLOAT64, peer, h->comm->nccl, h->stream));
+  }
+  HPB_NCCL(g_nccl.GroupEnd());
+  HPB_CUDA(cudaMemcpyAsync(d_scratch[0] + me, d_val[0], sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  HPB_CUDA(cudaMemcpyAsync(h->h_mr, d_scratch[0], np * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  HPB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < np; k++) h_out[0][k] = h->h_mr[k];
+  return HPB_OK;
+}
+
 int comm_free(hpb_solver* h)
 {
   if (!h) return HPB_OK;

@@ -96,10 +96,14 @@ int hpb_setup_host(hpb_solver* h)
                     c.hyp_scheme);
   if (c.muscl_limiter < HPB_LIMITER_GMM || c.muscl_limiter > HPB_LIMITER_SUPERBEE)
     return hpb_fail(HPB_ERR_INVALID, "muscl limiter %d not supported (gmm, minmod, vanleer, superbee)", c.muscl_limiter);
+  if ((c.hyp_scheme == HPB_SCHEME_CRWENO5 || c.hyp_scheme == HPB_SCHEME_CUPW5) && c.interp_char)
+    for (int d = 0; d < nd; d++)
+      if (c.iproc[d] != 1)     // blocktridiagLU.c stages 2-3 (block reduced system across ranks) are not built
+        return hpb_fail(HPB_ERR_INVALID, "characteristic compact schemes (crweno5, cupw5) need iproc = 1 along every dimension "
+                                         "(component-wise ones run decomposed)");
   if (c.hyp_scheme == HPB_SCHEME_CRWENO5 || c.hyp_scheme == HPB_SCHEME_CUPW5)
     for (int d = 0; d < nd; d++)
-      if (c.iproc[d] != 1)     // tridiagLU.c stages 2-3: reduced system across ranks, iterative by default
-        return hpb_fail(HPB_ERR_INVALID, "compact schemes (crweno5, cupw5) need iproc = 1 along every dimension");
+      if (c.iproc[d] > 64) return hpb_fail(HPB_ERR_INVALID, "compact schemes: at most 64 ranks along one dimension");
   if (c.nzones > HPB_MAX_ZONES) return hpb_fail(HPB_ERR_INVALID, "too many boundary zones");
   int nranks = 1;
   for (int d = 0; d < nd; d++) {
@@ -124,6 +128,8 @@ int hpb_setup_host(hpb_solver* h)
     G.xoff[d] = xo;
     xo += G.P[d];
   }
+  for (int d = 0; d < 3; d++) { G.lo_phys[d] = 1; G.hi_phys[d] = 1; }
+  for (int d = 0; d < nd; d++) { G.lo_phys[d] = (h->ip[d] == 0); G.hi_phys[d] = (h->ip[d] == c.iproc[d] - 1); }
   G.st[0] = 1; G.st[1] = G.P[0]; G.st[2] = (long long)G.P[0] * G.P[1];
   G.npg = (long long)G.P[0] * G.P[1] * G.P[2];
 

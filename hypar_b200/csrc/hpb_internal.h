@@ -21,6 +21,8 @@ struct Geom {
   long long st[3];     // stride of dim d in cells
   long long npg;       // points with ghosts
   int xoff[3];         // offset of dim d in the concatenated x/dxinv arrays
+  int lo_phys[3], hi_phys[3];   // this block's low / high face of dim d lies on the domain boundary (ip == 0 / ip == iproc-1):
+                                // where the compact schemes close their systems (Interp1PrimFifthOrderCRWENO.c:158-160)
 };
 
 struct Phys {
@@ -88,6 +90,8 @@ struct hpb_solver {
   double *d_cell[2] = {nullptr, nullptr};
   double *d_tri[3] = {nullptr, nullptr, nullptr};
   double *d_bx = nullptr;          // characteristic compact schemes: right-hand side / solution of the block systems
+  double *d_mr = nullptr;          // compact schemes across ranks (compact_mr.cu): exchange rows, Jacobi scratch; 16 x systems
+  double *h_mr = nullptr;          // pinned: norms of the reduced-system iteration
   int *d_err = nullptr;
   // pipelined host-array stepping (hpb_pipe_*): copy streams, AoS staging of the incoming / outgoing field, events
   // [in ready, in free, out ready, out free]
@@ -156,6 +160,9 @@ void hyperbolic(hpb_solver* h, const double* u, double* out, bool negate, bool w
 void hyperbolic_generic(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src);
 // schemes other than WENO5: the reference's own sequence of pieces (HyperbolicFunction.c:167-222) with stored weights
 void hyperbolic_pieces(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src);
+// the same for a group of ranks (hpbc, below): the reconstructions of a compact scheme couple the ranks of a grid line
+int  hyperbolic_pieces_group(hpb_solver** hs, int n, const double* const* u, double* const* out, bool negate, bool with_source,
+                             double* const* src);
 int  tridiag_error(hpb_solver* h);      // 1 if a tridiagonal solve met a zero pivot since the last call (synchronises)
 // fused sweeps (sweep_fused.cu); qd != nullptr: the NavierStokes3D viscous terms are evaluated inside the sweeps
 bool fused_available(const hpb_solver* h);
@@ -214,4 +221,15 @@ int  xchg_wait(hpb_solver** hs, int n, int slot);    // the compute stream waits
 void unpack_faces(hpb_solver* h, int slot, double* a);
 int  comm_free(hpb_solver* h);
 bool comm_ready(const hpb_solver* h);
+// small messages along one dimension's line of ranks (compact schemes across ranks, compact_mr.cu), on the compute
+// streams. active[r] = 0 skips group member r.
+int  line_rank(const hpb_solver* h, int dir, int k);            // world rank of the block with ip[dir] = k on this rank's line
+// every member sends `send` (count doubles) to ip + step and receives into `recv` from ip - step (no wrap-around; a member
+// without the source keeps its recv buffer as it is)
+int  line_shift(hpb_solver** hs, int n, int dir, int step, double* const* send, double* const* recv, const long long* counts, const int* active);
+// both directions at once: recv_lo <- the low neighbour's send_hi, recv_hi <- the high neighbour's send_lo
+int  line_swap(hpb_solver** hs, int n, int dir, double* const* send_lo, double* const* send_hi, double* const* recv_lo,
+               double* const* recv_hi, const long long* counts, const int* active);
+// one device double per member -> on the host the values of all members of the member's line, ordered by ip[dir]
+int  line_gather(hpb_solver** hs, int n, int dir, double* const* d_val, double* const* d_scratch, double (*h_out)[64], const int* active);
 }

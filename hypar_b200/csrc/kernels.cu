@@ -3,6 +3,8 @@
 // and characteristic WENO5, Rusanov/Roe), flux divergence + gravity source, Navier-Stokes viscous
 // terms, LinearADR diffusion, RK stage updates and reductions.
 // The fused per-cell sweep kernels for the component-wise hot configurations live in sweep_fused.cu.
+#include <array>
+#include <vector>
 #include "hpb_internal.h"
 #include "physics.cuh"
 #include "weno.cuh"
@@ -818,11 +820,12 @@ __global__ void k_weights(Geom G, Phys ph, const double* __restrict__ fC, const 
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
   if (i0 >= M0) return;
   // optimal weights: WENO5 (0.1,0.6,0.3); CRWENO5 (0.2,0.5,0.3) except on the two physical-boundary interfaces
-  // (WENOFifthOrderCalculateWeights.c:205-225; compact schemes run with iproc = 1, so these are interfaces 0 and N)
+  // (WENOFifthOrderCalculateWeights.c:205-225: interface 0 of the first block and interface N of the last one along dir)
   double c1 = 0.1, c2 = 0.6, c3 = 0.3;
   {
     const int iI = (dir == 0 ? i0 : dir == 1 ? i1 : i2);
-    if (ph.scheme == HPB_SCHEME_CRWENO5 && iI != 0 && iI != G.N[dir]) { c1 = 0.2; c2 = 0.5; c3 = 0.3; }
+    const bool bnd = (iI == 0 && G.lo_phys[dir]) || (iI == G.N[dir] && G.hi_phys[dir]);
+    if (ph.scheme == HPB_SCHEME_CRWENO5 && !bnd) { c1 = 0.2; c2 = 0.5; c3 = 0.3; }
   }
   const long long q = i0 + (long long)M0 * (i1 + (long long)M1 * i2);
   const long long ni = (long long)M0 * M1 * M2;
@@ -954,7 +957,7 @@ __global__ void k_compact_rows(Geom G, Phys ph, const double* __restrict__ fC, c
   const long long pm1 = cell_index(G, i0, i1, i2) - st;
   const int blk = (upw < 0 ? 2 : 0) + (uflag ? 1 : 0);
   const int iI = (dir == 0 ? i0 : dir == 1 ? i1 : i2);
-  const bool bnd = (iI == 0) || (iI == G.N[dir]);
+  const bool bnd = (iI == 0 && G.lo_phys[dir]) || (iI == G.N[dir] && G.hi_phys[dir]);
   long long ps[5];
   for (int k = 0; k < 5; k++) ps[k] = (upw > 0) ? pm1 + (k - 2) * st : pm1 + (3 - k) * st;
   for (int v = 0; v < NV; v++) {
@@ -1035,6 +1038,163 @@ __global__ void k_tridiag(Geom G, int dir, double* __restrict__ A, double* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// The same systems when the grid line is split among ranks: TridiagLU/tridiagLU.c:84-274 with all four stages, the
+// reduced system (one row per rank) solved by TridiagLU/tridiagIterJacobi.c:64-238 as the reference does by default
+// (tridiagLUInit.c:70-76: jacobi, maxiter 10, atol 1e-12, rtol 1e-10, norm evaluated), and the hand-over of the shared
+// interface of Interp1PrimFifthOrderCRWENO.c:206-223. One thread per system; `n` = rows on this rank (N, or N + 1 on
+// the last rank of the line); `first` = this is the first rank of the line (tridiagLU's rank == 0). Exchange buffers:
+// [k * nsys + sys]. Operation order follows the reference line by line (compiled without FMA contraction).
+struct TriLine {
+  int T0, T1; long long s0, s1, qs, ni;
+};
+__device__ __forceinline__ TriLine tri_line(const Geom& G, int dir)
+{
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  TriLine L;
+  L.ni = (long long)M0 * M1 * M2;
+  if (dir == 0)      { L.T0 = M1; L.T1 = M2; L.s0 = M0;  L.s1 = (long long)M0 * M1; L.qs = 1; }
+  else if (dir == 1) { L.T0 = M0; L.T1 = M2; L.s0 = 1;   L.s1 = (long long)M0 * M1; L.qs = M0; }
+  else               { L.T0 = M0; L.T1 = M1; L.s0 = 1;   L.s1 = M0;                 L.qs = (long long)M0 * M1; }
+  return L;
+}
+// system index and base offset of this thread's system; false when out of range
+__device__ __forceinline__ bool tri_sys(const Geom& G, int dir, const TriLine& L, long long& sys, long long& base)
+{
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y, v = blockIdx.z;
+  if (t0 >= L.T0 || t1 >= L.T1) return false;
+  sys = t0 + (long long)L.T0 * (t1 + (long long)L.T1 * v);
+  base = v * L.ni + t0 * L.s0 + t1 * L.s1;
+  return true;
+}
+
+// stage 1 (tridiagLU.c:140-157) + the last row packed for the next rank (:166-171)
+__global__ void k_mr_stage1(Geom G, int dir, int n, int first, double* __restrict__ A, double* __restrict__ B, double* __restrict__ Cc,
+                            double* __restrict__ X, double* __restrict__ sendrow, long long nsys, int* __restrict__ err)
+{
+  const TriLine L = tri_line(G, dir);
+  long long sys, base;
+  if (!tri_sys(G, dir, L, sys, base)) return;
+  double *a = A + base, *b = B + base, *c = Cc + base, *x = X + base;
+  const long long qs = L.qs;
+  for (int i = (first ? 1 : 2); i < n; i++) {
+    const double bm = b[(i - 1) * qs];
+    if (bm == 0) { *err = 1; return; }
+    const double factor = a[i * qs] / bm;
+    b[i * qs] -= factor * c[(i - 1) * qs];
+    a[i * qs] = -factor * a[(i - 1) * qs];
+    x[i * qs] -= factor * x[(i - 1) * qs];
+    if (!first) {
+      const double f2 = c[0] / b[(i - 1) * qs];
+      c[0]  = -f2 * c[(i - 1) * qs];
+      b[0] -=  f2 * a[(i - 1) * qs];
+      x[0] -=  f2 * x[(i - 1) * qs];
+    }
+  }
+  sendrow[0 * nsys + sys] = a[(n - 1) * qs];
+  sendrow[1 * nsys + sys] = b[(n - 1) * qs];
+  sendrow[2 * nsys + sys] = c[(n - 1) * qs];
+  sendrow[3 * nsys + sys] = x[(n - 1) * qs];
+}
+
+// stage 2 (tridiagLU.c:182-202), ranks other than the first; then the start of the Jacobi iteration on the reduced row
+// (tridiagIterJacobi.c:97-113: diagonal check, rhs saved, initial guess x = rhs / b). red = [rhs | x | sendL=sendR | recvL | recvR]
+__global__ void k_mr_stage2(Geom G, int dir, int n, int first, double atol, double* __restrict__ A, double* __restrict__ B,
+                            double* __restrict__ Cc, double* __restrict__ X, const double* __restrict__ recvrow,
+                            double* __restrict__ red, long long nsys, int* __restrict__ err)
+{
+  const TriLine L = tri_line(G, dir);
+  long long sys, base;
+  if (!tri_sys(G, dir, L, sys, base)) return;
+  if (first) {                       // tridiagLU.c:218: the first rank enters the reduced system with (0, 1, 0 | 0)
+    red[0 * nsys + sys] = 0.0; red[1 * nsys + sys] = 0.0 / 1.0; red[2 * nsys + sys] = 0.0 / 1.0;
+    return;
+  }
+  double *a = A + base, *b = B + base, *c = Cc + base, *x = X + base;
+  const long long qs = L.qs;
+  const double am1 = recvrow[0 * nsys + sys], bm1 = recvrow[1 * nsys + sys], cm1 = recvrow[2 * nsys + sys], xm1 = recvrow[3 * nsys + sys];
+  if (bm1 == 0) { *err = 1; return; }
+  double factor = a[0] / bm1;
+  b[0] -= factor * cm1;
+  a[0]  = -factor * am1;
+  x[0] -= factor * xm1;
+  if (b[(n - 1) * qs] == 0) { *err = 1; return; }
+  factor = c[0] / b[(n - 1) * qs];
+  b[0] -= factor * a[(n - 1) * qs];
+  c[0]  = -factor * c[(n - 1) * qs];
+  x[0] -= factor * x[(n - 1) * qs];
+  if (b[0] * b[0] < atol * atol) { *err = 2; return; }
+  red[0 * nsys + sys] = x[0];            // rhs
+  x[0] /= b[0];                          // initial guess
+  red[1 * nsys + sys] = x[0];
+  red[2 * nsys + sys] = x[0];            // what the neighbours receive
+}
+
+// one Jacobi iteration on the reduced row (tridiagIterJacobi.c:150-160 norm, :186 update): pass 0 = this rank's part of
+// the squared residual norm (summed over the systems by a fixed tree), pass 1 = the correction
+__global__ void k_mr_jacobi(Geom G, int dir, int first, int pass, const double* __restrict__ A, const double* __restrict__ B,
+                            const double* __restrict__ Cc, double* __restrict__ X, double* __restrict__ red, long long nsys,
+                            double* __restrict__ part)
+{
+  const TriLine L = tri_line(G, dir);
+  long long sys, base;
+  double contrib = 0.0;
+  if (tri_sys(G, dir, L, sys, base) && !first) {
+    const double a = A[base], b = B[base], c = Cc[base];
+    const double rhs = red[0 * nsys + sys], rl = red[3 * nsys + sys], rr = red[4 * nsys + sys];
+    double* x = X + base;
+    if (pass == 0) {
+      const double r = a * rl + b * x[0] + c * rr - rhs;
+      contrib = r * r;
+    } else {
+      x[0] = (rhs - a * rl - c * rr) / b;
+      red[1 * nsys + sys] = x[0];
+      red[2 * nsys + sys] = x[0];
+    }
+  }
+  if (pass == 0) {
+    const double v = block_reduce(contrib, false);
+    if (threadIdx.x == 0) part[blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z)] = v;
+  }
+}
+__global__ void k_mr_sum(const double* __restrict__ part, long long n, double* __restrict__ out)
+{
+  double v = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
+  v = block_reduce(v, false);
+  if (threadIdx.x == 0) out[0] = v;
+}
+
+// stage 4 (tridiagLU.c:244-257): xp1 = the next rank's reduced solution (0 on the last rank); then the first-interface
+// solution packed for the previous rank (Interp1PrimFifthOrderCRWENO.c:214)
+__global__ void k_mr_stage4(Geom G, int dir, int n, int first, const double* __restrict__ A, const double* __restrict__ B,
+                            const double* __restrict__ Cc, double* __restrict__ X, const double* __restrict__ xp1,
+                            double* __restrict__ sendfirst, long long nsys, int* __restrict__ err)
+{
+  const TriLine L = tri_line(G, dir);
+  long long sys, base;
+  if (!tri_sys(G, dir, L, sys, base)) return;
+  const double *a = A + base, *b = B + base, *c = Cc + base;
+  double* x = X + base;
+  const long long qs = L.qs;
+  const int il = n - 1;
+  if (b[il * qs] == 0) { *err = 1; return; }
+  x[il * qs] = (x[il * qs] - a[il * qs] * x[0] - c[il * qs] * xp1[sys]) / b[il * qs];
+  for (int i = il - 1; i > (first ? 0 : 1) - 1; i--) {
+    if (b[i * qs] == 0) { *err = 1; return; }
+    x[i * qs] = (x[i * qs] - c[i * qs] * x[(i + 1) * qs] - a[i * qs] * x[0]) / b[i * qs];
+  }
+  sendfirst[sys] = x[0];
+}
+// the solution of the shared interface N arrives from the next rank (Interp1PrimFifthOrderCRWENO.c:222)
+__global__ void k_mr_put_last(Geom G, int dir, double* __restrict__ X, const double* __restrict__ recvfirst)
+{
+  const TriLine L = tri_line(G, dir);
+  long long sys, base;
+  if (!tri_sys(G, dir, L, sys, base)) return;
+  X[base + (long long)G.N[dir] * L.qs] = recvfirst[sys];
+}
+
+// ------------------------------------------------------------------------------------------
 // Compact schemes on characteristic variables (Interp1PrimFifthOrderCRWENOChar.c:95-277,
 // Interp1PrimFifthOrderCompactUpwindChar.c:85-264): one BLOCK tridiagonal system per grid line. Row blocks are
 // (coefficient) x L(uavg), the right-hand side is the characteristic candidate combination, the unknown is the
@@ -1068,7 +1228,7 @@ __global__ void k_compact_rows_char(Geom G, Phys ph, const double* __restrict__ 
   const int blk = (upw < 0 ? 2 : 0) + (uflag ? 1 : 0);
   int iI; long long sys, Nsys;
   compact_sys_index(dir, i0, i1, i2, M0, M1, M2, iI, sys, Nsys);
-  const bool bnd = (iI == 0) || (iI == G.N[dir]);
+  const bool bnd = (iI == 0 && G.lo_phys[dir]) || (iI == G.N[dir] && G.hi_phys[dir]);
   long long ps[5];
   for (int k = 0; k < 5; k++) ps[k] = (upw > 0) ? pm1 + (k - 2) * st : pm1 + (3 - k) * st;
   double UL[NV], UR[NV], uavg[NV], lam[NV], L[NV * NV], R[NV * NV];
@@ -1581,6 +1741,177 @@ void hyperbolic_pieces(hpb_solver* h, const double* u, double* out, bool negate,
   }
 }
 
+// ---- compact schemes with the grid line split among ranks. Group style (hpb_internal.h: hpbc): `hs` = one solver with
+// the NCCL transport, every rank with the in-process one; each step loops over the group.
+static long long mr_nsys(const hpb_solver* h, int dir)
+{
+  const Geom& G = h->geo;
+  const long long M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
+  return M[0] * M[1] * M[2] / M[dir] * G.nvars;
+}
+static int mr_ensure(hpb_solver* h)
+{
+  if (h->d_mr) return HPB_OK;
+  long long m = 0;
+  for (int d = 0; d < h->geo.ndims; d++) { const long long k = mr_nsys(h, d); if (k > m) m = k; }
+  const size_t bytes = (size_t)(17 * m + 4096) * sizeof(double);
+  if (cudaMalloc((void**)&h->d_mr, bytes) != cudaSuccess) return hpb_fail(HPB_ERR_ALLOC, "compact schemes across ranks: scratch allocation failed");
+  cudaMemset(h->d_mr, 0, bytes);
+  cudaStreamSynchronize(cudaStreamLegacy);
+  if (cudaMallocHost((void**)&h->h_mr, 128 * sizeof(double)) != cudaSuccess) return hpb_fail(HPB_ERR_ALLOC, "pinned alloc");
+  return HPB_OK;
+}
+
+// the tridiagonal solve of the rows the group's k_compact_rows launches have left in d_tri[0..2] / X[r] (tridiagLU.c with
+// the Jacobi reduced solve, then the shared interface from the next rank)
+static int compact_solve_group(hpb_solver** hs, int n, int dir, double* const* X)
+{
+  const int tpb = 64;
+  const double atol = 1e-12, rtol = 1e-10;      // tridiagLUInit.c:70-76 (lusolver.inp is not read: defaults)
+  const int maxiter = 10;
+  std::vector<double*> sendrow(n), recvrow(n), red_x(n), red_sx(n), red_rl(n), red_rr(n), xp1(n), sfirst(n), rfirst(n), dnorm(n), dgath(n);
+  std::vector<int> active(n, 1), first(n), last(n), rows(n);
+  std::vector<dim3> grid(n);
+  std::vector<long long> nsys(n), nsys4(n);
+  for (int r = 0; r < n; r++) {
+    hpb_solver* h = hs[r];
+    int rc = mr_ensure(h); if (rc) return rc;
+    const Geom& G = h->geo;
+    const int M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
+    int T0, T1;
+    if (dir == 0) { T0 = M[1]; T1 = M[2]; } else if (dir == 1) { T0 = M[0]; T1 = M[2]; } else { T0 = M[0]; T1 = M[1]; }
+    grid[r] = dim3((T0 + tpb - 1) / tpb, T1, G.nvars);
+    nsys[r] = mr_nsys(h, dir); nsys4[r] = 4 * nsys[r];
+    first[r] = G.lo_phys[dir]; last[r] = G.hi_phys[dir];
+    rows[r] = G.N[dir] + (last[r] ? 1 : 0);       // all ranks but the last leave the shared interface to the next one (:208-209)
+    double* m = h->d_mr;
+    sendrow[r] = m; recvrow[r] = m + 4 * nsys[r];
+    double* red = m + 8 * nsys[r];                 // [rhs | x | sent x | recvL | recvR | xp1]
+    red_x[r] = red + nsys[r]; red_sx[r] = red + 2 * nsys[r]; red_rl[r] = red + 3 * nsys[r]; red_rr[r] = red + 4 * nsys[r];
+    xp1[r] = red + 5 * nsys[r];
+    sfirst[r] = m + 14 * nsys[r]; rfirst[r] = m + 15 * nsys[r];
+    dnorm[r] = m + 16 * nsys[r]; dgath[r] = dnorm[r] + 8;     // + partial sums from dnorm + 128 on
+  }
+#define EACH_R for (int r = 0; r < n; r++)
+#define HCUR hpb_solver* h = hs[r]; cudaSetDevice(h->device); const Geom& G = h->geo; (void)G
+  EACH_R { HCUR;
+    cudaMemsetAsync(h->d_mr + 8 * nsys[r] + 3 * nsys[r], 0, 3 * nsys[r] * sizeof(double), h->stream);     // recvL, recvR, xp1
+    k_mr_stage1<<<grid[r], tpb, 0, h->stream>>>(G, dir, rows[r], first[r], h->d_tri[0], h->d_tri[1], h->d_tri[2], X[r],
+                                                sendrow[r], nsys[r], h->d_err); LAUNCHED(h); }
+  { int rc = hpbc::line_shift(hs, n, dir, +1, sendrow.data(), recvrow.data(), nsys4.data(), nullptr); if (rc) return rc; }
+  EACH_R { HCUR;
+    k_mr_stage2<<<grid[r], tpb, 0, h->stream>>>(G, dir, rows[r], first[r], atol, h->d_tri[0], h->d_tri[1], h->d_tri[2], X[r],
+                                                recvrow[r], h->d_mr + 8 * nsys[r], nsys[r], h->d_err); LAUNCHED(h); }
+  // reduced system: Jacobi (tridiagIterJacobi.c:128-190); members of one line of ranks stop together
+  std::vector<double> gnorm(n, 0.0), norm0(n, 0.0);
+  std::vector<std::array<double, 64>> hn(n);
+  for (int iter = 0; ; iter++) {
+    bool any = false;
+    EACH_R {
+      if (!active[r]) continue;
+      if (iter >= maxiter || (iter && gnorm[r] < atol) || (iter && gnorm[r] / norm0[r] < rtol)) active[r] = 0;
+      any = any || active[r];
+    }
+    if (!any) break;
+    { int rc = hpbc::line_swap(hs, n, dir, red_sx.data(), red_sx.data(), red_rl.data(), red_rr.data(), nsys.data(), active.data()); if (rc) return rc; }
+    EACH_R { if (!active[r]) continue; HCUR;
+      const long long nb = (long long)grid[r].x * grid[r].y * grid[r].z;
+      k_mr_jacobi<<<grid[r], tpb, 0, h->stream>>>(G, dir, first[r], 0, h->d_tri[0], h->d_tri[1], h->d_tri[2], X[r], h->d_mr + 8 * nsys[r],
+                                                  nsys[r], dnorm[r] + 128); LAUNCHED(h);
+      if (nb > 3900) return hpb_fail(HPB_ERR_INVALID, "compact schemes across ranks: more than 3900 thread blocks per solve");
+      k_mr_sum<<<1, 256, 0, h->stream>>>(dnorm[r] + 128, nb, dnorm[r]); LAUNCHED(h); }
+    { int rc = hpbc::line_gather(hs, n, dir, dnorm.data(), dgath.data(), reinterpret_cast<double (*)[64]>(hn.data()), active.data()); if (rc) return rc; }
+    EACH_R { if (!active[r]) continue;
+      const int np = hs[r]->cfg.iproc[dir];
+      double sum = hn[r][0];                                   // the order of a rank-0-rooted reduction: ((r0 + r1) + r2) ...
+      for (int k = 1; k < np; k++) sum += hn[r][k];
+      gnorm[r] = sqrt(sum / np);                               // NT = sum of the local sizes = ranks on the line (:118)
+      if (!iter) norm0[r] = gnorm[r];
+      HCUR;
+      k_mr_jacobi<<<grid[r], tpb, 0, h->stream>>>(G, dir, first[r], 1, h->d_tri[0], h->d_tri[1], h->d_tri[2], X[r], h->d_mr + 8 * nsys[r],
+                                                  nsys[r], nullptr); LAUNCHED(h); }
+  }
+  // each rank gets the first x of the next one (tridiagLU.c:228-233), back substitution, the shared interface
+  { int rc = hpbc::line_shift(hs, n, dir, -1, red_x.data(), xp1.data(), nsys.data(), nullptr); if (rc) return rc; }
+  EACH_R { HCUR;
+    k_mr_stage4<<<grid[r], tpb, 0, h->stream>>>(G, dir, rows[r], first[r], h->d_tri[0], h->d_tri[1], h->d_tri[2], X[r], xp1[r],
+                                                sfirst[r], nsys[r], h->d_err); LAUNCHED(h); }
+  { int rc = hpbc::line_shift(hs, n, dir, -1, sfirst.data(), rfirst.data(), nsys.data(), nullptr); if (rc) return rc; }
+  EACH_R { if (last[r]) continue; HCUR;
+    k_mr_put_last<<<grid[r], tpb, 0, h->stream>>>(G, dir, X[r], rfirst[r]); LAUNCHED(h); }
+#undef EACH_R
+#undef HCUR
+  return HPB_OK;
+}
+
+static int weno_interp_group(hpb_solver** hs, int n, double* const* fI, double* const* fC, const double* const* u,
+                             double* const* w, int upw, int dir, int uflag)
+{
+  for (int r = 0; r < n; r++) { cudaSetDevice(hs[r]->device); weno_interp(hs[r], fI[r], fC[r], u[r], w[r], upw, dir, uflag); }
+  const hpb_solver* h0 = hs[0];
+  const bool compact = (h0->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h0->cfg.hyp_scheme == HPB_SCHEME_CUPW5);
+  if (compact && h0->cfg.iproc[dir] > 1) return compact_solve_group(hs, n, dir, fI);
+  return HPB_OK;
+}
+
+// hyperbolic_pieces for a group of ranks (the reconstructions of a compact scheme couple them)
+int hyperbolic_pieces_group(hpb_solver** hs, int n, const double* const* u, double* const* out, bool negate, bool with_source,
+                            double* const* src)
+{
+  const int nd = hs[0]->geo.ndims;
+  std::vector<double*> fC(n), uC(n), fL(n), fR(n), uL(n), uR(n), w(n);
+  std::vector<long long> wo(n, 0);
+  for (int d = 0; d < nd; d++) {
+    for (int r = 0; r < n; r++) {
+      hpb_solver* h = hs[r];
+      cudaSetDevice(h->device);
+      const Geom& G = h->geo;
+      const long long ni = (long long)(G.N[0] + (d == 0)) * (G.N[1] + (d == 1)) * (G.N[2] + (d == 2));
+      fC[r] = h->d_cell[0]; uC[r] = h->d_cell[1];
+      fL[r] = h->d_iface[1]; fR[r] = h->d_iface[2]; uL[r] = h->d_iface[3]; uR[r] = h->d_iface[4];
+      w[r] = h->d_w + wo[r];
+      wo[r] += 12 * ni * G.nvars;
+      flux(h, u[r], fC[r], d);
+      if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5) { weno_weights(h, fC[r], u[r], d, w[r]); h->w_valid = true; }
+      modified_solution(h, u[r], uC[r]);
+    }
+    int rc;
+    if ((rc = weno_interp_group(hs, n, uL.data(), uC.data(), u, w.data(),  1, d, 1))) return rc;
+    if ((rc = weno_interp_group(hs, n, uR.data(), uC.data(), u, w.data(), -1, d, 1))) return rc;
+    if ((rc = weno_interp_group(hs, n, fL.data(), fC.data(), u, w.data(),  1, d, 0))) return rc;
+    if ((rc = weno_interp_group(hs, n, fR.data(), fC.data(), u, w.data(), -1, d, 0))) return rc;
+    for (int r = 0; r < n; r++) {
+      hpb_solver* h = hs[r];
+      cudaSetDevice(h->device);
+      const Geom& G = h->geo;
+      upwind(h, h->d_fI, fL[r], fR[r], uL[r], uR[r], u[r], d);
+      const int mode = negate ? (d == 0 ? 0 : 1) : (d == 0 ? 2 : 3);
+      k_divergence<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, h->d_dxinv, h->d_fI, d, out[r], mode); LAUNCHED(h);
+    }
+    const bool grav = hs[0]->phys.has_grav && with_source && hs[0]->phys.grav[d] != 0.0;
+    if (grav) {
+      for (int r = 0; r < n; r++) {
+        hpb_solver* h = hs[r];
+        cudaSetDevice(h->device);
+        const Geom& G = h->geo;
+        k_ns3d_source_fn<<<(unsigned)((G.npg + 255) / 256), 256, 0, h->stream>>>(G, h->d_gravg, d, fC[r]); LAUNCHED(h);
+      }
+      if ((rc = weno_interp_group(hs, n, fL.data(), fC.data(), u, w.data(),  1, d, 0))) return rc;
+      if ((rc = weno_interp_group(hs, n, fR.data(), fC.data(), u, w.data(), -1, d, 0))) return rc;
+      for (int r = 0; r < n; r++) {
+        hpb_solver* h = hs[r];
+        cudaSetDevice(h->device);
+        const Geom& G = h->geo;
+        const long long ni = (long long)(G.N[0] + (d == 0)) * (G.N[1] + (d == 1)) * (G.N[2] + (d == 2));
+        k_ns3d_source_avg<<<(unsigned)((ni + 255) / 256), 256, 0, h->stream>>>(ni, d, G.nvars - 1, fL[r], fR[r], h->d_sI); LAUNCHED(h);
+        k_ns3d_source<<<grid3(G.N[0], G.N[1], G.N[2]), TPB, 0, h->stream>>>(G, h->phys, h->d_dxinv, u[r], h->d_gravf, h->d_sI, d, src[r]);
+        LAUNCHED(h);
+      }
+    }
+  }
+  return HPB_OK;
+}
+
 int tridiag_error(hpb_solver* h)
 {
   if (!h->d_err) return 0;
@@ -1750,6 +2081,7 @@ void weno_interp(hpb_solver* h, double* fI, const double* fC, const double* u, c
     // rows, then one thread per (line, component) system; the solution replaces the right-hand side in fI
     k_compact_rows<<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, fC, w, upw, dir, uflag,
                                                                     h->d_tri[0], h->d_tri[1], h->d_tri[2], fI); LAUNCHED(h);
+    if (h->cfg.iproc[dir] > 1) return;          // the line is split among ranks: compact_solve_group finishes the job
     int T0, T1;
     if (dir == 0) { T0 = M[1]; T1 = M[2]; } else if (dir == 1) { T0 = M[0]; T1 = M[2]; } else { T0 = M[0]; T1 = M[1]; }
     const int tpb = 64;

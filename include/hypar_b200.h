@@ -333,6 +333,7 @@ int hpb_comm_stats(const hpb_solver* h, long long* messages_sent, long long* byt
 int hpb_exchange_plan(const hpb_solver* h, int slot, int* ops, long long* counts, int* nops);
 /* MPIExchangeBoundariesnD on the device solution: ghost faces of u <- the neighbours' interior layers. Blocking. */
 int hpb_ExchangeBoundariesnD(hpb_solver* h);
+int hpb_ExchangeBoundariesLocal(hpb_solver** ranks, int nranks);      /* the same for in-process ranks */
 /* TimePreStep (BCs + halo of u) + TimeRK + step completion, nsteps times; this rank's part (NCCL transport) */
 int hpb_TimeStepDistributed(hpb_solver* h);
 int hpb_TimeStepsDistributed(hpb_solver* h, int nsteps);

@@ -175,6 +175,11 @@ class LocalRanks:
         self._sync()
         return [sv.get_stage_rhs(0) for sv in self.sv]
 
+    def exchange_boundaries(self):
+        """MPIExchangeBoundariesnD on the device solutions (hpb_ExchangeBoundariesLocal)"""
+        sv = self.sv[0]
+        sv._ck(sv.L.hpb_ExchangeBoundariesLocal(self._arr, self.nranks))
+
     def time_step(self, n=1):
         sv = self.sv[0]
         sv._ck(sv.L.hpb_TimeStepsLocal(self._arr, self.nranks, n))

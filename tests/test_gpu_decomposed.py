@@ -140,3 +140,81 @@ def test_overlapped_call_sequence_is_identical(need_gpu, case):
         assert np.array_equal(a, b), f"rank {r}: u after 2 steps differs between the schedules"
     A.close()
     B.close()
+
+
+@pytest.mark.parametrize("case", [DECOMP[2], DECOMP[4], DECOMP[5]], ids=lambda c: c.name)
+def test_exchange_boundaries_on_the_device_solution(need_gpu, case):
+    """hpb_ExchangeBoundariesnD / ...Local = MPIExchangeBoundariesnD (MPIExchangeBoundariesnD.c:42-173) on the device solution:
+    every face ghost layer of every rank equals the multi-rank oracle's after its exchange (the oracle is pinned to the
+    multi-rank reference, tests/test_oracle_multirank_ref.py); interiors, physical faces, edges and corners are untouched."""
+    MO = MultiRankOracle(case)
+    u0 = MO.local_u0()
+    LR = LocalRanks(case, use_fused=True)
+    LR.set_solution(u0)
+    LR.exchange_boundaries()
+    got = LR.get_solution()
+    ref = [u.copy() for u in u0]
+    MO.exchange(ref)
+    for r in range(MO.nranks):
+        assert np.array_equal(got[r], ref[r]), f"rank {r}: ghost layers differ after the exchange"
+    # the plan the library reports moved what it says: messages and bytes sent by rank 0
+    msgs, nbytes = LR.sv[0].comm_stats()
+    plan = LR.sv[0].exchange_plan(0)
+    sends = [p for p in plan if p[0] == "send"]
+    assert msgs == len(sends) and nbytes == 8 * sum(p[3] for p in sends)
+    LR.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# compact schemes with the grid lines split among ranks (SURVEY 8f rank 4): TridiagLU/tridiagLU.c:84-274 with all four stages,
+# the reduced system solved by tridiagIterJacobi.c as the reference does by default, and the hand-over of the shared
+# interface (Interp1PrimFifthOrderCRWENO.c:206-223). The checker is the REAL reference running with the same number of ranks
+# (oracle/_ref/hypar_ref_mp on the multi-process MPI shim): the multi-rank solve is decomposition-dependent by design (the
+# reduced system is iterated to 1e-10), so only the same algorithm on the same decomposition can match -- bit for bit.
+def _compact_cases():
+    C = [cases.ns2d_vortex((40, 27), "mapped", iproc=(2, 2), scheme="crweno5"),
+         cases.ns3d_turbulence((26, 25, 27), "z", iproc=(2, 2, 2), scheme="crweno5"),          # viscous, 8 ranks
+         cases.ns3d_rising_bubble((14, 26, 12), "yc", iproc=(1, 2, 1), scheme="crweno5"),       # gravity source reconstructions
+         cases.ns2d_vortex((28, 40), "js", scheme="cupw5", iproc=(1, 3)),
+         cases.ns3d_density_wave((16, 12, 26), "js", iproc=(1, 1, 4), scheme="crweno5")]        # 4 ranks on one line
+    a = cases.linear_advection_sine(96, "z", scheme="crweno5")
+    a.solver["iproc"] = [3]
+    b = cases.euler1d_sod(101, "js", interp="components", upwinding="roe", scheme="cupw5")
+    b.solver["iproc"] = [2]
+    C += [a, b]
+    for c in C:
+        c.name += "_iproc" + "x".join(str(v) for v in c.solver["iproc"])
+    return C
+
+
+COMPACT_MR = _compact_cases()
+
+
+@pytest.mark.parametrize("case", COMPACT_MR, ids=[c.name for c in COMPACT_MR])
+@pytest.mark.parametrize("overlap", [False, True], ids=["serial", "overlap"])
+def test_compact_schemes_across_ranks(need_gpu, case, overlap):
+    from test_oracle_multirank_ref import EXE, run_ref_mp
+    import os
+    if not os.access(EXE, os.X_OK):
+        pytest.fail(f"{EXE} is missing: build it where the reference tree is available (make -C oracle refmp)")
+    nr = int(np.prod(case.solver["iproc"]))
+    ref = run_ref_mp(case, "rhs", nranks=nr)
+    MO = MultiRankOracle(case)                 # only for the initial blocks and their shapes
+    LR = LocalRanks(case, use_fused=False, sweepwise=overlap)
+    LR.set_solution(MO.local_u0())
+    rhs = LR.rhs()
+    for r in range(nr):
+        a = ref[f"rhs.r{r:04d}"]["data"]
+        assert np.isfinite(rhs[r]).all()
+        assert np.array_equal(rhs[r].ravel(), a), \
+            f"rank {r}: rhs differs from the {nr}-rank reference by {np.abs(rhs[r].ravel() - a).max():.3e} (max {np.abs(a).max():.3e})"
+    ref = run_ref_mp(case, "steps", [2], nranks=nr)
+    LR.set_solution(MO.local_u0())
+    LR.time_step(2)
+    u = LR.get_solution()
+    for r in range(nr):
+        S = MO.S[r]
+        a = S.interior(ref[f"ufinal.r{r:04d}"]["data"].reshape(S.shape_g()))
+        b = S.interior(u[r])
+        assert np.array_equal(a, b), f"rank {r}: u after 2 steps differs from the {nr}-rank reference by {np.abs(a - b).max():.3e}"
+    LR.close()

@@ -75,6 +75,35 @@ def diagnostics_and_io(rank, world, local, iproc):
     return ok
 
 
+def compact_across_ranks(rank, world, local, iproc):
+    """compact scheme with its grid lines split among the ranks (tridiagLU's four stages + Jacobi reduced solve over the
+    library's NCCL line exchanges) against the REAL reference running with the same ranks (oracle/_ref/hypar_ref_mp)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_multirank_ref import EXE, run_ref_mp
+    if not os.access(EXE, os.X_OK):
+        if rank == 0:
+            print("[compact] oracle/_ref/hypar_ref_mp missing: skipped", flush=True)
+        return True
+    ok = True
+    for name, case in (("crweno5 visc", cases.ns3d_turbulence((26, 25, 27), "z", iproc=iproc, scheme="crweno5")),
+                       ("cupw5 bubble", cases.ns3d_rising_bubble((26, 24, 28), "yc", iproc=iproc, scheme="cupw5"))):
+        ref = run_ref_mp(case, "steps", [2], nranks=world)
+        ds = DistributedSolver(case.solver, case.boundary, case.physics, case.weno, case.x, rank=rank, device=local, use_fused=False)
+        MO = MultiRankOracle(case)
+        ds.solver.set_solution(MO.local_u0()[rank])
+        ds.time_steps(2)
+        u = ds.solver.get_solution()
+        S = MO.S[rank]
+        a = S.interior(ref[f"ufinal.r{rank:04d}"]["data"].reshape(S.shape_g()))
+        b = S.interior(u)
+        good = bool(np.array_equal(a, b))
+        ok = ok and good
+        print(f"[rank {rank}/{world}] iproc {iproc} {name}: u(2 steps) vs the {world}-rank reference: max diff {np.abs(a - b).max():.2e} "
+              f"{'bit-identical ok' if good else 'FAIL'}", flush=True)
+        ds.solver.close()
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -127,6 +156,7 @@ def main():
                       flush=True)
                 ds.solver.close()
     ok = diagnostics_and_io(rank, world, local, iprocs[0]) and ok
+    ok = compact_across_ranks(rank, world, local, iprocs[0]) and ok
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
     dist.destroy_process_group()
