@@ -468,6 +468,7 @@ def gpu_arm(args):
     #            the 1-GPU rate of this run's per-GPU block size
     #   c5b    : configs[4] -- rising thermal bubble with the gravity source, WENO5-YC, SSPRK3, 512^3 per GPU (1024^3 at 8)
     tma_launches = sv.tma_launches
+    fp64_peak = sv.fp64_issue_peak() if rank == 0 else None      # measured live on this GPU (hpb_fp64_issue_peak)
     comm_msgs, comm_bytes = sv.comm_stats() if stepper is not None else (0, 0)
     sub = {}
     if not args.no_sub and args.workload == "c4":
@@ -511,12 +512,13 @@ def gpu_arm(args):
     achieved = SWEEP_BYTES[dom] * npts_local / (dom_ms * 1e-3) / 1e9
     total_prof = sum(v[0] for v in prof.values())
     # DRAM traffic and FP64-pipe activity of the same kernel from the committed ncu --set full capture (512^3 per launch)
-    traffic, fp64_pct, ncu_src = None, None, None
+    traffic, fp64_pct, ncu_src, fp64_instr = None, None, None, None
     try:
         prof_ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_sweep_512.json")))
         if tuple(nloc) == (512, 512, 512) and dom in prof_ncu and tma_launches > 0:
             traffic = float(prof_ncu[dom]["dram_bytes_read"] + prof_ncu[dom]["dram_bytes_write"]) / 1e9
             fp64_pct = prof_ncu[dom]["fp64_pipe_active_pct"]
+            fp64_instr = prof_ncu[dom].get("fp64_thread_instr")
             ncu_src = "profiles/ncu_sweep_512.json"
     except Exception:
         pass
@@ -530,6 +532,14 @@ def gpu_arm(args):
         "whole_stage": {"bytes_per_point_stage": STAGE_BYTES,
                         "achieved": STAGE_BYTES * npts_local * nstages * args.steps / (ms * 1e-3) / 1e9,
                         "frac": STAGE_BYTES * npts_local * nstages * args.steps / (ms * 1e-3) / 1e9 / peak},
+        # the binding roofline: FP64 thread-instructions of the same launch (DFMA + DMUL + DADD executed, from the committed
+        # ncu source-page capture of this kernel at 512^3: profiles/ncu_sweep_512.json) over its live CUDA-event time, against
+        # the FP64 issue peak measured live on this GPU
+        "fp64": (None if not (fp64_instr and fp64_peak) else {
+            "bound": "fp64 issue", "achieved": fp64_instr / (dom_ms * 1e-3) / 1e12, "peak": fp64_peak / 1e12, "unit": "T thread-instr/s",
+            "frac": fp64_instr / (dom_ms * 1e-3) / fp64_peak, "fp64_thread_instr_per_launch": fp64_instr,
+            "fp64_thread_instr_per_cell": fp64_instr / npts_local,
+            "peak_source": "hpb_fp64_issue_peak: DMUL chains, 8 CTAs x 256 threads per SM, measured in this run"}),
         "note": "FP64-issue-bound kernel (DESIGN.md): the HBM fraction is reported as the metric demands; the FP64 pipe "
                 "is the binding unit (fp64_pipe_active_pct_ncu); traffic exceeds the algorithmic bytes by the 8 "
                 "derivative scalars (64 B/point) the viscous flux reads",

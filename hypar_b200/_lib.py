@@ -64,7 +64,7 @@ SYMBOLS = [
     "hpb_dev_get_stage_rhs", "hpb_nstages", "hpb_needs_viscous_exchange",
     "hpb_dev_VolumeIntegral", "hpb_dev_StageBoundaryIntegral", "hpb_dev_StepBoundaryIntegral", "hpb_BoundaryIntegral",
     "hpb_CalculateConservationError", "hpb_dev_ErrorSums",
-    "hpb_stream", "hpb_synchronize", "hpb_kernel_launch_count", "hpb_tma_launch_count", "hpb_profile_enable", "hpb_profile_query",
+    "hpb_stream", "hpb_synchronize", "hpb_kernel_launch_count", "hpb_tma_launch_count", "hpb_profile_enable", "hpb_profile_query", "hpb_fp64_issue_peak",
 ]
 
 _lib = None
@@ -161,6 +161,7 @@ def load():
     L.hpb_kernel_launch_count.restype = C.c_longlong
     L.hpb_tma_launch_count.argtypes = [vp]
     L.hpb_tma_launch_count.restype = C.c_longlong
+    L.hpb_fp64_issue_peak.argtypes = [vp, dp]
     L.hpb_profile_enable.argtypes = [vp, C.c_int]
     L.hpb_profile_query.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_longlong)]
     _lib = L

@@ -395,6 +395,48 @@ extern "C" int hpb_profile_query(hpb_solver* h, int category, double* total_ms, 
   return HPB_OK;
 }
 
+// ------------------------------------------------------------------------------------ FP64 issue peak, measured live
+// The production sweeps are bound by the FP64 pipe, not by HBM: this is the denominator of that
+// roofline, measured on the device the solver runs on -- 8 independent DMUL chains per thread, 8 CTAs of 256 threads per
+// SM, best of 4 launches (DMUL and DADD issue at the same rate; DFMA is ~8 % slower on the B200: profiles/r01_microbench.txt).
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a)
+{
+  double x0 = threadIdx.x * 1e-9 + 1.0, x1 = x0 + 0.1, x2 = x0 + 0.2, x3 = x0 + 0.3, x4 = x0 + 0.4, x5 = x0 + 0.5, x6 = x0 + 0.6, x7 = x0 + 0.7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) { x0 *= a; x1 *= a; x2 *= a; x3 *= a; x4 *= a; x5 *= a; x6 *= a; x7 *= a; }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int hpb_fp64_issue_peak(hpb_solver* h, double* thread_instr_per_s)
+{
+  TRY(need_device(h));
+  if (!thread_instr_per_s) return hpb_fail(HPB_ERR_INVALID, "fp64_issue_peak: null argument");
+  TRY(sync_check(h, "fp64_issue_peak"));
+  cudaDeviceProp p;
+  HPB_CUDA(cudaGetDeviceProperties(&p, h->device));
+  const int blocks = p.multiProcessorCount * 8, threads = 256, iters = 2048;
+  double* out = nullptr;
+  HPB_CUDA(cudaMalloc((void**)&out, sizeof(double) * blocks * threads));
+  cudaEvent_t a, b;
+  HPB_CUDA(cudaEventCreate(&a)); HPB_CUDA(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(a, h->stream);
+    k_fp64_peak<<<blocks, threads, 0, h->stream>>>(out, iters, 0.999999);
+    cudaEventRecord(b, h->stream);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+  HPB_CUDA(cudaGetLastError());
+  *thread_instr_per_s = (double)blocks * threads * iters * 64.0 / (best * 1e-3);
+  return HPB_OK;
+}
+
 // ------------------------------------------------------------------------------------ RHS assembly (device)
 // rhs = -hyp + par + source of TimeRHSFunctionExplicit.c:70-92, split at the viscous halo exchange.
 // Production path: [Q-derivatives] | sweeps with the viscous flux and the gravity source inside.

@@ -532,6 +532,12 @@ class Solver:
 
     PROF = {"sweep_x": 0, "sweep_y": 1, "sweep_z": 2, "viscous": 3, "rk": 4, "bc": 5, "halo": 6, "other": 7}
 
+    def fp64_issue_peak(self) -> float:
+        """FP64 thread-instructions per second this device issues at most (measured live)"""
+        v = C.c_double()
+        self._ck(self.L.hpb_fp64_issue_peak(self.h, C.byref(v)))
+        return v.value
+
     def profile_enable(self, on: bool = True) -> None:
         self._ck(self.L.hpb_profile_enable(self.h, int(on)))
 
