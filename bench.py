@@ -422,7 +422,9 @@ def gpu_arm(args):
         if not np.isfinite(u_host).all():
             raise RuntimeError("non-finite values in the host solution after the end-to-end steps")
 
-        e2e_steps = max(args.steps, 16)
+        # the pipeline has a fixed fill / drain cost (the first H2D and the last D2H, ~100 ms each at 512^3, cannot hide behind a
+        # step): 40 steps amortise it to ~5 ms per step (16 steps of round 1 left 12.5 ms per step in the figure)
+        e2e_steps = max(args.steps, 40)
         u_out = u_host                               # results land in the first pinned array
 
         def e2e_submit():
