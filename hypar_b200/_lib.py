@@ -40,6 +40,7 @@ class Config(C.Structure):
         ("device", C.c_int), ("use_fused", C.c_int), ("conservation_check", C.c_int),
         ("hyp_scheme", C.c_int), ("muscl_limiter", C.c_int), ("muscl_eps", C.c_double),
         ("gravity_type", C.c_int), ("advection_field", C.POINTER(C.c_double)),
+        ("weno_rc", C.c_double), ("weno_xi", C.c_double),
         ("par_space_type", C.c_int),
     ]
 

@@ -195,11 +195,16 @@ def _sfx(scheme: str) -> str:
 
 
 def weno_inp(kind: str = "js", eps: float = 1e-6, no_limiting: int = 0) -> Dict[str, object]:
-    """kind in {js, mapped, z, yc} (WENOInitialize.c:62-96)."""
-    return {
+    """kind in {js, mapped, z, yc} (WENOInitialize.c:62-96); the hybridisation parameters of hcweno5 ride on the
+    kind as "+rc<value>" / "+xi<value>" (e.g. "mapped+rc0.2+xi0.01"; defaults 0.3, 0.001, WENOInitialize.c:57-58)."""
+    kind, *opts = kind.split("+")
+    w = {
         "mapped": int(kind == "mapped"), "borges": int(kind == "z"), "yc": int(kind == "yc"),
         "no_limiting": no_limiting, "epsilon": float(eps), "p": 2.0, "rc": 0.3, "xi": 0.001,
     }
+    for o in opts:
+        w[o[:2]] = float(o[2:])
+    return w
 
 
 def _zones(ndims, kind_per_face, lo, hi, wall_velocity=None):

@@ -45,6 +45,7 @@ extern "C" void hpb_config_defaults(hpb_config* c)
   c->par_scheme = 2;                                          // ReadInputs.c:135
   c->rk_type = HPB_RK_44;
   c->weno_type = HPB_WENO_JS; c->no_limiting = 0; c->weno_eps = 1e-6;   // WENOInitialize.c:51-60
+  c->weno_rc = 0.3; c->weno_xi = 0.001;
   c->upwind = HPB_UPWIND_ROE;
   c->gamma = 1.4; c->Re = -1.0; c->Pr = 0.72; c->Minf = 1.0;   // NavierStokes3DInitialize.c:78-91
   c->rho_ref = 1.0; c->p_ref = 1.0; c->R = 1.0; c->HB = 1; c->N_bv = 0.0;
@@ -146,7 +147,7 @@ static int ensure_pieces(hpb_solver* h)
   for (int k = 0; k < 2; k++) TRY(dalloc(&h->d_cell[k], n));
   for (int k = 0; k < 5; k++) TRY(dalloc(&h->d_iface[k], nif_max(h) * h->geo.nvars));
   TRY(dalloc(&h->d_w, woff(h, h->geo.ndims)));
-  if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h->cfg.hyp_scheme == HPB_SCHEME_CUPW5) {
+  if (hpb_scheme_is_compact(h->cfg.hyp_scheme)) {
     // component-wise: one scalar row per interface and component; characteristic: one nvars x nvars block per interface
     const long long blk = (h->phys.interp_char ? (long long)h->geo.nvars * h->geo.nvars : h->geo.nvars);
     for (int k = 0; k < 3; k++) TRY(dalloc(&h->d_tri[k], nif_max(h) * blk));
@@ -597,7 +598,7 @@ extern "C" int hpb_SetInterpLimiterVar(hpb_solver* h, const double* fC, const do
 {
   TRY(need_device(h)); TRY(tmp(h, 0)); TRY(tmp(h, 1));
   if (dir < 0 || dir >= h->geo.ndims) return hpb_fail(HPB_ERR_INVALID, "SetInterpLimiterVar: dir %d", dir);
-  if (h->cfg.hyp_scheme != HPB_SCHEME_WENO5 && h->cfg.hyp_scheme != HPB_SCHEME_CRWENO5)
+  if (!hpb_scheme_has_weights(h->cfg.hyp_scheme))
     return HPB_OK;             // linear schemes: the reference leaves the pointer NULL (InitializeSolvers.c:194)
   TRY(dalloc(&h->d_w, woff(h, h->geo.ndims)));
   TRY(upload(h, fC, h->d_tmp[0], h->geo.npg, h->geo.nvars));
@@ -1077,7 +1078,7 @@ static int dist_stage(Grp& G, int s)
   } else {
     const hpb_solver* h0 = G.hs[0];
     bool split_compact = false;       // a compact scheme whose grid lines are split among ranks: the reconstructions couple the ranks
-    if (h0->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h0->cfg.hyp_scheme == HPB_SCHEME_CUPW5)
+    if (hpb_scheme_is_compact(h0->cfg.hyp_scheme))
       for (int d = 0; d < h0->geo.ndims; d++) split_compact = split_compact || h0->cfg.iproc[d] > 1;
     if (split_compact) {
       std::vector<const double*> U(G.n);

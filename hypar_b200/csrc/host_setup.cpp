@@ -91,17 +91,17 @@ int hpb_setup_host(hpb_solver* h)
     for (int i = 0; i < nd * c.nvars; i++)
       if (c.diffusion[i] != 0.0)       // LinearADR installs GFunction AND HFunction: every form is a different discretisation
         return hpb_fail(HPB_ERR_INVALID, "LinearADR diffusion is on the B200 path as par_space_type nonconservative-1stage only");
-  if (c.hyp_scheme < HPB_SCHEME_WENO5 || c.hyp_scheme > HPB_SCHEME_MUSCL3)
-    return hpb_fail(HPB_ERR_INVALID, "hyp_space_scheme %d not supported (weno5, crweno5, cupw5, upw5, 1, 2, 4, muscl2, muscl3)",
+  if (c.hyp_scheme < HPB_SCHEME_WENO5 || c.hyp_scheme > HPB_SCHEME_HCWENO5)
+    return hpb_fail(HPB_ERR_INVALID, "hyp_space_scheme %d not supported (weno5, crweno5, hcweno5, cupw5, upw5, 1, 2, 4, muscl2, muscl3)",
                     c.hyp_scheme);
   if (c.muscl_limiter < HPB_LIMITER_GMM || c.muscl_limiter > HPB_LIMITER_SUPERBEE)
     return hpb_fail(HPB_ERR_INVALID, "muscl limiter %d not supported (gmm, minmod, vanleer, superbee)", c.muscl_limiter);
-  if ((c.hyp_scheme == HPB_SCHEME_CRWENO5 || c.hyp_scheme == HPB_SCHEME_CUPW5) && c.interp_char)
+  if (hpb_scheme_is_compact(c.hyp_scheme) && c.interp_char && c.nvars > 1)
     for (int d = 0; d < nd; d++)
       if (c.iproc[d] != 1)     // blocktridiagLU.c stages 2-3 (block reduced system across ranks) are not built
-        return hpb_fail(HPB_ERR_INVALID, "characteristic compact schemes (crweno5, cupw5) need iproc = 1 along every dimension "
+        return hpb_fail(HPB_ERR_INVALID, "characteristic compact schemes (crweno5, hcweno5, cupw5) need iproc = 1 along every dimension "
                                          "(component-wise ones run decomposed)");
-  if (c.hyp_scheme == HPB_SCHEME_CRWENO5 || c.hyp_scheme == HPB_SCHEME_CUPW5)
+  if (hpb_scheme_is_compact(c.hyp_scheme))
     for (int d = 0; d < nd; d++)
       if (c.iproc[d] > 64) return hpb_fail(HPB_ERR_INVALID, "compact schemes: at most 64 ranks along one dimension");
   if (c.nzones > HPB_MAX_ZONES) return hpb_fail(HPB_ERR_INVALID, "too many boundary zones");
@@ -237,6 +237,7 @@ int hpb_setup_host(hpb_solver* h)
   P.interp_char = (c.interp_char && c.nvars > 1) ? 1 : 0;        // WENOInitialize.c:156
   P.upwind = c.upwind; P.par_scheme = c.par_scheme; P.has_grav = has_grav ? 1 : 0;
   P.scheme = c.hyp_scheme; P.muscl_limiter = c.muscl_limiter; P.muscl_eps = c.muscl_eps;
+  P.hc_rc = c.weno_rc; P.hc_xi = c.weno_xi;
   P.eps = c.weno_eps; P.gamma = c.gamma;
   P.Re = c.Re / c.Minf;                                          // NavierStokes3DInitialize.c:368
   P.Pr = c.Pr;

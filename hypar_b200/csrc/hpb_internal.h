@@ -25,11 +25,16 @@ struct Geom {
                                 // where the compact schemes close their systems (Interp1PrimFifthOrderCRWENO.c:158-160)
 };
 
+// the schemes that solve a (block) tridiagonal system per grid line / that keep nonlinear weights (InitializeSolvers.c:262-346)
+static inline bool hpb_scheme_is_compact(int s) { return s == HPB_SCHEME_CRWENO5 || s == HPB_SCHEME_CUPW5 || s == HPB_SCHEME_HCWENO5; }
+static inline bool hpb_scheme_has_weights(int s) { return s == HPB_SCHEME_WENO5 || s == HPB_SCHEME_CRWENO5 || s == HPB_SCHEME_HCWENO5; }
+
 struct Phys {
   int model, weno, no_limiting, interp_char, upwind, par_scheme, has_grav;
   int scheme;                        // HPB_SCHEME_*
   int muscl_limiter;                 // HPB_LIMITER_* (muscl2)
   double muscl_eps;                  // muscl3
+  double hc_rc, hc_xi;               // hcweno5: weno.inp rc, xi
   double eps, gamma, Re, Pr, RT;     // Re already / Minf ; RT = p0/rho0
   double grav[3];
   double adv[15], diff[15];

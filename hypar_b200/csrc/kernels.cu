@@ -939,6 +939,21 @@ __global__ void k_interp(Geom G, Phys ph, const double* __restrict__ fC, const d
 // Interp1PrimFifthOrderCRWENO.c:80-237, Interp1PrimFifthOrderCompactUpwind.c:73-228. One tridiagonal system per
 // grid line and component; rows of the two physical-boundary interfaces are the explicit WENO5 / fifth-order
 // upwind value (a = c = 0, b = 1). Row arrays share the interface layout [v*ni + q]; r is solved in place.
+// hcweno5 (Interp1PrimFifthOrderHCWENO.c:65-230): rows (sigma/2, 1, sigma/6) and the right-hand side
+// sigma fCompact + (1 - sigma) fWENO with the hybridisation parameter sigma of :153-168 (0 on the physical boundary).
+__device__ __forceinline__ double hcweno_sigma(const Phys& ph, bool bnd, double fm2, double fm1, double fp1, double fp2)
+{
+  if (bnd) return 0.0;
+#define HC_ABS(a) ((a) < 0 ? -(a) : (a))
+  const double cuckoo = (0.9 * ph.hc_rc / (1.0 - 0.9 * ph.hc_rc)) * ph.hc_xi * ph.hc_xi;
+  const double df_jm12 = fm1 - fm2, df_jp12 = fp1 - fm1, df_jp32 = fp2 - fp1;
+  const double r_j   = (HC_ABS(2 * df_jp12 * df_jm12) + cuckoo) / (df_jp12 * df_jp12 + df_jm12 * df_jm12 + cuckoo);
+  const double r_jp1 = (HC_ABS(2 * df_jp32 * df_jp12) + cuckoo) / (df_jp32 * df_jp32 + df_jp12 * df_jp12 + cuckoo);
+#undef HC_ABS
+  const double r_int = (r_j < r_jp1 ? r_j : r_jp1);
+  return ((r_int / ph.hc_rc) < 1.0 ? (r_int / ph.hc_rc) : 1.0);
+}
+
 __global__ void k_compact_rows(Geom G, Phys ph, const double* __restrict__ fC, const double* __restrict__ w, int upw,
                                int dir, int uflag, double* __restrict__ A, double* __restrict__ B,
                                double* __restrict__ Cc, double* __restrict__ R)
@@ -964,7 +979,20 @@ __global__ void k_compact_rows(Geom G, Phys ph, const double* __restrict__ fC, c
     const double fm3 = fC[v * G.npg + ps[0]], fm2 = fC[v * G.npg + ps[1]], fm1 = fC[v * G.npg + ps[2]],
                  fp1 = fC[v * G.npg + ps[3]], fp2 = fC[v * G.npg + ps[4]];
     double a, b, c, r;
-    if (ph.scheme == HPB_SCHEME_CRWENO5) {
+    if (ph.scheme == HPB_SCHEME_HCWENO5) {      // the candidates are always the WENO5 ones (HCWENO.c:140-143)
+      const double one_half = 1.0 / 2.0;
+      const double w1 = w[((3 * blk + 0) * NV + v) * ni + q], w2 = w[((3 * blk + 1) * NV + v) * ni + q],
+                   w3 = w[((3 * blk + 2) * NV + v) * ni + q];
+      const double f1 = (2 * one_sixth) * fm3 - (7.0 * one_sixth) * fm2 + (11.0 * one_sixth) * fm1;
+      const double f2 = (-one_sixth) * fm2 + (5.0 * one_sixth) * fm1 + (2 * one_sixth) * fp1;
+      const double f3 = (2 * one_sixth) * fm1 + (5 * one_sixth) * fp1 - (one_sixth) * fp2;
+      const double sigma = hcweno_sigma(ph, bnd, fm2, fm1, fp1, fp2);
+      if (upw > 0) { a = one_half * sigma; b = 1.0; c = one_sixth * sigma; }
+      else         { c = one_half * sigma; b = 1.0; a = one_sixth * sigma; }
+      const double fWENO = w1 * f1 + w2 * f2 + w3 * f3;
+      const double fCompact = one_sixth * (one_third * fm2 + 19.0 * one_third * fm1 + 10.0 * one_third * fp1);
+      r = sigma * fCompact + (1.0 - sigma) * fWENO;
+    } else if (ph.scheme == HPB_SCHEME_CRWENO5) {
       const double w1 = w[((3 * blk + 0) * NV + v) * ni + q], w2 = w[((3 * blk + 1) * NV + v) * ni + q],
                    w3 = w[((3 * blk + 2) * NV + v) * ni + q];
       double f1, f2, f3;
@@ -1253,6 +1281,34 @@ __global__ void k_compact_rows_char(Geom G, Phys ph, const double* __restrict__ 
     }
     const double fm3 = c[0], fm2 = c[1], fm1 = c[2], fp1 = c[3], fp2 = c[4];
     double lo, di, hi, f;
+    if (ph.scheme == HPB_SCHEME_HCWENO5) {      // Interp1PrimFifthOrderHCWENOChar.c:171-230
+      const double one_half = 1.0 / 2.0;
+      const double w1 = w[((3 * blk + 0) * NV + v) * ni + q], w2 = w[((3 * blk + 1) * NV + v) * ni + q],
+                   w3 = w[((3 * blk + 2) * NV + v) * ni + q];
+      double f1, f2, f3;
+      if (bnd) {
+        f1 = (2 * one_sixth) * fm3 - (7.0 * one_sixth) * fm2 + (11.0 * one_sixth) * fm1;
+        f2 = (-one_sixth) * fm2 + (5.0 * one_sixth) * fm1 + (2 * one_sixth) * fp1;
+        f3 = (2 * one_sixth) * fm1 + (5 * one_sixth) * fp1 - (one_sixth) * fp2;
+      } else {
+        f1 = (one_sixth) * (fm2 + 5 * fm1);
+        f2 = (one_sixth) * (5 * fm1 + fp1);
+        f3 = (one_sixth) * (fm1 + 5 * fp1);
+      }
+      const double sigma = hcweno_sigma(ph, bnd, fm2, fm1, fp1, fp2);
+      const double fWENO = w1 * f1 + w2 * f2 + w3 * f3;
+      const double fCompact = one_sixth * (one_third * fm2 + 19.0 * one_third * fm1 + 10.0 * one_third * fp1);
+      F[((long long)iI * NV + v) * Nsys + sys] = sigma * fCompact + (1.0 - sigma) * fWENO;
+#pragma unroll
+      for (int k = 0; k < NV; k++) {           // sigma = 0 rows keep the reference's signed zeros: no shortcut
+        double a, b, cc;
+        if (upw > 0) { a = (one_half * sigma) * L[v * NV + k]; b = (1.0) * L[v * NV + k]; cc = (one_sixth * sigma) * L[v * NV + k]; }
+        else         { cc = (one_half * sigma) * L[v * NV + k]; b = (1.0) * L[v * NV + k]; a = (one_sixth * sigma) * L[v * NV + k]; }
+        const long long e = ((long long)iI * NV * NV + v * NV + k) * Nsys + sys;
+        A[e] = a; B[e] = b; Cc[e] = cc;
+      }
+      continue;
+    }
     if (ph.scheme == HPB_SCHEME_CRWENO5) {
       const double w1 = w[((3 * blk + 0) * NV + v) * ni + q], w2 = w[((3 * blk + 1) * NV + v) * ni + q],
                    w3 = w[((3 * blk + 2) * NV + v) * ni + q];
@@ -1710,7 +1766,7 @@ void hyperbolic_pieces(hpb_solver* h, const double* u, double* out, bool negate,
 {
   const Geom& G = h->geo;
   const bool grav = h->phys.has_grav;
-  const bool has_w = (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5);
+  const bool has_w = hpb_scheme_has_weights(h->cfg.hyp_scheme);
   double *fC = h->d_cell[0], *uC = h->d_cell[1];
   double *fL = h->d_iface[1], *fR = h->d_iface[2], *uL = h->d_iface[3], *uR = h->d_iface[4];
   long long wo = 0;              // the weights of direction d live where the fine-grained API keeps them (capi.cu: woff)
@@ -1849,7 +1905,7 @@ static int weno_interp_group(hpb_solver** hs, int n, double* const* fI, double* 
 {
   for (int r = 0; r < n; r++) { cudaSetDevice(hs[r]->device); weno_interp(hs[r], fI[r], fC[r], u[r], w[r], upw, dir, uflag); }
   const hpb_solver* h0 = hs[0];
-  const bool compact = (h0->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h0->cfg.hyp_scheme == HPB_SCHEME_CUPW5);
+  const bool compact = hpb_scheme_is_compact(h0->cfg.hyp_scheme);
   if (compact && h0->cfg.iproc[dir] > 1) return compact_solve_group(hs, n, dir, fI);
   return HPB_OK;
 }
@@ -1872,7 +1928,7 @@ int hyperbolic_pieces_group(hpb_solver** hs, int n, const double* const* u, doub
       w[r] = h->d_w + wo[r];
       wo[r] += 12 * ni * G.nvars;
       flux(h, u[r], fC[r], d);
-      if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5) { weno_weights(h, fC[r], u[r], d, w[r]); h->w_valid = true; }
+      if (hpb_scheme_has_weights(h->cfg.hyp_scheme)) { weno_weights(h, fC[r], u[r], d, w[r]); h->w_valid = true; }
       modified_solution(h, u[r], uC[r]);
     }
     int rc;
@@ -2056,14 +2112,14 @@ void weno_interp(hpb_solver* h, double* fI, const double* fC, const double* u, c
 {
   const Geom& G = h->geo;
   const int M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
-  if (h->cfg.hyp_scheme >= HPB_SCHEME_UPW5) {
+  if (h->cfg.hyp_scheme >= HPB_SCHEME_UPW5 && !hpb_scheme_is_compact(h->cfg.hyp_scheme)) {
 #define CALL(M_) k_interp_upw5<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, fC, u, upw, dir, fI)
     MODEL_SWITCH(h->cfg.model, CALL)
 #undef CALL
     LAUNCHED(h);
     return;
   }
-  if ((h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h->cfg.hyp_scheme == HPB_SCHEME_CUPW5) && h->phys.interp_char) {
+  if (hpb_scheme_is_compact(h->cfg.hyp_scheme) && h->phys.interp_char) {
     // characteristic variant: block rows, then one thread per grid line (block tridiagonal system)
     int T0, T1;
     if (dir == 0) { T0 = M[1]; T1 = M[2]; } else if (dir == 1) { T0 = M[0]; T1 = M[2]; } else { T0 = M[0]; T1 = M[1]; }
@@ -2077,7 +2133,7 @@ void weno_interp(hpb_solver* h, double* fI, const double* fC, const double* u, c
     LAUNCHED(h); LAUNCHED(h);
     return;
   }
-  if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5 || h->cfg.hyp_scheme == HPB_SCHEME_CUPW5) {
+  if (hpb_scheme_is_compact(h->cfg.hyp_scheme)) {
     // rows, then one thread per (line, component) system; the solution replaces the right-hand side in fI
     k_compact_rows<<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, fC, w, upw, dir, uflag,
                                                                     h->d_tri[0], h->d_tri[1], h->d_tri[2], fI); LAUNCHED(h);
@@ -2143,7 +2199,7 @@ void boundary_flux(hpb_solver* h, const double* u, int d, double* sbi)
     for (int k = 0; k < d; k++) wo += 12LL * (G.N[0] + (k == 0)) * (G.N[1] + (k == 1)) * (G.N[2] + (k == 2)) * G.nvars;
     double* w = h->d_w + wo;
     flux(h, u, fC, d);
-    if (h->cfg.hyp_scheme == HPB_SCHEME_CRWENO5) weno_weights(h, fC, u, d, w);
+    if (hpb_scheme_has_weights(h->cfg.hyp_scheme)) weno_weights(h, fC, u, d, w);
     modified_solution(h, u, uC);
     weno_interp(h, h->d_iface[3], uC, u, w,  1, d, 1);
     weno_interp(h, h->d_iface[4], uC, u, w, -1, d, 1);

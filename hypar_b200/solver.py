@@ -25,7 +25,7 @@ BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "d
 PAR_TYPES = {"nonconservative-1stage": 0, "nonconservative-1.5stage": 1, "nonconservative-2stage": 2, "conservative-1stage": 3}
 UPWINDS = {"roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 RK_TYPES = {"44": 0, "ssprk3": 1, "tvdrk3": 1, "1fe": 2, "22": 3, "33": 4}
-SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6, "muscl2": 7, "muscl3": 8}
+SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6, "muscl2": 7, "muscl3": 8, "hcweno5": 9}
 LIMITERS = {"gmm": 0, "minmod": 1, "vanleer": 2, "superbee": 3}
 FIELD_U, FIELD_QDERIVX, FIELD_QDERIVY = 0, 1, 2
 
@@ -63,7 +63,7 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     c.model = MODELS[model]
     scheme = str(solver.get("hyp_space_scheme", "1"))
     if scheme not in SCHEMES:
-        raise HyParB200Error(f"hyp_space_scheme '{scheme}' is not on the B200 path (weno5, crweno5, cupw5, upw5, 1, 2, 4, muscl2, muscl3)")
+        raise HyParB200Error(f"hyp_space_scheme '{scheme}' is not on the B200 path (weno5, crweno5, hcweno5, cupw5, upw5, 1, 2, 4, muscl2, muscl3)")
     c.hyp_scheme = SCHEMES[scheme]
     mu = muscl or {}
     c.muscl_eps = float(mu.get("epsilon", 1e-3))                         # MUSCLInitialize.c:26-27
@@ -93,6 +93,7 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     c.weno_type = 3 if int(w.get("yc", 0)) else 2 if int(w.get("borges", 0)) else 1 if int(w.get("mapped", 0)) else 0
     c.no_limiting = int(w.get("no_limiting", 0))
     c.weno_eps = float(w.get("epsilon", 1e-6))
+    c.weno_rc, c.weno_xi = float(w.get("rc", 0.3)), float(w.get("xi", 0.001))     # WENOInitialize.c:57-58
     ph = physics or {}
     if c.model == 0:
         c.upwind = 0

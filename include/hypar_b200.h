@@ -76,6 +76,7 @@ extern "C" {
 #define HPB_SCHEME_FOURTH  6    /* "4": fourth-order central (Interp1PrimFourthOrderCentral.c) */
 #define HPB_SCHEME_MUSCL2  7    /* "muscl2": Interp1PrimSecondOrderMUSCL.c, limiter from muscl.inp */
 #define HPB_SCHEME_MUSCL3  8    /* "muscl3": Interp1PrimThirdOrderMUSCL.c (Koren), epsilon from muscl.inp */
+#define HPB_SCHEME_HCWENO5 9    /* "hcweno5": hybrid compact-WENO5 (Interp1PrimFifthOrderHCWENO.c), component-wise; rc, xi from weno.inp */
 /* muscl.inp `limiter` -- MUSCLInitialize.c:62-75, src/LimiterFunctions/ */
 #define HPB_LIMITER_GMM      0
 #define HPB_LIMITER_MINMOD   1
@@ -172,6 +173,7 @@ typedef struct hpb_config {
                                           advection field on the GLOBAL grid, [point][ndims*nvars], points ordered like the
                                           solution in initial.inp (no ghosts); NULL = constant advection[]. Copied by
                                           hpb_create.                                                          */
+  double weno_rc, weno_xi;             /* weno.inp `rc`, `xi` (WENOInitialize.c:53-54: 0.3, 0.001): hybridisation parameters of hcweno5 */
   int    par_space_type;               /* HPB_PAR_*: LinearADR with a non-zero diffusion coefficient is on the device only
                                           as nonconservative-1stage -- the other forms are different arithmetic
                                           (ParabolicFunctionNC2Stage.c / NC1_5Stage / Cons1Stage) and fail in hpb_create */

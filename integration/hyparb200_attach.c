@@ -222,6 +222,7 @@ static int attach_one(SimulationObject *sim, int n, int nsims)
   int scheme = -1;
   if      (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_WENO_))           scheme = HPB_SCHEME_WENO5;
   else if (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_CRWENO_))         scheme = HPB_SCHEME_CRWENO5;
+  else if (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_HCWENO_))         scheme = HPB_SCHEME_HCWENO5;
   else if (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_COMPACT_UPWIND_)) scheme = HPB_SCHEME_CUPW5;
   else if (!strcmp(s->spatial_scheme_hyp, _FIFTH_ORDER_UPWIND_))         scheme = HPB_SCHEME_UPW5;
   else if (!strcmp(s->spatial_scheme_hyp, _FIRST_ORDER_UPWIND_))         scheme = HPB_SCHEME_FIRST;
@@ -230,7 +231,7 @@ static int attach_one(SimulationObject *sim, int n, int nsims)
   else if (!strcmp(s->spatial_scheme_hyp, _SECOND_ORDER_MUSCL_))         scheme = HPB_SCHEME_MUSCL2;
   else if (!strcmp(s->spatial_scheme_hyp, _THIRD_ORDER_MUSCL_))          scheme = HPB_SCHEME_MUSCL3;
   if (scheme < 0 || strcmp(s->time_scheme, _RK_) || strcmp(s->SplitHyperbolicFlux, "no") || s->flag_ib) {
-    fprintf(stderr, "hyparb200_attach: only weno5 / crweno5 / cupw5 / upw5 + explicit RK without flux splitting / "
+    fprintf(stderr, "hyparb200_attach: only weno5 / crweno5 / hcweno5 / cupw5 / upw5 / 1 / 2 / 4 / muscl2 / muscl3 + explicit RK without flux splitting / "
                     "immersed boundaries is on the B200 path\n");
     return 1;
   }
@@ -262,10 +263,10 @@ static int attach_one(SimulationObject *sim, int n, int nsims)
     c.muscl_limiter = !strcmp(mp->limiter_type, _LIM_MM_) ? HPB_LIMITER_MINMOD : !strcmp(mp->limiter_type, _LIM_VANLEER_) ? HPB_LIMITER_VANLEER
                     : !strcmp(mp->limiter_type, _LIM_SUPERBEE_) ? HPB_LIMITER_SUPERBEE : HPB_LIMITER_GMM;
   }
-  if (scheme == HPB_SCHEME_WENO5 || scheme == HPB_SCHEME_CRWENO5) {   /* s->interp is NULL for the linear schemes */
+  if (scheme == HPB_SCHEME_WENO5 || scheme == HPB_SCHEME_CRWENO5 || scheme == HPB_SCHEME_HCWENO5) {   /* s->interp is NULL for the linear schemes */
     WENOParameters *w = (WENOParameters*) s->interp;
     c.weno_type = w->yc ? HPB_WENO_YC : w->borges ? HPB_WENO_Z : w->mapped ? HPB_WENO_M : HPB_WENO_JS;
-    c.no_limiting = w->no_limiting;  c.weno_eps = w->eps;
+    c.no_limiting = w->no_limiting;  c.weno_eps = w->eps;  c.weno_rc = w->rc;  c.weno_xi = w->xi;
   }
 
   if (!strcmp(s->model, _NAVIER_STOKES_3D_)) {

@@ -26,7 +26,7 @@ MODELS = {"linear-advection-diffusion-reaction": 0, "euler1d": 1, "navierstokes2
 BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "dirichlet": 4, "subsonic-inflow": 5,
            "subsonic-outflow": 6, "subsonic-ambivalent": 7, "supersonic-inflow": 8, "supersonic-outflow": 9, "sponge": 10}
 UPWINDS = {"default": 0, "roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
-SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6, "muscl2": 7, "muscl3": 8}
+SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6, "muscl2": 7, "muscl3": 8, "hcweno5": 9}
 LIMITERS = {"gmm": 0, "minmod": 1, "vanleer": 2, "superbee": 3}
 
 
@@ -52,7 +52,7 @@ class Ctx(C.Structure):
                 ("x", C.POINTER(C.c_double)), ("dxinv", C.POINTER(C.c_double)),
                 ("grav_f", C.POINTER(C.c_double)), ("grav_g", C.POINTER(C.c_double)),
                 ("scheme", C.c_int), ("muscl_limiter", C.c_int), ("muscl_eps", C.c_double), ("grav_type", C.c_int),
-                ("adv_field", C.POINTER(C.c_double))]
+                ("adv_field", C.POINTER(C.c_double)), ("weno_rc", C.c_double), ("weno_xi", C.c_double)]
 
 
 _lib = None
@@ -335,6 +335,7 @@ class Setup:
         c.weno_type = 3 if int(w.get("yc", 0)) else 2 if int(w.get("borges", 0)) else 1 if int(w.get("mapped", 0)) else 0
         c.no_limiting = int(w.get("no_limiting", 0))
         c.weno_eps = float(w.get("epsilon", 1e-6))
+        c.weno_rc, c.weno_xi = float(w.get("rc", 0.3)), float(w.get("xi", 0.001))     # WENOInitialize.c:57-58
         c.interp_char = int(s.get("hyp_interp_type", "characteristic") == "characteristic")
         up = ph.get("upwinding", "roe" if c.model in (1, 3) else "default")
         c.upwind = UPWINDS.get(up, 0) if c.model != 0 else 0

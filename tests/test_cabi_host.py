@@ -180,7 +180,7 @@ def test_decomposed_zone_extents_of_open_boundaries_and_sponges():
 
 
 @pytest.mark.parametrize("mutate, msg", [
-    (lambda c: c.solver.__setitem__("hyp_space_scheme", "hcweno5"), "weno5"),
+    (lambda c: c.solver.__setitem__("hyp_space_scheme", "weno7"), "weno5"),
     # compact schemes split among ranks: component-wise ones run (tests/test_gpu_decomposed.py), characteristic ones do not
     (lambda c: (c.solver.__setitem__("hyp_space_scheme", "cupw5"), c.solver.__setitem__("iproc", [1, 2, 1]),
                 c.solver.__setitem__("hyp_interp_type", "characteristic")), "iproc"),
@@ -221,7 +221,7 @@ def test_linear_diffusion_in_another_form_fails_loudly(pst):
         Solver.from_case(case)
 
 
-@pytest.mark.parametrize("scheme", ["crweno5", "cupw5", "upw5", "1", "2", "4", "muscl2", "muscl3"])
+@pytest.mark.parametrize("scheme", ["crweno5", "hcweno5", "cupw5", "upw5", "1", "2", "4", "muscl2", "muscl3"])
 def test_compact_and_linear_schemes_are_accepted(scheme):
     """crweno5 / cupw5 (one rank per line) and upw5 (any decomposition) set up like weno5"""
     case = cases.ns3d_rising_bubble((12, 12, 12), "yc", scheme=scheme)

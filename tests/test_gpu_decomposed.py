@@ -176,7 +176,9 @@ def _compact_cases():
          cases.ns3d_turbulence((26, 25, 27), "z", iproc=(2, 2, 2), scheme="crweno5"),          # viscous, 8 ranks
          cases.ns3d_rising_bubble((14, 26, 12), "yc", iproc=(1, 2, 1), scheme="crweno5"),       # gravity source reconstructions
          cases.ns2d_vortex((28, 40), "js", scheme="cupw5", iproc=(1, 3)),
-         cases.ns3d_density_wave((16, 12, 26), "js", iproc=(1, 1, 4), scheme="crweno5")]        # 4 ranks on one line
+         cases.ns3d_density_wave((16, 12, 26), "js", iproc=(1, 1, 4), scheme="crweno5"),        # 4 ranks on one line
+         cases.ns2d_vortex((40, 27), "z", iproc=(2, 2), scheme="hcweno5"),                      # hybrid compact-WENO5 across ranks
+         cases.ns3d_rising_bubble((14, 26, 12), "mapped+rc0.2", iproc=(1, 3, 1), scheme="hcweno5")]
     a = cases.linear_advection_sine(96, "z", scheme="crweno5")
     a.solver["iproc"] = [3]
     b = cases.euler1d_sod(101, "js", interp="components", upwinding="roe", scheme="cupw5")

@@ -47,6 +47,7 @@ CASES = [
     _prep(cases.ns2d_vortex((32, 24), "mapped", scheme="crweno5")),
     _prep(cases.ns3d_rising_bubble((12, 16, 10), "yc", scheme="crweno5"), n_iter=4, screen=1),
     _prep(cases.euler1d_sod(101, "js", interp="components", scheme="cupw5")),
+    _prep(cases.ns2d_vortex((32, 24), "z+rc0.5", scheme="hcweno5")),                    # weno.inp rc read by HyPar, handed over by the glue
     _prep(cases.ns2d_vortex((32, 24), "js", upwinding="roe", interp="characteristic")),       # NavierStokes2D char + Roe
     _prep(cases.ns2d_rising_bubble((24, 28), "yc"), n_iter=4, screen=1),                      # NavierStokes2D + gravity
     _prep(cases.ns_channel((28, 24), "js"), n_iter=4),                                        # inflow / outflow / walls

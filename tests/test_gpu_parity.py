@@ -167,6 +167,17 @@ def _cases():
     C.append(cases.ns_channel((28, 3), "js"))
     C.append(cases.ns2d_vortex((3, 24), "mapped", scheme="crweno5"))
     C.append(cases.linear_advection_nd((3, 20), "js", diffusion=[0.01, 0.02]))
+    # hybrid compact-WENO5 (Interp1PrimFifthOrderHCWENO.c / ...HCWENOChar.c): component-wise and characteristic
+    C.append(cases.linear_advection_sine(96, "z", scheme="hcweno5"))
+    C.append(cases.euler1d_sod(151, "mapped+rc0.5", interp="components", upwinding="rusanov", scheme="hcweno5"))
+    C.append(cases.euler1d_sod(101, "js", scheme="hcweno5"))
+    C.append(cases.euler1d_sod(101, "yc+rc0.5+xi0.01", upwinding="llf-char", gravity=1.0, scheme="hcweno5"))
+    C.append(cases.ns2d_vortex((28, 40), "js", scheme="hcweno5"))
+    C.append(cases.ns2d_vortex((24, 20), "z", upwinding="roe", interp="characteristic", scheme="hcweno5"))
+    C.append(cases.ns3d_turbulence((14, 10, 12), "z", scheme="hcweno5"))
+    C.append(cases.ns3d_rising_bubble((10, 14, 12), "mapped+rc0.2", scheme="hcweno5"))
+    C.append(cases.with_characteristic(cases.ns3d_turbulence((12, 10, 14), "mapped", viscous=True, upwinding="roe", scheme="hcweno5")))
+    C.append(cases.burgers_nd((20, 24), "yc", scheme="hcweno5"))
     return C
 
 
@@ -345,7 +356,7 @@ def test_function_pointer_pieces(need_gpu, case):
         uc_in = np.where(np.isfinite(uc_ref), uc_ref, 0.0)
         w_ref = O.weno_weights(f_in, u, d)
         sv.SetInterpLimiterVar(f_in, u, d)
-        if case.solver["hyp_space_scheme"] in ("weno5", "crweno5"):     # the linear schemes keep no weights
+        if case.solver["hyp_space_scheme"] in ("weno5", "crweno5", "hcweno5"):     # the linear schemes keep no weights
             w = sv.GetInterpWeights(d)
             assert np.array_equal(w, w_ref), f"weights dir {d}: {np.abs(w - w_ref).max():.3e}"
         outs = {}

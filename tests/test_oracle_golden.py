@@ -40,7 +40,7 @@ def same(a, b, what):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 41
+    assert len(GOLDEN) >= 45
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -226,6 +226,14 @@ def _live_cases():
         cases.euler1d_sod(101, "mapped", interp="components", upwinding="llf-char", gravity=1.0),
         cases.euler1d_sod(101, "z", upwinding="roe", gravity=1.0, gravity_type=1),
         cases.euler1d_sod(101, "yc", interp="components", upwinding="llf-char", gravity=0.5, scheme="crweno5"),
+        # hybrid compact-WENO5 (second half), component-wise and characteristic, default and other rc / xi
+        cases.linear_advection_sine(96, "mapped", scheme="hcweno5"),
+        cases.euler1d_sod(151, "mapped+rc0.5", interp="components", upwinding="rusanov", scheme="hcweno5"),
+        cases.euler1d_sod(101, "js", scheme="hcweno5"),
+        cases.ns2d_vortex((24, 40), "js", scheme="hcweno5"),
+        cases.ns3d_turbulence((14, 10, 12), "z+xi0.01", scheme="hcweno5"),
+        cases.with_characteristic(cases.ns3d_turbulence((12, 10, 14), "mapped", viscous=True, upwinding="roe", scheme="hcweno5")),
+        cases.ns3d_rising_bubble((10, 14, 12), "yc", scheme="hcweno5"),
         # the other explicit RK tableaux (TimeExplicitRKInitialize.c:27-79) and forward Euler (TimeForwardEuler.c)
         cases.with_time_scheme(cases.linear_advection_sine(96, "js"), "rk", "1fe"),
         cases.with_time_scheme(cases.euler1d_sod(101, "mapped"), "rk", "22"),

@@ -69,6 +69,11 @@ GOLDEN = [
     ("burgers2d_z", "burgers_nd", dict(n=(24, 20), weno="z"), "hypar_ref", True),
     ("linadvvar2d_js", "linear_advection_varying", dict(n=(24, 20), weno="js"), "hypar_ref", True),
     ("linadvvar1d_mapped_ext", "linear_advection_varying", dict(n=(80,), weno="mapped", periodic=False, tstype="ssprk3"), "hypar_ref_mpi1", True),
+    # hybrid compact-WENO5 (Interp1PrimFifthOrderHCWENO.c / ...HCWENOChar.c), default and non-default rc / xi
+    ("c1_linadv_hcweno_z", "linear_advection_sine", dict(n=64, weno="z", scheme="hcweno5"), "hypar_ref", True),
+    ("c3_vortex_hcweno_js_char_roe", "ns2d_vortex", dict(n=(20, 16), weno="js+rc0.5+xi0.01", upwinding="roe", interp="characteristic", scheme="hcweno5"), "hypar_ref_mpi1", True),
+    ("c5b_bubble_hcweno_mapped", "ns3d_rising_bubble", dict(n=(12, 16, 10), weno="mapped+rc0.2", scheme="hcweno5"), "hypar_ref_mpi1", False),
+    ("c2_sod_hcweno_yc_char_llf_gravity", "euler1d_sod", dict(n=101, weno="yc", upwinding="llf-char", gravity=1.0, scheme="hcweno5"), "hypar_ref", False),
     ("c2_sod_upw5_comp_rusanov", "euler1d_sod", dict(n=101, weno="js", interp="components", upwinding="rusanov", scheme="upw5"), "hypar_ref", True),
 ]
 
