@@ -41,7 +41,7 @@ class Config(C.Structure):
         ("hyp_scheme", C.c_int), ("muscl_limiter", C.c_int), ("muscl_eps", C.c_double),
         ("gravity_type", C.c_int), ("advection_field", C.POINTER(C.c_double)),
         ("weno_rc", C.c_double), ("weno_xi", C.c_double),
-        ("par_space_type", C.c_int),
+        ("par_space_type", C.c_int), ("glm_ee_mode", C.c_int),
     ]
 
 
@@ -65,6 +65,7 @@ SYMBOLS = [
     "hpb_dev_get_stage_rhs", "hpb_nstages", "hpb_needs_viscous_exchange",
     "hpb_dev_VolumeIntegral", "hpb_dev_StageBoundaryIntegral", "hpb_dev_StepBoundaryIntegral", "hpb_BoundaryIntegral",
     "hpb_CalculateConservationError", "hpb_dev_ErrorSums",
+    "hpb_dev_get_aux_solution", "hpb_dev_set_aux_solution", "hpb_dev_GLMGEEErrorSums", "hpb_glmgee_gamma",
     "hpb_stream", "hpb_synchronize", "hpb_kernel_launch_count", "hpb_tma_launch_count", "hpb_profile_enable", "hpb_profile_query", "hpb_fp64_issue_peak",
 ]
 
@@ -156,6 +157,11 @@ def load():
     L.hpb_BoundaryIntegral.argtypes = [vp, dp, dp]
     L.hpb_CalculateConservationError.argtypes = [C.c_int, dp, dp, dp, dp]
     L.hpb_dev_ErrorSums.argtypes = [vp, dp, dp]
+    L.hpb_dev_get_aux_solution.argtypes = [vp, dp]
+    L.hpb_dev_set_aux_solution.argtypes = [vp, dp]
+    L.hpb_dev_GLMGEEErrorSums.argtypes = [vp, dp, dp]
+    L.hpb_glmgee_gamma.argtypes = [vp]
+    L.hpb_glmgee_gamma.restype = C.c_double
     L.hpb_stream.argtypes = [vp]
     L.hpb_stream.restype = vp
     L.hpb_kernel_launch_count.argtypes = [vp]

@@ -35,6 +35,7 @@ class Case:
     u0: np.ndarray                 # shape (N_{nd-1}, ..., N_0, nvars)
     muscl: Optional[Dict[str, object]] = None      # muscl.inp (epsilon, limiter) for muscl2 / muscl3
     advection_field: Optional[np.ndarray] = None   # LinearADR `advection_filename advection`: shape (N_{nd-1},...,N_0, ndims*nvars)
+    glm_gee: Optional[Dict[str, object]] = None    # glm_gee.inp (ee_mode yeps | yyt) for time_scheme glm-gee
 
     @property
     def ndims(self) -> int:
@@ -57,6 +58,8 @@ class Case:
             hypario.write_keyword_file(os.path.join(d, "weno.inp"), self.weno)
         if self.muscl is not None:
             hypario.write_keyword_file(os.path.join(d, "muscl.inp"), self.muscl)
+        if self.glm_gee is not None:
+            hypario.write_keyword_file(os.path.join(d, "glm_gee.inp"), self.glm_gee)
         ipt = str(self.solver.get("ip_file_type", "binary"))
         if self.advection_field is not None:           # same layout and flavour as initial.inp (ReadArray.c:173-256)
             hypario.write_initial(os.path.join(d, "advection.inp"), self.x, self.advection_field, ipt)
@@ -76,12 +79,14 @@ def from_directory(path: str) -> Case:
     for k in ("advection", "diffusion", "gravity"):
         if k in ph:
             ph[k] = [float(v) for v in (ph[k] if isinstance(ph[k], (list, tuple)) else [ph[k]])]
-    wf, mf = os.path.join(path, "weno.inp"), os.path.join(path, "muscl.inp")
+    wf, mf, gf = os.path.join(path, "weno.inp"), os.path.join(path, "muscl.inp"), os.path.join(path, "glm_gee.inp")
     w = hypario.read_keyword_file(wf) if os.path.exists(wf) else None
     mu = hypario.read_keyword_file(mf) if os.path.exists(mf) else None
+    gg = hypario.read_keyword_file(gf) if os.path.exists(gf) else None
     ipt = str(s.get("ip_file_type", "ascii"))
     x, u0 = hypario.read_initial(os.path.join(path, "initial.inp"), s["size"], nv, ipt)
-    case = Case(name=os.path.basename(os.path.normpath(path)), solver=s, boundary=b, physics=ph, weno=w, x=x, u0=u0, muscl=mu)
+    case = Case(name=os.path.basename(os.path.normpath(path)), solver=s, boundary=b, physics=ph, weno=w, x=x, u0=u0, muscl=mu,
+                glm_gee=gg)
     if str(ph.get("advection_filename", "none")) != "none":
         fn = os.path.join(path, str(ph["advection_filename"]) + ".inp")
         if os.path.exists(fn):
@@ -160,6 +165,22 @@ def with_time_scheme(case: "Case", time_scheme: str, tstype: str = " ") -> "Case
         del case.solver["time_scheme_type"]          # no type keyword for forward Euler (ReadInputs.c:131)
     case.name += f"_{time_scheme}{'' if time_scheme == 'euler' else tstype}"
     return case
+
+
+def with_glmgee(case: "Case", tstype: str, ee_mode: Optional[str] = None) -> "Case":
+    """the same case advanced by a general linear method with global error estimation (solver.inp time_scheme glm-gee,
+    time_scheme_type 23 | 24 | 25i | 35 | exrk2a | rk32g1 | rk285ex; glm_gee.inp ee_mode yeps (default) | yyt)"""
+    case = with_time_scheme(case, "glm-gee", tstype)
+    if ee_mode is not None:
+        case.glm_gee = {"ee_mode": ee_mode}
+        case.name += "_" + ee_mode
+    return case
+
+
+def glmgee(base: str, tstype: str, ee_mode: Optional[str] = None, **kwargs) -> "Case":
+    """builder form of with_glmgee (fixtures name a builder and its keyword arguments): base = name of a builder here"""
+    kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in kwargs.items()}
+    return with_glmgee(globals()[base](**kw), tstype, ee_mode)
 
 
 def with_characteristic(case: "Case") -> "Case":

@@ -178,7 +178,7 @@ static int ensure_generic(hpb_solver* h)
 }
 
 // boundary-flux bookkeeping (conservation_check): 6 slots of 2*ndims*nvars sums + the compact face scratch
-static constexpr int CONS_SLOT_LAST = 4, CONS_SLOT_STEP = 5, CONS_NSLOT = 6;
+static constexpr int CONS_SLOT_LAST = HPB_MAX_STAGES, CONS_SLOT_STEP = HPB_MAX_STAGES + 1, CONS_NSLOT = HPB_MAX_STAGES + 2;
 static int nbf(const hpb_solver* h) { return 2 * h->geo.ndims * h->geo.nvars; }
 static double* cons_slot(hpb_solver* h, int slot) { return h->d_cons + (size_t)slot * nbf(h); }
 static int ensure_conservation(hpb_solver* h)
@@ -201,6 +201,7 @@ static int alloc_main(hpb_solver* h)
   const long long n = ncell(h);
   TRY(dalloc(&h->d_u, n)); TRY(dalloc(&h->d_U, n));
   for (int s = 0; s < h->rk.ns; s++) TRY(dalloc(&h->d_Udot[s], n));
+  if (h->rk.glm) { TRY(dalloc(&h->d_aux, n)); TRY(dalloc(&h->d_aux2, n)); }
   if (fused_visc(h)) TRY(dalloc(&h->d_qd4, 12 * h->geo.npg));
   if (!fused_path(h) || (viscous_on(h) && !fused_visc(h))) TRY(ensure_generic(h));
   TRY(dalloc(&h->d_part, hpbk::diag_partial_size()));
@@ -276,9 +277,10 @@ extern "C" int hpb_destroy(hpb_solver* h)
   hpbc::comm_free(h);          // before the halo buffers go (it frees them itself when NCCL allocated them)
   double** ptrs[] = { &h->d_x, &h->d_dxinv, &h->d_gravf, &h->d_gravg, &h->d_u, &h->d_U, &h->d_fI, &h->d_sI,
                       &h->d_FV, &h->d_stage_aos, &h->d_w, &h->d_red, &h->d_qd4, &h->d_par, &h->d_src,
-                      &h->d_cons, &h->d_face, &h->d_part };
+                      &h->d_cons, &h->d_face, &h->d_part, &h->d_aux, &h->d_aux2 };
   for (double** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
-  for (int i = 0; i < 4; i++) { if (h->d_Udot[i]) cudaFree(h->d_Udot[i]); if (h->d_tmp[i]) cudaFree(h->d_tmp[i]); }
+  for (int i = 0; i < HPB_MAX_STAGES; i++) if (h->d_Udot[i]) cudaFree(h->d_Udot[i]);
+  for (int i = 0; i < 4; i++) if (h->d_tmp[i]) cudaFree(h->d_tmp[i]);
   for (int i = 0; i < 3; i++) if (h->d_QD[i]) cudaFree(h->d_QD[i]);
   for (int i = 0; i < 5; i++) if (h->d_iface[i]) cudaFree(h->d_iface[i]);
   for (int i = 0; i < 2; i++) if (h->d_cell[i]) cudaFree(h->d_cell[i]);
@@ -711,6 +713,7 @@ extern "C" int hpb_dev_set_solution(hpb_solver* h, const double* u_host)
   TRY(need_device(h));
   TRY(upload(h, u_host, h->d_u, h->geo.npg, h->geo.nvars));
   h->u_halo_valid = false;
+  h->aux_valid = false;           // GLM-GEE: the auxiliary solution restarts with the new solution (TimeInitialize.c:156-169)
   return sync_check(h, "dev_set_solution");
 }
 
@@ -748,8 +751,28 @@ static double* stage_U(hpb_solver* h, int s)
   return h->d_U;
 }
 
+// TimeGLMGEE.c:45-155 on one rank. Every stage value is a combination of the solution, the auxiliary solution and the
+// earlier stage right-hand sides (stage 0 included: C[0] need not be (1, 0)).
+static int step_single_glm(hpb_solver* h)
+{
+  hpbk::apply_bc(h, h->d_u);                     // TimePreStep.c:50-76
+  if (!h->aux_valid) hpbk::glm_aux_init(h);
+  for (int j = 0; j < h->rk.ns; j++) {
+    hpbk::glm_stage(h, j);                       // TimeGLMGEE.c:66-80
+    hpbk::apply_bc(h, h->d_U);                   // TimeRHSFunctionExplicit.c:46
+    TRY(rhs_part_a(h, h->d_U, h->d_Udot[j]));
+    TRY(rhs_part_b(h, h->d_U, h->d_Udot[j]));
+    stage_boundary_flux(h, h->d_U, j);           // :107-112
+  }
+  hpbk::glm_finish(h);                           // :116-151
+  if (h->cfg.conservation_check) hpbk::step_boundary_integral(h, cons_slot(h, 0), cons_slot(h, CONS_SLOT_STEP));   // :131-140: dt B[0][i]
+  h->t += h->cfg.dt;
+  return check_async(h, "TimeStep (glm-gee)");
+}
+
 static int step_single(hpb_solver* h)
 {
+  if (h->rk.glm) return step_single_glm(h);
   // TimePreStep.c:50-76: boundary conditions on u (the step norm of TimePostStep is formed from the stage
   // right-hand sides afterwards: no copy of u is kept)
   hpbk::apply_bc(h, h->d_u);
@@ -787,6 +810,7 @@ extern "C" int hpb_TimeIntegrate(hpb_solver* h, double* u, int nsteps, double t0
   SINGLE_RANK_ONLY(h, "TimeIntegrate");
   h->t = t0;
   TRY(upload(h, u, h->d_u, h->geo.npg, h->geo.nvars));
+  h->aux_valid = false;
   for (int i = 0; i < nsteps; i++) TRY(step_single(h));
   return download(h, h->d_u, u, h->geo.npg, h->geo.nvars);
 }
@@ -818,6 +842,7 @@ extern "C" int hpb_pipe_upload(hpb_solver* h, const double* u_in, double t0)
   HPB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pipe[EV_IN_READY], 0));
   hpbk::aos_to_soa(h, h->d_pipe_in, h->d_u, h->geo.npg, h->geo.nvars);
   h->u_halo_valid = false;
+  h->aux_valid = false;
   HPB_CUDA(cudaEventRecord(h->ev_pipe[EV_IN_FREE], h->stream));
   h->t = t0;
   return check_async(h, "pipe_upload");
@@ -880,7 +905,8 @@ extern "C" int hpb_dev_ComputeCFL(hpb_solver* h, double* cfl_local_max)
 extern "C" int hpb_dev_StepNormSumSq(hpb_solver* h, double* sumsq_local)
 {
   TRY(need_device(h));
-  hpbk::step_norm_sumsq(h, sumsq_local);
+  if (h->rk.glm) hpbk::sumsq_diff(h, h->d_u, h->d_U, sumsq_local);      // glm_finish left the previous solution in d_U
+  else hpbk::step_norm_sumsq(h, sumsq_local);
   return check_async(h, "dev_StepNormSumSq");
 }
 
@@ -949,6 +975,38 @@ extern "C" int hpb_dev_ErrorSums(hpb_solver* h, const double* uex_host, double* 
   hpbk::diff_norm_sums(h, h->d_tmp[0], nullptr, sums);          // CalculateError.c:68-84 (solution norms)
   hpbk::diff_norm_sums(h, h->d_tmp[0], h->d_u, sums + 3);      // :87-104 (uex - u)
   return check_async(h, "dev_ErrorSums");
+}
+
+// ---- GLM-GEE: the auxiliary solution and the error estimate (TimeGetAuxSolutions.c, TimeError.c:43-127)
+extern "C" double hpb_glmgee_gamma(const hpb_solver* h) { return h->rk.glm ? h->rk.gamma : 0.0; }
+extern "C" int hpb_dev_get_aux_solution(hpb_solver* h, double* uaux_host)
+{
+  TRY(need_device(h));
+  if (!h->rk.glm) return hpb_fail(HPB_ERR_INVALID, "dev_get_aux_solution: the time integrator keeps no auxiliary solution (glm-gee only)");
+  if (!h->aux_valid) hpbk::glm_aux_init(h);
+  return download(h, h->d_aux, uaux_host, h->geo.npg, h->geo.nvars);
+}
+extern "C" int hpb_dev_set_aux_solution(hpb_solver* h, const double* uaux_host)
+{
+  TRY(need_device(h));
+  if (!h->rk.glm) return hpb_fail(HPB_ERR_INVALID, "dev_set_aux_solution: the time integrator keeps no auxiliary solution (glm-gee only)");
+  TRY(upload(h, uaux_host, h->d_aux, h->geo.npg, h->geo.nvars));
+  h->aux_valid = true;
+  return sync_check(h, "dev_set_aux_solution");
+}
+extern "C" int hpb_dev_GLMGEEErrorSums(hpb_solver* h, const double* uex_host, double* sums)
+{
+  TRY(need_device(h));
+  if (!h->rk.glm) return hpb_fail(HPB_ERR_INVALID, "dev_GLMGEEErrorSums: time_scheme is not glm-gee");
+  if (!sums) return hpb_fail(HPB_ERR_INVALID, "dev_GLMGEEErrorSums: null argument");
+  for (int k = 0; k < 3; k++) TRY(tmp(h, k));
+  if (!h->aux_valid) hpbk::glm_aux_init(h);
+  if (uex_host) TRY(upload(h, uex_host, h->d_tmp[0], h->geo.npg, h->geo.nvars));
+  hpbk::glm_error_fields(h, uex_host ? h->d_tmp[0] : nullptr, h->d_tmp[1], h->d_tmp[2]);
+  hpbk::diff_norm_sums(h, h->d_u, nullptr, sums);              // TimeError.c:55-70
+  hpbk::diff_norm_sums(h, h->d_tmp[1], nullptr, sums + 3);    // :73-87
+  hpbk::diff_norm_sums(h, h->d_tmp[2], nullptr, sums + 6);    // :89-106
+  return check_async(h, "dev_GLMGEEErrorSums");
 }
 
 extern "C" int hpb_dev_RHS(hpb_solver* h, double t, double* rhs_host)
@@ -1024,6 +1082,7 @@ static int dist_prestep(Grp& G)
 {
   bool valid = true;
   EACH(h) { TRY(need_device(h)); hpbk::apply_bc(h, h->d_u); valid = valid && h->u_halo_valid; }     // TimePreStep.c:50-56
+  EACH(h) if (h->rk.glm && !h->aux_valid) hpbk::glm_aux_init(h);
   if (!valid) {
     TRY(exchange_u_serial(G, false));                                                                 // TimePreStep.c:57-76
     EACH(h) h->u_halo_valid = true;
@@ -1035,7 +1094,12 @@ static int dist_stage(Grp& G, int s)
 {
   const bool overlap = G.hs[0]->overlap != 0;
   // ---- stage solution with boundary conditions and halo (TimeRK.c:131-141, TimeRHSFunctionExplicit.c:46-60)
-  if (s == 0) {
+  if (G.hs[0]->rk.glm) {
+    // GLM-GEE: every stage value combines the solution and the auxiliary solution (TimeGLMGEE.c:66-80); formed on the
+    // whole block, then boundary conditions and the halo where the reference has them (serial exchange of the stage value)
+    EACH(h) { TRY(need_device(h)); hpbk::glm_stage(h, s); h->U_cur = h->d_U; hpbk::apply_bc(h, h->U_cur); }
+    TRY(exchange_u_serial(G, true));
+  } else if (s == 0) {
     EACH(h) h->U_cur = h->d_u;                 // TimePreStep has just filled its ghosts
   } else if (overlap) {
     TRY(hpbc::fill_begin(G.hs, G.n, hpbc::SLOT_U));
@@ -1116,6 +1180,17 @@ static int dist_stage(Grp& G, int s)
 
 static int dist_finish(Grp& G)
 {
+  if (G.hs[0]->rk.glm) {
+    EACH(h) {
+      TRY(need_device(h));
+      hpbk::glm_finish(h);                                                                // TimeGLMGEE.c:116-151
+      if (h->cfg.conservation_check) hpbk::step_boundary_integral(h, cons_slot(h, 0), cons_slot(h, CONS_SLOT_STEP));
+      h->t += h->cfg.dt;
+      h->u_halo_valid = false;
+    }
+    EACH(h) TRY(check_async(h, "distributed step (glm-gee)"));
+    return HPB_OK;
+  }
   const bool overlap = G.hs[0]->overlap != 0;
   if (overlap) {
     // u^{n+1} on the face layers first (reads the old u), its exchange under the full update

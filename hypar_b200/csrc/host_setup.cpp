@@ -12,6 +12,7 @@
 #include <math.h>
 #include <string.h>
 #include "hpb_internal.h"
+#include "glmgee_tables.h"
 
 extern "C" int hpb_partition1d(int nglobal, int nproc, int rank)
 {
@@ -60,8 +61,12 @@ int hpb_setup_host(hpb_solver* h)
                     model_nv[c.model], nd, c.nvars);
   if (c.nvars < 1 || c.nvars > HPB_MAX_NVARS) return hpb_fail(HPB_ERR_INVALID, "nvars = %d not supported", c.nvars);
   if (c.weno_type < 0 || c.weno_type > 3) return hpb_fail(HPB_ERR_INVALID, "unknown WENO weight type %d", c.weno_type);
-  if (c.rk_type < HPB_RK_44 || c.rk_type > HPB_RK_33)
-    return hpb_fail(HPB_ERR_INVALID, "time_scheme_type %d not supported (rk 1fe, 22, 33, 44, ssprk3)", c.rk_type);
+  const bool glm = (c.rk_type >= HPB_GLMGEE_23 && c.rk_type <= HPB_GLMGEE_RK285EX);
+  if ((c.rk_type < HPB_RK_44 || c.rk_type > HPB_RK_33) && !glm)
+    return hpb_fail(HPB_ERR_INVALID, "time_scheme_type %d not supported (rk 1fe, 22, 33, 44, ssprk3; glm-gee 23, 24, 25i, 35, "
+                                     "exrk2a, rk32g1, rk285ex)", c.rk_type);
+  if (glm && c.glm_ee_mode != HPB_GLM_YEPS && c.glm_ee_mode != HPB_GLM_YYT)
+    return hpb_fail(HPB_ERR_INVALID, "glm-gee: ee_mode %d (yeps, yyt)", c.glm_ee_mode);
   if ((c.model == HPB_MODEL_NS3D || c.model == HPB_MODEL_NS2D || c.model == HPB_MODEL_EULER1D) &&
       (c.upwind < HPB_UPWIND_ROE || c.upwind > HPB_UPWIND_LLF))
     return hpb_fail(HPB_ERR_INVALID, "upwinding %d not implemented (roe, rusanov, rf-char, llf-char)", c.upwind);
@@ -363,7 +368,15 @@ int hpb_setup_host(hpb_solver* h)
   // ---- RK tableau
   RKTableau& T = h->rk;
   memset(&T, 0, sizeof(T));
-  if (c.rk_type == HPB_RK_44) {
+  if (c.rk_type >= HPB_GLMGEE_23) {             // TimeGLMGEEInitialize.c:41-495 (tables: glmgee_tables.h)
+    const glmgee_table& M = GLMGEE_TABLES[c.rk_type - HPB_GLMGEE_23];
+    const int m = c.glm_ee_mode, s = M.s;
+    T.ns = s; T.glm = 1; T.mode = m; T.gamma = M.gamma;
+    for (int k = 0; k < s * s; k++) T.A[k] = M.A[m][k];
+    for (int k = 0; k < s; k++) { T.b[k] = M.B[m][k]; T.b1[k] = M.B[m][s + k]; T.c[k] = M.c[m][k]; }
+    for (int k = 0; k < 2 * s; k++) T.C[k] = M.C[m][k];
+    for (int k = 0; k < 4; k++) T.D[k] = M.D[m][k];
+  } else if (c.rk_type == HPB_RK_44) {
     T.ns = 4;
     T.A[4] = 0.5; T.A[9] = 0.5; T.A[14] = 1.0;
     T.c[0] = 0.0; T.c[1] = T.c[2] = 0.5; T.c[3] = 1.0;

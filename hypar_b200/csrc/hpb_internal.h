@@ -51,7 +51,13 @@ struct ZoneDev {
   double xs, xe;                  // sponge: start and end coordinate along dim
 };
 
-struct RKTableau { int ns; double A[16], b[4], c[4]; };
+// explicit RK (TimeExplicitRKInitialize.c) or GLM-GEE (glm = 1; TimeGLMGEEInitialize.c: A = stage coefficients, b = the
+// first row of B, b1 = its second row, C (s x 2) and D (2 x 2) weight the solution and the auxiliary solution)
+#define HPB_MAX_STAGES 9
+struct RKTableau {
+  int ns; double A[HPB_MAX_STAGES * HPB_MAX_STAGES], b[HPB_MAX_STAGES], c[HPB_MAX_STAGES];
+  int glm, mode; double b1[HPB_MAX_STAGES], C[HPB_MAX_STAGES * 2], D[4], gamma;
+};
 
 // ---------------------------------------------------------------------------------------------
 struct hpb_solver {
@@ -78,7 +84,9 @@ struct hpb_solver {
   double *d_u = nullptr;           // solution (SoA, ghosts)
   double *d_U = nullptr;           // stage solution
   double *U_cur = nullptr;         // distributed step: the array holding the current stage solution (d_u for stage 0)
-  double *d_Udot[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *d_Udot[HPB_MAX_STAGES] = {};
+  double *d_aux = nullptr, *d_aux2 = nullptr;   // GLM-GEE: the auxiliary solution (TS->U[r]) and its next value
+  bool aux_valid = false;          // d_aux holds the auxiliary solution of the current d_u (else: TimeInitialize.c:156-169 at the next step)
   double *d_fI = nullptr;          // interface flux (generic path), max over dirs
   double *d_sI = nullptr;          // interface gravity-source function (generic path)
   double *d_QD[3] = {nullptr, nullptr, nullptr};   // scaled primitive derivatives (viscous)
@@ -190,6 +198,12 @@ void step_norm_sumsq(hpb_solver* h, double* out_host);   // from the stage right
 // conservation / error diagnostics (deterministic reductions)
 void boundary_flux(hpb_solver* h, const double* u, int d, double* sbi);
 void step_boundary_integral(hpb_solver* h, const double* bf, double* step_bi);
+// GLM-GEE (TimeGLMGEE.c): stage value j into d_U, step completion (d_u and d_aux advance; d_U keeps the previous u
+// for the step norm), the auxiliary solution's initial value, the estimated error / error of the estimate
+void glm_aux_init(hpb_solver* h);
+void glm_stage(hpb_solver* h, int j);
+void glm_finish(hpb_solver* h);
+void glm_error_fields(hpb_solver* h, const double* uex, double* est, double* dif);
 void volume_integral(hpb_solver* h, const double* u, double* out_host);
 void diff_norm_sums(hpb_solver* h, const double* a, const double* b, double* out_host);
 int diag_partial_size();

@@ -571,6 +571,41 @@ __global__ void k_rk_combine(const double* __restrict__ u, RKArgs args, double* 
   }
 }
 
+// GLM-GEE (TimeGLMGEE.c:66-80, 116-129): out = c0 u ; out += c1 aux ; out += a_i k_i in order -- _ArrayScaleCopy1D_
+// followed by _ArrayAXPY_s, every product and sum rounded on its own like the reference's loops
+struct GLMArgs { const double* k[HPB_MAX_STAGES]; double a[HPB_MAX_STAGES]; int n; double c0, c1; };
+__global__ void k_glm_combine(const double* __restrict__ u, const double* __restrict__ aux, GLMArgs args,
+                              double* __restrict__ out, long long n)
+{
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    double t = __dmul_rn(args.c0, u[i]);
+    t = __dadd_rn(t, __dmul_rn(args.c1, aux[i]));
+    for (int s = 0; s < args.n; s++) t = __dadd_rn(t, __dmul_rn(args.a[s], args.k[s][i]));
+    out[i] = t;
+  }
+}
+__global__ void k_swap(double* __restrict__ a, double* __restrict__ b, long long n)
+{
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) { const double t = a[i]; a[i] = b[i]; b[i] = t; }
+}
+// TimeError.c:47-52, 87-89: est = aux (yeps) or (u - aux) * (1/(1-gamma)) (yyt); dif = (1.0 u + (-1.0) uex) + (-1.0) est
+__global__ void k_glm_error_fields(const double* __restrict__ u, const double* __restrict__ aux, const double* __restrict__ uex,
+                                   int mode, double f, double* __restrict__ est, double* __restrict__ dif, long long n)
+{
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const double e = (mode == HPB_GLM_YEPS) ? aux[i] : __dmul_rn(__dadd_rn(u[i], -aux[i]), f);
+    est[i] = e;
+    if (uex) dif[i] = __dadd_rn(__dadd_rn(__dmul_rn(1.0, u[i]), __dmul_rn(-1.0, uex[i])), __dmul_rn(-1.0, e));
+    else dif[i] = 0.0;
+  }
+}
+
 // exact path: rhs = (rhs + par) + src, the summation order of TimeRHSFunctionExplicit.c:89-92 (rhs holds -hyp)
 __global__ void k_combine_rhs(double* __restrict__ rhs, const double* __restrict__ par, const double* __restrict__ src, long long n)
 {
@@ -2041,6 +2076,57 @@ void rk_finish(hpb_solver* h)
   RKArgs a; a.n = h->rk.ns;
   for (int s = 0; s < h->rk.ns; s++) { a.k[s] = h->d_Udot[s]; a.a[s] = h->cfg.dt * h->rk.b[s]; }
   k_rk_combine<<<grid1(n), 256, 0, h->stream>>>(h->d_u, a, h->d_u, n); LAUNCHED(h);
+}
+
+// ---- GLM-GEE (TimeGLMGEE.c:45-155; r = 2: the solution and one auxiliary solution)
+void glm_aux_init(hpb_solver* h)
+{
+  // TimeInitialize.c:156-169: the auxiliary solution starts as a copy of u (yyt) or as zero (yeps)
+  const long long n = h->geo.npg * h->geo.nvars;
+  if (h->rk.mode == HPB_GLM_YYT) { k_copy<<<grid1(n), 256, 0, h->stream>>>(h->d_aux, h->d_u, n); LAUNCHED(h); }
+  else set_zero(h, h->d_aux, n);
+  h->aux_valid = true;
+}
+
+static GLMArgs glm_args(const hpb_solver* h, const double* row, int count, double c0, double c1)
+{
+  GLMArgs a; a.n = 0; a.c0 = c0; a.c1 = c1;
+  for (int i = 0; i < count; i++) {
+    const double c = h->cfg.dt * row[i];
+    if (c == 0.0) continue;              // the reference adds 0 * k as well: a no-op on finite data
+    a.k[a.n] = h->d_Udot[i]; a.a[a.n] = c; a.n++;
+  }
+  return a;
+}
+
+void glm_stage(hpb_solver* h, int j)
+{
+  ProfScope ps(h, HPB_PROF_RK);
+  const long long n = h->geo.npg * h->geo.nvars;
+  const int s = h->rk.ns;
+  const GLMArgs a = glm_args(h, h->rk.A + j * s, j, h->rk.C[2 * j], h->rk.C[2 * j + 1]);     // TimeGLMGEE.c:70-79
+  k_glm_combine<<<grid1(n), 256, 0, h->stream>>>(h->d_u, h->d_aux, a, h->d_U, n); LAUNCHED(h);
+}
+
+void glm_finish(hpb_solver* h)
+{
+  ProfScope ps(h, HPB_PROF_RK);
+  const long long n = h->geo.npg * h->geo.nvars;
+  const int s = h->rk.ns;
+  // TimeGLMGEE.c:116-129: both new quantities from the OLD solution and auxiliary solution, then :143-151
+  const GLMArgs a0 = glm_args(h, h->rk.b, s, h->rk.D[0], h->rk.D[1]);
+  const GLMArgs a1 = glm_args(h, h->rk.b1, s, h->rk.D[2], h->rk.D[3]);
+  k_glm_combine<<<grid1(n), 256, 0, h->stream>>>(h->d_u, h->d_aux, a0, h->d_U, n); LAUNCHED(h);
+  k_glm_combine<<<grid1(n), 256, 0, h->stream>>>(h->d_u, h->d_aux, a1, h->d_aux2, n); LAUNCHED(h);
+  k_swap<<<grid1(n), 256, 0, h->stream>>>(h->d_u, h->d_U, n); LAUNCHED(h);       // d_U keeps the previous solution (step norm)
+  double* t = h->d_aux; h->d_aux = h->d_aux2; h->d_aux2 = t;
+}
+
+void glm_error_fields(hpb_solver* h, const double* uex, double* est, double* dif)
+{
+  const long long n = h->geo.npg * h->geo.nvars;
+  k_glm_error_fields<<<grid1(n), 256, 0, h->stream>>>(h->d_u, h->d_aux, uex, h->rk.mode, (1.0 / (1.0 - h->rk.gamma)), est, dif, n);
+  LAUNCHED(h);
 }
 
 void cfl(hpb_solver* h, const double* u, double dt, double* out_host)

@@ -25,6 +25,8 @@ BCTYPES = {"periodic": 0, "extrapolate": 1, "slip-wall": 2, "noslip-wall": 3, "d
 PAR_TYPES = {"nonconservative-1stage": 0, "nonconservative-1.5stage": 1, "nonconservative-2stage": 2, "conservative-1stage": 3}
 UPWINDS = {"roe": 1, "rusanov": 2, "rf-char": 3, "llf-char": 4}
 RK_TYPES = {"44": 0, "ssprk3": 1, "tvdrk3": 1, "1fe": 2, "22": 3, "33": 4}
+GLMGEE_TYPES = {"23": 16, "24": 17, "25i": 18, "35": 19, "exrk2a": 20, "rk32g1": 21, "rk285ex": 22}
+GLMGEE_MODES = {"yeps": 0, "yyt": 1}
 SCHEMES = {"weno5": 0, "crweno5": 1, "cupw5": 2, "upw5": 3, "1": 4, "2": 5, "4": 6, "muscl2": 7, "muscl3": 8, "hcweno5": 9}
 LIMITERS = {"gmm": 0, "minmod": 1, "vanleer": 2, "superbee": 3}
 FIELD_U, FIELD_QDERIVX, FIELD_QDERIVY = 0, 1, 2
@@ -43,7 +45,7 @@ def _dp(a: np.ndarray):
 def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], physics: Dict[str, object],
                        weno: Optional[Dict[str, object]], x: Sequence[np.ndarray], rank: int = 0,
                        device: int = -1, use_fused: bool = True, muscl: Optional[Dict[str, object]] = None,
-                       advection_field: Optional[np.ndarray] = None):
+                       advection_field: Optional[np.ndarray] = None, glm_gee: Optional[Dict[str, object]] = None):
     """Translate the contents of solver.inp / boundary.inp / physics.inp / weno.inp / muscl.inp (as parsed
     dictionaries) into an ``hpb_config``. Unsupported choices raise here or in ``hpb_create``."""
     L = _lib.load()
@@ -69,12 +71,22 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
     c.muscl_eps = float(mu.get("epsilon", 1e-3))                         # MUSCLInitialize.c:26-27
     c.muscl_limiter = LIMITERS.get(str(mu.get("limiter", "gmm")), 0)     # :72-75: unknown names fall back to gmm
     ts = str(solver.get("time_scheme", "euler"))
-    if ts not in ("rk", "euler"):
-        raise HyParB200Error(f"time_scheme '{ts}' is not on the B200 path (rk, euler)")
-    tst = str(solver.get("time_scheme_type", " ")) if ts == "rk" else "1fe"     # TimeForwardEuler.c = RK "1fe"
-    if tst not in RK_TYPES:
-        raise HyParB200Error(f"time_scheme_type '{tst}' is not on the B200 path (1fe, 22, 33, 44, ssprk3, tvdrk3)")
-    c.rk_type = RK_TYPES[tst]
+    if ts not in ("rk", "euler", "glm-gee"):
+        raise HyParB200Error(f"time_scheme '{ts}' is not on the B200 path (rk, euler, glm-gee)")
+    if ts == "glm-gee":                                   # TimeGLMGEEInitialize.c:41-70, glm_gee.inp :431-470
+        tst = str(solver.get("time_scheme_type", " "))
+        if tst not in GLMGEE_TYPES:
+            raise HyParB200Error(f"time_scheme_type '{tst}' is not a glm-gee method (23, 24, 25i, 35, exrk2a, rk32g1, rk285ex)")
+        c.rk_type = GLMGEE_TYPES[tst]
+        mode = str((glm_gee or {}).get("ee_mode", "yeps"))
+        if mode not in GLMGEE_MODES:
+            raise HyParB200Error(f"glm_gee.inp: ee_mode '{mode}' (yeps, yyt)")
+        c.glm_ee_mode = GLMGEE_MODES[mode]
+    else:
+        tst = str(solver.get("time_scheme_type", " ")) if ts == "rk" else "1fe"     # TimeForwardEuler.c = RK "1fe"
+        if tst not in RK_TYPES:
+            raise HyParB200Error(f"time_scheme_type '{tst}' is not on the B200 path (1fe, 22, 33, 44, ssprk3, tvdrk3)")
+        c.rk_type = RK_TYPES[tst]
     if str(solver.get("immersed_body", "none")) != "none":
         raise HyParB200Error("immersed bodies are not on the B200 path")
     if str(solver.get("hyp_flux_split", "no")) != "no":
@@ -173,12 +185,12 @@ class Solver:
     """One rank of the B200 explicit-RHS path."""
 
     def __init__(self, solver: Dict[str, object], boundary, physics, weno, x, rank: int = 0,
-                 device: int = -1, use_fused: bool = True, muscl=None, advection_field=None):
+                 device: int = -1, use_fused: bool = True, muscl=None, advection_field=None, glm_gee=None):
         self.L = _lib.load()
         self.inputs = {"solver": solver, "boundary": boundary, "physics": physics, "weno": weno, "muscl": muscl,
-                       "advection_field": advection_field}
+                       "advection_field": advection_field, "glm_gee": glm_gee}
         cfg, self._xg = config_from_inputs(solver, boundary, physics, weno, x, rank, device, use_fused, muscl,
-                                           advection_field)
+                                           advection_field, glm_gee)
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.hpb_create(C.byref(cfg), C.byref(self.h))
@@ -202,7 +214,8 @@ class Solver:
     @classmethod
     def from_case(cls, case, rank: int = 0, device: int = -1, use_fused: bool = True) -> "Solver":
         return cls(case.solver, case.boundary, case.physics, case.weno, case.x, rank, device, use_fused,
-                   muscl=getattr(case, "muscl", None), advection_field=getattr(case, "advection_field", None))
+                   muscl=getattr(case, "muscl", None), advection_field=getattr(case, "advection_field", None),
+                   glm_gee=getattr(case, "glm_gee", None))
 
     @classmethod
     def from_directory(cls, path: str, rank: int = 0, device: int = -1, use_fused: bool = True) -> "Solver":
@@ -231,7 +244,9 @@ class Solver:
             fn = os.path.join(path, str(ph["advection_filename"]) + ".inp")
             if os.path.exists(fn):
                 af = hypario.read_initial(fn, s["size"], nd * nv, ipt)[1]
-        obj = cls(s, b, ph, w, x, rank, device, use_fused, muscl=mu, advection_field=af)
+        gf = os.path.join(path, "glm_gee.inp")
+        gg = hypario.read_keyword_file(gf) if os.path.exists(gf) else None
+        obj = cls(s, b, ph, w, x, rank, device, use_fused, muscl=mu, advection_field=af, glm_gee=gg)
         obj.u0_global = u0
         return obj
 
@@ -506,6 +521,36 @@ class Solver:
         out = np.zeros(6)
         self._ck(self.L.hpb_dev_ErrorSums(self.h, _dp(uex), _dp(out)))
         return out
+
+    # -- GLM-GEE (time_scheme glm-gee): the auxiliary solution and the estimated global error
+    def get_aux_solution(self) -> np.ndarray:
+        """TimeGetAuxSolutions.c: the auxiliary solution the GLM-GEE method propagates (HyPar layout, with ghosts)"""
+        out = np.zeros(self.npoints_local_wghosts * self.nvars)
+        self._ck(self.L.hpb_dev_get_aux_solution(self.h, _dp(out)))
+        return out
+
+    def set_aux_solution(self, uaux: np.ndarray) -> None:
+        self._ck(self.L.hpb_dev_set_aux_solution(self.h, _dp(np.ascontiguousarray(uaux, dtype=np.float64).ravel())))
+
+    def dev_GLMGEEErrorSums(self, uex: Optional[np.ndarray] = None) -> np.ndarray:
+        out = np.zeros(9)
+        self._ck(self.L.hpb_dev_GLMGEEErrorSums(self.h, _dp(uex) if uex is not None else None, _dp(out)))
+        return out
+
+    def glmgee_error(self, uex: Optional[np.ndarray] = None, sums: Optional[np.ndarray] = None) -> np.ndarray:
+        """the six numbers TimeError.c:43-127 writes to glm_err.dat after dt (L1, L2, Linf of the estimated error, then of
+        (u - uex) - estimate, or -1 without uex). `sums`: the nine sums already reduced over the ranks (sum, sum, max)."""
+        s = self.dev_GLMGEEErrorSums(uex) if sums is None else np.asarray(sums, dtype=np.float64)
+        npg = float(np.prod(self.dim_global))
+        norm = lambda t: np.array([t[0] / npg, np.sqrt(t[1] / npg), t[2]])
+        sol, err = norm(s[0:3]), np.empty(6)
+        err[0:3] = norm(s[3:6])
+        err[3:6] = norm(s[6:9]) if uex is not None else -1.0
+        if (sol > 1e-15).all():
+            err[0:3] /= sol
+            if uex is not None:
+                err[3:6] /= sol
+        return err
 
     def synchronize(self) -> None:
         self._ck(self.L.hpb_synchronize(self.h))

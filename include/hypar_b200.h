@@ -105,6 +105,18 @@ extern "C" {
 #define HPB_RK_1FE    2   /* "1fe"; also time_scheme "euler" (TimeForwardEuler.c: the same update) */
 #define HPB_RK_22     3
 #define HPB_RK_33     4
+/* time_scheme "glm-gee" (general linear methods with global error estimation, TimeGLMGEE.c:45-155): rk_type holds the
+   method -- reference TimeGLMGEEInitialize.c:41-70, include/timeintegration_struct.h:209-257 */
+#define HPB_GLMGEE_23      16
+#define HPB_GLMGEE_24      17
+#define HPB_GLMGEE_25I     18
+#define HPB_GLMGEE_35      19
+#define HPB_GLMGEE_EXRK2A  20
+#define HPB_GLMGEE_RK32G1  21
+#define HPB_GLMGEE_RK285EX 22
+/* glm_gee.inp `ee_mode` (TimeGLMGEEInitialize.c:431-470; default yeps) */
+#define HPB_GLM_YEPS 0
+#define HPB_GLM_YYT  1
 
 /* par_space_type -- reference InitializeSolvers.c:107-176 (the form of the parabolic term) */
 #define HPB_PAR_NC_1STAGE   0   /* "nonconservative-1stage" (default, ReadInputs.c:134): ParabolicFunctionNC1Stage  */
@@ -136,7 +148,7 @@ typedef struct hpb_config {
   int    model;                        /* HPB_MODEL_*                                    */
   int    interp_char;                  /* hyp_interp_type: 1 characteristic, 0 components*/
   int    par_scheme;                   /* par_space_scheme: 2 or 4                       */
-  int    rk_type;                      /* HPB_RK_*                                       */
+  int    rk_type;                      /* HPB_RK_* (time_scheme rk / euler) or HPB_GLMGEE_* (time_scheme glm-gee) */
   double dt;
   /* --- weno.inp --- */
   int    weno_type;                    /* HPB_WENO_*                                     */
@@ -177,6 +189,7 @@ typedef struct hpb_config {
   int    par_space_type;               /* HPB_PAR_*: LinearADR with a non-zero diffusion coefficient is on the device only
                                           as nonconservative-1stage -- the other forms are different arithmetic
                                           (ParabolicFunctionNC2Stage.c / NC1_5Stage / Cons1Stage) and fail in hpb_create */
+  int    glm_ee_mode;                  /* HPB_GLM_*: glm_gee.inp `ee_mode` of the GLM-GEE methods                */
 } hpb_config;
 
 typedef struct hpb_solver hpb_solver;
@@ -296,6 +309,20 @@ int hpb_CalculateConservationError(int nvars, const double* vol, const double* v
 /* sums[0..2] = (sum |uex|, sum uex^2, max |uex|), sums[3..5] = the same of (u_dev - uex), over this rank's
    interior points and all components; uex_host: exact solution, HyPar layout (local + ghosts) */
 int hpb_dev_ErrorSums(hpb_solver* h, const double* uex_host, double* sums /* [6] */);
+/* ---- GLM-GEE: time_scheme glm-gee advances the solution and ONE auxiliary solution (r = 2) that
+ * carries the global-error estimate. hpb_TimeStep(s) / hpb_TimeStepsDistributed / hpb_TimeStepsLocal run
+ *   TimeGLMGEE           src/TimeIntegration/TimeGLMGEE.c:45-155 (stage values :66-113, step completion :116-151)
+ * when cfg.rk_type is one of HPB_GLMGEE_*. The auxiliary solution starts as TimeInitialize.c:156-169 sets it (a copy of
+ * the solution for ee_mode yyt, zero for yeps) at the first step after hpb_dev_set_solution.
+ *   TimeGetAuxSolutions  src/TimeIntegration/TimeGetAuxSolutions.c:30-63 (op_aux files)    hpb_dev_get_aux_solution
+ *   TimeError            src/TimeIntegration/TimeError.c:43-127 (glm_err.dat)              hpb_dev_GLMGEEErrorSums
+ * sums[0..2] = (sum |u|, sum u^2, max |u|), sums[3..5] = the same of the estimated error (the auxiliary solution, or
+ * (u - aux)/(1 - gamma) for yyt), sums[6..8] = the same of (u - uex) - estimate (uex_host may be NULL: zeros), over this
+ * rank's interior points; the caller reduces over ranks and normalises as TimeError.c:53-118 does. */
+int hpb_dev_get_aux_solution(hpb_solver* h, double* uaux_host);
+int hpb_dev_set_aux_solution(hpb_solver* h, const double* uaux_host);
+int hpb_dev_GLMGEEErrorSums(hpb_solver* h, const double* uex_host, double* sums /* [9] */);
+double hpb_glmgee_gamma(const hpb_solver* h);       /* GLMGEEParameters::gamma of the method (0 for explicit RK) */
 /* evaluate rhs(u_dev) once into an internal buffer and copy it to the host (HyPar layout) */
 int hpb_dev_RHS(hpb_solver* h, double t, double* rhs_host /* may be NULL */);
 

@@ -185,6 +185,37 @@ static int B200_TimeRK(void *ts)
   return 0;
 }
 
+/* ---- HyPar::TimeIntegrate = TimeGLMGEE (TimeGLMGEE.c:45): the solution and the auxiliary solution TS->U[r] advance
+   together. TimeGetAuxSolutions (the op_aux files of OutputSolution.cpp:42-79) and TimeError (glm_err.dat) read TS->U[r],
+   so it is refreshed from the device whenever the solution's host mirror is. */
+static int B200_TimeGLMGEE(void *ts)
+{
+  TimeIntegration  *TS  = (TimeIntegration*) ts;
+  SimulationObject *sim = (SimulationObject*) TS->simulation;
+  for (int ns = 0; ns < g.nsims; ns++) {
+    HyPar *solver = &sim[ns].solver;
+    hpb_solver *h = H(solver);
+    GLMGEEParameters *p = (GLMGEEParameters*) solver->msti;
+    double *aux = TS->U[p->r] + TS->u_offsets[ns];
+    const int cons = !strcmp(solver->ConservationCheck, "yes");
+    if (!g.resident) {         /* the host arrays are the state: both go up, one step, both come back */
+      hpb_dev_set_solution(h, solver->u);  hpb_dev_set_aux_solution(h, aux);  die_on_error("set_solution");
+      hpb_TimeStep(h);                                                         die_on_error("TimeStep");
+      hpb_dev_get_solution(h, solver->u);  hpb_dev_get_aux_solution(h, aux);  die_on_error("get_solution");
+    } else {
+      if (sim[ns].mpi.nproc > 1) { hpb_TimeStepsDistributed(h, 1); die_on_error("TimeStepsDistributed"); }
+      else                       { hpb_TimeStep(h); die_on_error("TimeStep"); }
+      const int it = TS->iter + 1;
+      const int refresh = (it % solver->screen_op_iter == 0) || ((it + 1) % solver->screen_op_iter == 0)
+                       || (it % solver->file_op_iter == 0) || (it == TS->n_iter);
+      if (refresh) { hpb_dev_get_solution(h, solver->u); hpb_dev_get_aux_solution(h, aux); die_on_error("get_solution"); }
+    }
+    if (cons) { hpb_dev_StepBoundaryIntegral(h, solver->StepBoundaryIntegral); die_on_error("StepBoundaryIntegral"); }
+  }
+  g.steps++;
+  return 0;
+}
+
 static int upwind_choice(const char *name)
 {
   if (!strcmp(name, _RUSANOV_)) return HPB_UPWIND_RUSANOV;
@@ -230,8 +261,9 @@ static int attach_one(SimulationObject *sim, int n, int nsims)
   else if (!strcmp(s->spatial_scheme_hyp, _FOURTH_ORDER_CENTRAL_))       scheme = HPB_SCHEME_FOURTH;
   else if (!strcmp(s->spatial_scheme_hyp, _SECOND_ORDER_MUSCL_))         scheme = HPB_SCHEME_MUSCL2;
   else if (!strcmp(s->spatial_scheme_hyp, _THIRD_ORDER_MUSCL_))          scheme = HPB_SCHEME_MUSCL3;
-  if (scheme < 0 || strcmp(s->time_scheme, _RK_) || strcmp(s->SplitHyperbolicFlux, "no") || s->flag_ib) {
-    fprintf(stderr, "hyparb200_attach: only weno5 / crweno5 / hcweno5 / cupw5 / upw5 / 1 / 2 / 4 / muscl2 / muscl3 + explicit RK without flux splitting / "
+  const int glm = !strcmp(s->time_scheme, _GLM_GEE_);
+  if (scheme < 0 || (strcmp(s->time_scheme, _RK_) && !glm) || strcmp(s->SplitHyperbolicFlux, "no") || s->flag_ib) {
+    fprintf(stderr, "hyparb200_attach: only weno5 / crweno5 / hcweno5 / cupw5 / upw5 / 1 / 2 / 4 / muscl2 / muscl3 + explicit RK / GLM-GEE without flux splitting / "
                     "immersed boundaries is on the B200 path\n");
     return 1;
   }
@@ -246,7 +278,13 @@ static int attach_one(SimulationObject *sim, int n, int nsims)
   c.ndims = s->ndims;  c.nvars = s->nvars;  c.ghosts = s->ghosts;  c.rank = mpi->rank;  c.dt = s->dt;
   for (int d = 0; d < s->ndims; d++) { c.dim_global[d] = s->dim_global[d]; c.iproc[d] = mpi->iproc[d]; }
   c.interp_char = !strcmp(s->interp_type, _CHARACTERISTIC_);
-  if      (!strcmp(s->time_scheme_type, _RK_44_))     c.rk_type = HPB_RK_44;
+  if (glm) {
+    const char *names[] = { _GLM_GEE_23_, _GLM_GEE_24_, _GLM_GEE_25I_, _GLM_GEE_35_, _GLM_GEE_EXRK2A_, _GLM_GEE_RK32G1_, _GLM_GEE_RK285EX_ };
+    c.rk_type = -1;
+    for (int k = 0; k < 7; k++) if (!strcmp(s->time_scheme_type, names[k])) c.rk_type = HPB_GLMGEE_23 + k;
+    c.glm_ee_mode = !strcmp(((GLMGEEParameters*) s->msti)->ee_mode, _GLM_GEE_YYT_) ? HPB_GLM_YYT : HPB_GLM_YEPS;
+  }
+  else if (!strcmp(s->time_scheme_type, _RK_44_))     c.rk_type = HPB_RK_44;
   else if (!strcmp(s->time_scheme_type, _RK_SSP3_) || !strcmp(s->time_scheme_type, _RK_TVD3_)) c.rk_type = HPB_RK_SSPRK3;
   else if (!strcmp(s->time_scheme_type, _RK_1FE_))    c.rk_type = HPB_RK_1FE;
   else if (!strcmp(s->time_scheme_type, _RK_22_))     c.rk_type = HPB_RK_22;
@@ -397,7 +435,7 @@ static int attach_one(SimulationObject *sim, int n, int nsims)
   s->ComputeCFL               = B200_ComputeCFL;
   ref_VolumeIntegral          = s->VolumeIntegralFunction;
   s->VolumeIntegralFunction   = B200_VolumeIntegral;
-  s->TimeIntegrate            = B200_TimeRK;        /* picked up by TimeInitialize.c:55 */
+  s->TimeIntegrate            = glm ? B200_TimeGLMGEE : B200_TimeRK;        /* picked up by TimeInitialize.c:55 */
   if (!mpi->rank) printf("hypar_b200 attached%s: %s, %s mode, device %d%s\n", (nsims > 1 ? " (one solver per simulation)" : ""),
                          hpb_version(), g.resident ? "resident" : "host", c.device,
                          mpi->nproc > 1 ? ", in-library NCCL halo exchange" : "");

@@ -84,6 +84,9 @@ def lib():
         _lib.hpo_conservation_error.argtypes = [C.c_int, dp, dp, dp, dp]
         _lib.hpo_set_boundary_flux_sink.argtypes = [dp]
         _lib.hpo_norm_sums.argtypes = [cp, dp, dp, dp]
+        _lib.hpo_time_step_glmgee.argtypes = [cp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_int]
+        _lib.hpo_glmgee_error.argtypes = [cp, dp, dp, C.c_int, C.c_int, dp, dp]
+        _lib.hpo_glmgee_gamma.restype = C.c_double
     return _lib
 
 
@@ -485,6 +488,22 @@ class Oracle:
     def cfl(self, u, dt):
         return float(self.L.hpo_cfl(self.c, _p(u), C.c_double(dt)))
 
+    # ---- GLM-GEE (TimeGLMGEE.c): the solution and one auxiliary solution
+    def glmgee_aux0(self, u, mode):
+        """TimeInitialize.c:156-169: the auxiliary solution before the first step"""
+        return u.copy() if mode == 1 else np.zeros_like(u)
+
+    def time_step_glmgee(self, u, uaux, dt, method, mode, mpi_semantics=None):
+        ms = self.s.mpi_semantics if mpi_semantics is None else mpi_semantics
+        self.L.hpo_time_step_glmgee(self.c, _p(u), _p(uaux), C.c_double(dt), C.c_int(method), C.c_int(mode), C.c_int(int(ms)))
+        return u, uaux
+
+    def glmgee_error(self, u, uaux, method, mode, uex=None):
+        """the six numbers TimeError.c writes to glm_err.dat (after dt)"""
+        out = np.zeros(6)
+        self.L.hpo_glmgee_error(self.c, _p(u), _p(uaux), C.c_int(method), C.c_int(mode), _p(uex) if uex is not None else None, _p(out))
+        return out
+
     # ---- conservation diagnostics (VolumeIntegral.c, BoundaryIntegral.c, CalculateConservationError.c, the
     #      StageBoundaryIntegral bookkeeping of HyperbolicFunction.c:103-106 / TimeRK.c:172-193); local (this rank's) parts
     def stage_boundary_integral(self, u, mpi_semantics=None):
@@ -534,6 +553,27 @@ class Oracle:
 
 
 RK_TYPES = {"44": 0, "ssprk3": 1, "tvdrk3": 1, "1fe": 2, "22": 3, "33": 4}
+
+
+GLMGEE_METHODS = {"23": 0, "24": 1, "25i": 2, "35": 3, "exrk2a": 4, "rk32g1": 5, "rk285ex": 6}
+GLMGEE_MODES = {"yeps": 0, "yyt": 1}
+
+
+def glmgee_of(case):
+    """(method, mode) of a case advanced by time_scheme glm-gee, else None"""
+    if str(case.solver.get("time_scheme", "rk")) != "glm-gee":
+        return None
+    gg = getattr(case, "glm_gee", None) or {}
+    return GLMGEE_METHODS[str(case.solver["time_scheme_type"])], GLMGEE_MODES[str(gg.get("ee_mode", "yeps"))]
+
+
+def glmgee_table(method: int, mode: int):
+    """the coefficient table the oracle uses (oracle/glmgee_tables.h) as numpy arrays"""
+    L = lib()
+    s = L.hpo_glmgee_nstages(C.c_int(method))
+    t = {"s": s, "A": np.zeros(s * s), "B": np.zeros(2 * s), "C": np.zeros(2 * s), "D": np.zeros(4)}
+    L.hpo_glmgee_coefficients(C.c_int(method), C.c_int(mode), _p(t["A"]), _p(t["B"]), _p(t["C"]), _p(t["D"]))
+    return t
 
 
 def rk_type_of(case) -> int:

@@ -18,7 +18,11 @@
  *                               dumps ref_ufinal.bin (with ghosts) and prints per-step wctime; with
  *                               `conservation_check yes` also the volume / boundary-flux integrals and the
  *                               conservation error of every step; with an `exact.inp` in the directory also
- *                               CalculateError's three norms (errors.dat)
+ *                               CalculateError's three norms (errors.dat); with `time_scheme glm-gee` also
+ *                               ref_uaux.bin (the auxiliary solution TS->U[r]) and TimeError's six norms (glm_err.dat)
+ *   hypar_ref glmgee         -> the coefficient tables TimeGLMGEEInitialize.c builds for the method and ee_mode of the
+ *                               run directory (solver.inp time_scheme_type, glm_gee.inp), as hexadecimal floats:
+ *                               tools/make_glmgee_tables.py turns them into the tables of the oracle and of the library
  *
  * All dumps: header {int ndims, nvars, ghosts, dim[ndims]} then raw doubles in the
  * reference's own layout (ghost-padded AoS for cell arrays).
@@ -44,6 +48,7 @@
 
 extern "C" int TimeRHSFunctionExplicit(double*, double*, void*, void*, double);
 extern "C" int CalculateError(void*, void*);
+extern "C" int TimeError(void*, void*, double*);
 
 static int g_rank = 0, g_nproc = 1;
 static void dump(const char* name_in, const HyPar* s, const double* a, long n)
@@ -230,15 +235,35 @@ int main(int argc, char** argv)
     }
     printf("TOTAL_WCTIME %.6e NSTEPS %d\n", total, nsteps);
     dump("ref_ufinal.bin", solver, solver->u, nc);
+    const bool glmgee = !strcmp(solver->time_scheme, _GLM_GEE_);
+    if (glmgee) dump("ref_uaux.bin", solver, TS.U[((GLMGEEParameters*) solver->msti)->r], nc);
     { /* CalculateError.c (errors.dat): only when the run directory holds exact.inp */
       FILE* fe = fopen("exact.inp", "rb");
       if (fe) {
         fclose(fe);
         CalculateError(solver, mpi);
         printf("ERRORS %.17e %.17e %.17e\n", solver->error[0], solver->error[1], solver->error[2]);
+      } else if (glmgee) TimeError(solver, mpi, NULL);      /* what CalculateError.c:60 does without an exact solution */
+      if (glmgee && !rank) {                                /* TimeError.c:121-127 wrote glm_err.dat */
+        FILE* fg = fopen("glm_err.dat", "r");
+        double v[7] = {0,0,0,0,0,0,0};
+        if (fg) { for (int k = 0; k < 7; k++) if (fscanf(fg, "%lf", &v[k]) != 1) break; fclose(fg); }
+        printf("GLMERR %.17e %.17e %.17e %.17e %.17e %.17e\n", v[1], v[2], v[3], v[4], v[5], v[6]);
       }
     }
     TimeCleanup(&TS);
+
+  } else if (!strcmp(mode, "glmgee")) {
+
+    if (strcmp(solver->time_scheme, _GLM_GEE_)) { fprintf(stderr, "time_scheme is not glm-gee\n"); return 4; }
+    GLMGEEParameters* p = (GLMGEEParameters*) solver->msti;
+    const int s = p->nstages, r = p->r;
+    printf("GLMGEE %s %s %d %d %a\n", solver->time_scheme_type, p->ee_mode, s, r, p->gamma);
+    printf("A");  for (int k = 0; k < s*s; k++) printf(" %a", p->A[k]);  printf("\n");
+    printf("B");  for (int k = 0; k < r*s; k++) printf(" %a", p->B[k]);  printf("\n");
+    printf("C");  for (int k = 0; k < s*r; k++) printf(" %a", p->C[k]);  printf("\n");
+    printf("D");  for (int k = 0; k < r*r; k++) printf(" %a", p->D[k]);  printf("\n");
+    printf("c");  for (int k = 0; k < s;   k++) printf(" %a", p->c[k]);  printf("\n");
 
   } else {
     fprintf(stderr, "unknown mode %s\n", mode);

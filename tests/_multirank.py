@@ -114,6 +114,34 @@ class MultiRankOracle:
         return u
 
 
+    def time_step_glmgee(self, u, uaux, dt, method, mode):
+        """TimePreStep BC/halo + TimeGLMGEE (TimeGLMGEE.c:66-151) on every rank, in place (u and uaux)."""
+        T = hpo.glmgee_table(method, mode)
+        s, A, B, Cm, D = T["s"], T["A"], T["B"], T["C"], T["D"]
+        for r in range(self.nranks):
+            self.O[r].apply_bc(u[r])
+        self.exchange(u)
+        k = []
+        for j in range(s):
+            U = [Cm[2 * j] * x for x in u]
+            for r in range(self.nranks):
+                U[r] += Cm[2 * j + 1] * uaux[r]
+                for i in range(j):
+                    U[r] += (dt * A[j * s + i]) * k[i][r]
+            k.append(self.rhs(U))
+        new = []
+        for j in range(2):
+            V = [D[2 * j] * x for x in u]
+            for r in range(self.nranks):
+                V[r] += D[2 * j + 1] * uaux[r]
+                for i in range(s):
+                    V[r] += (dt * B[j * s + i]) * k[i][r]
+            new.append(V)
+        for r in range(self.nranks):
+            u[r][...] = new[0][r]
+            uaux[r][...] = new[1][r]
+        return u, uaux
+
     def time_step_cons(self, u, dt, rk_type):
         """time_step with the boundary-flux bookkeeping of TimeRK.c:172-193; returns [StepBoundaryIntegral_r]"""
         A, b, c = np.zeros(16), np.zeros(4), np.zeros(4)

@@ -155,6 +155,42 @@ def test_hypar_executable_with_library_attached(need_exes, case, variant, tmp_pa
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# GLM-GEE through the glue (HyPar::TimeIntegrate = TimeGLMGEE): the solution files, the auxiliary-solution files
+# OutputSolution.cpp:42-79 writes through TimeGetAuxSolutions (ts0_*.bin)
+GLM = [_prep(cases.with_glmgee(cases.ns2d_vortex((32, 24), "yc"), "exrk2a", "yyt"), cons=False),
+       _prep(cases.with_glmgee(cases.ns3d_turbulence((14, 12, 10), "mapped"), "rk32g1"), n_iter=4, cons=False),
+       _prep(cases.with_glmgee(cases.euler1d_sod(101, "js"), "23"), cons=True)]
+
+
+@pytest.mark.parametrize("case", GLM, ids=[c.name for c in GLM])
+@pytest.mark.parametrize("variant", ["exact-resident", "exact-host", "fused-resident"])
+def test_glmgee_through_the_glue(need_exes, case, variant, tmp_path):
+    path, mode = variant.split("-")
+    dref, dnew = str(tmp_path / "ref"), str(tmp_path / "b200")
+    case.write(dref)
+    case.write(dnew)
+    _run(REF_EXE, dref)
+    out_new = _run(B200_EXE, dnew, {"HYPARB200_USE_FUSED": "0" if path == "exact" else "1", "HYPARB200_MODE": mode})
+    assert "hypar_b200 attached" in out_new
+    for pat, least in (("op_*.bin", 3), ("ts0_*.bin", 2)):       # no auxiliary file with the initial solution (no integrator yet)
+        files = sorted(os.path.basename(f) for f in glob.glob(os.path.join(dref, pat)))
+        assert len(files) >= least, (pat, files)
+        assert files == sorted(os.path.basename(f) for f in glob.glob(os.path.join(dnew, pat)))
+        scale = np.abs(hypario.read_op_bin(os.path.join(dref, sorted(glob.glob(os.path.join(dref, "op_*.bin")))[-1]))[1]).max()
+        for f in files:
+            a, b = os.path.join(dref, f), os.path.join(dnew, f)
+            viscous = float(case.physics.get("Re", -1.0)) > 0
+            if path == "exact" and not viscous:
+                assert filecmp.cmp(a, b, shallow=False), f"{f}: not byte-identical to the reference's file"
+            else:
+                ua, ub = hypario.read_op_bin(a)[1], hypario.read_op_bin(b)[1]
+                assert np.abs(ua - ub).max() <= (1e-11 if path == "fused" else 1e-14) * scale, f"{f}: {np.abs(ua - ub).max():.3e}"
+    # glm_err.dat is not compared: HyPar's main calls CalculateError after TimeCleanup, where TimeError returns at once
+    # (TimeError.c:41: the integrator is gone) -- the file is never written; tests/test_gpu_glmgee.py checks those norms
+    assert not os.path.exists(os.path.join(dref, "glm_err.dat")) and not os.path.exists(os.path.join(dnew, "glm_err.dat"))
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # ensembles (nsims > 1, TimeRK.c:50-93) through the glue: one library solver per SimulationObject
 REF_MAIN = os.path.join(ROOT, "oracle", "_ref", "hypar_ref_main")
 

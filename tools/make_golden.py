@@ -74,6 +74,12 @@ GOLDEN = [
     ("c3_vortex_hcweno_js_char_roe", "ns2d_vortex", dict(n=(20, 16), weno="js+rc0.5+xi0.01", upwinding="roe", interp="characteristic", scheme="hcweno5"), "hypar_ref_mpi1", True),
     ("c5b_bubble_hcweno_mapped", "ns3d_rising_bubble", dict(n=(12, 16, 10), weno="mapped+rc0.2", scheme="hcweno5"), "hypar_ref_mpi1", False),
     ("c2_sod_hcweno_yc_char_llf_gravity", "euler1d_sod", dict(n=101, weno="yc", upwinding="llf-char", gravity=1.0, scheme="hcweno5"), "hypar_ref", False),
+    # GLM-GEE time integrators (TimeGLMGEE.c): the solution, the auxiliary solution and TimeError's norms after 3 steps
+    ("glm_linadv_23_yeps", "glmgee", dict(base="linear_advection_sine", tstype="23", n=64, weno="js"), "hypar_ref", False),
+    ("glm_vortex_exrk2a_yyt", "glmgee", dict(base="ns2d_vortex", tstype="exrk2a", ee_mode="yyt", n=(20, 16), weno="yc"), "hypar_ref_mpi1", False),
+    ("glm_turb_rk32g1_yeps_visc", "glmgee", dict(base="ns3d_turbulence", tstype="rk32g1", n=(10, 8, 8), weno="mapped"), "hypar_ref_mpi1", False),
+    ("glm_bubble_rk285ex_yyt", "glmgee", dict(base="ns3d_rising_bubble", tstype="rk285ex", ee_mode="yyt", n=(10, 12, 8), weno="js"), "hypar_ref", False),
+    ("glm_sod_35_yyt", "glmgee", dict(base="euler1d_sod", tstype="35", ee_mode="yyt", n=101, weno="z"), "hypar_ref", False),
     ("c2_sod_upw5_comp_rusanov", "euler1d_sod", dict(n=101, weno="js", interp="components", upwinding="rusanov", scheme="upw5"), "hypar_ref", True),
 ]
 
@@ -115,6 +121,10 @@ def main():
         o = run_reference(case, "steps", [3], exe=exe)
         case.solver["conservation_check"] = "no"
         data["steps3_u"] = o["ufinal"]["data"]
+        if "uaux" in o:                                      # time_scheme glm-gee
+            import re
+            data["steps3_uaux"] = o["uaux"]["data"]
+            data["steps3_glmerr"] = np.array([float(v) for v in re.search(r"GLMERR (.*)", o["stdout"]).group(1).split()])
         cons = parse_conservation(o["stdout"])
         data["cons_vol0"] = cons["vol0"]
         data["cons_steps"] = np.array(cons["cons"])          # per step: VolumeIntegral | TotalBoundaryIntegral | ConservationError
@@ -129,7 +139,9 @@ def main():
         meta = {"builder": builder, "kwargs": {k: (list(v) if isinstance(v, tuple) else v) for k, v in kwargs.items()},
                 "exe": exe, "reference": "debog/hypar sources under /root/reference, gcc -O3 -std=c99 (oracle/Makefile)"}
         data["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
-        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **data)
+        sub = os.path.join(out_dir, "glmgee") if builder == "glmgee" else out_dir      # own directory, own tests
+        os.makedirs(sub, exist_ok=True)
+        np.savez_compressed(os.path.join(sub, name + ".npz"), **data)
         print(name, {k: v.shape for k, v in data.items() if k != "meta"} if False else len(data))
 
 
