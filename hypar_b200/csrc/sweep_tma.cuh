@@ -629,9 +629,18 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
     __syncwarp();
 
     // ---------------- shift (warp-private): the last 5 records and the interface-flux carry move to the front
-    for (int i = l; i < LY::NFREC * 5; i += 32) {
-      const int f = i / 5, r = i % 5;
-      rec[f * NREC + rbase + r] = rec[f * NREC + rbase + TL + r];
+    // Lane l < 25 owns record r = l % 5 of the fields l / 5 + {0, 5, 10, ...}: one address per lane, the fields at
+    // compile-time offsets, all loads before the stores (profiles/r02c: the i / 5, i % 5 loop over 5 NFREC elements was
+    // 5.6 % of the warp-stall samples of every sweep)
+    if (l < 25) {
+      const int f0 = (l * 13) >> 6;                       // l / 5 for l < 32
+      double* p = rec + f0 * NREC + rbase + (l - 5 * f0);
+      constexpr int NG = (LY::NFREC + 4) / 5;
+      double t[NG];
+#pragma unroll
+      for (int k = 0; k < NG; k++) if (5 * k + 5 <= LY::NFREC || f0 + 5 * k < LY::NFREC) t[k] = p[5 * k * NREC + TL];
+#pragma unroll
+      for (int k = 0; k < NG; k++) if (5 * k + 5 <= LY::NFREC || f0 + 5 * k < LY::NFREC) p[5 * k * NREC] = t[k];
     }
     if (l < LY::NFF) exF[l * NEX + xbase] = exF[l * NEX + xbase + TL];
     __syncwarp();
