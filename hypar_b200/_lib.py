@@ -61,7 +61,7 @@ SYMBOLS = [
     "hpb_comm_get_unique_id", "hpb_comm_nccl_version", "hpb_comm_init_nccl", "hpb_comm_init_local", "hpb_comm_finalize",
     "hpb_comm_kind", "hpb_comm_allreduce", "hpb_comm_stats", "hpb_exchange_plan", "hpb_ExchangeBoundariesnD", "hpb_ExchangeBoundariesLocal",
     "hpb_TimeStepDistributed", "hpb_TimeStepsDistributed", "hpb_RHSFunctionDistributed", "hpb_TimeStepsLocal",
-    "hpb_RHSFunctionLocal", "hpb_set_overlap", "hpb_stage_overlap_supported",
+    "hpb_RHSFunctionLocal", "hpb_set_overlap", "hpb_stage_overlap_supported", "hpb_set_stage_fusion", "hpb_stage_fusion_active",
     "hpb_dev_get_stage_rhs", "hpb_nstages", "hpb_needs_viscous_exchange",
     "hpb_dev_VolumeIntegral", "hpb_dev_StageBoundaryIntegral", "hpb_dev_StepBoundaryIntegral", "hpb_BoundaryIntegral",
     "hpb_CalculateConservationError", "hpb_dev_ErrorSums",
@@ -150,6 +150,8 @@ def load():
     L.hpb_RHSFunctionLocal.argtypes = [C.POINTER(vp), C.c_int]
     L.hpb_ExchangeBoundariesLocal.argtypes = [C.POINTER(vp), C.c_int]
     L.hpb_set_overlap.argtypes = [vp, C.c_int]
+    L.hpb_set_stage_fusion.argtypes = [vp, C.c_int]
+    L.hpb_stage_fusion_active.argtypes = [vp]
     L.hpb_dev_get_stage_rhs.argtypes = [vp, C.c_int, dp]
     L.hpb_dev_VolumeIntegral.argtypes = [vp, dp]
     L.hpb_dev_StageBoundaryIntegral.argtypes = [vp, C.c_int, dp]

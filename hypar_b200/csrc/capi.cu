@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include "hpb_internal.h"
@@ -196,12 +197,14 @@ static void stage_boundary_flux(hpb_solver* h, const double* U, int slot, int on
   for (int d = 0; d < h->geo.ndims; d++) if (only_dir < 0 || d == only_dir) hpbk::boundary_flux(h, U, d, cons_slot(h, slot));
 }
 
+static bool stage_fusion_on(const hpb_solver* h);
 static int alloc_main(hpb_solver* h)
 {
   const long long n = ncell(h);
   TRY(dalloc(&h->d_u, n)); TRY(dalloc(&h->d_U, n));
   for (int s = 0; s < h->rk.ns; s++) TRY(dalloc(&h->d_Udot[s], n));
   if (h->rk.glm) { TRY(dalloc(&h->d_aux, n)); TRY(dalloc(&h->d_aux2, n)); }
+  if (stage_fusion_on(h) && !h->rk.glm && h->rk.ns > 1) TRY(dalloc(&h->d_U2, n));
   if (fused_visc(h)) TRY(dalloc(&h->d_qd4, 12 * h->geo.npg));
   if (!fused_path(h) || (viscous_on(h) && !fused_visc(h))) TRY(ensure_generic(h));
   TRY(dalloc(&h->d_part, hpbk::diag_partial_size()));
@@ -220,6 +223,7 @@ extern "C" int hpb_create(const hpb_config* cfg, hpb_solver** out)
   h->cfg = *cfg;
   int rc = hpb_setup_host(h);
   if (rc) { delete h; return rc; }
+  { const char* e = getenv("HPB_STAGE_FUSION"); if (e && e[0] == '0') h->stage_fusion = 0; }     // A/B measurements (bench.py)
   // keep a private copy of the global grid (the caller's pointer need not outlive this call)
   h->cfg.x_global = nullptr;
 
@@ -277,7 +281,7 @@ extern "C" int hpb_destroy(hpb_solver* h)
   hpbc::comm_free(h);          // before the halo buffers go (it frees them itself when NCCL allocated them)
   double** ptrs[] = { &h->d_x, &h->d_dxinv, &h->d_gravf, &h->d_gravg, &h->d_u, &h->d_U, &h->d_fI, &h->d_sI,
                       &h->d_FV, &h->d_stage_aos, &h->d_w, &h->d_red, &h->d_qd4, &h->d_par, &h->d_src,
-                      &h->d_cons, &h->d_face, &h->d_part, &h->d_aux, &h->d_aux2 };
+                      &h->d_cons, &h->d_face, &h->d_part, &h->d_aux, &h->d_aux2, &h->d_U2 };
   for (double** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
   for (int i = 0; i < HPB_MAX_STAGES; i++) if (h->d_Udot[i]) cudaFree(h->d_Udot[i]);
   for (int i = 0; i < 4; i++) if (h->d_tmp[i]) cudaFree(h->d_tmp[i]);
@@ -445,13 +449,33 @@ extern "C" int hpb_fp64_issue_peak(hpb_solver* h, double* thread_instr_per_s)
 // Production path: [Q-derivatives] | sweeps with the viscous flux and the gravity source inside.
 // Exact path (use_fused = 0 or a configuration the fused kernels do not cover): generic kernels, par and
 // source accumulated separately and combined in the reference's order, so that the result is bit-identical.
-static int rhs_part_a(hpb_solver* h, const double* U, double* rhs)
+// Stage fusion (sweep_tma.cuh, RKF): when row s+1 of the explicit RK tableau has the single entry a_{s+1,s} -- every row of
+// RK4, the second of SSPRK3 -- the last sweep of stage s also writes U_{s+1} = u + a dt k_s (TimeRK.c:131-141) with
+// k_rk_combine's own two roundings, so the results do not change by a bit. Needs the sweeps to be the last contribution to
+// the right-hand side: no sponge (added after the sweeps), viscous terms inside the sweeps or absent.
+static bool stage_fusion_on(const hpb_solver* h)
+{
+  return h->stage_fusion && hpbk::stage_fusion_available(h) && !hpbk::has_sponge(h) && (fused_visc(h) || !viscous_on(h));
+}
+// where the sweeps of stage s (stage solution U) may put the next stage solution, and its coefficient; nullptr = not fusable
+static double* fused_next_stage(hpb_solver* h, int s, const double* U, double* adt)
+{
+  const RKTableau& T = h->rk;
+  if (s < 0 || T.glm || s + 1 >= T.ns || !stage_fusion_on(h)) return nullptr;
+  for (int i = 0; i < s; i++) if (T.A[(s + 1) * T.ns + i] != 0.0) return nullptr;
+  const double a = T.A[(s + 1) * T.ns + s];
+  if (a == 0.0 || !h->d_U2) return nullptr;
+  *adt = h->cfg.dt * a;
+  return (U == h->d_U) ? h->d_U2 : h->d_U;
+}
+
+static int rhs_part_a(hpb_solver* h, const double* U, double* rhs, double* unext = nullptr, double adt = 0.0)
 {
   if (fused_path(h)) {
     if (fused_visc(h)) {
       TRY(hpbk::qderiv_fused(h, U));
     } else {
-      if (!hpbk::hyperbolic_fused(h, U, rhs, /*negate=*/true, /*with_source=*/true, rhs, nullptr))
+      if (!hpbk::hyperbolic_fused(h, U, rhs, /*negate=*/true, /*with_source=*/true, rhs, nullptr, -1, unext, adt))
         return hpb_fail(HPB_ERR_CUDA, "right-hand side: the fused sweep refused the launch");
       if (viscous_on(h)) hpbk::parabolic_phase1(h, U);          // NavierStokes2D viscous terms: generic kernels
     }
@@ -464,11 +488,11 @@ static int rhs_part_a(hpb_solver* h, const double* U, double* rhs)
   if (viscous_on(h)) hpbk::parabolic_phase1(h, U);
   return HPB_OK;
 }
-static int rhs_part_b(hpb_solver* h, const double* U, double* rhs)
+static int rhs_part_b(hpb_solver* h, const double* U, double* rhs, double* unext = nullptr, double adt = 0.0)
 {
   if (fused_path(h)) {
     if (fused_visc(h)) {
-      if (!hpbk::hyperbolic_fused(h, U, rhs, true, true, rhs, h->d_qd4))
+      if (!hpbk::hyperbolic_fused(h, U, rhs, true, true, rhs, h->d_qd4, -1, unext, adt))
         return hpb_fail(HPB_ERR_CUDA, "right-hand side: the fused sweep refused the launch");
     }
     else if (viscous_on(h)) hpbk::parabolic_phase2(h, U, rhs, /*accumulate=*/true);
@@ -746,7 +770,8 @@ extern "C" int hpb_dev_fill_solution_from_global(hpb_solver* h, const double* ug
 // re-applied by the RHS are idempotent), saving one pass over memory per step.
 static double* stage_U(hpb_solver* h, int s)
 {
-  if (s == 0) return h->d_u;
+  if (s == 0) { h->U_pre = nullptr; return h->d_u; }
+  if (h->U_pre) { double* p = h->U_pre; h->U_pre = nullptr; return p; }     // formed by the last sweep of stage s-1
   hpbk::rk_stage(h, s);
   return h->d_U;
 }
@@ -779,8 +804,11 @@ static int step_single(hpb_solver* h)
   for (int s = 0; s < h->rk.ns; s++) {
     double* U = stage_U(h, s);                  // TimeRK.c:131-141
     if (s > 0) hpbk::apply_bc(h, U);            // TimeRHSFunctionExplicit.c:46 (stage 0 is u itself: just done)
-    TRY(rhs_part_a(h, U, h->d_Udot[s]));
-    TRY(rhs_part_b(h, U, h->d_Udot[s]));
+    double adt = 0.0;
+    double* unext = fused_next_stage(h, s, U, &adt);
+    TRY(rhs_part_a(h, U, h->d_Udot[s], unext, adt));
+    TRY(rhs_part_b(h, U, h->d_Udot[s], unext, adt));
+    h->U_pre = unext;
     stage_boundary_flux(h, U, s);               // TimeRK.c:172-177 (BoundaryFlux[s] = StageBoundaryIntegral)
   }
   hpbk::rk_finish(h);                           // TimeRK.c:182-193
@@ -1090,7 +1118,7 @@ static int dist_prestep(Grp& G)
   return HPB_OK;
 }
 
-static int dist_stage(Grp& G, int s)
+static int dist_stage(Grp& G, int s, bool fuse = true)
 {
   const bool overlap = G.hs[0]->overlap != 0;
   // ---- stage solution with boundary conditions and halo (TimeRK.c:131-141, TimeRHSFunctionExplicit.c:46-60)
@@ -1112,8 +1140,11 @@ static int dist_stage(Grp& G, int s)
     EACH(h) { TRY(need_device(h)); h->U_cur = stage_U(h, s); hpbk::apply_bc(h, h->U_cur); }
     TRY(exchange_u_serial(G, true));
   }
-  // ---- right-hand side
+  // ---- right-hand side (its last sweep may form the next stage solution: fused_next_stage)
   const bool visc = viscous_on(G.hs[0]);
+  std::vector<double*> unext(G.n, nullptr);
+  std::vector<double> adt(G.n, 0.0);
+  if (fuse) EACH(h) unext[r_] = fused_next_stage(h, s, h->U_cur, &adt[r_]);
   if (overlap && hpb_stage_overlap_supported(G.hs[0])) {
     const bool fv = fused_visc(G.hs[0]);
     const int nd = G.hs[0]->geo.ndims;
@@ -1134,7 +1165,7 @@ static int dist_stage(Grp& G, int s)
       EACH(h) {
         TRY(need_device(h));
         double* rhs = h->d_Udot[s];
-        if (!hpbk::hyperbolic_fused(h, h->U_cur, rhs, true, true, rhs, fv ? h->d_qd4 : nullptr, d))
+        if (!hpbk::hyperbolic_fused(h, h->U_cur, rhs, true, true, rhs, fv ? h->d_qd4 : nullptr, d, unext[r_], adt[r_]))
           return hpb_fail(HPB_ERR_CUDA, "distributed step: fused sweep of direction %d refused the launch", d);
         stage_boundary_flux(h, h->U_cur, s, d);
       }
@@ -1159,7 +1190,7 @@ static int dist_stage(Grp& G, int s)
         if (viscous_on(h)) hpbk::parabolic_phase1(h, h->U_cur);
       }
     } else {
-      EACH(h) { TRY(need_device(h)); TRY(rhs_part_a(h, h->U_cur, h->d_Udot[s])); }
+      EACH(h) { TRY(need_device(h)); TRY(rhs_part_a(h, h->U_cur, h->d_Udot[s], unext[r_], adt[r_])); }
     }
     if (visc) {
       for (int slot = hpbc::SLOT_Q0; slot <= hpbc::SLOT_Q12; slot++) {
@@ -1172,8 +1203,9 @@ static int dist_stage(Grp& G, int s)
         EACH(h) { TRY(need_device(h)); hpbc::unpack_faces(h, slot, nullptr); }
       }
     }
-    EACH(h) { TRY(need_device(h)); TRY(rhs_part_b(h, h->U_cur, h->d_Udot[s])); stage_boundary_flux(h, h->U_cur, s); }
+    EACH(h) { TRY(need_device(h)); TRY(rhs_part_b(h, h->U_cur, h->d_Udot[s], unext[r_], adt[r_])); stage_boundary_flux(h, h->U_cur, s); }
   }
+  EACH(h) h->U_pre = unext[r_];
   EACH(h) TRY(check_async(h, "distributed stage"));
   return HPB_OK;
 }
@@ -1240,7 +1272,7 @@ static int dist_steps(Grp& G, int nsteps)
 static int dist_rhs(Grp& G)
 {
   TRY(dist_prestep(G));
-  return dist_stage(G, 0);
+  return dist_stage(G, 0, /*fuse=*/false);
 }
 
 // NCCL transport: this rank's part; only enqueues (no host synchronisation: hpb_synchronize when the result is needed)
@@ -1288,6 +1320,19 @@ extern "C" int hpb_ExchangeBoundariesLocal(hpb_solver** hs, int nranks)
   TRY(exchange_u_serial(G, false));
   EACH(h) { h->u_halo_valid = true; TRY(sync_check(h, "ExchangeBoundariesLocal")); }
   return HPB_OK;
+}
+
+extern "C" int hpb_set_stage_fusion(hpb_solver* h, int on)
+{
+  if (!h) return hpb_fail(HPB_ERR_INVALID, "set_stage_fusion: null solver");
+  h->stage_fusion = on ? 1 : 0;
+  h->U_pre = nullptr;
+  if (on && h->device_ready && stage_fusion_on(h) && !h->rk.glm && h->rk.ns > 1) TRY(dalloc(&h->d_U2, ncell(h)));
+  return HPB_OK;
+}
+extern "C" int hpb_stage_fusion_active(const hpb_solver* h)
+{
+  return (stage_fusion_on(h) && h->d_U2 && !h->rk.glm) ? 1 : 0;
 }
 
 extern "C" int hpb_set_overlap(hpb_solver* h, int on)

@@ -83,6 +83,10 @@ struct hpb_solver {
   double *d_x = nullptr, *d_dxinv = nullptr, *d_gravf = nullptr, *d_gravg = nullptr;
   double *d_u = nullptr;           // solution (SoA, ghosts)
   double *d_U = nullptr;           // stage solution
+  double *d_U2 = nullptr;          // second stage-solution array: the last sweep of a stage writes the NEXT stage solution while
+                                   // it still reads the current one (sweep_tma.cuh, RKF)
+  double *U_pre = nullptr;         // the next stage solution if the sweeps of the current stage have formed it, else nullptr
+  int stage_fusion = 1;            // hpb_set_stage_fusion: allow that (default); 0 = every stage vector by k_rk_combine
   double *U_cur = nullptr;         // distributed step: the array holding the current stage solution (d_u for stage 0)
   double *d_Udot[HPB_MAX_STAGES] = {};
   double *d_aux = nullptr, *d_aux2 = nullptr;   // GLM-GEE: the auxiliary solution (TS->U[r]) and its next value
@@ -179,8 +183,11 @@ int  hyperbolic_pieces_group(hpb_solver** hs, int n, const double* const* u, dou
 int  tridiag_error(hpb_solver* h);      // 1 if a tridiagonal solve met a zero pivot since the last call (synchronises)
 // fused sweeps (sweep_fused.cu); qd != nullptr: the NavierStokes3D viscous terms are evaluated inside the sweeps
 bool fused_available(const hpb_solver* h);
+// unext != nullptr: the sweep of the last direction also writes the next RK stage solution u + adt * out there (only when
+// stage_fusion_available(h); out = the complete right-hand side: nothing may be added to it afterwards)
 bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src,
-                      const double* qd, int only_dir = -1);
+                      const double* qd, int only_dir = -1, double* unext = nullptr, double adt = 0.0);
+bool stage_fusion_available(const hpb_solver* h);
 // fused viscous path (viscous_fused.cu)
 int qderiv_fused(hpb_solver* h, const double* u, int part = 0);
 // exact path: rhs = (rhs + par) + src in the reference's order (TimeRHSFunctionExplicit.c:89-92)

@@ -79,6 +79,8 @@ bool tma_maps_for(hpb_solver* h, const SweepArgs& a, bool xs, bool grav, bool vi
   tm->qd = tm->u; tm->gf = tm->u; tm->gg = tm->u;
   if (visc && !get_map(h, a.qd, 12, 1, kind, &tm->qd)) return false;
   if (grav && (!get_map(h, a.gf, 1, 1, kind, &tm->gf) || !get_map(h, a.gg, 1, 1, kind, &tm->gg))) return false;
+  tm->un = tm->u;
+  if (a.unext != nullptr && (xs || !get_map(h, a.unext, nv, nv, kind, &tm->un))) return false;
   return true;
 }
 
@@ -108,11 +110,24 @@ bool fused_available(const hpb_solver* h)
   return true;
 }
 
+// Can the last direction's sweep of this configuration also write the next RK stage solution (sweep_tma.cuh, RKF)? The
+// TMA-fed kernel must be the one that runs (2-D / 3-D fluid model, component-wise, even padded row length, driver entry
+// point) and the sweeps must be the last contribution to the right-hand side (the caller checks the rest: capi.cu).
+bool stage_fusion_available(const hpb_solver* h)
+{
+  const hpb_config& c = h->cfg;
+  if (!fused_available(h) || c.use_fused == 2 || h->phys.interp_char) return false;
+  if (c.model != HPB_MODEL_NS2D && c.model != HPB_MODEL_NS3D) return false;
+  if ((h->geo.P[0] & 1) || h->geo.ndims < 2 || h->geo.g != HPB_G || !hpbf::tma_available()) return false;
+  return true;
+}
+
 bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src,
-                      const double* qd, int only_dir)
+                      const double* qd, int only_dir, double* unext, double adt)
 {
   if (with_source && src != nullptr && src != out) return false;     // the fused kernels accumulate the source into `out`
   const Geom& G = h->geo;
+  if (unext != nullptr && (!negate || unext == u || unext == out || !stage_fusion_available(h))) return false;
   const int wt = h->phys.no_limiting ? hpbf::WT_NOLIM : h->phys.weno;
   for (int d = 0; d < G.ndims; d++) {
     if (only_dir >= 0 && d != only_dir) continue;
@@ -124,6 +139,7 @@ bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, 
     a.with_source = (with_source && h->phys.has_grav && h->phys.grav[d] != 0.0 && src != nullptr) ? 1 : 0;
     a.qd = qd;
     a.upw = (h->cfg.upwind == HPB_UPWIND_ROE) ? 1 : 0;
+    a.unext = (d == G.ndims - 1) ? unext : nullptr; a.adt = adt;
     {
       static const int tab[3][8] = { { 0, 1, 2, 3, 4, 5, 8, 10 }, { 4, 5, 6, 7, 0, 1, 9, 10 }, { 8, 9, 10, 11, 0, 2, 5, 6 } };
       for (int k = 0; k < 8; k++) a.qidx[k] = tab[d][k];

@@ -31,18 +31,19 @@ static bool launch_one(hpb_solver* h, const SweepArgs& a)
 // TMA variant (sweep_tma.cuh): NavierStokes2D/3D, even padded row length, x-sweep overwriting / y-,z-sweeps
 // accumulating (what hyperbolic_fused always asks for). Returns false when not applicable: the caller then
 // launches k_sweep.
-template <int MODEL, int WT, bool XS, bool GRAV, bool VISC, bool CHR = false>
+template <int MODEL, int WT, bool XS, bool GRAV, bool VISC, bool CHR = false, bool RKF = false>
 static bool launch_one_tma(hpb_solver* h, const SweepArgs& a)
 {
-  using LY = TmaLayout<MODEL, GRAV, VISC>;
+  using LY = TmaLayout<MODEL, GRAV, VISC, RKF>;
   constexpr size_t smem = LY::smem_bytes;
   if (smem > 227 * 1024) return false;
   const bool accumulate = (a.mode & 1) != 0;
   if (XS == accumulate) return false;
   TmaMaps tm;
+  if (RKF != (a.unext != nullptr)) return false;
   if (!tma_maps_for(h, a, XS, GRAV, VISC, &tm)) return false;
   static unsigned long long configured = 0ull;        // per device ordinal, as above
-  auto kern = k_sweep_tma<MODEL, WT, XS, GRAV, VISC, CHR>;
+  auto kern = k_sweep_tma<MODEL, WT, XS, GRAV, VISC, CHR, RKF>;
   const unsigned long long dbit = 1ull << (h->device & 63);
   if (!(configured & dbit)) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -68,13 +69,17 @@ static bool launch_pick(hpb_solver* h, const SweepArgs& a)
   if (MODEL != HPB_MODEL_LINEAR_ADR && h->phys.interp_char) {
     // characteristic-wise reconstruction: the TMA-fed kernel only (fused_available has checked that it applies), no gravity
     constexpr int M2 = (MODEL == HPB_MODEL_LINEAR_ADR) ? HPB_MODEL_NS3D : MODEL;
-    if (GRAV) return false;
+    if (GRAV || a.unext != nullptr) return false;
     return launch_one_tma<M2, WT, MAPX, false, VISC, true>(h, a);
   }
   if (MODEL != HPB_MODEL_LINEAR_ADR && h->cfg.use_fused != 2) {
     constexpr int M2 = (MODEL == HPB_MODEL_LINEAR_ADR) ? HPB_MODEL_NS3D : MODEL;   // never instantiated for LinearADR
+    // the last direction's sweep that also forms the next RK stage solution (accumulating sweeps only; the caller has
+    // checked that the TMA-fed kernel applies -- there is no other kernel that writes a.unext)
+    if (!MAPX && a.unext != nullptr) return launch_one_tma<M2, WT, false, GRAV, VISC, false, true>(h, a);
     if (launch_one_tma<M2, WT, MAPX, GRAV, VISC>(h, a)) return true;
   }
+  if (a.unext != nullptr) return false;
   return launch_one<MODEL, WT, MAPX, GRAV, VISC>(h, a);
 }
 

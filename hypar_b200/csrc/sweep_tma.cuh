@@ -20,6 +20,14 @@
 //            box is clipped at the array bounds by the TMA).  x-sweep (always the first direction:
 //            overwrites): lanes run along x, so each warp stores its own 256 contiguous bytes from
 //            registers.
+//   stage    RKF variant of the LAST direction's sweep (y in 2-D, z in 3-D): instead of adding its flux difference to the
+//            right-hand side in L2, the CTA loads the tile of the right-hand side accumulated so far into the result tile
+//            (TMA, issued as soon as the previous step's stores have read it), completes k = rhs + own part there, forms the
+//            next stage solution u + (a dt) k from the cell's record -- the two roundings of k_rk_combine -- and stores BOTH
+//            tiles with plain cp.async.bulk.tensor stores: the stage-vector pass over memory (TimeRK.c:131-141) disappears
+//            under a kernel that is bound by the FP64 pipe. Cells of the tile outside the interior are written back
+//            unchanged (k) or as zero (next stage solution: ghost lines / ghost cells, filled by the boundary conditions
+//            and the halo exchange afterwards).
 //   sync     no __syncthreads in the march. The last warp to finish reading the input tile of step m
 //            (shared atomic counter) issues the loads of step m+1; the last warp to stage its results
 //            issues the reduce and, when the TMA has read the tile, frees it through an mbarrier. Warps
@@ -49,6 +57,7 @@ namespace hpbf {
 
 struct TmaMaps {
   CUtensorMap u, qd, out, gf, gg;
+  CUtensorMap un;          // RKF: the next stage solution
 };
 // host (sweep_fused.cu): descriptors for the arrays of one launch; false when the TMA path does not apply
 // (driver entry point missing, odd padded row length, misaligned array)
@@ -86,13 +95,18 @@ __device__ __forceinline__ void tma_reduce_add4(const CUtensorMap* m, const void
   asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                :: "l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_store4(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3)
+{
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :: "l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // shared-memory carve-up (doubles). TMA tiles first (the 64-byte swizzle is a function of address bits 4..8: the
 // dynamic shared memory is declared 1024-byte aligned and every tile is 2048 B), then the warp-private
 // records and exchanges of k_sweep. Without gravity the mass flux rho*v_d IS the conserved momentum component
 // (to rounding), so its record field, reconstruction and exchange slot are dropped (SKIPF0).
-template <int MODEL, bool GRAV, bool VISC>
+template <int MODEL, bool GRAV, bool VISC, bool RKF = false>
 struct TmaLayout {
   using SL = SweepLayout<MODEL, GRAV, VISC>;
   static constexpr int NV = RecLayout<MODEL>::NV;
@@ -121,10 +135,11 @@ struct TmaLayout {
   static constexpr int NFIN = SL::NFSTG;                    // input fields: u, (gf, gg), (8 derivative scalars)
   static constexpr int o_in = 0;
   static constexpr int o_out = o_in + NFIN * TILE;          // result tile (y-/z-sweeps)
-  static constexpr int o_rec = o_out + NV * TILE;
+  static constexpr int o_ust = o_out + NV * TILE;           // RKF: tile of the next stage solution
+  static constexpr int o_rec = o_ust + (RKF ? NV * TILE : 0);
   static constexpr int o_exL = o_rec + NFREC * NREC;
-  static constexpr int o_exF = o_exL + NFL * NEX;
-  static constexpr int o_sync = o_exF + NFF * NEX;          // 2 mbarriers + 2 counters
+  static constexpr int o_car = o_exL + NFL * NEX;           // interface-flux carry of every line (lane 31 -> lane 0 of the next step)
+  static constexpr int o_sync = o_car + NFF * TW;           // 3 mbarriers (full, free, rin) + 2 counters
   static constexpr size_t smem_bytes = sizeof(double) * (size_t)(o_sync + 4);
 };
 
@@ -140,10 +155,11 @@ struct TmaLayout {
 // the sign of the shear rows, which cancels against the sign of the matching column (WENO is odd in its data and its
 // weights are even). Only (q0, beta, dn) of the six cells are kept in registers; the shear fields re-read their
 // component. No gravity in this variant.
-template <int MODEL, int WT, bool XS, bool GRAV, bool VISC, bool CHR = false>
+template <int MODEL, int WT, bool XS, bool GRAV, bool VISC, bool CHR = false, bool RKF = false>
 __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __grid_constant__ TmaMaps tm)
 {
-  using LY = TmaLayout<MODEL, GRAV, VISC>;
+  static_assert(!(RKF && XS), "the stage-vector variant belongs to the accumulating sweeps");
+  using LY = TmaLayout<MODEL, GRAV, VISC, RKF>;
   using SL = SweepLayout<MODEL, GRAV, VISC>;
   constexpr int NV = LY::NV;
   constexpr int NDV = NV - 2;
@@ -156,11 +172,13 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
   double* ost = smem + LY::o_out;
   double* rec = smem + LY::o_rec;
   double* exL = smem + LY::o_exL;
-  double* exF = smem + LY::o_exF;
+  double* car = smem + LY::o_car;
+  double* ust = smem + LY::o_ust;
   unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(smem + LY::o_sync);
   unsigned long long* free_bar = full_bar + 1;
   unsigned* cons_cnt = reinterpret_cast<unsigned*>(full_bar + 2);
   unsigned* res_cnt = cons_cnt + 1;
+  unsigned long long* rin_bar = full_bar + 3;
 
   const Geom& G = a.G;
   const int dir = a.dir;
@@ -225,16 +243,26 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
     }
   };
 
+  auto issue_rin = [&](int m) {
+    // RKF, executed by ONE thread: the right-hand side accumulated by the earlier directions on the cells step m writes
+    mbar_expect_tx(rin_bar, (unsigned)(NV * TILE * sizeof(double)));
+    const int cd = TL * m + G.g;
+    int c0 = tc0, c1t = tc1, c2t = tc2;
+    if (dir == 1) c1t = cd; else c2t = cd;
+    tma_load4(ost, &tm.out, rin_bar, c0, c1t, c2t, 0);
+  };
+
   if ((smem_u32(smem) & 1023u) != 0) __trap();      // the swizzled tiles assume the declared alignment
   if (tid == 0) {
     mbar_init(full_bar, 1);
     mbar_init(free_bar, 1);
+    mbar_init(rin_bar, 1);
     *cons_cnt = 0; *res_cnt = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
   __syncthreads();
-  if (tid == 0) issue_loads(-1);
+  if (tid == 0) { issue_loads(-1); if (RKF && M > 0) issue_rin(0); }
 
   for (int m = -1; m < M; m++) {
     const int c1 = TL * m + 3 + l;
@@ -422,9 +450,6 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
         }
       }
       fh[NV - 1] = fma(ek, g0, fma(H, gm + gp, fma(vn, gdif, shear_e)));
-      const int exo = xbase + l + 1;
-#pragma unroll
-      for (int v = 0; v < NV; v++) exF[v * NEX + exo] = fh[v];
     }
     __syncwarp();
     } else {
@@ -545,14 +570,9 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
           fh[v] = (fL + fRv[v]) - alpha * (uRv[v] - uL);          // 2 x the interface flux; the factor 1/2 is in dxih
         }
       }
-      const int exo = xbase + l + 1;
-#pragma unroll
-      for (int v = 0; v < NV; v++) exF[v * NEX + exo] = fh[v];
       if (G3 && a.with_source) {
         Sh[0] = 0.5 * (exL[(LY::xZ + 0) * NEX + exl] + sR[0]);
         Sh[1] = 0.5 * (exL[(LY::xZ + 1) * NEX + exl] + sR[1]);
-        exF[(NV + 0) * NEX + exo] = Sh[0];
-        exF[(NV + 1) * NEX + exo] = Sh[1];
       }
     }
     __syncwarp();
@@ -562,20 +582,28 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
 
     }
 
-    // ---------------- P4: cell jo = j-1 = 32m+l (position l+2): interfaces j-1/2 (own) and j-3/2 (neighbour / carry)
+    // ---------------- P4: cell jo = j-1 = 32m+l (position l+2): interfaces j-1/2 (own) and j-3/2 (the lane below; lane 0:
+    // the carry lane 31 left in the previous step). The interface fluxes travel by warp shuffle, not through shared memory.
     if (m >= 0) {
       const bool out_ok = line_ok && jo >= 0 && jo < N;
       double res[NV];
+      double Sl[2] = { 0.0, 0.0 };
 #pragma unroll
-      for (int v = 0; v < NV; v++) res[v] = 0.0;
-      if (out_ok) {
-        const int exl = xbase + l;
-        const int co = cc - 1;
+      for (int v = 0; v < NV; v++) {
+        double fl = __shfl_up_sync(0xffffffffu, fh[v], 1);
+        if (l == 0) fl = car[v * TW + w];
+        const double t = dxih * (fh[v] - fl);
+        res[v] = out_ok ? ((a.mode < 2) ? -t : t) : 0.0;
+      }
+      if (G3 && a.with_source) {
 #pragma unroll
-        for (int v = 0; v < NV; v++) {
-          const double t = dxih * (fh[v] - exF[v * NEX + exl]);
-          res[v] = (a.mode < 2) ? -t : t;
+        for (int k = 0; k < 2; k++) {
+          Sl[k] = __shfl_up_sync(0xffffffffu, Sh[k], 1);
+          if (l == 0) Sl[k] = car[(NV + k) * TW + w];
         }
+      }
+      if (out_ok) {
+        const int co = cc - 1;
         if (V3) {
           // par_v += dxinv * (FV[j-2] - 8 FV[j-1] + 8 FV[j+1] - FV[j+2]) / 12   (components 1..4)
           const double dxi12 = dxi * (1.0 / 12.0);
@@ -591,8 +619,8 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
           const double vd = rec[(LY::rVEL + dir) * NREC + co];
           const double f = rec[LY::rGF * NREC + co];
           const double tmm = rho * a.ph.RT, te = rho * a.ph.RT * vd;
-          const double sm = (tmm * f) * (Sh[0] - exF[(NV + 0) * NEX + exl]) * dxi;
-          const double se = (te * f) * (Sh[1] - exF[(NV + 1) * NEX + exl]) * dxi;
+          const double sm = (tmm * f) * (Sh[0] - Sl[0]) * dxi;
+          const double se = (te * f) * (Sh[1] - Sl[1]) * dxi;
 #pragma unroll
           for (int v = 1; v < NV; v++) res[v] += ((v == dir + 1) ? sm : 0.0) + ((v == NV - 1) ? se : 0.0);
         }
@@ -604,9 +632,22 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
           for (int v = 0; v < NV; v++) XS_STORE(a.out + v * npg + pline + jo, res[v]);
         }
       } else {
-        if (m >= 1) mbar_wait(free_bar, (unsigned)(m - 1) & 1u);     // the reduce of step m-1 has read the tile
+        if (RKF) {
+          // the tile holds the right-hand side of the earlier directions (and the stores of step m-1 have read it):
+          // complete k in place, next stage solution beside it -- k_rk_combine's two roundings, no contraction
+          mbar_wait(rin_bar, (unsigned)m & 1u);
+          const int co = cc - 1;
 #pragma unroll
-        for (int v = 0; v < NV; v++) ost[v * TILE + sidx] = res[v];
+          for (int v = 0; v < NV; v++) {
+            const double kf = __dadd_rn(ost[v * TILE + sidx], res[v]);
+            ost[v * TILE + sidx] = kf;
+            ust[v * TILE + sidx] = out_ok ? __dadd_rn(rec[(LY::rU + v) * NREC + co], __dmul_rn(a.adt, kf)) : 0.0;
+          }
+        } else {
+          if (m >= 1) mbar_wait(free_bar, (unsigned)(m - 1) & 1u);     // the reduce of step m-1 has read the tile
+#pragma unroll
+          for (int v = 0; v < NV; v++) ost[v * TILE + sidx] = res[v];
+        }
         fence_proxy_async();
         __syncwarp();
         if (l == 0) {
@@ -618,15 +659,25 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
             const int cd = TL * m + G.g;
             int c0 = tc0, c1t = tc1, c2t = tc2;
             if (dir == 1) c1t = cd; else c2t = cd;
-            tma_reduce_add4(&tm.out, ost, c0, c1t, c2t, 0);
+            if (RKF) {
+              tma_store4(&tm.out, ost, c0, c1t, c2t, 0);
+              tma_store4(&tm.un, ust, c0, c1t, c2t, 0);
+            } else tma_reduce_add4(&tm.out, ost, c0, c1t, c2t, 0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            mbar_arrive(free_bar);
+            if (RKF) { if (m + 1 < M) issue_rin(m + 1); }
+            else mbar_arrive(free_bar);
           }
         }
       }
     }
     __syncwarp();
+    // carry of the interface fluxes for lane 0 of the next step (also from the start-up step, whose lane 31 owns interface -1/2)
+    if (l == 31) {
+#pragma unroll
+      for (int v = 0; v < NV; v++) car[v * TW + w] = fh[v];
+      if (G3 && a.with_source) { car[(NV + 0) * TW + w] = Sh[0]; car[(NV + 1) * TW + w] = Sh[1]; }
+    }
 
     // ---------------- shift (warp-private): the last 5 records and the interface-flux carry move to the front
     // Lane l < 25 owns record r = l % 5 of the fields l / 5 + {0, 5, 10, ...}: one address per lane, the fields at
@@ -642,7 +693,6 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
 #pragma unroll
       for (int k = 0; k < NG; k++) if (5 * k + 5 <= LY::NFREC || f0 + 5 * k < LY::NFREC) p[5 * k * NREC] = t[k];
     }
-    if (l < LY::NFF) exF[l * NEX + xbase] = exF[l * NEX + xbase + TL];
     __syncwarp();
   }
 }

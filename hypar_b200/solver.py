@@ -609,6 +609,14 @@ class Solver:
     def set_overlap(self, on: bool) -> None:
         self._ck(self.L.hpb_set_overlap(self.h, int(bool(on))))
 
+    def set_stage_fusion(self, on: bool) -> None:
+        """the last sweep of an RK stage also writes the next stage solution (default on where it applies)"""
+        self._ck(self.L.hpb_set_stage_fusion(self.h, int(bool(on))))
+
+    @property
+    def stage_fusion_active(self) -> bool:
+        return bool(self.L.hpb_stage_fusion_active(self.h))
+
     def TimeStepsDistributed(self, n: int = 1) -> None:
         self._ck(self.L.hpb_TimeStepsDistributed(self.h, n))
 

@@ -378,6 +378,13 @@ int hpb_RHSFunctionLocal(hpb_solver** ranks, int nranks);
  * unpack in sequence at the reference's call sites. Results are bit-identical. */
 int hpb_set_overlap(hpb_solver* h, int on);
 int hpb_stage_overlap_supported(const hpb_solver* h);     /* 1: this configuration is driven sweep by sweep when overlapped */
+/* Stage fusion, 1 (default): where row s+1 of the explicit RK tableau has the single entry a_{s+1,s} (every row of RK4, the
+ * second of SSPRK3: TimeExplicitRKInitialize.c:58-79) the last directional sweep of stage s also writes the stage solution
+ * U_{s+1} = u + a dt k_s of TimeRK.c:131-141 -- same two roundings, bit-identical results, one pass over memory less per
+ * stage. 0: every stage solution by its own kernel. Applies to the TMA-fed sweeps (NavierStokes2D / 3D, component-wise,
+ * no sponge); hpb_stage_fusion_active says whether this solver uses it. */
+int hpb_set_stage_fusion(hpb_solver* h, int on);
+int hpb_stage_fusion_active(const hpb_solver* h);
 int hpb_dev_get_stage_rhs(hpb_solver* h, int stage, double* rhs_host);   /* Udot[stage] -> host (HyPar layout) */
 int hpb_nstages(const hpb_solver* h);
 int hpb_needs_viscous_exchange(const hpb_solver* h);
