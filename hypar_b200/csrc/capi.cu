@@ -475,7 +475,7 @@ static int rhs_part_a(hpb_solver* h, const double* U, double* rhs, double* unext
     if (fused_visc(h)) {
       TRY(hpbk::qderiv_fused(h, U));
     } else {
-      if (!hpbk::hyperbolic_fused(h, U, rhs, /*negate=*/true, /*with_source=*/true, rhs, nullptr, -1, unext, adt))
+      if (!hpbk::hyperbolic_fused(h, U, rhs, /*negate=*/true, /*with_source=*/true, rhs, nullptr, -1, unext, adt, h->d_u))
         return hpb_fail(HPB_ERR_CUDA, "right-hand side: the fused sweep refused the launch");
       if (viscous_on(h)) hpbk::parabolic_phase1(h, U);          // NavierStokes2D viscous terms: generic kernels
     }
@@ -492,7 +492,7 @@ static int rhs_part_b(hpb_solver* h, const double* U, double* rhs, double* unext
 {
   if (fused_path(h)) {
     if (fused_visc(h)) {
-      if (!hpbk::hyperbolic_fused(h, U, rhs, true, true, rhs, h->d_qd4, -1, unext, adt))
+      if (!hpbk::hyperbolic_fused(h, U, rhs, true, true, rhs, h->d_qd4, -1, unext, adt, h->d_u))
         return hpb_fail(HPB_ERR_CUDA, "right-hand side: the fused sweep refused the launch");
     }
     else if (viscous_on(h)) hpbk::parabolic_phase2(h, U, rhs, /*accumulate=*/true);
@@ -1165,7 +1165,7 @@ static int dist_stage(Grp& G, int s, bool fuse = true)
       EACH(h) {
         TRY(need_device(h));
         double* rhs = h->d_Udot[s];
-        if (!hpbk::hyperbolic_fused(h, h->U_cur, rhs, true, true, rhs, fv ? h->d_qd4 : nullptr, d, unext[r_], adt[r_]))
+        if (!hpbk::hyperbolic_fused(h, h->U_cur, rhs, true, true, rhs, fv ? h->d_qd4 : nullptr, d, unext[r_], adt[r_], h->d_u))
           return hpb_fail(HPB_ERR_CUDA, "distributed step: fused sweep of direction %d refused the launch", d);
         stage_boundary_flux(h, h->U_cur, s, d);
       }

@@ -183,10 +183,11 @@ int  hyperbolic_pieces_group(hpb_solver** hs, int n, const double* const* u, dou
 int  tridiag_error(hpb_solver* h);      // 1 if a tridiagonal solve met a zero pivot since the last call (synchronises)
 // fused sweeps (sweep_fused.cu); qd != nullptr: the NavierStokes3D viscous terms are evaluated inside the sweeps
 bool fused_available(const hpb_solver* h);
-// unext != nullptr: the sweep of the last direction also writes the next RK stage solution u + adt * out there (only when
-// stage_fusion_available(h); out = the complete right-hand side: nothing may be added to it afterwards)
+// unext != nullptr: the sweep of the last direction also writes the next RK stage solution ubase + adt * out there (only
+// when stage_fusion_available(h); out = the complete right-hand side: nothing may be added to it afterwards; ubase = u^n)
 bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src,
-                      const double* qd, int only_dir = -1, double* unext = nullptr, double adt = 0.0);
+                      const double* qd, int only_dir = -1, double* unext = nullptr, double adt = 0.0,
+                      const double* ubase = nullptr);
 bool stage_fusion_available(const hpb_solver* h);
 // fused viscous path (viscous_fused.cu)
 int qderiv_fused(hpb_solver* h, const double* u, int part = 0);

@@ -79,8 +79,8 @@ bool tma_maps_for(hpb_solver* h, const SweepArgs& a, bool xs, bool grav, bool vi
   tm->qd = tm->u; tm->gf = tm->u; tm->gg = tm->u;
   if (visc && !get_map(h, a.qd, 12, 1, kind, &tm->qd)) return false;
   if (grav && (!get_map(h, a.gf, 1, 1, kind, &tm->gf) || !get_map(h, a.gg, 1, 1, kind, &tm->gg))) return false;
-  tm->un = tm->u;
-  if (a.unext != nullptr && (xs || !get_map(h, a.unext, nv, nv, kind, &tm->un))) return false;
+  tm->un = tm->u; tm->u0 = tm->u;
+  if (a.unext != nullptr && (xs || !get_map(h, a.unext, nv, nv, kind, &tm->un) || !get_map(h, a.ubase, nv, nv, kind, &tm->u0))) return false;
   return true;
 }
 
@@ -123,11 +123,11 @@ bool stage_fusion_available(const hpb_solver* h)
 }
 
 bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, bool with_source, double* src,
-                      const double* qd, int only_dir, double* unext, double adt)
+                      const double* qd, int only_dir, double* unext, double adt, const double* ubase)
 {
   if (with_source && src != nullptr && src != out) return false;     // the fused kernels accumulate the source into `out`
   const Geom& G = h->geo;
-  if (unext != nullptr && (!negate || unext == u || unext == out || !stage_fusion_available(h))) return false;
+  if (unext != nullptr && (!negate || !ubase || unext == u || unext == out || unext == ubase || !stage_fusion_available(h))) return false;
   const int wt = h->phys.no_limiting ? hpbf::WT_NOLIM : h->phys.weno;
   for (int d = 0; d < G.ndims; d++) {
     if (only_dir >= 0 && d != only_dir) continue;
@@ -139,7 +139,7 @@ bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, 
     a.with_source = (with_source && h->phys.has_grav && h->phys.grav[d] != 0.0 && src != nullptr) ? 1 : 0;
     a.qd = qd;
     a.upw = (h->cfg.upwind == HPB_UPWIND_ROE) ? 1 : 0;
-    a.unext = (d == G.ndims - 1) ? unext : nullptr; a.adt = adt;
+    a.unext = (d == G.ndims - 1) ? unext : nullptr; a.adt = adt; a.ubase = ubase;
     {
       static const int tab[3][8] = { { 0, 1, 2, 3, 4, 5, 8, 10 }, { 4, 5, 6, 7, 0, 1, 9, 10 }, { 8, 9, 10, 11, 0, 2, 5, 6 } };
       for (int k = 0; k < 8; k++) a.qidx[k] = tab[d][k];

@@ -79,7 +79,8 @@ struct SweepArgs {
   int upw;               // fluid models: 0 = Rusanov, 1 = Roe with Harten's entropy fix
   int qidx[8];           // VISC: the 8 derivative scalars the viscous flux of `dir` needs (indices dir*4+comp into qd):
                          //   dir 0: ux vx wx Tx | uy vy | uz wz   dir 1: uy vy wy Ty | ux vx | vz wz   dir 2: uz vz wz Tz | ux wx | vy wy
-  double* unext;         // last direction only (sweep_tma.cuh, RKF): where the next stage solution u + adt * out goes, or nullptr
+  double* unext;         // last direction only (sweep_tma.cuh, RKF): where the next stage solution ubase + adt * out goes, or nullptr
+  const double* ubase;   //   the solution at the start of the step (u^n; the sweep's input u is the stage solution)
   double adt;            //   a_{s+1,s} dt of the explicit RK tableau (TimeRK.c:131-141)
 };
 

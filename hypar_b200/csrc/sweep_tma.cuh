@@ -22,8 +22,9 @@
 //            registers.
 //   stage    RKF variant of the LAST direction's sweep (y in 2-D, z in 3-D): instead of adding its flux difference to the
 //            right-hand side in L2, the CTA loads the tile of the right-hand side accumulated so far into the result tile
-//            (TMA, issued as soon as the previous step's stores have read it), completes k = rhs + own part there, forms the
-//            next stage solution u + (a dt) k from the cell's record -- the two roundings of k_rk_combine -- and stores BOTH
+//            and the tile of u^n into the tile of the next stage solution (TMA, issued as soon as the previous step's stores
+//            have read them), completes k = rhs + own part in place, forms the next stage solution u^n + (a dt) k in place
+//            beside it -- the two roundings of k_rk_combine -- and stores BOTH
 //            tiles with plain cp.async.bulk.tensor stores: the stage-vector pass over memory (TimeRK.c:131-141) disappears
 //            under a kernel that is bound by the FP64 pipe. Cells of the tile outside the interior are written back
 //            unchanged (k) or as zero (next stage solution: ghost lines / ghost cells, filled by the boundary conditions
@@ -57,7 +58,7 @@ namespace hpbf {
 
 struct TmaMaps {
   CUtensorMap u, qd, out, gf, gg;
-  CUtensorMap un;          // RKF: the next stage solution
+  CUtensorMap un, u0;      // RKF: the next stage solution; the solution u^n at the start of the step
 };
 // host (sweep_fused.cu): descriptors for the arrays of one launch; false when the TMA path does not apply
 // (driver entry point missing, odd padded row length, misaligned array)
@@ -245,11 +246,13 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
 
   auto issue_rin = [&](int m) {
     // RKF, executed by ONE thread: the right-hand side accumulated by the earlier directions on the cells step m writes
-    mbar_expect_tx(rin_bar, (unsigned)(NV * TILE * sizeof(double)));
+    // and u^n there (the stage solution in the records is U_s, not u^n, from the second stage on)
+    mbar_expect_tx(rin_bar, (unsigned)(2 * NV * TILE * sizeof(double)));
     const int cd = TL * m + G.g;
     int c0 = tc0, c1t = tc1, c2t = tc2;
     if (dir == 1) c1t = cd; else c2t = cd;
     tma_load4(ost, &tm.out, rin_bar, c0, c1t, c2t, 0);
+    tma_load4(ust, &tm.u0, rin_bar, c0, c1t, c2t, 0);
   };
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();      // the swizzled tiles assume the declared alignment
@@ -633,15 +636,15 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
         }
       } else {
         if (RKF) {
-          // the tile holds the right-hand side of the earlier directions (and the stores of step m-1 have read it):
-          // complete k in place, next stage solution beside it -- k_rk_combine's two roundings, no contraction
+          // the tiles hold the right-hand side of the earlier directions and u^n (and the stores of step m-1 have read
+          // them): complete k in place, next stage solution in place beside it -- k_rk_combine's two roundings, no contraction
           mbar_wait(rin_bar, (unsigned)m & 1u);
-          const int co = cc - 1;
 #pragma unroll
           for (int v = 0; v < NV; v++) {
             const double kf = __dadd_rn(ost[v * TILE + sidx], res[v]);
             ost[v * TILE + sidx] = kf;
-            ust[v * TILE + sidx] = out_ok ? __dadd_rn(rec[(LY::rU + v) * NREC + co], __dmul_rn(a.adt, kf)) : 0.0;
+            const double un = ust[v * TILE + sidx];
+            ust[v * TILE + sidx] = out_ok ? __dadd_rn(un, __dmul_rn(a.adt, kf)) : 0.0;
           }
         } else {
           if (m >= 1) mbar_wait(free_bar, (unsigned)(m - 1) & 1u);     // the reduce of step m-1 has read the tile

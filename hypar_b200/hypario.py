@@ -446,10 +446,14 @@ def _pack_block(x_local: Sequence[np.ndarray], u_local: np.ndarray) -> np.ndarra
 
 
 def write_parallel_block(root_ext: str, rank: int, dim_global, iproc, nvars: int, n_io: int,
-                         x_local: Sequence[np.ndarray], u_local: np.ndarray, record: int = 0) -> str:
+                         x_local: Sequence[np.ndarray], u_local: np.ndarray, record: int = 0, truncate: bool = False) -> str:
     """This rank's block of <root_ext>.<nnnn> (root_ext = "op.bin": WriteArrayParallel's filename_root).
     record = how many output times are already in the file (op_overwrite = no appends; yes -> always 0).
-    u_local: (N_{nd-1},...,N_0,nvars), no ghosts. Returns the file name."""
+    u_local: (N_{nd-1},...,N_0,nvars), no ghosts. Returns the file name.
+    truncate: cut the file at the end of this record. WriteArrayParallel opens the file "wb" on the first write of a run
+    (and on every write with op_overwrite yes), so a longer file left by an earlier run loses its trailing records; here
+    every rank writes on its own, so the caller asks for the cut -- and may only do so when no rank starts record r+1
+    before all have finished record r (a barrier between output times), else a faster rank's next record would be cut."""
     nproc = int(np.prod(iproc))
     g, first, last = io_group(nproc, n_io, rank)
     fname = f"{root_ext}.{g:04d}"
@@ -462,6 +466,9 @@ def write_parallel_block(root_ext: str, rank: int, dim_global, iproc, nvars: int
         mv, done = memoryview(buf).cast("B"), 0
         while done < len(mv):                        # pwrite may be partial beyond 2 GiB
             done += os.pwrite(fd, mv[done:done + (1 << 30)], off + done)
+        end = 8 * (record + 1) * group_total
+        if truncate and os.fstat(fd).st_size > end:       # shrinks only: nothing of this or an earlier record lies beyond
+            os.ftruncate(fd, end)
     finally:
         os.close(fd)
     return fname

@@ -466,11 +466,12 @@ class Solver:
             off += n + 2 * g
         return out
 
-    def write_solution_parallel(self, root_ext: str = "op.bin", n_io: int = 1, record: int = 0) -> str:
-        """WriteArrayParallel (WriteArray.c:139-323): the device solution of this rank into <root_ext>.<nnnn>"""
+    def write_solution_parallel(self, root_ext: str = "op.bin", n_io: int = 1, record: int = 0, truncate: bool = False) -> str:
+        """WriteArrayParallel (WriteArray.c:139-323): the device solution of this rank into <root_ext>.<nnnn>
+        (truncate: see hypario.write_parallel_block -- only with a barrier between output times)"""
         u = np.ascontiguousarray(self.interior(self.get_solution()))
         return hypario.write_parallel_block(root_ext, self.rank, self.dim_global, self.iproc, self.nvars, n_io,
-                                            self.local_grid(), u, record)
+                                            self.local_grid(), u, record, truncate)
 
     def load_solution_parallel(self, fname_root: str = "initial", n_io: int = 1, mode: str = "parallel") -> None:
         """ReadArrayParallel / ReadArrayMPI_IO (ReadArray.c:293-650): this rank's block of <fname_root>_par.inp.<nnnn>

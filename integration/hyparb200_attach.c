@@ -366,7 +366,10 @@ static int attach_one(SimulationObject *sim, int n, int nsims)
   if (c.upwind < 0) { fprintf(stderr, "hyparb200_attach: upwinding scheme is not on the B200 path (roe, rusanov, rf-char, llf-char)\n"); return 1; }
 
   DomainBoundary *b = (DomainBoundary*) s->boundary;
-  if (s->nBoundaryZones > HPB_MAX_ZONES) return 1;
+  if (s->nBoundaryZones > HPB_MAX_ZONES) {
+    fprintf(stderr, "hyparb200_attach: %d boundary zones (at most %d)\n", s->nBoundaryZones, HPB_MAX_ZONES);
+    return 1;
+  }
   c.nzones = s->nBoundaryZones;
   for (int n = 0; n < c.nzones; n++) {
     c.zones[n].type = bc_type(b[n].bctype);

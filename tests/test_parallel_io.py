@@ -103,6 +103,28 @@ def test_concurrent_rank_writers(tmp_path):
         assert np.array_equal(np.fromfile(f"op.bin.{g:04d}"), np.concatenate(want))
 
 
+def test_stale_records_of_an_earlier_run_are_cut(tmp_path):
+    """WriteArrayParallel opens "wb" on the first write of a run: a longer file from an earlier run must not keep its
+    trailing records (stitching tools read to EOF). The rank-parallel writer cuts at the end of the record on request."""
+    os.chdir(tmp_path)
+    dg, ip, nv = [12, 10], [2, 1], 3
+    x, u = _field(dg, nv)
+    for rec in range(3):                                   # an earlier run: three output times
+        for r in range(2):
+            xl, ul = _block(x, u, dg, ip, r)
+            H.write_parallel_block("op.bin", r, dg, ip, nv, 1, xl, ul + rec, record=rec)
+    long_size = os.path.getsize("op.bin.0000")
+    for r in range(2):                                     # this run: one output time
+        xl, ul = _block(x, u, dg, ip, r)
+        H.write_parallel_block("op.bin", r, dg, ip, nv, 1, xl, ul + 7, record=0, truncate=True)
+    assert os.path.getsize("op.bin.0000") * 3 == long_size
+    want = []
+    for r in range(2):
+        xl, ul = _block(x, u, dg, ip, r)
+        want.append(np.concatenate([np.concatenate(xl), (ul + 7).reshape(-1)]))
+    assert np.array_equal(np.fromfile("op.bin.0000"), np.concatenate(want))
+
+
 @pytest.mark.parametrize("mode", ["parallel 1", "mpi-io 1"])
 def test_formats_against_the_reference_live(tmp_path, mode):
     """the unmodified reference (1-rank MPI-semantics build) reads the partitioned input we split and writes

@@ -34,8 +34,13 @@ def single(case, mode, steps=1):
     sv.TimeSteps(steps)
     u = sv.get_solution()
     assert np.isfinite(u).all()
-    print(f"{case.name:40s} use_fused={mode}: rhs err/terms {err:.2e}, {sv.kernel_launches} launches ({sv.tma_launches} TMA sweeps)", flush=True)
-    assert err <= (0.0 if mode == 0 else 1e-9)
+    ur = S.local_u0()
+    for _ in range(steps):
+        O.time_step(ur, float(case.solver["dt"]), hpo.rk_type_of(case))
+    e2 = np.abs(S.interior(u) - S.interior(ur)).max() / np.abs(S.interior(ur)).max()
+    print(f"{case.name:40s} use_fused={mode}: rhs err/terms {err:.2e}, {steps} step(s) rel err {e2:.2e}, {sv.kernel_launches} launches "
+          f"({sv.tma_launches} TMA sweeps, stage fusion {'on' if sv.stage_fusion_active else 'off'})", flush=True)
+    assert err <= (0.0 if mode == 0 else 1e-9) and e2 <= (0.0 if mode == 0 else 1e-11)
     sv.close()
 
 
@@ -59,7 +64,10 @@ err = max(np.abs(a - b).max() for a, b in zip(rhs, rhs_ref)) / max(np.abs(b).max
 LR.time_step(1)
 u = LR.get_solution()
 assert all(np.isfinite(x).all() for x in u)
-print(f"decomposed 2x2x2, overlapped schedule: rhs rel err {err:.2e}", flush=True)
-assert err <= 1e-11
+ur = MO.local_u0()
+MO.time_step(ur, float(case.solver["dt"]), hpo.rk_type_of(case))
+e2 = max(np.abs(MO.S[r].interior(u[r]) - MO.S[r].interior(ur[r])).max() for r in range(MO.nranks))
+print(f"decomposed 2x2x2, overlapped schedule: rhs rel err {err:.2e}, one step abs err {e2:.2e}", flush=True)
+assert err <= 1e-11 and e2 <= 1e-11
 LR.close()
 print("SANITIZE CASES OK", flush=True)
