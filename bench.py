@@ -40,7 +40,10 @@ NSTAGES = 4
 # algorithmic bytes per point (FP64, nvars = 5), DESIGN.md section "Roofline":
 #   one directional sweep launch: read u (40 B) + read-modify-write rhs (80 B; the first direction only writes: 40 B)
 #   whole RK stage (k never stored twice): 200 B  
-SWEEP_BYTES = {"sweep_x": 80.0, "sweep_y": 120.0, "sweep_z": 120.0}
+# "sweep_fused": the last direction's sweep that also forms the next RK stage solution (stage fusion): read the
+# stage solution (40) + read-modify-write of the right-hand side (80) + read u^n (40) + write the next stage solution (40) -- the
+# whole-stage figure of SURVEY 8(d)
+SWEEP_BYTES = {"sweep_x": 80.0, "sweep_y": 120.0, "sweep_z": 120.0, "sweep_fused": 200.0}
 STAGE_BYTES = 200.0
 
 
@@ -544,7 +547,8 @@ def gpu_arm(args):
             "peak_source": "hpb_fp64_issue_peak: DMUL chains, 8 CTAs x 256 threads per SM, measured in this run"}),
         "note": "FP64-issue-bound kernel (DESIGN.md): the HBM fraction is reported as the metric demands; the FP64 pipe "
                 "is the binding unit (fp64_pipe_active_pct_ncu); traffic exceeds the algorithmic bytes by the 8 "
-                "derivative scalars (64 B/point) the viscous flux reads",
+                "derivative scalars (64 B/point) the viscous flux reads. sweep_fused = the last direction's sweep that also "
+                "forms the next RK stage solution: 200 B/point, the whole-stage figure of SURVEY 8(d)",
     }
 
     # ---- CPU baseline: the reference itself on a bounded sample
@@ -589,6 +593,8 @@ def gpu_arm(args):
                        "in-library ncclSend/ncclRecv on a communication stream, overlapped: u faces under the full-array RK "
                        "update, Q-derivative faces of dims 1.. under the x-sweep (hpb_TimeStepsDistributed, no Python in the step)"
                        if stepper.overlap else "in-library ncclSend/ncclRecv, serial (hpb_TimeStepsDistributed)")),
+                   "stage_fusion": ("the last sweep of an RK stage also writes the next stage solution (bit-identical to the unfused "
+                                    "schedule; HPB_STAGE_FUSION=0 turns it off)" if sv.stage_fusion_active else "off"),
                    "l2": "working set (5.6 GB per array) >> L2, no flush needed",
                    "host_numa_bind": (f"{len(numa_cpus)} GPU-local CPUs" if numa_cpus else "none")},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,

@@ -145,7 +145,7 @@ bool hyperbolic_fused(hpb_solver* h, const double* u, double* out, bool negate, 
       for (int k = 0; k < 8; k++) a.qidx[k] = tab[d][k];
     }
     a.nlines = (d == 0 ? G.N[1] * G.N[2] : d == 1 ? G.N[0] * G.N[2] : G.N[0] * G.N[1]);
-    ProfScope ps(h, HPB_PROF_SWEEP_X + d);
+    ProfScope ps(h, a.unext ? HPB_PROF_SWEEP_FUSED : HPB_PROF_SWEEP_X + d);
     bool ok;
     switch (wt) {
       case HPB_WENO_JS: ok = hpbf::launch_sweep<HPB_WENO_JS>(h, a); break;

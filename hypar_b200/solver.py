@@ -577,7 +577,7 @@ class Solver:
     def time(self) -> float:
         return float(self.L.hpb_current_time(self.h))
 
-    PROF = {"sweep_x": 0, "sweep_y": 1, "sweep_z": 2, "viscous": 3, "rk": 4, "bc": 5, "halo": 6, "other": 7}
+    PROF = {"sweep_x": 0, "sweep_y": 1, "sweep_z": 2, "viscous": 3, "rk": 4, "bc": 5, "halo": 6, "other": 7, "sweep_fused": 8}
 
     def fp64_issue_peak(self) -> float:
         """FP64 thread-instructions per second this device issues at most (measured live)"""

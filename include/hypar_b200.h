@@ -406,7 +406,8 @@ long long hpb_tma_launch_count(const hpb_solver* h);      /* of those, launches 
 #define HPB_PROF_BC       5   /* boundary-condition kernels */
 #define HPB_PROF_HALO     6   /* pack / unpack kernels */
 #define HPB_PROF_OTHER    7
-#define HPB_PROF_NCAT     8
+#define HPB_PROF_SWEEP_FUSED 8   /* the last direction's sweep when it also writes the next RK stage solution (stage fusion) */
+#define HPB_PROF_NCAT     9
 /* FP64 issue peak of the solver's device in thread-instructions per second, measured live (the denominator of the FP64
    roofline of the sweeps: bench.py roofline.fp64) */
 int hpb_fp64_issue_peak(hpb_solver* h, double* thread_instr_per_s);
