@@ -290,6 +290,9 @@ extern "C" int hpb_destroy(hpb_solver* h)
   for (int i = 0; i < 2; i++) if (h->d_cell[i]) cudaFree(h->d_cell[i]);
   for (int i = 0; i < 3; i++) if (h->d_tri[i]) cudaFree(h->d_tri[i]);
   if (h->d_err) cudaFree(h->d_err);
+  if (h->d_mr) cudaFree(h->d_mr);
+  if (h->d_bmr) cudaFree(h->d_bmr);
+  if (h->h_mr) cudaFreeHost(h->h_mr);
   if (h->d_bx) cudaFree(h->d_bx);
   if (h->d_advf) cudaFree(h->d_advf);
   if (h->d_pipe_in) cudaFree(h->d_pipe_in);

@@ -101,11 +101,6 @@ int hpb_setup_host(hpb_solver* h)
                     c.hyp_scheme);
   if (c.muscl_limiter < HPB_LIMITER_GMM || c.muscl_limiter > HPB_LIMITER_SUPERBEE)
     return hpb_fail(HPB_ERR_INVALID, "muscl limiter %d not supported (gmm, minmod, vanleer, superbee)", c.muscl_limiter);
-  if (hpb_scheme_is_compact(c.hyp_scheme) && c.interp_char && c.nvars > 1)
-    for (int d = 0; d < nd; d++)
-      if (c.iproc[d] != 1)     // blocktridiagLU.c stages 2-3 (block reduced system across ranks) are not built
-        return hpb_fail(HPB_ERR_INVALID, "characteristic compact schemes (crweno5, hcweno5, cupw5) need iproc = 1 along every dimension "
-                                         "(component-wise ones run decomposed)");
   if (hpb_scheme_is_compact(c.hyp_scheme))
     for (int d = 0; d < nd; d++)
       if (c.iproc[d] > 64) return hpb_fail(HPB_ERR_INVALID, "compact schemes: at most 64 ranks along one dimension");

@@ -108,6 +108,7 @@ struct hpb_solver {
   double *d_tri[3] = {nullptr, nullptr, nullptr};
   double *d_bx = nullptr;          // characteristic compact schemes: right-hand side / solution of the block systems
   double *d_mr = nullptr;          // compact schemes across ranks (compact_mr.cu): exchange rows, Jacobi scratch; 16 x systems
+  double *d_bmr = nullptr;         // the same for the block systems of the characteristic compact schemes
   double *h_mr = nullptr;          // pinned: norms of the reduced-system iteration
   int *d_err = nullptr;
   // pipelined host-array stepping (hpb_pipe_*): copy streams, AoS staging of the incoming / outgoing field, events

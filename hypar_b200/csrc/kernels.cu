@@ -1494,6 +1494,220 @@ __global__ void k_block_tridiag(Geom G, int dir, double* __restrict__ A, double*
     for (int v = 0; v < N; v++) fI[v * ni + qbase + i * qs] = X[((long long)i * N + v) * Nsys + sys];
 }
 
+// ------------------------------------------------------------------------------------------
+// The block systems of the characteristic compact schemes when the grid line is split among ranks:
+// TridiagLU/blocktridiagLU.c:103-320 with all four stages, the reduced system (one block row per rank) solved by
+// TridiagLU/blocktridiagIterJacobi.c:92-297 as the reference does by default, and the hand-over of the shared interface
+// (Interp1PrimFifthOrderCRWENOChar.c:246-263). One thread per grid line, block / vector storage of k_compact_rows_char,
+// `n` = rows on this rank, `first` = first rank of the line. Exchange buffers: element e of block k of system sys at
+// [(k*N*N + e)*Nsys + sys] (k = a, b, c of the last row), the vector after them at [(3*N*N + v)*Nsys + sys]; reduced-system
+// vectors at [v*Nsys + sys]. Operation order follows the reference macro by macro (compiled without FMA contraction).
+template <int N> __device__ __forceinline__ void bt_vload(const double* __restrict__ X, long long row, long long Nsys, long long sys, double* x)
+{
+  for (int v = 0; v < N; v++) x[v] = X[(row * N + v) * Nsys + sys];
+}
+template <int N> __device__ __forceinline__ void bt_vstore(double* __restrict__ X, long long row, long long Nsys, long long sys, const double* x)
+{
+  for (int v = 0; v < N; v++) X[(row * N + v) * Nsys + sys] = x[v];
+}
+template <int N> __device__ __forceinline__ void bt_matvec(const double* A, const double* x, double* y)     // _MatVecMultiply_
+{
+  for (int i = 0; i < N; i++) { double s = 0; for (int j = 0; j < N; j++) s += (A[i * N + j] * x[j]); y[i] = s; }
+}
+__device__ __forceinline__ bool bmr_sys(const Geom& G, int dir, long long& Nsys, long long& sys, long long& qbase, long long& qs, long long& ni)
+{
+  const int M0 = G.N[0] + (dir == 0), M1 = G.N[1] + (dir == 1), M2 = G.N[2] + (dir == 2);
+  ni = (long long)M0 * M1 * M2;
+  int T0, T1; long long s0, s1;
+  if (dir == 0)      { T0 = M1; T1 = M2; s0 = M0;  s1 = (long long)M0 * M1; qs = 1; }
+  else if (dir == 1) { T0 = M0; T1 = M2; s0 = 1;   s1 = (long long)M0 * M1; qs = M0; }
+  else               { T0 = M0; T1 = M1; s0 = 1;   s1 = M0;                 qs = (long long)M0 * M1; }
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y;
+  Nsys = (long long)T0 * T1;
+  if (t0 >= T0 || t1 >= T1) return false;
+  sys = t0 + (long long)T0 * t1;
+  qbase = t0 * s0 + t1 * s1;
+  return true;
+}
+
+// stage 1 (blocktridiagLU.c:150-171) + the last row packed for the next rank (:181-190)
+template <int MODEL>
+__global__ void k_bmr_stage1(Geom G, int dir, int n, int first, double* __restrict__ A, double* __restrict__ B, double* __restrict__ Cc,
+                             double* __restrict__ X, double* __restrict__ sendrow)
+{
+  constexpr int N = ModelTraits<MODEL>::NV;
+  long long Nsys, sys, qbase, qs, ni;
+  if (!bmr_sys(G, dir, Nsys, sys, qbase, qs, ni)) return;
+  double binv[N * N], factor[N * N], am[N * N], bm[N * N], cm[N * N], a[N * N], b[N * N], xm[N], x[N];
+  for (int i = (first ? 1 : 2); i < n; i++) {
+    bt_load<N>(B, i - 1, Nsys, sys, bm); bt_load<N>(Cc, i - 1, Nsys, sys, cm); bt_load<N>(A, i - 1, Nsys, sys, am);
+    bt_vload<N>(X, i - 1, Nsys, sys, xm);
+    bt_load<N>(A, i, Nsys, sys, a); bt_load<N>(B, i, Nsys, sys, b); bt_vload<N>(X, i, Nsys, sys, x);
+    bt_invert<N>(bm, binv);
+    bt_mul<N>(a, binv, factor);
+    bt_mul_sub<N>(b, factor, cm);
+    for (int e = 0; e < N * N; e++) a[e] = 0.0;
+    bt_mul_sub<N>(a, factor, am);
+    bt_matvec_sub<N>(x, factor, xm);
+    bt_store<N>(A, i, Nsys, sys, a); bt_store<N>(B, i, Nsys, sys, b); bt_vstore<N>(X, i, Nsys, sys, x);
+    if (!first) {                    // the same elimination into row 0 (:163-169)
+      double c0[N * N], b0[N * N], x0[N];
+      bt_load<N>(Cc, 0, Nsys, sys, c0); bt_load<N>(B, 0, Nsys, sys, b0); bt_vload<N>(X, 0, Nsys, sys, x0);
+      bt_mul<N>(c0, binv, factor);
+      for (int e = 0; e < N * N; e++) c0[e] = 0.0;
+      bt_mul_sub<N>(c0, factor, cm);
+      bt_mul_sub<N>(b0, factor, am);
+      bt_matvec_sub<N>(x0, factor, xm);
+      bt_store<N>(Cc, 0, Nsys, sys, c0); bt_store<N>(B, 0, Nsys, sys, b0); bt_vstore<N>(X, 0, Nsys, sys, x0);
+    }
+  }
+  bt_load<N>(A, n - 1, Nsys, sys, a); bt_store<N>(sendrow, 0, Nsys, sys, a);
+  bt_load<N>(B, n - 1, Nsys, sys, a); bt_store<N>(sendrow, 1, Nsys, sys, a);
+  bt_load<N>(Cc, n - 1, Nsys, sys, a); bt_store<N>(sendrow, 2, Nsys, sys, a);
+  bt_vload<N>(X, n - 1, Nsys, sys, x);
+  for (int v = 0; v < N; v++) sendrow[(3LL * N * N + v) * Nsys + sys] = x[v];
+}
+
+// stage 2 (blocktridiagLU.c:199-222), ranks other than the first; then the start of the Jacobi iteration on the reduced
+// block row (blocktridiagIterJacobi.c:116-126: rhs saved, initial guess x = b^-1 rhs). The first rank enters the reduced
+// system with (0, I, 0 | 0) (blocktridiagLU.c:247). red = [rhs | x | sent x | recvL | recvR | xp1], N*Nsys each
+template <int MODEL>
+__global__ void k_bmr_stage2(Geom G, int dir, int n, int first, double* __restrict__ A, double* __restrict__ B, double* __restrict__ Cc,
+                             double* __restrict__ X, const double* __restrict__ recvrow, double* __restrict__ red)
+{
+  constexpr int N = ModelTraits<MODEL>::NV;
+  long long Nsys, sys, qbase, qs, ni;
+  if (!bmr_sys(G, dir, Nsys, sys, qbase, qs, ni)) return;
+  const long long NS = (long long)N * Nsys;
+  if (first) {
+    for (int v = 0; v < N; v++) { red[0 * NS + v * Nsys + sys] = 0.0; red[1 * NS + v * Nsys + sys] = 0.0; red[2 * NS + v * Nsys + sys] = 0.0; }
+    return;
+  }
+  double am1[N * N], bm1[N * N], cm1[N * N], xm1[N], binv[N * N], factor[N * N], a0[N * N], b0[N * N], c0[N * N], x0[N];
+  bt_load<N>(recvrow, 0, Nsys, sys, am1); bt_load<N>(recvrow, 1, Nsys, sys, bm1); bt_load<N>(recvrow, 2, Nsys, sys, cm1);
+  for (int v = 0; v < N; v++) xm1[v] = recvrow[(3LL * N * N + v) * Nsys + sys];
+  bt_load<N>(A, 0, Nsys, sys, a0); bt_load<N>(B, 0, Nsys, sys, b0); bt_load<N>(Cc, 0, Nsys, sys, c0); bt_vload<N>(X, 0, Nsys, sys, x0);
+  bt_invert<N>(bm1, binv);
+  bt_mul<N>(a0, binv, factor);
+  bt_mul_sub<N>(b0, factor, cm1);
+  for (int e = 0; e < N * N; e++) a0[e] = 0.0;
+  bt_mul_sub<N>(a0, factor, am1);
+  bt_matvec_sub<N>(x0, factor, xm1);
+  double al[N * N], bl[N * N], cl[N * N], xl[N];
+  bt_load<N>(A, n - 1, Nsys, sys, al); bt_load<N>(B, n - 1, Nsys, sys, bl); bt_load<N>(Cc, n - 1, Nsys, sys, cl); bt_vload<N>(X, n - 1, Nsys, sys, xl);
+  bt_invert<N>(bl, binv);
+  bt_mul<N>(c0, binv, factor);
+  bt_mul_sub<N>(b0, factor, al);
+  for (int e = 0; e < N * N; e++) c0[e] = 0.0;
+  bt_mul_sub<N>(c0, factor, cl);
+  bt_matvec_sub<N>(x0, factor, xl);
+  bt_store<N>(A, 0, Nsys, sys, a0); bt_store<N>(B, 0, Nsys, sys, b0); bt_store<N>(Cc, 0, Nsys, sys, c0);
+  // Jacobi: rhs = x0, x = b0^-1 rhs
+  double xg[N];
+  bt_invert<N>(b0, binv);
+  bt_matvec<N>(binv, x0, xg);
+  bt_vstore<N>(X, 0, Nsys, sys, xg);
+  for (int v = 0; v < N; v++) { red[0 * NS + v * Nsys + sys] = x0[v]; red[1 * NS + v * Nsys + sys] = xg[v]; red[2 * NS + v * Nsys + sys] = xg[v]; }
+}
+
+// one Jacobi iteration on the reduced block row (blocktridiagIterJacobi.c:205-216 norm, :276-283 update), n = 1 per rank
+template <int MODEL>
+__global__ void k_bmr_jacobi(Geom G, int dir, int first, int pass, const double* __restrict__ A, const double* __restrict__ B,
+                             const double* __restrict__ Cc, double* __restrict__ X, double* __restrict__ red, double* __restrict__ part)
+{
+  constexpr int N = ModelTraits<MODEL>::NV;
+  long long Nsys, sys, qbase, qs, ni;
+  double contrib = 0.0;
+  if (bmr_sys(G, dir, Nsys, sys, qbase, qs, ni) && !first) {
+    const long long NS = (long long)N * Nsys;
+    double a[N * N], b[N * N], c[N * N], rhs[N], x[N], rl[N], rr[N];
+    bt_load<N>(A, 0, Nsys, sys, a); bt_load<N>(B, 0, Nsys, sys, b); bt_load<N>(Cc, 0, Nsys, sys, c);
+    for (int v = 0; v < N; v++) {
+      rhs[v] = red[0 * NS + v * Nsys + sys]; x[v] = red[1 * NS + v * Nsys + sys];
+      rl[v] = red[3 * NS + v * Nsys + sys]; rr[v] = red[4 * NS + v * Nsys + sys];
+    }
+    if (pass == 0) {
+      double err[N];
+      for (int v = 0; v < N; v++) err[v] = rhs[v];
+      bt_matvec_sub<N>(err, a, rl);
+      bt_matvec_sub<N>(err, b, x);
+      bt_matvec_sub<N>(err, c, rr);
+      for (int v = 0; v < N; v++) contrib += (err[v] * err[v]);
+    } else {
+      double xt[N], binv[N * N], xn[N];
+      for (int v = 0; v < N; v++) xt[v] = rhs[v];
+      bt_matvec_sub<N>(xt, a, rl);
+      bt_matvec_sub<N>(xt, c, rr);
+      bt_invert<N>(b, binv);
+      bt_matvec<N>(binv, xt, xn);
+      bt_vstore<N>(X, 0, Nsys, sys, xn);
+      for (int v = 0; v < N; v++) { red[1 * NS + v * Nsys + sys] = xn[v]; red[2 * NS + v * Nsys + sys] = xn[v]; }
+    }
+  }
+  if (pass == 0) {
+    const double v = block_reduce(contrib, false);
+    if (threadIdx.x == 0) part[blockIdx.x + (long long)gridDim.x * blockIdx.y] = v;
+  }
+}
+
+// what each rank sends to the previous one after the reduced solve: its row-0 x (blocktridiagLU.c:262: the first rank's is
+// its own row 0 as stage 1 left it -- its Jacobi ran on a private (0, I, 0 | 0))
+template <int MODEL>
+__global__ void k_bmr_row0(Geom G, int dir, const double* __restrict__ X, double* __restrict__ out)
+{
+  constexpr int N = ModelTraits<MODEL>::NV;
+  long long Nsys, sys, qbase, qs, ni;
+  if (!bmr_sys(G, dir, Nsys, sys, qbase, qs, ni)) return;
+  for (int v = 0; v < N; v++) out[v * Nsys + sys] = X[((long long)0 * N + v) * Nsys + sys];
+}
+
+// stage 4 (blocktridiagLU.c:281-301): xp1 = the next rank's row-0 x (0 on the last rank); the solution goes to the interface
+// array; row 0 packed for the previous rank (the shared interface, Interp1PrimFifthOrderCRWENOChar.c:254)
+template <int MODEL>
+__global__ void k_bmr_stage4(Geom G, int dir, int n, int first, const double* __restrict__ A, const double* __restrict__ B,
+                             const double* __restrict__ Cc, double* __restrict__ X, const double* __restrict__ xp1,
+                             double* __restrict__ sendfirst, double* __restrict__ fI)
+{
+  constexpr int N = ModelTraits<MODEL>::NV;
+  long long Nsys, sys, qbase, qs, ni;
+  if (!bmr_sys(G, dir, Nsys, sys, qbase, qs, ni)) return;
+  double a[N * N], b[N * N], c[N * N], binv[N * N], x[N], x0[N], xn[N], xt[N];
+  bt_vload<N>(X, 0, Nsys, sys, x0);
+  for (int v = 0; v < N; v++) xn[v] = xp1[v * Nsys + sys];
+  {
+    const int i = n - 1;
+    bt_load<N>(A, i, Nsys, sys, a); bt_load<N>(B, i, Nsys, sys, b); bt_load<N>(Cc, i, Nsys, sys, c); bt_vload<N>(X, i, Nsys, sys, x);
+    bt_invert<N>(b, binv);
+    bt_matvec_sub<N>(x, a, x0);
+    bt_matvec_sub<N>(x, c, xn);
+    bt_matvec<N>(binv, x, xt);
+    bt_vstore<N>(X, i, Nsys, sys, xt);
+    for (int v = 0; v < N; v++) xn[v] = xt[v];
+  }
+  for (int i = n - 2; i > (first ? 0 : 1) - 1; i--) {
+    bt_load<N>(A, i, Nsys, sys, a); bt_load<N>(B, i, Nsys, sys, b); bt_load<N>(Cc, i, Nsys, sys, c); bt_vload<N>(X, i, Nsys, sys, x);
+    bt_invert<N>(b, binv);
+    bt_matvec_sub<N>(x, c, xn);
+    if (i > 0) bt_matvec_sub<N>(x, a, x0);
+    else       bt_matvec_sub<N>(x, a, x);           // row 0 of the first rank: the reference's x + d*bs IS this row
+    bt_matvec<N>(binv, x, xt);
+    bt_vstore<N>(X, i, Nsys, sys, xt);
+    for (int v = 0; v < N; v++) xn[v] = xt[v];
+  }
+  for (int i = 0; i < n; i++)
+    for (int v = 0; v < N; v++) fI[v * ni + qbase + i * qs] = X[((long long)i * N + v) * Nsys + sys];
+  for (int v = 0; v < N; v++) sendfirst[v * Nsys + sys] = X[((long long)0 * N + v) * Nsys + sys];
+}
+// the solution of the shared interface N arrives from the next rank (Interp1PrimFifthOrderCRWENOChar.c:262)
+template <int MODEL>
+__global__ void k_bmr_put_last(Geom G, int dir, double* __restrict__ fI, const double* __restrict__ recvfirst)
+{
+  constexpr int N = ModelTraits<MODEL>::NV;
+  long long Nsys, sys, qbase, qs, ni;
+  if (!bmr_sys(G, dir, Nsys, sys, qbase, qs, ni)) return;
+  for (int v = 0; v < N; v++) fI[v * ni + qbase + (long long)G.N[dir] * qs] = recvfirst[v * Nsys + sys];
+}
+
 // the linear schemes, component-wise: Interp1PrimFifthOrderUpwind.c:60-147, Interp1PrimFirstOrderUpwind.c:78-84,
 // Interp1PrimSecondOrderCentral.c:80-88, Interp1PrimFourthOrderCentral.c:96-120
 // ... and the MUSCL schemes: Interp1PrimSecondOrderMUSCL.c:118-156 (limiters of src/LimiterFunctions/),
@@ -1935,13 +2149,121 @@ static int compact_solve_group(hpb_solver** hs, int n, int dir, double* const* X
   return HPB_OK;
 }
 
+// the same for the block systems of the characteristic compact schemes (blocktridiagLU.c with the block Jacobi reduced
+// solve): rows in d_tri[0..2], right-hand side / solution in d_bx, result into the interface arrays fI[r]
+static int block_compact_solve_group(hpb_solver** hs, int n, int dir, double* const* fI)
+{
+  const int tpb = 64;
+  const double atol = 1e-12, rtol = 1e-10;      // tridiagLUInit.c:70-76 (lusolver.inp is not read: defaults)
+  const int maxiter = 10;
+  std::vector<double*> sendrow(n), recvrow(n), red(n), red_sx(n), red_rl(n), red_rr(n), xp1(n), xs1(n), sfirst(n), rfirst(n), dnorm(n), dgath(n);
+  std::vector<int> active(n, 1), first(n), last(n), rows(n);
+  std::vector<dim3> grid(n);
+  std::vector<long long> nline(n), nrow(n), nvec(n);
+  for (int r = 0; r < n; r++) {
+    hpb_solver* h = hs[r];
+    const Geom& G = h->geo;
+    const int N = G.nvars;
+    long long m = 0;
+    for (int d = 0; d < G.ndims; d++) { const long long k = mr_nsys(h, d) / N; if (k > m) m = k; }
+    const long long per = 2LL * (3 * N * N + N) + 9LL * N;       // send row, receive row, 6 reduced vectors, xs1, first-row send / receive
+    if (!h->d_bmr) {
+      cudaSetDevice(h->device);
+      const size_t bytes = (size_t)(per * m + 8192) * sizeof(double);
+      if (cudaMalloc((void**)&h->d_bmr, bytes) != cudaSuccess) return hpb_fail(HPB_ERR_ALLOC, "characteristic compact schemes across ranks: scratch allocation failed");
+      cudaMemset(h->d_bmr, 0, bytes);
+      cudaStreamSynchronize(cudaStreamLegacy);
+      if (!h->h_mr && cudaMallocHost((void**)&h->h_mr, 128 * sizeof(double)) != cudaSuccess) return hpb_fail(HPB_ERR_ALLOC, "pinned alloc");
+    }
+    const int M[3] = { G.N[0] + (dir == 0), G.N[1] + (dir == 1), G.N[2] + (dir == 2) };
+    int T0, T1;
+    if (dir == 0) { T0 = M[1]; T1 = M[2]; } else if (dir == 1) { T0 = M[0]; T1 = M[2]; } else { T0 = M[0]; T1 = M[1]; }
+    grid[r] = dim3((T0 + tpb - 1) / tpb, T1, 1);
+    nline[r] = (long long)T0 * T1; nrow[r] = (3LL * N * N + N) * nline[r]; nvec[r] = (long long)N * nline[r];
+    first[r] = G.lo_phys[dir]; last[r] = G.hi_phys[dir];
+    rows[r] = G.N[dir] + (last[r] ? 1 : 0);
+    double* p = h->d_bmr;
+    sendrow[r] = p; p += nrow[r]; recvrow[r] = p; p += nrow[r];
+    red[r] = p; red_sx[r] = p + 2 * nvec[r]; red_rl[r] = p + 3 * nvec[r]; red_rr[r] = p + 4 * nvec[r]; xp1[r] = p + 5 * nvec[r]; p += 6 * nvec[r];
+    xs1[r] = p; p += nvec[r]; sfirst[r] = p; p += nvec[r]; rfirst[r] = p; p += nvec[r];
+    dnorm[r] = h->d_bmr + per * m; dgath[r] = dnorm[r] + 8;        // + partial sums from dnorm + 128 on
+  }
+#define EACH_R for (int r = 0; r < n; r++)
+#define HCUR hpb_solver* h = hs[r]; cudaSetDevice(h->device); const Geom& G = h->geo; (void)G
+  EACH_R { HCUR;
+    cudaMemsetAsync(red_rl[r], 0, 3 * nvec[r] * sizeof(double), h->stream);     // recvL, recvR, xp1
+#define CALL(M_) k_bmr_stage1<M_><<<grid[r], tpb, 0, h->stream>>>(G, dir, rows[r], first[r], h->d_tri[0], h->d_tri[1], h->d_tri[2], h->d_bx, sendrow[r])
+    MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+    LAUNCHED(h); }
+  { int rc = hpbc::line_shift(hs, n, dir, +1, sendrow.data(), recvrow.data(), nrow.data(), nullptr); if (rc) return rc; }
+  EACH_R { HCUR;
+#define CALL(M_) k_bmr_stage2<M_><<<grid[r], tpb, 0, h->stream>>>(G, dir, rows[r], first[r], h->d_tri[0], h->d_tri[1], h->d_tri[2], h->d_bx, recvrow[r], red[r])
+    MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+    LAUNCHED(h); }
+  std::vector<double> gnorm(n, 0.0), norm0(n, 0.0);
+  std::vector<std::array<double, 64>> hn(n);
+  for (int iter = 0; ; iter++) {
+    bool any = false;
+    EACH_R {
+      if (!active[r]) continue;
+      if (iter >= maxiter || (iter && gnorm[r] < atol) || (iter && gnorm[r] / norm0[r] < rtol)) active[r] = 0;
+      any = any || active[r];
+    }
+    if (!any) break;
+    { int rc = hpbc::line_swap(hs, n, dir, red_sx.data(), red_sx.data(), red_rl.data(), red_rr.data(), nvec.data(), active.data()); if (rc) return rc; }
+    EACH_R { if (!active[r]) continue; HCUR;
+      const long long nb = (long long)grid[r].x * grid[r].y;
+      if (nb > 3900) return hpb_fail(HPB_ERR_INVALID, "compact schemes across ranks: more than 3900 thread blocks per solve");
+#define CALL(M_) k_bmr_jacobi<M_><<<grid[r], tpb, 0, h->stream>>>(G, dir, first[r], 0, h->d_tri[0], h->d_tri[1], h->d_tri[2], h->d_bx, red[r], dnorm[r] + 128)
+      MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+      LAUNCHED(h);
+      k_mr_sum<<<1, 256, 0, h->stream>>>(dnorm[r] + 128, nb, dnorm[r]); LAUNCHED(h); }
+    { int rc = hpbc::line_gather(hs, n, dir, dnorm.data(), dgath.data(), reinterpret_cast<double (*)[64]>(hn.data()), active.data()); if (rc) return rc; }
+    EACH_R { if (!active[r]) continue;
+      const int np = hs[r]->cfg.iproc[dir];
+      double sum = hn[r][0];
+      for (int k = 1; k < np; k++) sum += hn[r][k];
+      gnorm[r] = sqrt(sum / np);                               // NT = ranks on the line (blocktridiagIterJacobi.c:139)
+      if (!iter) norm0[r] = gnorm[r];
+      HCUR;
+#define CALL(M_) k_bmr_jacobi<M_><<<grid[r], tpb, 0, h->stream>>>(G, dir, first[r], 1, h->d_tri[0], h->d_tri[1], h->d_tri[2], h->d_bx, red[r], nullptr)
+      MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+      LAUNCHED(h); }
+  }
+  EACH_R { HCUR;
+#define CALL(M_) k_bmr_row0<M_><<<grid[r], tpb, 0, h->stream>>>(G, dir, h->d_bx, xs1[r])
+    MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+    LAUNCHED(h); }
+  { int rc = hpbc::line_shift(hs, n, dir, -1, xs1.data(), xp1.data(), nvec.data(), nullptr); if (rc) return rc; }
+  EACH_R { HCUR;
+#define CALL(M_) k_bmr_stage4<M_><<<grid[r], tpb, 0, h->stream>>>(G, dir, rows[r], first[r], h->d_tri[0], h->d_tri[1], h->d_tri[2], h->d_bx, xp1[r], sfirst[r], fI[r])
+    MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+    LAUNCHED(h); }
+  { int rc = hpbc::line_shift(hs, n, dir, -1, sfirst.data(), rfirst.data(), nvec.data(), nullptr); if (rc) return rc; }
+  EACH_R { if (last[r]) continue; HCUR;
+#define CALL(M_) k_bmr_put_last<M_><<<grid[r], tpb, 0, h->stream>>>(G, dir, fI[r], rfirst[r])
+    MODEL_SWITCH(h->cfg.model, CALL)
+#undef CALL
+    LAUNCHED(h); }
+#undef EACH_R
+#undef HCUR
+  return HPB_OK;
+}
+
 static int weno_interp_group(hpb_solver** hs, int n, double* const* fI, double* const* fC, const double* const* u,
                              double* const* w, int upw, int dir, int uflag)
 {
   for (int r = 0; r < n; r++) { cudaSetDevice(hs[r]->device); weno_interp(hs[r], fI[r], fC[r], u[r], w[r], upw, dir, uflag); }
   const hpb_solver* h0 = hs[0];
   const bool compact = hpb_scheme_is_compact(h0->cfg.hyp_scheme);
-  if (compact && h0->cfg.iproc[dir] > 1) return compact_solve_group(hs, n, dir, fI);
+  if (compact && h0->cfg.iproc[dir] > 1)
+    return h0->phys.interp_char ? block_compact_solve_group(hs, n, dir, fI) : compact_solve_group(hs, n, dir, fI);
   return HPB_OK;
 }
 
@@ -2210,13 +2532,14 @@ void weno_interp(hpb_solver* h, double* fI, const double* fC, const double* u, c
     int T0, T1;
     if (dir == 0) { T0 = M[1]; T1 = M[2]; } else if (dir == 1) { T0 = M[0]; T1 = M[2]; } else { T0 = M[0]; T1 = M[1]; }
     const int tpb = 64;
+    const bool split = h->cfg.iproc[dir] > 1;     // the line is split among ranks: block_compact_solve_group finishes the job
 #define CALL(M_) { k_compact_rows_char<M_><<<grid3(M[0], M[1], M[2]), TPB, 0, h->stream>>>(G, h->phys, fC, u, w, upw, dir, uflag, \
                        h->d_tri[0], h->d_tri[1], h->d_tri[2], h->d_bx); \
-                   k_block_tridiag<M_><<<dim3((T0 + tpb - 1) / tpb, T1, 1), tpb, 0, h->stream>>>(G, dir, h->d_tri[0], h->d_tri[1], \
+                   if (!split) k_block_tridiag<M_><<<dim3((T0 + tpb - 1) / tpb, T1, 1), tpb, 0, h->stream>>>(G, dir, h->d_tri[0], h->d_tri[1], \
                        h->d_tri[2], h->d_bx, fI); }
     MODEL_SWITCH(h->cfg.model, CALL)
 #undef CALL
-    LAUNCHED(h); LAUNCHED(h);
+    LAUNCHED(h); if (!split) LAUNCHED(h);
     return;
   }
   if (hpb_scheme_is_compact(h->cfg.hyp_scheme)) {

@@ -181,9 +181,8 @@ def test_decomposed_zone_extents_of_open_boundaries_and_sponges():
 
 @pytest.mark.parametrize("mutate, msg", [
     (lambda c: c.solver.__setitem__("hyp_space_scheme", "weno7"), "weno5"),
-    # compact schemes split among ranks: component-wise ones run (tests/test_gpu_decomposed.py), characteristic ones do not
-    (lambda c: (c.solver.__setitem__("hyp_space_scheme", "cupw5"), c.solver.__setitem__("iproc", [1, 2, 1]),
-                c.solver.__setitem__("hyp_interp_type", "characteristic")), "iproc"),
+    # (compact schemes split among ranks run, component-wise and characteristic: tests/test_gpu_decomposed.py)
+    (lambda c: (c.solver.__setitem__("hyp_space_scheme", "cupw5"), c.solver.__setitem__("iproc", [1, 80, 1])), "at most 64 ranks"),
     (lambda c: c.solver.__setitem__("time_scheme", "glm-gee"), "rk"),
     (lambda c: c.solver.__setitem__("time_scheme_type", "ssprk2"), "ssprk3"),
     (lambda c: c.solver.__setitem__("ghost", 2), "ghost"),

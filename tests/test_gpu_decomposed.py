@@ -178,12 +178,19 @@ def _compact_cases():
          cases.ns2d_vortex((28, 40), "js", scheme="cupw5", iproc=(1, 3)),
          cases.ns3d_density_wave((16, 12, 26), "js", iproc=(1, 1, 4), scheme="crweno5"),        # 4 ranks on one line
          cases.ns2d_vortex((40, 27), "z", iproc=(2, 2), scheme="hcweno5"),                      # hybrid compact-WENO5 across ranks
-         cases.ns3d_rising_bubble((14, 26, 12), "mapped+rc0.2", iproc=(1, 3, 1), scheme="hcweno5")]
+         cases.ns3d_rising_bubble((14, 26, 12), "mapped+rc0.2", iproc=(1, 3, 1), scheme="hcweno5"),
+         # characteristic compact schemes: BLOCK tridiagonal systems across ranks (blocktridiagLU.c stages 1-4, block Jacobi)
+         cases.ns2d_vortex((40, 27), "z", upwinding="roe", interp="characteristic", iproc=(2, 2), scheme="crweno5"),
+         cases.with_characteristic(cases.ns3d_turbulence((14, 12, 26), "mapped", viscous=False, upwinding="roe", iproc=(1, 1, 2), scheme="crweno5")),
+         cases.with_characteristic(cases.ns3d_turbulence((26, 12, 13), "js", upwinding="rf-char", iproc=(2, 1, 1), scheme="cupw5")),
+         cases.with_characteristic(cases.ns3d_density_wave((12, 14, 39), "yc", iproc=(1, 1, 3), scheme="hcweno5"))]
     a = cases.linear_advection_sine(96, "z", scheme="crweno5")
     a.solver["iproc"] = [3]
     b = cases.euler1d_sod(101, "js", interp="components", upwinding="roe", scheme="cupw5")
     b.solver["iproc"] = [2]
-    C += [a, b]
+    c = cases.euler1d_sod(121, "mapped", upwinding="roe", scheme="crweno5")              # characteristic, 1-D, three ranks
+    c.solver["iproc"] = [3]
+    C += [a, b, c]
     for c in C:
         c.name += "_iproc" + "x".join(str(v) for v in c.solver["iproc"])
     return C
