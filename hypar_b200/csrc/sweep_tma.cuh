@@ -266,6 +266,11 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
   }
   __syncthreads();
   if (tid == 0) { issue_loads(-1); if (RKF && M > 0) issue_rin(0); }
+  // this thread has issued the result stores / the reduce of the previous step and still owes the wait for their shared-memory
+  // reads (then: the tiles' next loads, or the release of the result tile). The wait is taken after P1 of the NEXT step, not
+  // right after the issue: the warp that stages last is the slowest of its CTA, and everything it does alone delays them all
+  // (profiles/r02l: the input-tile wait of the other warps doubled when it also waited for the stores and issued the loads)
+  bool pend = false;
 
   for (int m = -1; m < M; m++) {
     const int c1 = TL * m + 3 + l;
@@ -343,6 +348,12 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
       if ((old & (TW - 1)) == TW - 1 && m + 1 < M) {
         __threadfence_block();
         issue_loads(m + 1);
+      }
+      if (!XS && pend) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (RKF) issue_rin(m);               // the tiles of step m-1 have been read: this step's right-hand side and u^n
+        else mbar_arrive(free_bar);
+        pend = false;
       }
     }
 
@@ -667,9 +678,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
               tma_store4(&tm.un, ust, c0, c1t, c2t, 0);
             } else tma_reduce_add4(&tm.out, ost, c0, c1t, c2t, 0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (RKF) { if (m + 1 < M) issue_rin(m + 1); }
-            else mbar_arrive(free_bar);
+            pend = true;                     // the wait and what follows it: after P1 of the next step (above)
           }
         }
       }
@@ -698,6 +707,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
     }
     __syncwarp();
   }
+  if (!XS && pend) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // shared memory stays valid until the last tiles are read
 }
 
 } // namespace hpbf
