@@ -473,6 +473,7 @@ def gpu_arm(args):
     #            the 1-GPU rate of this run's per-GPU block size
     #   c5b    : configs[4] -- rising thermal bubble with the gravity source, WENO5-YC, SSPRK3, 512^3 per GPU (1024^3 at 8)
     tma_launches = sv.tma_launches
+    stage_fusion = sv.stage_fusion_active          # (the solver is closed before the line is assembled)
     fp64_peak = sv.fp64_issue_peak() if rank == 0 else None      # measured live on this GPU (hpb_fp64_issue_peak)
     comm_msgs, comm_bytes = sv.comm_stats() if stepper is not None else (0, 0)
     sub = {}
@@ -594,7 +595,7 @@ def gpu_arm(args):
                        "update, Q-derivative faces of dims 1.. under the x-sweep (hpb_TimeStepsDistributed, no Python in the step)"
                        if stepper.overlap else "in-library ncclSend/ncclRecv, serial (hpb_TimeStepsDistributed)")),
                    "stage_fusion": ("the last sweep of an RK stage also writes the next stage solution (bit-identical to the unfused "
-                                    "schedule; HPB_STAGE_FUSION=0 turns it off)" if sv.stage_fusion_active else "off"),
+                                    "schedule; HPB_STAGE_FUSION=0 turns it off)" if stage_fusion else "off"),
                    "l2": "working set (5.6 GB per array) >> L2, no flush needed",
                    "host_numa_bind": (f"{len(numa_cpus)} GPU-local CPUs" if numa_cpus else "none")},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,

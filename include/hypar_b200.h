@@ -63,10 +63,12 @@ extern "C" {
 #define HPB_UPWIND_RF      3    /* "rf-char":  characteristic-based Roe-fixed (Euler1D, NavierStokes3D)          */
 #define HPB_UPWIND_LLF     4    /* "llf-char": characteristic-based local Lax-Friedrichs (Euler1D, NavierStokes3D) */
 
-/* solver.inp `hyp_space_scheme` -- reference src/Simulation/InitializeSolvers.c:232-330. The compact schemes
+/* solver.inp `hyp_space_scheme` -- reference src/Simulation/InitializeSolvers.c:232-346. The compact schemes
    solve one tridiagonal system per grid line and component (Interp1PrimFifthOrderCRWENO.c:80,
-   Interp1PrimFifthOrderCompactUpwind.c:73, TridiagLU/tridiagLU.c:84); component-wise, iproc = 1 along every
-   dimension. Anything but WENO5 runs on the reference-exact kernels. */
+   Interp1PrimFifthOrderCompactUpwind.c:73, Interp1PrimFifthOrderHCWENO.c:65; TridiagLU/tridiagLU.c:84) or, with
+   hyp_interp_type characteristic, one block tridiagonal system per grid line (...Char.c; blocktridiagLU.c:103);
+   the grid lines may be split among ranks (all four stages of the reference's solve with its Jacobi reduced
+   system). Anything but WENO5 runs on the reference-exact kernels. */
 #define HPB_SCHEME_WENO5   0    /* "weno5"   */
 #define HPB_SCHEME_CRWENO5 1    /* "crweno5" */
 #define HPB_SCHEME_CUPW5   2    /* "cupw5": fifth-order compact upwind */
@@ -76,7 +78,7 @@ extern "C" {
 #define HPB_SCHEME_FOURTH  6    /* "4": fourth-order central (Interp1PrimFourthOrderCentral.c) */
 #define HPB_SCHEME_MUSCL2  7    /* "muscl2": Interp1PrimSecondOrderMUSCL.c, limiter from muscl.inp */
 #define HPB_SCHEME_MUSCL3  8    /* "muscl3": Interp1PrimThirdOrderMUSCL.c (Koren), epsilon from muscl.inp */
-#define HPB_SCHEME_HCWENO5 9    /* "hcweno5": hybrid compact-WENO5 (Interp1PrimFifthOrderHCWENO.c), component-wise; rc, xi from weno.inp */
+#define HPB_SCHEME_HCWENO5 9    /* "hcweno5": hybrid compact-WENO5 (Interp1PrimFifthOrderHCWENO.c / ...HCWENOChar.c); rc, xi from weno.inp */
 /* muscl.inp `limiter` -- MUSCLInitialize.c:62-75, src/LimiterFunctions/ */
 #define HPB_LIMITER_GMM      0
 #define HPB_LIMITER_MINMOD   1
