@@ -86,7 +86,11 @@ def compact_across_ranks(rank, world, local, iproc):
         return True
     ok = True
     for name, case in (("crweno5 visc", cases.ns3d_turbulence((26, 25, 27), "z", iproc=iproc, scheme="crweno5")),
-                       ("cupw5 bubble", cases.ns3d_rising_bubble((26, 24, 28), "yc", iproc=iproc, scheme="cupw5"))):
+                       ("cupw5 bubble", cases.ns3d_rising_bubble((26, 24, 28), "yc", iproc=iproc, scheme="cupw5")),
+                       # characteristic: block tridiagonal systems across the ranks (blocktridiagLU + block Jacobi)
+                       ("crweno5 char roe", cases.with_characteristic(cases.ns3d_turbulence((26, 25, 27), "mapped", viscous=False,
+                                                                                          upwinding="roe", iproc=iproc, scheme="crweno5"))),
+                       ("hcweno5", cases.ns3d_density_wave((26, 24, 28), "js", iproc=iproc, scheme="hcweno5"))):
         ref = run_ref_mp(case, "steps", [2], nranks=world)
         ds = DistributedSolver(case.solver, case.boundary, case.physics, case.weno, case.x, rank=rank, device=local, use_fused=False)
         MO = MultiRankOracle(case)
@@ -100,6 +104,33 @@ def compact_across_ranks(rank, world, local, iproc):
         ok = ok and good
         print(f"[rank {rank}/{world}] iproc {iproc} {name}: u(2 steps) vs the {world}-rank reference: max diff {np.abs(a - b).max():.2e} "
               f"{'bit-identical ok' if good else 'FAIL'}", flush=True)
+        ds.solver.close()
+    return ok
+
+
+def glmgee_over_nccl(rank, world, local, iproc):
+    """GLM-GEE (TimeGLMGEE.c) through hpb_TimeStepsDistributed: solution and auxiliary solution against the decomposed oracle"""
+    ok = True
+    case = cases.with_glmgee(cases.ns3d_turbulence((26, 25, 27), "mapped", iproc=iproc), "exrk2a", "yyt")
+    m, mode = hpo.glmgee_of(case)
+    MO = MultiRankOracle(case)
+    u = MO.local_u0()
+    ua = [MO.O[r].glmgee_aux0(u[r], mode) for r in range(world)]
+    for _ in range(2):
+        MO.time_step_glmgee(u, ua, float(case.solver["dt"]), m, mode)
+    S = MO.S[rank]
+    for fused in (False, True):
+        ds = DistributedSolver(case.solver, case.boundary, case.physics, case.weno, case.x, rank=rank, device=local,
+                               use_fused=fused, glm_gee=case.glm_gee)
+        ds.solver.set_solution(MO.local_u0()[rank])
+        ds.time_steps(2)
+        a, b = S.interior(ds.solver.get_solution()), S.interior(ds.solver.get_aux_solution())
+        ra, rb = S.interior(u[rank]), S.interior(ua[rank])
+        e = max(np.abs(a - ra).max(), np.abs(b - rb).max()) / np.abs(ra).max()
+        good = (e <= 1e-11) if fused else (e <= 1e-14)       # exact path: bit-identical but for the viscosity law's libm ulp
+        ok = ok and good
+        print(f"[rank {rank}/{world}] iproc {iproc} glm-gee exrk2a yyt {'fused' if fused else 'exact'}: u and aux (2 steps) rel err "
+              f"{e:.2e} {'ok' if good else 'FAIL'}", flush=True)
         ds.solver.close()
     return ok
 
@@ -157,6 +188,7 @@ def main():
                 ds.solver.close()
     ok = diagnostics_and_io(rank, world, local, iprocs[0]) and ok
     ok = compact_across_ranks(rank, world, local, iprocs[0]) and ok
+    ok = glmgee_over_nccl(rank, world, local, iprocs[0]) and ok
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
     dist.destroy_process_group()
