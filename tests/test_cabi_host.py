@@ -183,7 +183,10 @@ def test_decomposed_zone_extents_of_open_boundaries_and_sponges():
     (lambda c: c.solver.__setitem__("hyp_space_scheme", "weno7"), "weno5"),
     # (compact schemes split among ranks run, component-wise and characteristic: tests/test_gpu_decomposed.py)
     (lambda c: (c.solver.__setitem__("hyp_space_scheme", "cupw5"), c.solver.__setitem__("iproc", [1, 80, 1])), "at most 64 ranks"),
-    (lambda c: c.solver.__setitem__("time_scheme", "glm-gee"), "rk"),
+    (lambda c: c.solver.__setitem__("time_scheme", "arkimex"), "rk"),
+    (lambda c: (c.solver.__setitem__("time_scheme", "glm-gee"), c.solver.__setitem__("time_scheme_type", "44")), "glm-gee method"),
+    (lambda c: (c.solver.__setitem__("time_scheme", "glm-gee"), c.solver.__setitem__("time_scheme_type", "23"),
+                setattr(c, "glm_gee", {"ee_mode": "both"})), "ee_mode"),
     (lambda c: c.solver.__setitem__("time_scheme_type", "ssprk2"), "ssprk3"),
     (lambda c: c.solver.__setitem__("ghost", 2), "ghost"),
     (lambda c: c.solver.__setitem__("model", "shallow-water-2d"), "model"),
