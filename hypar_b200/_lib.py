@@ -42,6 +42,8 @@ class Config(C.Structure):
         ("gravity_type", C.c_int), ("advection_field", C.POINTER(C.c_double)),
         ("weno_rc", C.c_double), ("weno_xi", C.c_double),
         ("par_space_type", C.c_int), ("glm_ee_mode", C.c_int),
+        ("lu_maxiter", C.c_int), ("lu_evaluate_norm", C.c_int), ("lu_atol", C.c_double), ("lu_rtol", C.c_double),
+        ("lu_gather_and_solve", C.c_int),
     ]
 
 

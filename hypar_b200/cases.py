@@ -36,6 +36,7 @@ class Case:
     muscl: Optional[Dict[str, object]] = None      # muscl.inp (epsilon, limiter) for muscl2 / muscl3
     advection_field: Optional[np.ndarray] = None   # LinearADR `advection_filename advection`: shape (N_{nd-1},...,N_0, ndims*nvars)
     glm_gee: Optional[Dict[str, object]] = None    # glm_gee.inp (ee_mode yeps | yyt) for time_scheme glm-gee
+    lusolver: Optional[Dict[str, object]] = None   # lusolver.inp (maxiter, atol, rtol, evaluate_norm): compact schemes across ranks
 
     @property
     def ndims(self) -> int:
@@ -60,6 +61,8 @@ class Case:
             hypario.write_keyword_file(os.path.join(d, "muscl.inp"), self.muscl)
         if self.glm_gee is not None:
             hypario.write_keyword_file(os.path.join(d, "glm_gee.inp"), self.glm_gee)
+        if self.lusolver is not None:
+            hypario.write_keyword_file(os.path.join(d, "lusolver.inp"), self.lusolver)
         ipt = str(self.solver.get("ip_file_type", "binary"))
         if self.advection_field is not None:           # same layout and flavour as initial.inp (ReadArray.c:173-256)
             hypario.write_initial(os.path.join(d, "advection.inp"), self.x, self.advection_field, ipt)
@@ -83,10 +86,12 @@ def from_directory(path: str) -> Case:
     w = hypario.read_keyword_file(wf) if os.path.exists(wf) else None
     mu = hypario.read_keyword_file(mf) if os.path.exists(mf) else None
     gg = hypario.read_keyword_file(gf) if os.path.exists(gf) else None
+    lf = os.path.join(path, "lusolver.inp")
+    lu = hypario.read_keyword_file(lf) if os.path.exists(lf) else None
     ipt = str(s.get("ip_file_type", "ascii"))
     x, u0 = hypario.read_initial(os.path.join(path, "initial.inp"), s["size"], nv, ipt)
     case = Case(name=os.path.basename(os.path.normpath(path)), solver=s, boundary=b, physics=ph, weno=w, x=x, u0=u0, muscl=mu,
-                glm_gee=gg)
+                glm_gee=gg, lusolver=lu)
     if str(ph.get("advection_filename", "none")) != "none":
         fn = os.path.join(path, str(ph["advection_filename"]) + ".inp")
         if os.path.exists(fn):

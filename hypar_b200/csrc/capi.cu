@@ -47,6 +47,7 @@ extern "C" void hpb_config_defaults(hpb_config* c)
   c->rk_type = HPB_RK_44;
   c->weno_type = HPB_WENO_JS; c->no_limiting = 0; c->weno_eps = 1e-6;   // WENOInitialize.c:51-60
   c->weno_rc = 0.3; c->weno_xi = 0.001;
+  c->lu_maxiter = 10; c->lu_evaluate_norm = 1; c->lu_atol = 1e-12; c->lu_rtol = 1e-10;   // tridiagLUInit.c:54-61
   c->upwind = HPB_UPWIND_ROE;
   c->gamma = 1.4; c->Re = -1.0; c->Pr = 0.72; c->Minf = 1.0;   // NavierStokes3DInitialize.c:78-91
   c->rho_ref = 1.0; c->p_ref = 1.0; c->R = 1.0; c->HB = 1; c->N_bv = 0.0;

@@ -101,6 +101,13 @@ int hpb_setup_host(hpb_solver* h)
                     c.hyp_scheme);
   if (c.muscl_limiter < HPB_LIMITER_GMM || c.muscl_limiter > HPB_LIMITER_SUPERBEE)
     return hpb_fail(HPB_ERR_INVALID, "muscl limiter %d not supported (gmm, minmod, vanleer, superbee)", c.muscl_limiter);
+  if (hpb_scheme_is_compact(c.hyp_scheme)) {
+    bool split = false;
+    for (int d = 0; d < nd; d++) split = split || c.iproc[d] > 1;
+    if (split && c.lu_gather_and_solve)
+      return hpb_fail(HPB_ERR_INVALID, "lusolver.inp: reducedsolvetype gather-and-solve is not on the B200 path (jacobi)");
+    if (c.lu_maxiter < 0) return hpb_fail(HPB_ERR_INVALID, "lusolver.inp: maxiter %d", c.lu_maxiter);
+  }
   if (hpb_scheme_is_compact(c.hyp_scheme))
     for (int d = 0; d < nd; d++)
       if (c.iproc[d] > 64) return hpb_fail(HPB_ERR_INVALID, "compact schemes: at most 64 ranks along one dimension");

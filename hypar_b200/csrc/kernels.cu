@@ -2072,8 +2072,10 @@ static int mr_ensure(hpb_solver* h)
 static int compact_solve_group(hpb_solver** hs, int n, int dir, double* const* X)
 {
   const int tpb = 64;
-  const double atol = 1e-12, rtol = 1e-10;      // tridiagLUInit.c:70-76 (lusolver.inp is not read: defaults)
-  const int maxiter = 10;
+  // lusolver.inp (tridiagLUInit.c:54-90; defaults jacobi, maxiter 10, atol 1e-12, rtol 1e-10, norm evaluated)
+  const double atol = hs[0]->cfg.lu_atol, rtol = hs[0]->cfg.lu_rtol;
+  const int maxiter = hs[0]->cfg.lu_maxiter;
+  const bool evalnorm = hs[0]->cfg.lu_evaluate_norm != 0;
   std::vector<double*> sendrow(n), recvrow(n), red_x(n), red_sx(n), red_rl(n), red_rr(n), xp1(n), sfirst(n), rfirst(n), dnorm(n), dgath(n);
   std::vector<int> active(n, 1), first(n), last(n), rows(n);
   std::vector<dim3> grid(n);
@@ -2114,24 +2116,26 @@ static int compact_solve_group(hpb_solver** hs, int n, int dir, double* const* X
     bool any = false;
     EACH_R {
       if (!active[r]) continue;
-      if (iter >= maxiter || (iter && gnorm[r] < atol) || (iter && gnorm[r] / norm0[r] < rtol)) active[r] = 0;
+      if (iter >= maxiter || (iter && evalnorm && gnorm[r] < atol) || (iter && evalnorm && gnorm[r] / norm0[r] < rtol)) active[r] = 0;
       any = any || active[r];
     }
     if (!any) break;
     { int rc = hpbc::line_swap(hs, n, dir, red_sx.data(), red_sx.data(), red_rl.data(), red_rr.data(), nsys.data(), active.data()); if (rc) return rc; }
-    EACH_R { if (!active[r]) continue; HCUR;
+    if (evalnorm) EACH_R { if (!active[r]) continue; HCUR;
       const long long nb = (long long)grid[r].x * grid[r].y * grid[r].z;
       k_mr_jacobi<<<grid[r], tpb, 0, h->stream>>>(G, dir, first[r], 0, h->d_tri[0], h->d_tri[1], h->d_tri[2], X[r], h->d_mr + 8 * nsys[r],
                                                   nsys[r], dnorm[r] + 128); LAUNCHED(h);
       if (nb > 3900) return hpb_fail(HPB_ERR_INVALID, "compact schemes across ranks: more than 3900 thread blocks per solve");
       k_mr_sum<<<1, 256, 0, h->stream>>>(dnorm[r] + 128, nb, dnorm[r]); LAUNCHED(h); }
-    { int rc = hpbc::line_gather(hs, n, dir, dnorm.data(), dgath.data(), reinterpret_cast<double (*)[64]>(hn.data()), active.data()); if (rc) return rc; }
+    if (evalnorm) { int rc = hpbc::line_gather(hs, n, dir, dnorm.data(), dgath.data(), reinterpret_cast<double (*)[64]>(hn.data()), active.data()); if (rc) return rc; }
     EACH_R { if (!active[r]) continue;
-      const int np = hs[r]->cfg.iproc[dir];
-      double sum = hn[r][0];                                   // the order of a rank-0-rooted reduction: ((r0 + r1) + r2) ...
-      for (int k = 1; k < np; k++) sum += hn[r][k];
-      gnorm[r] = sqrt(sum / np);                               // NT = sum of the local sizes = ranks on the line (:118)
-      if (!iter) norm0[r] = gnorm[r];
+      if (evalnorm) {
+        const int np = hs[r]->cfg.iproc[dir];
+        double sum = hn[r][0];                                   // the order of a rank-0-rooted reduction: ((r0 + r1) + r2) ...
+        for (int k = 1; k < np; k++) sum += hn[r][k];
+        gnorm[r] = sqrt(sum / np);                               // NT = sum of the local sizes = ranks on the line (:118)
+        if (!iter) norm0[r] = gnorm[r];
+      }
       HCUR;
       k_mr_jacobi<<<grid[r], tpb, 0, h->stream>>>(G, dir, first[r], 1, h->d_tri[0], h->d_tri[1], h->d_tri[2], X[r], h->d_mr + 8 * nsys[r],
                                                   nsys[r], nullptr); LAUNCHED(h); }
@@ -2154,8 +2158,10 @@ static int compact_solve_group(hpb_solver** hs, int n, int dir, double* const* X
 static int block_compact_solve_group(hpb_solver** hs, int n, int dir, double* const* fI)
 {
   const int tpb = 64;
-  const double atol = 1e-12, rtol = 1e-10;      // tridiagLUInit.c:70-76 (lusolver.inp is not read: defaults)
-  const int maxiter = 10;
+  // lusolver.inp (tridiagLUInit.c:54-90; defaults jacobi, maxiter 10, atol 1e-12, rtol 1e-10, norm evaluated)
+  const double atol = hs[0]->cfg.lu_atol, rtol = hs[0]->cfg.lu_rtol;
+  const int maxiter = hs[0]->cfg.lu_maxiter;
+  const bool evalnorm = hs[0]->cfg.lu_evaluate_norm != 0;
   std::vector<double*> sendrow(n), recvrow(n), red(n), red_sx(n), red_rl(n), red_rr(n), xp1(n), xs1(n), sfirst(n), rfirst(n), dnorm(n), dgath(n);
   std::vector<int> active(n, 1), first(n), last(n), rows(n);
   std::vector<dim3> grid(n);
@@ -2208,12 +2214,12 @@ static int block_compact_solve_group(hpb_solver** hs, int n, int dir, double* co
     bool any = false;
     EACH_R {
       if (!active[r]) continue;
-      if (iter >= maxiter || (iter && gnorm[r] < atol) || (iter && gnorm[r] / norm0[r] < rtol)) active[r] = 0;
+      if (iter >= maxiter || (iter && evalnorm && gnorm[r] < atol) || (iter && evalnorm && gnorm[r] / norm0[r] < rtol)) active[r] = 0;
       any = any || active[r];
     }
     if (!any) break;
     { int rc = hpbc::line_swap(hs, n, dir, red_sx.data(), red_sx.data(), red_rl.data(), red_rr.data(), nvec.data(), active.data()); if (rc) return rc; }
-    EACH_R { if (!active[r]) continue; HCUR;
+    if (evalnorm) EACH_R { if (!active[r]) continue; HCUR;
       const long long nb = (long long)grid[r].x * grid[r].y;
       if (nb > 3900) return hpb_fail(HPB_ERR_INVALID, "compact schemes across ranks: more than 3900 thread blocks per solve");
 #define CALL(M_) k_bmr_jacobi<M_><<<grid[r], tpb, 0, h->stream>>>(G, dir, first[r], 0, h->d_tri[0], h->d_tri[1], h->d_tri[2], h->d_bx, red[r], dnorm[r] + 128)
@@ -2221,13 +2227,15 @@ static int block_compact_solve_group(hpb_solver** hs, int n, int dir, double* co
 #undef CALL
       LAUNCHED(h);
       k_mr_sum<<<1, 256, 0, h->stream>>>(dnorm[r] + 128, nb, dnorm[r]); LAUNCHED(h); }
-    { int rc = hpbc::line_gather(hs, n, dir, dnorm.data(), dgath.data(), reinterpret_cast<double (*)[64]>(hn.data()), active.data()); if (rc) return rc; }
+    if (evalnorm) { int rc = hpbc::line_gather(hs, n, dir, dnorm.data(), dgath.data(), reinterpret_cast<double (*)[64]>(hn.data()), active.data()); if (rc) return rc; }
     EACH_R { if (!active[r]) continue;
-      const int np = hs[r]->cfg.iproc[dir];
-      double sum = hn[r][0];
-      for (int k = 1; k < np; k++) sum += hn[r][k];
-      gnorm[r] = sqrt(sum / np);                               // NT = ranks on the line (blocktridiagIterJacobi.c:139)
-      if (!iter) norm0[r] = gnorm[r];
+      if (evalnorm) {
+        const int np = hs[r]->cfg.iproc[dir];
+        double sum = hn[r][0];
+        for (int k = 1; k < np; k++) sum += hn[r][k];
+        gnorm[r] = sqrt(sum / np);                               // NT = ranks on the line (blocktridiagIterJacobi.c:139)
+        if (!iter) norm0[r] = gnorm[r];
+      }
       HCUR;
 #define CALL(M_) k_bmr_jacobi<M_><<<grid[r], tpb, 0, h->stream>>>(G, dir, first[r], 1, h->d_tri[0], h->d_tri[1], h->d_tri[2], h->d_bx, red[r], nullptr)
       MODEL_SWITCH(h->cfg.model, CALL)

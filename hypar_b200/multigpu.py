@@ -111,12 +111,12 @@ class DistributedSolver:
     """
 
     def __init__(self, solver_inp, boundary, physics, weno, x, rank: int, device: int, group=None,
-                 use_fused: bool = True, overlap: bool = True, muscl=None, advection_field=None, glm_gee=None):
+                 use_fused: bool = True, overlap: bool = True, muscl=None, advection_field=None, glm_gee=None, lusolver=None):
         import torch
         import torch.distributed as dist
         self.torch = torch
         self.solver = Solver(solver_inp, boundary, physics, weno, x, rank=rank, device=device, use_fused=use_fused,
-                             muscl=muscl, advection_field=advection_field, glm_gee=glm_gee)
+                             muscl=muscl, advection_field=advection_field, glm_gee=glm_gee, lusolver=lusolver)
         sv = self.solver
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.ExternalStream(sv.stream, device=self.device)

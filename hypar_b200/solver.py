@@ -45,7 +45,8 @@ def _dp(a: np.ndarray):
 def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], physics: Dict[str, object],
                        weno: Optional[Dict[str, object]], x: Sequence[np.ndarray], rank: int = 0,
                        device: int = -1, use_fused: bool = True, muscl: Optional[Dict[str, object]] = None,
-                       advection_field: Optional[np.ndarray] = None, glm_gee: Optional[Dict[str, object]] = None):
+                       advection_field: Optional[np.ndarray] = None, glm_gee: Optional[Dict[str, object]] = None,
+                       lusolver: Optional[Dict[str, object]] = None):
     """Translate the contents of solver.inp / boundary.inp / physics.inp / weno.inp / muscl.inp (as parsed
     dictionaries) into an ``hpb_config``. Unsupported choices raise here or in ``hpb_create``."""
     L = _lib.load()
@@ -87,6 +88,13 @@ def config_from_inputs(solver: Dict[str, object], boundary: Sequence[dict], phys
         if tst not in RK_TYPES:
             raise HyParB200Error(f"time_scheme_type '{tst}' is not on the B200 path (1fe, 22, 33, 44, ssprk3, tvdrk3)")
         c.rk_type = RK_TYPES[tst]
+    lu = lusolver or {}                                   # lusolver.inp (tridiagLUInit.c:54-90): compact schemes across ranks
+    c.lu_maxiter, c.lu_evaluate_norm = int(lu.get("maxiter", 10)), int(lu.get("evaluate_norm", 1))
+    c.lu_atol, c.lu_rtol = float(lu.get("atol", 1e-12)), float(lu.get("rtol", 1e-10))
+    rst = str(lu.get("reducedsolvetype", "jacobi"))
+    if rst not in ("jacobi", "gather-and-solve"):
+        raise HyParB200Error(f"lusolver.inp: reducedsolvetype '{rst}' (jacobi, gather-and-solve)")
+    c.lu_gather_and_solve = int(rst == "gather-and-solve")
     if str(solver.get("immersed_body", "none")) != "none":
         raise HyParB200Error("immersed bodies are not on the B200 path")
     if str(solver.get("hyp_flux_split", "no")) != "no":
@@ -185,12 +193,12 @@ class Solver:
     """One rank of the B200 explicit-RHS path."""
 
     def __init__(self, solver: Dict[str, object], boundary, physics, weno, x, rank: int = 0,
-                 device: int = -1, use_fused: bool = True, muscl=None, advection_field=None, glm_gee=None):
+                 device: int = -1, use_fused: bool = True, muscl=None, advection_field=None, glm_gee=None, lusolver=None):
         self.L = _lib.load()
         self.inputs = {"solver": solver, "boundary": boundary, "physics": physics, "weno": weno, "muscl": muscl,
-                       "advection_field": advection_field, "glm_gee": glm_gee}
+                       "advection_field": advection_field, "glm_gee": glm_gee, "lusolver": lusolver}
         cfg, self._xg = config_from_inputs(solver, boundary, physics, weno, x, rank, device, use_fused, muscl,
-                                           advection_field, glm_gee)
+                                           advection_field, glm_gee, lusolver)
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.hpb_create(C.byref(cfg), C.byref(self.h))
@@ -215,7 +223,7 @@ class Solver:
     def from_case(cls, case, rank: int = 0, device: int = -1, use_fused: bool = True) -> "Solver":
         return cls(case.solver, case.boundary, case.physics, case.weno, case.x, rank, device, use_fused,
                    muscl=getattr(case, "muscl", None), advection_field=getattr(case, "advection_field", None),
-                   glm_gee=getattr(case, "glm_gee", None))
+                   glm_gee=getattr(case, "glm_gee", None), lusolver=getattr(case, "lusolver", None))
 
     @classmethod
     def from_directory(cls, path: str, rank: int = 0, device: int = -1, use_fused: bool = True) -> "Solver":
@@ -246,7 +254,9 @@ class Solver:
                 af = hypario.read_initial(fn, s["size"], nd * nv, ipt)[1]
         gf = os.path.join(path, "glm_gee.inp")
         gg = hypario.read_keyword_file(gf) if os.path.exists(gf) else None
-        obj = cls(s, b, ph, w, x, rank, device, use_fused, muscl=mu, advection_field=af, glm_gee=gg)
+        lf = os.path.join(path, "lusolver.inp")
+        lu = hypario.read_keyword_file(lf) if os.path.exists(lf) else None
+        obj = cls(s, b, ph, w, x, rank, device, use_fused, muscl=mu, advection_field=af, glm_gee=gg, lusolver=lu)
         obj.u0_global = u0
         return obj
 

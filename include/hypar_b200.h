@@ -192,6 +192,12 @@ typedef struct hpb_config {
                                           as nonconservative-1stage -- the other forms are different arithmetic
                                           (ParabolicFunctionNC2Stage.c / NC1_5Stage / Cons1Stage) and fail in hpb_create */
   int    glm_ee_mode;                  /* HPB_GLM_*: glm_gee.inp `ee_mode` of the GLM-GEE methods                */
+  /* --- lusolver.inp (tridiagLUInit.c:54-90): the reduced system of the compact schemes when a grid line is split among ranks
+     (tridiagIterJacobi.c / blocktridiagIterJacobi.c). reducedsolvetype "gather-and-solve" is not built: hpb_create fails. */
+  int    lu_maxiter;                   /* default 10                                                              */
+  int    lu_evaluate_norm;             /* default 1: stop on atol / rtol as well; 0: exactly maxiter iterations    */
+  double lu_atol, lu_rtol;             /* defaults 1e-12, 1e-10                                                    */
+  int    lu_gather_and_solve;          /* 1 = reducedsolvetype gather-and-solve (refused)                          */
 } hpb_config;
 
 typedef struct hpb_solver hpb_solver;

@@ -41,6 +41,7 @@
 #include <boundaryconditions.h>
 #include <interpolation.h>
 #include <limiters.h>
+#include <tridiagLU.h>
 #include <physicalmodels/linearadr.h>
 #include <physicalmodels/euler1d.h>
 #include <physicalmodels/navierstokes2d.h>
@@ -300,6 +301,11 @@ static int attach_one(SimulationObject *sim, int n, int nsims)
     c.muscl_eps = mp->eps;
     c.muscl_limiter = !strcmp(mp->limiter_type, _LIM_MM_) ? HPB_LIMITER_MINMOD : !strcmp(mp->limiter_type, _LIM_VANLEER_) ? HPB_LIMITER_VANLEER
                     : !strcmp(mp->limiter_type, _LIM_SUPERBEE_) ? HPB_LIMITER_SUPERBEE : HPB_LIMITER_GMM;
+  }
+  if (s->lusolver) {               /* compact schemes: lusolver.inp as tridiagLUInit read it (reduced system across ranks) */
+    TridiagLU *lu = (TridiagLU*) s->lusolver;
+    c.lu_maxiter = lu->maxiter;  c.lu_evaluate_norm = lu->evaluate_norm;  c.lu_atol = lu->atol;  c.lu_rtol = lu->rtol;
+    c.lu_gather_and_solve = !strcmp(lu->reducedsolvetype, _TRIDIAG_GS_);
   }
   if (scheme == HPB_SCHEME_WENO5 || scheme == HPB_SCHEME_CRWENO5 || scheme == HPB_SCHEME_HCWENO5) {   /* s->interp is NULL for the linear schemes */
     WENOParameters *w = (WENOParameters*) s->interp;

@@ -183,6 +183,8 @@ def test_decomposed_zone_extents_of_open_boundaries_and_sponges():
     (lambda c: c.solver.__setitem__("hyp_space_scheme", "weno7"), "weno5"),
     # (compact schemes split among ranks run, component-wise and characteristic: tests/test_gpu_decomposed.py)
     (lambda c: (c.solver.__setitem__("hyp_space_scheme", "cupw5"), c.solver.__setitem__("iproc", [1, 80, 1])), "at most 64 ranks"),
+    (lambda c: (c.solver.__setitem__("hyp_space_scheme", "crweno5"), c.solver.__setitem__("iproc", [1, 2, 1]),
+                setattr(c, "lusolver", {"reducedsolvetype": "gather-and-solve"})), "gather-and-solve"),
     (lambda c: c.solver.__setitem__("time_scheme", "arkimex"), "rk"),
     (lambda c: (c.solver.__setitem__("time_scheme", "glm-gee"), c.solver.__setitem__("time_scheme_type", "44")), "glm-gee method"),
     (lambda c: (c.solver.__setitem__("time_scheme", "glm-gee"), c.solver.__setitem__("time_scheme_type", "23"),

@@ -191,6 +191,18 @@ def _compact_cases():
     c = cases.euler1d_sod(121, "mapped", upwinding="roe", scheme="crweno5")              # characteristic, 1-D, three ranks
     c.solver["iproc"] = [3]
     C += [a, b, c]
+    # lusolver.inp (tridiagLUInit.c:54-90): the Jacobi iteration on the reduced system with other limits -- four ranks on a
+    # line, so that the iteration count matters (two ranks converge at the initial guess): a fixed count without the norm,
+    # a loose relative tolerance (stops on the norm), the block systems with a fixed count
+    for lu, tag in (({"maxiter": 1, "evaluate_norm": 0}, "lu1"), ({"maxiter": 10, "rtol": 1e-3}, "lurtol")):
+        d = cases.ns2d_vortex((28, 40), "js", scheme="cupw5", iproc=(1, 4))
+        d.lusolver = lu
+        d.name += "_" + tag
+        C.append(d)
+    e = cases.with_characteristic(cases.ns3d_density_wave((12, 14, 39), "yc", iproc=(1, 1, 3), scheme="crweno5"))
+    e.lusolver = {"maxiter": 2, "evaluate_norm": 0}
+    e.name += "_lu2"
+    C.append(e)
     for c in C:
         c.name += "_iproc" + "x".join(str(v) for v in c.solver["iproc"])
     return C
