@@ -63,10 +63,28 @@ __device__ __forceinline__ double central4(double m2, double m1, double p1, doub
 {
   return __dmul_rn(__dsub_rn(fma(8.0, p1, fma(-8.0, m1, m2)), p2), 1.0 / 12.0);
 }
+// mu = T^0.76 = exp(0.76 log T) (raiseto, math_ops.h:37; NavierStokes3DParabolicFunction.c:174). HPB_MU_FAST (default): the
+// 25th root of T^19 instead of the double-precision exp and log (~100 FP64 instructions per point on a GPU whose FP64 pipe is
+// the scarce unit) -- single-precision seed y0 = powf(T, 0.76) (relative error e0 <~ 2e-6), then ONE Halley step for y^25 = T^19,
+// y1 = y0 ((n-1) y0^n + (n+1) a) / ((n+1) y0^n + (n-1) a), whose error is (n^2-1)/12 e0^3 = 52 e0^3 < 5e-16: ~25 FP64
+// instructions. 19/25 differs from the double 0.76 by 2.7e-17 (times |log T|: nothing). Both Q-derivative kernels share it, so a
+// point still gets the same bits whichever kernel evaluates it; the exact path (kernels.cu) keeps exp(0.76 log T).
+#ifndef HPB_MU_FAST
+#define HPB_MU_FAST 1
+#endif
 __device__ __forceinline__ double mu_over_Re(double T, double inv_Re)
 {
-  // mu = exp(0.76 log T) (raiseto, math_ops.h:37; NavierStokes3DParabolicFunction.c:174)
+#if HPB_MU_FAST
+  const double y0 = (double)powf((float)T, 0.76f);
+  const double y2 = __dmul_rn(y0, y0), y4 = __dmul_rn(y2, y2), y8 = __dmul_rn(y4, y4), y16 = __dmul_rn(y8, y8);
+  const double yn = __dmul_rn(__dmul_rn(y16, y8), y0);                       // y0^25
+  const double t2 = __dmul_rn(T, T), t4 = __dmul_rn(t2, t2), t8 = __dmul_rn(t4, t4), t16 = __dmul_rn(t8, t8);
+  const double an = __dmul_rn(__dmul_rn(t16, t2), T);                        // T^19
+  const double num = fma(26.0, an, __dmul_rn(24.0, yn)), den = fma(24.0, an, __dmul_rn(26.0, yn));
+  return __dmul_rn(__dmul_rn(__dmul_rn(y0, num), rcp_nr(den)), inv_Re);
+#else
   return __dmul_rn(exp(__dmul_rn(0.76, log(T))), inv_Re);
+#endif
 }
 
 __device__ __forceinline__ void prim4(const double* __restrict__ u, long long npg, long long p, double gamma, double (&q)[4])
