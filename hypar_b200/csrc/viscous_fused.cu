@@ -63,14 +63,16 @@ __device__ __forceinline__ double central4(double m2, double m1, double p1, doub
 {
   return __dmul_rn(__dsub_rn(fma(8.0, p1, fma(-8.0, m1, m2)), p2), 1.0 / 12.0);
 }
-// mu = T^0.76 = exp(0.76 log T) (raiseto, math_ops.h:37; NavierStokes3DParabolicFunction.c:174). HPB_MU_FAST (default): the
-// 25th root of T^19 instead of the double-precision exp and log (~100 FP64 instructions per point on a GPU whose FP64 pipe is
-// the scarce unit) -- single-precision seed y0 = powf(T, 0.76) (relative error e0 <~ 2e-6), then ONE Halley step for y^25 = T^19,
+// mu = T^0.76 = exp(0.76 log T) (raiseto, math_ops.h:37; NavierStokes3DParabolicFunction.c:174). HPB_MU_FAST = 1 (a measured
+// variant, NOT the default: profiles/r02s_bench_mufast.json against r02s_bench_muslow.json on the same box -- 18.75 against
+// 18.58 ms per step in these kernels, which wait for memory, not for the FP64 pipe; the whole GPU suite passes with it,
+// profiles/r02s_pytest_gpu.log): the 25th root of T^19 instead of the double-precision exp and log (~100 FP64 instructions per
+// point) -- single-precision seed y0 = powf(T, 0.76) (relative error e0 <~ 2e-6), then ONE Halley step for y^25 = T^19,
 // y1 = y0 ((n-1) y0^n + (n+1) a) / ((n+1) y0^n + (n-1) a), whose error is (n^2-1)/12 e0^3 = 52 e0^3 < 5e-16: ~25 FP64
 // instructions. 19/25 differs from the double 0.76 by 2.7e-17 (times |log T|: nothing). Both Q-derivative kernels share it, so a
 // point still gets the same bits whichever kernel evaluates it; the exact path (kernels.cu) keeps exp(0.76 log T).
 #ifndef HPB_MU_FAST
-#define HPB_MU_FAST 1
+#define HPB_MU_FAST 0
 #endif
 __device__ __forceinline__ double mu_over_Re(double T, double inv_Re)
 {
