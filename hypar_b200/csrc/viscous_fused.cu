@@ -183,7 +183,11 @@ __global__ void __launch_bounds__(128) k_qderiv3(const QD3Args a)
 #else
 #define QD_STORE(ptr, val) (*(ptr) = (val))
 #endif
-constexpr int QTX = 32, QTY = Q_TY, QH = 2;
+#ifndef Q_TX
+#define Q_TX 32       // 64 x 8 tiles (longer contiguous rows per output stream) measured in profiles/r02v_variants.txt
+#endif
+constexpr int QTX = Q_TX, QTY = Q_TY, QH = 2;
+static_assert(4 * QTY + 4 * QTX <= QTX * QTY, "every halo point of a plane needs a thread");
 constexpr int QSX = QTX + 2 * QH + 1;      // padded row (37): conflict-free column access is not needed, rows are read along x
 constexpr int QSY = QTY + 2 * QH;
 
