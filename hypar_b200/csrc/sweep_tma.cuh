@@ -44,6 +44,10 @@
 #include <cuda.h>
 #include "sweep_fused.cuh"
 
+// where the thread that issued the result stores takes the owed wait: after P1 of the next step (0, default) or at its top (1)
+#ifndef HPB_PEND_TOP
+#define HPB_PEND_TOP 0
+#endif
 // x-sweep result stores: plain (default) or streaming (-DHPB_XS_STCS=1; measured in profiles/r02f_variants.txt)
 #ifndef HPB_XS_STCS
 #define HPB_XS_STCS 0
@@ -282,6 +286,15 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
     if (jo >= 0 && jo < N) dxi = dxl[jo];
     const double dxih = 0.5 * dxi;
 
+#if HPB_PEND_TOP
+    // (variant: the owed wait at the top of the step, before this warp waits for its own input tile)
+    if (!XS && pend) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (RKF) issue_rin(m);
+      else mbar_arrive(free_bar);
+      pend = false;
+    }
+#endif
     mbar_wait(full_bar, (unsigned)(m + 1) & 1u);
 
     // ---------------- P1: record of cell c1 = 32m+3+l (record position 5+l)
@@ -349,12 +362,14 @@ __global__ void __launch_bounds__(NT, 2) k_sweep_tma(const SweepArgs a, const __
         __threadfence_block();
         issue_loads(m + 1);
       }
+#if !HPB_PEND_TOP
       if (!XS && pend) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         if (RKF) issue_rin(m);               // the tiles of step m-1 have been read: this step's right-hand side and u^n
         else mbar_arrive(free_bar);
         pend = false;
       }
+#endif
     }
 
     const int cc = rbase + l + 3;
